@@ -1,0 +1,267 @@
+/*
+ * mlb200.h -- C ABI of the B200-native DSPVector voice-chain engine.
+ *
+ * This is the drop-in boundary for ONE hot path of madronalib: the DSPVector
+ * processing chain (generators -> stateful filters -> elementwise ops) batched
+ * over many independent voices.  The reference has no FFI for this path (it is
+ * header-only C++ templates), so each entry point below cites the reference
+ * interface it stands in for.  Everything here is plain C: pointers, sizes and
+ * int status codes; no C++ or torch types cross the boundary.
+ *
+ * Vocabulary follows the reference:
+ *   block   = one DSPVector = kFloatsPerDSPVector = 64 samples
+ *             (reference: source/DSP/MLDSPMath.h:8-9)
+ *   row     = 64 contiguous f32 (256 B); a DSPVectorArray<ROWS> is ROWS rows
+ *             (reference: source/DSP/MLDSPOps.h:94-127)
+ *   voice   = one independent processor instance = one row of a Bank<T,ROWS>
+ *             (reference: source/DSP/MLDSPFunctional.h:321-360)
+ *   graph   = a fixed DAG of generator / filter / op nodes evaluated once per
+ *             block for every voice (what a user's SignalProcessFn does with
+ *             functors; reference: source/app/MLSignalProcessBuffer.h:18,
+ *             examples/audio-and-midi/sine.cpp:21-43; the absent source/procs
+ *             runtime graph, source/procs/MLProcMultiply.cpp:29-46)
+ *
+ * Signal layout (all f32, little endian), for T blocks and V voices:
+ *   inputs   in [T][n_in ][V][64]   -- plane (t,k) is exactly the
+ *                                      DSPVectorArray<V> a Bank::operator()
+ *                                      receives as argument k on block t
+ *   outputs  out[T][n_out][V][64]   -- plane (t,c) is the DSPVectorArray<V>
+ *                                      a Bank would return for output c
+ *   mix bus  mix[T][n_out][64]      -- sum over voices of each output plane
+ *                                      (reference: addRows, MLDSPOps.h:1349-1359;
+ *                                       Synth::processVector, source/app/MLSynth.h:36-60)
+ *
+ * Per-voice state and coefficients are struct-of-arrays of 32-bit words:
+ *   state[n_state_words][V]  (u32 / f32 bit patterns), coef[n_coef_words][V] (f32)
+ * Word order = node order, then slot order as listed in MLB_OP_TABLE below.
+ */
+#ifndef MLB200_H
+#define MLB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLB_BLOCK 64           /* kFloatsPerDSPVector, MLDSPMath.h:8-9 */
+#define MLB_MAX_INS 3
+#define MLB_FDN_LINES 8        /* FDN<8>, MLDSPFilters.h:1162 */
+#define MLB_ABI_VERSION 1
+
+/* ---- status codes (the reference has no error channel) ---- */
+enum {
+  MLB_OK = 0,
+  MLB_ERR_INVALID = 1,   /* bad argument / malformed graph */
+  MLB_ERR_CUDA = 2,      /* CUDA runtime / driver error (see mlb_last_error) */
+  MLB_ERR_NO_DEVICE = 3, /* no usable sm_100 device: there is NO CPU fallback */
+  MLB_ERR_ALLOC = 4,
+  MLB_ERR_UNSUPPORTED = 5
+};
+
+/*
+ * Node table: X(NAME, id, n_in, n_state, n_coef)
+ *   n_in    signal inputs (rows produced by earlier nodes)
+ *   n_state per-voice 32-bit state words carried block to block
+ *   n_coef  per-voice f32 coefficient words
+ * Citations: G = source/DSP/MLDSPGens.h, F = source/DSP/MLDSPFilters.h,
+ *            O = source/DSP/MLDSPOps.h, M = source/DSP/MLDSPMathSSE.h
+ */
+#define MLB_OP_TABLE(X)                                                                  \
+  /* sources */                                                                          \
+  X(INPUT, 0, 0, 0, 0)          /* external signal row in[t][iarg][v][:]             */ \
+  X(PARAM, 1, 0, 0, 1)          /* per-voice float -> DSPVector broadcast, O:157     */ \
+  /* generators */                                                                       \
+  X(NOISE, 2, 0, 1, 0)          /* NoiseGen, G:109-148; state: mSeed                 */ \
+  X(PHASOR, 3, 1, 1, 0)         /* PhasorGen(freq), G:177-203; state: mOmega32       */ \
+  X(SINE, 4, 1, 1, 0)           /* SineGen(freq), G:316-338,373-381; state: mOmega32 */ \
+  X(SAW, 5, 1, 1, 0)            /* SawGen(freq), G:285-311,362-369,395-402           */ \
+  X(PULSE, 6, 2, 1, 0)          /* PulseGen(freq,width), G:342-358,383-393           */ \
+  X(TICK, 7, 1, 1, 0)           /* TickGen(freq), G:24-47; state: mOmega (f32)       */ \
+  /* SVF family ("Biquad" stand-ins) -- state: ic1eq, ic2eq */                           \
+  X(LOPASS, 10, 1, 2, 3)        /* F:51-133   coef g0,g1,g2                          */ \
+  X(HIPASS, 11, 1, 2, 4)        /* F:155-197  coef g0,g1,g2,k                        */ \
+  X(BANDPASS, 12, 1, 2, 3)      /* F:199-240  coef g0,g1,g2                          */ \
+  X(LOSHELF, 13, 1, 2, 5)       /* F:242-302  coef a1,a2,a3,m1,m2                    */ \
+  X(HISHELF, 14, 1, 2, 6)       /* F:321-383  coef a1,a2,a3,m0,m1,m2                 */ \
+  X(BELL, 15, 1, 2, 4)          /* F:402-442  coef a1,a2,a3,m1                       */ \
+  /* one-pole family */                                                                  \
+  X(ONEPOLE, 16, 1, 1, 2)       /* F:446-481  state y1; coef a0,b1                   */ \
+  X(DCBLOCKER, 17, 1, 2, 1)     /* F:489-513  state x1,y1; coef c                    */ \
+  X(DIFFERENTIATOR, 18, 1, 1, 0)/* F:517-535  state x1                               */ \
+  X(INTEGRATOR, 19, 1, 1, 1)    /* F:539-558  state y1; coef leak                    */ \
+  /* FDN<8>: mono in -> stereo out.  Output row of FDN8 is sumL, FDN8_R(in=fdn) is   */ \
+  /* sumR (concatRows(sumL,sumR), F:1237).  state: 8 OnePole y1.  coef: 8x a0,b1,    */ \
+  /* 8 feedback gains, 8 delay lengths (float-valued ints).  Delay rings + carried   */ \
+  /* mDelayInputVectors live in separate delay memory (mlb_graph_delay_bytes).       */ \
+  X(FDN8, 20, 1, 8, 32)         /* F:1162-1239                                       */ \
+  X(FDN8_R, 21, 1, 0, 0)                                                                 \
+  /* unary float ops, O:584-614,825 */                                                   \
+  X(SQRT, 30, 1, 0, 0)                                                                   \
+  X(SQRT_APPROX, 31, 1, 0, 0)                                                            \
+  X(ABS, 32, 1, 0, 0)                                                                    \
+  X(SIGN, 33, 1, 0, 0)                                                                   \
+  X(SIGNBIT, 34, 1, 0, 0)                                                                \
+  X(SIN, 35, 1, 0, 0)                                                                    \
+  X(COS, 36, 1, 0, 0)                                                                    \
+  X(LOG, 37, 1, 0, 0)                                                                    \
+  X(EXP, 38, 1, 0, 0)                                                                    \
+  X(LOG2, 39, 1, 0, 0)                                                                   \
+  X(EXP2, 40, 1, 0, 0)                                                                   \
+  X(SIN_APPROX, 41, 1, 0, 0)                                                             \
+  X(COS_APPROX, 42, 1, 0, 0)                                                             \
+  X(EXP_APPROX, 43, 1, 0, 0)                                                             \
+  X(LOG_APPROX, 44, 1, 0, 0)                                                             \
+  X(LOG2_APPROX, 45, 1, 0, 0)                                                            \
+  X(EXP2_APPROX, 46, 1, 0, 0)                                                            \
+  X(FRACTIONAL_PART, 47, 1, 0, 0)                                                        \
+  /* binary float ops, O:640-649 */                                                      \
+  X(ADD, 50, 2, 0, 0)                                                                    \
+  X(SUBTRACT, 51, 2, 0, 0)                                                               \
+  X(MULTIPLY, 52, 2, 0, 0)                                                               \
+  X(DIVIDE, 53, 2, 0, 0)                                                                 \
+  X(DIVIDE_APPROX, 54, 2, 0, 0)                                                          \
+  X(POW, 55, 2, 0, 0)                                                                    \
+  X(POW_APPROX, 56, 2, 0, 0)                                                             \
+  X(MIN, 57, 2, 0, 0)                                                                    \
+  X(MAX, 58, 2, 0, 0)                                                                    \
+  /* ternary float ops, O:744-748 */                                                     \
+  X(LERP, 60, 3, 0, 0)                                                                   \
+  X(INVERSE_LERP, 61, 3, 0, 0)                                                           \
+  X(CLAMP, 62, 3, 0, 0)                                                                  \
+  X(WITHIN, 63, 3, 0, 0)                                                                 \
+  /* conversions, O:796-797,819-820 (int rows are 32-bit patterns in f32 storage) */     \
+  X(ROUND_F2I, 70, 1, 0, 0)                                                              \
+  X(TRUNC_F2I, 71, 1, 0, 0)                                                              \
+  X(INT_TO_FLOAT, 72, 1, 0, 0)                                                           \
+  X(UNSIGNED_TO_FLOAT, 73, 1, 0, 0)                                                      \
+  /* comparisons -> all-ones / zero masks, O:851-856 */                                  \
+  X(EQUAL, 80, 2, 0, 0)                                                                  \
+  X(NOT_EQUAL, 81, 2, 0, 0)                                                              \
+  X(GREATER_THAN, 82, 2, 0, 0)                                                           \
+  X(GREATER_EQUAL, 83, 2, 0, 0)                                                          \
+  X(LESS_THAN, 84, 2, 0, 0)                                                              \
+  X(LESS_EQUAL, 85, 2, 0, 0)                                                             \
+  /* select(a, b, mask) bitwise, O:886,917; int add/sub O:713-714 */                     \
+  X(SELECT, 90, 3, 0, 0)                                                                 \
+  X(ADD_INT32, 91, 2, 0, 0)                                                              \
+  X(SUBTRACT_INT32, 92, 2, 0, 0)
+
+typedef enum mlb_op {
+#define MLB_X_ENUM(NAME, id, nin, nst, nco) MLB_OP_##NAME = id,
+  MLB_OP_TABLE(MLB_X_ENUM)
+#undef MLB_X_ENUM
+  MLB_OP__END = 93
+} mlb_op;
+
+/* One node of a voice graph.  in[] index earlier nodes (topological order). */
+typedef struct mlb_node {
+  int32_t op;               /* mlb_op */
+  int32_t in[MLB_MAX_INS];  /* producer node indices, -1 = unused */
+  int32_t iarg;             /* INPUT: external input plane index k */
+} mlb_node;
+
+/* Word offsets of every node inside the state / coef SoA. */
+typedef struct mlb_layout {
+  int32_t n_state_words;
+  int32_t n_coef_words;
+  int32_t n_inputs;   /* 1 + max iarg over INPUT nodes, 0 if none */
+} mlb_layout;
+
+/* op metadata (pure host functions, no GPU needed) */
+int mlb_op_info(int op, int* n_in, int* n_state, int* n_coef); /* MLB_OK or MLB_ERR_INVALID */
+const char* mlb_op_name(int op);
+/* validate a graph and compute its SoA layout; state_off/coef_off may be NULL,
+ * else they receive n_nodes word offsets each. */
+int mlb_graph_layout(const mlb_node* nodes, int n_nodes, mlb_layout* layout,
+                     int32_t* state_off, int32_t* coef_off);
+
+/* ---- coefficient design on the host (glibc libm, same as the reference) ----
+ * Each writes the node's coef words for ONE voice.  Cited reference makeCoeffs:
+ * Lopass F:85-95, Hipass F:168-178, Bandpass F:212-222, LoShelf F:270-281,
+ * HiShelf F:350-362, Bell F:415-425, OnePole F:458-462, DCBlocker F:498,
+ * dBToGain F:30. */
+void mlb_coeffs_lopass(float omega, float k, float out3[3]);
+void mlb_coeffs_hipass(float omega, float k, float out4[4]);
+void mlb_coeffs_bandpass(float omega, float k, float out3[3]);
+void mlb_coeffs_loshelf(float omega, float k, float A, float out5[5]);
+void mlb_coeffs_hishelf(float omega, float k, float A, float out6[6]);
+void mlb_coeffs_bell(float omega, float k, float A, float out4[4]);
+void mlb_coeffs_onepole(float omega, float out2[2]);
+float mlb_coeffs_dcblocker(float omega);
+float mlb_db_to_gain(float dB);
+/* FDN<8>::setDelaysInSamples / setFilterCutoffs / mFeedbackGains, F:1171-1191.
+ * Fills the 32 coef words of an FDN8 node for one voice:
+ * [0..7]=a0, [8..15]=b1, [16..23]=feedback gain, [24..31]=len=max(1,int(time)-64). */
+void mlb_coeffs_fdn8(const float times[8], const float cutoffs[8], const float gains[8],
+                     float out32[32]);
+
+/* ---- device / context ---- */
+int mlb_init(int device);          /* select device, check sm_100; MLB_ERR_NO_DEVICE if absent */
+int mlb_device_count(void);        /* 0 when no GPU: callers must fail loudly, not fall back */
+const char* mlb_last_error(void);  /* thread-local message of the last failing call */
+int mlb_abi_version(void);
+long long mlb_kernel_launches(void); /* count of kernels this library launched (process-wide) */
+
+/* ---- stateless elementwise ops on device or host buffers (K3) ----
+ * y[i] = op(x1[i], x2[i], x3[i]) for n_rows*64 elements; unused inputs NULL.
+ * Stands in for every DEFINE_OP* function of MLDSPOps.h:567-918 applied to a
+ * DSPVectorArray<n_rows>.  *_device: pointers are device memory, async on
+ * `stream` (a cudaStream_t passed as void*).  *_host: pointers are host memory;
+ * the call copies in, launches, copies out and synchronises. */
+int mlb_map_device(int op, const float* x1, const float* x2, const float* x3, float* y,
+                   size_t n_rows, void* stream);
+int mlb_map_host(int op, const float* x1, const float* x2, const float* x3, float* y,
+                 size_t n_rows);
+
+/* ---- voice graphs: Bank<>-shaped batched processors ---- */
+typedef struct mlb_graph mlb_graph; /* opaque; owns device state, coefs, delay memory */
+
+/* flags for mlb_graph_create */
+#define MLB_GRAPH_EXACT 0u        /* bit-exact with the reference SSE path (default) */
+#define MLB_GRAPH_FAST 1u         /* allow FMA contraction (stated tolerance) */
+#define MLB_GRAPH_FORCE_GENERIC 2u /* skip fused specialisations, use the graph interpreter kernel */
+
+/* Create a graph for n_voices voices on the current device.
+ * outs[n_out] = node indices whose rows are written to out planes / mix bus.
+ * Stands in for declaring Bank<T,ROWS> members / functor structs
+ * (MLDSPFunctional.h:321-326; examples/audio-and-midi/sine.cpp:17-19). */
+int mlb_graph_create(const mlb_node* nodes, int n_nodes, const int32_t* outs, int n_out,
+                     int n_voices, unsigned flags, mlb_graph** out_graph);
+int mlb_graph_destroy(mlb_graph* g);
+int mlb_graph_layout_of(const mlb_graph* g, mlb_layout* layout);
+/* name of the kernel variant chosen ("fused:sine_lopass_gain", "generic", ...) */
+const char* mlb_graph_kernel_name(const mlb_graph* g);
+
+/* Upload / download SoA words for ALL voices: host buffers of n_words*V words.
+ * set_coefs stands in for assigning `coeffs` members (F:80,166,...);
+ * set_state / get_state for clear()/setSeed()/reading state members
+ * (G:116,182,379; F:66-70,478-480). */
+int mlb_graph_set_coefs(mlb_graph* g, const float* coef_host /*[n_coef_words][V]*/);
+int mlb_graph_set_state(mlb_graph* g, const uint32_t* state_host /*[n_state_words][V]*/);
+int mlb_graph_get_state(mlb_graph* g, uint32_t* state_host);
+/* zero delay memory + delay write index (IntegerDelay::clear, F:832; FDN carried vectors) */
+int mlb_graph_clear_delays(mlb_graph* g);
+size_t mlb_graph_delay_bytes(const mlb_graph* g);
+
+/* Process n_blocks blocks for all voices.  Stands in for n_blocks successive
+ * Bank::operator() calls (MLDSPFunctional.h:328-337) / SignalProcessFn
+ * invocations (MLSignalProcessBuffer.cpp:57-78) fused into ONE kernel launch.
+ * Any of in/out/mix may be NULL when the graph has no INPUT nodes / the caller
+ * does not want that product.  _device: device pointers, async on stream.
+ * _host: host pointers (pinned or pageable); H2D, launch, D2H, synchronise. */
+int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float* out_dev, float* mix_dev,
+                             int n_blocks, void* stream);
+int mlb_graph_process_host(mlb_graph* g, const float* in_host, float* out_host, float* mix_host,
+                           int n_blocks);
+
+/* Duration in milliseconds of the most recent chain kernel launched by
+ * process_device, measured with CUDA events on the launching stream
+ * (blocks until that launch has finished). */
+int mlb_graph_last_kernel_ms(mlb_graph* g, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLB200_H */

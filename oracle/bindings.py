@@ -1,0 +1,169 @@
+"""ctypes bindings for the two CPU checkers -- TEST INFRASTRUCTURE ONLY.
+
+  RefOracle   oracle/_ref/libmlref.so  : the unmodified reference (madronalib SSE
+              path) compiled in place from /root/reference (oracle/Makefile `ref`).
+  PortOracle  oracle/_port/libmlport.so: our plain-C restatement (oracle/port/mlport.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module.  Nothing under madronalib_b200/ does.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional, Tuple
+
+import numpy as np
+
+from madronalib_b200.graph import BLOCK, GraphSpec
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_LIB = os.path.join(_HERE, "_ref", "libmlref.so")
+PORT_LIB = os.path.join(_HERE, "_port", "libmlport.so")
+
+_vp = ctypes.c_void_p
+
+
+def build(target: str = "all") -> None:
+    """Compile the checkers (port always; ref only where /root/reference exists)."""
+    subprocess.run(["make", "-C", _HERE, target], check=True, stdout=subprocess.DEVNULL)
+
+
+def ref_available() -> bool:
+    return os.path.exists(REF_LIB)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+class _Oracle:
+    prefix = ""
+    path = ""
+
+    def __init__(self):
+        if not os.path.exists(self.path):
+            raise FileNotFoundError(f"{self.path} not built; run `make -C oracle`")
+        self.lib = ctypes.CDLL(self.path)
+        p = self.prefix
+        L = self.lib
+        getattr(L, p + "graph_create").restype = _vp
+        getattr(L, p + "graph_create").argtypes = [_vp, ctypes.c_int, _vp, ctypes.c_int,
+                                                     ctypes.c_int, _vp]
+        getattr(L, p + "graph_destroy").argtypes = [_vp]
+        getattr(L, p + "graph_set_state").argtypes = [_vp, _vp]
+        getattr(L, p + "graph_get_state").argtypes = [_vp, _vp]
+        for name, nargs in (("lopass", 2), ("hipass", 2), ("bandpass", 2), ("loshelf", 3),
+                            ("hishelf", 3), ("bell", 3), ("onepole", 1)):
+            fn = getattr(L, p + "coeffs_" + name)
+            fn.argtypes = [ctypes.c_float] * nargs + [_vp]
+            fn.restype = None
+        getattr(L, p + "coeffs_dcblocker").argtypes = [ctypes.c_float]
+        getattr(L, p + "coeffs_dcblocker").restype = ctypes.c_float
+        getattr(L, p + "db_to_gain").argtypes = [ctypes.c_float]
+        getattr(L, p + "db_to_gain").restype = ctypes.c_float
+
+    # -- coefficient design --
+    def coeffs(self, kind: str, *args: float) -> np.ndarray:
+        n = {"lopass": 3, "hipass": 4, "bandpass": 3, "loshelf": 5, "hishelf": 6, "bell": 4,
+             "onepole": 2}[kind]
+        out = np.zeros(n, np.float32)
+        getattr(self.lib, self.prefix + "coeffs_" + kind)(*[ctypes.c_float(a) for a in args],
+                                                          _ptr(out))
+        return out
+
+    def coeffs_dcblocker(self, omega: float) -> float:
+        return float(getattr(self.lib, self.prefix + "coeffs_dcblocker")(omega))
+
+    def db_to_gain(self, db: float) -> float:
+        return float(getattr(self.lib, self.prefix + "db_to_gain")(db))
+
+    # -- graphs --
+    def _process(self, h, inp, out, mix, T, nthreads, mix_mode, n_shards):
+        raise NotImplementedError
+
+    def run(self, spec: GraphSpec, n_voices: int, n_blocks: int, inp: Optional[np.ndarray],
+            state: np.ndarray, coef: np.ndarray, want_out: bool = True, want_mix: bool = False,
+            nthreads: int = 1, mix_mode: int = 0, n_shards: int = 1,
+            splits: Optional[Tuple[int, ...]] = None):
+        """Run T blocks from `state`; returns (out, mix, state_after).
+
+        inp [T][n_in][V][64] f32; out [T][n_out][V][64]; mix [T][n_out][64].
+        `splits`: process in several successive calls of these block counts
+        (state carried inside the oracle object), to test launch-boundary continuity.
+        """
+        V, T = n_voices, n_blocks
+        p = self.prefix
+        coef = np.ascontiguousarray(coef, np.float32)
+        state = np.ascontiguousarray(state, np.uint32)
+        assert coef.shape == (spec.n_coef, V) and state.shape == (spec.n_state, V)
+        if spec.n_in:
+            inp = np.ascontiguousarray(inp, np.float32)
+            assert inp.shape == (T, spec.n_in, V, BLOCK), inp.shape
+        nodes, outs = spec.c_nodes(), spec.c_outs()
+        h = getattr(self.lib, p + "graph_create")(nodes, spec.n_nodes, outs, spec.n_out, V,
+                                                  _ptr(coef) if coef.size else None)
+        if not h:
+            raise RuntimeError("oracle rejected graph")
+        try:
+            if state.size:
+                getattr(self.lib, p + "graph_set_state")(h, _ptr(state))
+            out = np.zeros((T, spec.n_out, V, BLOCK), np.float32) if want_out else None
+            mix = np.zeros((T, spec.n_out, BLOCK), np.float32) if want_mix else None
+            t0 = 0
+            for n in (splits or (T,)):
+                i = inp[t0:t0 + n] if spec.n_in else None
+                o = out[t0:t0 + n] if want_out else None
+                m = mix[t0:t0 + n] if want_mix else None
+                self._process(h, _ptr(i), _ptr(o), _ptr(m), n, nthreads, mix_mode, n_shards)
+                t0 += n
+            assert t0 == T
+            st = np.zeros_like(state)
+            if state.size:
+                getattr(self.lib, p + "graph_get_state")(h, _ptr(st))
+        finally:
+            getattr(self.lib, p + "graph_destroy")(h)
+        return out, mix, st
+
+
+class RefOracle(_Oracle):
+    prefix = "mlref_"
+    path = REF_LIB
+
+    def __init__(self):
+        super().__init__()
+        self.lib.mlref_graph_process.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int]
+        self.lib.mlref_chain_sine_lopass_gain.restype = ctypes.c_double
+        self.lib.mlref_chain_sine_lopass_gain.argtypes = [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp,
+                                                          _vp, _vp, _vp, ctypes.c_int]
+
+    def _process(self, h, inp, out, mix, T, nthreads, mix_mode, n_shards):
+        if mix is not None and mix_mode != 0:
+            raise ValueError("the reference only sums voices left to right (mix_mode 0)")
+        self.lib.mlref_graph_process(h, inp, out, mix, T, nthreads)
+
+    def sizeof(self, which: int) -> int:
+        return int(self.lib.mlref_sizeof(which))
+
+    def chain_sine_lopass_gain(self, inp: np.ndarray, coef3: np.ndarray, gain: np.ndarray,
+                               phase: np.ndarray, ic: np.ndarray, nthreads: int):
+        """The reference's own chain loop (struct Voice{SineGen; Lopass}); returns (out, seconds)."""
+        T, V, _ = inp.shape
+        out = np.empty_like(inp)
+        sec = self.lib.mlref_chain_sine_lopass_gain(V, T, _ptr(inp), _ptr(out), _ptr(coef3),
+                                                    _ptr(gain), _ptr(phase), _ptr(ic), nthreads)
+        return out, float(sec)
+
+
+class PortOracle(_Oracle):
+    prefix = "mlport_"
+    path = PORT_LIB
+
+    def __init__(self):
+        super().__init__()
+        self.lib.mlport_graph_process.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int,
+                                                  ctypes.c_int, ctypes.c_int]
+
+    def _process(self, h, inp, out, mix, T, nthreads, mix_mode, n_shards):
+        self.lib.mlport_graph_process(h, inp, out, mix, T, nthreads, mix_mode, n_shards)

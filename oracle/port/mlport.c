@@ -1,0 +1,1022 @@
+/*
+ * oracle/port/mlport.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain-C, CPU-only restatement of madronalib's DSPVector hot path: every
+ * function follows the cited reference file:line, one f32 lane at a time
+ * (each SSE op on 4 lanes == the same scalar op on each lane).
+ * It exists so that the CUDA kernels can be checked on a machine where
+ * /root/reference does not exist (the GPU box).  It is pinned against the
+ * compiled reference itself (oracle/_ref/libmlref.so) and against the
+ * committed golden vectors by tests/test_oracle_*.py.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library.  madronalib_b200/ never does.
+ *
+ * Build: gcc -O2 -ffp-contract=off -msse2 -mfpmath=sse (oracle/Makefile) so
+ * that every mul/add is a separately rounded IEEE binary32 operation, like the
+ * SSE2 instructions the reference compiles to.
+ *
+ * Abbreviations: G = source/DSP/MLDSPGens.h, F = source/DSP/MLDSPFilters.h,
+ * O = source/DSP/MLDSPOps.h, M = source/DSP/MLDSPMathSSE.h,
+ * S = source/DSP/MLDSPScalarMath.h
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <xmmintrin.h> /* only for _mm_rcp_ss/_mm_rsqrt_ss: the 12-bit hardware approximations */
+
+#include "mlb200.h"
+
+#define NB MLB_BLOCK
+
+static inline uint32_t f2u(float f)
+{
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+static inline float u2f(uint32_t u)
+{
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+/* ------------------------------------------------------------------ */
+/* L0 primitives (M:75-135, 221-241)                                   */
+
+/* _mm_cvtps_epi32 (M:124): round to nearest even; NaN / out of range ->
+ * "integer indefinite" 0x80000000. */
+static inline int32_t cvt_round(float x)
+{
+  if (!(fabsf(x) < 2147483648.0f)) return INT32_MIN;
+  return (int32_t)rintf(x); /* default rounding mode = RN-even */
+}
+/* _mm_cvttps_epi32 (M:125): truncate, same overflow rule */
+static inline int32_t cvt_trunc(float x)
+{
+  if (!(fabsf(x) < 2147483648.0f)) return INT32_MIN;
+  return (int32_t)x;
+}
+/* vecUnsignedIntToFloat (M:130-135): t = (float)(int)(v >> 1); return t + t */
+static inline float unsigned_to_float(uint32_t v)
+{
+  float t = (float)(int32_t)(v >> 1);
+  return t + t;
+}
+/* _mm_min_ps / _mm_max_ps (M:80-81): second operand when unordered or equal */
+static inline float sse_min(float a, float b) { return a < b ? a : b; }
+static inline float sse_max(float a, float b) { return a > b ? a : b; }
+static inline float mask_f(int c) { return u2f(c ? 0xFFFFFFFFu : 0u); }
+static inline float sel_bits(float a, float b, uint32_t m) /* vecSelect M:221-241 */
+{
+  return u2f((m & f2u(a)) | (~m & f2u(b)));
+}
+static inline float sse_rcp(float x) { return _mm_cvtss_f32(_mm_rcp_ss(_mm_set_ss(x))); }
+static inline float sse_rsqrt(float x) { return _mm_cvtss_f32(_mm_rsqrt_ss(_mm_set_ss(x))); }
+
+/* ------------------------------------------------------------------ */
+/* precise transcendental functions (cephes via sse_mathfun)            */
+
+/* vecLog, M:308-373 */
+static float ml_log(float x)
+{
+  const int invalid = (x <= 0.0f);
+  x = sse_max(x, u2f(0x00800000u)); /* cut off denormals (M:314) */
+  int32_t emm0 = (int32_t)(f2u(x) >> 23);
+  x = u2f((f2u(x) & ~0x7f800000u) | f2u(0.5f));
+  emm0 -= 0x7f;
+  float e = (float)emm0;
+  e = e + 1.0f;
+  const int m = (x < 0.707106781186547524f);
+  float tmp = m ? x : 0.0f;
+  x = x - 1.0f;
+  e = e - (m ? 1.0f : 0.0f);
+  x = x + tmp;
+  float z = x * x;
+  float y = 7.0376836292E-2f;
+  y = y * x;
+  y = y + -1.1514610310E-1f;
+  y = y * x;
+  y = y + 1.1676998740E-1f;
+  y = y * x;
+  y = y + -1.2420140846E-1f;
+  y = y * x;
+  y = y + 1.4249322787E-1f;
+  y = y * x;
+  y = y + -1.6668057665E-1f;
+  y = y * x;
+  y = y + 2.0000714765E-1f;
+  y = y * x;
+  y = y + -2.4999993993E-1f;
+  y = y * x;
+  y = y + 3.3333331174E-1f;
+  y = y * x;
+  y = y * z;
+  tmp = e * -2.12194440e-4f;
+  y = y + tmp;
+  tmp = z * 0.5f;
+  y = y - tmp;
+  tmp = e * 0.693359375f;
+  x = x + y;
+  x = x + tmp;
+  if (invalid) x = u2f(f2u(x) | 0xFFFFFFFFu); /* M:371 */
+  return x;
+}
+
+/* vecExp, M:389-440 */
+static float ml_exp(float x)
+{
+  x = sse_min(x, 88.3762626647949f);
+  x = sse_max(x, -88.3762626647949f);
+  float fx = x * 1.44269504088896341f;
+  fx = fx + 0.5f;
+  int32_t emm0 = cvt_trunc(fx);
+  float tmp = (float)emm0;
+  float mask = (tmp > fx) ? 1.0f : 0.0f;
+  fx = tmp - mask;
+  tmp = fx * 0.693359375f;
+  float z = fx * -2.12194440e-4f;
+  x = x - tmp;
+  x = x - z;
+  z = x * x;
+  float y = 1.9875691500E-4f;
+  y = y * x;
+  y = y + 1.3981999507E-3f;
+  y = y * x;
+  y = y + 8.3334519073E-3f;
+  y = y * x;
+  y = y + 4.1665795894E-2f;
+  y = y * x;
+  y = y + 1.6666665459E-1f;
+  y = y * x;
+  y = y + 5.0000001201E-1f;
+  y = y * z;
+  y = y + x;
+  y = y + 1.0f;
+  emm0 = cvt_trunc(fx);
+  emm0 = (int32_t)((uint32_t)(emm0 + 0x7f) << 23);
+  return y * u2f((uint32_t)emm0);
+}
+
+/* shared tail of vecSin / vecCos: M:515-558 / M:591-635 */
+static float sincos_poly(float x, float y, uint32_t poly_mask, uint32_t sign_bit)
+{
+  float xmm1 = y * -0.78515625f;
+  float xmm2 = y * -2.4187564849853515625e-4f;
+  float xmm3 = y * -3.77489497744594108e-8f;
+  x = x + xmm1;
+  x = x + xmm2;
+  x = x + xmm3;
+  y = 2.443315711809948E-005f;
+  float z = x * x;
+  y = y * z;
+  y = y + -1.388731625493765E-003f;
+  y = y * z;
+  y = y + 4.166664568298827E-002f;
+  y = y * z;
+  y = y * z;
+  float tmp = z * 0.5f;
+  y = y - tmp;
+  y = y + 1.0f;
+  float y2 = -1.9515295891E-4f;
+  y2 = y2 * z;
+  y2 = y2 + 8.3321608736E-3f;
+  y2 = y2 * z;
+  y2 = y2 + -1.6666654611E-1f;
+  y2 = y2 * z;
+  y2 = y2 * x;
+  y2 = y2 + x;
+  y2 = u2f(poly_mask & f2u(y2));
+  y = u2f(~poly_mask & f2u(y));
+  y = y + y2;
+  return u2f(f2u(y) ^ sign_bit);
+}
+
+/* vecSin, M:479-559 */
+static float ml_sin(float x)
+{
+  uint32_t sign_bit = f2u(x) & 0x80000000u;
+  x = u2f(f2u(x) & 0x7FFFFFFFu);
+  float y = x * 1.27323954473516f;
+  int32_t emm2 = cvt_trunc(y);
+  emm2 = (int32_t)(((uint32_t)emm2 + 1u) & ~1u);
+  y = (float)emm2;
+  uint32_t emm0 = ((uint32_t)emm2 & 4u) << 29;
+  uint32_t poly_mask = (((uint32_t)emm2 & 2u) == 0u) ? 0xFFFFFFFFu : 0u;
+  sign_bit ^= emm0;
+  return sincos_poly(x, y, poly_mask, sign_bit);
+}
+
+/* vecCos, M:562-636 */
+static float ml_cos(float x)
+{
+  x = u2f(f2u(x) & 0x7FFFFFFFu);
+  float y = x * 1.27323954473516f;
+  int32_t emm2 = cvt_trunc(y);
+  emm2 = (int32_t)(((uint32_t)emm2 + 1u) & ~1u);
+  y = (float)emm2;
+  emm2 = (int32_t)((uint32_t)emm2 - 2u);
+  uint32_t emm0 = (~(uint32_t)emm2 & 4u) << 29;
+  uint32_t poly_mask = (((uint32_t)emm2 & 2u) == 0u) ? 0xFFFFFFFFu : 0u;
+  return sincos_poly(x, y, poly_mask, emm0);
+}
+
+/* ------------------------------------------------------------------ */
+/* polynomial approximations, M:752-864                                 */
+
+static float ml_sin_approx(float x) /* M:758-772 */
+{
+  float x2 = x * x;
+  return x * (0.99997937679290771484375f +
+              x2 * (-0.166624367237091064453125f +
+                    x2 * (8.30897875130176544189453125e-3f +
+                          x2 * (-1.92649182281456887722015380859375e-4f +
+                                x2 * 2.147840177713078446686267852783203125e-6f))));
+}
+static float ml_cos_approx(float x) /* M:780-792 */
+{
+  float x2 = x * x;
+  return 0.999959766864776611328125f +
+         x2 * (-0.4997930824756622314453125f +
+               x2 * (4.1496001183986663818359375e-2f +
+                     x2 * (-1.33926304988563060760498046875e-3f +
+                           x2 * 1.8791708498611114919185638427734375e-5f)));
+}
+static float ml_exp_approx(float x) /* M:802-829 */
+{
+  float val2 = x * 12102203.1615614f + 1065353216.f;
+  float val3 = sse_min(val2, 2139095040.f);
+  float val4 = sse_max(val3, 0.0f);
+  uint32_t val4i = (uint32_t)cvt_trunc(val4);
+  float xu = u2f(val4i & 0x7F800000u);
+  float b = u2f((val4i & 0x7FFFFFu) | 0x3F800000u);
+  return xu * (0.510397365625862338668154f +
+               b * (0.310670891004095530771135f +
+                    b * (0.168143436463395944830000f +
+                         b * (-2.88093587581985443087955e-3f +
+                              b * 1.3671023382430374383648148e-2f))));
+}
+static float ml_log_approx(float val) /* M:839-864 */
+{
+  uint32_t vi = f2u(val);
+  int32_t expi = (int32_t)(vi >> 23);
+  /* vecSelect(kLogC1Vec, FLT_MIN, val > 0) */
+  float addcst = (val > 0.0f) ? -89.970756366f : u2f(0x00800000u);
+  float x = u2f((vi & 0x7FFFFFu) | 0x3F800000u);
+  float poly = x * (3.529304993f +
+                    x * (-2.461222105f +
+                         x * (1.130626167f + x * (-0.288739945f + x * 3.110401639e-2f))));
+  float addCstResult = addcst + 0.69314718055995f * (float)expi;
+  return poly + addCstResult;
+}
+
+/* O:601-604,613-614 */
+#define K_LOG_TWO 0.69314718055994529f
+#define K_LOG_TWO_R 1.4426950408889634f
+
+/* ------------------------------------------------------------------ */
+/* stateless ops on one lane (O:584-614, 640-649, 744-748, 796-856)     */
+
+static float op1(int op, float x)
+{
+  switch (op)
+  {
+    case MLB_OP_SQRT: return sqrtf(x);                  /* vecSqrt M:83 */
+    case MLB_OP_SQRT_APPROX: return x * sse_rsqrt(x);   /* M:84-85 */
+    case MLB_OP_ABS: return u2f(f2u(x) & 0x7FFFFFFFu);  /* M:86 */
+    case MLB_OP_SIGN:                                   /* M:88-90 */
+      return u2f(((f2u(x) & 0x80000000u) | 0x3F800000u) & (x != -0.0f ? 0xFFFFFFFFu : 0u));
+    case MLB_OP_SIGNBIT: return u2f((f2u(x) & 0x80000000u) | 0x3F800000u); /* M:92 */
+    case MLB_OP_SIN: return ml_sin(x);
+    case MLB_OP_COS: return ml_cos(x);
+    case MLB_OP_LOG: return ml_log(x);
+    case MLB_OP_EXP: return ml_exp(x);
+    case MLB_OP_LOG2: return ml_log(x) * K_LOG_TWO_R;
+    case MLB_OP_EXP2: return ml_exp(K_LOG_TWO * x);
+    case MLB_OP_SIN_APPROX: return ml_sin_approx(x);
+    case MLB_OP_COS_APPROX: return ml_cos_approx(x);
+    case MLB_OP_EXP_APPROX: return ml_exp_approx(x);
+    case MLB_OP_LOG_APPROX: return ml_log_approx(x);
+    case MLB_OP_LOG2_APPROX: return ml_log_approx(x) * K_LOG_TWO_R;
+    case MLB_OP_EXP2_APPROX: return ml_exp_approx(K_LOG_TWO * x);
+    case MLB_OP_FRACTIONAL_PART: return x - (float)cvt_trunc(x); /* O:825 */
+    case MLB_OP_ROUND_F2I: return u2f((uint32_t)cvt_round(x));
+    case MLB_OP_TRUNC_F2I: return u2f((uint32_t)cvt_trunc(x));
+    case MLB_OP_INT_TO_FLOAT: return (float)(int32_t)f2u(x);
+    case MLB_OP_UNSIGNED_TO_FLOAT: return unsigned_to_float(f2u(x));
+  }
+  return 0.0f;
+}
+
+static float op2(int op, float a, float b)
+{
+  switch (op)
+  {
+    case MLB_OP_ADD: return a + b;
+    case MLB_OP_SUBTRACT: return a - b;
+    case MLB_OP_MULTIPLY: return a * b;
+    case MLB_OP_DIVIDE: return a / b;
+    case MLB_OP_DIVIDE_APPROX: return a * sse_rcp(b);             /* M:79 */
+    case MLB_OP_POW: return ml_exp(ml_log(a) * b);                /* O:646 */
+    case MLB_OP_POW_APPROX: return ml_exp_approx(ml_log_approx(a) * b);
+    case MLB_OP_MIN: return sse_min(a, b);
+    case MLB_OP_MAX: return sse_max(a, b);
+    case MLB_OP_EQUAL: return mask_f(a == b);
+    case MLB_OP_NOT_EQUAL: return mask_f(!(a == b)); /* cmpneq: true when unordered */
+    case MLB_OP_GREATER_THAN: return mask_f(a > b);
+    case MLB_OP_GREATER_EQUAL: return mask_f(a >= b);
+    case MLB_OP_LESS_THAN: return mask_f(a < b);
+    case MLB_OP_LESS_EQUAL: return mask_f(a <= b);
+    case MLB_OP_ADD_INT32: return u2f(f2u(a) + f2u(b));
+    case MLB_OP_SUBTRACT_INT32: return u2f(f2u(a) - f2u(b));
+  }
+  return 0.0f;
+}
+
+static float op3(int op, float a, float b, float c)
+{
+  switch (op)
+  {
+    case MLB_OP_LERP: return a + (c * (b - a));           /* O:744 */
+    case MLB_OP_INVERSE_LERP: return (c - a) / (b - a);   /* O:745 */
+    case MLB_OP_CLAMP: return sse_min(sse_max(a, b), c);  /* M:93 */
+    case MLB_OP_WITHIN: return u2f(f2u(mask_f(a >= b)) & f2u(mask_f(a < c))); /* M:94 */
+    case MLB_OP_SELECT: return sel_bits(a, b, f2u(c));    /* O:886 */
+  }
+  return 0.0f;
+}
+
+/* ------------------------------------------------------------------ */
+/* generators                                                           */
+
+/* NoiseGen::operator(), G:115,132-142 */
+static void gen_noise(uint32_t* seed, float* y)
+{
+  uint32_t s = *seed;
+  for (int i = 0; i < NB; ++i)
+  {
+    s = s * 0x0019660Du + 0x3C6EF35Fu;
+    uint32_t temp = ((s >> 9) & 0x007FFFFFu) | 0x3F800000u;
+    y[i] = u2f(temp) * 2.f - 3.f;
+  }
+  *seed = s;
+}
+
+/* PhasorGen::operator(), G:187-203.  stepsPerCycle = 2^32, cyclesPerStep = 2^-32 */
+static void gen_phasor(uint32_t* omega32, const float* freq, float* y)
+{
+  uint32_t om = *omega32;
+  for (int n = 0; n < NB; ++n)
+  {
+    float steps = freq[n] * 4294967296.0f;
+    int32_t isteps = cvt_round(steps);
+    om += (uint32_t)isteps;
+    y[n] = unsigned_to_float(om) * (1.0f / 4294967296.0f);
+  }
+  *omega32 = om;
+}
+
+/* phasorToSine, G:316-338.  The constants come from the reference's constexpr
+ * Newton sqrt with tolerance 1e-3 (S:224,230-235): sqrt2 = 0x1.6a0a0ap+0, NOT
+ * sqrt(2).  Bit patterns verified against the compiled reference. */
+#define K_SQRT2 0x1.6a0a0ap+0f
+#define K_DOMAIN 0x1.6a0a0ap+2f  /* sqrt2 * 4 */
+#define K_FLIP 0x1.6a0a0ap+1f    /* sqrt2 * 2 */
+#define K_INV_RANGE 0x1.0f876cp+0f /* 1 / (sqrt2 - sqrt2^3/6) */
+#define K_ONE_SIXTH 0x1.555556p-3f
+static inline float phasor_to_sine(float ph)
+{
+  float omega = ph * K_DOMAIN + (-K_SQRT2);
+  float tri = (omega > K_SQRT2) ? (K_FLIP - omega) : omega;
+  return (K_INV_RANGE * tri) * (1.0f - (tri * tri) * K_ONE_SIXTH);
+}
+
+/* polyBLEP, G:285-311 */
+static inline float poly_blep(float t, float dt)
+{
+  float c = 0.f;
+  if (t < dt)
+  {
+    t = t / dt;
+    c = t + t - t * t - 1.0f;
+  }
+  else if (t > 1.0f - dt)
+  {
+    t = (t - 1.0f) / dt;
+    c = t * t + t + t + 1.0f;
+  }
+  return c;
+}
+
+/* TickGen::operator(), G:29-46 */
+static void gen_tick(uint32_t* st, const float* freq, float* y)
+{
+  float om = u2f(*st);
+  for (int n = 0; n < NB; ++n)
+  {
+    y[n] = 0.f;
+    om += freq[n];
+    if (om > 1.0f)
+    {
+      om -= 1.0f;
+      y[n] = 1.0f;
+    }
+  }
+  *st = f2u(om);
+}
+
+/* ------------------------------------------------------------------ */
+/* filters                                                              */
+
+/* shared SVF core for Lopass/Hipass/Bandpass (F:121-131,183-194,227-237) */
+#define SVF_G_CORE                         \
+  float v0 = x[n];                         \
+  float t0 = v0 - ic2;                     \
+  float t1 = g0 * t0 + g1 * ic1;           \
+  float t2 = g2 * t0 + g0 * ic1;
+
+static void flt_lopass(uint32_t* st, const float* c, const float* x, float* y)
+{
+  float ic1 = u2f(st[0]), ic2 = u2f(st[1]);
+  const float g0 = c[0], g1 = c[1], g2 = c[2];
+  for (int n = 0; n < NB; ++n)
+  {
+    SVF_G_CORE
+    float v2 = t2 + ic2;
+    ic1 += 2.0f * t1;
+    ic2 += 2.0f * t2;
+    y[n] = v2;
+  }
+  st[0] = f2u(ic1), st[1] = f2u(ic2);
+}
+static void flt_hipass(uint32_t* st, const float* c, const float* x, float* y)
+{
+  float ic1 = u2f(st[0]), ic2 = u2f(st[1]);
+  const float g0 = c[0], g1 = c[1], g2 = c[2], k = c[3];
+  for (int n = 0; n < NB; ++n)
+  {
+    SVF_G_CORE
+    float v1 = t1 + ic1;
+    float v2 = t2 + ic2;
+    ic1 += 2.0f * t1;
+    ic2 += 2.0f * t2;
+    y[n] = v0 - k * v1 - v2;
+  }
+  st[0] = f2u(ic1), st[1] = f2u(ic2);
+}
+static void flt_bandpass(uint32_t* st, const float* c, const float* x, float* y)
+{
+  float ic1 = u2f(st[0]), ic2 = u2f(st[1]);
+  const float g0 = c[0], g1 = c[1], g2 = c[2];
+  for (int n = 0; n < NB; ++n)
+  {
+    SVF_G_CORE
+    float v1 = t1 + ic1;
+    ic1 += 2.0f * t1;
+    ic2 += 2.0f * t2;
+    y[n] = v1;
+  }
+  st[0] = f2u(ic1), st[1] = f2u(ic2);
+}
+
+/* shared SVF core for the shelves and bell (F:293-298, 374-379, 432-437) */
+#define SVF_A_CORE                          \
+  float v0 = x[n];                          \
+  float v3 = v0 - ic2;                      \
+  float v1 = a1 * ic1 + a2 * v3;            \
+  float v2 = ic2 + a2 * ic1 + a3 * v3;      \
+  ic1 = 2 * v1 - ic1;                       \
+  ic2 = 2 * v2 - ic2;
+
+static void flt_loshelf(uint32_t* st, const float* c, const float* x, float* y)
+{
+  float ic1 = u2f(st[0]), ic2 = u2f(st[1]);
+  const float a1 = c[0], a2 = c[1], a3 = c[2], m1 = c[3], m2 = c[4];
+  for (int n = 0; n < NB; ++n)
+  {
+    SVF_A_CORE
+    y[n] = v0 + m1 * v1 + m2 * v2;
+  }
+  st[0] = f2u(ic1), st[1] = f2u(ic2);
+}
+static void flt_hishelf(uint32_t* st, const float* c, const float* x, float* y)
+{
+  float ic1 = u2f(st[0]), ic2 = u2f(st[1]);
+  const float a1 = c[0], a2 = c[1], a3 = c[2], m0 = c[3], m1 = c[4], m2 = c[5];
+  for (int n = 0; n < NB; ++n)
+  {
+    SVF_A_CORE
+    y[n] = m0 * v0 + m1 * v1 + m2 * v2;
+  }
+  st[0] = f2u(ic1), st[1] = f2u(ic2);
+}
+static void flt_bell(uint32_t* st, const float* c, const float* x, float* y)
+{
+  float ic1 = u2f(st[0]), ic2 = u2f(st[1]);
+  const float a1 = c[0], a2 = c[1], a3 = c[2], m1 = c[3];
+  for (int n = 0; n < NB; ++n)
+  {
+    SVF_A_CORE
+    (void)v2;
+    y[n] = v0 + m1 * v1;
+  }
+  st[0] = f2u(ic1), st[1] = f2u(ic2);
+}
+
+/* OnePole::operator(), F:466-475 */
+static void flt_onepole(uint32_t* st, const float* c, const float* x, float* y)
+{
+  float y1 = u2f(st[0]);
+  const float a0 = c[0], b1 = c[1];
+  for (int n = 0; n < NB; ++n)
+  {
+    y1 = a0 * x[n] + b1 * y1;
+    y[n] = y1;
+  }
+  st[0] = f2u(y1);
+}
+/* DCBlocker::operator(), F:500-512 */
+static void flt_dcblocker(uint32_t* st, const float* c, const float* x, float* y)
+{
+  float x1 = u2f(st[0]), y1 = u2f(st[1]);
+  const float k = c[0];
+  for (int n = 0; n < NB; ++n)
+  {
+    const float x0 = x[n];
+    const float y0 = x0 - x1 + k * y1;
+    y1 = y0;
+    x1 = x0;
+    y[n] = y0;
+  }
+  st[0] = f2u(x1), st[1] = f2u(y1);
+}
+/* Differentiator::operator(), F:522-534 */
+static void flt_differentiator(uint32_t* st, const float* x, float* y)
+{
+  float x1 = u2f(st[0]);
+  y[0] = x[0] - x1;
+  for (int n = 1; n < NB; ++n) y[n] = x[n] - x[n - 1];
+  st[0] = f2u(x[NB - 1]);
+}
+/* Integrator::operator(), F:547-557 */
+static void flt_integrator(uint32_t* st, const float* c, const float* x, float* y)
+{
+  float y1 = u2f(st[0]);
+  const float leak = c[0];
+  for (int n = 0; n < NB; ++n)
+  {
+    y1 -= y1 * leak;
+    y1 += x[n];
+    y[n] = y1;
+  }
+  st[0] = f2u(y1);
+}
+
+/* ------------------------------------------------------------------ */
+/* IntegerDelay + FDN<8>                                                */
+
+/* bitsToContain, S:31-36 */
+static int bits_to_contain(int x)
+{
+  int e;
+  for (e = 0; (1 << e) < x; e++)
+    ;
+  return e;
+}
+
+typedef struct fdn8_mem
+{
+  float* ring[8];      /* IntegerDelay::mBuffer, F:803 */
+  uint32_t mask[8];    /* mLengthMask */
+  uint32_t widx[8];    /* mWriteIndex */
+  int len[8];          /* mIntDelayInSamples */
+  float carry[8][NB];  /* FDN::mDelayInputVectors, F:1167 */
+} fdn8_mem;
+
+static void fdn8_mem_init(fdn8_mem* m, const float* coef32)
+{
+  memset(m, 0, sizeof(*m));
+  for (int n = 0; n < 8; ++n)
+  {
+    int len = (int)coef32[24 + n];
+    /* setMaxDelayInSamples(len): newSize = 1 << bitsToContain(dMax + 64), F:822-830 */
+    int size = 1 << bits_to_contain(len + NB);
+    m->ring[n] = (float*)calloc((size_t)size, sizeof(float));
+    m->mask[n] = (uint32_t)size - 1u;
+    m->len[n] = len;
+  }
+}
+static void fdn8_mem_free(fdn8_mem* m)
+{
+  for (int n = 0; n < 8; ++n) free(m->ring[n]);
+}
+
+/* IntegerDelay::operator()(vx), F:834-875: block write at w, block read at (w-d)&mask.
+ * Sample-by-sample indexing with the mask reproduces both wrap splits. */
+static void integer_delay(fdn8_mem* m, int n, const float* x, float* y)
+{
+  float* buf = m->ring[n];
+  const uint32_t mask = m->mask[n];
+  const uint32_t w = m->widx[n];
+  for (int i = 0; i < NB; ++i) buf[(w + (uint32_t)i) & mask] = x[i];
+  const uint32_t r = (w - (uint32_t)m->len[n]) & mask;
+  for (int i = 0; i < NB; ++i) y[i] = buf[(r + (uint32_t)i) & mask];
+  m->widx[n] = (w + NB) & mask;
+}
+
+/* FDN<8>::operator(), F:1195-1238.  st: 8 OnePole y1; coef32: a0[8] b1[8] gain[8] len[8] */
+static void fdn8_process(fdn8_mem* m, uint32_t* st, const float* coef32, const float* x,
+                         float* outL, float* outR)
+{
+  float d[8][NB];
+  for (int n = 0; n < 8; ++n) integer_delay(m, n, m->carry[n], d[n]); /* F:1198-1201 */
+
+  for (int i = 0; i < NB; ++i)
+  {
+    /* DSPVector sumR, sumL default-construct to zero (O:153), F:1204-1215 */
+    float sumR = 0.f, sumL = 0.f;
+    for (int n = 0; n < 8; ++n)
+    {
+      if (n & 1)
+        sumL = sumL + d[n][i];
+      else
+        sumR = sumR + d[n][i];
+    }
+    outL[i] = sumL;
+    outR[i] = sumR;
+    float sum = 0.f; /* F:1223-1228 */
+    for (int n = 0; n < 8; ++n) sum = sum + d[n][i];
+    sum = sum * (2.0f / 8);
+    for (int n = 0; n < 8; ++n) d[n][i] = d[n][i] - sum; /* F:1232 */
+  }
+  for (int n = 0; n < 8; ++n)
+  {
+    /* F:1233-1234: filters[n](v) * gain[n] + x */
+    float y1 = u2f(st[n]);
+    const float a0 = coef32[n], b1 = coef32[8 + n], g = coef32[16 + n];
+    for (int i = 0; i < NB; ++i)
+    {
+      y1 = a0 * d[n][i] + b1 * y1;
+      m->carry[n][i] = y1 * g + x[i];
+    }
+    st[n] = f2u(y1);
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* graph runner                                                         */
+
+static int op_info(int op, int* nin, int* nst, int* nco)
+{
+  switch (op)
+  {
+#define MLB_X_CASE(NAME, id, a, b, c) \
+  case id:                            \
+    *nin = a, *nst = b, *nco = c;     \
+    return 1;
+    MLB_OP_TABLE(MLB_X_CASE)
+#undef MLB_X_CASE
+  }
+  return 0;
+}
+
+typedef struct mlport_graph
+{
+  mlb_node* nodes;
+  int n_nodes;
+  int* outs;
+  int n_out;
+  int* st_off;
+  int* co_off;
+  int n_state, n_coef, n_in, V;
+  uint32_t* state; /* [n_state][V] */
+  float* coef;     /* [n_coef][V] */
+  fdn8_mem** fdn;  /* [n_nodes] -> array of V, or NULL */
+} mlport_graph;
+
+int mlport_abi_version(void) { return MLB_ABI_VERSION; }
+
+void mlport_graph_destroy(mlport_graph* g)
+{
+  if (!g) return;
+  if (g->fdn)
+  {
+    for (int i = 0; i < g->n_nodes; ++i)
+      if (g->fdn[i])
+      {
+        for (int v = 0; v < g->V; ++v) fdn8_mem_free(&g->fdn[i][v]);
+        free(g->fdn[i]);
+      }
+    free(g->fdn);
+  }
+  free(g->nodes);
+  free(g->outs);
+  free(g->st_off);
+  free(g->co_off);
+  free(g->state);
+  free(g->coef);
+  free(g);
+}
+
+mlport_graph* mlport_graph_create(const mlb_node* nodes, int n_nodes, const int32_t* outs,
+                                  int n_out, int V, const float* coef)
+{
+  mlport_graph* g = (mlport_graph*)calloc(1, sizeof(*g));
+  g->nodes = (mlb_node*)malloc(sizeof(mlb_node) * (size_t)n_nodes);
+  memcpy(g->nodes, nodes, sizeof(mlb_node) * (size_t)n_nodes);
+  g->n_nodes = n_nodes;
+  g->outs = (int*)malloc(sizeof(int) * (size_t)(n_out > 0 ? n_out : 1));
+  for (int i = 0; i < n_out; ++i) g->outs[i] = outs[i];
+  g->n_out = n_out;
+  g->V = V;
+  g->st_off = (int*)calloc((size_t)n_nodes, sizeof(int));
+  g->co_off = (int*)calloc((size_t)n_nodes, sizeof(int));
+  g->fdn = (fdn8_mem**)calloc((size_t)n_nodes, sizeof(fdn8_mem*));
+  for (int i = 0; i < n_nodes; ++i)
+  {
+    int a, b, c;
+    if (!op_info(nodes[i].op, &a, &b, &c))
+    {
+      mlport_graph_destroy(g);
+      return NULL;
+    }
+    g->st_off[i] = g->n_state;
+    g->co_off[i] = g->n_coef;
+    g->n_state += b;
+    g->n_coef += c;
+    if (nodes[i].op == MLB_OP_INPUT && nodes[i].iarg + 1 > g->n_in) g->n_in = nodes[i].iarg + 1;
+  }
+  g->state = (uint32_t*)calloc((size_t)(g->n_state > 0 ? g->n_state : 1) * (size_t)V, 4);
+  g->coef = (float*)calloc((size_t)(g->n_coef > 0 ? g->n_coef : 1) * (size_t)V, 4);
+  if (coef && g->n_coef) memcpy(g->coef, coef, (size_t)g->n_coef * (size_t)V * 4);
+  for (int i = 0; i < n_nodes; ++i)
+    if (nodes[i].op == MLB_OP_FDN8)
+    {
+      g->fdn[i] = (fdn8_mem*)calloc((size_t)V, sizeof(fdn8_mem));
+      float c32[32];
+      for (int v = 0; v < V; ++v)
+      {
+        for (int k = 0; k < 32; ++k) c32[k] = g->coef[(size_t)(g->co_off[i] + k) * V + v];
+        fdn8_mem_init(&g->fdn[i][v], c32);
+      }
+    }
+  return g;
+}
+
+void mlport_graph_set_state(mlport_graph* g, const uint32_t* state)
+{
+  if (g->n_state) memcpy(g->state, state, (size_t)g->n_state * (size_t)g->V * 4);
+}
+void mlport_graph_get_state(mlport_graph* g, uint32_t* state)
+{
+  if (g->n_state) memcpy(state, g->state, (size_t)g->n_state * (size_t)g->V * 4);
+}
+
+typedef struct job
+{
+  mlport_graph* g;
+  const float* in;
+  float* out;
+  int T, v0, v1;
+} job;
+
+static void run_voices(mlport_graph* g, const float* in, float* out, int T, int v0, int v1)
+{
+  const int N = g->n_nodes, V = g->V;
+  float(*rows)[NB] = (float(*)[NB])malloc(sizeof(float) * NB * (size_t)N);
+  float(*rows2)[NB] = (float(*)[NB])malloc(sizeof(float) * NB * (size_t)N);
+  uint32_t st[16];
+  float co[64];
+  for (int v = v0; v < v1; ++v)
+    for (int t = 0; t < T; ++t)
+    {
+      for (int i = 0; i < N; ++i)
+      {
+        const mlb_node* nd = &g->nodes[i];
+        int nin, nst, nco;
+        op_info(nd->op, &nin, &nst, &nco);
+        for (int k = 0; k < nst; ++k) st[k] = g->state[(size_t)(g->st_off[i] + k) * V + v];
+        for (int k = 0; k < nco; ++k) co[k] = g->coef[(size_t)(g->co_off[i] + k) * V + v];
+        const float* a = nd->in[0] >= 0 ? rows[nd->in[0]] : NULL;
+        const float* b = nd->in[1] >= 0 ? rows[nd->in[1]] : NULL;
+        const float* c = nd->in[2] >= 0 ? rows[nd->in[2]] : NULL;
+        float* y = rows[i];
+        switch (nd->op)
+        {
+          case MLB_OP_INPUT:
+            memcpy(y, in + (((size_t)t * g->n_in + nd->iarg) * V + v) * NB, sizeof(float) * NB);
+            break;
+          case MLB_OP_PARAM: /* DSPVector(float k): broadcast, O:157,171-182 */
+            for (int n = 0; n < NB; ++n) y[n] = co[0];
+            break;
+          case MLB_OP_NOISE: gen_noise(&st[0], y); break;
+          case MLB_OP_PHASOR: gen_phasor(&st[0], a, y); break;
+          case MLB_OP_SINE: /* SineGen, G:380 */
+            gen_phasor(&st[0], a, y);
+            for (int n = 0; n < NB; ++n) y[n] = phasor_to_sine(y[n]);
+            break;
+          case MLB_OP_SAW: /* phasorToSaw, G:362-369 */
+            gen_phasor(&st[0], a, y);
+            for (int n = 0; n < NB; ++n)
+            {
+              float saw = y[n] * 2.f - 1.f;
+              y[n] = saw - poly_blep(y[n], a[n]);
+            }
+            break;
+          case MLB_OP_PULSE: /* phasorToPulse, G:342-358 */
+            gen_phasor(&st[0], a, y);
+            for (int n = 0; n < NB; ++n)
+            {
+              float om = y[n], w = b[n];
+              float p = (om >= w) ? -1.f : 1.f;
+              p = p + poly_blep(om, a[n]);
+              float t = om - w + 1.0f;
+              float down = t - (float)cvt_trunc(t); /* fractionalPart, O:825 */
+              p = p - poly_blep(down, a[n]);
+              y[n] = p;
+            }
+            break;
+          case MLB_OP_TICK: gen_tick(&st[0], a, y); break;
+          case MLB_OP_LOPASS: flt_lopass(st, co, a, y); break;
+          case MLB_OP_HIPASS: flt_hipass(st, co, a, y); break;
+          case MLB_OP_BANDPASS: flt_bandpass(st, co, a, y); break;
+          case MLB_OP_LOSHELF: flt_loshelf(st, co, a, y); break;
+          case MLB_OP_HISHELF: flt_hishelf(st, co, a, y); break;
+          case MLB_OP_BELL: flt_bell(st, co, a, y); break;
+          case MLB_OP_ONEPOLE: flt_onepole(st, co, a, y); break;
+          case MLB_OP_DCBLOCKER: flt_dcblocker(st, co, a, y); break;
+          case MLB_OP_DIFFERENTIATOR: flt_differentiator(st, a, y); break;
+          case MLB_OP_INTEGRATOR: flt_integrator(st, co, a, y); break;
+          case MLB_OP_FDN8: fdn8_process(&g->fdn[i][v], st, co, a, y, rows2[i]); break;
+          case MLB_OP_FDN8_R: memcpy(y, rows2[nd->in[0]], sizeof(float) * NB); break;
+          default:
+            if (nin == 1)
+              for (int n = 0; n < NB; ++n) y[n] = op1(nd->op, a[n]);
+            else if (nin == 2)
+              for (int n = 0; n < NB; ++n) y[n] = op2(nd->op, a[n], b[n]);
+            else
+              for (int n = 0; n < NB; ++n) y[n] = op3(nd->op, a[n], b[n], c[n]);
+        }
+        for (int k = 0; k < nst; ++k) g->state[(size_t)(g->st_off[i] + k) * V + v] = st[k];
+      }
+      if (out)
+        for (int c = 0; c < g->n_out; ++c)
+          memcpy(out + (((size_t)t * g->n_out + c) * V + v) * NB, rows[g->outs[c]],
+                 sizeof(float) * NB);
+    }
+  free(rows);
+  free(rows2);
+}
+
+static void* job_main(void* p)
+{
+  job* j = (job*)p;
+  run_voices(j->g, j->in, j->out, j->T, j->v0, j->v1);
+  return NULL;
+}
+
+/*
+ * mix_mode 0: reference order -- voices summed left to right v = 0..V-1 starting
+ *             from +0 (addRows, O:1349-1359).
+ * mix_mode 1: the device order -- voices in groups of 32 consecutive voices, each
+ *             group summed left to right starting from its first voice... see
+ *             DESIGN.md "mix bus"; group partials then summed left to right
+ *             starting from +0, in `n_shards` contiguous shards (one per GPU) whose
+ *             partial sums are finally added left to right starting from +0.
+ */
+void mlport_graph_process(mlport_graph* g, const float* in, float* out, float* mix, int T,
+                          int nthreads, int mix_mode, int n_shards)
+{
+  const int V = g->V;
+  float* o = out;
+  float* scratch = NULL;
+  if (!o && mix)
+  {
+    scratch = (float*)malloc(sizeof(float) * (size_t)T * (size_t)g->n_out * (size_t)V * NB);
+    o = scratch;
+  }
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > V) nthreads = V > 0 ? V : 1;
+  if (nthreads == 1)
+    run_voices(g, in, o, T, 0, V);
+  else
+  {
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nthreads);
+    job* jobs = (job*)malloc(sizeof(job) * (size_t)nthreads);
+    for (int i = 0; i < nthreads; ++i)
+    {
+      jobs[i].g = g, jobs[i].in = in, jobs[i].out = o, jobs[i].T = T;
+      jobs[i].v0 = (int)((long long)V * i / nthreads);
+      jobs[i].v1 = (int)((long long)V * (i + 1) / nthreads);
+      pthread_create(&th[i], NULL, job_main, &jobs[i]);
+    }
+    for (int i = 0; i < nthreads; ++i) pthread_join(th[i], NULL);
+    free(th);
+    free(jobs);
+  }
+  if (mix)
+  {
+    if (n_shards < 1) n_shards = 1;
+    for (int t = 0; t < T; ++t)
+      for (int c = 0; c < g->n_out; ++c)
+      {
+        const float* plane = o + ((size_t)t * g->n_out + c) * (size_t)V * NB;
+        float* m = mix + ((size_t)t * g->n_out + c) * NB;
+        for (int n = 0; n < NB; ++n)
+        {
+          if (mix_mode == 0)
+          {
+            float acc = 0.f;
+            for (int v = 0; v < V; ++v) acc = acc + plane[(size_t)v * NB + n];
+            m[n] = acc;
+          }
+          else
+          {
+            float total = 0.f;
+            for (int s = 0; s < n_shards; ++s)
+            {
+              /* shard s owns voices [s*V/S, (s+1)*V/S) exactly like bench.py's sharding */
+              int s0 = (int)((long long)V * s / n_shards), s1 = (int)((long long)V * (s + 1) / n_shards);
+              float shard = 0.f;
+              for (int g0 = s0; g0 < s1; g0 += 32)
+              {
+                int g1 = g0 + 32 < s1 ? g0 + 32 : s1;
+                float grp = 0.f;
+                for (int v = g0; v < g1; ++v) grp = grp + plane[(size_t)v * NB + n];
+                shard = shard + grp;
+              }
+              total = total + shard;
+            }
+            m[n] = total;
+          }
+        }
+      }
+  }
+  free(scratch);
+}
+
+/* ---- coefficient design (host libm, same calls as the reference) ---- */
+#define K_PI 3.1415926535897932384626433f    /* S:24 */
+#define K_TWO_PI 6.2831853071795864769252867f /* S:23 */
+
+static void svf_g(float omega, float k, float* g0, float* g1, float* g2)
+{
+  /* F:85-95 (identical bodies at F:168-178, 212-222) */
+  float piOmega = K_PI * omega;
+  float s1 = sinf(piOmega);
+  float s2 = sinf(2.0f * piOmega);
+  float nrm = 1.0f / (2.f + k * s2);
+  *g0 = s2 * nrm;
+  *g1 = (-2.f * s1 * s1 - k * s2) * nrm;
+  *g2 = (2.0f * s1 * s1) * nrm;
+}
+void mlport_coeffs_lopass(float omega, float k, float* o) { svf_g(omega, k, &o[0], &o[1], &o[2]); }
+void mlport_coeffs_hipass(float omega, float k, float* o)
+{
+  svf_g(omega, k, &o[0], &o[1], &o[2]);
+  o[3] = k;
+}
+void mlport_coeffs_bandpass(float omega, float k, float* o) { svf_g(omega, k, &o[0], &o[1], &o[2]); }
+void mlport_coeffs_loshelf(float omega, float k, float A, float* r) /* F:270-281 */
+{
+  float piOmega = K_PI * omega;
+  float g = tanf(piOmega) / sqrtf(A);
+  r[0] = 1.f / (1.f + g * (g + k));
+  r[1] = g * r[0];
+  r[2] = g * r[1];
+  r[3] = k * (A - 1.f);
+  r[4] = (A * A - 1.f);
+}
+void mlport_coeffs_hishelf(float omega, float k, float A, float* r) /* F:350-362 */
+{
+  float piOmega = K_PI * omega;
+  float g = tanf(piOmega) * sqrtf(A);
+  r[0] = 1.f / (1.f + g * (g + k));
+  r[1] = g * r[0];
+  r[2] = g * r[1];
+  r[3] = A * A;
+  r[4] = k * (1.f - A) * A;
+  r[5] = (1.f - A * A);
+}
+void mlport_coeffs_bell(float omega, float k, float A, float* r) /* F:415-425 */
+{
+  float kc = k / A;
+  float piOmega = K_PI * omega;
+  float g = tanf(piOmega);
+  float a1 = 1.f / (1.f + g * (g + kc));
+  float a2 = g * a1;
+  float a3 = g * a2;
+  float m1 = kc * (A * A - 1.f);
+  r[0] = a1, r[1] = a2, r[2] = a3, r[3] = m1;
+}
+void mlport_coeffs_onepole(float omega, float* r) /* F:458-462 */
+{
+  float x = expf(-omega * K_TWO_PI);
+  r[0] = 1.f - x;
+  r[1] = x;
+}
+float mlport_coeffs_dcblocker(float omega) { return cosf(omega); } /* F:498 */
+float mlport_db_to_gain(float dB) { return powf(10.f, dB / 40.f); } /* F:30 */

@@ -1,0 +1,640 @@
+// oracle/ref/mlref.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Runs voice graphs through the UNMODIFIED reference implementation
+// (madronalib's header-only SSE DSP layer), compiled in place from
+// /root/reference by oracle/Makefile into oracle/_ref/libmlref.so.  No reference
+// source is copied into this repository: this file only #includes the headers
+// where they lie and calls the reference's own functors.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+// reference legs may load the resulting library.  The product path
+// (madronalib_b200/) never does.
+//
+// Build flags that matter (see oracle/Makefile and SURVEY.md section 8c):
+//   -fno-strict-aliasing   the reference reads DSPVectorArrayInt through float*
+//   -ffp-contract=off      scalar recurrences must stay mul-then-add (SSE2)
+//   -include cstdint -include cstddef   libstdc++ 13 needs them (MLDSPMathSSE.h:68-72)
+//   -fno-access-control    read/write private functor state (mOmega32, ic1eq, ...)
+//                          without touching the reference sources
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#include "MLDSPOps.h"
+#include "MLDSPFilters.h"
+#include "MLDSPGens.h"
+#include "MLDSPFunctional.h"
+
+#include "mlb200.h"
+
+using namespace ml;
+
+namespace
+{
+struct OpInfo
+{
+  int nin, nst, nco;
+};
+
+bool opInfo(int op, OpInfo& oi)
+{
+  switch (op)
+  {
+#define MLB_X_CASE(NAME, id, nin, nst, nco) \
+  case id:                                  \
+    oi = {nin, nst, nco};                   \
+    return true;
+    MLB_OP_TABLE(MLB_X_CASE)
+#undef MLB_X_CASE
+  }
+  return false;
+}
+
+inline uint32_t f2u(float f)
+{
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  return u;
+}
+inline float u2f(uint32_t u)
+{
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+
+// reinterpret a float row as an int row and back (the reference's int vectors
+// share storage with float vectors, MLDSPOps.h:392-421)
+inline DSPVectorInt asInt(const DSPVector& x)
+{
+  DSPVectorInt r;
+  std::memcpy(r.getBufferInt(), x.getConstBuffer(), sizeof(float) * kFloatsPerDSPVector);
+  return r;
+}
+inline DSPVector asFloat(const DSPVectorInt& x)
+{
+  DSPVector r;
+  std::memcpy(r.getBuffer(), x.getConstBufferInt(), sizeof(float) * kFloatsPerDSPVector);
+  return r;
+}
+
+// One voice's processor for one node.  Holds the reference functor by value.
+struct Proc
+{
+  virtual ~Proc() {}
+  virtual void setCoefs(const float*) {}
+  virtual void loadState(const uint32_t*) {}
+  virtual void storeState(uint32_t*) const {}
+  // returns output row; out2 only for FDN8
+  virtual DSPVector run(const DSPVector* const* in, DSPVector* out2) = 0;
+};
+
+struct PParam : Proc
+{
+  float k{0};
+  void setCoefs(const float* c) override { k = c[0]; }
+  DSPVector run(const DSPVector* const*, DSPVector*) override { return DSPVector(k); }
+};
+struct PNoise : Proc
+{
+  NoiseGen g;
+  void loadState(const uint32_t* s) override { g.setSeed(s[0]); }
+  void storeState(uint32_t* s) const override { s[0] = g.mSeed; }
+  DSPVector run(const DSPVector* const*, DSPVector*) override { return g(); }
+};
+struct PPhasor : Proc
+{
+  PhasorGen g;
+  void loadState(const uint32_t* s) override { g.clear(s[0]); }
+  void storeState(uint32_t* s) const override { s[0] = g.mOmega32; }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return g(*in[0]); }
+};
+struct PSine : Proc
+{
+  SineGen g;
+  void loadState(const uint32_t* s) override { g._phasor.clear(s[0]); }
+  void storeState(uint32_t* s) const override { s[0] = g._phasor.mOmega32; }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return g(*in[0]); }
+};
+struct PSaw : Proc
+{
+  SawGen g;
+  void loadState(const uint32_t* s) override { g._phasor.clear(s[0]); }
+  void storeState(uint32_t* s) const override { s[0] = g._phasor.mOmega32; }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return g(*in[0]); }
+};
+struct PPulse : Proc
+{
+  PulseGen g;
+  void loadState(const uint32_t* s) override { g._phasor.clear(s[0]); }
+  void storeState(uint32_t* s) const override { s[0] = g._phasor.mOmega32; }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return g(*in[0], *in[1]); }
+};
+struct PTick : Proc
+{
+  TickGen g;
+  void loadState(const uint32_t* s) override { g.mOmega = u2f(s[0]); }
+  void storeState(uint32_t* s) const override { s[0] = f2u(g.mOmega); }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return g(*in[0]); }
+};
+
+#define SVF_STATE(f)                                                                 \
+  void loadState(const uint32_t* s) override { f.ic1eq = u2f(s[0]), f.ic2eq = u2f(s[1]); } \
+  void storeState(uint32_t* s) const override { s[0] = f2u(f.ic1eq), s[1] = f2u(f.ic2eq); }
+
+struct PLopass : Proc
+{
+  Lopass f;
+  void setCoefs(const float* c) override { f.coeffs = {c[0], c[1], c[2]}; }
+  SVF_STATE(f)
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0]); }
+};
+struct PHipass : Proc
+{
+  Hipass f;
+  void setCoefs(const float* c) override { f.coeffs = {c[0], c[1], c[2], c[3]}; }
+  SVF_STATE(f)
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0]); }
+};
+struct PBandpass : Proc
+{
+  Bandpass f;
+  void setCoefs(const float* c) override { f.coeffs = {c[0], c[1], c[2]}; }
+  SVF_STATE(f)
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0]); }
+};
+struct PLoShelf : Proc
+{
+  LoShelf f;
+  void setCoefs(const float* c) override { f.coeffs = {c[0], c[1], c[2], c[3], c[4]}; }
+  SVF_STATE(f)
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0]); }
+};
+struct PHiShelf : Proc
+{
+  HiShelf f;
+  void setCoefs(const float* c) override { f.coeffs = {c[0], c[1], c[2], c[3], c[4], c[5]}; }
+  SVF_STATE(f)
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0]); }
+};
+struct PBell : Proc
+{
+  Bell f;
+  void setCoefs(const float* c) override { f.coeffs = {c[0], c[1], c[2], c[3]}; }
+  SVF_STATE(f)
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0]); }
+};
+struct POnePole : Proc
+{
+  OnePole f;
+  void setCoefs(const float* c) override { f.coeffs = {c[0], c[1]}; }
+  void loadState(const uint32_t* s) override { f.y1 = u2f(s[0]); }
+  void storeState(uint32_t* s) const override { s[0] = f2u(f.y1); }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0]); }
+};
+struct PDCBlocker : Proc
+{
+  DCBlocker f;
+  void setCoefs(const float* c) override { f.coeffs = c[0]; }
+  void loadState(const uint32_t* s) override { f.x1 = u2f(s[0]), f.y1 = u2f(s[1]); }
+  void storeState(uint32_t* s) const override { s[0] = f2u(f.x1), s[1] = f2u(f.y1); }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0]); }
+};
+struct PDifferentiator : Proc
+{
+  Differentiator f;
+  void loadState(const uint32_t* s) override { f._x1 = u2f(s[0]); }
+  void storeState(uint32_t* s) const override { s[0] = f2u(f._x1); }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0]); }
+};
+struct PIntegrator : Proc
+{
+  Integrator f;
+  void setCoefs(const float* c) override { f.mLeak = c[0]; }
+  void loadState(const uint32_t* s) override { f.y1 = u2f(s[0]); }
+  void storeState(uint32_t* s) const override { s[0] = f2u(f.y1); }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0]); }
+};
+
+// FDN<8> as shipped never allocates its IntegerDelay buffers; the
+// oracle allocates them through the delays' own public setMaxDelayInSamples,
+// reaching the private array with -fno-access-control.  Everything else is the
+// reference's FDN<8>::operator() untouched.
+struct PFDN8 : Proc
+{
+  FDN<8> f;
+  void setCoefs(const float* c) override
+  {
+    for (int n = 0; n < 8; ++n)
+    {
+      f.mFilters[n].coeffs = {c[n], c[8 + n]};
+      f.mFeedbackGains[n] = c[16 + n];
+      int len = static_cast<int>(c[24 + n]);
+      f.mDelays[n].setMaxDelayInSamples(static_cast<float>(len));
+      f.mDelays[n].setDelayInSamples(len);
+    }
+  }
+  void loadState(const uint32_t* s) override
+  {
+    for (int n = 0; n < 8; ++n) f.mFilters[n].y1 = u2f(s[n]);
+  }
+  void storeState(uint32_t* s) const override
+  {
+    for (int n = 0; n < 8; ++n) s[n] = f2u(f.mFilters[n].y1);
+  }
+  DSPVector run(const DSPVector* const* in, DSPVector* out2) override
+  {
+    DSPVectorArray<2> y = f(*in[0]);
+    *out2 = y.constRow(1);  // sumR
+    return y.constRow(0);   // sumL
+  }
+};
+
+struct PStateless : Proc
+{
+  int op;
+  explicit PStateless(int o) : op(o) {}
+  DSPVector run(const DSPVector* const* in, DSPVector*) override
+  {
+    const DSPVector& a = *in[0];
+    switch (op)
+    {
+      case MLB_OP_SQRT: return sqrt(a);
+      case MLB_OP_SQRT_APPROX: return sqrtApprox(a);
+      case MLB_OP_ABS: return abs(a);
+      case MLB_OP_SIGN: return sign(a);
+      case MLB_OP_SIGNBIT: return signBit(a);
+      case MLB_OP_SIN: return sin(a);
+      case MLB_OP_COS: return cos(a);
+      case MLB_OP_LOG: return log(a);
+      case MLB_OP_EXP: return exp(a);
+      case MLB_OP_LOG2: return log2(a);
+      case MLB_OP_EXP2: return exp2(a);
+      case MLB_OP_SIN_APPROX: return sinApprox(a);
+      case MLB_OP_COS_APPROX: return cosApprox(a);
+      case MLB_OP_EXP_APPROX: return expApprox(a);
+      case MLB_OP_LOG_APPROX: return logApprox(a);
+      case MLB_OP_LOG2_APPROX: return log2Approx(a);
+      case MLB_OP_EXP2_APPROX: return exp2Approx(a);
+      case MLB_OP_FRACTIONAL_PART: return fractionalPart(a);
+      case MLB_OP_ROUND_F2I: return asFloat(roundFloatToInt(a));
+      case MLB_OP_TRUNC_F2I: return asFloat(truncateFloatToInt(a));
+      case MLB_OP_INT_TO_FLOAT: return intToFloat(asInt(a));
+      case MLB_OP_UNSIGNED_TO_FLOAT: return unsignedIntToFloat(asInt(a));
+      default: break;
+    }
+    const DSPVector& b = *in[1];
+    switch (op)
+    {
+      case MLB_OP_ADD: return add(a, b);
+      case MLB_OP_SUBTRACT: return subtract(a, b);
+      case MLB_OP_MULTIPLY: return multiply(a, b);
+      case MLB_OP_DIVIDE: return divide(a, b);
+      case MLB_OP_DIVIDE_APPROX: return divideApprox(a, b);
+      case MLB_OP_POW: return pow(a, b);
+      case MLB_OP_POW_APPROX: return powApprox(a, b);
+      case MLB_OP_MIN: return min(a, b);
+      case MLB_OP_MAX: return max(a, b);
+      case MLB_OP_EQUAL: return asFloat(equal(a, b));
+      case MLB_OP_NOT_EQUAL: return asFloat(notEqual(a, b));
+      case MLB_OP_GREATER_THAN: return asFloat(greaterThan(a, b));
+      case MLB_OP_GREATER_EQUAL: return asFloat(greaterThanOrEqual(a, b));
+      case MLB_OP_LESS_THAN: return asFloat(lessThan(a, b));
+      case MLB_OP_LESS_EQUAL: return asFloat(lessThanOrEqual(a, b));
+      case MLB_OP_ADD_INT32: return asFloat(addInt32(asInt(a), asInt(b)));
+      case MLB_OP_SUBTRACT_INT32: return asFloat(subtractInt32(asInt(a), asInt(b)));
+      default: break;
+    }
+    const DSPVector& c = *in[2];
+    switch (op)
+    {
+      case MLB_OP_LERP: return lerp(a, b, c);
+      case MLB_OP_INVERSE_LERP: return inverseLerp(a, b, c);
+      case MLB_OP_CLAMP: return clamp(a, b, c);
+      case MLB_OP_WITHIN: return within(a, b, c);
+      case MLB_OP_SELECT: return select(a, b, asInt(c));
+      default: break;
+    }
+    return DSPVector(0.f);
+  }
+};
+
+Proc* makeProc(int op)
+{
+  switch (op)
+  {
+    case MLB_OP_PARAM: return new PParam;
+    case MLB_OP_NOISE: return new PNoise;
+    case MLB_OP_PHASOR: return new PPhasor;
+    case MLB_OP_SINE: return new PSine;
+    case MLB_OP_SAW: return new PSaw;
+    case MLB_OP_PULSE: return new PPulse;
+    case MLB_OP_TICK: return new PTick;
+    case MLB_OP_LOPASS: return new PLopass;
+    case MLB_OP_HIPASS: return new PHipass;
+    case MLB_OP_BANDPASS: return new PBandpass;
+    case MLB_OP_LOSHELF: return new PLoShelf;
+    case MLB_OP_HISHELF: return new PHiShelf;
+    case MLB_OP_BELL: return new PBell;
+    case MLB_OP_ONEPOLE: return new POnePole;
+    case MLB_OP_DCBLOCKER: return new PDCBlocker;
+    case MLB_OP_DIFFERENTIATOR: return new PDifferentiator;
+    case MLB_OP_INTEGRATOR: return new PIntegrator;
+    case MLB_OP_FDN8: return new PFDN8;
+    case MLB_OP_INPUT:
+    case MLB_OP_FDN8_R: return nullptr;
+    default: return new PStateless(op);
+  }
+}
+
+struct Graph
+{
+  std::vector<mlb_node> nodes;
+  std::vector<int> outs;
+  std::vector<int> stOff, coOff;
+  int nState{0}, nCoef{0}, nIn{0}, V{0};
+  // procs[v][node]
+  std::vector<std::vector<std::unique_ptr<Proc>>> procs;
+};
+}  // namespace
+
+extern "C"
+{
+struct mlref_graph
+{
+  Graph g;
+};
+
+int mlref_abi_version() { return MLB_ABI_VERSION; }
+
+// Create per-voice reference functors for a graph.  coef: [n_coef_words][V].
+mlref_graph* mlref_graph_create(const mlb_node* nodes, int n_nodes, const int32_t* outs, int n_out,
+                                int V, const float* coef)
+{
+  auto* h = new mlref_graph;
+  Graph& g = h->g;
+  g.nodes.assign(nodes, nodes + n_nodes);
+  g.outs.assign(outs, outs + n_out);
+  g.V = V;
+  g.stOff.resize(n_nodes);
+  g.coOff.resize(n_nodes);
+  for (int i = 0; i < n_nodes; ++i)
+  {
+    OpInfo oi;
+    if (!opInfo(nodes[i].op, oi))
+    {
+      delete h;
+      return nullptr;
+    }
+    g.stOff[i] = g.nState;
+    g.coOff[i] = g.nCoef;
+    g.nState += oi.nst;
+    g.nCoef += oi.nco;
+    if (nodes[i].op == MLB_OP_INPUT) g.nIn = std::max(g.nIn, nodes[i].iarg + 1);
+  }
+  g.procs.resize(V);
+  std::vector<float> c(64);
+  for (int v = 0; v < V; ++v)
+  {
+    g.procs[v].resize(n_nodes);
+    for (int i = 0; i < n_nodes; ++i)
+    {
+      OpInfo oi;
+      opInfo(nodes[i].op, oi);
+      g.procs[v][i].reset(makeProc(nodes[i].op));
+      if (g.procs[v][i] && oi.nco > 0)
+      {
+        for (int k = 0; k < oi.nco; ++k) c[k] = coef[(size_t)(g.coOff[i] + k) * V + v];
+        g.procs[v][i]->setCoefs(c.data());
+      }
+    }
+  }
+  return h;
+}
+
+void mlref_graph_destroy(mlref_graph* h) { delete h; }
+
+void mlref_graph_set_state(mlref_graph* h, const uint32_t* state)
+{
+  Graph& g = h->g;
+  uint32_t s[16];
+  for (int v = 0; v < g.V; ++v)
+    for (size_t i = 0; i < g.nodes.size(); ++i)
+    {
+      OpInfo oi;
+      opInfo(g.nodes[i].op, oi);
+      if (!g.procs[v][i] || oi.nst == 0) continue;
+      for (int k = 0; k < oi.nst; ++k) s[k] = state[(size_t)(g.stOff[i] + k) * g.V + v];
+      g.procs[v][i]->loadState(s);
+    }
+}
+
+void mlref_graph_get_state(mlref_graph* h, uint32_t* state)
+{
+  Graph& g = h->g;
+  uint32_t s[16];
+  for (int v = 0; v < g.V; ++v)
+    for (size_t i = 0; i < g.nodes.size(); ++i)
+    {
+      OpInfo oi;
+      opInfo(g.nodes[i].op, oi);
+      if (!g.procs[v][i] || oi.nst == 0) continue;
+      g.procs[v][i]->storeState(s);
+      for (int k = 0; k < oi.nst; ++k) state[(size_t)(g.stOff[i] + k) * g.V + v] = s[k];
+    }
+}
+
+// Process T blocks.  in [T][n_in][V][64], out [T][n_out][V][64] (may be null),
+// mix [T][n_out][64] (may be null): voices summed left to right, v = 0..V-1,
+// exactly as addRows does (MLDSPOps.h:1349-1359).
+void mlref_graph_process(mlref_graph* h, const float* in, float* out, float* mix, int T,
+                         int nthreads)
+{
+  Graph& g = h->g;
+  const int V = g.V;
+  const int N = (int)g.nodes.size();
+  const int nOut = (int)g.outs.size();
+  if (nthreads < 1) nthreads = 1;
+  nthreads = std::min(nthreads, std::max(1, V));
+
+  // per-voice outputs are needed for the ordered mix; if the caller wants mix
+  // but not out, use a scratch out.
+  std::vector<float> scratch;
+  float* o = out;
+  if (!o && mix)
+  {
+    scratch.resize((size_t)T * nOut * V * 64);
+    o = scratch.data();
+  }
+
+  auto worker = [&](int v0, int v1)
+  {
+    std::vector<DSPVector> rows(N);
+    std::vector<DSPVector> rows2(N);  // second output (FDN8 sumR)
+    for (int v = v0; v < v1; ++v)
+    {
+      for (int t = 0; t < T; ++t)
+      {
+        for (int i = 0; i < N; ++i)
+        {
+          const mlb_node& nd = g.nodes[i];
+          if (nd.op == MLB_OP_INPUT)
+          {
+            rows[i] = DSPVector(in + (((size_t)t * g.nIn + nd.iarg) * V + v) * 64);
+            continue;
+          }
+          if (nd.op == MLB_OP_FDN8_R)
+          {
+            rows[i] = rows2[nd.in[0]];
+            continue;
+          }
+          const DSPVector* ins[3] = {nullptr, nullptr, nullptr};
+          for (int k = 0; k < 3; ++k)
+            if (nd.in[k] >= 0) ins[k] = &rows[nd.in[k]];
+          rows[i] = g.procs[v][i]->run(ins, &rows2[i]);
+        }
+        if (o)
+          for (int c = 0; c < nOut; ++c)
+            store(rows[g.outs[c]], o + (((size_t)t * nOut + c) * V + v) * 64);
+      }
+    }
+  };
+
+  if (nthreads == 1)
+    worker(0, V);
+  else
+  {
+    std::vector<std::thread> th;
+    for (int i = 0; i < nthreads; ++i)
+    {
+      int v0 = (int)((long long)V * i / nthreads), v1 = (int)((long long)V * (i + 1) / nthreads);
+      th.emplace_back(worker, v0, v1);
+    }
+    for (auto& t : th) t.join();
+  }
+
+  if (mix)
+  {
+    for (int t = 0; t < T; ++t)
+      for (int c = 0; c < nOut; ++c)
+      {
+        DSPVector acc{0.f};
+        for (int v = 0; v < V; ++v)
+          acc = add(acc, DSPVector(o + (((size_t)t * nOut + c) * V + v) * 64));
+        store(acc, mix + ((size_t)t * nOut + c) * 64);
+      }
+  }
+}
+
+// ---- coefficient design straight from the reference's makeCoeffs ----
+void mlref_coeffs_lopass(float omega, float k, float* o)
+{
+  auto c = Lopass::makeCoeffs(omega, k);
+  o[0] = c[0], o[1] = c[1], o[2] = c[2];
+}
+void mlref_coeffs_hipass(float omega, float k, float* o)
+{
+  auto c = Hipass::makeCoeffs(omega, k);
+  o[0] = c.g0, o[1] = c.g1, o[2] = c.g2, o[3] = c.k;
+}
+void mlref_coeffs_bandpass(float omega, float k, float* o)
+{
+  auto c = Bandpass::makeCoeffs(omega, k);
+  o[0] = c.g0, o[1] = c.g1, o[2] = c.g2;
+}
+void mlref_coeffs_loshelf(float omega, float k, float A, float* o)
+{
+  auto c = LoShelf::makeCoeffs({omega, k, A});
+  for (int i = 0; i < 5; ++i) o[i] = c[i];
+}
+void mlref_coeffs_hishelf(float omega, float k, float A, float* o)
+{
+  auto c = HiShelf::makeCoeffs({omega, k, A});
+  for (int i = 0; i < 6; ++i) o[i] = c[i];
+}
+void mlref_coeffs_bell(float omega, float k, float A, float* o)
+{
+  auto c = Bell::makeCoeffs(omega, k, A);
+  o[0] = c.a1, o[1] = c.a2, o[2] = c.a3, o[3] = c.m1;
+}
+void mlref_coeffs_onepole(float omega, float* o)
+{
+  auto c = OnePole::makeCoeffs(omega);
+  o[0] = c.a0, o[1] = c.b1;
+}
+float mlref_coeffs_dcblocker(float omega) { return DCBlocker::makeCoeffs(omega); }
+float mlref_db_to_gain(float dB) { return dBToGain(dB); }
+
+// sizes the survey pins (Appendix A) -- lets a test check this really is the reference
+int mlref_sizeof(int which)
+{
+  switch (which)
+  {
+    case 0: return (int)sizeof(DSPVector);
+    case 1: return (int)sizeof(Lopass);
+    case 2: return (int)sizeof(OnePole);
+    case 3: return (int)sizeof(SineGen);
+    case 4: return (int)sizeof(IntegerDelay);
+    case 5: return (int)sizeof(FDN<8>);
+  }
+  return -1;
+}
+
+// ---- the reference's own chain loop, as a user would write it (CPU baseline) ----
+// struct Voice{SineGen s; Lopass lp;};  out_v = lp(s(freq_v)) * gain
+// (SURVEY 8d "CPU baseline beside it").  Contract R:
+// in/out [T][V][64].  Returns seconds of wall time for the processing loop.
+double mlref_chain_sine_lopass_gain(int V, int T, const float* in, float* out,
+                                    const float* coef3 /*[3][V]*/, const float* gain /*[V]*/,
+                                    uint32_t* phase /*[V] io*/, float* ic /*[2][V] io*/,
+                                    int nthreads)
+{
+  struct Voice
+  {
+    SineGen s;
+    Lopass lp;
+  };
+  std::vector<Voice> voices(V);
+  for (int v = 0; v < V; ++v)
+  {
+    voices[v].s._phasor.clear(phase[v]);
+    voices[v].lp.coeffs = {coef3[v], coef3[V + v], coef3[2 * V + v]};
+    voices[v].lp.ic1eq = ic[v];
+    voices[v].lp.ic2eq = ic[V + v];
+  }
+  if (nthreads < 1) nthreads = 1;
+  nthreads = std::min(nthreads, std::max(1, V));
+  auto worker = [&](int v0, int v1)
+  {
+    for (int t = 0; t < T; ++t)
+      for (int v = v0; v < v1; ++v)
+      {
+        const size_t off = ((size_t)t * V + v) * 64;
+        DSPVector y = voices[v].lp(voices[v].s(DSPVector(in + off))) * DSPVector(gain[v]);
+        store(y, out + off);
+      }
+  };
+  auto t0 = std::chrono::steady_clock::now();
+  if (nthreads == 1)
+    worker(0, V);
+  else
+  {
+    std::vector<std::thread> th;
+    for (int i = 0; i < nthreads; ++i)
+      th.emplace_back(worker, (int)((long long)V * i / nthreads),
+                      (int)((long long)V * (i + 1) / nthreads));
+    for (auto& t : th) t.join();
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  for (int v = 0; v < V; ++v)
+  {
+    phase[v] = voices[v].s._phasor.mOmega32;
+    ic[v] = voices[v].lp.ic1eq;
+    ic[V + v] = voices[v].lp.ic2eq;
+  }
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+}  // extern "C"
