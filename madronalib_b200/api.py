@@ -1,0 +1,242 @@
+"""Python host mirror of the C ABI in ``include/mlb200.h`` (ctypes over libmlb200.so).
+
+The library is the product; this module only marshals pointers.  There is NO CPU
+fallback: if ``libmlb200.so`` is missing, or no sm_100 GPU is visible, calls raise.
+
+``VoiceGraph`` is the batched analogue of the reference's ``Bank<T, ROWS>``
+(reference: source/DSP/MLDSPFunctional.h:321-360) with ``ROWS`` chosen at run time:
+``process`` = n_blocks successive ``Bank::operator()`` calls fused in one launch.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+from .graph import BLOCK, GraphSpec, Layout, Node, OP_ID
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmlb200.so")
+
+_vp = ctypes.c_void_p
+_cf = ctypes.c_float
+
+FLAG_EXACT = 0
+FLAG_FAST = 1
+FLAG_FORCE_GENERIC = 2
+
+
+class MlbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"mlb200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load libmlb200.so (built by ``python -m madronalib_b200.build``); fail loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            f"{LIB_PATH} not found: build it with `python -m madronalib_b200.build` "
+            "(there is no CPU fallback)")
+    L = ctypes.CDLL(LIB_PATH)
+    L.mlb_last_error.restype = ctypes.c_char_p
+    L.mlb_op_name.restype = ctypes.c_char_p
+    L.mlb_op_name.argtypes = [ctypes.c_int]
+    L.mlb_op_info.argtypes = [ctypes.c_int, _vp, _vp, _vp]
+    L.mlb_graph_layout.argtypes = [_vp, ctypes.c_int, _vp, _vp, _vp]
+    L.mlb_kernel_launches.restype = ctypes.c_longlong
+    L.mlb_init.argtypes = [ctypes.c_int]
+    L.mlb_graph_create.argtypes = [_vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_uint, ctypes.POINTER(_vp)]
+    L.mlb_graph_destroy.argtypes = [_vp]
+    L.mlb_graph_layout_of.argtypes = [_vp, _vp]
+    L.mlb_graph_kernel_name.restype = ctypes.c_char_p
+    L.mlb_graph_kernel_name.argtypes = [_vp]
+    L.mlb_graph_set_coefs.argtypes = [_vp, _vp]
+    L.mlb_graph_set_state.argtypes = [_vp, _vp]
+    L.mlb_graph_get_state.argtypes = [_vp, _vp]
+    L.mlb_graph_clear_delays.argtypes = [_vp]
+    L.mlb_graph_delay_bytes.restype = ctypes.c_size_t
+    L.mlb_graph_delay_bytes.argtypes = [_vp]
+    L.mlb_graph_process_device.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, _vp]
+    L.mlb_graph_process_host.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int]
+    L.mlb_graph_last_kernel_ms.argtypes = [_vp, _vp]
+    L.mlb_map_device.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]
+    L.mlb_map_host.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_size_t]
+    for name, n in (("lopass", 2), ("hipass", 2), ("bandpass", 2), ("loshelf", 3), ("hishelf", 3),
+                    ("bell", 3), ("onepole", 1)):
+        fn = getattr(L, "mlb_coeffs_" + name)
+        fn.argtypes = [_cf] * n + [_vp]
+        fn.restype = None
+    L.mlb_coeffs_dcblocker.argtypes = [_cf]
+    L.mlb_coeffs_dcblocker.restype = _cf
+    L.mlb_db_to_gain.argtypes = [_cf]
+    L.mlb_db_to_gain.restype = _cf
+    L.mlb_coeffs_fdn8.argtypes = [_vp, _vp, _vp, _vp]
+    L.mlb_coeffs_fdn8.restype = None
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise MlbError(rc, lib().mlb_last_error().decode())
+
+
+def _ptr(a) -> Optional[int]:
+    """Raw address of a numpy array / torch tensor / int / None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+def device_count() -> int:
+    return int(lib().mlb_device_count())
+
+
+def init(device: int = 0) -> None:
+    _check(lib().mlb_init(device))
+
+
+def kernel_launches() -> int:
+    return int(lib().mlb_kernel_launches())
+
+
+# ---- coefficient design (host libm; same calls as the reference's makeCoeffs) ----
+_NCOEF = {"lopass": 3, "hipass": 4, "bandpass": 3, "loshelf": 5, "hishelf": 6, "bell": 4, "onepole": 2}
+
+
+def coeffs(kind: str, *args: float) -> np.ndarray:
+    out = np.zeros(_NCOEF[kind], np.float32)
+    getattr(lib(), "mlb_coeffs_" + kind)(*[_cf(a) for a in args], out.ctypes.data)
+    return out
+
+
+def coeffs_dcblocker(omega: float) -> float:
+    return float(lib().mlb_coeffs_dcblocker(omega))
+
+
+def db_to_gain(db: float) -> float:
+    return float(lib().mlb_db_to_gain(db))
+
+
+def coeffs_fdn8(times, cutoffs, gains) -> np.ndarray:
+    t = np.ascontiguousarray(times, np.float32)
+    c = np.ascontiguousarray(cutoffs, np.float32)
+    g = np.ascontiguousarray(gains, np.float32)
+    out = np.zeros(32, np.float32)
+    lib().mlb_coeffs_fdn8(t.ctypes.data, c.ctypes.data, g.ctypes.data, out.ctypes.data)
+    return out
+
+
+# ---- stateless elementwise ops (every DEFINE_OP* of MLDSPOps.h) ----
+def map_host(op: str, x1: np.ndarray, x2: Optional[np.ndarray] = None,
+             x3: Optional[np.ndarray] = None) -> np.ndarray:
+    """y = op(x1[, x2[, x3]]) on arrays of shape [n_rows, 64] (host in, host out, GPU compute)."""
+    x1 = np.ascontiguousarray(x1, np.float32)
+    assert x1.size % BLOCK == 0
+    xs = [None if x is None else np.ascontiguousarray(x, np.float32) for x in (x2, x3)]
+    y = np.empty_like(x1)
+    _check(lib().mlb_map_host(OP_ID[op.upper()], x1.ctypes.data, _ptr(xs[0]), _ptr(xs[1]),
+                              y.ctypes.data, x1.size // BLOCK))
+    return y
+
+
+def map_device(op: str, x1, x2, x3, y, n_rows: int, stream: int = 0) -> None:
+    _check(lib().mlb_map_device(OP_ID[op.upper()], _ptr(x1), _ptr(x2), _ptr(x3), _ptr(y), n_rows,
+                                stream or None))
+
+
+class VoiceGraph:
+    """Device-resident bank of ``n_voices`` identical graphs (one voice per CUDA lane)."""
+
+    def __init__(self, spec: GraphSpec, n_voices: int, flags: int = FLAG_EXACT):
+        self.spec = spec
+        self.n_voices = int(n_voices)
+        self._h = _vp()
+        L = lib()
+        nodes, outs = spec.c_nodes(), spec.c_outs()
+        _check(L.mlb_graph_create(nodes, spec.n_nodes, outs, spec.n_out, self.n_voices, flags,
+                                  ctypes.byref(self._h)))
+        lay = Layout()
+        _check(L.mlb_graph_layout_of(self._h, ctypes.byref(lay)))
+        assert (lay.n_state_words, lay.n_coef_words, lay.n_inputs) == (spec.n_state, spec.n_coef,
+                                                                       spec.n_in)
+
+    def close(self) -> None:
+        if self._h:
+            lib().mlb_graph_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def kernel_name(self) -> str:
+        return lib().mlb_graph_kernel_name(self._h).decode()
+
+    @property
+    def delay_bytes(self) -> int:
+        return int(lib().mlb_graph_delay_bytes(self._h))
+
+    def set_coefs(self, coef: np.ndarray) -> None:
+        coef = np.ascontiguousarray(coef, np.float32)
+        assert coef.shape == (self.spec.n_coef, self.n_voices), coef.shape
+        _check(lib().mlb_graph_set_coefs(self._h, coef.ctypes.data if coef.size else None))
+
+    def set_state(self, state: np.ndarray) -> None:
+        state = np.ascontiguousarray(state, np.uint32)
+        assert state.shape == (self.spec.n_state, self.n_voices), state.shape
+        _check(lib().mlb_graph_set_state(self._h, state.ctypes.data if state.size else None))
+
+    def get_state(self) -> np.ndarray:
+        st = np.zeros((self.spec.n_state, self.n_voices), np.uint32)
+        _check(lib().mlb_graph_get_state(self._h, st.ctypes.data if st.size else None))
+        return st
+
+    def clear_delays(self) -> None:
+        _check(lib().mlb_graph_clear_delays(self._h))
+
+    def process_host(self, inp: Optional[np.ndarray], n_blocks: int, want_out: bool = True,
+                     want_mix: bool = False, out: Optional[np.ndarray] = None,
+                     mix: Optional[np.ndarray] = None):
+        """Host buffers in, host buffers out; H2D + one kernel + D2H inside the call."""
+        s, V, T = self.spec, self.n_voices, int(n_blocks)
+        if s.n_in:
+            assert inp is not None and inp.dtype == np.float32 and inp.flags["C_CONTIGUOUS"]
+            assert inp.shape == (T, s.n_in, V, BLOCK), inp.shape
+        if want_out and out is None:
+            out = np.empty((T, s.n_out, V, BLOCK), np.float32)
+        if want_mix and mix is None:
+            mix = np.empty((T, s.n_out, BLOCK), np.float32)
+        _check(lib().mlb_graph_process_host(self._h, _ptr(inp) if s.n_in else None,
+                                            _ptr(out) if want_out else None,
+                                            _ptr(mix) if want_mix else None, T))
+        return out, mix
+
+    def process_device(self, inp, out, mix, n_blocks: int, stream: int = 0) -> None:
+        """Device pointers (torch tensors / ints); asynchronous on ``stream`` (cudaStream_t)."""
+        _check(lib().mlb_graph_process_device(self._h, _ptr(inp), _ptr(out), _ptr(mix), int(n_blocks),
+                                              stream or None))
+
+    def last_kernel_ms(self) -> float:
+        ms = ctypes.c_float(0)
+        _check(lib().mlb_graph_last_kernel_ms(self._h, ctypes.byref(ms)))
+        return float(ms.value)

@@ -1,0 +1,53 @@
+"""Build madronalib_b200/libmlb200.so (C ABI + sm_100a kernels) in-tree with nvcc.
+
+Usage: python -m madronalib_b200.build [--force]
+nvcc cross-compiles without a GPU; the .so travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libmlb200.so")
+SOURCES = ["mlb200.cu"]
+DEPS = ["mlb200.cu", "ops.cuh", "tma.cuh", "chain_kernel.cuh", "generic_kernel.cuh", "fdn_kernel.cuh",
+        os.path.join("..", "..", "include", "mlb200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    # IEEE semantics: denormals kept, correctly rounded div/sqrt (reference default FP env,
+    # SURVEY appendix A); exact-mode code uses __fmul_rn/__fadd_rn so -fmad cannot fuse it
+    "-ftz=false", "-prec-div=true", "-prec-sqrt=true",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-O2",
+    "-shared",
+]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building libmlb200.so")
+    if verbose:
+        sys.stderr.write(r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,1064 @@
+// mlb200.cu -- host side of the C ABI declared in include/mlb200.h.
+//
+// Owns device memory for per-voice state / coefficients / delay lines, recognises linear
+// chains that have a fused sm_100a kernel (chain_kernel.cuh), builds the TMA tensor maps
+// and launches ONE kernel per process call.  Everything else goes through the graph
+// interpreter kernel (generic_kernel.cuh).  There is no CPU compute path in this library:
+// without an sm_100 device every processing entry point returns MLB_ERR_NO_DEVICE.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mlb200.h"
+#include "chain_kernel.cuh"
+#include "fdn_kernel.cuh"
+#include "generic_kernel.cuh"
+
+using namespace mlb;
+
+// ------------------------------------------------------------------------------------------
+// errors, counters
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU_CHECK(expr)                                                                      \
+  do                                                                                        \
+  {                                                                                         \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return fail(MLB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),   \
+                  __FILE__, __LINE__);                                                      \
+  } while (0)
+
+extern "C" const char* mlb_last_error(void) { return g_err; }
+extern "C" int mlb_abi_version(void) { return MLB_ABI_VERSION; }
+extern "C" long long mlb_kernel_launches(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------
+// op metadata and graph layout (host only)
+
+extern "C" int mlb_op_info(int op, int* n_in, int* n_state, int* n_coef)
+{
+  switch (op)
+  {
+#define MLB_X_INFO(NAME, id, nin, nst, nco) \
+  case id:                                  \
+    if (n_in) *n_in = nin;                  \
+    if (n_state) *n_state = nst;            \
+    if (n_coef) *n_coef = nco;              \
+    return MLB_OK;
+    MLB_OP_TABLE(MLB_X_INFO)
+#undef MLB_X_INFO
+  }
+  return MLB_ERR_INVALID;
+}
+
+extern "C" const char* mlb_op_name(int op)
+{
+  switch (op)
+  {
+#define MLB_X_NAME(NAME, id, nin, nst, nco) \
+  case id: return #NAME;
+    MLB_OP_TABLE(MLB_X_NAME)
+#undef MLB_X_NAME
+  }
+  return "?";
+}
+
+extern "C" int mlb_graph_layout(const mlb_node* nodes, int n_nodes, mlb_layout* layout,
+                                int32_t* state_off, int32_t* coef_off)
+{
+  if (!nodes || n_nodes <= 0 || !layout) return fail(MLB_ERR_INVALID, "null graph");
+  int ns = 0, nc = 0, nin_planes = 0, n_fdn = 0;
+  for (int i = 0; i < n_nodes; ++i)
+  {
+    int nin, nst, nco;
+    if (mlb_op_info(nodes[i].op, &nin, &nst, &nco) != MLB_OK)
+      return fail(MLB_ERR_INVALID, "node %d: unknown op %d", i, nodes[i].op);
+    for (int k = 0; k < MLB_MAX_INS; ++k)
+    {
+      const int src = nodes[i].in[k];
+      if (k < nin)
+      {
+        if (src < 0 || src >= i)
+          return fail(MLB_ERR_INVALID, "node %d (%s): input %d must be an earlier node", i,
+                      mlb_op_name(nodes[i].op), k);
+      }
+      else if (src != -1)
+        return fail(MLB_ERR_INVALID, "node %d (%s): unused input %d must be -1", i,
+                    mlb_op_name(nodes[i].op), k);
+    }
+    if (nodes[i].op == MLB_OP_INPUT)
+    {
+      if (nodes[i].iarg < 0 || nodes[i].iarg >= 64)
+        return fail(MLB_ERR_INVALID, "node %d: INPUT plane %d out of range", i, nodes[i].iarg);
+      nin_planes = std::max(nin_planes, nodes[i].iarg + 1);
+    }
+    if (nodes[i].op == MLB_OP_FDN8_R && nodes[nodes[i].in[0]].op != MLB_OP_FDN8)
+      return fail(MLB_ERR_INVALID, "node %d: FDN8_R must read an FDN8 node", i);
+    if (nodes[i].op == MLB_OP_FDN8) ++n_fdn;
+    if (state_off) state_off[i] = ns;
+    if (coef_off) coef_off[i] = nc;
+    ns += nst;
+    nc += nco;
+  }
+  if (n_fdn > 1) return fail(MLB_ERR_UNSUPPORTED, "at most one FDN8 node per graph");
+  layout->n_state_words = ns;
+  layout->n_coef_words = nc;
+  layout->n_inputs = nin_planes;
+  return MLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// coefficient design on the host with glibc libm -- the same calls the reference makes, so
+// coefficients are bit-identical by construction (SURVEY 8c "third-party arithmetic").
+
+static const float kPiF = 3.1415926535897932384626433f;     // ScalarMath.h:24
+static const float kTwoPiF = 6.2831853071795864769252867f;  // ScalarMath.h:23
+
+static void svf_g(float omega, float k, float* g0, float* g1, float* g2)
+{
+  volatile float piOmega = kPiF * omega;
+  volatile float s1 = sinf(piOmega);
+  volatile float s2 = sinf(2.0f * piOmega);
+  volatile float nrm = 1.0f / (2.f + k * s2);
+  *g0 = s2 * nrm;
+  volatile float a = -2.f * s1 * s1;
+  volatile float b = k * s2;
+  volatile float c = a - b;
+  *g1 = c * nrm;
+  volatile float d = 2.0f * s1 * s1;
+  *g2 = d * nrm;
+}
+extern "C" void mlb_coeffs_lopass(float omega, float k, float o[3]) { svf_g(omega, k, &o[0], &o[1], &o[2]); }
+extern "C" void mlb_coeffs_hipass(float omega, float k, float o[4])
+{
+  svf_g(omega, k, &o[0], &o[1], &o[2]);
+  o[3] = k;
+}
+extern "C" void mlb_coeffs_bandpass(float omega, float k, float o[3]) { svf_g(omega, k, &o[0], &o[1], &o[2]); }
+extern "C" void mlb_coeffs_loshelf(float omega, float k, float A, float r[5])
+{
+  volatile float piOmega = kPiF * omega;
+  volatile float g = tanf(piOmega) / sqrtf(A);
+  volatile float t0 = g + k;
+  volatile float t1 = g * t0;
+  volatile float t2 = 1.f + t1;
+  r[0] = 1.f / t2;
+  r[1] = g * r[0];
+  r[2] = g * r[1];
+  volatile float am1 = A - 1.f;
+  r[3] = k * am1;
+  volatile float aa = A * A;
+  r[4] = aa - 1.f;
+}
+extern "C" void mlb_coeffs_hishelf(float omega, float k, float A, float r[6])
+{
+  volatile float piOmega = kPiF * omega;
+  volatile float g = tanf(piOmega) * sqrtf(A);
+  volatile float t0 = g + k;
+  volatile float t1 = g * t0;
+  volatile float t2 = 1.f + t1;
+  r[0] = 1.f / t2;
+  r[1] = g * r[0];
+  r[2] = g * r[1];
+  r[3] = A * A;
+  volatile float oma = 1.f - A;
+  volatile float koma = k * oma;
+  r[4] = koma * A;
+  volatile float aa = A * A;
+  r[5] = 1.f - aa;
+}
+extern "C" void mlb_coeffs_bell(float omega, float k, float A, float r[4])
+{
+  volatile float kc = k / A;
+  volatile float piOmega = kPiF * omega;
+  volatile float g = tanf(piOmega);
+  volatile float t0 = g + kc;
+  volatile float t1 = g * t0;
+  volatile float t2 = 1.f + t1;
+  volatile float a1 = 1.f / t2;
+  volatile float a2 = g * a1;
+  volatile float a3 = g * a2;
+  volatile float aa = A * A;
+  volatile float aam1 = aa - 1.f;
+  r[0] = a1, r[1] = a2, r[2] = a3, r[3] = kc * aam1;
+}
+extern "C" void mlb_coeffs_onepole(float omega, float r[2])
+{
+  volatile float arg = -omega * kTwoPiF;
+  volatile float x = expf(arg);
+  r[0] = 1.f - x;
+  r[1] = x;
+}
+extern "C" float mlb_coeffs_dcblocker(float omega) { return cosf(omega); }
+extern "C" float mlb_db_to_gain(float dB)
+{
+  volatile float e = dB / 40.f;
+  return powf(10.f, e);
+}
+extern "C" void mlb_coeffs_fdn8(const float times[8], const float cutoffs[8], const float gains[8],
+                                float out32[32])
+{
+  for (int n = 0; n < 8; ++n)
+  {
+    float c[2];
+    mlb_coeffs_onepole(cutoffs[n], c);
+    out32[n] = c[0];
+    out32[8 + n] = c[1];
+    out32[16 + n] = gains[n];
+    // FDN::setDelaysInSamples, F:1173-1183: int len = times[n] - 64; len = max(1, len)
+    int len = (int)(times[n] - (float)MLB_BLOCK);
+    out32[24 + n] = (float)std::max(1, len);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// device
+
+static int g_device = -1;
+static int g_sm_count = 0;
+static size_t g_smem_optin = 0;
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+extern "C" int mlb_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" int mlb_init(int device)
+{
+  int n = mlb_device_count();
+  if (n <= 0)
+    return fail(MLB_ERR_NO_DEVICE,
+                "no CUDA device visible: this library has no CPU fallback (sm_100a kernels only)");
+  if (device < 0 || device >= n) return fail(MLB_ERR_INVALID, "device %d out of range (%d)", device, n);
+  CU_CHECK(cudaSetDevice(device));
+  cudaDeviceProp p;
+  CU_CHECK(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10)
+    return fail(MLB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library ships sm_100a code only",
+                device, p.major, p.minor);
+  g_sm_count = p.multiProcessorCount;
+  g_smem_optin = p.sharedMemPerBlockOptin;
+  if (!g_encode)
+  {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn)
+      return fail(MLB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = (EncodeTiledFn)fn;
+  }
+  g_device = device;
+  return MLB_OK;
+}
+
+static int ensure_init()
+{
+  if (g_device >= 0)
+  {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != g_device) cudaSetDevice(g_device);
+    return MLB_OK;
+  }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess)
+  {
+    cudaGetLastError();
+    dev = 0;
+  }
+  return mlb_init(dev);
+}
+
+// tensor map over planes of [V][64] f32: dims {64, V, n_planes}, box {32, 32, 1}, 128B swizzle
+static int make_plane_map(CUtensorMap* map, const float* base, int V, long long n_planes,
+                          long long plane_stride_floats)
+{
+  cuuint64_t dims[3] = {(cuuint64_t)MLB_BLOCK, (cuuint64_t)V, (cuuint64_t)n_planes};
+  cuuint64_t strides[2] = {(cuuint64_t)MLB_BLOCK * 4, (cuuint64_t)plane_stride_floats * 4};
+  cuuint32_t box[3] = {(cuuint32_t)kTileSamples, (cuuint32_t)kTileVoices, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MLB_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
+  return MLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused chain registry
+
+typedef void (*ChainKernelFn)(const CUtensorMap, const CUtensorMap, const ChainArgs);
+struct FusedEntry
+{
+  int gen, src, f1, f2, gain, exact;
+  ChainKernelFn fn;
+  const char* name;
+  bool has_in;
+};
+
+#define N_ (-1)
+// (GEN, SRC, F1, F2, GAIN)
+#define MLB_FUSED_LIST(X)                                                   \
+  X(MLB_OP_SINE, SRC_INPUT, MLB_OP_LOPASS, N_, true)   /* config 1 / A */   \
+  X(MLB_OP_SINE, SRC_PARAM, MLB_OP_LOPASS, N_, true)   /* contract S / M */ \
+  X(MLB_OP_SINE, SRC_INPUT, MLB_OP_LOPASS, N_, false)  /* config 2 */       \
+  X(MLB_OP_SINE, SRC_INPUT, MLB_OP_HIPASS, N_, false)                       \
+  X(MLB_OP_SINE, SRC_INPUT, MLB_OP_BANDPASS, N_, false)                     \
+  X(MLB_OP_SINE, SRC_INPUT, MLB_OP_LOSHELF, N_, false)                      \
+  X(MLB_OP_SINE, SRC_INPUT, MLB_OP_HISHELF, N_, false)                      \
+  X(MLB_OP_SINE, SRC_INPUT, MLB_OP_BELL, N_, false)                         \
+  X(MLB_OP_PHASOR, SRC_INPUT, MLB_OP_LOPASS, MLB_OP_ONEPOLE, false) /* config 3 */ \
+  X(MLB_OP_SINE, SRC_INPUT, N_, N_, false)                                  \
+  X(MLB_OP_PHASOR, SRC_INPUT, N_, N_, false)                                \
+  X(MLB_OP_SAW, SRC_INPUT, N_, N_, false)                                   \
+  X(MLB_OP_NOISE, SRC_NONE, N_, N_, false)                                  \
+  X(MLB_OP_NOISE, SRC_NONE, MLB_OP_LOPASS, N_, true)                        \
+  X(N_, SRC_INPUT, MLB_OP_LOPASS, N_, false)                                \
+  X(N_, SRC_INPUT, MLB_OP_ONEPOLE, N_, false)                               \
+  X(N_, SRC_INPUT, MLB_OP_DCBLOCKER, N_, false)
+
+static const FusedEntry g_fused[] = {
+#define MLB_X_ENTRY(G, S, F1, F2, GN)                                                          \
+  {G, S, F1, F2, GN, 1, chain_kernel<Chain<G, S, F1, F2, GN, true>>, #G "+" #F1 "+" #F2 "+" #GN, \
+   S == SRC_INPUT},                                                                            \
+      {G, S, F1, F2, GN, 0, chain_kernel<Chain<G, S, F1, F2, GN, false>>,                        \
+       #G "+" #F1 "+" #F2 "+" #GN "(fast)", S == SRC_INPUT},
+    MLB_FUSED_LIST(MLB_X_ENTRY)
+#undef MLB_X_ENTRY
+};
+
+// ------------------------------------------------------------------------------------------
+// graph object
+
+enum GraphKind
+{
+  KIND_FUSED = 0,
+  KIND_FDN = 1,
+  KIND_GENERIC = 2
+};
+
+struct mlb_graph
+{
+  std::vector<mlb_node> nodes;
+  std::vector<int32_t> outs;
+  std::vector<int32_t> st_off, co_off;
+  mlb_layout layout{};
+  int V = 0;
+  unsigned flags = 0;
+  bool exact = true;
+  int kind = KIND_GENERIC;
+  std::string kernel_name;
+
+  // device SoA
+  uint32_t* d_state = nullptr;
+  float* d_coef = nullptr;
+  std::vector<float> h_coef;  // host mirror (ring sizing, FDN descriptors)
+
+  // fused chain
+  const FusedEntry* fused = nullptr;
+  ChainArgs cargs{};
+
+  // FM3 -> FDN8 specialisation
+  FdnArgs fargs{};
+
+  // generic interpreter
+  std::vector<GNode> gnodes;
+  GNode* d_gnodes = nullptr;
+  int n_slots = 0;
+
+  // FDN delay memory
+  int fdn_node = -1;
+  float* d_ring = nullptr;
+  float* d_carry = nullptr;
+  int ring_len = 0;
+  long long blocks_done = 0;
+
+  // mix bus partials
+  float* d_partial = nullptr;
+  size_t partial_cap = 0;
+
+  // staging for the host entry point
+  float *d_in = nullptr, *d_out = nullptr, *d_mix = nullptr;
+  size_t in_cap = 0, out_cap = 0, mix_cap = 0;
+  cudaStream_t stream = nullptr;
+
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+};
+
+static bool is_filter(int op)
+{
+  switch (op)
+  {
+    case MLB_OP_LOPASS:
+    case MLB_OP_HIPASS:
+    case MLB_OP_BANDPASS:
+    case MLB_OP_LOSHELF:
+    case MLB_OP_HISHELF:
+    case MLB_OP_BELL:
+    case MLB_OP_ONEPOLE:
+    case MLB_OP_DCBLOCKER:
+    case MLB_OP_DIFFERENTIATOR:
+    case MLB_OP_INTEGRATOR: return true;
+  }
+  return false;
+}
+static bool is_gen1(int op)
+{
+  return op == MLB_OP_SINE || op == MLB_OP_PHASOR || op == MLB_OP_SAW || op == MLB_OP_TICK;
+}
+
+// Recognise  out = [gain *] F2( F1( GEN(src) ) )  and fill g->cargs index maps.
+static bool match_fused_chain(mlb_graph* g)
+{
+  if (g->outs.size() != 1) return false;
+  const auto& N = g->nodes;
+  std::vector<char> used(N.size(), 0);
+  int y = g->outs[0];
+  int gain_node = -1;
+  if (N[y].op == MLB_OP_MULTIPLY)
+  {
+    const int a = N[y].in[0], b = N[y].in[1];
+    used[y] = 1;
+    if (N[b].op == MLB_OP_PARAM && N[a].op != MLB_OP_PARAM)
+      gain_node = b, y = a;
+    else if (N[a].op == MLB_OP_PARAM && N[b].op != MLB_OP_PARAM)
+      gain_node = a, y = b;
+    else
+      return false;
+    used[gain_node] = 1;
+  }
+  int filt[2] = {-1, -1};
+  int nf = 0;
+  while (is_filter(N[y].op))
+  {
+    if (nf == 2) return false;
+    filt[nf++] = y;
+    used[y] = 1;
+    y = N[y].in[0];
+  }
+  // filt[] is output-side first: reverse into signal order
+  int f1 = -1, f2 = -1;
+  if (nf == 1) f1 = filt[0];
+  if (nf == 2) f1 = filt[1], f2 = filt[0];
+  int gen = -1, src = SRC_NONE, src_node = -1, gen_node = -1;
+  if (is_gen1(N[y].op))
+  {
+    gen = N[y].op, gen_node = y;
+    used[y] = 1;
+    src_node = N[y].in[0];
+  }
+  else if (N[y].op == MLB_OP_NOISE)
+  {
+    gen = MLB_OP_NOISE, gen_node = y;
+    used[y] = 1;
+  }
+  else
+    src_node = y;
+  if (src_node >= 0)
+  {
+    used[src_node] = 1;
+    if (N[src_node].op == MLB_OP_INPUT)
+      src = SRC_INPUT;
+    else if (N[src_node].op == MLB_OP_PARAM)
+      src = SRC_PARAM;
+    else
+      return false;
+  }
+  for (char u : used)
+    if (!u) return false;  // every node must be on the chain (unused stateful nodes still tick)
+  const int f1op = f1 >= 0 ? N[f1].op : -1, f2op = f2 >= 0 ? N[f2].op : -1;
+  for (const FusedEntry& e : g_fused)
+  {
+    if (e.gen == gen && e.src == src && e.f1 == f1op && e.f2 == f2op &&
+        e.gain == (gain_node >= 0 ? 1 : 0) && e.exact == (g->exact ? 1 : 0))
+    {
+      g->fused = &e;
+      ChainArgs& c = g->cargs;
+      memset(&c, 0, sizeof(c));
+      int si = 0, ci = 0;
+      auto add_state = [&](int node)
+      {
+        int nst = 0;
+        mlb_op_info(N[node].op, nullptr, &nst, nullptr);
+        for (int k = 0; k < nst; ++k) c.st_idx[si++] = g->st_off[node] + k;
+      };
+      auto add_coef = [&](int node)
+      {
+        int nco = 0;
+        mlb_op_info(N[node].op, nullptr, nullptr, &nco);
+        for (int k = 0; k < nco; ++k) c.co_idx[ci++] = g->co_off[node] + k;
+      };
+      if (gen_node >= 0) add_state(gen_node);
+      if (f1 >= 0) add_state(f1);
+      if (f2 >= 0) add_state(f2);
+      if (src == SRC_PARAM) add_coef(src_node);
+      if (f1 >= 0) add_coef(f1);
+      if (f2 >= 0) add_coef(f2);
+      if (gain_node >= 0) add_coef(gain_node);
+      c.in_plane = (src == SRC_INPUT) ? N[src_node].iarg : 0;
+      g->kernel_name = std::string("fused:") + e.name;
+      return true;
+    }
+  }
+  return false;
+}
+
+// Build the interpreter program: operand kinds, shared-memory slot allocation by liveness.
+static int build_generic(mlb_graph* g)
+{
+  const auto& N = g->nodes;
+  const int n = (int)N.size();
+  std::vector<int> last_use(n, -1);
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < MLB_MAX_INS; ++k)
+      if (N[i].in[k] >= 0) last_use[N[i].in[k]] = i;
+  // FDN8_R keeps its FDN8's second row alive: treat reads of FDN8_R as reads of that slot
+  std::vector<int> slot(n, -1), slot2(n, -1);
+  std::vector<int> free_slots;
+  int n_slots = 0;
+  auto alloc = [&]()
+  {
+    if (!free_slots.empty())
+    {
+      int s = free_slots.back();
+      free_slots.pop_back();
+      return s;
+    }
+    return n_slots++;
+  };
+  g->gnodes.assign(n, GNode{});
+  std::vector<int> out_plane(n, -1);
+  for (size_t c = 0; c < g->outs.size(); ++c)
+  {
+    if (out_plane[g->outs[c]] >= 0)
+      return fail(MLB_ERR_UNSUPPORTED, "a node may appear only once in outs");
+    out_plane[g->outs[c]] = (int)c;
+  }
+  for (int i = 0; i < n; ++i)
+  {
+    GNode& gn = g->gnodes[i];
+    gn.op = N[i].op;
+    gn.st_off = g->st_off[i];
+    gn.co_off = g->co_off[i];
+    gn.iarg = N[i].iarg;
+    gn.out_plane = out_plane[i];
+    gn.out_slot = gn.out_slot2 = -1;
+    for (int k = 0; k < MLB_MAX_INS; ++k)
+    {
+      const int src = N[i].in[k];
+      gn.in_kind[k] = OPERAND_NONE;
+      gn.in_ref[k] = 0;
+      if (src < 0) continue;
+      if (N[src].op == MLB_OP_PARAM)
+      {
+        gn.in_kind[k] = OPERAND_PARAM;
+        gn.in_ref[k] = g->co_off[src];
+      }
+      else
+      {
+        gn.in_kind[k] = OPERAND_SLOT;
+        gn.in_ref[k] = slot[src];
+      }
+    }
+    // allocate the output slot BEFORE freeing inputs: nodes never run in place
+    if (N[i].op == MLB_OP_FDN8_R)
+      slot[i] = slot2[N[i].in[0]];
+    else if (N[i].op != MLB_OP_PARAM)
+      slot[i] = alloc();
+    if (N[i].op == MLB_OP_FDN8) slot2[i] = alloc();
+    gn.out_slot = slot[i];
+    gn.out_slot2 = slot2[i];
+    // release rows whose last reader is this node
+    for (int j = 0; j < i; ++j)
+    {
+      if (slot[j] < 0 || N[j].op == MLB_OP_FDN8_R) continue;
+      if (last_use[j] == i) free_slots.push_back(slot[j]);
+      if (N[j].op == MLB_OP_FDN8)
+      {
+        // second row is read only through FDN8_R nodes; free it when their last reader ran
+        int lu = -1;
+        bool has_r = false;
+        for (int q = j + 1; q < n; ++q)
+          if (N[q].op == MLB_OP_FDN8_R && N[q].in[0] == j)
+          {
+            has_r = true;
+            lu = std::max(lu, std::max(last_use[q], q));
+          }
+        if ((has_r && lu == i) || (!has_r && i == j)) free_slots.push_back(slot2[j]);
+      }
+    }
+    // a row nobody reads can be recycled right after it was written out
+    if (slot[i] >= 0 && last_use[i] < 0 && N[i].op != MLB_OP_FDN8_R) free_slots.push_back(slot[i]);
+  }
+  g->n_slots = std::max(1, n_slots);
+  const size_t smem = (size_t)g->n_slots * kSlotBytes;
+  if (smem > g_smem_optin)
+    return fail(MLB_ERR_UNSUPPORTED, "graph needs %d live rows (%zu B shared memory > %zu)",
+                g->n_slots, smem, g_smem_optin);
+  g->kernel_name = g->exact ? "generic" : "generic(fast)";
+  return MLB_OK;
+}
+
+extern "C" int mlb_graph_create(const mlb_node* nodes, int n_nodes, const int32_t* outs, int n_out,
+                                int n_voices, unsigned flags, mlb_graph** out_graph)
+{
+  if (!out_graph) return fail(MLB_ERR_INVALID, "out_graph is null");
+  *out_graph = nullptr;
+  if (n_voices <= 0) return fail(MLB_ERR_INVALID, "n_voices must be positive");
+  if (n_out < 0 || (n_out > 0 && !outs)) return fail(MLB_ERR_INVALID, "bad outs");
+  mlb_layout lay;
+  std::vector<int32_t> so(std::max(1, n_nodes)), co(std::max(1, n_nodes));
+  int rc = mlb_graph_layout(nodes, n_nodes, &lay, so.data(), co.data());
+  if (rc != MLB_OK) return rc;
+  for (int c = 0; c < n_out; ++c)
+    if (outs[c] < 0 || outs[c] >= n_nodes) return fail(MLB_ERR_INVALID, "outs[%d] out of range", c);
+  rc = ensure_init();
+  if (rc != MLB_OK) return rc;
+
+  mlb_graph* g = new mlb_graph;
+  g->nodes.assign(nodes, nodes + n_nodes);
+  g->outs.assign(outs, outs + n_out);
+  g->st_off = so;
+  g->co_off = co;
+  g->layout = lay;
+  g->V = n_voices;
+  g->flags = flags;
+  g->exact = !(flags & MLB_GRAPH_FAST);
+  for (int i = 0; i < n_nodes; ++i)
+    if (nodes[i].op == MLB_OP_FDN8) g->fdn_node = i;
+
+  auto cleanup = [&](int code)
+  {
+    mlb_graph_destroy(g);
+    return code;
+  };
+  const size_t V = (size_t)n_voices;
+  if (cudaMalloc(&g->d_state, std::max<size_t>(1, lay.n_state_words) * V * 4) != cudaSuccess ||
+      cudaMalloc(&g->d_coef, std::max<size_t>(1, lay.n_coef_words) * V * 4) != cudaSuccess)
+    return cleanup(fail(MLB_ERR_ALLOC, "cudaMalloc of voice state failed: %s",
+                        cudaGetErrorString(cudaGetLastError())));
+  cudaMemset(g->d_state, 0, std::max<size_t>(1, lay.n_state_words) * V * 4);
+  cudaMemset(g->d_coef, 0, std::max<size_t>(1, lay.n_coef_words) * V * 4);
+  g->h_coef.assign((size_t)lay.n_coef_words * V, 0.f);
+  cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
+  cudaEventCreate(&g->ev0);
+  cudaEventCreate(&g->ev1);
+
+  bool matched = false;
+  if (!(flags & MLB_GRAPH_FORCE_GENERIC))
+  {
+    matched = match_fused_chain(g);
+    if (matched) g->kind = KIND_FUSED;
+    if (!matched && match_fm3_fdn8(g->nodes, g->outs, g->st_off, g->co_off, &g->fargs))
+    {
+      matched = true;
+      g->kind = KIND_FDN;
+      g->kernel_name = g->exact ? "fused:fm3_fdn8" : "fused:fm3_fdn8(fast)";
+    }
+  }
+  if (!matched)
+  {
+    g->kind = KIND_GENERIC;
+    rc = build_generic(g);
+    if (rc != MLB_OK) return cleanup(rc);
+    if (cudaMalloc(&g->d_gnodes, sizeof(GNode) * g->gnodes.size()) != cudaSuccess)
+      return cleanup(fail(MLB_ERR_ALLOC, "cudaMalloc of graph program failed"));
+    cudaMemcpy(g->d_gnodes, g->gnodes.data(), sizeof(GNode) * g->gnodes.size(),
+               cudaMemcpyHostToDevice);
+  }
+  *out_graph = g;
+  return MLB_OK;
+}
+
+extern "C" int mlb_graph_destroy(mlb_graph* g)
+{
+  if (!g) return MLB_OK;
+  cudaFree(g->d_state);
+  cudaFree(g->d_coef);
+  cudaFree(g->d_gnodes);
+  cudaFree(g->d_ring);
+  cudaFree(g->d_carry);
+  cudaFree(g->d_partial);
+  cudaFree(g->d_in);
+  cudaFree(g->d_out);
+  cudaFree(g->d_mix);
+  if (g->ev0) cudaEventDestroy(g->ev0);
+  if (g->ev1) cudaEventDestroy(g->ev1);
+  if (g->stream) cudaStreamDestroy(g->stream);
+  delete g;
+  return MLB_OK;
+}
+
+extern "C" int mlb_graph_layout_of(const mlb_graph* g, mlb_layout* layout)
+{
+  if (!g || !layout) return fail(MLB_ERR_INVALID, "null");
+  *layout = g->layout;
+  return MLB_OK;
+}
+extern "C" const char* mlb_graph_kernel_name(const mlb_graph* g) { return g ? g->kernel_name.c_str() : ""; }
+
+// (re)allocate FDN delay memory when the coefficient upload changes the longest delay
+static int size_delay_memory(mlb_graph* g)
+{
+  if (g->fdn_node < 0) return MLB_OK;
+  const size_t V = (size_t)g->V;
+  const int base = g->co_off[g->fdn_node] + 24;
+  int max_len = 1;
+  for (int l = 0; l < 8; ++l)
+    for (size_t v = 0; v < V; ++v)
+    {
+      const float f = g->h_coef[(size_t)(base + l) * V + v];
+      if (!(f >= 1.0f) || f > 16777216.0f || f != std::floor(f))
+        return fail(MLB_ERR_INVALID, "FDN8 delay length coef must be an integer >= 1 (voice %zu line %d: %g)",
+                    v, l, (double)f);
+      max_len = std::max(max_len, (int)f);
+    }
+  // IntegerDelay::setMaxDelayInSamples, F:822-830: size = 1 << bitsToContain(dMax + 64)
+  int ring = 1;
+  while (ring < max_len + MLB_BLOCK) ring <<= 1;
+  if (ring != g->ring_len)
+  {
+    cudaFree(g->d_ring);
+    cudaFree(g->d_carry);
+    g->d_ring = g->d_carry = nullptr;
+    const size_t ring_bytes = V * 8 * (size_t)ring * 4, carry_bytes = V * 8 * MLB_BLOCK * 4;
+    if (cudaMalloc(&g->d_ring, ring_bytes) != cudaSuccess || cudaMalloc(&g->d_carry, carry_bytes) != cudaSuccess)
+      return fail(MLB_ERR_ALLOC, "cudaMalloc of %zu B delay memory failed", ring_bytes + carry_bytes);
+    g->ring_len = ring;
+    return mlb_graph_clear_delays(g);
+  }
+  return MLB_OK;
+}
+
+extern "C" int mlb_graph_set_coefs(mlb_graph* g, const float* coef_host)
+{
+  if (!g) return fail(MLB_ERR_INVALID, "null graph");
+  if (g->layout.n_coef_words == 0) return MLB_OK;
+  if (!coef_host) return fail(MLB_ERR_INVALID, "null coefs");
+  const size_t bytes = (size_t)g->layout.n_coef_words * g->V * 4;
+  memcpy(g->h_coef.data(), coef_host, bytes);
+  int rc = size_delay_memory(g);
+  if (rc != MLB_OK) return rc;
+  CU_CHECK(cudaMemcpy(g->d_coef, coef_host, bytes, cudaMemcpyHostToDevice));
+  return MLB_OK;
+}
+extern "C" int mlb_graph_set_state(mlb_graph* g, const uint32_t* state_host)
+{
+  if (!g) return fail(MLB_ERR_INVALID, "null graph");
+  if (g->layout.n_state_words == 0) return MLB_OK;
+  if (!state_host) return fail(MLB_ERR_INVALID, "null state");
+  CU_CHECK(cudaMemcpy(g->d_state, state_host, (size_t)g->layout.n_state_words * g->V * 4,
+                      cudaMemcpyHostToDevice));
+  return MLB_OK;
+}
+extern "C" int mlb_graph_get_state(mlb_graph* g, uint32_t* state_host)
+{
+  if (!g) return fail(MLB_ERR_INVALID, "null graph");
+  if (g->layout.n_state_words == 0) return MLB_OK;
+  if (!state_host) return fail(MLB_ERR_INVALID, "null state");
+  CU_CHECK(cudaDeviceSynchronize());
+  CU_CHECK(cudaMemcpy(state_host, g->d_state, (size_t)g->layout.n_state_words * g->V * 4,
+                      cudaMemcpyDeviceToHost));
+  return MLB_OK;
+}
+extern "C" int mlb_graph_clear_delays(mlb_graph* g)
+{
+  if (!g) return fail(MLB_ERR_INVALID, "null graph");
+  g->blocks_done = 0;
+  if (g->d_ring)
+  {
+    CU_CHECK(cudaMemset(g->d_ring, 0, (size_t)g->V * 8 * g->ring_len * 4));
+    CU_CHECK(cudaMemset(g->d_carry, 0, (size_t)g->V * 8 * MLB_BLOCK * 4));
+  }
+  return MLB_OK;
+}
+extern "C" size_t mlb_graph_delay_bytes(const mlb_graph* g)
+{
+  if (!g || !g->d_ring) return 0;
+  return (size_t)g->V * 8 * ((size_t)g->ring_len + MLB_BLOCK) * 4;
+}
+
+static int env_int(const char* name, int dflt)
+{
+  const char* s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+static int ensure_partial(mlb_graph* g, int T, int n_groups)
+{
+  const size_t need = (size_t)T * std::max<size_t>(1, g->outs.size()) * n_groups * MLB_BLOCK * 4;
+  if (need > g->partial_cap)
+  {
+    cudaFree(g->d_partial);
+    g->d_partial = nullptr;
+    g->partial_cap = 0;
+    if (cudaMalloc(&g->d_partial, need) != cudaSuccess)
+      return fail(MLB_ERR_ALLOC, "cudaMalloc of %zu B mix partials failed", need);
+    g->partial_cap = need;
+  }
+  return MLB_OK;
+}
+
+extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float* out_dev,
+                                        float* mix_dev, int n_blocks, void* stream_v)
+{
+  if (!g) return fail(MLB_ERR_INVALID, "null graph");
+  if (n_blocks <= 0) return fail(MLB_ERR_INVALID, "n_blocks must be positive");
+  if (g->layout.n_inputs > 0 && !in_dev) return fail(MLB_ERR_INVALID, "graph has INPUT nodes but in is null");
+  if (g->outs.empty() && (out_dev || mix_dev)) return fail(MLB_ERR_INVALID, "graph has no outputs");
+  if (g->fdn_node >= 0 && !g->d_ring)
+    return fail(MLB_ERR_INVALID, "FDN8 graph: call mlb_graph_set_coefs before processing");
+  int rc = ensure_init();
+  if (rc != MLB_OK) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  const int V = g->V, T = n_blocks;
+  const int n_groups = (V + 31) / 32;
+  const int n_out = (int)g->outs.size(), n_in = g->layout.n_inputs;
+  if (mix_dev)
+  {
+    rc = ensure_partial(g, T, n_groups);
+    if (rc != MLB_OK) return rc;
+  }
+
+  cudaEventRecord(g->ev0, stream);
+  if (g->kind == KIND_FUSED)
+  {
+    const FusedEntry& e = *g->fused;
+    ChainArgs a = g->cargs;
+    a.state = g->d_state;
+    a.coef = g->d_coef;
+    a.mix_partial = mix_dev ? g->d_partial : nullptr;
+    a.V = V;
+    a.T = T;
+    a.n_in_planes = std::max(1, n_in);
+    a.n_out_planes = 1;
+    a.out_plane = 0;
+    a.n_groups = n_groups;
+    a.write_out = out_dev ? 1 : 0;
+    // launch shape: W warps per CTA, S tile stages per warp (DESIGN.md "occupancy")
+    int W = env_int("MLB_CHAIN_WARPS", 1);
+    W = std::min(std::max(W, 1), 4);
+    const int n_ctas = (n_groups + W - 1) / W;
+    const int ctas_per_sm = (n_ctas + g_sm_count - 1) / g_sm_count;
+    int S;
+    if (!e.has_in)
+      S = 2;
+    else
+    {
+      const size_t budget = (size_t)227 * 1024 / std::max(1, ctas_per_sm);
+      const size_t fixed = 1024 /*reserved*/ + 1024 /*align*/ + 64 * (size_t)W;
+      S = budget > fixed ? (int)((budget - fixed) / ((size_t)W * kTileBytes)) : 3;
+      S = std::min(std::max(S, 3), 8);
+      S = env_int("MLB_CHAIN_STAGES", S);
+      S = std::min(std::max(S, 2), 16);
+    }
+    a.stages = S;
+    const size_t smem = (size_t)W * S * kTileBytes + 1024 + (size_t)W * S * 8;
+    if (smem > g_smem_optin) return fail(MLB_ERR_INVALID, "chain launch needs %zu B shared memory", smem);
+    CUtensorMap in_map, out_map;
+    memset(&in_map, 0, sizeof(in_map));
+    memset(&out_map, 0, sizeof(out_map));
+    if (e.has_in)
+    {
+      rc = make_plane_map(&in_map, in_dev, V, (long long)T * a.n_in_planes, (long long)V * MLB_BLOCK);
+      if (rc != MLB_OK) return rc;
+    }
+    if (out_dev)
+    {
+      rc = make_plane_map(&out_map, out_dev, V, (long long)T, (long long)V * MLB_BLOCK);
+      if (rc != MLB_OK) return rc;
+    }
+    CU_CHECK(cudaFuncSetAttribute((const void*)e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    e.fn<<<n_ctas, W * 32, smem, stream>>>(in_map, out_map, a);
+    ++g_launches;
+  }
+  else if (g->kind == KIND_FDN)
+  {
+    rc = launch_fm3_fdn8(g->fargs, g->exact, g->d_state, g->d_coef, g->d_ring, g->d_carry,
+                         g->ring_len, g->blocks_done, in_dev, out_dev,
+                         mix_dev ? g->d_partial : nullptr, V, T, n_groups, g_sm_count, stream);
+    if (rc != MLB_OK) return fail(rc, "fm3_fdn8 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ++g_launches;
+  }
+  else
+  {
+    GenericArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nodes = g->d_gnodes;
+    a.n_nodes = (int)g->gnodes.size();
+    a.state = g->d_state;
+    a.coef = g->d_coef;
+    a.in = in_dev;
+    a.out = out_dev;
+    a.mix_partial = mix_dev ? g->d_partial : nullptr;
+    a.V = V, a.T = T, a.n_in = std::max(1, n_in), a.n_out = std::max(1, n_out);
+    a.n_groups = n_groups, a.n_slots = g->n_slots;
+    a.fdn_ring = g->d_ring, a.fdn_carry = g->d_carry, a.fdn_ring_len = g->ring_len;
+    a.blocks_done = g->blocks_done;
+    const size_t smem = (size_t)g->n_slots * kSlotBytes;
+    if (g->exact)
+    {
+      CU_CHECK(cudaFuncSetAttribute((const void*)generic_graph_kernel<true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      generic_graph_kernel<true><<<n_groups, 32, smem, stream>>>(a);
+    }
+    else
+    {
+      CU_CHECK(cudaFuncSetAttribute((const void*)generic_graph_kernel<false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      generic_graph_kernel<false><<<n_groups, 32, smem, stream>>>(a);
+    }
+    ++g_launches;
+  }
+  cudaEventRecord(g->ev1, stream);
+  g->timed = true;
+  CU_CHECK(cudaGetLastError());
+  if (g->fdn_node >= 0) g->blocks_done += T;
+  if (mix_dev)
+  {
+    mix_reduce_kernel<<<T * std::max(1, n_out), MLB_BLOCK, 0, stream>>>(g->d_partial, mix_dev, n_groups);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+  }
+  return MLB_OK;
+}
+
+static int ensure_buf(float** p, size_t* cap, size_t bytes)
+{
+  if (bytes <= *cap) return MLB_OK;
+  cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  if (cudaMalloc(p, bytes) != cudaSuccess) return fail(MLB_ERR_ALLOC, "cudaMalloc of %zu B staging failed", bytes);
+  *cap = bytes;
+  return MLB_OK;
+}
+
+extern "C" int mlb_graph_process_host(mlb_graph* g, const float* in_host, float* out_host,
+                                      float* mix_host, int n_blocks)
+{
+  if (!g) return fail(MLB_ERR_INVALID, "null graph");
+  if (n_blocks <= 0) return fail(MLB_ERR_INVALID, "n_blocks must be positive");
+  int rc = ensure_init();
+  if (rc != MLB_OK) return rc;
+  const size_t V = (size_t)g->V, T = (size_t)n_blocks;
+  const size_t n_in = (size_t)g->layout.n_inputs, n_out = g->outs.size();
+  const size_t in_bytes = T * n_in * V * MLB_BLOCK * 4, out_bytes = T * n_out * V * MLB_BLOCK * 4;
+  const size_t mix_bytes = T * n_out * MLB_BLOCK * 4;
+  if (n_in && !in_host) return fail(MLB_ERR_INVALID, "graph has INPUT nodes but in is null");
+  if (n_in && (rc = ensure_buf(&g->d_in, &g->in_cap, in_bytes)) != MLB_OK) return rc;
+  if (out_host && (rc = ensure_buf(&g->d_out, &g->out_cap, out_bytes)) != MLB_OK) return rc;
+  if (mix_host && (rc = ensure_buf(&g->d_mix, &g->mix_cap, mix_bytes)) != MLB_OK) return rc;
+  cudaStream_t s = g->stream;
+  if (n_in) CU_CHECK(cudaMemcpyAsync(g->d_in, in_host, in_bytes, cudaMemcpyHostToDevice, s));
+  rc = mlb_graph_process_device(g, n_in ? g->d_in : nullptr, out_host ? g->d_out : nullptr,
+                                mix_host ? g->d_mix : nullptr, n_blocks, s);
+  if (rc != MLB_OK) return rc;
+  if (out_host) CU_CHECK(cudaMemcpyAsync(out_host, g->d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+  if (mix_host) CU_CHECK(cudaMemcpyAsync(mix_host, g->d_mix, mix_bytes, cudaMemcpyDeviceToHost, s));
+  CU_CHECK(cudaStreamSynchronize(s));
+  return MLB_OK;
+}
+
+extern "C" int mlb_graph_last_kernel_ms(mlb_graph* g, float* ms)
+{
+  if (!g || !ms) return fail(MLB_ERR_INVALID, "null");
+  if (!g->timed) return fail(MLB_ERR_INVALID, "no launch recorded yet");
+  CU_CHECK(cudaEventSynchronize(g->ev1));
+  CU_CHECK(cudaEventElapsedTime(ms, g->ev0, g->ev1));
+  return MLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// stateless elementwise ops
+
+extern "C" int mlb_map_device(int op, const float* x1, const float* x2, const float* x3, float* y,
+                              size_t n_rows, void* stream)
+{
+  int nin, nst, nco;
+  if (mlb_op_info(op, &nin, &nst, &nco) != MLB_OK || nst != 0 || nco != 0 || nin < 1 ||
+      op == MLB_OP_FDN8_R)
+    return fail(MLB_ERR_INVALID, "op %d is not a stateless elementwise op", op);
+  if (!x1 || !y || (nin >= 2 && !x2) || (nin >= 3 && !x3)) return fail(MLB_ERR_INVALID, "null operand");
+  if (n_rows == 0) return MLB_OK;
+  int rc = ensure_init();
+  if (rc != MLB_OK) return rc;
+  const size_t n4 = n_rows * (MLB_BLOCK / 4);
+  const int threads = 256;
+  const size_t want = (n4 + threads - 1) / threads;
+  const int blocks = (int)std::min<size_t>(want, (size_t)g_sm_count * 16);
+  map_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(
+      op, (const float4*)x1, nin >= 2 ? (const float4*)x2 : nullptr,
+      nin >= 3 ? (const float4*)x3 : nullptr, (float4*)y, n4);
+  ++g_launches;
+  CU_CHECK(cudaGetLastError());
+  return MLB_OK;
+}
+
+extern "C" int mlb_map_host(int op, const float* x1, const float* x2, const float* x3, float* y,
+                            size_t n_rows)
+{
+  int nin, nst, nco;
+  if (mlb_op_info(op, &nin, &nst, &nco) != MLB_OK) return fail(MLB_ERR_INVALID, "unknown op %d", op);
+  if (n_rows == 0) return MLB_OK;
+  int rc = ensure_init();
+  if (rc != MLB_OK) return rc;
+  const size_t bytes = n_rows * MLB_BLOCK * 4;
+  float* d[4] = {nullptr, nullptr, nullptr, nullptr};
+  const float* h[3] = {x1, x2, x3};
+  auto freeall = [&]()
+  {
+    for (float* p : d) cudaFree(p);
+  };
+  for (int k = 0; k < 4; ++k)
+  {
+    if (k < 3 && (k >= nin || !h[k])) continue;
+    if (cudaMalloc(&d[k], bytes) != cudaSuccess)
+    {
+      freeall();
+      return fail(MLB_ERR_ALLOC, "cudaMalloc of %zu B failed", bytes);
+    }
+    if (k < 3) cudaMemcpy(d[k], h[k], bytes, cudaMemcpyHostToDevice);
+  }
+  rc = mlb_map_device(op, d[0], d[1], d[2], d[3], n_rows, nullptr);
+  if (rc == MLB_OK)
+  {
+    cudaError_t e = cudaMemcpy(y, d[3], bytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(MLB_ERR_CUDA, "map copy-out failed: %s", cudaGetErrorString(e));
+  }
+  freeall();
+  return rc;
+}

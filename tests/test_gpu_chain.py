@@ -1,0 +1,176 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracles."""
+import numpy as np
+import pytest
+
+from madronalib_b200 import workloads as wl
+from madronalib_b200.graph import GraphSpec, OP_ID
+from tests.common import assert_same_bits, assert_state_equal, run_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config1_pinned_values(gpu):
+    """SURVEY 8c spot values of the reference: 0.5*Lopass{0.1,1.0}(SineGen.clear()(440/48000))."""
+    w = wl.config_1()
+    out, _, _, name = run_gpu(gpu, w, 1, w.inputs(1))
+    assert name.startswith("fused:")
+    y = out[0, 0, 0]
+    assert float(y[0]).hex() == "-0x1.09e6400000000p-9"
+    assert float(y[1]).hex() == "-0x1.5cd8fa0000000p-7"
+    assert float(y[63]).hex() == "0x1.b253900000000p-3"
+
+
+def test_sinegen_one_cycle_ends_at_zero(gpu):
+    """Reference Tests/dspGensTest.cpp:22-31: |SineGen(1/64)[63]| < dBToAmp(-120)."""
+    g = GraphSpec()
+    g.output(g.node("SINE", g.input(0)))
+    w = wl.Workload("sine", g, 1, g.new_coefs(1), g.new_state(1))
+    w.state[0] = wl.SINE_ZERO_PHASE
+    inp = np.full((1, 1, 1, 64), 1.0 / 64, np.float32)
+    out, _, _, _ = run_gpu(gpu, w, 1, inp)
+    assert abs(out[0, 0, 0, 63]) < 10.0 ** (-120 / 20.0)
+    assert float(out[0, 0, 0, 63]).hex() == "-0x1.0f876c0000000p-22"
+
+
+@pytest.mark.parametrize("n_voices,n_blocks", [(1, 3), (31, 2), (32, 4), (200, 5), (1000, 3)])
+def test_config_a_bit_exact(gpu, port, n_voices, n_blocks):
+    w = wl.config_a(n_voices)
+    inp = w.inputs(n_blocks)
+    inp[0, 0, 0, :4] = [0.6, 0.5, -0.3, np.nan] if n_voices >= 1 else 0  # cvtps2dq overflow canaries
+    po, _, ps = port.run(w.spec, n_voices, n_blocks, inp, w.state, w.coef)
+    go, _, gs, name = run_gpu(gpu, w, n_blocks, inp)
+    assert name.startswith("fused:"), name
+    assert_same_bits(go, po, "config A out")
+    assert_state_equal(gs, ps, "config A state")
+
+
+def test_config_a_against_reference_itself(gpu, ref):
+    w = wl.config_a(96)
+    inp = w.inputs(6)
+    ro, _, rs = ref.run(w.spec, 96, 6, inp, w.state, w.coef)
+    go, _, gs, _ = run_gpu(gpu, w, 6, inp)
+    assert_same_bits(go, ro, "config A vs reference")
+    assert_state_equal(gs, rs)
+
+
+def test_launch_boundary_continuity(gpu, port):
+    """State carried across launches: 2+1+4 blocks == 7 blocks."""
+    w = wl.config_a(100)
+    inp = w.inputs(7)
+    po, _, ps = port.run(w.spec, 100, 7, inp, w.state, w.coef)
+    go, _, gs, _ = run_gpu(gpu, w, 7, inp, splits=(2, 1, 4))
+    assert_same_bits(go, po)
+    assert_state_equal(gs, ps)
+
+
+@pytest.mark.parametrize("kind", ["lopass", "hipass", "bandpass", "loshelf", "hishelf", "bell"])
+def test_config2_svf_family(gpu, port, kind):
+    w = wl.config_2(kind, 160)
+    inp = w.inputs(4)
+    po, _, ps = port.run(w.spec, 160, 4, inp, w.state, w.coef)
+    go, _, gs, name = run_gpu(gpu, w, 4, inp)
+    assert name.startswith("fused:"), name
+    assert_same_bits(go, po, kind)
+    assert_state_equal(gs, ps, kind)
+
+
+def test_config3_phasor_lopass_onepole(gpu, port):
+    w = wl.config_3(300)
+    inp = w.inputs(5)
+    po, _, ps = port.run(w.spec, 300, 5, inp, w.state, w.coef)
+    go, _, gs, name = run_gpu(gpu, w, 5, inp)
+    assert name.startswith("fused:"), name
+    assert_same_bits(go, po)
+    assert_state_equal(gs, ps)
+
+
+def test_generic_kernel_equals_fused(gpu, port):
+    w = wl.config_a(70)
+    inp = w.inputs(3)
+    fo, _, fs, fname = run_gpu(gpu, w, 3, inp)
+    go, _, gs, gname = run_gpu(gpu, w, 3, inp, flags=gpu.FLAG_FORCE_GENERIC)
+    assert fname.startswith("fused:") and gname == "generic"
+    assert_same_bits(go, fo)
+    assert_state_equal(gs, fs)
+
+
+def test_mix_bus(gpu, port):
+    """Mix bus = sum over voices.  Bit-exact against the port in the device summation order
+    (32-voice groups left to right, groups left to right); within (V-1)*eps*sum|x_v| of the
+    reference's strict left-to-right order (SURVEY hard part 8)."""
+    V, T = 200, 3
+    w = wl.config_a(V)
+    inp = w.inputs(T)
+    po, pm1, _ = port.run(w.spec, V, T, inp, w.state, w.coef, want_mix=True, mix_mode=1)
+    _, pm0, _ = port.run(w.spec, V, T, inp, w.state, w.coef, want_mix=True, mix_mode=0)
+    for flags in (0, gpu.FLAG_FORCE_GENERIC):
+        go, gm, _, _ = run_gpu(gpu, w, T, inp, flags=flags, want_mix=True)
+        assert_same_bits(go, po)
+        assert_same_bits(gm, pm1, "mix (device order)")
+        tol = V * np.finfo(np.float32).eps * np.abs(po).sum(axis=2).max()  # (n-1) eps sum|x_i|
+        assert np.abs(gm - pm0).max() <= tol
+
+
+def test_noise_chain_no_input(gpu, port):
+    g = GraphSpec()
+    n = g.node("NOISE")
+    lp = g.node("LOPASS", n)
+    k = g.param()
+    g.output(g.node("MULTIPLY", lp, k))
+    V, T = 77, 4
+    coef = g.new_coefs(V)
+    coef[0:3] = gpu.coeffs("lopass", 0.05, 0.7)[:, None]
+    coef[3] = 0.25
+    st = g.new_state(V)
+    st[0] = np.arange(V)
+    w = wl.Workload("noise", g, V, coef, st)
+    po, _, ps = port.run(g, V, T, None, st, coef)
+    go, _, gs, name = run_gpu(gpu, w, T, None)
+    assert name.startswith("fused:"), name
+    assert_same_bits(go, po)
+    assert_state_equal(gs, ps)
+
+
+def test_contract_s_scalar_param_input(gpu, port):
+    """DSPVector(float) broadcast of a per-voice frequency (examples/audio-and-midi/sine.cpp:33)."""
+    g = GraphSpec()
+    f = g.param()
+    s = g.node("SINE", f)
+    lp = g.node("LOPASS", s)
+    k = g.param()
+    g.output(g.node("MULTIPLY", lp, k))
+    V, T = 130, 4
+    coef = g.new_coefs(V)
+    coef[0] = wl.base_freq(V)
+    coef[1:4] = gpu.coeffs("lopass", 0.1, 0.5)[:, None]
+    coef[4] = 0.1
+    st = g.new_state(V)
+    st[0] = wl.SINE_ZERO_PHASE
+    w = wl.Workload("contract_s", g, V, coef, st)
+    po, pm, ps = port.run(g, V, T, None, st, coef, want_mix=True, mix_mode=1)
+    go, gm, gs, name = run_gpu(gpu, w, T, None, want_mix=True)
+    assert name.startswith("fused:"), name
+    assert_same_bits(go, po)
+    assert_same_bits(gm, pm)
+    assert_state_equal(gs, ps)
+
+
+def test_config4_fm3_fdn8(gpu, port):
+    V, T = 48, 14
+    w = wl.config_4(V)
+    inp = w.inputs(T)
+    po, pm, ps = port.run(w.spec, V, T, inp, w.state, w.coef, want_mix=True, mix_mode=1)
+    go, gm, gs, name = run_gpu(gpu, w, T, inp, want_mix=True, splits=(5, 9))
+    assert_same_bits(go, po, "fm3_fdn8 " + name)
+    assert_same_bits(gm, pm)
+    assert_state_equal(gs, ps)
+    assert np.abs(go).max() > 0.1  # the reverb tail is really there
+
+
+def test_config5_chain256(gpu, port):
+    V, T = 40, 3
+    w = wl.config_5(V, 256)
+    po, _, ps = port.run(w.spec, V, T, None, w.state, w.coef)
+    go, _, gs, name = run_gpu(gpu, w, T, None)
+    assert_same_bits(go, po, "chain256 " + name)
+    assert_state_equal(gs, ps)
