@@ -1,0 +1,251 @@
+// mlb200.hpp -- C++17 host mirror of the reference's value/functor API over the C ABI (mlb200.h).
+//
+// Same spellings and value semantics as the reference where the host keeps data
+// (reference: source/DSP/MLDSPOps.h:94-353 DSPVectorArray<ROWS>, :361 DSPVector,
+// :523-533 load/store, :157 implicit float -> vector, :337-352 operator+ - * /), plus
+// `mlb::DeviceBank`, the batched analogue of `Bank<T, ROWS>` (source/DSP/MLDSPFunctional.h:321-360)
+// whose ROWS is chosen at run time and whose operator() runs on the GPU.
+//
+// Header only; link against libmlb200.so.  Elementwise operators on host DSPVectorArrays
+// are computed on the GPU through mlb_map_host (there is no CPU arithmetic path in this
+// project); use DeviceBank / graphs for anything performance relevant.
+#pragma once
+#include <array>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "mlb200.h"
+
+constexpr size_t kFloatsPerDSPVectorBits = 6;  // reference MLDSPMath.h:8
+constexpr size_t kFloatsPerDSPVector = 1 << kFloatsPerDSPVectorBits;
+static_assert(kFloatsPerDSPVector == MLB_BLOCK, "block size");
+
+namespace mlb
+{
+struct Error : std::runtime_error
+{
+  int code;
+  Error(int c, const char* m) : std::runtime_error(m), code(c) {}
+};
+inline void check(int rc)
+{
+  if (rc != MLB_OK) throw Error(rc, mlb_last_error());
+}
+
+// ---- DSPVectorArray<ROWS>: ROWS x 64 f32, row-major, 16-byte aligned, value semantics ----
+template <size_t ROWS>
+class DSPVectorArray
+{
+  alignas(16) float data_[kFloatsPerDSPVector * ROWS];
+
+ public:
+  DSPVectorArray() { std::memset(data_, 0, sizeof(data_)); }  // zero fill, MLDSPOps.h:153
+  DSPVectorArray(float k) { operator=(k); }                   // broadcast, MLDSPOps.h:157
+  explicit DSPVectorArray(const float* p) { std::memcpy(data_, p, sizeof(data_)); }
+  DSPVectorArray& operator=(float k)
+  {
+    for (float& f : data_) f = k;
+    return *this;
+  }
+  float* getBuffer() { return data_; }
+  const float* getConstBuffer() const { return data_; }
+  float& operator[](size_t i) { return data_[i]; }
+  float operator[](size_t i) const { return data_[i]; }
+  DSPVectorArray<1>& row(int j) { return *reinterpret_cast<DSPVectorArray<1>*>(data_ + kFloatsPerDSPVector * j); }
+  const DSPVectorArray<1>& constRow(int j) const
+  {
+    return *reinterpret_cast<const DSPVectorArray<1>*>(data_ + kFloatsPerDSPVector * j);
+  }
+  bool operator==(const DSPVectorArray& o) const
+  {
+    for (size_t i = 0; i < kFloatsPerDSPVector * ROWS; ++i)
+      if (data_[i] != o.data_[i]) return false;
+    return true;
+  }
+
+  friend DSPVectorArray map2(int op, const DSPVectorArray& a, const DSPVectorArray& b)
+  {
+    DSPVectorArray y;
+    check(mlb_map_host(op, a.data_, b.data_, nullptr, y.data_, ROWS));
+    return y;
+  }
+  friend DSPVectorArray operator+(const DSPVectorArray& a, const DSPVectorArray& b) { return map2(MLB_OP_ADD, a, b); }
+  friend DSPVectorArray operator-(const DSPVectorArray& a, const DSPVectorArray& b) { return map2(MLB_OP_SUBTRACT, a, b); }
+  friend DSPVectorArray operator*(const DSPVectorArray& a, const DSPVectorArray& b) { return map2(MLB_OP_MULTIPLY, a, b); }
+  friend DSPVectorArray operator/(const DSPVectorArray& a, const DSPVectorArray& b) { return map2(MLB_OP_DIVIDE, a, b); }
+};
+using DSPVector = DSPVectorArray<1>;
+
+template <size_t ROWS>
+inline void load(DSPVectorArray<ROWS>& dst, const float* src) { std::memcpy(dst.getBuffer(), src, sizeof(float) * kFloatsPerDSPVector * ROWS); }
+template <size_t ROWS>
+inline void store(const DSPVectorArray<ROWS>& src, float* dst) { std::memcpy(dst, src.getConstBuffer(), sizeof(float) * kFloatsPerDSPVector * ROWS); }
+
+#define MLB_DEFINE_OP1(NAME, OP)                                            \
+  template <size_t ROWS>                                                    \
+  inline DSPVectorArray<ROWS> NAME(const DSPVectorArray<ROWS>& x)           \
+  {                                                                         \
+    DSPVectorArray<ROWS> y;                                                 \
+    check(mlb_map_host(OP, x.getConstBuffer(), nullptr, nullptr, y.getBuffer(), ROWS)); \
+    return y;                                                               \
+  }
+MLB_DEFINE_OP1(sqrt, MLB_OP_SQRT)
+MLB_DEFINE_OP1(abs, MLB_OP_ABS)
+MLB_DEFINE_OP1(sign, MLB_OP_SIGN)
+MLB_DEFINE_OP1(signBit, MLB_OP_SIGNBIT)
+MLB_DEFINE_OP1(sin, MLB_OP_SIN)
+MLB_DEFINE_OP1(cos, MLB_OP_COS)
+MLB_DEFINE_OP1(log, MLB_OP_LOG)
+MLB_DEFINE_OP1(exp, MLB_OP_EXP)
+MLB_DEFINE_OP1(log2, MLB_OP_LOG2)
+MLB_DEFINE_OP1(exp2, MLB_OP_EXP2)
+MLB_DEFINE_OP1(sinApprox, MLB_OP_SIN_APPROX)
+MLB_DEFINE_OP1(cosApprox, MLB_OP_COS_APPROX)
+MLB_DEFINE_OP1(expApprox, MLB_OP_EXP_APPROX)
+MLB_DEFINE_OP1(logApprox, MLB_OP_LOG_APPROX)
+MLB_DEFINE_OP1(fractionalPart, MLB_OP_FRACTIONAL_PART)
+#undef MLB_DEFINE_OP1
+
+#define MLB_DEFINE_OP2(NAME, OP)                                                              \
+  template <size_t ROWS>                                                                      \
+  inline DSPVectorArray<ROWS> NAME(const DSPVectorArray<ROWS>& a, const DSPVectorArray<ROWS>& b) \
+  {                                                                                           \
+    DSPVectorArray<ROWS> y;                                                                   \
+    check(mlb_map_host(OP, a.getConstBuffer(), b.getConstBuffer(), nullptr, y.getBuffer(), ROWS)); \
+    return y;                                                                                 \
+  }
+MLB_DEFINE_OP2(add, MLB_OP_ADD)
+MLB_DEFINE_OP2(subtract, MLB_OP_SUBTRACT)
+MLB_DEFINE_OP2(multiply, MLB_OP_MULTIPLY)
+MLB_DEFINE_OP2(divide, MLB_OP_DIVIDE)
+MLB_DEFINE_OP2(pow, MLB_OP_POW)
+MLB_DEFINE_OP2(min, MLB_OP_MIN)
+MLB_DEFINE_OP2(max, MLB_OP_MAX)
+#undef MLB_DEFINE_OP2
+
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> lerp(const DSPVectorArray<ROWS>& a, const DSPVectorArray<ROWS>& b,
+                                 const DSPVectorArray<ROWS>& m)
+{
+  DSPVectorArray<ROWS> y;
+  check(mlb_map_host(MLB_OP_LERP, a.getConstBuffer(), b.getConstBuffer(), m.getConstBuffer(), y.getBuffer(), ROWS));
+  return y;
+}
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> clamp(const DSPVectorArray<ROWS>& x, const DSPVectorArray<ROWS>& lo,
+                                  const DSPVectorArray<ROWS>& hi)
+{
+  DSPVectorArray<ROWS> y;
+  check(mlb_map_host(MLB_OP_CLAMP, x.getConstBuffer(), lo.getConstBuffer(), hi.getConstBuffer(), y.getBuffer(), ROWS));
+  return y;
+}
+
+// ---- Graph: a fixed DAG of functors, built in the reference's functional style ----
+class Graph
+{
+  std::vector<mlb_node> nodes_;
+  std::vector<int32_t> outs_;
+
+  int add(int op, int a = -1, int b = -1, int c = -1, int iarg = 0)
+  {
+    mlb_node n{op, {a, b, c}, iarg};
+    nodes_.push_back(n);
+    return (int)nodes_.size() - 1;
+  }
+
+ public:
+  using Sig = int;  // a node's output row
+  Sig input(int plane = 0) { return add(MLB_OP_INPUT, -1, -1, -1, plane); }
+  Sig param() { return add(MLB_OP_PARAM); }  // per-voice float, broadcast like DSPVector(float)
+  Sig noise() { return add(MLB_OP_NOISE); }
+  Sig phasor(Sig f) { return add(MLB_OP_PHASOR, f); }
+  Sig sine(Sig f) { return add(MLB_OP_SINE, f); }
+  Sig saw(Sig f) { return add(MLB_OP_SAW, f); }
+  Sig pulse(Sig f, Sig w) { return add(MLB_OP_PULSE, f, w); }
+  Sig lopass(Sig x) { return add(MLB_OP_LOPASS, x); }
+  Sig hipass(Sig x) { return add(MLB_OP_HIPASS, x); }
+  Sig bandpass(Sig x) { return add(MLB_OP_BANDPASS, x); }
+  Sig loShelf(Sig x) { return add(MLB_OP_LOSHELF, x); }
+  Sig hiShelf(Sig x) { return add(MLB_OP_HISHELF, x); }
+  Sig bell(Sig x) { return add(MLB_OP_BELL, x); }
+  Sig onePole(Sig x) { return add(MLB_OP_ONEPOLE, x); }
+  Sig dcBlocker(Sig x) { return add(MLB_OP_DCBLOCKER, x); }
+  Sig fdn8(Sig x) { return add(MLB_OP_FDN8, x); }
+  Sig fdn8Right(Sig fdn) { return add(MLB_OP_FDN8_R, fdn); }
+  Sig op1(int op, Sig x) { return add(op, x); }
+  Sig op2(int op, Sig a, Sig b) { return add(op, a, b); }
+  Sig op3(int op, Sig a, Sig b, Sig c) { return add(op, a, b, c); }
+  Sig multiply(Sig a, Sig b) { return add(MLB_OP_MULTIPLY, a, b); }
+  Sig add2(Sig a, Sig b) { return add(MLB_OP_ADD, a, b); }
+  void output(Sig s) { outs_.push_back(s); }
+
+  const std::vector<mlb_node>& nodes() const { return nodes_; }
+  const std::vector<int32_t>& outs() const { return outs_; }
+};
+
+// ---- DeviceBank: `rows` voices of one graph, resident on the GPU ----
+class DeviceBank
+{
+  mlb_graph* g_ = nullptr;
+  int rows_ = 0;
+  mlb_layout layout_{};
+  std::vector<int32_t> st_off_, co_off_;
+  std::vector<float> coef_;
+  std::vector<uint32_t> state_;
+  int n_out_ = 0;
+
+ public:
+  DeviceBank(const Graph& graph, int rows, unsigned flags = MLB_GRAPH_EXACT) : rows_(rows)
+  {
+    const auto& n = graph.nodes();
+    st_off_.resize(n.size());
+    co_off_.resize(n.size());
+    check(mlb_graph_layout(n.data(), (int)n.size(), &layout_, st_off_.data(), co_off_.data()));
+    check(mlb_graph_create(n.data(), (int)n.size(), graph.outs().data(), (int)graph.outs().size(), rows, flags, &g_));
+    coef_.assign((size_t)layout_.n_coef_words * rows, 0.f);
+    state_.assign((size_t)layout_.n_state_words * rows, 0u);
+    n_out_ = (int)graph.outs().size();
+  }
+  ~DeviceBank() { mlb_graph_destroy(g_); }
+  DeviceBank(const DeviceBank&) = delete;
+  DeviceBank& operator=(const DeviceBank&) = delete;
+
+  int rows() const { return rows_; }
+  const char* kernelName() const { return mlb_graph_kernel_name(g_); }
+
+  // like assigning `bank[row].coeffs = T::makeCoeffs(...)` in the reference
+  void setCoeffs(int node, int row, const float* c, int n)
+  {
+    for (int k = 0; k < n; ++k) coef_[(size_t)(co_off_[node] + k) * rows_ + row] = c[k];
+  }
+  void setParam(int node, int row, float v) { setCoeffs(node, row, &v, 1); }
+  void setStateWord(int node, int slot, int row, uint32_t w) { state_[(size_t)(st_off_[node] + slot) * rows_ + row] = w; }
+  void commit()  // upload coefficients and state
+  {
+    check(mlb_graph_set_coefs(g_, coef_.data()));
+    check(mlb_graph_set_state(g_, state_.data()));
+  }
+  void readState()
+  {
+    check(mlb_graph_get_state(g_, state_.data()));
+  }
+  uint32_t stateWord(int node, int slot, int row) const { return state_[(size_t)(st_off_[node] + slot) * rows_ + row]; }
+  void clear() { check(mlb_graph_clear_delays(g_)); }
+
+  // n_blocks successive Bank::operator() calls: in [T][n_in][rows][64], out [T][n_out][rows][64]
+  void process(const float* in, float* out, float* mix, int n_blocks) { check(mlb_graph_process_host(g_, in, out, mix, n_blocks)); }
+
+  // one block, reference-shaped: DSPVectorArray<ROWS> in -> DSPVectorArray<ROWS> out
+  template <size_t ROWS>
+  DSPVectorArray<ROWS> operator()(const DSPVectorArray<ROWS>& x)
+  {
+    if ((int)ROWS != rows_ || n_out_ != 1) throw Error(MLB_ERR_INVALID, "DeviceBank: shape mismatch");
+    DSPVectorArray<ROWS> y;
+    process(x.getConstBuffer(), y.getBuffer(), nullptr, 1);
+    return y;
+  }
+};
+
+}  // namespace mlb

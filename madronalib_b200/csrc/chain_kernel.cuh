@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(128)
     chain_kernel(const __grid_constant__ CUtensorMap in_map,
                  const __grid_constant__ CUtensorMap out_map, const ChainArgs a)
 {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];  // SWIZZLE_128B atom = 1024 B
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int W = blockDim.x >> 5;
@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(128)
   const int v = v0 + lane;
   const bool live = v < a.V;
 
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atom = 1024 B
+  const uint32_t base = smem_u32(smem_raw);
+  if (base & 1023u) __trap();  // the swizzle formula below assumes 1024-byte aligned tiles
   const uint32_t tiles = base + (uint32_t)(warp * S) * kTileBytes;
   const uint32_t bars = base + (uint32_t)(W * S) * kTileBytes + (uint32_t)(warp * S) * 8u;
 
@@ -161,6 +162,16 @@ __global__ void __launch_bounds__(128)
   const uint32_t row_off = (uint32_t)lane * 128u;
   const uint32_t sw = (uint32_t)(lane & 7) << 4;
 
+  uint32_t mix_off[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    mix_off[j] = ((((uint32_t)lane >> 2) ^ (uint32_t)j) << 4) + (((uint32_t)lane & 3u) << 2);
+  const bool full_group = (v0 + kTileVoices <= a.V);
+  // partial[t*n_out + plane][group][h*32 + lane]; advanced by one block every second tile
+  float* mix_row = a.mix_partial
+                       ? a.mix_partial + ((size_t)a.out_plane * a.n_groups + group) * MLB_BLOCK + lane
+                       : nullptr;
+  const size_t mix_block_stride = (size_t)a.n_out_planes * a.n_groups * MLB_BLOCK;
   int s = 0;            // stage of tile k
   uint32_t parity = 0;  // parity of the current use of stage s
   for (int k = 0; k < total; ++k)
@@ -177,37 +188,46 @@ __global__ void __launch_bounds__(128)
       __syncwarp();
     }
 
-    // ---- 32 samples of this lane's voice, in place ----
+    // ---- 32 samples of this lane's voice, in place.  All eight LDS.128 are issued first so
+    // their latency overlaps the arithmetic (the asm volatile accessors keep program order) ----
+    float4 xin[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      xin[j] = P::HAS_IN ? lds128(tile + row_off + (((uint32_t)j << 4) ^ sw))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
     {
-      const uint32_t addr = tile + row_off + (((uint32_t)j << 4) ^ sw);
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (P::HAS_IN) x = lds128(addr);
       float4 y;
-      y.x = P::tick(x.x, st, co);
-      y.y = P::tick(x.y, st, co);
-      y.z = P::tick(x.z, st, co);
-      y.w = P::tick(x.w, st, co);
-      sts128(addr, y);
+      y.x = P::tick(xin[j].x, st, co);
+      y.y = P::tick(xin[j].y, st, co);
+      y.z = P::tick(xin[j].z, st, co);
+      y.w = P::tick(xin[j].w, st, co);
+      sts128(tile + row_off + (((uint32_t)j << 4) ^ sw), y);
     }
 
     const int t = k >> 1, h = k & 1;
     if (a.mix_partial != nullptr)
     {
-      // lane n sums sample column n over the 32 voice rows, rows in voice order
+      // lane n sums sample column n over the 32 voice rows, rows in voice order, from +0.
+      // Element (r, n) sits at r*128 + (((n>>2) ^ (r&7)) << 4) + (n&3)*4: mix_off[r&7] holds the
+      // lane-dependent part, the rest folds into LDS immediates.
       __syncwarp();
       float acc = 0.0f;
-      const uint32_t cj = (uint32_t)(lane >> 2), cw = (uint32_t)(lane & 3) << 2;
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r)
+      if (full_group)
       {
-        // rows beyond V were zero-filled by TMA but then processed: skip them
-        const float xv = lds32(tile + (uint32_t)r * 128u + ((cj ^ (uint32_t)(r & 7)) << 4) + cw);
-        if (v0 + r < a.V) acc = __fadd_rn(acc, xv);
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          acc = __fadd_rn(acc, lds32(tile + mix_off[r & 7] + (uint32_t)r * 128u));
       }
-      a.mix_partial[((size_t)(t * a.n_out_planes + a.out_plane) * a.n_groups + group) * MLB_BLOCK +
-                    h * kTileSamples + lane] = acc;
+      else
+      {
+        // ragged last group: rows beyond V hold garbage computed from zero-filled input
+        for (int r = 0; r < 32; ++r)
+          if (v0 + r < a.V) acc = __fadd_rn(acc, lds32(tile + mix_off[r & 7] + (uint32_t)r * 128u));
+      }
+      mix_row[h * kTileSamples] = acc;
+      if (h) mix_row += mix_block_stride;
     }
 
     // make this lane's generic-proxy writes visible to the TMA unit, then hand over
@@ -249,25 +269,43 @@ __global__ void __launch_bounds__(128)
   __syncwarp();
 }
 
-// second stage of the mix bus: mix[p][n] = sum over groups g = 0..G-1 (in order) of
-// partial[p][g][n], starting from +0 (like DSPVector vy{0.f} in addRows, O:1352).
-__global__ void __launch_bounds__(64) mix_reduce_kernel(const float* __restrict__ partial,
-                                                        float* __restrict__ mix, int n_groups)
+// second stage of the mix bus.  Deterministic two-level sum (DESIGN.md "mix bus"):
+//   chunk[c][n] = sum over the (up to) 64 group partials of chunk c, in group order, from +0
+//   mix[p][n]   = sum over chunks c = 0..C-1, in order, from +0
+// One CTA per plane, 64 x 16 threads: thread (n, w) owns chunks w, w+16, ...
+constexpr int kMixChunkGroups = 64;  // 64 groups x 32 voices = 2048 voices per chunk
+__global__ void __launch_bounds__(1024) mix_reduce_kernel(const float* __restrict__ partial,
+                                                          float* __restrict__ chunk_scratch,
+                                                          float* __restrict__ mix, int n_groups)
 {
-  const int p = blockIdx.x, n = threadIdx.x;
+  const int p = blockIdx.x, n = threadIdx.x, w = threadIdx.y;
+  const int n_chunks = (n_groups + kMixChunkGroups - 1) / kMixChunkGroups;
   const float* src = partial + (size_t)p * n_groups * MLB_BLOCK + n;
-  float acc = 0.0f;
-  int g = 0;
-  for (; g + 8 <= n_groups; g += 8)
+  float* scratch = chunk_scratch + (size_t)p * n_chunks * MLB_BLOCK + n;
+  for (int c = w; c < n_chunks; c += blockDim.y)
   {
-    float x[8];
+    const int g0 = c * kMixChunkGroups;
+    const int g1 = min(g0 + kMixChunkGroups, n_groups);
+    float acc = 0.0f;
+    int g = g0;
+    for (; g + 8 <= g1; g += 8)
+    {
+      float x[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = src[(size_t)(g + i) * MLB_BLOCK];
+      for (int i = 0; i < 8; ++i) x[i] = src[(size_t)(g + i) * MLB_BLOCK];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc = __fadd_rn(acc, x[i]);
+      for (int i = 0; i < 8; ++i) acc = __fadd_rn(acc, x[i]);
+    }
+    for (; g < g1; ++g) acc = __fadd_rn(acc, src[(size_t)g * MLB_BLOCK]);
+    scratch[(size_t)c * MLB_BLOCK] = acc;
   }
-  for (; g < n_groups; ++g) acc = __fadd_rn(acc, src[(size_t)g * MLB_BLOCK]);
-  mix[(size_t)p * MLB_BLOCK + n] = acc;
+  __syncthreads();  // also orders the global scratch writes within the CTA
+  if (w == 0)
+  {
+    float acc = 0.0f;
+    for (int c = 0; c < n_chunks; ++c) acc = __fadd_rn(acc, scratch[(size_t)c * MLB_BLOCK]);
+    mix[(size_t)p * MLB_BLOCK + n] = acc;
+  }
 }
 
 }  // namespace mlb

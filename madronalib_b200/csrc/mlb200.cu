@@ -819,7 +819,9 @@ static int env_int(const char* name, int dflt)
 
 static int ensure_partial(mlb_graph* g, int T, int n_groups)
 {
-  const size_t need = (size_t)T * std::max<size_t>(1, g->outs.size()) * n_groups * MLB_BLOCK * 4;
+  // per-group partials followed by the per-chunk scratch of mix_reduce_kernel
+  const size_t n_chunks = ((size_t)n_groups + kMixChunkGroups - 1) / kMixChunkGroups;
+  const size_t need = (size_t)T * std::max<size_t>(1, g->outs.size()) * ((size_t)n_groups + n_chunks) * MLB_BLOCK * 4;
   if (need > g->partial_cap)
   {
     cudaFree(g->d_partial);
@@ -879,14 +881,14 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
     else
     {
       const size_t budget = (size_t)227 * 1024 / std::max(1, ctas_per_sm);
-      const size_t fixed = 1024 /*reserved*/ + 1024 /*align*/ + 64 * (size_t)W;
+      const size_t fixed = 1024 /*reserved per CTA*/ + 64 * (size_t)W;
       S = budget > fixed ? (int)((budget - fixed) / ((size_t)W * kTileBytes)) : 3;
       S = std::min(std::max(S, 3), 8);
       S = env_int("MLB_CHAIN_STAGES", S);
       S = std::min(std::max(S, 2), 16);
     }
     a.stages = S;
-    const size_t smem = (size_t)W * S * kTileBytes + 1024 + (size_t)W * S * 8;
+    const size_t smem = (size_t)W * S * kTileBytes + (size_t)W * S * 8;
     if (smem > g_smem_optin) return fail(MLB_ERR_INVALID, "chain launch needs %zu B shared memory", smem);
     CUtensorMap in_map, out_map;
     memset(&in_map, 0, sizeof(in_map));
@@ -949,7 +951,9 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
   if (g->fdn_node >= 0) g->blocks_done += T;
   if (mix_dev)
   {
-    mix_reduce_kernel<<<T * std::max(1, n_out), MLB_BLOCK, 0, stream>>>(g->d_partial, mix_dev, n_groups);
+    float* scratch = g->d_partial + (size_t)T * std::max(1, n_out) * n_groups * MLB_BLOCK;
+    mix_reduce_kernel<<<T * std::max(1, n_out), dim3(MLB_BLOCK, 16), 0, stream>>>(g->d_partial, scratch,
+                                                                                   mix_dev, n_groups);
     ++g_launches;
     CU_CHECK(cudaGetLastError());
   }

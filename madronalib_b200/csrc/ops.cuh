@@ -343,11 +343,11 @@ MLB_DEV float phase_to_phasor(uint32_t phase)
 // phasorToSine, G:316-338, with the reference's constexpr-Newton sqrt2 = 0x1.6a0a0ap+0
 // (S:224,230-235).  The first multiply is merged with the exact 2^-31 phasor
 // scaling: RN(t * (domain * 2^-31)) == RN((t * 2^-31) * domain), no underflow possible.
-#define MLB_K_SQRT2 1.41421568393707275390625f          /* 0x1.6a0a0ap+0 */
-#define MLB_K_FLIP 2.8284313678741455078125f            /* 0x1.6a0a0ap+1 */
-#define MLB_K_DOMAIN_2M31 2.63417043974399258e-09f      /* 0x1.6a0a0ap+2 * 2^-31 = 0x1.6a0a0ap-29 */
-#define MLB_K_INV_RANGE 1.06065642833709716796875f      /* 0x1.0f876cp+0 */
-#define MLB_K_ONE_SIXTH 0.16666667163372039794921875f   /* 0x1.555556p-3 */
+#define MLB_K_SQRT2 0x1.6a0a0ap+0f        /* 1.41421568393707275390625 (bits 0x3fb50505), not sqrt(2) */
+#define MLB_K_FLIP 0x1.6a0a0ap+1f         /* sqrt2 * 2 */
+#define MLB_K_DOMAIN_2M31 0x1.6a0a0ap-29f /* (sqrt2 * 4) * 2^-31 */
+#define MLB_K_INV_RANGE 0x1.0f876cp+0f    /* 1 / (sqrt2 - sqrt2^3 / 6) = 1.0606601238250732421875 */
+#define MLB_K_ONE_SIXTH 0x1.555556p-3f    /* 1.0f / 6.f */
 template <bool EX>
 MLB_DEV float phase_to_sine(uint32_t phase)
 {

@@ -1,0 +1,51 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed), voices sharded, one collective.
+
+Voices are independent units (reference: Bank rows never exchange data,
+source/DSP/MLDSPFunctional.h:328-337), so the data path needs NO collective; the only
+exchange is the sum of the per-rank mix buses (reference pattern: Synth::processVector
+accumulating voices into the outputs, source/app/MLSynth.h:36-60), a [T][n_out][64] f32
+all-reduce -- NCCL over NVLink on GPUs, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+
+def shard_range(n_voices: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous voice range [v0, v1) owned by `rank`."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    return n_voices * rank // world, n_voices * (rank + 1) // world
+
+
+class MixBusReducer:
+    """Double-buffered asynchronous all-reduce of the mix bus.
+
+    ``submit(i, tensor)`` issues the all-reduce of step i's partial mix bus on the process
+    group's stream and returns immediately, so it overlaps the next step's kernel;
+    ``wait(i)`` (called before buffer i&1 is reused, or at the end) completes it.
+    """
+
+    def __init__(self, dist_module=None):
+        self.dist = dist_module
+        self.pending: List[Optional[object]] = [None, None]
+
+    @property
+    def active(self) -> bool:
+        return self.dist is not None and self.dist.is_initialized() and self.dist.get_world_size() > 1
+
+    def wait(self, i: int) -> None:
+        w = self.pending[i & 1]
+        if w is not None:
+            w.wait()
+            self.pending[i & 1] = None
+
+    def submit(self, i: int, tensor) -> None:
+        if not self.active:
+            return
+        self.wait(i)
+        self.pending[i & 1] = self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM, async_op=True)
+
+    def drain(self) -> None:
+        self.wait(0)
+        self.wait(1)

@@ -881,11 +881,10 @@ static void* job_main(void* p)
 /*
  * mix_mode 0: reference order -- voices summed left to right v = 0..V-1 starting
  *             from +0 (addRows, O:1349-1359).
- * mix_mode 1: the device order -- voices in groups of 32 consecutive voices, each
- *             group summed left to right starting from its first voice... see
- *             DESIGN.md "mix bus"; group partials then summed left to right
- *             starting from +0, in `n_shards` contiguous shards (one per GPU) whose
- *             partial sums are finally added left to right starting from +0.
+ * mix_mode 1: the device order (DESIGN.md "mix bus") -- every level is a left-to-right
+ *             sum starting from +0: 32 consecutive voices -> group; 64 consecutive
+ *             groups -> chunk; chunks -> shard (one contiguous shard per GPU);
+ *             shards -> total.
  */
 void mlport_graph_process(mlport_graph* g, const float* in, float* out, float* mix, int T,
                           int nthreads, int mix_mode, int n_shards)
@@ -941,12 +940,18 @@ void mlport_graph_process(mlport_graph* g, const float* in, float* out, float* m
               /* shard s owns voices [s*V/S, (s+1)*V/S) exactly like bench.py's sharding */
               int s0 = (int)((long long)V * s / n_shards), s1 = (int)((long long)V * (s + 1) / n_shards);
               float shard = 0.f;
-              for (int g0 = s0; g0 < s1; g0 += 32)
+              for (int c0 = s0; c0 < s1; c0 += 64 * 32) /* chunks of 64 groups */
               {
-                int g1 = g0 + 32 < s1 ? g0 + 32 : s1;
-                float grp = 0.f;
-                for (int v = g0; v < g1; ++v) grp = grp + plane[(size_t)v * NB + n];
-                shard = shard + grp;
+                int c1 = c0 + 64 * 32 < s1 ? c0 + 64 * 32 : s1;
+                float chunk = 0.f;
+                for (int g0 = c0; g0 < c1; g0 += 32)
+                {
+                  int g1 = g0 + 32 < c1 ? g0 + 32 : c1;
+                  float grp = 0.f;
+                  for (int v = g0; v < g1; ++v) grp = grp + plane[(size_t)v * NB + n];
+                  chunk = chunk + grp;
+                }
+                shard = shard + chunk;
               }
               total = total + shard;
             }

@@ -111,6 +111,18 @@ def test_mix_bus(gpu, port):
         assert np.abs(gm - pm0).max() <= tol
 
 
+def test_mix_bus_many_chunks(gpu, port):
+    """More than one 2048-voice chunk and a ragged last group: exercises every level of the
+    deterministic mix-bus tree (32-voice groups -> 64-group chunks -> total)."""
+    V, T = 2 * 2048 + 100, 2
+    w = wl.config_a(V)
+    inp = w.inputs(T)
+    po, pm1, _ = port.run(w.spec, V, T, inp, w.state, w.coef, want_mix=True, mix_mode=1, nthreads=8)
+    go, gm, _, _ = run_gpu(gpu, w, T, inp, want_mix=True)
+    assert_same_bits(go, po)
+    assert_same_bits(gm, pm1, "mix (device order, 3 chunks)")
+
+
 def test_noise_chain_no_input(gpu, port):
     g = GraphSpec()
     n = g.node("NOISE")

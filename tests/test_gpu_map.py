@@ -39,10 +39,13 @@ def test_map_op(gpu, port, name):
     want = want[0, 0]
     got = gpu.map_host(name, x[0], x[1] if nin > 1 else None, x[2] if nin > 2 else None)
     if name in HW_APPROX:
-        ok = np.isfinite(want) & np.isfinite(got)
+        # rcpps/rsqrtps treat denormal operands as zero; the GPU does not: compare normal inputs
+        tiny = np.finfo(np.float32).tiny
+        normal = np.all((np.abs(x[:nin]) >= tiny) | (x[:nin] == 0) | ~np.isfinite(x[:nin]), axis=0)
+        ok = np.isfinite(want) & np.isfinite(got) & normal
         rel = np.abs(got[ok] - want[ok]) / np.maximum(np.abs(want[ok]), 1e-30)
         assert rel.max() <= 2 * HW_APPROX[name]
-        assert np.array_equal(np.isnan(got), np.isnan(want))
+        assert np.array_equal(np.isnan(got)[normal], np.isnan(want)[normal])
     else:
         assert_same_bits(got, want, name)
 
