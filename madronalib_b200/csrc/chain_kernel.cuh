@@ -4,17 +4,23 @@
 // Work decomposition (DESIGN.md "K1/K2"):
 //   * one LANE per voice: all oscillator / filter state and coefficients live in registers
 //     for the whole launch (loaded once, stored once, SoA, coalesced 4 B/lane);
-//   * one WARP per 32 consecutive voices; warps are fully independent (no __syncthreads):
-//     each warp owns a private ring of `stages` 4 KB shared-memory tiles and its own
+//   * one WARP per 32 consecutive voices (a "group"); the grid is persistent and work units
+//     (a quarter of the launch's blocks for one group) come from an atomic queue; warps are
+//     otherwise fully independent (no __syncthreads):
+//     each warp owns a private ring of `stages` 8 KB shared-memory blocks and its own
 //     mbarriers, and walks time sequentially (the recurrences cannot be split in time);
-//   * a tile is 32 voices x 32 samples of one plane of the reference layout
-//     [plane][V][64] f32, moved by ONE TMA instruction (cp.async.bulk.tensor.3d, box
-//     {32 samples, 32 voices, 1 plane}, SWIZZLE_128B).  With the 128-byte swizzle lane r
-//     finds 16-byte chunk j of its own row at  r*128 + ((j ^ (r & 7)) << 4): the eight
-//     lanes of every quarter-warp hit eight different 16-byte bank groups, so the
-//     per-lane LDS.128 / STS.128 row walk is bank-conflict free;
-//   * results are written IN PLACE into the tile and leave through a TMA store
-//     (UTMASTG); ragged V is clipped by the tensor map (zero fill on load, clip on store);
+//   * the unit of transfer is one 64-sample block of 32 voices = 32 FULL 256-byte rows of one
+//     plane of the reference layout [plane][V][64] f32 (8 KB), moved by ONE TMA instruction
+//     through a 4-D tensor map {32 samples, V voices, 2 halves, planes} with strides
+//     {256 B, 128 B, V*256 B} and box {32, 32, 2, 1}: it lands in shared memory as two 4 KB
+//     half tiles [half][voice][32 samples], each SWIZZLE_128B.  (Fetching half rows with a
+//     3-D map measured 5.8 TB/s in a pure TMA copy; full rows measure 6.2-6.4 TB/s, see
+//     tools/ubench/tma_copy.cu and profiles/.)  With the 128-byte swizzle lane r finds
+//     16-byte chunk j of its own row at  r*128 + ((j ^ (r & 7)) << 4): the eight lanes of
+//     every quarter-warp hit eight different 16-byte bank groups, so the per-lane LDS.128 /
+//     STS.128 row walk is bank-conflict free;
+//   * results are written IN PLACE into the block and leave through one TMA store
+//     (UTMASTG.4D); ragged V is clipped by the tensor map (zero fill on load, clip on store);
 //   * optional mix bus: after a tile is computed, lane n sums column n over the 32 voice
 //     rows (conflict-free through the same swizzle) into partial[plane][group][64];
 //     a second tiny kernel adds the per-group partials in group order (deterministic).
@@ -26,7 +32,9 @@ namespace mlb
 {
 constexpr int kTileSamples = 32;
 constexpr int kTileVoices = 32;
-constexpr int kTileBytes = kTileSamples * kTileVoices * 4;  // 4096
+constexpr int kTileBytes = kTileSamples * kTileVoices * 4;  // 4096: one 128B-swizzled half tile
+constexpr int kBlockBytes = 2 * kTileBytes;                 // 8192: 32 voices x one 64-sample block
+constexpr int kChainMaxWarps = 14;                          // 14 x 2 stages x 8 KB = 224 KB per SM
 constexpr int kMaxChainState = 8;
 constexpr int kMaxChainCoef = 16;
 
@@ -71,6 +79,9 @@ struct ChainArgs
   int n_groups;                 // ceil(V/32)
   int write_out;                // store per-voice output planes
   int stages;
+  unsigned* sched;              // [0] unit counter (zeroed per launch), [1 + g] chunks finished
+  unsigned progress_base;       // value of progress[g] at launch
+  int chunk_blocks, n_chunks;   // blocks per work unit, units per group
   int st_idx[kMaxChainState];  // SoA word index of each register state slot
   int co_idx[kMaxChainCoef];
 };
@@ -104,8 +115,21 @@ struct Chain
   }
 };
 
+// Work distribution: the launch is cut into units (chunk c, group g) = `chunk_blocks`
+// consecutive blocks of one 32-voice group, numbered chunk-major u = c * n_groups + g and
+// handed out by an atomic counter, so any number of resident warps stays balanced.  A voice's
+// time axis is sequential, so unit (c, g) may start only after (c-1, g) stored its state:
+// progress[g] counts finished chunks; chunk-major order means that predecessor was handed
+// out a whole round earlier and is practically always done.  A warp always holds its current
+// unit and the next one, so its TMA load stream runs S-1 blocks ahead across unit boundaries.
+struct UnitCursor
+{
+  int unit;  // unit id, >= total when exhausted
+  int g, t0, nblk;
+};
+
 template <class P>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kChainMaxWarps * 32)
     chain_kernel(const __grid_constant__ CUtensorMap in_map,
                  const __grid_constant__ CUtensorMap out_map, const ChainArgs a)
 {
@@ -114,16 +138,39 @@ __global__ void __launch_bounds__(128)
   const int warp = threadIdx.x >> 5;
   const int W = blockDim.x >> 5;
   const int S = a.stages;
-  const int group = blockIdx.x * W + warp;
-  const int v0 = group * kTileVoices;
-  if (v0 >= a.V) return;  // warp-uniform; warps never synchronise with each other
-  const int v = v0 + lane;
-  const bool live = v < a.V;
+  const int total_units = a.n_chunks * a.n_groups;
 
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();  // the swizzle formula below assumes 1024-byte aligned tiles
-  const uint32_t tiles = base + (uint32_t)(warp * S) * kTileBytes;
-  const uint32_t bars = base + (uint32_t)(W * S) * kTileBytes + (uint32_t)(warp * S) * 8u;
+  const uint32_t blocks = base + (uint32_t)(warp * S) * kBlockBytes;
+  const uint32_t bars = base + (uint32_t)(W * S) * kBlockBytes + (uint32_t)(warp * S) * 8u;
+
+  auto grab = [&]() -> int
+  {
+    int u = 0;
+    if (lane == 0) u = (int)atomicAdd(a.sched, 1u);
+    return __shfl_sync(0xffffffffu, u, 0);
+  };
+  auto decode = [&](int u) -> UnitCursor
+  {
+    UnitCursor c;
+    c.unit = u;
+    const int ch = u / a.n_groups;
+    c.g = u - ch * a.n_groups;
+    c.t0 = ch * a.chunk_blocks;
+    const int rest = a.T - c.t0;
+    c.nblk = (u < total_units) ? (rest < a.chunk_blocks ? rest : a.chunk_blocks) : 0;
+    return c;
+  };
+
+  UnitCursor cur = decode(grab());
+  if (cur.unit >= total_units) return;  // warp-uniform; warps never synchronise with each other
+  // The next unit is reserved only when the load stream is about to need it (S-1 blocks before
+  // the end of `cur`): reserving earlier would put more units in flight than there are groups
+  // and make warps wait on predecessors that are still being computed.
+  UnitCursor nxt = cur;
+  nxt.nblk = 0;
+  bool have_nxt = false;
 
   if (lane == 0)
   {
@@ -137,134 +184,193 @@ __global__ void __launch_bounds__(128)
   }
   __syncwarp();
 
-  // ---- state and coefficients: HBM -> registers, once per launch ----
-  uint32_t st[P::NS > 0 ? P::NS : 1];
-  float co[P::NC > 0 ? P::NC : 1];
-#pragma unroll
-  for (int i = 0; i < P::NS; ++i) st[i] = live ? a.state[(size_t)a.st_idx[i] * a.V + v] : 0u;
-#pragma unroll
-  for (int i = 0; i < P::NC; ++i) co[i] = live ? a.coef[(size_t)a.co_idx[i] * a.V + v] : 0.0f;
-
-  const int total = a.T * 2;  // two 32-sample tiles per 64-sample block
-  // prologue: fill S-1 stages
-  if (P::HAS_IN && lane == 0)
+  // ---- TMA load stream (lane 0): one op = one 64-sample block of 32 voices = 32 full
+  // 256-byte rows (8 KB), landing as two 128B-swizzled 4 KB half tiles ----
+  int ld_in_nxt = 0;  // 0: the load cursor is inside `cur`, 1: inside `nxt`
+  int ld_blk = 0;     // next block of that unit to request
+  int ld_stage = 0;   // stage the next load goes to
+  auto issue_next_load = [&]() -> bool
   {
-    const int pre = (S - 1 < total) ? (S - 1) : total;
-    for (int k = 0; k < pre; ++k)
+    const UnitCursor& u = ld_in_nxt ? nxt : cur;
+    if (ld_blk >= u.nblk) return false;  // stream exhausted (or next unit not known yet)
+    const uint32_t bar = bars + 8u * ld_stage;
+    mbar_arrive_expect_tx(bar, kBlockBytes);
+    tma_load_4d(blocks + (uint32_t)ld_stage * kBlockBytes, &in_map, bar, 0, u.g * kTileVoices, 0,
+                (u.t0 + ld_blk) * a.n_in_planes + a.in_plane, kEvictFirst);
+    if (++ld_stage == S) ld_stage = 0;
+    if (++ld_blk == u.nblk && !ld_in_nxt)
     {
-      const uint32_t bar = bars + 8u * k;
-      mbar_arrive_expect_tx(bar, kTileBytes);
-      tma_load_3d(tiles + (uint32_t)k * kTileBytes, &in_map, bar, (k & 1) * kTileSamples, v0,
-                  (k >> 1) * a.n_in_planes + a.in_plane, kEvictFirst);
+      ld_in_nxt = 1;
+      ld_blk = 0;
     }
-  }
+    return true;
+  };
+  int ahead = 0;  // (lane 0) loads issued minus blocks whose computation has started
+  if (P::HAS_IN && lane == 0)
+    while (ahead < S - 1 && issue_next_load()) ++ahead;
 
   const uint32_t row_off = (uint32_t)lane * 128u;
   const uint32_t sw = (uint32_t)(lane & 7) << 4;
-
   uint32_t mix_off[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     mix_off[j] = ((((uint32_t)lane >> 2) ^ (uint32_t)j) << 4) + (((uint32_t)lane & 3u) << 2);
-  const bool full_group = (v0 + kTileVoices <= a.V);
-  // partial[t*n_out + plane][group][h*32 + lane]; advanced by one block every second tile
-  float* mix_row = a.mix_partial
-                       ? a.mix_partial + ((size_t)a.out_plane * a.n_groups + group) * MLB_BLOCK + lane
-                       : nullptr;
   const size_t mix_block_stride = (size_t)a.n_out_planes * a.n_groups * MLB_BLOCK;
-  int s = 0;            // stage of tile k
+
+  uint32_t st[P::NS > 0 ? P::NS : 1];
+  float co[P::NC > 0 ? P::NC : 1];
+  int s = 0;            // stage of the block being computed
   uint32_t parity = 0;  // parity of the current use of stage s
-  for (int k = 0; k < total; ++k)
+  int stores = 0;       // bulk stores issued by this warp so far
+
+  while (cur.unit < total_units)
   {
-    const uint32_t tile = tiles + (uint32_t)s * kTileBytes;
-    if (P::HAS_IN)
+    // ---- unit start: wait for this group's previous chunk, then state HBM -> registers ----
+    const int v0 = cur.g * kTileVoices;
+    const int v = v0 + lane;
+    const bool live = v < a.V;
+    const bool full_group = (v0 + kTileVoices <= a.V);
+    if (cur.t0 > 0)
     {
-      mbar_wait(bars + 8u * s, parity);
+      const unsigned want = a.progress_base + (unsigned)(cur.t0 / a.chunk_blocks);
+      const volatile unsigned* pr = a.sched + 1 + cur.g;
+      while ((int)(*pr - want) < 0) __nanosleep(64);
+      __threadfence();  // acquire: the predecessor's state stores are visible
     }
-    else
-    {
-      // output-only ring: the store that last read this stage (tile k-S) must be done
-      if (lane == 0) bulk_wait_read<1>();
-      __syncwarp();
-    }
-
-    // ---- 32 samples of this lane's voice, in place.  All eight LDS.128 are issued first so
-    // their latency overlaps the arithmetic (the asm volatile accessors keep program order) ----
-    float4 xin[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      xin[j] = P::HAS_IN ? lds128(tile + row_off + (((uint32_t)j << 4) ^ sw))
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < P::NS; ++i)
+      st[i] = live ? __ldcg(a.state + (size_t)a.st_idx[i] * a.V + v) : 0u;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-    {
-      float4 y;
-      y.x = P::tick(xin[j].x, st, co);
-      y.y = P::tick(xin[j].y, st, co);
-      y.z = P::tick(xin[j].z, st, co);
-      y.w = P::tick(xin[j].w, st, co);
-      sts128(tile + row_off + (((uint32_t)j << 4) ^ sw), y);
-    }
+    for (int i = 0; i < P::NC; ++i) co[i] = live ? a.coef[(size_t)a.co_idx[i] * a.V + v] : 0.0f;
+    // partial[t*n_out + plane][group][h*32 + lane]
+    float* mix_row = a.mix_partial ? a.mix_partial + (size_t)cur.t0 * mix_block_stride +
+                                         ((size_t)a.out_plane * a.n_groups + cur.g) * MLB_BLOCK + lane
+                                   : nullptr;
 
-    const int t = k >> 1, h = k & 1;
-    if (a.mix_partial != nullptr)
+    for (int b = 0; b < cur.nblk; ++b)
     {
-      // lane n sums sample column n over the 32 voice rows, rows in voice order, from +0.
-      // Element (r, n) sits at r*128 + (((n>>2) ^ (r&7)) << 4) + (n&3)*4: mix_off[r&7] holds the
-      // lane-dependent part, the rest folds into LDS immediates.
-      __syncwarp();
-      float acc = 0.0f;
-      if (full_group)
+      if (!have_nxt && b >= cur.nblk - (S - 1))
       {
-#pragma unroll
-        for (int r = 0; r < 32; ++r)
-          acc = __fadd_rn(acc, lds32(tile + mix_off[r & 7] + (uint32_t)r * 128u));
+        nxt = decode(grab());
+        have_nxt = true;
+      }
+      const uint32_t blk = blocks + (uint32_t)s * kBlockBytes;
+      if (P::HAS_IN)
+      {
+        --ahead;
+        mbar_wait(bars + 8u * s, parity);
       }
       else
       {
-        // ragged last group: rows beyond V hold garbage computed from zero-filled input
-        for (int r = 0; r < 32; ++r)
-          if (v0 + r < a.V) acc = __fadd_rn(acc, lds32(tile + mix_off[r & 7] + (uint32_t)r * 128u));
+        // output-only ring (2 stages): the store that last read this stage is done
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
       }
-      mix_row[h * kTileSamples] = acc;
-      if (h) mix_row += mix_block_stride;
-    }
 
-    // make this lane's generic-proxy writes visible to the TMA unit, then hand over
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0)
-    {
-      if (a.write_out)
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h)
       {
-        tma_store_3d(&out_map, tile, h * kTileSamples, v0, t * a.n_out_planes + a.out_plane);
-        bulk_commit();
-      }
-      if (P::HAS_IN)
-      {
-        const int kn = k + S - 1;  // next tile to fetch, into the stage tile k-1 used
-        if (kn < total)
+        const uint32_t tile = blk + (uint32_t)h * kTileBytes;
+        // all eight LDS.128 first so their latency overlaps the arithmetic
+        float4 xin[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          xin[j] = P::HAS_IN ? lds128(tile + row_off + (((uint32_t)j << 4) ^ sw))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
         {
-          if (a.write_out && k >= 1) bulk_wait_read<1>();  // store k-1 finished reading smem
-          const int sn = (s == 0) ? (S - 1) : (s - 1);
-          const uint32_t bar = bars + 8u * sn;
-          mbar_arrive_expect_tx(bar, kTileBytes);
-          tma_load_3d(tiles + (uint32_t)sn * kTileBytes, &in_map, bar, (kn & 1) * kTileSamples, v0,
-                      (kn >> 1) * a.n_in_planes + a.in_plane, kEvictFirst);
+          float4 y;
+          y.x = P::tick(xin[j].x, st, co);
+          y.y = P::tick(xin[j].y, st, co);
+          y.z = P::tick(xin[j].z, st, co);
+          y.w = P::tick(xin[j].w, st, co);
+          sts128(tile + row_off + (((uint32_t)j << 4) ^ sw), y);
+          if (P::HAS_IN && j == 3 && h == 0 && lane == 0)
+          {
+            // Refill point, a quarter block after the previous block's store was issued: that
+            // store has drained its shared-memory reads by now, so the wait does not stall.
+            if (a.write_out && stores > 0) bulk_wait_read<0>();
+            while (ahead < S - 1 && issue_next_load()) ++ahead;
+          }
+        }
+
+        if (a.mix_partial != nullptr)
+        {
+          // lane n sums sample column n over the 32 voice rows, rows in voice order, from +0.
+          // Element (r, n) sits at r*128 + (((n>>2) ^ (r&7)) << 4) + (n&3)*4: mix_off[r&7]
+          // holds the lane-dependent part, the rest folds into LDS immediates.
+          __syncwarp();
+          float acc = 0.0f;
+          if (full_group)
+          {
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              acc = __fadd_rn(acc, lds32(tile + mix_off[r & 7] + (uint32_t)r * 128u));
+          }
+          else
+          {
+            // ragged last group: rows beyond V hold garbage computed from zero-filled input
+            for (int r = 0; r < 32; ++r)
+              if (v0 + r < a.V)
+                acc = __fadd_rn(acc, lds32(tile + mix_off[r & 7] + (uint32_t)r * 128u));
+          }
+          mix_row[h * kTileSamples] = acc;
         }
       }
+      if (a.mix_partial != nullptr) mix_row += mix_block_stride;
+
+      // make this lane's generic-proxy writes visible to the TMA unit, then hand the block over
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && a.write_out)
+      {
+        tma_store_4d(&out_map, blk, 0, v0, 0, (cur.t0 + b) * a.n_out_planes + a.out_plane);
+        bulk_commit();
+      }
+      ++stores;
+      if (++s == S)
+      {
+        s = 0;
+        parity ^= 1u;
+      }
     }
-    if (++s == S)
+
+    // ---- unit done: state back to HBM, publish progress, move to the next unit ----
+#pragma unroll
+    for (int i = 0; i < P::NS; ++i)
+      if (live) __stcg(a.state + (size_t)a.st_idx[i] * a.V + v, st[i]);
+    if (a.n_chunks > 1)
     {
-      s = 0;
-      parity ^= 1u;
+      __threadfence();  // release: state stores before the progress flag
+      __syncwarp();
+      if (lane == 0)
+        atomicExch(a.sched + 1 + cur.g, a.progress_base + (unsigned)(cur.t0 / a.chunk_blocks) + 1u);
+    }
+    if (!have_nxt) nxt = decode(grab());
+    cur = nxt;
+    nxt.nblk = 0;
+    have_nxt = false;
+    // The load cursor was inside the old `nxt`, which is now `cur` (it always is when there are
+    // loads: every block of a unit is requested before it is computed).  If it already
+    // requested all of it (units shorter than the ring), move on and top the ring up again.
+    if (ld_in_nxt)
+      ld_in_nxt = 0;
+    else
+      ld_blk = 0;
+    if (!ld_in_nxt && ld_blk >= cur.nblk)
+    {
+      ld_in_nxt = 1;
+      ld_blk = 0;
+    }
+    if (P::HAS_IN && lane == 0 && ahead < S - 1)
+    {
+      if (a.write_out) bulk_wait_read<0>();  // all stages but the ones in flight are free again
+      while (ahead < S - 1 && issue_next_load()) ++ahead;
     }
   }
 
-  // ---- state back to HBM; shared memory must outlive the last bulk stores ----
-#pragma unroll
-  for (int i = 0; i < P::NS; ++i)
-    if (live) a.state[(size_t)a.st_idx[i] * a.V + v] = st[i];
+  // shared memory must outlive the last bulk stores
   if (lane == 0) bulk_wait_read<0>();
   __syncwarp();
 }

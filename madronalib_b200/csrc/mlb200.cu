@@ -301,15 +301,18 @@ static int ensure_init()
   return mlb_init(dev);
 }
 
-// tensor map over planes of [V][64] f32: dims {64, V, n_planes}, box {32, 32, 1}, 128B swizzle
-static int make_plane_map(CUtensorMap* map, const float* base, int V, long long n_planes,
+// Tensor map over planes of [V][64] f32 that moves FULL 256-byte rows yet lands as two
+// 128B-swizzled half tiles: dims {32 samples, V voices, 2 halves, n_planes} with strides
+// {256 B, 128 B, plane} and box {32, 32, 2, 1} (8 KB per TMA op).
+static int make_block_map(CUtensorMap* map, const float* base, int V, long long n_planes,
                           long long plane_stride_floats)
 {
-  cuuint64_t dims[3] = {(cuuint64_t)MLB_BLOCK, (cuuint64_t)V, (cuuint64_t)n_planes};
-  cuuint64_t strides[2] = {(cuuint64_t)MLB_BLOCK * 4, (cuuint64_t)plane_stride_floats * 4};
-  cuuint32_t box[3] = {(cuuint32_t)kTileSamples, (cuuint32_t)kTileVoices, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
+  cuuint64_t dims[4] = {(cuuint64_t)kTileSamples, (cuuint64_t)V, 2, (cuuint64_t)n_planes};
+  cuuint64_t strides[3] = {(cuuint64_t)MLB_BLOCK * 4, (cuuint64_t)kTileSamples * 4,
+                           (cuuint64_t)plane_stride_floats * 4};
+  cuuint32_t box[4] = {(cuuint32_t)kTileSamples, (cuuint32_t)kTileVoices, 2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(MLB_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
@@ -404,6 +407,10 @@ struct mlb_graph
   float* d_carry = nullptr;
   int ring_len = 0;
   long long blocks_done = 0;
+
+  // chain scheduler: [0] unit counter, [1 + g] finished chunks of group g (monotonic)
+  unsigned* d_sched = nullptr;
+  unsigned progress_base = 0;
 
   // mix bus partials
   float* d_partial = nullptr;
@@ -670,6 +677,12 @@ extern "C" int mlb_graph_create(const mlb_node* nodes, int n_nodes, const int32_
       cudaMalloc(&g->d_coef, std::max<size_t>(1, lay.n_coef_words) * V * 4) != cudaSuccess)
     return cleanup(fail(MLB_ERR_ALLOC, "cudaMalloc of voice state failed: %s",
                         cudaGetErrorString(cudaGetLastError())));
+  {
+    const size_t n_groups = (V + 31) / 32;
+    if (cudaMalloc(&g->d_sched, (n_groups + 1) * 4) != cudaSuccess)
+      return cleanup(fail(MLB_ERR_ALLOC, "cudaMalloc of scheduler words failed"));
+    cudaMemset(g->d_sched, 0, (n_groups + 1) * 4);
+  }
   cudaMemset(g->d_state, 0, std::max<size_t>(1, lay.n_state_words) * V * 4);
   cudaMemset(g->d_coef, 0, std::max<size_t>(1, lay.n_coef_words) * V * 4);
   g->h_coef.assign((size_t)lay.n_coef_words * V, 0.f);
@@ -712,6 +725,7 @@ extern "C" int mlb_graph_destroy(mlb_graph* g)
   cudaFree(g->d_ring);
   cudaFree(g->d_carry);
   cudaFree(g->d_partial);
+  cudaFree(g->d_sched);
   cudaFree(g->d_in);
   cudaFree(g->d_out);
   cudaFree(g->d_mix);
@@ -870,37 +884,58 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
     a.out_plane = 0;
     a.n_groups = n_groups;
     a.write_out = out_dev ? 1 : 0;
-    // launch shape: W warps per CTA, S tile stages per warp (DESIGN.md "occupancy")
-    int W = env_int("MLB_CHAIN_WARPS", 1);
-    W = std::min(std::max(W, 1), 4);
-    const int n_ctas = (n_groups + W - 1) / W;
-    const int ctas_per_sm = (n_ctas + g_sm_count - 1) / g_sm_count;
-    int S;
-    if (!e.has_in)
-      S = 2;
+    // Launch shape (DESIGN.md "occupancy").  The grid is persistent: one CTA of W warps per SM,
+    // each warp owns a ring of S 8-KB blocks and pulls (group, chunk) work units from an atomic
+    // queue.  W is a multiple of 4 so the four SM sub-partitions carry equal warp counts; small
+    // banks simply get one warp per group.
+    const size_t budget = (size_t)g_smem_optin - 64;
+    int W, S;
+    if (n_groups <= g_sm_count * 4)
+      W = std::max(1, (n_groups + g_sm_count - 1) / g_sm_count);
     else
+      W = 12;  // 3 warps per SM sub-partition, 2-stage rings (197 KB): measured best (profiles/)
+    W = env_int("MLB_CHAIN_WARPS", W);
+    W = std::min(std::max(W, 1), kChainMaxWarps);
+    S = 2;
+    if (e.has_in)
     {
-      const size_t budget = (size_t)227 * 1024 / std::max(1, ctas_per_sm);
-      const size_t fixed = 1024 /*reserved per CTA*/ + 64 * (size_t)W;
-      S = budget > fixed ? (int)((budget - fixed) / ((size_t)W * kTileBytes)) : 3;
-      S = std::min(std::max(S, 3), 8);
+      S = (int)(budget / ((size_t)W * (kBlockBytes + 8)));
+      S = std::min(std::max(S, 2), 6);
       S = env_int("MLB_CHAIN_STAGES", S);
-      S = std::min(std::max(S, 2), 16);
+      S = std::min(std::max(S, 2), 12);
     }
     a.stages = S;
-    const size_t smem = (size_t)W * S * kTileBytes + (size_t)W * S * 8;
+    // work units: (group, chunk of blocks).  Aim at >= 6 units per resident warp so the tail of
+    // the dynamic schedule costs < 1/6 of a unit column; chunks never shorter than 8 blocks.
+    {
+      const int n_warps_resident = g_sm_count * W;
+      int n_chunks = (int)((6LL * n_warps_resident + n_groups - 1) / n_groups);
+      n_chunks = std::min(std::max(n_chunks, 1), std::max(1, T / 8));
+      n_chunks = env_int("MLB_CHAIN_CHUNKS", n_chunks);
+      n_chunks = std::min(std::max(n_chunks, 1), T);
+      a.chunk_blocks = (T + n_chunks - 1) / n_chunks;
+      a.n_chunks = (T + a.chunk_blocks - 1) / a.chunk_blocks;
+      a.sched = g->d_sched;
+      a.progress_base = g->progress_base;
+      if (a.n_chunks > 1) g->progress_base += (unsigned)a.n_chunks;
+      CU_CHECK(cudaMemsetAsync(g->d_sched, 0, 4, stream));
+    }
+    const size_t smem = (size_t)W * S * kBlockBytes + (size_t)W * S * 8;
     if (smem > g_smem_optin) return fail(MLB_ERR_INVALID, "chain launch needs %zu B shared memory", smem);
+    const int ctas_per_sm = std::max<size_t>(1, (size_t)(227 * 1024) / (smem + 1024));
+    int n_ctas = std::min((n_groups + W - 1) / W, g_sm_count * ctas_per_sm);
+    n_ctas = std::min(std::max(env_int("MLB_CHAIN_CTAS", n_ctas), 1), (n_groups + W - 1) / W);
     CUtensorMap in_map, out_map;
     memset(&in_map, 0, sizeof(in_map));
     memset(&out_map, 0, sizeof(out_map));
     if (e.has_in)
     {
-      rc = make_plane_map(&in_map, in_dev, V, (long long)T * a.n_in_planes, (long long)V * MLB_BLOCK);
+      rc = make_block_map(&in_map, in_dev, V, (long long)T * a.n_in_planes, (long long)V * MLB_BLOCK);
       if (rc != MLB_OK) return rc;
     }
     if (out_dev)
     {
-      rc = make_plane_map(&out_map, out_dev, V, (long long)T, (long long)V * MLB_BLOCK);
+      rc = make_block_map(&out_map, out_dev, V, (long long)T, (long long)V * MLB_BLOCK);
       if (rc != MLB_OK) return rc;
     }
     CU_CHECK(cudaFuncSetAttribute((const void*)e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -53,6 +53,30 @@ def test_config_a_against_reference_itself(gpu, ref):
     assert_state_equal(gs, rs)
 
 
+@pytest.mark.parametrize("n_voices,n_blocks,chunks,warps", [(100, 24, None, None), (333, 7, 4, None),
+                                                            (96, 9, 9, 3), (2100, 16, 2, 2)])
+def test_dynamic_work_units(gpu, port, monkeypatch, n_voices, n_blocks, chunks, warps):
+    """The launch is cut into (group, chunk) work units pulled from an atomic queue; a voice's
+    state hops between warps at chunk boundaries.  Any chunking must give identical bits."""
+    if chunks is not None:
+        monkeypatch.setenv("MLB_CHAIN_CHUNKS", str(chunks))
+    if warps is not None:
+        monkeypatch.setenv("MLB_CHAIN_WARPS", str(warps))
+    w = wl.config_a(n_voices)
+    inp = w.inputs(n_blocks)
+    po, pm, ps = port.run(w.spec, n_voices, n_blocks, inp, w.state, w.coef, want_mix=True, mix_mode=1,
+                          nthreads=4)
+    go, gm, gs, name = run_gpu(gpu, w, n_blocks, inp, want_mix=True)
+    assert name.startswith("fused:"), name
+    assert_same_bits(go, po, "out")
+    assert_same_bits(gm, pm, "mix")
+    assert_state_equal(gs, ps)
+    # and again in two launches (progress counters carry over)
+    go2, _, gs2, _ = run_gpu(gpu, w, n_blocks, inp, splits=(n_blocks // 2, n_blocks - n_blocks // 2))
+    assert_same_bits(go2, po, "out (two launches)")
+    assert_state_equal(gs2, ps)
+
+
 def test_launch_boundary_continuity(gpu, port):
     """State carried across launches: 2+1+4 blocks == 7 blocks."""
     w = wl.config_a(100)
