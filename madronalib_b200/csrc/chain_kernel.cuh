@@ -73,13 +73,16 @@ struct ChainArgs
   uint32_t* state;     // [n_state_words][V]
   const float* coef;   // [n_coef_words][V]
   float* mix_partial;  // [T*n_out_planes][n_groups][64] or nullptr
-  int V, T;
+  int V, T;                     // voices of this launch (a slice of the bank), blocks
+  int v_stride;                 // voices of the whole bank = row length of the state/coef SoA
   int n_in_planes, in_plane;    // tile z = t*n_in_planes + in_plane
   int n_out_planes, out_plane;  // tile z = t*n_out_planes + out_plane
-  int n_groups;                 // ceil(V/32)
+  int n_groups;                 // ceil(V/32) groups of this launch
+  int groups_stride;            // groups of the whole bank = row length of the mix partials
   int write_out;                // store per-voice output planes
   int stages;
-  unsigned* sched;              // [0] unit counter (zeroed per launch), [1 + g] chunks finished
+  unsigned* sched;              // unit counter (zeroed per launch)
+  unsigned* progress;           // [g] chunks finished by group g of this launch (monotonic)
   unsigned progress_base;       // value of progress[g] at launch
   int chunk_blocks, n_chunks;   // blocks per work unit, units per group
   int st_idx[kMaxChainState];  // SoA word index of each register state slot
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(kChainMaxWarps * 32)
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     mix_off[j] = ((((uint32_t)lane >> 2) ^ (uint32_t)j) << 4) + (((uint32_t)lane & 3u) << 2);
-  const size_t mix_block_stride = (size_t)a.n_out_planes * a.n_groups * MLB_BLOCK;
+  const size_t mix_block_stride = (size_t)a.n_out_planes * a.groups_stride * MLB_BLOCK;
 
   uint32_t st[P::NS > 0 ? P::NS : 1];
   float co[P::NC > 0 ? P::NC : 1];
@@ -233,18 +236,18 @@ __global__ void __launch_bounds__(kChainMaxWarps * 32)
     if (cur.t0 > 0)
     {
       const unsigned want = a.progress_base + (unsigned)(cur.t0 / a.chunk_blocks);
-      const volatile unsigned* pr = a.sched + 1 + cur.g;
+      const volatile unsigned* pr = a.progress + cur.g;
       while ((int)(*pr - want) < 0) __nanosleep(64);
       __threadfence();  // acquire: the predecessor's state stores are visible
     }
 #pragma unroll
     for (int i = 0; i < P::NS; ++i)
-      st[i] = live ? __ldcg(a.state + (size_t)a.st_idx[i] * a.V + v) : 0u;
+      st[i] = live ? __ldcg(a.state + (size_t)a.st_idx[i] * a.v_stride + v) : 0u;
 #pragma unroll
-    for (int i = 0; i < P::NC; ++i) co[i] = live ? a.coef[(size_t)a.co_idx[i] * a.V + v] : 0.0f;
+    for (int i = 0; i < P::NC; ++i) co[i] = live ? a.coef[(size_t)a.co_idx[i] * a.v_stride + v] : 0.0f;
     // partial[t*n_out + plane][group][h*32 + lane]
     float* mix_row = a.mix_partial ? a.mix_partial + (size_t)cur.t0 * mix_block_stride +
-                                         ((size_t)a.out_plane * a.n_groups + cur.g) * MLB_BLOCK + lane
+                                         ((size_t)a.out_plane * a.groups_stride + cur.g) * MLB_BLOCK + lane
                                    : nullptr;
 
     for (int b = 0; b < cur.nblk; ++b)
@@ -339,13 +342,13 @@ __global__ void __launch_bounds__(kChainMaxWarps * 32)
     // ---- unit done: state back to HBM, publish progress, move to the next unit ----
 #pragma unroll
     for (int i = 0; i < P::NS; ++i)
-      if (live) __stcg(a.state + (size_t)a.st_idx[i] * a.V + v, st[i]);
+      if (live) __stcg(a.state + (size_t)a.st_idx[i] * a.v_stride + v, st[i]);
     if (a.n_chunks > 1)
     {
       __threadfence();  // release: state stores before the progress flag
       __syncwarp();
       if (lane == 0)
-        atomicExch(a.sched + 1 + cur.g, a.progress_base + (unsigned)(cur.t0 / a.chunk_blocks) + 1u);
+        atomicExch(a.progress + cur.g, a.progress_base + (unsigned)(cur.t0 / a.chunk_blocks) + 1u);
     }
     if (!have_nxt) nxt = decode(grab());
     cur = nxt;

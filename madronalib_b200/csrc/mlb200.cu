@@ -411,6 +411,7 @@ struct mlb_graph
   // chain scheduler: [0] unit counter, [1 + g] finished chunks of group g (monotonic)
   unsigned* d_sched = nullptr;
   unsigned progress_base = 0;
+  int launch_chunks = 1;  // chunks per group of the launch in flight (advances progress_base)
 
   // mix bus partials
   float* d_partial = nullptr;
@@ -419,7 +420,8 @@ struct mlb_graph
   // staging for the host entry point
   float *d_in = nullptr, *d_out = nullptr, *d_mix = nullptr;
   size_t in_cap = 0, out_cap = 0, mix_cap = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_up[16] = {}, ev_k[16] = {};
 
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
@@ -687,6 +689,13 @@ extern "C" int mlb_graph_create(const mlb_node* nodes, int n_nodes, const int32_
   cudaMemset(g->d_coef, 0, std::max<size_t>(1, lay.n_coef_words) * V * 4);
   g->h_coef.assign((size_t)lay.n_coef_words * V, 0.f);
   cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&g->s_h2d, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&g->s_d2h, cudaStreamNonBlocking);
+  for (int i = 0; i < 16; ++i)
+  {
+    cudaEventCreateWithFlags(&g->ev_up[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&g->ev_k[i], cudaEventDisableTiming);
+  }
   cudaEventCreate(&g->ev0);
   cudaEventCreate(&g->ev1);
 
@@ -731,6 +740,13 @@ extern "C" int mlb_graph_destroy(mlb_graph* g)
   cudaFree(g->d_mix);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
+  for (int i = 0; i < 16; ++i)
+  {
+    if (g->ev_up[i]) cudaEventDestroy(g->ev_up[i]);
+    if (g->ev_k[i]) cudaEventDestroy(g->ev_k[i]);
+  }
+  if (g->s_h2d) cudaStreamDestroy(g->s_h2d);
+  if (g->s_d2h) cudaStreamDestroy(g->s_d2h);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
   return MLB_OK;
@@ -848,6 +864,94 @@ static int ensure_partial(mlb_graph* g, int T, int n_groups)
   return MLB_OK;
 }
 
+// Launch the fused chain kernel for the voice slice [va, vb) (va a multiple of 32) of the bank.
+// in_dev / out_dev are the FULL planes [T][n][V][64]; the tensor maps, SoA pointers, mix
+// partials and progress words are offset to the slice.
+static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev, bool want_mix, int T,
+                              cudaStream_t stream, int va, int vb, int force_chunks = 0)
+{
+  const FusedEntry& e = *g->fused;
+  const int V = g->V, Vs = vb - va;
+  const int groups_total = (V + 31) / 32, n_groups = (Vs + 31) / 32;
+  const int n_in = g->layout.n_inputs;
+  int rc;
+  ChainArgs a = g->cargs;
+  a.state = g->d_state + va;
+  a.coef = g->d_coef + va;
+  a.mix_partial = want_mix ? g->d_partial + (size_t)(va / 32) * MLB_BLOCK : nullptr;
+  a.V = Vs;
+  a.T = T;
+  a.v_stride = V;
+  a.n_in_planes = std::max(1, n_in);
+  a.n_out_planes = 1;
+  a.out_plane = 0;
+  a.n_groups = n_groups;
+  a.groups_stride = groups_total;
+  a.write_out = out_dev ? 1 : 0;
+  // Launch shape (DESIGN.md "occupancy").  The grid is persistent: one CTA of W warps per SM,
+  // each warp owns a ring of S 8-KB blocks and pulls (group, chunk) work units from an atomic
+  // queue.  W is a multiple of 4 so the four SM sub-partitions carry equal warp counts; small
+  // banks simply get one warp per group.
+  const size_t budget = (size_t)g_smem_optin - 64;
+  int W, S;
+  if (n_groups <= g_sm_count * 4)
+    W = std::max(1, (n_groups + g_sm_count - 1) / g_sm_count);
+  else
+    W = 12;  // 3 warps per SM sub-partition, 2-stage rings (197 KB): measured best (profiles/)
+  W = env_int("MLB_CHAIN_WARPS", W);
+  W = std::min(std::max(W, 1), kChainMaxWarps);
+  S = 2;
+  if (e.has_in)
+  {
+    S = (int)(budget / ((size_t)W * (kBlockBytes + 8)));
+    S = std::min(std::max(S, 2), 6);
+    S = env_int("MLB_CHAIN_STAGES", S);
+    S = std::min(std::max(S, 2), 12);
+  }
+  a.stages = S;
+  // work units: (group, chunk of blocks).  Aim at >= 6 units per resident warp so the tail of
+  // the dynamic schedule costs < 1/6 of a unit column; chunks never shorter than 8 blocks.
+  {
+    const int n_warps_resident = g_sm_count * W;
+    int n_chunks = (int)((6LL * n_warps_resident + n_groups - 1) / n_groups);
+    n_chunks = std::min(std::max(n_chunks, 1), std::max(1, T / 8));
+    n_chunks = env_int("MLB_CHAIN_CHUNKS", n_chunks);
+    if (force_chunks > 0) n_chunks = force_chunks;  // all slices of one call must agree
+    n_chunks = std::min(std::max(n_chunks, 1), T);
+    a.chunk_blocks = (T + n_chunks - 1) / n_chunks;
+    a.n_chunks = (T + a.chunk_blocks - 1) / a.chunk_blocks;
+    a.sched = g->d_sched;
+    a.progress = g->d_sched + 1 + va / 32;
+    a.progress_base = g->progress_base;
+    g->launch_chunks = a.n_chunks;
+    CU_CHECK(cudaMemsetAsync(g->d_sched, 0, 4, stream));
+  }
+  const size_t smem = (size_t)W * S * kBlockBytes + (size_t)W * S * 8;
+  if (smem > g_smem_optin) return fail(MLB_ERR_INVALID, "chain launch needs %zu B shared memory", smem);
+  const int ctas_per_sm = std::max<size_t>(1, (size_t)(227 * 1024) / (smem + 1024));
+  int n_ctas = std::min((n_groups + W - 1) / W, g_sm_count * ctas_per_sm);
+  n_ctas = std::min(std::max(env_int("MLB_CHAIN_CTAS", n_ctas), 1), (n_groups + W - 1) / W);
+  CUtensorMap in_map, out_map;
+  memset(&in_map, 0, sizeof(in_map));
+  memset(&out_map, 0, sizeof(out_map));
+  if (e.has_in)
+  {
+    rc = make_block_map(&in_map, in_dev + (size_t)va * MLB_BLOCK, Vs, (long long)T * a.n_in_planes,
+                        (long long)V * MLB_BLOCK);
+    if (rc != MLB_OK) return rc;
+  }
+  if (out_dev)
+  {
+    rc = make_block_map(&out_map, out_dev + (size_t)va * MLB_BLOCK, Vs, (long long)T, (long long)V * MLB_BLOCK);
+    if (rc != MLB_OK) return rc;
+  }
+  CU_CHECK(cudaFuncSetAttribute((const void*)e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  e.fn<<<n_ctas, W * 32, smem, stream>>>(in_map, out_map, a);
+  ++g_launches;
+  CU_CHECK(cudaGetLastError());
+  return MLB_OK;
+}
+
 extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float* out_dev,
                                         float* mix_dev, int n_blocks, void* stream_v)
 {
@@ -872,75 +976,9 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
   cudaEventRecord(g->ev0, stream);
   if (g->kind == KIND_FUSED)
   {
-    const FusedEntry& e = *g->fused;
-    ChainArgs a = g->cargs;
-    a.state = g->d_state;
-    a.coef = g->d_coef;
-    a.mix_partial = mix_dev ? g->d_partial : nullptr;
-    a.V = V;
-    a.T = T;
-    a.n_in_planes = std::max(1, n_in);
-    a.n_out_planes = 1;
-    a.out_plane = 0;
-    a.n_groups = n_groups;
-    a.write_out = out_dev ? 1 : 0;
-    // Launch shape (DESIGN.md "occupancy").  The grid is persistent: one CTA of W warps per SM,
-    // each warp owns a ring of S 8-KB blocks and pulls (group, chunk) work units from an atomic
-    // queue.  W is a multiple of 4 so the four SM sub-partitions carry equal warp counts; small
-    // banks simply get one warp per group.
-    const size_t budget = (size_t)g_smem_optin - 64;
-    int W, S;
-    if (n_groups <= g_sm_count * 4)
-      W = std::max(1, (n_groups + g_sm_count - 1) / g_sm_count);
-    else
-      W = 12;  // 3 warps per SM sub-partition, 2-stage rings (197 KB): measured best (profiles/)
-    W = env_int("MLB_CHAIN_WARPS", W);
-    W = std::min(std::max(W, 1), kChainMaxWarps);
-    S = 2;
-    if (e.has_in)
-    {
-      S = (int)(budget / ((size_t)W * (kBlockBytes + 8)));
-      S = std::min(std::max(S, 2), 6);
-      S = env_int("MLB_CHAIN_STAGES", S);
-      S = std::min(std::max(S, 2), 12);
-    }
-    a.stages = S;
-    // work units: (group, chunk of blocks).  Aim at >= 6 units per resident warp so the tail of
-    // the dynamic schedule costs < 1/6 of a unit column; chunks never shorter than 8 blocks.
-    {
-      const int n_warps_resident = g_sm_count * W;
-      int n_chunks = (int)((6LL * n_warps_resident + n_groups - 1) / n_groups);
-      n_chunks = std::min(std::max(n_chunks, 1), std::max(1, T / 8));
-      n_chunks = env_int("MLB_CHAIN_CHUNKS", n_chunks);
-      n_chunks = std::min(std::max(n_chunks, 1), T);
-      a.chunk_blocks = (T + n_chunks - 1) / n_chunks;
-      a.n_chunks = (T + a.chunk_blocks - 1) / a.chunk_blocks;
-      a.sched = g->d_sched;
-      a.progress_base = g->progress_base;
-      if (a.n_chunks > 1) g->progress_base += (unsigned)a.n_chunks;
-      CU_CHECK(cudaMemsetAsync(g->d_sched, 0, 4, stream));
-    }
-    const size_t smem = (size_t)W * S * kBlockBytes + (size_t)W * S * 8;
-    if (smem > g_smem_optin) return fail(MLB_ERR_INVALID, "chain launch needs %zu B shared memory", smem);
-    const int ctas_per_sm = std::max<size_t>(1, (size_t)(227 * 1024) / (smem + 1024));
-    int n_ctas = std::min((n_groups + W - 1) / W, g_sm_count * ctas_per_sm);
-    n_ctas = std::min(std::max(env_int("MLB_CHAIN_CTAS", n_ctas), 1), (n_groups + W - 1) / W);
-    CUtensorMap in_map, out_map;
-    memset(&in_map, 0, sizeof(in_map));
-    memset(&out_map, 0, sizeof(out_map));
-    if (e.has_in)
-    {
-      rc = make_block_map(&in_map, in_dev, V, (long long)T * a.n_in_planes, (long long)V * MLB_BLOCK);
-      if (rc != MLB_OK) return rc;
-    }
-    if (out_dev)
-    {
-      rc = make_block_map(&out_map, out_dev, V, (long long)T, (long long)V * MLB_BLOCK);
-      if (rc != MLB_OK) return rc;
-    }
-    CU_CHECK(cudaFuncSetAttribute((const void*)e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    e.fn<<<n_ctas, W * 32, smem, stream>>>(in_map, out_map, a);
-    ++g_launches;
+    rc = launch_chain_slice(g, in_dev, out_dev, mix_dev != nullptr, T, stream, 0, V);
+    if (rc != MLB_OK) return rc;
+    if (g->launch_chunks > 1) g->progress_base += (unsigned)g->launch_chunks;
   }
   else if (g->kind == KIND_FDN)
   {
@@ -1022,6 +1060,59 @@ extern "C" int mlb_graph_process_host(mlb_graph* g, const float* in_host, float*
   if (out_host && (rc = ensure_buf(&g->d_out, &g->out_cap, out_bytes)) != MLB_OK) return rc;
   if (mix_host && (rc = ensure_buf(&g->d_mix, &g->mix_cap, mix_bytes)) != MLB_OK) return rc;
   cudaStream_t s = g->stream;
+  // Large fused banks: pipeline over voice slices so that the H2D copy of slice p+1, the kernel
+  // of slice p and the D2H copy of slice p-1 overlap (three streams; PCIe is full duplex).
+  // A slice is a strided window [T*n][va:vb][64] of the host planes -> cudaMemcpy2DAsync.
+  const int n_slices_env = env_int("MLB_HOST_SLICES", 16);
+  if (g->kind == KIND_FUSED && n_slices_env > 1 && g->V >= 4096 && in_bytes + out_bytes >= ((size_t)32 << 20))
+  {
+    const int n_slices = std::min(n_slices_env, 16);
+    int per = (g->V + n_slices - 1) / n_slices;
+    per = (per + 31) / 32 * 32;
+    const size_t pitch = V * MLB_BLOCK * 4;
+    if (mix_host && (rc = ensure_partial(g, n_blocks, (g->V + 31) / 32)) != MLB_OK) return rc;
+    int chunks = 0;
+    cudaEventRecord(g->ev0, s);
+    for (int p = 0, va = 0; va < g->V; ++p, va += per)
+    {
+      const int vb = std::min(g->V, va + per);
+      const size_t width = (size_t)(vb - va) * MLB_BLOCK * 4;
+      if (n_in)
+      {
+        CU_CHECK(cudaMemcpy2DAsync(g->d_in + (size_t)va * MLB_BLOCK, pitch, in_host + (size_t)va * MLB_BLOCK,
+                                   pitch, width, T * n_in, cudaMemcpyHostToDevice, g->s_h2d));
+        CU_CHECK(cudaEventRecord(g->ev_up[p], g->s_h2d));
+        CU_CHECK(cudaStreamWaitEvent(s, g->ev_up[p], 0));
+      }
+      rc = launch_chain_slice(g, n_in ? g->d_in : nullptr, out_host ? g->d_out : nullptr, mix_host != nullptr,
+                              n_blocks, s, va, vb, chunks);
+      if (rc != MLB_OK) return rc;
+      chunks = g->launch_chunks;
+      if (out_host)
+      {
+        CU_CHECK(cudaEventRecord(g->ev_k[p], s));
+        CU_CHECK(cudaStreamWaitEvent(g->s_d2h, g->ev_k[p], 0));
+        CU_CHECK(cudaMemcpy2DAsync(out_host + (size_t)va * MLB_BLOCK, pitch, g->d_out + (size_t)va * MLB_BLOCK,
+                                   pitch, width, T * n_out, cudaMemcpyDeviceToHost, g->s_d2h));
+      }
+    }
+    cudaEventRecord(g->ev1, s);
+    g->timed = true;
+    if (g->launch_chunks > 1) g->progress_base += (unsigned)g->launch_chunks;
+    if (mix_host)
+    {
+      const int n_groups = (g->V + 31) / 32;
+      float* scratch = g->d_partial + T * std::max<size_t>(1, n_out) * n_groups * MLB_BLOCK;
+      mix_reduce_kernel<<<(int)(T * std::max<size_t>(1, n_out)), dim3(MLB_BLOCK, 16), 0, s>>>(g->d_partial, scratch,
+                                                                                            g->d_mix, n_groups);
+      ++g_launches;
+      CU_CHECK(cudaGetLastError());
+      CU_CHECK(cudaMemcpyAsync(mix_host, g->d_mix, mix_bytes, cudaMemcpyDeviceToHost, s));
+    }
+    CU_CHECK(cudaStreamSynchronize(s));
+    CU_CHECK(cudaStreamSynchronize(g->s_d2h));
+    return MLB_OK;
+  }
   if (n_in) CU_CHECK(cudaMemcpyAsync(g->d_in, in_host, in_bytes, cudaMemcpyHostToDevice, s));
   rc = mlb_graph_process_device(g, n_in ? g->d_in : nullptr, out_host ? g->d_out : nullptr,
                                 mix_host ? g->d_mix : nullptr, n_blocks, s);

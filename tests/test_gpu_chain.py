@@ -77,6 +77,21 @@ def test_dynamic_work_units(gpu, port, monkeypatch, n_voices, n_blocks, chunks, 
     assert_state_equal(gs2, ps)
 
 
+@pytest.mark.parametrize("slices", [1, 5, 8])
+def test_host_entry_point_voice_slices(gpu, port, monkeypatch, slices):
+    """mlb_graph_process_host pipelines big banks over voice slices (H2D / kernel / D2H on three
+    streams); the result must not depend on the slicing."""
+    monkeypatch.setenv("MLB_HOST_SLICES", str(slices))
+    V, T = 4200 + 7, 17
+    w = wl.config_a(V)
+    inp = w.inputs(T)
+    po, pm, ps = port.run(w.spec, V, T, inp, w.state, w.coef, want_mix=True, mix_mode=1, nthreads=8)
+    go, gm, gs, _ = run_gpu(gpu, w, T, inp, want_mix=True, splits=(9, 8))
+    assert_same_bits(go, po, "out")
+    assert_same_bits(gm, pm, "mix")
+    assert_state_equal(gs, ps)
+
+
 def test_launch_boundary_continuity(gpu, port):
     """State carried across launches: 2+1+4 blocks == 7 blocks."""
     w = wl.config_a(100)
