@@ -126,9 +126,11 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
-def reference_chain_runner(n_voices: int, n_blocks: int):
-    """Returns (run_once() -> seconds, kind, voice_samples_per_pass).  Uses the compiled
-    reference (oracle/_ref) when present, else the plain-C port (oracle/_port)."""
+def reference_chain_runner(n_voices: int, n_blocks: int, repeats: int = 1):
+    """Returns (run_once() -> seconds, kind, threads).  One call = `repeats` passes over
+    n_voices x n_blocks of config A with the compiled reference's own functors (oracle/_ref,
+    struct Voice{SineGen; Lopass}) on all host threads; falls back to the plain-C port
+    (oracle/_port) only where the reference library was never built."""
     from madronalib_b200 import workloads as wl
     from oracle import bindings
 
@@ -144,7 +146,7 @@ def reference_chain_runner(n_voices: int, n_blocks: int):
         x = np.ascontiguousarray(inp[:, 0])
 
         def run_once():
-            _, sec = R.chain_sine_lopass_gain(x, coef3, gain, phase, ic, nthreads)
+            _, sec = R.chain_sine_lopass_gain(x, coef3, gain, phase, ic, nthreads, repeats)
             return sec
         return run_once, "reference", nthreads
     if not os.path.exists(bindings.PORT_LIB):
@@ -153,43 +155,51 @@ def reference_chain_runner(n_voices: int, n_blocks: int):
 
     def run_once():
         t0 = time.perf_counter()
-        P.run(w.spec, n_voices, n_blocks, inp, w.state, w.coef, nthreads=nthreads)
+        for _ in range(repeats):
+            P.run(w.spec, n_voices, n_blocks, inp, w.state, w.coef, nthreads=nthreads)
         return time.perf_counter() - t0
     return run_once, "port", nthreads
 
 
+REF_VOICES = 32768  # bounded sample: half the bank (2 x 0.5 GB host buffers), same per-voice work
+REF_REPEATS = 4     # passes per step inside one thread launch (amortises thread start-up)
+
+
 def cpu_baseline(budget_s: float = 12.0):
     """Time the reference chain on a bounded sample of the same workload."""
-    V = N_VOICES // 4  # 16 384 voices x 64 blocks = 6.7e7 voice-samples per pass
-    run_once, kind, nthreads = reference_chain_runner(V, N_BLOCKS)
+    V = REF_VOICES
+    run_once, kind, nthreads = reference_chain_runner(V, N_BLOCKS, REF_REPEATS)
     run_once()  # warm-up (page faults, thread start)
     secs, t_start = [], time.perf_counter()
-    while len(secs) < 3 or (time.perf_counter() - t_start < budget_s and len(secs) < 50):
+    while len(secs) < 3 or (time.perf_counter() - t_start < budget_s and len(secs) < 40):
         secs.append(run_once())
-    vs = V * N_BLOCKS * BLOCK
+    vs = V * N_BLOCKS * BLOCK * REF_REPEATS
     best = float(np.median(secs))
     return {"value": vs / best, "unit": UNIT, "cores": nthreads, "kind": kind,
-            "sample": f"{V} voices x {N_BLOCKS} blocks x {len(secs)} passes of config A "
-                      f"(median pass {best * 1e3:.1f} ms), std::thread x {nthreads}"}
+            "sample": f"{V} voices x {N_BLOCKS} blocks x {REF_REPEATS} passes per call, {len(secs)} calls "
+                      f"of config A (median call {best * 1e3:.1f} ms), std::thread x {nthreads}"}
 
 
 def run_reference_arm(args):
     rank, _, world = dist_env()
     if rank != 0:
         return 0
-    V = N_VOICES // 4
-    run_once, kind, nthreads = reference_chain_runner(V, N_BLOCKS)
+    V, reps = REF_VOICES, REF_REPEATS
+    run_once, kind, nthreads = reference_chain_runner(V, N_BLOCKS, reps)
     t = run_once()
     # keep the whole run within a few minutes: shrink the per-step sample if needed
     total_steps = args.steps + args.warmup
-    while t * total_steps > 150.0 and V > 1024:
-        V //= 2
-        run_once, kind, nthreads = reference_chain_runner(V, N_BLOCKS)
+    while t * total_steps > 150.0 and (reps > 1 or V > 1024):
+        if reps > 1:
+            reps //= 2
+        else:
+            V //= 2
+        run_once, kind, nthreads = reference_chain_runner(V, N_BLOCKS, reps)
         t = run_once()
     for _ in range(args.warmup):
         run_once()
     secs = [run_once() for _ in range(args.steps)]
-    vs = V * N_BLOCKS * BLOCK
+    vs = V * N_BLOCKS * BLOCK * reps
     total = float(np.sum(secs))
     value = vs * args.steps / total
     line = {
@@ -198,10 +208,11 @@ def run_reference_arm(args):
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "config A: SineGen->Lopass(SVF)->gain, contract R, 48 kHz; "
-                               f"bounded sample {V} voices x {N_BLOCKS} blocks per step",
-                   "voices": V, "blocks_per_step": N_BLOCKS},
+                               f"bounded sample {V} voices x {N_BLOCKS} blocks x {reps} passes per step",
+                   "voices": V, "blocks_per_step": N_BLOCKS * reps},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": kind,
-                         "sample": f"{V} voices x {N_BLOCKS} blocks per step, {args.steps} steps"},
+                         "sample": f"{V} voices x {N_BLOCKS} blocks x {reps} passes per step, "
+                                   f"{args.steps} steps"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -253,22 +264,18 @@ def run_cuda_arm(args):
     stream = torch.cuda.current_stream()
     sh = stream.cuda_stream
 
-    pending = [None, None]
+    from madronalib_b200.parallel import MixBusReducer
+    reducer = MixBusReducer(dist)
 
     def step(i: int):
         m = d_mix[i & 1]
-        if pending[i & 1] is not None:  # all-reduce issued two steps ago on this buffer
-            pending[i & 1].wait()
-            pending[i & 1] = None
+        reducer.wait(i)  # the all-reduce issued two steps ago on this buffer
         graph.process_device(d_in, d_out, m if use_mix else None, T, sh)
-        if dist is not None and use_mix:
-            pending[i & 1] = dist.all_reduce(m, op=dist.ReduceOp.SUM, async_op=True)
+        if use_mix:
+            reducer.submit(i, m)  # NCCL all-reduce of the [T][1][64] mix bus, overlaps step i+1
 
     def drain():
-        for k in (0, 1):
-            if pending[k] is not None:
-                pending[k].wait()
-                pending[k] = None
+        reducer.drain()
 
     def barrier():
         if dist is not None:

@@ -136,7 +136,7 @@ class RefOracle(_Oracle):
         self.lib.mlref_graph_process.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int]
         self.lib.mlref_chain_sine_lopass_gain.restype = ctypes.c_double
         self.lib.mlref_chain_sine_lopass_gain.argtypes = [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp,
-                                                          _vp, _vp, _vp, ctypes.c_int]
+                                                          _vp, _vp, _vp, ctypes.c_int, ctypes.c_int]
 
     def _process(self, h, inp, out, mix, T, nthreads, mix_mode, n_shards):
         if mix is not None and mix_mode != 0:
@@ -147,12 +147,12 @@ class RefOracle(_Oracle):
         return int(self.lib.mlref_sizeof(which))
 
     def chain_sine_lopass_gain(self, inp: np.ndarray, coef3: np.ndarray, gain: np.ndarray,
-                               phase: np.ndarray, ic: np.ndarray, nthreads: int):
+                               phase: np.ndarray, ic: np.ndarray, nthreads: int, repeats: int = 1):
         """The reference's own chain loop (struct Voice{SineGen; Lopass}); returns (out, seconds)."""
         T, V, _ = inp.shape
         out = np.empty_like(inp)
         sec = self.lib.mlref_chain_sine_lopass_gain(V, T, _ptr(inp), _ptr(out), _ptr(coef3),
-                                                    _ptr(gain), _ptr(phase), _ptr(ic), nthreads)
+                                                    _ptr(gain), _ptr(phase), _ptr(ic), nthreads, repeats)
         return out, float(sec)
 
 

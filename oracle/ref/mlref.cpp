@@ -590,7 +590,7 @@ int mlref_sizeof(int which)
 double mlref_chain_sine_lopass_gain(int V, int T, const float* in, float* out,
                                     const float* coef3 /*[3][V]*/, const float* gain /*[V]*/,
                                     uint32_t* phase /*[V] io*/, float* ic /*[2][V] io*/,
-                                    int nthreads)
+                                    int nthreads, int repeats)
 {
   struct Voice
   {
@@ -607,15 +607,19 @@ double mlref_chain_sine_lopass_gain(int V, int T, const float* in, float* out,
   }
   if (nthreads < 1) nthreads = 1;
   nthreads = std::min(nthreads, std::max(1, V));
+  if (repeats < 1) repeats = 1;
+  // `repeats` passes over the same T input blocks inside one thread launch (state carries on),
+  // so that thread start-up is amortised when this loop is used as the CPU baseline.
   auto worker = [&](int v0, int v1)
   {
-    for (int t = 0; t < T; ++t)
-      for (int v = v0; v < v1; ++v)
-      {
-        const size_t off = ((size_t)t * V + v) * 64;
-        DSPVector y = voices[v].lp(voices[v].s(DSPVector(in + off))) * DSPVector(gain[v]);
-        store(y, out + off);
-      }
+    for (int r = 0; r < repeats; ++r)
+      for (int t = 0; t < T; ++t)
+        for (int v = v0; v < v1; ++v)
+        {
+          const size_t off = ((size_t)t * V + v) * 64;
+          DSPVector y = voices[v].lp(voices[v].s(DSPVector(in + off))) * DSPVector(gain[v]);
+          store(y, out + off);
+        }
   };
   auto t0 = std::chrono::steady_clock::now();
   if (nthreads == 1)

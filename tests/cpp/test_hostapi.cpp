@@ -1,0 +1,152 @@
+// tests/cpp/test_hostapi.cpp -- the reference's own hot-path assertions, restated against the
+// C++ host mirror (include/mlb200.hpp) of the B200 engine.  Mirrors:
+//   Tests/dspGensTest.cpp:15-31   (SineGen one cycle ends at 0)
+//   Tests/dspOpsTest.cpp:77-106   (precision of sin/cos/log/exp, precise < 2e-6, approx < 2e-4)
+//   Tests/dspOpsTest.cpp:148-165  (lerp, fractionalPart)
+//   Tests/dspOpsTest.cpp:273-293  (Bank<SineGen, 5> runs)
+// plus the SURVEY 8c pinned value of 0.5 * Lopass{0.1,1.0}(SineGen.clear()(440/48000)).
+// Exit code 0 = all assertions hold; 77 = no GPU (the library refuses to compute on the CPU).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "mlb200.hpp"
+
+using namespace mlb;
+
+static int g_checks = 0, g_fail = 0;
+#define REQUIRE(cond)                                                   \
+  do                                                                    \
+  {                                                                     \
+    ++g_checks;                                                         \
+    if (!(cond))                                                        \
+    {                                                                   \
+      ++g_fail;                                                         \
+      std::printf("REQUIRE failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); \
+    }                                                                   \
+  } while (0)
+
+static DSPVector rangeClosed(float start, float end)  // reference MLDSPOps.h:978-982
+{
+  DSPVector v;
+  const float interval = (end - start) / (kFloatsPerDSPVector - 1.f);
+  for (size_t i = 0; i < kFloatsPerDSPVector; ++i) v[i] = (float)i * interval + start;
+  return v;
+}
+static float maxAbsDiff(const DSPVector& a, const DSPVector& b, const DSPVector* domain = nullptr)
+{
+  float m = 0.f;
+  for (size_t i = 0; i < kFloatsPerDSPVector; ++i)
+  {
+    if (domain && !((*domain)[i] > 0.f)) continue;
+    const float d = std::fabs(a[i] - b[i]);
+    if (d > m) m = d;
+  }
+  return m;
+}
+
+int main()
+{
+  if (mlb_device_count() < 1)
+  {
+    // no silent fallback: creating a bank must fail loudly
+    Graph g;
+    g.output(g.sine(g.input(0)));
+    bool threw = false;
+    try { DeviceBank b(g, 4); } catch (const Error& e) { threw = (e.code == MLB_ERR_NO_DEVICE); }
+    std::printf("no GPU visible: DeviceBank creation %s\n", threw ? "failed loudly (ok)" : "DID NOT FAIL");
+    return threw ? 77 : 1;
+  }
+
+  // ---- dsp_gens: one cycle of sine should end at 0 ----
+  {
+    Graph g;
+    const int f = g.input(0), s = g.sine(f);
+    g.output(s);
+    DeviceBank bank(g, 1);
+    bank.setStateWord(s, 0, 0, 0xC0000000u);  // SineGen::clear()
+    bank.commit();
+    DSPVector v1 = bank(DSPVector(1.f / kFloatsPerDSPVector));
+    const float epsilon = std::pow(10.f, -120.f / 20.f);  // dBToAmp(-120)
+    REQUIRE(std::fabs(v1[kFloatsPerDSPVector - 1]) < epsilon);
+  }
+
+  // ---- pinned reference value: 0.5 * Lopass{makeCoeffs(0.1, 1.0)}(SineGen.clear()(440/48000)) ----
+  {
+    Graph g;
+    const int f = g.input(0), s = g.sine(f), lp = g.lopass(s), k = g.param(), y = g.multiply(lp, k);
+    g.output(y);
+    DeviceBank bank(g, 1);
+    float c[3];
+    mlb_coeffs_lopass(0.1f, 1.0f, c);
+    bank.setCoeffs(lp, 0, c, 3);
+    bank.setParam(k, 0, 0.5f);
+    bank.setStateWord(s, 0, 0, 0xC0000000u);
+    bank.commit();
+    REQUIRE(std::strncmp(bank.kernelName(), "fused:", 6) == 0);
+    DSPVector out = bank(DSPVector(440.f / 48000.f));
+    REQUIRE(out[0] == -0x1.09e64p-9f);
+    REQUIRE(out[1] == -0x1.5cd8fap-7f);
+    REQUIRE(out[63] == 0x1.b2539p-3f);
+  }
+
+  // ---- dsp_ops precision: precise < 2e-6, approx < 2e-4 vs libm on rangeClosed(-pi, pi) ----
+  {
+    const float kPi = 3.1415926535897932384626433f;
+    DSPVector a = rangeClosed(-kPi, kPi);
+    DSPVector nat;
+    for (size_t i = 0; i < kFloatsPerDSPVector; ++i) nat[i] = std::sin(a[i]);
+    REQUIRE(maxAbsDiff(nat, sin(a)) < 2e-6f);
+    REQUIRE(maxAbsDiff(nat, sinApprox(a)) < 2e-4f);
+    for (size_t i = 0; i < kFloatsPerDSPVector; ++i) nat[i] = std::cos(a[i]);
+    REQUIRE(maxAbsDiff(nat, cos(a)) < 2e-6f);
+    REQUIRE(maxAbsDiff(nat, cosApprox(a)) < 2e-4f);
+    for (size_t i = 0; i < kFloatsPerDSPVector; ++i) nat[i] = std::exp(a[i]);
+    REQUIRE(maxAbsDiff(nat, exp(a)) < 2e-6f);
+    REQUIRE(maxAbsDiff(nat, expApprox(a)) < 2e-4f);
+    for (size_t i = 0; i < kFloatsPerDSPVector; ++i) nat[i] = a[i] > 0 ? std::log(a[i]) : 0.f;
+    REQUIRE(maxAbsDiff(nat, log(a), &a) < 2e-6f);  // x <= 0 drops out of the reference's max() too
+    REQUIRE(maxAbsDiff(nat, logApprox(a), &a) < 2e-4f);
+  }
+
+  // ---- lerp / convert ----
+  {
+    DSPVector a;
+    for (size_t i = 0; i < kFloatsPerDSPVector; ++i) a[i] = (float)i;
+    DSPVector b(0.f);
+    DSPVector c = lerp(a, b, DSPVector(0.5f));
+    REQUIRE(c[kFloatsPerDSPVector - 1] == (kFloatsPerDSPVector - 1) * 0.5f);
+    DSPVector fa = fractionalPart(DSPVector(1.25f)), fb = fractionalPart(DSPVector(-1.25f));
+    REQUIRE(fa[kFloatsPerDSPVector - 1] == -fb[kFloatsPerDSPVector - 1]);
+    // operators with implicit float -> DSPVector conversion (MLDSPOps.h:157)
+    DSPVector d = a * 2.f + 1.f;
+    REQUIRE(d[10] == 21.f);
+    DSPVectorArray<2> e(3.f);
+    REQUIRE((e * e)[100] == 9.f);
+  }
+
+  // ---- Bank<SineGen, 5>-shaped bank: rows are independent voices ----
+  {
+    Graph g;
+    const int f = g.input(0), s = g.sine(f);
+    g.output(s);
+    DeviceBank bank(g, 5);
+    for (int r = 0; r < 5; ++r) bank.setStateWord(s, 0, r, 0xC0000000u);
+    bank.commit();
+    DSPVectorArray<5> freqs;
+    for (int r = 0; r < 5; ++r) freqs.row(r) = DSPVector(0.01f * (r + 1));
+    DSPVectorArray<5> y = bank(freqs);
+    DeviceBank one(g, 1);
+    one.setStateWord(s, 0, 0, 0xC0000000u);
+    one.commit();
+    DSPVector y3 = one(DSPVector(0.04f));
+    REQUIRE(y.constRow(3) == y3);  // row 3 of the bank == a single voice at the same frequency
+    REQUIRE(!(y.constRow(0) == y.constRow(1)));
+    bank.readState();
+    REQUIRE(bank.stateWord(s, 0, 2) != 0xC0000000u);  // phase advanced
+  }
+
+  std::printf("%s: %d assertions, %d failed, %lld kernels launched\n", g_fail ? "FAILED" : "ALL PASSED", g_checks,
+              g_fail, mlb_kernel_launches());
+  return g_fail ? 1 : 0;
+}
