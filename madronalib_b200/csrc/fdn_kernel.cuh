@@ -1,27 +1,389 @@
-// fdn_kernel.cuh -- fused 3-operator FM -> FDN<8> kernel (config 4).  Placeholder until the
-// specialised kernel lands: graphs of this shape run through the generic interpreter.
+// fdn_kernel.cuh -- fused [3-operator FM ->] FDN<8> kernel (config 4; reference
+// MLDSPFilters.h:1162-1239 FDN<SIZE>, :801-914 IntegerDelay, MLDSPGens.h:373-381 SineGen).
+//
+// Decomposition: one LANE per (voice, delay line): 8 lanes per voice, 4 voices per warp, warps
+// independent.  Delay rings live in HBM as [voice][line][R] f32 (R = 2^k >= maxlen + 64), the
+// genuinely bandwidth-heavy part of the path: 8 x (256 B read + 256 B write) per voice-block
+// = 64 B/voice-sample of the 76 B/voice-sample total.  Per 64-sample block a warp
+//   0. waits for its lanes' ring reads (cp.async.bulk 1-D, 16-byte-aligned 272 B over-read of
+//      the 64-sample window that starts `len` samples behind the write position) and the
+//      voices' input rows;
+//   G. generator: the 8 lanes of a voice split the 64 samples (8 each); PhasorGen's u32 phase
+//      accumulation is an integer prefix sum, so it is done exactly with a per-lane prefix and
+//      a 3-step shuffle scan; three sines (two modulators, carrier) -> x row in shared memory;
+//   B. Householder mixing: lanes re-distribute (lane k takes samples k, k+8, ...) and read all
+//      8 lines of their samples from shared memory, so the sums  sumOfDelays, sumL, sumR are
+//      formed in the reference's left-to-right order in registers, no shuffles;
+//      v = d - (2/8) * sum is written back in place, sumL / sumR rows are built;
+//   C. per line again: OnePole recurrence, * feedback gain, + x  -> next block's delay input,
+//      written in place (LDS.128 / STS.128, bank-conflict free with the 68-float row stride);
+//   S. each lane bulk-stores its 256 B vector into its ring at w + 64, two lanes store the
+//      L / R rows; after the stores completed the next block's ring reads are issued (short
+//      delays read what was just written).
+// The reference's mDelayInputVectors (the vector a block hands to the next one) is never
+// materialised separately: it is exactly what the next block writes into the ring at its write
+// position, so it is written there directly at the end of the block that produces it.
 #pragma once
 #include <vector>
 
 #include "ops.cuh"
+#include "tma.cuh"
 
 namespace mlb
 {
 struct FdnArgs
 {
-  int dummy;
+  int gen;                                  // 0: x = input plane, 1: 3-operator FM of the input plane
+  int st_ph1, st_ph2, st_phc, st_y1;        // SoA state word indices (y1: first of 8)
+  int co_r1, co_r2, co_i1, co_i2, co_one;   // PARAM coef word indices
+  int co_fdn;                               // first of the 32 FDN8 coef words
+  int in_plane;
 };
 
-inline bool match_fm3_fdn8(const std::vector<mlb_node>&, const std::vector<int32_t>&,
-                           const std::vector<int32_t>&, const std::vector<int32_t>&, FdnArgs*)
+struct FdnLaunch
 {
-  return false;
+  FdnArgs f;
+  uint32_t* state;
+  const float* coef;
+  float* ring;
+  const float* in;  // [T][n_in][V][64]
+  float* out;       // [T][2][V][64] (L plane, R plane)
+  int ring_len;
+  long long blocks_done;
+  int V, T, n_in;
+};
+
+constexpr int kFdnRow = 68;                        // floats per delay row: 16-B aligned, = 4 mod 32
+constexpr int kFdnVoice = 8 * kFdnRow + 3 * 64 + 8;  // d rows + f/L row + x row + R row (+pad: = 8 mod 32)
+constexpr int kFdnWarpsPerCta = 4;
+
+template <bool EX>
+__global__ void __launch_bounds__(kFdnWarpsPerCta * 32) fdn8_kernel(const FdnLaunch a)
+{
+  extern __shared__ __align__(16) float fdn_smem[];
+  using ar = A<EX>;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int vq = lane >> 3, k = lane & 7;  // voice within the warp, delay line / sample slot
+  const int v = (blockIdx.x * kFdnWarpsPerCta + warp) * 4 + vq;
+  if ((blockIdx.x * kFdnWarpsPerCta + warp) * 4 >= a.V) return;  // warp-uniform
+  const bool live = v < a.V;
+  const unsigned gmask = 0xffu << (vq * 8);  // the 8 lanes of this voice (documentation only)
+  (void)gmask;
+
+  float* vbase = fdn_smem + (size_t)(warp * 4 + vq) * kFdnVoice;
+  float* drow = vbase + k * kFdnRow;        // this lane's delay row (phase C view)
+  float* frow = vbase + 8 * kFdnRow;        // input row, later the sumL row
+  float* xrow = frow + 64;
+  float* rrow = xrow + 64;
+  const uint32_t s_vbase = smem_u32(vbase), s_drow = smem_u32(drow), s_frow = smem_u32(frow),
+                 s_xrow = smem_u32(xrow), s_rrow = smem_u32(rrow);
+  const uint32_t bar = smem_u32(fdn_smem + (size_t)kFdnWarpsPerCta * 4 * kFdnVoice) + warp * 8u;
+
+  if (lane == 0)
+  {
+    mbar_init(bar, 32);
+    fence_mbar_init();
+  }
+  __syncwarp();
+
+  // ---- per-lane constants and state ----
+  const size_t V = (size_t)a.V;
+  const int vv = live ? v : 0;
+  const float a0 = a.coef[(size_t)(a.f.co_fdn + k) * V + vv];
+  const float b1 = a.coef[(size_t)(a.f.co_fdn + 8 + k) * V + vv];
+  const float gn = a.coef[(size_t)(a.f.co_fdn + 16 + k) * V + vv];
+  const uint32_t len = (uint32_t)(int)a.coef[(size_t)(a.f.co_fdn + 24 + k) * V + vv];
+  float y1 = u2f(a.state[(size_t)(a.f.st_y1 + k) * V + vv]);
+  float r1 = 0, r2 = 0, i1 = 0, i2 = 0, one = 0;
+  uint32_t ph1 = 0, ph2 = 0, phc = 0;
+  if (a.f.gen == 1)
+  {
+    r1 = a.coef[(size_t)a.f.co_r1 * V + vv], r2 = a.coef[(size_t)a.f.co_r2 * V + vv];
+    i1 = a.coef[(size_t)a.f.co_i1 * V + vv], i2 = a.coef[(size_t)a.f.co_i2 * V + vv];
+    one = a.coef[(size_t)a.f.co_one * V + vv];
+    ph1 = a.state[(size_t)a.f.st_ph1 * V + vv], ph2 = a.state[(size_t)a.f.st_ph2 * V + vv];
+    phc = a.state[(size_t)a.f.st_phc * V + vv];
+  }
+  const uint32_t mask = (uint32_t)a.ring_len - 1u;
+  float* ring = a.ring + ((size_t)vv * 8 + k) * a.ring_len;
+
+  // issue this lane's loads for block t: the 64-sample window that starts len behind w_t
+  auto issue_loads = [&](int t) -> uint32_t
+  {
+    const uint32_t w = (uint32_t)(((a.blocks_done + t) * MLB_BLOCK) & (long long)mask);
+    const uint32_t r = (w - len) & mask;
+    const uint32_t al = r & ~3u;
+    uint32_t bytes = 0;
+    if (live)
+    {
+      const uint32_t first = min((uint32_t)kFdnRow, (uint32_t)a.ring_len - al);  // floats before the wrap
+      bytes = kFdnRow * 4;
+      if (k == 0) bytes += MLB_BLOCK * 4;
+      mbar_arrive_expect_tx(bar, bytes);
+      bulk_load_1d(s_drow, ring + al, first * 4, bar);
+      if (first < (uint32_t)kFdnRow) bulk_load_1d(s_drow + first * 4, ring, (kFdnRow - first) * 4, bar);
+      if (k == 0)
+        bulk_load_1d(a.f.gen == 1 ? s_frow : s_xrow,
+                     a.in + (((size_t)t * a.n_in + a.f.in_plane) * V + v) * MLB_BLOCK, MLB_BLOCK * 4, bar);
+    }
+    else
+    {
+      mbar_arrive_expect_tx(bar, 0);
+    }
+    return r & 3u;  // offset of the window inside the over-read row
+  };
+
+  uint32_t off = issue_loads(0);
+  uint32_t parity = 0;
+  for (int t = 0; t < a.T; ++t)
+  {
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+
+    // ---- G: three sines for samples 8k .. 8k+7 of this voice ----
+    if (a.f.gen == 1)
+    {
+      float f[8];
+      {
+        const float4 q0 = lds128(s_frow + (uint32_t)k * 32u), q1 = lds128(s_frow + (uint32_t)k * 32u + 16u);
+        f[0] = q0.x, f[1] = q0.y, f[2] = q0.z, f[3] = q0.w, f[4] = q1.x, f[5] = q1.y, f[6] = q1.z, f[7] = q1.w;
+      }
+      // inclusive integer prefix of the per-sample phase increments, then across the 8 lanes
+      auto scan_phases = [&](const float (&freq)[8], uint32_t& ph0, uint32_t (&phase)[8])
+      {
+        uint32_t run = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+        {
+          run += (uint32_t)cvt_round(ar::mul(freq[j], 4294967296.0f));
+          phase[j] = run;
+        }
+        uint32_t sc = run;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1)
+        {
+          const uint32_t up = __shfl_up_sync(0xffffffffu, sc, d, 8);
+          if (k >= d) sc += up;
+        }
+        const uint32_t excl = sc - run + ph0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) phase[j] += excl;
+        ph0 += __shfl_sync(0xffffffffu, sc, 7, 8);
+      };
+      float fa[8], fb[8];
+      uint32_t pa[8], pb[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fa[j] = ar::mul(f[j], r1), fb[j] = ar::mul(f[j], r2);
+      scan_phases(fa, ph1, pa);
+      scan_phases(fb, ph2, pb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+      {
+        const float m1 = phase_to_sine<EX>(pa[j]), m2 = phase_to_sine<EX>(pb[j]);
+        const float bsum = ar::add(ar::add(one, ar::mul(m1, i1)), ar::mul(m2, i2));
+        fa[j] = ar::mul(f[j], bsum);
+      }
+      scan_phases(fa, phc, pa);
+      float4 x0, x1;
+      x0.x = phase_to_sine<EX>(pa[0]), x0.y = phase_to_sine<EX>(pa[1]);
+      x0.z = phase_to_sine<EX>(pa[2]), x0.w = phase_to_sine<EX>(pa[3]);
+      x1.x = phase_to_sine<EX>(pa[4]), x1.y = phase_to_sine<EX>(pa[5]);
+      x1.z = phase_to_sine<EX>(pa[6]), x1.w = phase_to_sine<EX>(pa[7]);
+      sts128(s_xrow + (uint32_t)k * 32u, x0);
+      sts128(s_xrow + (uint32_t)k * 32u + 16u, x1);
+    }
+
+    // ---- B: Householder mixing, lane k owns samples k, k+8, ..., k+56 of its voice ----
+    {
+      uint32_t offs[8];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) offs[n] = __shfl_sync(0xffffffffu, off, n, 8);
+      float d[8][8];
+#pragma unroll
+      for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          d[n][j] = lds32(s_vbase + (uint32_t)(n * kFdnRow + k + 8 * j) * 4u + offs[n] * 4u);
+      __syncwarp();  // every lane holds its samples before rows are overwritten in place
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+      {
+        // DSPVector sumR, sumL, sumOfDelays start from zero and add lines left to right (F:1204-1227)
+        float sumR = 0.f, sumL = 0.f, sum = 0.f;
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+        {
+          if (n & 1)
+            sumL = __fadd_rn(sumL, d[n][j]);
+          else
+            sumR = __fadd_rn(sumR, d[n][j]);
+          sum = __fadd_rn(sum, d[n][j]);
+        }
+        sum = __fmul_rn(sum, 0.25f);  // 2 / SIZE
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+          sts32(s_vbase + (uint32_t)(n * kFdnRow + k + 8 * j) * 4u, __fsub_rn(d[n][j], sum));
+        sts32(s_frow + (uint32_t)(k + 8 * j) * 4u, sumL);
+        sts32(s_rrow + (uint32_t)(k + 8 * j) * 4u, sumR);
+      }
+    }
+    __syncwarp();
+
+    // ---- C: per line: OnePole, feedback gain, + x -> next block's delay input, in place ----
+#pragma unroll 4
+    for (int q = 0; q < 16; ++q)
+    {
+      const float4 vq4 = lds128(s_drow + (uint32_t)q * 16u);
+      const float4 xq4 = lds128(s_xrow + (uint32_t)q * 16u);
+      float4 u;
+      y1 = ar::mul_add_mul(a0, vq4.x, b1, y1);
+      u.x = ar::add(ar::mul(y1, gn), xq4.x);
+      y1 = ar::mul_add_mul(a0, vq4.y, b1, y1);
+      u.y = ar::add(ar::mul(y1, gn), xq4.y);
+      y1 = ar::mul_add_mul(a0, vq4.z, b1, y1);
+      u.z = ar::add(ar::mul(y1, gn), xq4.z);
+      y1 = ar::mul_add_mul(a0, vq4.w, b1, y1);
+      u.w = ar::add(ar::mul(y1, gn), xq4.w);
+      sts128(s_drow + (uint32_t)q * 16u, u);
+    }
+
+    // ---- S: rings and outputs ----
+    fence_proxy_async();
+    __syncwarp();
+    if (live)
+    {
+      const uint32_t wn = (uint32_t)(((a.blocks_done + t + 1) * MLB_BLOCK) & (long long)mask);
+      bulk_store_1d(ring + wn, s_drow, MLB_BLOCK * 4);
+      if (k == 0) bulk_store_1d(a.out + (((size_t)t * 2 + 0) * V + v) * MLB_BLOCK, s_frow, MLB_BLOCK * 4);
+      if (k == 1) bulk_store_1d(a.out + (((size_t)t * 2 + 1) * V + v) * MLB_BLOCK, s_rrow, MLB_BLOCK * 4);
+      bulk_commit();
+      bulk_wait_all<0>();  // written data is visible before the next block's (possibly short) reads
+    }
+    __syncwarp();
+    if (t + 1 < a.T) off = issue_loads(t + 1);
+  }
+
+  if (live)
+  {
+    a.state[(size_t)(a.f.st_y1 + k) * V + v] = f2u(y1);
+    if (a.f.gen == 1 && k == 0)
+    {
+      a.state[(size_t)a.f.st_ph1 * V + v] = ph1;
+      a.state[(size_t)a.f.st_ph2 * V + v] = ph2;
+      a.state[(size_t)a.f.st_phc * V + v] = phc;
+    }
+  }
 }
 
-inline int launch_fm3_fdn8(const FdnArgs&, bool, uint32_t*, const float*, float*, float*, int,
-                           long long, const float*, float*, float*, int, int, int, int,
-                           cudaStream_t)
+// Mix-bus partials for kernels that do not produce them in their epilogue:
+// partial[p][g][n] = sum over the 32 voices of group g (voice order, from +0) of plane[p][v][n].
+__global__ void __launch_bounds__(64) mix_partial_from_planes_kernel(const float* __restrict__ planes,
+                                                                      float* __restrict__ partial, int V,
+                                                                      int n_groups)
 {
-  return MLB_ERR_UNSUPPORTED;
+  const int g = blockIdx.x, p = blockIdx.y, n = threadIdx.x;
+  const float* src = planes + ((size_t)p * V + (size_t)g * 32) * MLB_BLOCK + n;
+  const int cnt = min(32, V - g * 32);
+  float acc = 0.f;
+  for (int r = 0; r < cnt; ++r) acc = __fadd_rn(acc, src[(size_t)r * MLB_BLOCK]);
+  partial[((size_t)p * n_groups + g) * MLB_BLOCK + n] = acc;
+}
+
+// ---- host side: recognise INPUT [-> 3-op FM] -> FDN8 (+ FDN8_R) ----
+inline bool match_fm3_fdn8(const std::vector<mlb_node>& N, const std::vector<int32_t>& outs,
+                           const std::vector<int32_t>& st_off, const std::vector<int32_t>& co_off,
+                           FdnArgs* f)
+{
+  if (outs.size() != 2) return false;
+  const int nl = outs[0], nr = outs[1];
+  if (N[nl].op != MLB_OP_FDN8 || N[nr].op != MLB_OP_FDN8_R || N[nr].in[0] != nl) return false;
+  std::vector<char> used(N.size(), 0);
+  used[nl] = used[nr] = 1;
+  f->st_y1 = st_off[nl];
+  f->co_fdn = co_off[nl];
+  const int x = N[nl].in[0];
+  used[x] = 1;
+  auto all_used = [&]()
+  {
+    for (char u : used)
+      if (!u) return false;
+    return true;
+  };
+  if (N[x].op == MLB_OP_INPUT)
+  {
+    f->gen = 0;
+    f->in_plane = N[x].iarg;
+    return all_used();
+  }
+  // carrier = SINE(MULTIPLY(f, ADD(ADD(one, MULTIPLY(m1, i1)), MULTIPLY(m2, i2))))
+  auto is = [&](int n, int op) { return n >= 0 && N[n].op == op; };
+  // split a commutative binary node into (the operand with op `want`, the other one)
+  auto split = [&](int node, int want, int* a, int* b) -> bool
+  {
+    const int p = N[node].in[0], q = N[node].in[1];
+    if (is(p, want) && !is(q, want)) { *a = p, *b = q; return true; }
+    if (is(q, want) && !is(p, want)) { *a = q, *b = p; return true; }
+    return false;
+  };
+  if (!is(x, MLB_OP_SINE)) return false;
+  const int mulc = N[x].in[0];
+  if (!is(mulc, MLB_OP_MULTIPLY)) return false;
+  used[mulc] = 1;
+  int fin, bsum;
+  if (!split(mulc, MLB_OP_INPUT, &fin, &bsum)) return false;
+  if (!is(bsum, MLB_OP_ADD)) return false;
+  used[fin] = used[bsum] = 1;
+  // bsum = ADD(a1, mul2) with a1 = ADD(one, mul1): the reference order (one + m1*i1) + m2*i2
+  const int a1 = N[bsum].in[0], mul2 = N[bsum].in[1];
+  if (!is(a1, MLB_OP_ADD) || !is(mul2, MLB_OP_MULTIPLY)) return false;
+  const int onep = N[a1].in[0], mul1 = N[a1].in[1];
+  if (!is(onep, MLB_OP_PARAM) || !is(mul1, MLB_OP_MULTIPLY)) return false;
+  used[a1] = used[mul2] = used[onep] = used[mul1] = 1;
+  int s1, p1, s2, p2;
+  if (!split(mul1, MLB_OP_SINE, &s1, &p1) || !is(p1, MLB_OP_PARAM)) return false;
+  if (!split(mul2, MLB_OP_SINE, &s2, &p2) || !is(p2, MLB_OP_PARAM)) return false;
+  used[s1] = used[p1] = used[s2] = used[p2] = 1;
+  const int m1 = N[s1].in[0], m2 = N[s2].in[0];
+  if (!is(m1, MLB_OP_MULTIPLY) || !is(m2, MLB_OP_MULTIPLY)) return false;
+  used[m1] = used[m2] = 1;
+  int f1, q1, f2, q2;
+  if (!split(m1, MLB_OP_INPUT, &f1, &q1) || !is(q1, MLB_OP_PARAM) || f1 != fin) return false;
+  if (!split(m2, MLB_OP_INPUT, &f2, &q2) || !is(q2, MLB_OP_PARAM) || f2 != fin) return false;
+  used[q1] = used[q2] = 1;
+  if (!all_used()) return false;
+  f->gen = 1;
+  f->in_plane = N[fin].iarg;
+  f->st_ph1 = st_off[s1], f->st_ph2 = st_off[s2], f->st_phc = st_off[x];
+  f->co_r1 = co_off[q1], f->co_r2 = co_off[q2], f->co_i1 = co_off[p1], f->co_i2 = co_off[p2];
+  f->co_one = co_off[onep];
+  return true;
+}
+
+inline int launch_fm3_fdn8(const FdnArgs& f, bool exact, uint32_t* state, const float* coef, float* ring,
+                           float* /*carry*/, int ring_len, long long blocks_done, const float* in, float* out,
+                           int V, int T, int n_in, cudaStream_t stream)
+{
+  FdnLaunch a;
+  a.f = f;
+  a.state = state, a.coef = coef, a.ring = ring, a.in = in, a.out = out;
+  a.ring_len = ring_len, a.blocks_done = blocks_done;
+  a.V = V, a.T = T, a.n_in = n_in;
+  const int voices_per_cta = kFdnWarpsPerCta * 4;
+  const int n_ctas = (V + voices_per_cta - 1) / voices_per_cta;
+  const size_t smem = (size_t)kFdnWarpsPerCta * 4 * kFdnVoice * 4 + kFdnWarpsPerCta * 8;
+  cudaError_t e;
+  if (exact)
+  {
+    e = cudaFuncSetAttribute((const void*)fdn8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return MLB_ERR_CUDA;
+    fdn8_kernel<true><<<n_ctas, kFdnWarpsPerCta * 32, smem, stream>>>(a);
+  }
+  else
+  {
+    e = cudaFuncSetAttribute((const void*)fdn8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return MLB_ERR_CUDA;
+    fdn8_kernel<false><<<n_ctas, kFdnWarpsPerCta * 32, smem, stream>>>(a);
+  }
+  return cudaGetLastError() == cudaSuccess ? MLB_OK : MLB_ERR_CUDA;
 }
 }  // namespace mlb

@@ -847,6 +847,17 @@ static int env_int(const char* name, int dflt)
   return (s && *s) ? atoi(s) : dflt;
 }
 
+static int ensure_buf(float** p, size_t* cap, size_t bytes)
+{
+  if (bytes <= *cap) return MLB_OK;
+  cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  if (cudaMalloc(p, bytes) != cudaSuccess) return fail(MLB_ERR_ALLOC, "cudaMalloc of %zu B staging failed", bytes);
+  *cap = bytes;
+  return MLB_OK;
+}
+
 static int ensure_partial(mlb_graph* g, int T, int n_groups)
 {
   // per-group partials followed by the per-chunk scratch of mix_reduce_kernel
@@ -982,11 +993,24 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
   }
   else if (g->kind == KIND_FDN)
   {
-    rc = launch_fm3_fdn8(g->fargs, g->exact, g->d_state, g->d_coef, g->d_ring, g->d_carry,
-                         g->ring_len, g->blocks_done, in_dev, out_dev,
-                         mix_dev ? g->d_partial : nullptr, V, T, n_groups, g_sm_count, stream);
-    if (rc != MLB_OK) return fail(rc, "fm3_fdn8 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    // outputs are needed for the mix bus even when the caller does not want them
+    float* planes = out_dev;
+    if (!planes)
+    {
+      rc = ensure_buf(&g->d_out, &g->out_cap, (size_t)T * 2 * V * MLB_BLOCK * 4);
+      if (rc != MLB_OK) return rc;
+      planes = g->d_out;
+    }
+    rc = launch_fm3_fdn8(g->fargs, g->exact, g->d_state, g->d_coef, g->d_ring, g->d_carry, g->ring_len,
+                         g->blocks_done, in_dev, planes, V, T, std::max(1, n_in), stream);
+    if (rc != MLB_OK) return fail(rc, "fdn8 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     ++g_launches;
+    if (mix_dev)
+    {
+      mix_partial_from_planes_kernel<<<dim3(n_groups, T * 2), MLB_BLOCK, 0, stream>>>(planes, g->d_partial, V,
+                                                                                      n_groups);
+      ++g_launches;
+    }
   }
   else
   {
@@ -1030,17 +1054,6 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
     ++g_launches;
     CU_CHECK(cudaGetLastError());
   }
-  return MLB_OK;
-}
-
-static int ensure_buf(float** p, size_t* cap, size_t bytes)
-{
-  if (bytes <= *cap) return MLB_OK;
-  cudaFree(*p);
-  *p = nullptr;
-  *cap = 0;
-  if (cudaMalloc(p, bytes) != cudaSuccess) return fail(MLB_ERR_ALLOC, "cudaMalloc of %zu B staging failed", bytes);
-  *cap = bytes;
   return MLB_OK;
 }
 

@@ -218,6 +218,43 @@ def test_config4_fm3_fdn8(gpu, port):
     assert np.abs(go).max() > 0.1  # the reverb tail is really there
 
 
+@pytest.mark.parametrize("n_voices,n_blocks,splits", [(50, 20, (7, 13)), (4, 3, None), (130, 6, (1, 5))])
+def test_fdn8_fused_and_generic_agree_with_oracle(gpu, port, n_voices, n_blocks, splits):
+    """FM3 -> FDN8 on the fused kernel and on the graph interpreter, ragged voice counts,
+    delays shorter and longer than a block, several launches (ring write index carries over)."""
+    w = wl.config_4(n_voices)
+    inp = w.inputs(n_blocks)
+    po, pm, ps = port.run(w.spec, n_voices, n_blocks, inp, w.state, w.coef, want_mix=True, mix_mode=1)
+    for flags, kind in ((0, "fused:fm3_fdn8"), (gpu.FLAG_FORCE_GENERIC, "generic")):
+        go, gm, gs, name = run_gpu(gpu, w, n_blocks, inp, flags=flags, want_mix=True, splits=splits)
+        assert name == kind, name
+        assert_same_bits(go, po, kind + " out")
+        assert_same_bits(gm, pm, kind + " mix")
+        assert_state_equal(gs, ps, kind)
+
+
+def test_fdn8_on_external_input(gpu, port):
+    """INPUT -> FDN8: the reverb fed with external audio (NoiseGen rows, seed = voice index)."""
+    g = GraphSpec()
+    x = g.input(0)
+    fl = g.node("FDN8", x)
+    fr = g.node("FDN8_R", fl)
+    g.output(fl, fr)
+    V, T = 37, 9
+    coef = g.new_coefs(V)
+    for v in range(V):
+        coef[:, v] = gpu.coeffs_fdn8(wl.FDN_TIMES + 32 * (v % 5), wl.FDN_CUTOFFS, np.full(8, 0.6, np.float32))
+    rng = np.random.default_rng(5)
+    inp = (rng.standard_normal((T, 1, V, 64)) * 0.1).astype(np.float32)
+    st = g.new_state(V)
+    w = wl.Workload("fdn_in", g, V, coef, st)
+    po, _, ps = port.run(g, V, T, inp, st, coef)
+    go, _, gs, name = run_gpu(gpu, w, T, inp, splits=(4, 5))
+    assert name == "fused:fm3_fdn8", name
+    assert_same_bits(go, po)
+    assert_state_equal(gs, ps)
+
+
 def test_config5_chain256(gpu, port):
     V, T = 40, 3
     w = wl.config_5(V, 256)

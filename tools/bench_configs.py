@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Kernel-resident timing of the other BASELINE.json configurations (2-5) at full size.
+
+    python tools/bench_configs.py [--steps K] [--only 2,3,4,5]
+
+Prints one JSON line per configuration: kernel name, mean CUDA-event kernel time, algorithmic
+bytes per launch, achieved GB/s and fraction of the measured HBM peak.
+Not the headline benchmark (that is bench.py / config A).
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+
+    from madronalib_b200 import api, workloads as wl
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--only", default="2,3,4,5")
+    ap.add_argument("--generic", action="store_true", help="force the graph interpreter kernel")
+    args = ap.parse_args()
+    only = set(args.only.split(","))
+    api.init(0)
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        peak = 6650.0
+    dev = torch.device("cuda", 0)
+    cfgs = []
+    if "2" in only:
+        for kind in ("lopass", "hipass", "bell"):
+            cfgs.append(("config2_" + kind, wl.config_2(kind, 4096), 64, lambda V, T: 8.0 * V * T * 64))
+    if "3" in only:
+        cfgs.append(("config3", wl.config_3(65536), 64, lambda V, T: 8.0 * V * T * 64))
+    if "4" in only:
+        # ring 8 x (256 B r + 256 B w) + freq row in + 2 rows out per voice-block = 4864 B
+        cfgs.append(("config4", wl.config_4(16384), 16, lambda V, T: 4864.0 * V * T))
+    if "5" in only:
+        cfgs.append(("config5", wl.config_5(1024, 256), 16, lambda V, T: 256.0 * V * T))
+    for name, w, T, alg in cfgs:
+        V = w.n_voices
+        g = api.VoiceGraph(w.spec, V, api.FLAG_FORCE_GENERIC if args.generic else 0)
+        g.set_coefs(w.coef)
+        g.set_state(w.state)
+        inp = w.inputs(T)
+        d_in = torch.from_numpy(inp).to(dev) if inp is not None else None
+        d_out = torch.empty((T, w.spec.n_out, V, 64), dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()
+        sh = torch.cuda.current_stream().cuda_stream
+        for _ in range(3):
+            g.process_device(d_in, d_out, None, T, sh)
+        ms = []
+        for _ in range(args.steps):
+            g.process_device(d_in, d_out, None, T, sh)
+            ms.append(g.last_kernel_ms())
+        kms = float(np.mean(ms))
+        b = alg(V, T)
+        print(json.dumps({"config": name, "kernel": g.kernel_name, "voices": V, "blocks": T,
+                          "kernel_ms": kms, "voice_samples_per_s": V * T * 64 / (kms * 1e-3),
+                          "algorithmic_bytes": b, "achieved_gbs": b / (kms * 1e-3) / 1e9,
+                          "frac_of_measured_hbm_peak": b / (kms * 1e-3) / 1e9 / peak,
+                          "delay_memory_mb": g.delay_bytes / 1e6}), flush=True)
+        g.close()
+        del d_in, d_out
+
+
+if __name__ == "__main__":
+    main()
