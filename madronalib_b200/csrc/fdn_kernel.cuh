@@ -257,7 +257,12 @@ __global__ void __launch_bounds__(kFdnWarpsPerCta * 32) fdn8_kernel(const FdnLau
       if (k == 0) bulk_store_1d(a.out + (((size_t)t * 2 + 0) * V + v) * MLB_BLOCK, s_frow, MLB_BLOCK * 4);
       if (k == 1) bulk_store_1d(a.out + (((size_t)t * 2 + 1) * V + v) * MLB_BLOCK, s_rrow, MLB_BLOCK * 4);
       bulk_commit();
-      bulk_wait_all<0>();  // written data is visible before the next block's (possibly short) reads
+      // A delay shorter than a block reads what this block has just written: wait until the
+      // store is globally performed.  Longer delays only need the row buffer back.
+      if (len < (uint32_t)MLB_BLOCK)
+        bulk_wait_all<0>();
+      else
+        bulk_wait_read<0>();
     }
     __syncwarp();
     if (t + 1 < a.T) off = issue_loads(t + 1);
