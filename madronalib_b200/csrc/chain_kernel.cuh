@@ -61,6 +61,20 @@ __host__ __device__ constexpr int op_nc(int op)
   return 0;
 }
 
+__host__ __device__ constexpr int op_nin(int op)
+{
+  switch (op)
+  {
+#define MLB_X_NI(NAME, id, nin, nst, nco) \
+  case id: return nin;
+    MLB_OP_TABLE(MLB_X_NI)
+#undef MLB_X_NI
+  }
+  return 0;
+}
+// the op table again, for dispatching the stateless elementwise ops
+#define MLB_OP_TABLE_STATELESS(X) MLB_OP_TABLE(X)
+
 enum ChainSrc
 {
   SRC_INPUT = 0,  // generator/filter input = external signal plane (Contract R)

@@ -1,21 +1,23 @@
 // generic_kernel.cuh -- graph interpreter: evaluates ANY voice graph (the "procs" launcher,
 // reference stub source/procs/MLProcMultiply.cpp:29-46) in one kernel launch per call, for
 // graphs that have no fused specialisation.  Lane per voice, warp per 32 voices; the rows a
-// node produces live in shared memory as [slot][sample][lane] (lane innermost, 33-word
-// stride: every scalar LDS/STS is bank-conflict free); stateful nodes keep their state in registers across
+// node produces live in shared memory as [slot][lane][68 floats] (per-lane rows walked with
+// LDS.128 / STS.128, bank-conflict free); stateful nodes keep their state in registers across
 // the 64-sample loop and read/write the SoA state once per block.  The op switch is hoisted
-// out of the sample loop for stateful nodes; node descriptors are read through the
-// read-only path.  Results are identical to the fused kernels (same device functions).
+// out of the sample loop for every node kind (one specialised row loop per op); node
+// descriptors are read through the read-only path.  Results are identical to the fused kernels (same device functions).
 #pragma once
 #include "ops.cuh"
 #include "tma.cuh"
 
 namespace mlb
 {
-// rows live in shared memory as [slot][sample][33 words]: the odd stride keeps both the
-// per-lane walk ([n][lane]) and the mix-bus column walk ([n = lane][voice]) conflict free
-constexpr uint32_t kRowStride = 33u * 4u;
-constexpr uint32_t kSlotBytes = MLB_BLOCK * kRowStride;
+// rows live in shared memory as [slot][lane][68 floats]: each lane walks its own row with
+// LDS.128 / STS.128 (row stride 68 words = 4 mod 32 -> the 8 lanes of a quarter-warp cover all
+// 32 banks), and the mix-bus column walk ([voice rr][sample = lane]) is conflict free too
+constexpr uint32_t kRowFloats = 68u;
+constexpr uint32_t kRowStride = kRowFloats * 4u;      // bytes between lanes
+constexpr uint32_t kSlotBytes = 32u * kRowStride;     // one row slot for a 32-voice group
 
 enum
 {
@@ -55,10 +57,14 @@ struct GenericArgs
 
 struct RowRef
 {
-  uint32_t addr;  // shared address of [sample 0][this lane], stride kRowStride per sample
+  uint32_t addr;  // shared address of this lane's row
   float k;
   bool is_row;
-  MLB_DEV float get(int n) const { return is_row ? lds32(addr + (uint32_t)n * kRowStride) : k; }
+  MLB_DEV float get(int n) const { return is_row ? lds32(addr + (uint32_t)n * 4u) : k; }
+  MLB_DEV float4 get4(int q) const
+  {
+    return is_row ? lds128(addr + (uint32_t)q * 16u) : make_float4(k, k, k, k);
+  }
 };
 
 template <int OP, bool EX>
@@ -72,9 +78,17 @@ MLB_DEV void run_filter_node(const GNode& nd, const GenericArgs& a, int v, bool 
   for (int i = 0; i < NS; ++i) st[i] = live ? a.state[(size_t)(nd.st_off + i) * a.V + v] : 0u;
 #pragma unroll
   for (int i = 0; i < NC; ++i) co[i] = live ? a.coef[(size_t)(nd.co_off + i) * a.V + v] : 0.f;
-#pragma unroll 4
-  for (int n = 0; n < MLB_BLOCK; ++n)
-    sts32(out_addr + (uint32_t)n * kRowStride, filter_tick<EX>(OP, x.get(n), st, co));
+#pragma unroll 2
+  for (int q = 0; q < 16; ++q)
+  {
+    const float4 xi = x.get4(q);
+    float4 y;
+    y.x = filter_tick<EX>(OP, xi.x, st, co);
+    y.y = filter_tick<EX>(OP, xi.y, st, co);
+    y.z = filter_tick<EX>(OP, xi.z, st, co);
+    y.w = filter_tick<EX>(OP, xi.w, st, co);
+    sts128(out_addr + (uint32_t)q * 16u, y);
+  }
 #pragma unroll
   for (int i = 0; i < NS; ++i)
     if (live) a.state[(size_t)(nd.st_off + i) * a.V + v] = st[i];
@@ -86,12 +100,56 @@ MLB_DEV void run_gen_node(const GNode& nd, const GenericArgs& a, int v, bool liv
 {
   uint32_t st[1];
   st[0] = live ? a.state[(size_t)nd.st_off * a.V + v] : 0u;
-#pragma unroll 4
-  for (int n = 0; n < MLB_BLOCK; ++n)
-    sts32(out_addr + (uint32_t)n * kRowStride,
-          gen_tick<EX>(OP, OP == MLB_OP_NOISE ? 0.f : f.get(n), OP == MLB_OP_PULSE ? w.get(n) : 0.f,
-                       st));
+#pragma unroll 2
+  for (int q = 0; q < 16; ++q)
+  {
+    const float4 fi = (OP == MLB_OP_NOISE) ? make_float4(0.f, 0.f, 0.f, 0.f) : f.get4(q);
+    const float4 wi = (OP == MLB_OP_PULSE) ? w.get4(q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 y;
+    y.x = gen_tick<EX>(OP, fi.x, wi.x, st);
+    y.y = gen_tick<EX>(OP, fi.y, wi.y, st);
+    y.z = gen_tick<EX>(OP, fi.z, wi.z, st);
+    y.w = gen_tick<EX>(OP, fi.w, wi.w, st);
+    sts128(out_addr + (uint32_t)q * 16u, y);
+  }
   if (live) a.state[(size_t)nd.st_off * a.V + v] = st[0];
+}
+
+// stateless elementwise node with the op known at compile time (the switch in op_apply folds)
+template <int OP, bool EX>
+MLB_DEV void run_stateless_node(RowRef x, RowRef b, RowRef c, uint32_t out_addr)
+{
+  constexpr int NIN = op_nin(OP);
+#pragma unroll 4
+  for (int q = 0; q < 16; ++q)
+  {
+    const float4 xi = x.get4(q);
+    const float4 bi = NIN >= 2 ? b.get4(q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 ci = NIN >= 3 ? c.get4(q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 y;
+    y.x = op_apply<EX>(OP, xi.x, bi.x, ci.x);
+    y.y = op_apply<EX>(OP, xi.y, bi.y, ci.y);
+    y.z = op_apply<EX>(OP, xi.z, bi.z, ci.z);
+    y.w = op_apply<EX>(OP, xi.w, bi.w, ci.w);
+    sts128(out_addr + (uint32_t)q * 16u, y);
+  }
+}
+
+// every stateless op gets its own specialised row loop
+template <bool EX>
+MLB_DEV void dispatch_stateless(int op, RowRef x, RowRef b, RowRef c, uint32_t out_addr)
+{
+  switch (op)
+  {
+#define MLB_X_STATELESS(NAME, id, nin, nst, nco)                           \
+  case id:                                                                 \
+    if constexpr (nst == 0 && nco == 0 && nin >= 1 && id != MLB_OP_FDN8_R) \
+      run_stateless_node<id, EX>(x, b, c, out_addr);                       \
+    break;
+    MLB_OP_TABLE_STATELESS(MLB_X_STATELESS)
+#undef MLB_X_STATELESS
+    default: break;
+  }
 }
 
 // FDN<8>::operator() for one voice per lane (reference F:1195-1238); rings in HBM.
@@ -136,8 +194,8 @@ MLB_DEV void run_fdn8_node(const GNode& nd, const GenericArgs& a, int v, bool li
         sumR = __fadd_rn(sumR, d[l]);
       sum = __fadd_rn(sum, d[l]);
     }
-    sts32(outL + (uint32_t)i * kRowStride, sumL);
-    sts32(outR + (uint32_t)i * kRowStride, sumR);
+    sts32(outL + (uint32_t)i * 4u, sumL);
+    sts32(outR + (uint32_t)i * 4u, sumR);
     sum = __fmul_rn(sum, 0.25f);  // 2/SIZE, exact
     const float xi = x.get(i);
 #pragma unroll
@@ -155,13 +213,13 @@ MLB_DEV void run_fdn8_node(const GNode& nd, const GenericArgs& a, int v, bool li
 template <bool EX>
 __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
 {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   const int lane = threadIdx.x;
   const int group = blockIdx.x;
   const int v0 = group * 32;
   const int v = v0 + lane;
   const bool live = v < a.V;
-  const uint32_t rows = smem_u32(smem_raw) + (uint32_t)lane * 4u;  // [slot][sample][lane]
+  const uint32_t rows = smem_u32(smem_raw) + (uint32_t)lane * kRowStride;  // [slot][lane][68]
 
   for (int t = 0; t < a.T; ++t)
   {
@@ -187,14 +245,8 @@ __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
           const float4* src = reinterpret_cast<const float4*>(
               a.in + (((size_t)t * a.n_in + nd.iarg) * a.V + (live ? v : 0)) * MLB_BLOCK);
 #pragma unroll 4
-          for (int j = 0; j < 16; ++j)
-          {
-            float4 q = live ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            sts32(o + (uint32_t)(4 * j + 0) * kRowStride, q.x);
-            sts32(o + (uint32_t)(4 * j + 1) * kRowStride, q.y);
-            sts32(o + (uint32_t)(4 * j + 2) * kRowStride, q.z);
-            sts32(o + (uint32_t)(4 * j + 3) * kRowStride, q.w);
-          }
+          for (int q = 0; q < 16; ++q)
+            sts128(o + (uint32_t)q * 16u, live ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f));
           break;
         }
 #define MLB_GEN_CASE(OPN) \
@@ -223,10 +275,7 @@ __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
           run_fdn8_node<EX>(nd, a, v, live, t, r[0], o,
                             rows + (uint32_t)nd.out_slot2 * kSlotBytes);
           break;
-        default:  // stateless elementwise op
-#pragma unroll 2
-          for (int n = 0; n < MLB_BLOCK; ++n)
-            sts32(o + (uint32_t)n * kRowStride, op_apply<EX>(nd.op, r[0].get(n), r[1].get(n), r[2].get(n)));
+        default: dispatch_stateless<EX>(nd.op, r[0], r[1], r[2], o); break;
       }
 
       if (nd.out_plane >= 0)
@@ -241,14 +290,13 @@ __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
           float4* dst = reinterpret_cast<float4*>(
               a.out + (((size_t)t * a.n_out + nd.out_plane) * a.V + v) * MLB_BLOCK);
 #pragma unroll 4
-          for (int j = 0; j < 16; ++j)
-            dst[j] = make_float4(y.get(4 * j), y.get(4 * j + 1), y.get(4 * j + 2), y.get(4 * j + 3));
+          for (int q = 0; q < 16; ++q) dst[q] = y.get4(q);
         }
         if (a.mix_partial != nullptr)
         {
           // lane n sums samples n and n+32 over the 32 voice rows of this group, in voice order
           __syncwarp();
-          const uint32_t colbase = o - (uint32_t)lane * 4u;  // [sample][lane 0]
+          const uint32_t colbase = o - (uint32_t)lane * kRowStride;  // [voice 0][sample 0]
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh)
           {
@@ -260,7 +308,7 @@ __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
               if (nd.op == MLB_OP_PARAM)
                 xv = __shfl_sync(0xffffffffu, y.k, rr);
               else
-                xv = lds32(colbase + (uint32_t)n * kRowStride + (uint32_t)rr * 4u);
+                xv = lds32(colbase + (uint32_t)rr * kRowStride + (uint32_t)n * 4u);
               if (v0 + rr < a.V) acc = __fadd_rn(acc, xv);
             }
             a.mix_partial[((size_t)(t * a.n_out + nd.out_plane) * a.n_groups + group) * MLB_BLOCK +
