@@ -53,12 +53,12 @@ struct FdnLaunch
   int V, T, n_in;
 };
 
-constexpr int kFdnRow = 68;                        // floats per delay row: 16-B aligned, = 4 mod 32
-constexpr int kFdnVoice = 8 * kFdnRow + 3 * 64 + 8;  // d rows + f/L row + x row + R row (+pad: = 8 mod 32)
+constexpr int kFdnRow = 68;                      // floats per delay row: 16-B aligned, = 4 mod 32
+constexpr int kFdnVoice = 8 * kFdnRow + 2 * 64 + 8;  // 8 delay rows + 2 input/x rows (+pad: = 8 mod 32)
 constexpr int kFdnWarpsPerCta = 4;
 
 template <bool EX>
-__global__ void __launch_bounds__(kFdnWarpsPerCta * 32) fdn8_kernel(const FdnLaunch a)
+__global__ void __launch_bounds__(kFdnWarpsPerCta * 32, 4) fdn8_kernel(const FdnLaunch a)
 {
   extern __shared__ __align__(16) float fdn_smem[];
   using ar = A<EX>;
@@ -67,21 +67,20 @@ __global__ void __launch_bounds__(kFdnWarpsPerCta * 32) fdn8_kernel(const FdnLau
   const int v = (blockIdx.x * kFdnWarpsPerCta + warp) * 4 + vq;
   if ((blockIdx.x * kFdnWarpsPerCta + warp) * 4 >= a.V) return;  // warp-uniform
   const bool live = v < a.V;
-  const unsigned gmask = 0xffu << (vq * 8);  // the 8 lanes of this voice (documentation only)
-  (void)gmask;
 
   float* vbase = fdn_smem + (size_t)(warp * 4 + vq) * kFdnVoice;
-  float* drow = vbase + k * kFdnRow;        // this lane's delay row (phase C view)
-  float* frow = vbase + 8 * kFdnRow;        // input row, later the sumL row
-  float* xrow = frow + 64;
-  float* rrow = xrow + 64;
-  const uint32_t s_vbase = smem_u32(vbase), s_drow = smem_u32(drow), s_frow = smem_u32(frow),
-                 s_xrow = smem_u32(xrow), s_rrow = smem_u32(rrow);
-  const uint32_t bar = smem_u32(fdn_smem + (size_t)kFdnWarpsPerCta * 4 * kFdnVoice) + warp * 8u;
+  // rows: 8 delay rows (this lane's: k), then two input rows: block t's freq row lands in
+  // xbuf[t & 1]; the generator turns it into the x row in place
+  const uint32_t s_vbase = smem_u32(vbase), s_drow = s_vbase + (uint32_t)(k * kFdnRow) * 4u;
+  const uint32_t s_xbuf0 = s_vbase + (uint32_t)(8 * kFdnRow) * 4u;
+  const uint32_t bars = smem_u32(fdn_smem + (size_t)kFdnWarpsPerCta * 4 * kFdnVoice) + warp * 24u;
+  const uint32_t ringbar = bars, xbar0 = bars + 8u;  // xbar[b] = xbar0 + 8 b
 
   if (lane == 0)
   {
-    mbar_init(bar, 32);
+    mbar_init(ringbar, 32);
+    mbar_init(xbar0, 4);
+    mbar_init(xbar0 + 8u, 4);
     fence_mbar_init();
   }
   __syncwarp();
@@ -106,92 +105,115 @@ __global__ void __launch_bounds__(kFdnWarpsPerCta * 32) fdn8_kernel(const FdnLau
   }
   const uint32_t mask = (uint32_t)a.ring_len - 1u;
   float* ring = a.ring + ((size_t)vv * 8 + k) * a.ring_len;
+  // a delay shorter than a block reads what the previous block has just written
+  const bool warp_has_short = __any_sync(0xffffffffu, live && len < (uint32_t)MLB_BLOCK);
 
-  // issue this lane's loads for block t: the 64-sample window that starts len behind w_t
-  auto issue_loads = [&](int t) -> uint32_t
+  // this lane's ring read for block t: the 64-sample window that starts len behind w_t,
+  // over-read to 16-byte alignment (68 floats), split in two when it wraps
+  auto issue_ring_load = [&](int t) -> uint32_t
   {
     const uint32_t w = (uint32_t)(((a.blocks_done + t) * MLB_BLOCK) & (long long)mask);
     const uint32_t r = (w - len) & mask;
     const uint32_t al = r & ~3u;
-    uint32_t bytes = 0;
     if (live)
     {
       const uint32_t first = min((uint32_t)kFdnRow, (uint32_t)a.ring_len - al);  // floats before the wrap
-      bytes = kFdnRow * 4;
-      if (k == 0) bytes += MLB_BLOCK * 4;
-      mbar_arrive_expect_tx(bar, bytes);
-      bulk_load_1d(s_drow, ring + al, first * 4, bar);
-      if (first < (uint32_t)kFdnRow) bulk_load_1d(s_drow + first * 4, ring, (kFdnRow - first) * 4, bar);
-      if (k == 0)
-        bulk_load_1d(a.f.gen == 1 ? s_frow : s_xrow,
-                     a.in + (((size_t)t * a.n_in + a.f.in_plane) * V + v) * MLB_BLOCK, MLB_BLOCK * 4, bar);
+      mbar_arrive_expect_tx(ringbar, kFdnRow * 4);
+      bulk_load_1d(s_drow, ring + al, first * 4, ringbar);
+      if (first < (uint32_t)kFdnRow) bulk_load_1d(s_drow + first * 4, ring, (kFdnRow - first) * 4, ringbar);
+    }
+    else
+    {
+      mbar_arrive_expect_tx(ringbar, 0);
+    }
+    return r & 3u;  // offset of the window inside the over-read row
+  };
+  // input row of block t (one lane per voice)
+  auto issue_x_load = [&](int t)
+  {
+    if (k != 0) return;
+    const uint32_t bar = xbar0 + 8u * (uint32_t)(t & 1);
+    if (live)
+    {
+      mbar_arrive_expect_tx(bar, MLB_BLOCK * 4);
+      bulk_load_1d(s_xbuf0 + (uint32_t)(t & 1) * 256u,
+                   a.in + (((size_t)t * a.n_in + a.f.in_plane) * V + v) * MLB_BLOCK, MLB_BLOCK * 4, bar);
     }
     else
     {
       mbar_arrive_expect_tx(bar, 0);
     }
-    return r & 3u;  // offset of the window inside the over-read row
   };
 
-  uint32_t off = issue_loads(0);
-  uint32_t parity = 0;
-  for (int t = 0; t < a.T; ++t)
+  // ---- G: the three sines of block t, samples 8k .. 8k+7 of this voice, in place in xbuf[t&1] ----
+  auto generate = [&](int t)
   {
-    mbar_wait(bar, parity);
-    parity ^= 1u;
-
-    // ---- G: three sines for samples 8k .. 8k+7 of this voice ----
-    if (a.f.gen == 1)
+    mbar_wait(xbar0 + 8u * (uint32_t)(t & 1), (uint32_t)((t >> 1) & 1));
+    if (a.f.gen != 1) return;  // external input: the row already is x
+    const uint32_t s_x = s_xbuf0 + (uint32_t)(t & 1) * 256u + (uint32_t)k * 32u;
+    float f[8];
     {
-      float f[8];
-      {
-        const float4 q0 = lds128(s_frow + (uint32_t)k * 32u), q1 = lds128(s_frow + (uint32_t)k * 32u + 16u);
-        f[0] = q0.x, f[1] = q0.y, f[2] = q0.z, f[3] = q0.w, f[4] = q1.x, f[5] = q1.y, f[6] = q1.z, f[7] = q1.w;
-      }
-      // inclusive integer prefix of the per-sample phase increments, then across the 8 lanes
-      auto scan_phases = [&](const float (&freq)[8], uint32_t& ph0, uint32_t (&phase)[8])
-      {
-        uint32_t run = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-        {
-          run += (uint32_t)cvt_round(ar::mul(freq[j], 4294967296.0f));
-          phase[j] = run;
-        }
-        uint32_t sc = run;
-#pragma unroll
-        for (int d = 1; d < 8; d <<= 1)
-        {
-          const uint32_t up = __shfl_up_sync(0xffffffffu, sc, d, 8);
-          if (k >= d) sc += up;
-        }
-        const uint32_t excl = sc - run + ph0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) phase[j] += excl;
-        ph0 += __shfl_sync(0xffffffffu, sc, 7, 8);
-      };
-      float fa[8], fb[8];
-      uint32_t pa[8], pb[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) fa[j] = ar::mul(f[j], r1), fb[j] = ar::mul(f[j], r2);
-      scan_phases(fa, ph1, pa);
-      scan_phases(fb, ph2, pb);
+      const float4 q0 = lds128(s_x), q1 = lds128(s_x + 16u);
+      f[0] = q0.x, f[1] = q0.y, f[2] = q0.z, f[3] = q0.w, f[4] = q1.x, f[5] = q1.y, f[6] = q1.z, f[7] = q1.w;
+    }
+    // inclusive integer prefix of the per-sample phase increments, then across the 8 lanes
+    auto scan_phases = [&](const float (&freq)[8], uint32_t& ph0, uint32_t (&phase)[8])
+    {
+      uint32_t run = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
       {
-        const float m1 = phase_to_sine<EX>(pa[j]), m2 = phase_to_sine<EX>(pb[j]);
-        const float bsum = ar::add(ar::add(one, ar::mul(m1, i1)), ar::mul(m2, i2));
-        fa[j] = ar::mul(f[j], bsum);
+        run += (uint32_t)cvt_round(ar::mul(freq[j], 4294967296.0f));
+        phase[j] = run;
       }
-      scan_phases(fa, phc, pa);
-      float4 x0, x1;
-      x0.x = phase_to_sine<EX>(pa[0]), x0.y = phase_to_sine<EX>(pa[1]);
-      x0.z = phase_to_sine<EX>(pa[2]), x0.w = phase_to_sine<EX>(pa[3]);
-      x1.x = phase_to_sine<EX>(pa[4]), x1.y = phase_to_sine<EX>(pa[5]);
-      x1.z = phase_to_sine<EX>(pa[6]), x1.w = phase_to_sine<EX>(pa[7]);
-      sts128(s_xrow + (uint32_t)k * 32u, x0);
-      sts128(s_xrow + (uint32_t)k * 32u + 16u, x1);
+      uint32_t sc = run;
+#pragma unroll
+      for (int d = 1; d < 8; d <<= 1)
+      {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, sc, d, 8);
+        if (k >= d) sc += up;
+      }
+      const uint32_t excl = sc - run + ph0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) phase[j] += excl;
+      ph0 += __shfl_sync(0xffffffffu, sc, 7, 8);
+    };
+    float fa[8], fb[8];
+    uint32_t pa[8], pb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) fa[j] = ar::mul(f[j], r1), fb[j] = ar::mul(f[j], r2);
+    scan_phases(fa, ph1, pa);
+    scan_phases(fb, ph2, pb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+    {
+      const float m1 = phase_to_sine<EX>(pa[j]), m2 = phase_to_sine<EX>(pb[j]);
+      const float bsum = ar::add(ar::add(one, ar::mul(m1, i1)), ar::mul(m2, i2));
+      fa[j] = ar::mul(f[j], bsum);
     }
+    scan_phases(fa, phc, pa);
+    float4 x0, x1;
+    x0.x = phase_to_sine<EX>(pa[0]), x0.y = phase_to_sine<EX>(pa[1]);
+    x0.z = phase_to_sine<EX>(pa[2]), x0.w = phase_to_sine<EX>(pa[3]);
+    x1.x = phase_to_sine<EX>(pa[4]), x1.y = phase_to_sine<EX>(pa[5]);
+    x1.z = phase_to_sine<EX>(pa[6]), x1.w = phase_to_sine<EX>(pa[7]);
+    sts128(s_x, x0);
+    sts128(s_x + 16u, x1);
+  };
+
+  // ---- prologue: ring(0), x(0), x(1) in flight; generate x(0) while the ring read lands ----
+  uint32_t off = issue_ring_load(0);
+  issue_x_load(0);
+  if (a.T > 1) issue_x_load(1);
+  generate(0);
+  __syncwarp();
+
+  uint32_t rparity = 0;
+  for (int t = 0; t < a.T; ++t)
+  {
+    const uint32_t s_xrow = s_xbuf0 + (uint32_t)(t & 1) * 256u;
+    mbar_wait(ringbar, rparity);
+    rparity ^= 1u;
 
     // ---- B: Householder mixing, lane k owns samples k, k+8, ..., k+56 of its voice ----
     {
@@ -205,6 +227,8 @@ __global__ void __launch_bounds__(kFdnWarpsPerCta * 32) fdn8_kernel(const FdnLau
         for (int j = 0; j < 8; ++j)
           d[n][j] = lds32(s_vbase + (uint32_t)(n * kFdnRow + k + 8 * j) * 4u + offs[n] * 4u);
       __syncwarp();  // every lane holds its samples before rows are overwritten in place
+      float* outL = a.out + (((size_t)t * 2 + 0) * V + vv) * MLB_BLOCK + k;
+      float* outR = a.out + (((size_t)t * 2 + 1) * V + vv) * MLB_BLOCK + k;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
       {
@@ -223,8 +247,12 @@ __global__ void __launch_bounds__(kFdnWarpsPerCta * 32) fdn8_kernel(const FdnLau
 #pragma unroll
         for (int n = 0; n < 8; ++n)
           sts32(s_vbase + (uint32_t)(n * kFdnRow + k + 8 * j) * 4u, __fsub_rn(d[n][j], sum));
-        sts32(s_frow + (uint32_t)(k + 8 * j) * 4u, sumL);
-        sts32(s_rrow + (uint32_t)(k + 8 * j) * 4u, sumR);
+        if (live)
+        {
+          // concatRows(sumL, sumR) (F:1237): the 8 lanes of a voice write one full 32-B sector
+          __stcs(outL + 8 * j, sumL);
+          __stcs(outR + 8 * j, sumR);
+        }
       }
     }
     __syncwarp();
@@ -247,29 +275,44 @@ __global__ void __launch_bounds__(kFdnWarpsPerCta * 32) fdn8_kernel(const FdnLau
       sts128(s_drow + (uint32_t)q * 16u, u);
     }
 
-    // ---- S: rings and outputs ----
+    // ---- S: next block's delay input goes straight to the ring position it will be read from ----
     fence_proxy_async();
     __syncwarp();
     if (live)
     {
       const uint32_t wn = (uint32_t)(((a.blocks_done + t + 1) * MLB_BLOCK) & (long long)mask);
       bulk_store_1d(ring + wn, s_drow, MLB_BLOCK * 4);
-      if (k == 0) bulk_store_1d(a.out + (((size_t)t * 2 + 0) * V + v) * MLB_BLOCK, s_frow, MLB_BLOCK * 4);
-      if (k == 1) bulk_store_1d(a.out + (((size_t)t * 2 + 1) * V + v) * MLB_BLOCK, s_rrow, MLB_BLOCK * 4);
       bulk_commit();
-      // A delay shorter than a block reads what this block has just written: wait until the
-      // store is globally performed.  Longer delays only need the row buffer back.
-      if (len < (uint32_t)MLB_BLOCK)
-        bulk_wait_all<0>();
-      else
-        bulk_wait_read<0>();
     }
-    __syncwarp();
-    if (t + 1 < a.T) off = issue_loads(t + 1);
+    if (t + 1 < a.T)
+    {
+      // x(t) is consumed: its buffer takes the input row of block t+2
+      if (t + 2 < a.T) issue_x_load(t + 2);
+      if (!warp_has_short)
+      {
+        // long delays only need the row buffer back: start the next ring read at once and hide
+        // its latency behind the generator of block t+1
+        if (live) bulk_wait_read<0>();
+        __syncwarp();
+        off = issue_ring_load(t + 1);
+        generate(t + 1);
+      }
+      else
+      {
+        // some line of this warp reads what was just written: generate first (hides the store
+        // latency), then wait until the stores are globally performed
+        generate(t + 1);
+        if (live) bulk_wait_all<0>();
+        __syncwarp();
+        off = issue_ring_load(t + 1);
+      }
+      __syncwarp();
+    }
   }
 
   if (live)
   {
+    bulk_wait_all<0>();
     a.state[(size_t)(a.f.st_y1 + k) * V + v] = f2u(y1);
     if (a.f.gen == 1 && k == 0)
     {
@@ -375,7 +418,7 @@ inline int launch_fm3_fdn8(const FdnArgs& f, bool exact, uint32_t* state, const 
   a.V = V, a.T = T, a.n_in = n_in;
   const int voices_per_cta = kFdnWarpsPerCta * 4;
   const int n_ctas = (V + voices_per_cta - 1) / voices_per_cta;
-  const size_t smem = (size_t)kFdnWarpsPerCta * 4 * kFdnVoice * 4 + kFdnWarpsPerCta * 8;
+  const size_t smem = (size_t)kFdnWarpsPerCta * 4 * kFdnVoice * 4 + kFdnWarpsPerCta * 24;
   cudaError_t e;
   if (exact)
   {

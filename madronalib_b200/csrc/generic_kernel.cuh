@@ -323,24 +323,43 @@ __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
 }
 
 // ---- K3: stateless elementwise ops over n_rows*64 elements (MLDSPOps.h:567-918) ----
-template <bool EX>
+// One instantiation per op (the switch in op_apply folds away); float4 per thread, grid-stride.
+template <int OP, bool EX>
 __global__ void __launch_bounds__(256)
-    map_kernel(int op, const float4* __restrict__ x1, const float4* __restrict__ x2,
+    map_kernel(const float4* __restrict__ x1, const float4* __restrict__ x2,
                const float4* __restrict__ x3, float4* __restrict__ y, size_t n4)
 {
+  constexpr int NIN = op_nin(OP);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
   {
-    const float4 a = x1[i];
-    const float4 b = x2 ? x2[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 c = x3 ? x3[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 a = __ldcs(x1 + i);
+    const float4 b = NIN >= 2 ? __ldcs(x2 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 c = NIN >= 3 ? __ldcs(x3 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 r;
-    r.x = op_apply<EX>(op, a.x, b.x, c.x);
-    r.y = op_apply<EX>(op, a.y, b.y, c.y);
-    r.z = op_apply<EX>(op, a.z, b.z, c.z);
-    r.w = op_apply<EX>(op, a.w, b.w, c.w);
-    y[i] = r;
+    r.x = op_apply<EX>(OP, a.x, b.x, c.x);
+    r.y = op_apply<EX>(OP, a.y, b.y, c.y);
+    r.z = op_apply<EX>(OP, a.z, b.z, c.z);
+    r.w = op_apply<EX>(OP, a.w, b.w, c.w);
+    __stcs(y + i, r);
   }
+}
+
+typedef void (*MapKernelFn)(const float4*, const float4*, const float4*, float4*, size_t);
+inline MapKernelFn map_kernel_for(int op)
+{
+  switch (op)
+  {
+#define MLB_X_MAP(NAME, id, nin, nst, nco)                                 \
+  case id:                                                                 \
+    if constexpr (nst == 0 && nco == 0 && nin >= 1 && id != MLB_OP_FDN8_R) \
+      return map_kernel<id, true>;                                         \
+    break;
+    MLB_OP_TABLE_STATELESS(MLB_X_MAP)
+#undef MLB_X_MAP
+    default: break;
+  }
+  return nullptr;
 }
 
 }  // namespace mlb

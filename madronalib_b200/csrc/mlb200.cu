@@ -1163,9 +1163,10 @@ extern "C" int mlb_map_device(int op, const float* x1, const float* x2, const fl
   const int threads = 256;
   const size_t want = (n4 + threads - 1) / threads;
   const int blocks = (int)std::min<size_t>(want, (size_t)g_sm_count * 16);
-  map_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(
-      op, (const float4*)x1, nin >= 2 ? (const float4*)x2 : nullptr,
-      nin >= 3 ? (const float4*)x3 : nullptr, (float4*)y, n4);
+  MapKernelFn fn = map_kernel_for(op);
+  if (!fn) return fail(MLB_ERR_INVALID, "op %d has no map kernel", op);
+  fn<<<blocks, threads, 0, (cudaStream_t)stream>>>((const float4*)x1, nin >= 2 ? (const float4*)x2 : nullptr,
+                                                   nin >= 3 ? (const float4*)x3 : nullptr, (float4*)y, n4);
   ++g_launches;
   CU_CHECK(cudaGetLastError());
   return MLB_OK;

@@ -24,7 +24,7 @@ def main():
     from madronalib_b200 import api, workloads as wl
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--only", default="2,3,4,5")
+    ap.add_argument("--only", default="2,3,4,5,map")
     ap.add_argument("--generic", action="store_true", help="force the graph interpreter kernel")
     args = ap.parse_args()
     only = set(args.only.split(","))
@@ -45,6 +45,30 @@ def main():
         cfgs.append(("config4", wl.config_4(16384), 16, lambda V, T: 4864.0 * V * T))
     if "5" in only:
         cfgs.append(("config5", wl.config_5(1024, 256), 16, lambda V, T: 256.0 * V * T))
+    if "map" in only:
+        # K3: stateless elementwise ops, n_rows x 64 elements resident in HBM
+        n_rows = 1 << 20  # 64 Mi elements = 256 MB per operand (> L2)
+        x1 = torch.rand((n_rows, 64), dtype=torch.float32, device=dev) * 4 - 2
+        x2 = torch.rand((n_rows, 64), dtype=torch.float32, device=dev) + 0.5
+        x3 = torch.rand((n_rows, 64), dtype=torch.float32, device=dev)
+        y = torch.empty_like(x1)
+        sh = torch.cuda.current_stream().cuda_stream
+        for op, nin in (("multiply", 2), ("sin", 1), ("exp", 1), ("log", 1), ("sin_approx", 1),
+                        ("pow", 2), ("lerp", 3), ("clamp", 3)):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(3):
+                api.map_device(op, x1, x2 if nin > 1 else None, x3 if nin > 2 else None, y, n_rows, sh)
+            e0.record()
+            for _ in range(args.steps):
+                api.map_device(op, x1, x2 if nin > 1 else None, x3 if nin > 2 else None, y, n_rows, sh)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            b = (nin + 1) * n_rows * 64 * 4.0
+            print(json.dumps({"config": "map_" + op, "kernel": "map_kernel", "rows": n_rows, "kernel_ms": ms,
+                              "algorithmic_bytes": b, "achieved_gbs": b / (ms * 1e-3) / 1e9,
+                              "frac_of_measured_hbm_peak": b / (ms * 1e-3) / 1e9 / peak}), flush=True)
+        del x1, x2, x3, y
     for name, w, T, alg in cfgs:
         V = w.n_voices
         g = api.VoiceGraph(w.spec, V, api.FLAG_FORCE_GENERIC if args.generic else 0)
