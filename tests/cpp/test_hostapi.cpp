@@ -9,8 +9,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "mlb200.hpp"
+#include "mlb200_host.hpp"
 
 using namespace mlb;
 
@@ -144,6 +146,58 @@ int main()
     REQUIRE(!(y.constRow(0) == y.constRow(1)));
     bank.readState();
     REQUIRE(bank.stateWord(s, 0, 2) != 0xC0000000u);  // phase advanced
+  }
+
+  // ---- the caller of the boundary: arbitrary host callback sizes, ONE launch per callback ----
+  // (reference: SignalProcessBuffer::process, source/app/MLSignalProcessBuffer.cpp:36-90, drives the
+  //  user's SignalProcessFn once per 64 frames; here the whole callback is one batched call whose
+  //  output is the mix bus of a 64-voice bank, like Synth::processVector summing voices)
+  {
+    const int V = 64;
+    Graph g;
+    const int f = g.param(), s = g.sine(f), lp = g.lopass(s), k = g.param(), y = g.multiply(lp, k);
+    g.output(y);
+    auto setup = [&](DeviceBank& bank) {
+      for (int v = 0; v < V; ++v)
+      {
+        float c[3];
+        mlb_coeffs_lopass(0.02f + 0.003f * v, 0.5f, c);
+        bank.setParam(f, v, (110.f + 3.f * v) / 48000.f);
+        bank.setCoeffs(lp, v, c, 3);
+        bank.setParam(k, v, 0.01f);
+        bank.setStateWord(s, 0, v, 0xC0000000u);
+      }
+      bank.commit();
+    };
+    // direct: 40 blocks of mix bus in one call
+    DeviceBank direct(g, V);
+    setup(direct);
+    std::vector<float> want(40 * 64);
+    direct.process(nullptr, nullptr, want.data(), 40);
+    // through the batched process buffer with awkward callback sizes
+    DeviceBank bank(g, V);
+    setup(bank);
+    BatchedSignalProcessBuffer spb(0, 1, 1024);
+    const long long launches0 = mlb_kernel_launches();
+    int callbacks = 0, vectors = 0;
+    std::vector<float> got;
+    const int sizes[] = {480, 17, 1000, 3, 64, 513, 129, 255};
+    for (int frames : sizes)
+    {
+      std::vector<float> buf(frames);
+      float* outs[1] = {buf.data()};
+      vectors += spb.process(nullptr, outs, frames, [&](const float*, float* out, int n) {
+        bank.process(nullptr, nullptr, out, n);  // out = mix bus [n][1][64]
+      });
+      ++callbacks;
+      got.insert(got.end(), buf.begin(), buf.end());
+    }
+    REQUIRE(got.size() <= want.size());
+    bool same = true;
+    for (size_t i = 0; i < got.size(); ++i) same = same && (got[i] == want[i]);
+    REQUIRE(same);  // the host sees one continuous stream, whatever the callback sizes
+    REQUIRE(vectors == (int)((got.size() + 63) / 64));
+    REQUIRE(mlb_kernel_launches() - launches0 <= 2 * callbacks);  // chain + mix-reduce per callback at most
   }
 
   std::printf("%s: %d assertions, %d failed, %lld kernels launched\n", g_fail ? "FAILED" : "ALL PASSED", g_checks,
