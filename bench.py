@@ -358,6 +358,42 @@ def run_cuda_arm(args):
            "d2h_bytes_per_step": int(h_out.numel() * 4 + (h_mix.nbytes if use_mix else 0)),
            "steps": n_e2e, "path": "mlb_graph_process_host (pinned host buffers, contract R)"}
 
+    # ---- other I/O contracts of the same chain through the same host entry point:
+    # S = per-voice scalar frequency (DSPVector(float) broadcast, examples/audio-and-midi/sine.cpp:33)
+    #     in, per-voice rows out;  M = scalar frequency in, mix bus out only (Synth::processVector).
+    # Reported beside the graded contract-R e2e, never as a fraction of the HBM roofline.
+    variants = {}
+    if not args.no_variants:
+        from madronalib_b200.graph import GraphSpec, SINE_ZERO_PHASE
+        gs = GraphSpec()
+        pf = gs.param()
+        ps = gs.node("SINE", pf)
+        plp = gs.node("LOPASS", ps)
+        pk = gs.param()
+        gs.output(gs.node("MULTIPLY", plp, pk))
+        coef_s = gs.new_coefs(V)
+        coef_s[0] = wl.base_freq(V)
+        coef_s[1:4] = w.coef[0:3]
+        coef_s[4] = w.coef[3]
+        st_s = gs.new_state(V)
+        st_s[0] = SINE_ZERO_PHASE
+        graph_s = api.VoiceGraph(gs, V, api.FLAG_FAST if args.fast else api.FLAG_EXACT)
+        graph_s.set_coefs(coef_s)
+        graph_s.set_state(st_s)
+        for name, want_out in (("contract_S", True), ("contract_M", False)):
+            graph_s.process_host(None, T, want_out=want_out, want_mix=True,
+                                 out=h_out.numpy() if want_out else None, mix=h_mix)
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                graph_s.process_host(None, T, want_out=want_out, want_mix=True,
+                                     out=h_out.numpy() if want_out else None, mix=h_mix)
+            dt = time.perf_counter() - t0
+            variants[name] = {"value": vs_per_step * n_e2e * world / dt, "unit": UNIT,
+                              "h2d_bytes_per_step": 0,
+                              "d2h_bytes_per_step": int((h_out.numel() * 4 if want_out else 0) + h_mix.nbytes),
+                              "kernel": graph_s.kernel_name}
+        graph_s.close()
+
     line = None
     if rank == 0:
         cpu = cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
@@ -375,7 +411,8 @@ def run_cuda_arm(args):
                 "l2": "inputs+outputs 2.1 GB per step >> 126 MB L2 (no flush needed)",
                 "kernel": graph.kernel_name,
             },
-            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "e2e": e2e, "e2e_other_contracts": variants,
+            "gpu_launches": int(launches),
             "clocks": sampler.summary() if sampler else None,
             "realtime_x": value / (world * V * 48000.0),
         }
@@ -401,6 +438,7 @@ def main():
     ap.add_argument("--fast", action="store_true", help="allow FMA contraction (not bit-exact)")
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the contract S / M e2e legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -177,7 +177,7 @@ int main()
     // through the batched process buffer with awkward callback sizes
     DeviceBank bank(g, V);
     setup(bank);
-    BatchedSignalProcessBuffer spb(0, 1, 1024);
+    BatchedSignalProcessBuffer spb(0, 1, 4096);  // kMaxProcessBlockFrames, source/app/MLAudioTask.h:25
     const long long launches0 = mlb_kernel_launches();
     int callbacks = 0, vectors = 0;
     std::vector<float> got;
