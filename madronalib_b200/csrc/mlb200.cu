@@ -1077,7 +1077,10 @@ extern "C" int mlb_graph_process_host(mlb_graph* g, const float* in_host, float*
   // of slice p and the D2H copy of slice p-1 overlap (three streams; PCIe is full duplex).
   // A slice is a strided window [T*n][va:vb][64] of the host planes -> cudaMemcpy2DAsync.
   const int n_slices_env = env_int("MLB_HOST_SLICES", 16);
-  if (g->kind == KIND_FUSED && n_slices_env > 1 && g->V >= 4096 && in_bytes + out_bytes >= ((size_t)32 << 20))
+  // Only planes that really cross PCIe count: a mix-only call (out_host == NULL) moves 256 B per
+  // block and must stay ONE launch -- 16 slice launches of a 4096-voice bank are latency-bound.
+  const size_t pcie_bytes = in_bytes + (out_host ? out_bytes : 0);
+  if (g->kind == KIND_FUSED && n_slices_env > 1 && g->V >= 4096 && pcie_bytes >= ((size_t)32 << 20))
   {
     const int n_slices = std::min(n_slices_env, 16);
     int per = (g->V + n_slices - 1) / n_slices;
