@@ -79,6 +79,8 @@ enum {
   X(SAW, 5, 1, 1, 0)            /* SawGen(freq), G:285-311,362-369,395-402           */ \
   X(PULSE, 6, 2, 1, 0)          /* PulseGen(freq,width), G:342-358,383-393           */ \
   X(TICK, 7, 1, 1, 0)           /* TickGen(freq), G:24-47; state: mOmega (f32)       */ \
+  X(ONESHOT, 8, 1, 3, 0)        /* OneShotGen(freq), G:221-252; state mOmega32,mGate,*/ \
+                                /* mOmegaPrev; trigger() = set_state {0,1,0}         */ \
   /* SVF family ("Biquad" stand-ins) -- state: ic1eq, ic2eq */                           \
   X(LOPASS, 10, 1, 2, 3)        /* F:51-133   coef g0,g1,g2                          */ \
   X(HIPASS, 11, 1, 2, 4)        /* F:155-197  coef g0,g1,g2,k                        */ \
@@ -97,6 +99,23 @@ enum {
   /* mDelayInputVectors live in separate delay memory (mlb_graph_delay_bytes).       */ \
   X(FDN8, 20, 1, 8, 32)         /* F:1162-1239                                       */ \
   X(FDN8_R, 21, 1, 0, 0)                                                                 \
+  /* envelope followers / envelopes / one-sample allpass */                              \
+  X(PEAK, 22, 1, 2, 3)          /* F:562-615 state y1,peakHoldCounter(i32); coef a0, */ \
+                                /* b1,peakHoldSamples (float-valued int)             */ \
+  X(RMS, 23, 1, 1, 2)           /* F:619-653 state y1; coef a0,b1                    */ \
+  X(ADSR, 24, 1, 8, 4)          /* F:657-797 state y,y1,x1,threshold,target,k,amp,   */ \
+                                /* segment(i32; 4 = off); coef ka,kd,s,kr            */ \
+  X(ALLPASS1, 25, 1, 2, 1)      /* F:918-964 state x1,y1; coef a                     */ \
+  /* control-rate smoothers: the scalar argument is sample 0 of the operand row      */ \
+  X(GLIDE, 26, 1, 3, 2)         /* LinearGlide(float), G:433-515; state step,target, */ \
+                                /* mVectorsRemaining(i32, -1 idle); coef             */ \
+                                /* mVectorsPerGlide (float-valued int), mDyPerVector;*/ \
+                                /* mCurrVec is a 64-float row in delay memory        */ \
+  X(INTERPOLATOR1, 27, 1, 1, 0) /* G:412-424 state currentValue                      */ \
+  X(SAMPLE_GLIDE, 28, 1, 4, 2)  /* SampleAccurateLinearGlide::nextSample per sample, */ \
+                                /* G:517-590; state curr,step,target,remaining(i32); */ \
+                                /* coef mSamplesPerGlide (float-valued int),         */ \
+                                /* mDyPerSample                                      */ \
   /* unary float ops, O:584-614,825 */                                                   \
   X(SQRT, 30, 1, 0, 0)                                                                   \
   X(SQRT_APPROX, 31, 1, 0, 0)                                                            \
@@ -146,13 +165,57 @@ enum {
   /* select(a, b, mask) bitwise, O:886,917; int add/sub O:713-714 */                     \
   X(SELECT, 90, 3, 0, 0)                                                                 \
   X(ADD_INT32, 91, 2, 0, 0)                                                              \
-  X(SUBTRACT_INT32, 92, 2, 0, 0)
+  X(SUBTRACT_INT32, 92, 2, 0, 0)                                                         \
+  /* ---- delay-memory ops (ids >= 100).  Rings and 64-float rows live in the graph's  */ \
+  /* delay memory (MLB_OP_MEM_TABLE below), zeroed by mlb_graph_set_coefs /           */ \
+  /* mlb_graph_clear_delays.  "maxDelay" is the argument the caller would hand to the */ \
+  /* functor's own setMaxDelayInSamples; the ring of voice v has                      */ \
+  /* 1 << bitsToContain(floor(maxDelay_v') + 64) samples (F:822-830).                 */ \
+  X(INTEGER_DELAY, 100, 1, 0, 2)      /* IntegerDelay(vx), F:834-875; coef delay      */ \
+                                      /* (float-valued int), maxDelay                 */ \
+  X(INTEGER_DELAY_VAR, 101, 2, 0, 1)  /* IntegerDelay(x, delay), F:877-896; coef      */ \
+                                      /* maxDelay                                     */ \
+  X(FRACTIONAL_DELAY, 102, 1, 2, 2)   /* FractionalDelay(vx), F:971-1030; state       */ \
+                                      /* allpass x1,y1; coef delay, maxDelay          */ \
+  X(FRACTIONAL_DELAY_VAR, 103, 2, 2, 1) /* FractionalDelay(vx, vDelay), F:1033-1042   */ \
+  X(PITCHBEND_DELAY, 104, 2, 8, 1)    /* PitchbendableDelay(x, vDelay), F:1079-1105;  */ \
+                                      /* state 2 x {x1,y1,intDelay(i32),apCoeff};     */ \
+                                      /* coef maxDelay                                */ \
+  X(ALLPASS_INT, 105, 1, 0, 3)        /* Allpass<IntegerDelay>(x), F:1111-1143; coef  */ \
+                                      /* mGain, delay, maxDelay                       */ \
+  X(ALLPASS_FRAC, 106, 1, 2, 3)       /* Allpass<FractionalDelay>(x); state x1,y1     */ \
+  X(ALLPASS_PB, 107, 2, 8, 2)         /* Allpass<PitchbendableDelay>(x, vDelay),      */ \
+                                      /* F:1145-1154; state as PITCHBEND_DELAY; coef  */ \
+                                      /* mGain, maxDelay                              */ \
+  /* one-block feedback edge (a DSPVector member kept between processVector calls,    */ \
+  /* examples/audio-and-midi/reverb.cpp:34,115-116): FEEDBACK_READ yields the row     */ \
+  /* stored by the FEEDBACK_WRITE of the previous block (zero at start);              */ \
+  /* FEEDBACK_WRITE(in0).iarg = node index of its FEEDBACK_READ; it passes in0 on.    */ \
+  X(FEEDBACK_READ, 108, 0, 0, 0)                                                         \
+  X(FEEDBACK_WRITE, 109, 1, 0, 0)
+
+/* Delay memory per voice: X(NAME, n_rows, n_rings) -- 64-float rows and rings. */
+#define MLB_OP_MEM_TABLE(X) \
+  X(GLIDE, 1, 0)            \
+  X(INTEGER_DELAY, 0, 1)    \
+  X(INTEGER_DELAY_VAR, 0, 1)\
+  X(FRACTIONAL_DELAY, 0, 1) \
+  X(FRACTIONAL_DELAY_VAR, 0, 1) \
+  X(PITCHBEND_DELAY, 0, 2)  \
+  X(ALLPASS_INT, 1, 1)      \
+  X(ALLPASS_FRAC, 1, 1)     \
+  X(ALLPASS_PB, 1, 2)       \
+  X(FEEDBACK_READ, 1, 0)
+
+/* ids in [MLB_OP_MAP_FIRST, MLB_OP_MAP_END) are the stateless elementwise ops (mlb_map_*) */
+#define MLB_OP_MAP_FIRST 30
+#define MLB_OP_MAP_END 100
 
 typedef enum mlb_op {
 #define MLB_X_ENUM(NAME, id, nin, nst, nco) MLB_OP_##NAME = id,
   MLB_OP_TABLE(MLB_X_ENUM)
 #undef MLB_X_ENUM
-  MLB_OP__END = 93
+  MLB_OP__END = 110
 } mlb_op;
 
 /* One node of a voice graph.  in[] index earlier nodes (topological order). */
@@ -191,6 +254,15 @@ void mlb_coeffs_bell(float omega, float k, float A, float out4[4]);
 void mlb_coeffs_onepole(float omega, float out2[2]);
 float mlb_coeffs_dcblocker(float omega);
 float mlb_db_to_gain(float dB);
+/* Peak::makeCoeffs F:578-582, RMS::makeCoeffs F:632-636 (a0, b1); ADSR::calcCoeffs F:676-683
+ * (ka, kd, s, kr); Allpass1::makeCoeffs F:936-941; LinearGlide::setGlideTimeInSamples G:443-448
+ * and SampleAccurateLinearGlide::setGlideTimeInSamples G:527-532 (count as float, 1/count). */
+void mlb_coeffs_peak(float omega, float out2[2]);
+void mlb_coeffs_rms(float omega, float out2[2]);
+void mlb_coeffs_adsr(float a, float d, float s, float r, float sr, float out4[4]);
+float mlb_coeffs_allpass1(float d);
+void mlb_coeffs_glide(float time_in_samples, float out2[2]);
+void mlb_coeffs_sample_glide(float time_in_samples, float out2[2]);
 /* FDN<8>::setDelaysInSamples / setFilterCutoffs / mFeedbackGains, F:1171-1191.
  * Fills the 32 coef words of an FDN8 node for one voice:
  * [0..7]=a0, [8..15]=b1, [16..23]=feedback gain, [24..31]=len=max(1,int(time)-64). */

@@ -72,12 +72,15 @@ def lib() -> ctypes.CDLL:
     L.mlb_map_device.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]
     L.mlb_map_host.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_size_t]
     for name, n in (("lopass", 2), ("hipass", 2), ("bandpass", 2), ("loshelf", 3), ("hishelf", 3),
-                    ("bell", 3), ("onepole", 1)):
+                    ("bell", 3), ("onepole", 1), ("peak", 1), ("rms", 1), ("adsr", 5), ("glide", 1),
+                    ("sample_glide", 1)):
         fn = getattr(L, "mlb_coeffs_" + name)
         fn.argtypes = [_cf] * n + [_vp]
         fn.restype = None
     L.mlb_coeffs_dcblocker.argtypes = [_cf]
     L.mlb_coeffs_dcblocker.restype = _cf
+    L.mlb_coeffs_allpass1.argtypes = [_cf]
+    L.mlb_coeffs_allpass1.restype = _cf
     L.mlb_db_to_gain.argtypes = [_cf]
     L.mlb_db_to_gain.restype = _cf
     L.mlb_coeffs_fdn8.argtypes = [_vp, _vp, _vp, _vp]
@@ -117,7 +120,8 @@ def kernel_launches() -> int:
 
 
 # ---- coefficient design (host libm; same calls as the reference's makeCoeffs) ----
-_NCOEF = {"lopass": 3, "hipass": 4, "bandpass": 3, "loshelf": 5, "hishelf": 6, "bell": 4, "onepole": 2}
+_NCOEF = {"lopass": 3, "hipass": 4, "bandpass": 3, "loshelf": 5, "hishelf": 6, "bell": 4, "onepole": 2,
+          "peak": 2, "rms": 2, "adsr": 4, "glide": 2, "sample_glide": 2}
 
 
 def coeffs(kind: str, *args: float) -> np.ndarray:
@@ -128,6 +132,10 @@ def coeffs(kind: str, *args: float) -> np.ndarray:
 
 def coeffs_dcblocker(omega: float) -> float:
     return float(lib().mlb_coeffs_dcblocker(omega))
+
+
+def coeffs_allpass1(d: float) -> float:
+    return float(lib().mlb_coeffs_allpass1(d))
 
 
 def db_to_gain(db: float) -> float:

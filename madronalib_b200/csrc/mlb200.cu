@@ -216,6 +216,40 @@ extern "C" float mlb_db_to_gain(float dB)
   volatile float e = dB / 40.f;
   return powf(10.f, e);
 }
+extern "C" void mlb_coeffs_peak(float omega, float r[2]) { mlb_coeffs_onepole(omega, r); }
+extern "C" void mlb_coeffs_rms(float omega, float r[2]) { mlb_coeffs_onepole(omega, r); }
+extern "C" void mlb_coeffs_adsr(float a, float d, float s, float rel, float sr, float o[4])
+{
+  const float minSegmentTime = 0.0002f;
+  volatile float invSr = 1.0f / sr;
+  volatile float num = kTwoPiF * invSr;
+  o[0] = num / (a > minSegmentTime ? a : minSegmentTime);
+  o[1] = num / (d > minSegmentTime ? d : minSegmentTime);
+  o[2] = s;
+  o[3] = num / (rel > minSegmentTime ? rel : minSegmentTime);
+}
+extern "C" float mlb_coeffs_allpass1(float d)
+{
+  volatile float xm1 = d - 1.f;
+  volatile float t0 = -0.53f * xm1;
+  volatile float t1 = 0.24f * xm1;
+  volatile float t2 = t1 * xm1;
+  return t0 + t2;
+}
+extern "C" void mlb_coeffs_glide(float t, float o[2])
+{
+  int n = (int)(t / (float)MLB_BLOCK);
+  if (n < 1) n = 1;
+  o[0] = (float)n;
+  o[1] = 1.0f / ((float)n + 0.f);
+}
+extern "C" void mlb_coeffs_sample_glide(float t, float o[2])
+{
+  int n = (int)t;
+  if (n < 1) n = 1;
+  o[0] = (float)n;
+  o[1] = 1.0f / (float)n;
+}
 extern "C" void mlb_coeffs_fdn8(const float times[8], const float cutoffs[8], const float gains[8],
                                 float out32[32])
 {

@@ -37,7 +37,18 @@ def _parse_op_table() -> Dict[str, Tuple[int, int, int, int]]:
     return table
 
 
+def _parse_mem_table() -> Dict[str, Tuple[int, int]]:
+    """name -> (n_rows, n_rings) of delay memory, parsed from MLB_OP_MEM_TABLE."""
+    with open(_HEADER, "r") as f:
+        text = f.read()
+    start = text.index("#define MLB_OP_MEM_TABLE(X)")
+    end = text.index("typedef enum mlb_op")
+    return {m.group(1): (int(m.group(2)), int(m.group(3)))
+            for m in re.finditer(r"X\(\s*([A-Z0-9_]+)\s*,\s*(\d+)\s*,\s*(\d+)\s*\)", text[start:end])}
+
+
 OP_TABLE = _parse_op_table()
+OP_MEM = _parse_mem_table()
 OP_ID = {name: v[0] for name, v in OP_TABLE.items()}
 OP_NAME = {v[0]: name for name, v in OP_TABLE.items()}
 OP_INFO = {v[0]: v[1:] for v in OP_TABLE.values()}  # id -> (n_in, n_state, n_coef)
@@ -86,6 +97,15 @@ class GraphSpec:
 
     def node(self, name: str, *inputs: int) -> int:
         return self._add(name.upper(), *inputs)
+
+    def feedback_read(self) -> int:
+        """The row stored by `feedback_write` on the previous block (zeros at start)."""
+        return self._add("FEEDBACK_READ")
+
+    def feedback_write(self, reader: int, src: int) -> int:
+        if self.ops[reader] != OP_ID["FEEDBACK_READ"]:
+            raise ValueError("feedback_write: target is not a FEEDBACK_READ node")
+        return self._add("FEEDBACK_WRITE", src, iarg=reader)
 
     def output(self, *nodes: int) -> "GraphSpec":
         self.outs.extend(nodes)
@@ -142,7 +162,18 @@ class GraphSpec:
         return (ctypes.c_int32 * max(1, self.n_out))(*self.outs)
 
     def new_state(self, n_voices: int) -> np.ndarray:
-        return np.zeros((max(1, self.n_state), n_voices), dtype=np.uint32)[: self.n_state]
+        """State of freshly constructed functors (zeros, except the idle markers below)."""
+        st = np.zeros((max(1, self.n_state), n_voices), dtype=np.uint32)[: self.n_state]
+        off = self.offsets()[0]
+        for i, op in enumerate(self.ops):
+            name = OP_NAME[op]
+            if name == "ADSR":            # segment{off}, MLDSPFilters.h:694
+                st[off[i] + 7] = 4
+            elif name == "GLIDE":         # mVectorsRemaining{-1}, MLDSPGens.h:440
+                st[off[i] + 2] = 0xFFFFFFFF
+            elif name == "SAMPLE_GLIDE":  # mSamplesRemaining{-1}, MLDSPGens.h:524
+                st[off[i] + 3] = 0xFFFFFFFF
+        return st
 
     def new_coefs(self, n_voices: int) -> np.ndarray:
         return np.zeros((max(1, self.n_coef), n_voices), dtype=np.float32)[: self.n_coef]
@@ -229,3 +260,55 @@ def graph_chain256(n_nodes: int = 256) -> GraphSpec:
         prev, x = x, y
         count += 1
     return g.output(x)
+
+
+# Aaltoverb (examples/audio-and-midi/reverb.cpp:21-123): allpass gains, setMaxDelayInSamples
+# arguments and delay-time scales of the ten Allpass<PitchbendableDelay> sections and the two
+# PitchbendableDelay feedback lines.
+AALTOVERB_AP_GAINS = (0.75, 0.70, 0.625, 0.625, 0.7, 0.7, 0.6, 0.6, 0.5, 0.5)
+AALTOVERB_AP_MAX = (500.0, 500.0, 1000.0, 1000.0, 2600.0, 2600.0, 8000.0, 8000.0, 10000.0, 10000.0)
+AALTOVERB_AP_SCALE = (0.00476, 0.00358, 0.00973, 0.00830, 0.029, 0.021, 0.078, 0.090, 0.111, 0.096)
+AALTOVERB_DELAY_MAX = 3500.0
+AALTOVERB_DELAY_SCALE = (0.0313, 0.0371)
+
+
+def graph_aaltoverb():
+    """The reverb of examples/audio-and-midi/reverb.cpp:68-123 as a voice graph (one reverb per voice).
+
+    Returns (spec, names) where names maps a label to its node index:
+      PARAM nodes  'size2' (sizeU*2, the LinearGlide target), 'feedback', 'sr', 'vmin' (64), 'zero',
+                   'apscale0..9', 'dscaleL', 'dscaleR'
+      delay nodes  'ap1..ap10' (ALLPASS_PB), 'delayL', 'delayR' (PITCHBEND_DELAY),
+                   'glideDelay', 'glideFeedback' (GLIDE)
+    Inputs: planes 0 and 1 (ctx->inputs[0], [1]); outputs: vTapL, vTapR.
+    """
+    g = GraphSpec()
+    n = {}
+    in0, in1 = g.input(0), g.input(1)
+    for key in ("size2", "feedback", "sr", "vmin", "zero"):
+        n[key] = g.param()
+    for i in range(10):
+        n["apscale%d" % i] = g.param()
+    n["dscaleL"], n["dscaleR"] = g.param(), g.param()
+    n["glideDelay"] = g.node("GLIDE", n["size2"])          # reverb.cpp:86
+    n["glideFeedback"] = g.node("GLIDE", n["feedback"])    # :87
+    dparam = g.node("MULTIPLY", n["sr"], n["glideDelay"])  # :93
+    vt = [g.node("MAX", g.node("MULTIPLY", n["apscale%d" % i], dparam), n["vmin"]) for i in range(10)]  # :94-103
+    mono = g.node("ADD", in0, in1)                         # :106
+
+    def ap(i, x):  # r->mAp<i+1>(x, vt<i+1>)
+        n["ap%d" % (i + 1)] = g.node("ALLPASS_PB", x, vt[i])
+        return n["ap%d" % (i + 1)]
+
+    diffused = ap(3, ap(2, ap(1, ap(0, mono))))            # :107
+    dtl = g.node("MAX", g.node("SUBTRACT", g.node("MULTIPLY", n["dscaleL"], dparam), n["vmin"]), n["zero"])  # :110
+    dtr = g.node("MAX", g.node("SUBTRACT", g.node("MULTIPLY", n["dscaleR"], dparam), n["vmin"]), n["zero"])  # :111
+    fbl, fbr = g.feedback_read(), g.feedback_read()        # mvFeedbackL, mvFeedbackR (:34)
+    n["delayL"] = g.node("PITCHBEND_DELAY", fbl, dtl)
+    n["delayR"] = g.node("PITCHBEND_DELAY", fbr, dtr)
+    tap_l = ap(6, ap(4, g.node("ADD", diffused, n["delayL"])))   # :114
+    tap_r = ap(7, ap(5, g.node("ADD", diffused, n["delayR"])))   # :115
+    g.feedback_write(fbr, g.node("MULTIPLY", ap(8, tap_l), n["glideFeedback"]))   # :118
+    g.feedback_write(fbl, g.node("MULTIPLY", ap(9, tap_r), n["glideFeedback"]))   # :119
+    g.output(tap_l, tap_r)
+    return g, n

@@ -177,3 +177,213 @@ def config_5(n_instances: int = 1024, n_nodes: int = 256) -> Workload:
     state = spec.new_state(n_instances)
     state[spec.state_slot(spec.ops.index(OP_ID["NOISE"]))] = np.arange(n_instances, dtype=np.uint32)
     return Workload("chain%d" % n_nodes, spec, n_instances, coef, state)
+
+
+# ---- one small workload per functor of the rest of the L2 set ----
+
+def _rows_inputs(fn):
+    """Wrap fn(T, t0) -> [T][n_in][V][64] into the Workload.inputs signature (voice slicing included)."""
+    def inputs(n_blocks, t0=0, v0=0, v1=None, out=None):
+        x = fn(n_blocks, t0)
+        return np.ascontiguousarray(x[:, :, v0:v1])
+    return inputs
+
+
+def _noise_rows(seed: int, n_voices: int, scale: float = 1.0):
+    def fn(T, t0):
+        out = np.empty((T, 1, n_voices, BLOCK), np.float32)
+        for t in range(T):
+            rng = np.random.default_rng(seed * 100003 + t0 + t)
+            out[t, 0] = (rng.standard_normal((n_voices, BLOCK)) * scale).astype(np.float32)
+        return out
+    return fn
+
+
+def functor_case(name: str, n_voices: int = 40) -> Workload:
+    """name in FUNCTOR_CASES.  Inputs are seeded noise / gates / slowly moving delay times."""
+    V = n_voices
+    g = GraphSpec()
+    vv = np.arange(V, dtype=np.float32)
+    noise = _noise_rows(11, V)
+
+    def two_planes(a, b):
+        return lambda T, t0: np.concatenate([a(T, t0), b(T, t0)], axis=1)
+
+    def delay_rows(lo, hi, rate):
+        # per-voice triangle sweep of the delay time between lo and hi samples
+        def fn(T, t0):
+            n = (np.arange(T * BLOCK, dtype=np.float64) + t0 * BLOCK)[None, :]
+            ph = (n * rate * (1.0 + 0.01 * vv[:, None].astype(np.float64)) + 0.37 * vv[:, None]) % 1.0
+            tri = 1.0 - np.abs(2.0 * ph - 1.0)
+            d = (lo + (hi - lo) * tri).astype(np.float32)              # [V][T*64]
+            return np.ascontiguousarray(d.reshape(V, T, BLOCK).transpose(1, 0, 2))[:, None]
+        return fn
+
+    if name == "oneshot":
+        y = g.node("ONESHOT", g.input(0))
+        g.output(y)
+        coef, state = g.new_coefs(V), g.new_state(V)
+        state[1, ::2] = 1  # every other voice triggered (mGate = 1)
+        fn = lambda T, t0: np.broadcast_to(((1.0 + vv) / np.float32(300.0)).astype(np.float32)[None, None, :, None],
+                                           (T, 1, V, BLOCK)).copy()
+    elif name in ("peak", "rms"):
+        y = g.node(name.upper(), g.input(0))
+        g.output(y)
+        coef, state = g.new_coefs(V), g.new_state(V)
+        for v in range(V):
+            c = api.coeffs(name, 0.0005 + 0.001 * v)
+            coef[0:2, v] = c
+        if name == "peak":
+            coef[2] = np.float32(100 + 7 * np.arange(V))
+
+        def fn(T, t0):  # bursts: noise gated by a slow square so that the hold/decay paths both run
+            x = noise(T, t0)
+            n = (np.arange(T * BLOCK) + t0 * BLOCK).reshape(T, 1, 1, BLOCK)
+            return (x * ((n // 150) % 3 == 0)).astype(np.float32)
+    elif name == "adsr":
+        y = g.node("ADSR", g.input(0))
+        g.output(y)
+        coef, state = g.new_coefs(V), g.new_state(V)
+        for v in range(V):
+            coef[:, v] = api.coeffs("adsr", 0.0005 + 0.0001 * v, 0.001 + 0.0002 * v, 0.25 + 0.5 * v / V,
+                                    0.002, SR)
+
+        def fn(T, t0):  # gate: amplitude 0.5+v/V while ((n + 17 v) mod 700) < 400, else 0
+            n = (np.arange(T * BLOCK) + t0 * BLOCK).reshape(T, 1, 1, BLOCK)
+            on = ((n + 17 * np.arange(V).reshape(1, 1, V, 1)) % 700) < 400
+            amp = (np.float32(0.5) + vv / np.float32(V)).reshape(1, 1, V, 1)
+            return (on * amp).astype(np.float32)
+    elif name == "allpass1":
+        y = g.node("ALLPASS1", g.input(0))
+        g.output(y)
+        coef, state = g.new_coefs(V), g.new_state(V)
+        coef[0] = [api.coeffs_allpass1(0.618 + v / V) for v in range(V)]
+        fn = noise
+    elif name in ("glide", "interpolator1", "sample_glide"):
+        y = g.node(name.upper(), g.input(0))
+        g.output(y)
+        coef, state = g.new_coefs(V), g.new_state(V)
+        if name == "glide":
+            for v in range(V):
+                coef[:, v] = api.coeffs("glide", 64.0 * (1 + v % 5))
+        if name == "sample_glide":
+            for v in range(V):
+                coef[:, v] = api.coeffs("sample_glide", 10.0 + 13 * v)
+
+        def fn(T, t0):  # a staircase: the target moves every (3 + v mod 4) blocks (every 90 samples for sample_glide)
+            out = np.empty((T, 1, V, BLOCK), np.float32)
+            for t in range(T):
+                if name == "sample_glide":
+                    n = (np.arange(BLOCK) + (t0 + t) * BLOCK)[None, :]
+                    out[t, 0] = (((n // 90 + np.arange(V)[:, None]) * 37 % 11) / np.float32(11.0)).astype(np.float32)
+                else:
+                    step = (t0 + t) // (3 + np.arange(V) % 4)
+                    out[t, 0] = (((step * 29 + np.arange(V)) % 13) / np.float32(13.0)).astype(np.float32)[:, None]
+            return out
+    elif name == "integer_delay":
+        y = g.node("INTEGER_DELAY", g.input(0))
+        g.output(y)
+        coef, state = g.new_coefs(V), g.new_state(V)
+        coef[0] = np.float32((np.arange(V) * 23) % 301)
+        coef[1] = np.float32(300 + (np.arange(V) % 3) * 400)   # rings of 512 / 1024 / 2048 samples
+        fn = noise
+    elif name == "integer_delay_var":
+        y = g.node("INTEGER_DELAY_VAR", g.input(0), g.input(1))
+        g.output(y)
+        coef, state = g.new_coefs(V), g.new_state(V)
+        coef[0] = np.float32(500)
+        fn = two_planes(noise, delay_rows(0.0, 500.0, 1.0 / 900.0))
+    elif name == "fractional_delay":
+        y = g.node("FRACTIONAL_DELAY", g.input(0))
+        g.output(y)
+        coef, state = g.new_coefs(V), g.new_state(V)
+        coef[0] = (np.float32(0.3) + vv * np.float32(7.77)).astype(np.float32)
+        coef[1] = np.float32(400)
+        fn = noise
+    elif name in ("fractional_delay_var", "pitchbend_delay"):
+        y = g.node(name.upper(), g.input(0), g.input(1))
+        g.output(y)
+        coef, state = g.new_coefs(V), g.new_state(V)
+        coef[0] = np.float32(1000)
+        fn = two_planes(noise, delay_rows(0.0, 1000.0, 1.0 / 5000.0))
+    elif name in ("allpass_int", "allpass_frac"):
+        y = g.node(name.upper(), g.input(0))
+        g.output(y)
+        coef, state = g.new_coefs(V), g.new_state(V)
+        coef[0] = (np.float32(0.3) + np.float32(0.5) * vv / np.float32(V)).astype(np.float32)
+        coef[1] = (np.float32(64.0) + vv * np.float32(11.37)).astype(np.float32)
+        coef[2] = np.float32(64 + 12 * V)
+        fn = noise
+    elif name == "allpass_pb":
+        y = g.node("ALLPASS_PB", g.input(0), g.input(1))
+        g.output(y)
+        coef, state = g.new_coefs(V), g.new_state(V)
+        coef[0] = (np.float32(0.3) + np.float32(0.5) * vv / np.float32(V)).astype(np.float32)
+        coef[1] = np.float32(1000)
+        fn = two_planes(noise, delay_rows(64.0, 1000.0, 1.0 / 5000.0))
+    elif name == "feedback":
+        # y = x + 0.5 * y[previous block]: a 64-sample comb through the feedback edge
+        x = g.input(0)
+        k = g.param()
+        fb = g.feedback_read()
+        y = g.node("ADD", x, g.node("MULTIPLY", fb, k))
+        g.feedback_write(fb, y)
+        g.output(y)
+        coef, state = g.new_coefs(V), g.new_state(V)
+        coef[0] = (np.float32(0.2) + np.float32(0.7) * vv / np.float32(V)).astype(np.float32)
+        fn = noise
+    else:
+        raise KeyError(name)
+    w = Workload("functor_" + name, g, V, coef, state)
+    w.inputs = _rows_inputs(fn)  # type: ignore[assignment]
+    return w
+
+
+FUNCTOR_CASES = ("oneshot", "peak", "rms", "adsr", "allpass1", "glide", "interpolator1", "sample_glide",
+                 "integer_delay", "integer_delay_var", "fractional_delay", "fractional_delay_var",
+                 "pitchbend_delay", "allpass_int", "allpass_frac", "allpass_pb", "feedback")
+
+
+def aaltoverb_feedback(size_u: float, decay_u: float) -> float:
+    """reverb.cpp:18-19,80-83: unityToLogParam({0.8, 20}) decay projection -> feedback gain (host-side
+    scalar maths; float like the reference's)."""
+    lo, hi = np.float32(0.8), np.float32(20.0)
+    decay_time = np.float32(lo * np.power(hi / lo, np.float32(decay_u), dtype=np.float32))
+    iters = np.float32(decay_time / np.float32(size_u * 0.5))
+    if decay_u >= 1.0:
+        return 1.0
+    return float(np.power(np.float32(0.001), np.float32(1.0) / iters, dtype=np.float32))
+
+
+def config_6(n_voices: int = 4096) -> Workload:
+    """Aaltoverb (examples/audio-and-midi/reverb.cpp) x n_voices independent stereo reverbs.
+    sizeU = 0.25 + 0.5 v/V, decayU = 0.5; glide time 0.1 s; input = noise bursts on both channels."""
+    from .graph import (AALTOVERB_AP_GAINS, AALTOVERB_AP_MAX, AALTOVERB_AP_SCALE, AALTOVERB_DELAY_MAX,
+                        AALTOVERB_DELAY_SCALE, graph_aaltoverb)
+    V = n_voices
+    spec, n = graph_aaltoverb()
+    coef, state = spec.new_coefs(V), spec.new_state(V)
+    size_u = (np.float32(0.25) + np.float32(0.5) * np.arange(V, dtype=np.float32) / np.float32(V)).astype(np.float32)
+    coef[spec.coef_slot(n["size2"])] = size_u * np.float32(2.0)
+    coef[spec.coef_slot(n["feedback"])] = [aaltoverb_feedback(float(s), 0.5) for s in size_u]
+    coef[spec.coef_slot(n["sr"])] = np.float32(SR)
+    coef[spec.coef_slot(n["vmin"])] = np.float32(BLOCK)
+    for i in range(10):
+        coef[spec.coef_slot(n["apscale%d" % i])] = np.float32(AALTOVERB_AP_SCALE[i])
+        coef[spec.coef_slot(n["ap%d" % (i + 1)], 0)] = np.float32(AALTOVERB_AP_GAINS[i])
+        coef[spec.coef_slot(n["ap%d" % (i + 1)], 1)] = np.float32(AALTOVERB_AP_MAX[i])
+    coef[spec.coef_slot(n["dscaleL"])] = np.float32(AALTOVERB_DELAY_SCALE[0])
+    coef[spec.coef_slot(n["dscaleR"])] = np.float32(AALTOVERB_DELAY_SCALE[1])
+    coef[spec.coef_slot(n["delayL"])] = coef[spec.coef_slot(n["delayR"])] = np.float32(AALTOVERB_DELAY_MAX)
+    glide = api.coeffs("glide", 0.1 * SR)
+    for key in ("glideDelay", "glideFeedback"):
+        _set(coef, spec, n[key], np.repeat(glide[:, None], V, 1))
+    w = Workload("aaltoverb", spec, V, coef, state)
+    nl, nr = _noise_rows(5, V, 0.25), _noise_rows(6, V, 0.25)
+
+    def fn(T, t0):  # a burst of noise for 6 blocks out of every 40, then the tail rings
+        x = np.concatenate([nl(T, t0), nr(T, t0)], axis=1)
+        on = ((np.arange(T) + t0) % 40 < 6).reshape(T, 1, 1, 1)
+        return (x * on).astype(np.float32)
+    w.inputs = _rows_inputs(fn)  # type: ignore[assignment]
+    return w

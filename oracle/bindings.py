@@ -55,7 +55,8 @@ class _Oracle:
         getattr(L, p + "graph_set_state").argtypes = [_vp, _vp]
         getattr(L, p + "graph_get_state").argtypes = [_vp, _vp]
         for name, nargs in (("lopass", 2), ("hipass", 2), ("bandpass", 2), ("loshelf", 3),
-                            ("hishelf", 3), ("bell", 3), ("onepole", 1)):
+                            ("hishelf", 3), ("bell", 3), ("onepole", 1), ("peak", 1), ("rms", 1),
+                            ("adsr", 5), ("glide", 1), ("sample_glide", 1)):
             fn = getattr(L, p + "coeffs_" + name)
             fn.argtypes = [ctypes.c_float] * nargs + [_vp]
             fn.restype = None
@@ -63,11 +64,13 @@ class _Oracle:
         getattr(L, p + "coeffs_dcblocker").restype = ctypes.c_float
         getattr(L, p + "db_to_gain").argtypes = [ctypes.c_float]
         getattr(L, p + "db_to_gain").restype = ctypes.c_float
+        getattr(L, p + "coeffs_allpass1").argtypes = [ctypes.c_float]
+        getattr(L, p + "coeffs_allpass1").restype = ctypes.c_float
 
     # -- coefficient design --
     def coeffs(self, kind: str, *args: float) -> np.ndarray:
         n = {"lopass": 3, "hipass": 4, "bandpass": 3, "loshelf": 5, "hishelf": 6, "bell": 4,
-             "onepole": 2}[kind]
+             "onepole": 2, "peak": 2, "rms": 2, "adsr": 4, "glide": 2, "sample_glide": 2}[kind]
         out = np.zeros(n, np.float32)
         getattr(self.lib, self.prefix + "coeffs_" + kind)(*[ctypes.c_float(a) for a in args],
                                                           _ptr(out))
@@ -75,6 +78,9 @@ class _Oracle:
 
     def coeffs_dcblocker(self, omega: float) -> float:
         return float(getattr(self.lib, self.prefix + "coeffs_dcblocker")(omega))
+
+    def coeffs_allpass1(self, d: float) -> float:
+        return float(getattr(self.lib, self.prefix + "coeffs_allpass1")(d))
 
     def db_to_gain(self, db: float) -> float:
         return float(getattr(self.lib, self.prefix + "db_to_gain")(db))
@@ -137,6 +143,19 @@ class RefOracle(_Oracle):
         self.lib.mlref_chain_sine_lopass_gain.restype = ctypes.c_double
         self.lib.mlref_chain_sine_lopass_gain.argtypes = [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp,
                                                           _vp, _vp, _vp, ctypes.c_int, ctypes.c_int]
+
+        self.lib.mlref_aaltoverb.restype = ctypes.c_double
+        self.lib.mlref_aaltoverb.argtypes = [ctypes.c_int, _vp, _vp, ctypes.c_float, ctypes.c_float,
+                                             ctypes.c_float, ctypes.c_int]
+
+    def aaltoverb(self, inp: np.ndarray, size_u2: float, feedback: float, glide_samples: float,
+                  repeats: int = 1):
+        """The reverb example's own per-vector body for ONE reverb; inp [T][2][64] -> (out, seconds)."""
+        inp = np.ascontiguousarray(inp, np.float32)
+        out = np.empty_like(inp)
+        sec = self.lib.mlref_aaltoverb(inp.shape[0], _ptr(inp), _ptr(out), size_u2, feedback,
+                                       glide_samples, repeats)
+        return out, float(sec)
 
     def _process(self, h, inp, out, mix, T, nthreads, mix_mode, n_shards):
         if mix is not None and mix_mode != 0:

@@ -666,6 +666,345 @@ static void fdn8_process(fdn8_mem* m, uint32_t* st, const float* coef32, const f
   }
 }
 
+
+/* ------------------------------------------------------------------ */
+/* the rest of the L2 functor set                    */
+
+/* OneShotGen::operator(), G:235-252 */
+static void gen_oneshot(uint32_t* st, const float* freq, float* y)
+{
+  uint32_t om = st[0], gate = st[1], prev = st[2];
+  for (int n = 0; n < NB; ++n)
+  {
+    int32_t isteps = cvt_round(freq[n] * 4294967296.0f);
+    om += (uint32_t)isteps * gate;
+    if (om < prev)
+    {
+      gate = 0;
+      om = 0;
+    }
+    prev = om;
+    y[n] = unsigned_to_float(om) * (1.0f / 4294967296.0f);
+  }
+  st[0] = om, st[1] = gate, st[2] = prev;
+}
+
+/* tail shared by Peak and RMS, F:613,651: select(sqrtApprox(vy), 0, vy > 1e-20) */
+static inline float follower_out(float v)
+{
+  return sel_bits(v * sse_rsqrt(v), 0.f, f2u(mask_f(v > (float)(1e-20))));
+}
+/* Peak::operator(), F:584-614.  st: y1, peakHoldCounter; c: a0, b1, peakHoldSamples */
+static void flt_peak(uint32_t* st, const float* c, const float* x, float* y)
+{
+  float y1 = u2f(st[0]);
+  int32_t counter = (int32_t)st[1];
+  const float a0 = c[0], b1 = c[1];
+  const int32_t hold = (int32_t)c[2];
+  for (int n = 0; n < NB; ++n)
+  {
+    const float xs = x[n] * x[n];
+    if (xs > y1)
+    {
+      y1 = xs;
+      counter = hold;
+    }
+    else if (counter <= 0)
+      y1 = a0 * xs + b1 * y1;
+    y[n] = follower_out(y1);
+  }
+  if (counter > 0) counter -= NB;
+  st[0] = f2u(y1), st[1] = (uint32_t)counter;
+}
+/* RMS::operator(), F:638-652 */
+static void flt_rms(uint32_t* st, const float* c, const float* x, float* y)
+{
+  float y1 = u2f(st[0]);
+  for (int n = 0; n < NB; ++n)
+  {
+    y1 = c[0] * (x[n] * x[n]) + c[1] * y1;
+    y[n] = follower_out(y1);
+  }
+  st[0] = f2u(y1);
+}
+
+/* ADSR::processSample, F:692-784.  st: y y1 x1 threshold target k amp segment; c: ka kd s kr */
+static void flt_adsr(uint32_t* st, const float* c, const float* x, float* out)
+{
+  float y = u2f(st[0]), y1 = u2f(st[1]), x1 = u2f(st[2]), threshold = u2f(st[3]);
+  float target = u2f(st[4]), k = u2f(st[5]), amp = u2f(st[6]);
+  int32_t segment = (int32_t)st[7];
+  const float ka = c[0], kd = c[1], sus = c[2], kr = c[3];
+  enum { A = 0, D = 1, S = 2, R = 3, off = 4 };
+  for (int n = 0; n < NB; ++n)
+  {
+    const float xn = x[n];
+    if (segment == off && xn == 0.f)
+    {
+      out[n] = 0.f;
+      continue;
+    }
+    const int crossed = ((y1 > threshold) != (y > threshold));
+    int recalc = 0;
+    if (crossed && segment < off)
+    {
+      segment++;
+      recalc = 1;
+    }
+    const int trigOn = (x1 == 0.f) && (xn > 0.f);
+    const int trigOff = (x1 > 0.f) && (xn == 0.f);
+    if (trigOn)
+    {
+      segment = A;
+      amp = xn;
+      recalc = 1;
+    }
+    else if (trigOff)
+    {
+      segment = R;
+      recalc = 1;
+    }
+    if (recalc)
+    {
+      float startEnv = 0.f, endEnv = 0.f;
+      switch (segment)
+      {
+        case A: startEnv = 0.f, endEnv = 1.f, k = ka; break;
+        case D: startEnv = 1.f, endEnv = sus, k = kd; break;
+        case S: startEnv = sus, endEnv = sus, k = 0.f, y1 = sus, y = sus; break;
+        case R: startEnv = sus, endEnv = 0.f, k = kr; break;
+        default: startEnv = 0.f, endEnv = 0.f, k = 0.f, y1 = 0.f, y = 0.f; break;
+      }
+      const float segmentBias = (endEnv - startEnv) * 0.1f;
+      threshold = endEnv;
+      target = endEnv + segmentBias;
+    }
+    x1 = xn;
+    y1 = y;
+    y = y + k * (target - y);
+    out[n] = y * amp;
+  }
+  st[0] = f2u(y), st[1] = f2u(y1), st[2] = f2u(x1), st[3] = f2u(threshold);
+  st[4] = f2u(target), st[5] = f2u(k), st[6] = f2u(amp), st[7] = (uint32_t)segment;
+}
+
+/* Allpass1::processSample, F:944-952 */
+static inline float allpass1_tick(float* x1, float* y1, float a, float x)
+{
+  float y = *x1 + (x - *y1) * a;
+  *x1 = x;
+  *y1 = y;
+  return y;
+}
+static void flt_allpass1(uint32_t* st, const float* c, const float* x, float* y)
+{
+  float x1 = u2f(st[0]), y1 = u2f(st[1]);
+  for (int n = 0; n < NB; ++n) y[n] = allpass1_tick(&x1, &y1, c[0], x[n]);
+  st[0] = f2u(x1), st[1] = f2u(y1);
+}
+
+/* LinearGlide::operator()(float), G:459-505.  curr = mCurrVec (delay memory);
+ * st: step, target, vectorsRemaining; c: vectorsPerGlide, dyPerVector */
+static void gen_glide(uint32_t* st, const float* c, float f, float* curr, float* y)
+{
+  float step = u2f(st[0]), target = u2f(st[1]);
+  int32_t remaining = (int32_t)st[2];
+  const int32_t per = (int32_t)c[0];
+  const float dyPerVector = c[1];
+  if (f != target)
+  {
+    target = f;
+    remaining = per;
+  }
+  if (remaining < 0)
+  {
+  }
+  else if (remaining == 0)
+  {
+    for (int n = 0; n < NB; ++n) curr[n] = target;
+    step = 0.f;
+    remaining--;
+  }
+  else if (remaining == per)
+  {
+    const float cv = curr[NB - 1];
+    const float dydv = (target - cv) * dyPerVector;
+    step = dydv;
+    for (int n = 0; n < NB; ++n) curr[n] = cv + ((float)(n + 1) / (float)NB) * step; /* kUnityRampVec G:409-410 */
+    remaining--;
+  }
+  else
+  {
+    for (int n = 0; n < NB; ++n) curr[n] = curr[n] + step;
+    remaining--;
+  }
+  memcpy(y, curr, sizeof(float) * NB);
+  st[0] = f2u(step), st[1] = f2u(target), st[2] = (uint32_t)remaining;
+}
+/* Interpolator1::operator()(float), G:416-422 */
+static void gen_interp1(uint32_t* st, float f, float* y)
+{
+  const float cur = u2f(st[0]);
+  const float dydt = f - cur;
+  for (int n = 0; n < NB; ++n) y[n] = cur + ((float)(n + 1) / (float)NB) * dydt;
+  st[0] = f2u(f);
+}
+/* SampleAccurateLinearGlide::nextSample, G:541-582 */
+static void gen_sample_glide(uint32_t* st, const float* c, const float* x, float* y)
+{
+  float curr = u2f(st[0]), step = u2f(st[1]), target = u2f(st[2]);
+  int32_t remaining = (int32_t)st[3];
+  const int32_t per = (int32_t)c[0];
+  for (int n = 0; n < NB; ++n)
+  {
+    if (x[n] != target)
+    {
+      target = x[n];
+      remaining = per;
+    }
+    if (remaining < 0)
+    {
+    }
+    else if (remaining == 0)
+    {
+      curr = target;
+      step = 0.f;
+      remaining--;
+    }
+    else if (remaining == per)
+    {
+      step = (target - curr) * c[1];
+      remaining--;
+    }
+    else
+    {
+      curr += step;
+      remaining--;
+    }
+    y[n] = curr;
+  }
+  st[0] = f2u(curr), st[1] = f2u(step), st[2] = f2u(target), st[3] = (uint32_t)remaining;
+}
+
+/* ---- delay memory of one voice of one node: up to 2 IntegerDelay rings + one 64-float row ---- */
+typedef struct delay_mem
+{
+  float* ring[2];   /* IntegerDelay::mBuffer, F:803 */
+  uint32_t mask[2]; /* mLengthMask */
+  uint32_t widx[2]; /* mWriteIndex */
+  float row[NB];    /* Allpass::vy1 (F:1115), LinearGlide::mCurrVec (G:435), feedback DSPVector */
+} delay_mem;
+
+/* IntegerDelay::setMaxDelayInSamples(float d), F:822-830 */
+static void ring_alloc(delay_mem* m, int r, float d)
+{
+  int dMax = (int)floorf(d);
+  int size = 1 << bits_to_contain(dMax + NB);
+  free(m->ring[r]);
+  m->ring[r] = (float*)calloc((size_t)size, sizeof(float));
+  m->mask[r] = (uint32_t)size - 1u;
+  m->widx[r] = 0;
+}
+/* IntegerDelay::operator()(vx) with delay d, F:834-875 */
+static void ring_block(delay_mem* m, int r, int d, const float* x, float* y)
+{
+  float* buf = m->ring[r];
+  const uint32_t mask = m->mask[r], w = m->widx[r];
+  for (int i = 0; i < NB; ++i) buf[(w + (uint32_t)i) & mask] = x[i];
+  const uint32_t rd = (w - (uint32_t)d) & mask;
+  for (int i = 0; i < NB; ++i) y[i] = buf[(rd + (uint32_t)i) & mask];
+  m->widx[r] = (w + NB) & mask;
+}
+/* IntegerDelay::processSample, F:898-912 */
+static inline float ring_tick(delay_mem* m, int r, int d, float x)
+{
+  float* buf = m->ring[r];
+  const uint32_t mask = m->mask[r], w = m->widx[r];
+  buf[w] = x;
+  const float y = buf[(w - (uint32_t)d) & mask];
+  m->widx[r] = (w + 1u) & mask;
+  return y;
+}
+/* FractionalDelay::setDelayInSamples, F:993-1008 + Allpass1::makeCoeffs F:936-941 */
+static void frac_split(float d, int32_t* delayInt, float* apCoeff)
+{
+  float fDelayInt = floorf(d);
+  int32_t di = cvt_trunc(fDelayInt);
+  float frac = d - fDelayInt;
+  if ((frac < 0.618f) && (di > 0))
+  {
+    frac += 1.f;
+    di -= 1;
+  }
+  *delayInt = di;
+  float xm1 = (frac - 1.f);
+  *apCoeff = -0.53f * xm1 + 0.24f * xm1 * xm1;
+}
+/* IntegerDelay::operator()(x, delay), F:877-896 */
+static void delay_int_var(delay_mem* m, const float* x, const float* dl, float* y)
+{
+  for (int n = 0; n < NB; ++n) y[n] = ring_tick(m, 0, cvt_trunc(dl[n]), x[n]);
+}
+/* FractionalDelay::operator()(vx), F:1014: allpass(integerDelay(vx)) */
+static void delay_frac(delay_mem* m, uint32_t* st, float d, const float* x, float* y)
+{
+  int32_t di;
+  float a, t[NB];
+  frac_split(d, &di, &a);
+  ring_block(m, 0, di, x, t);
+  float x1 = u2f(st[0]), y1 = u2f(st[1]);
+  for (int n = 0; n < NB; ++n) y[n] = allpass1_tick(&x1, &y1, a, t[n]);
+  st[0] = f2u(x1), st[1] = f2u(y1);
+}
+/* FractionalDelay::operator()(vx, vDelay), F:1033-1042 */
+static void delay_frac_var(delay_mem* m, uint32_t* st, const float* x, const float* dl, float* y)
+{
+  float x1 = u2f(st[0]), y1 = u2f(st[1]);
+  for (int n = 0; n < NB; ++n)
+  {
+    int32_t di;
+    float a;
+    frac_split(dl[n], &di, &a);
+    y[n] = allpass1_tick(&x1, &y1, a, ring_tick(m, 0, di, x[n]));
+  }
+  st[0] = f2u(x1), st[1] = f2u(y1);
+}
+/* PitchbendableDelay::operator(), F:1097-1104 with the tick/fade tables of F:1053-1076.
+ * st: 2 x {x1, y1, intDelay, apCoeff} */
+static void delay_pitchbend(delay_mem* m, uint32_t* st, const float* x, const float* dl, float* y)
+{
+  float o[2][NB];
+  for (int k = 0; k < 2; ++k)
+  {
+    float x1 = u2f(st[4 * k]), y1 = u2f(st[4 * k + 1]);
+    int32_t di = (int32_t)st[4 * k + 2];
+    float a = u2f(st[4 * k + 3]);
+    for (int n = 0; n < NB; ++n)
+    {
+      /* delay 1 may change when n % 32 == 16, delay 2 when n % 32 == 0 */
+      if ((n & 31) == (k == 0 ? 16 : 0)) frac_split(dl[n], &di, &a);
+      o[k][n] = allpass1_tick(&x1, &y1, a, ring_tick(m, k, di, x[n]));
+    }
+    st[4 * k] = f2u(x1), st[4 * k + 1] = f2u(y1), st[4 * k + 2] = (uint32_t)di, st[4 * k + 3] = f2u(a);
+  }
+  for (int n = 0; n < NB; ++n)
+  {
+    const int r = n & 31;
+    const float fade = 2.f * (r > 16 ? 1.0f - (float)r / 32.f : (float)r / 32.f);
+    y[n] = o[0][n] + fade * (o[1][n] - o[0][n]); /* lerp, O:744 */
+  }
+}
+/* Allpass<DELAY>::operator(), F:1135-1153: the delay call is made by the caller */
+static void allpass_pre(const delay_mem* m, float gain, const float* x, float* delayInput, float* y)
+{
+  const float g = -gain;
+  for (int n = 0; n < NB; ++n)
+  {
+    delayInput[n] = x[n] - m->row[n] * g;
+    y[n] = delayInput[n] * g + m->row[n];
+  }
+}
+
 /* ------------------------------------------------------------------ */
 /* graph runner                                                         */
 
@@ -695,6 +1034,7 @@ typedef struct mlport_graph
   uint32_t* state; /* [n_state][V] */
   float* coef;     /* [n_coef][V] */
   fdn8_mem** fdn;  /* [n_nodes] -> array of V, or NULL */
+  delay_mem** dmem; /* [n_nodes] -> array of V, or NULL */
 } mlport_graph;
 
 int mlport_abi_version(void) { return MLB_ABI_VERSION; }
@@ -711,6 +1051,16 @@ void mlport_graph_destroy(mlport_graph* g)
         free(g->fdn[i]);
       }
     free(g->fdn);
+  }
+  if (g->dmem)
+  {
+    for (int i = 0; i < g->n_nodes; ++i)
+      if (g->dmem[i])
+      {
+        for (int v = 0; v < g->V; ++v) free(g->dmem[i][v].ring[0]), free(g->dmem[i][v].ring[1]);
+        free(g->dmem[i]);
+      }
+    free(g->dmem);
   }
   free(g->nodes);
   free(g->outs);
@@ -735,6 +1085,7 @@ mlport_graph* mlport_graph_create(const mlb_node* nodes, int n_nodes, const int3
   g->st_off = (int*)calloc((size_t)n_nodes, sizeof(int));
   g->co_off = (int*)calloc((size_t)n_nodes, sizeof(int));
   g->fdn = (fdn8_mem**)calloc((size_t)n_nodes, sizeof(fdn8_mem*));
+  g->dmem = (delay_mem**)calloc((size_t)n_nodes, sizeof(delay_mem*));
   for (int i = 0; i < n_nodes; ++i)
   {
     int a, b, c;
@@ -763,6 +1114,48 @@ mlport_graph* mlport_graph_create(const mlb_node* nodes, int n_nodes, const int3
         fdn8_mem_init(&g->fdn[i][v], c32);
       }
     }
+  for (int i = 0; i < n_nodes; ++i)
+  {
+    int n_rows = 0, n_rings = 0;
+    switch (nodes[i].op)
+    {
+#define MLB_X_MEM(NAME, rows, rings) \
+  case MLB_OP_##NAME: n_rows = rows, n_rings = rings; break;
+      MLB_OP_MEM_TABLE(MLB_X_MEM)
+#undef MLB_X_MEM
+      default: break;
+    }
+    if (n_rows == 0 && n_rings == 0) continue;
+    g->dmem[i] = (delay_mem*)calloc((size_t)V, sizeof(delay_mem));
+    int a, b, nco;
+    op_info(nodes[i].op, &a, &b, &nco);
+    for (int v = 0; v < V; ++v)
+    {
+      if (n_rings == 0) continue;
+      /* the last coefficient word is the functor's setMaxDelayInSamples argument */
+      float md = g->coef[(size_t)(g->co_off[i] + nco - 1) * V + v];
+      switch (nodes[i].op)
+      {
+        case MLB_OP_ALLPASS_INT:  /* Allpass::setMaxDelayInSamples: d - 64, F:1125-1128 */
+          ring_alloc(&g->dmem[i][v], 0, md - (float)NB);
+          break;
+        case MLB_OP_ALLPASS_FRAC: /* ... then FractionalDelay: floorf(d), F:1010 */
+          ring_alloc(&g->dmem[i][v], 0, floorf(md - (float)NB));
+          break;
+        case MLB_OP_ALLPASS_PB:
+          ring_alloc(&g->dmem[i][v], 0, floorf(md - (float)NB));
+          ring_alloc(&g->dmem[i][v], 1, floorf(md - (float)NB));
+          break;
+        case MLB_OP_PITCHBEND_DELAY:
+          ring_alloc(&g->dmem[i][v], 0, floorf(md));
+          ring_alloc(&g->dmem[i][v], 1, floorf(md));
+          break;
+        case MLB_OP_FRACTIONAL_DELAY:
+        case MLB_OP_FRACTIONAL_DELAY_VAR: ring_alloc(&g->dmem[i][v], 0, floorf(md)); break;
+        default: ring_alloc(&g->dmem[i][v], 0, md); break;
+      }
+    }
+  }
   return g;
 }
 
@@ -852,6 +1245,50 @@ static void run_voices(mlport_graph* g, const float* in, float* out, int T, int 
           case MLB_OP_INTEGRATOR: flt_integrator(st, co, a, y); break;
           case MLB_OP_FDN8: fdn8_process(&g->fdn[i][v], st, co, a, y, rows2[i]); break;
           case MLB_OP_FDN8_R: memcpy(y, rows2[nd->in[0]], sizeof(float) * NB); break;
+          case MLB_OP_ONESHOT: gen_oneshot(st, a, y); break;
+          case MLB_OP_PEAK: flt_peak(st, co, a, y); break;
+          case MLB_OP_RMS: flt_rms(st, co, a, y); break;
+          case MLB_OP_ADSR: flt_adsr(st, co, a, y); break;
+          case MLB_OP_ALLPASS1: flt_allpass1(st, co, a, y); break;
+          case MLB_OP_GLIDE: gen_glide(st, co, a[0], g->dmem[i][v].row, y); break;
+          case MLB_OP_INTERPOLATOR1: gen_interp1(st, a[0], y); break;
+          case MLB_OP_SAMPLE_GLIDE: gen_sample_glide(st, co, a, y); break;
+          case MLB_OP_INTEGER_DELAY: ring_block(&g->dmem[i][v], 0, (int)co[0], a, y); break;
+          case MLB_OP_INTEGER_DELAY_VAR: delay_int_var(&g->dmem[i][v], a, b, y); break;
+          case MLB_OP_FRACTIONAL_DELAY: delay_frac(&g->dmem[i][v], st, co[0], a, y); break;
+          case MLB_OP_FRACTIONAL_DELAY_VAR: delay_frac_var(&g->dmem[i][v], st, a, b, y); break;
+          case MLB_OP_PITCHBEND_DELAY: delay_pitchbend(&g->dmem[i][v], st, a, b, y); break;
+          case MLB_OP_ALLPASS_INT:
+          {
+            /* Allpass::setDelayInSamples(d): IntegerDelay::setDelayInSamples(int(d - 64)), F:1123 */
+            delay_mem* m = &g->dmem[i][v];
+            float din[NB];
+            allpass_pre(m, co[0], a, din, y);
+            ring_block(m, 0, (int)(co[1] - (float)NB), din, m->row);
+            break;
+          }
+          case MLB_OP_ALLPASS_FRAC:
+          {
+            delay_mem* m = &g->dmem[i][v];
+            float din[NB];
+            allpass_pre(m, co[0], a, din, y);
+            delay_frac(m, st, co[1] - (float)NB, din, m->row);
+            break;
+          }
+          case MLB_OP_ALLPASS_PB:
+          {
+            delay_mem* m = &g->dmem[i][v];
+            float din[NB], dl[NB];
+            allpass_pre(m, co[0], a, din, y);
+            for (int n = 0; n < NB; ++n) dl[n] = b[n] - (float)NB; /* F:1151 */
+            delay_pitchbend(m, st, din, dl, m->row);
+            break;
+          }
+          case MLB_OP_FEEDBACK_READ: memcpy(y, g->dmem[i][v].row, sizeof(float) * NB); break;
+          case MLB_OP_FEEDBACK_WRITE:
+            memcpy(g->dmem[nd->iarg][v].row, a, sizeof(float) * NB);
+            memcpy(y, a, sizeof(float) * NB);
+            break;
           default:
             if (nin == 1)
               for (int n = 0; n < NB; ++n) y[n] = op1(nd->op, a[n]);
@@ -1025,3 +1462,35 @@ void mlport_coeffs_onepole(float omega, float* r) /* F:458-462 */
 }
 float mlport_coeffs_dcblocker(float omega) { return cosf(omega); } /* F:498 */
 float mlport_db_to_gain(float dB) { return powf(10.f, dB / 40.f); } /* F:30 */
+
+/* ---- SURVEY 8(f) row 2 coefficient design ---- */
+void mlport_coeffs_peak(float omega, float* r) { mlport_coeffs_onepole(omega, r); } /* F:578-582 */
+void mlport_coeffs_rms(float omega, float* r) { mlport_coeffs_onepole(omega, r); }  /* F:632-636 */
+void mlport_coeffs_adsr(float a, float d, float s, float rel, float sr, float* o) /* F:676-683 */
+{
+  const float minSegmentTime = 0.0002f;
+  const float invSr = 1.0f / sr;
+  o[0] = K_TWO_PI * invSr / sse_max(a, minSegmentTime);
+  o[1] = K_TWO_PI * invSr / sse_max(d, minSegmentTime);
+  o[2] = s;
+  o[3] = K_TWO_PI * invSr / sse_max(rel, minSegmentTime);
+}
+float mlport_coeffs_allpass1(float d) /* F:936-941 */
+{
+  float xm1 = (d - 1.f);
+  return -0.53f * xm1 + 0.24f * xm1 * xm1;
+}
+void mlport_coeffs_glide(float t, float* o) /* G:443-448 */
+{
+  int n = (int)(t / NB);
+  if (n < 1) n = 1;
+  o[0] = (float)n;
+  o[1] = 1.0f / ((float)n + 0.f);
+}
+void mlport_coeffs_sample_glide(float t, float* o) /* G:527-532 */
+{
+  int n = (int)t;
+  if (n < 1) n = 1;
+  o[0] = (float)n;
+  o[1] = 1.0f / (float)n;
+}

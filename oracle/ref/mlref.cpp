@@ -253,6 +253,220 @@ struct PFDN8 : Proc
   }
 };
 
+
+// ---- section 8(f) row 2: the rest of the L2 functor set ----
+struct POneShot : Proc
+{
+  OneShotGen g;
+  void loadState(const uint32_t* s) override { g.mOmega32 = s[0], g.mGate = s[1], g.mOmegaPrev = s[2]; }
+  void storeState(uint32_t* s) const override { s[0] = g.mOmega32, s[1] = g.mGate, s[2] = g.mOmegaPrev; }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return g(*in[0]); }
+};
+struct PPeak : Proc
+{
+  Peak f;
+  void setCoefs(const float* c) override
+  {
+    f.coeffs = {c[0], c[1]};
+    f.peakHoldSamples = static_cast<int>(c[2]);
+  }
+  void loadState(const uint32_t* s) override { f.y1 = u2f(s[0]), f.peakHoldCounter = (int)s[1]; }
+  void storeState(uint32_t* s) const override { s[0] = f2u(f.y1), s[1] = (uint32_t)f.peakHoldCounter; }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0]); }
+};
+struct PRMS : Proc
+{
+  RMS f;
+  void setCoefs(const float* c) override { f.coeffs = {c[0], c[1]}; }
+  void loadState(const uint32_t* s) override { f.y1 = u2f(s[0]); }
+  void storeState(uint32_t* s) const override { s[0] = f2u(f.y1); }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0]); }
+};
+struct PADSR : Proc
+{
+  ADSR f;
+  void setCoefs(const float* c) override { f.coeffs = {c[0], c[1], c[2], c[3]}; }
+  void loadState(const uint32_t* s) override
+  {
+    f.y = u2f(s[0]), f.y1 = u2f(s[1]), f.x1 = u2f(s[2]), f.threshold = u2f(s[3]);
+    f.target = u2f(s[4]), f.k = u2f(s[5]), f.amp = u2f(s[6]), f.segment = (int)s[7];
+  }
+  void storeState(uint32_t* s) const override
+  {
+    s[0] = f2u(f.y), s[1] = f2u(f.y1), s[2] = f2u(f.x1), s[3] = f2u(f.threshold);
+    s[4] = f2u(f.target), s[5] = f2u(f.k), s[6] = f2u(f.amp), s[7] = (uint32_t)f.segment;
+  }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0]); }
+};
+struct PAllpass1 : Proc
+{
+  Allpass1 f{0.f};
+  void setCoefs(const float* c) override { f.coeffs = c[0]; }
+  void loadState(const uint32_t* s) override { f.x1 = u2f(s[0]), f.y1 = u2f(s[1]); }
+  void storeState(uint32_t* s) const override { s[0] = f2u(f.x1), s[1] = f2u(f.y1); }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0]); }
+};
+struct PGlide : Proc
+{
+  LinearGlide g;
+  void setCoefs(const float* c) override
+  {
+    g.mVectorsPerGlide = static_cast<int>(c[0]);
+    g.mDyPerVector = c[1];
+  }
+  void loadState(const uint32_t* s) override
+  {
+    g.mStepVec = DSPVector(u2f(s[0]));
+    g.mTargetValue = u2f(s[1]);
+    g.mVectorsRemaining = (int)s[2];
+  }
+  void storeState(uint32_t* s) const override
+  {
+    s[0] = f2u(g.mStepVec[0]), s[1] = f2u(g.mTargetValue), s[2] = (uint32_t)g.mVectorsRemaining;
+  }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return g((*in[0])[0]); }
+};
+struct PInterp1 : Proc
+{
+  Interpolator1 g;
+  void loadState(const uint32_t* s) override { g.currentValue = u2f(s[0]); }
+  void storeState(uint32_t* s) const override { s[0] = f2u(g.currentValue); }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return g((*in[0])[0]); }
+};
+struct PSampleGlide : Proc
+{
+  SampleAccurateLinearGlide g;
+  void setCoefs(const float* c) override
+  {
+    g.mSamplesPerGlide = static_cast<int>(c[0]);
+    g.mDyPerSample = c[1];
+  }
+  void loadState(const uint32_t* s) override
+  {
+    g.mCurrValue = u2f(s[0]), g.mStepValue = u2f(s[1]), g.mTargetValue = u2f(s[2]);
+    g.mSamplesRemaining = (int)s[3];
+  }
+  void storeState(uint32_t* s) const override
+  {
+    s[0] = f2u(g.mCurrValue), s[1] = f2u(g.mStepValue), s[2] = f2u(g.mTargetValue);
+    s[3] = (uint32_t)g.mSamplesRemaining;
+  }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override
+  {
+    DSPVector y;
+    for (int n = 0; n < kFloatsPerDSPVector; ++n) y[n] = g.nextSample((*in[0])[n]);
+    return y;
+  }
+};
+struct PIntDelay : Proc
+{
+  IntegerDelay d;
+  void setCoefs(const float* c) override
+  {
+    d.setMaxDelayInSamples(c[1]);
+    d.setDelayInSamples(static_cast<int>(c[0]));
+  }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return d(*in[0]); }
+};
+struct PIntDelayVar : Proc
+{
+  IntegerDelay d;
+  void setCoefs(const float* c) override { d.setMaxDelayInSamples(c[0]); }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return d(*in[0], *in[1]); }
+};
+#define AP1_STATE(ap)                                                                   \
+  void loadState(const uint32_t* s) override { (ap).x1 = u2f(s[0]), (ap).y1 = u2f(s[1]); } \
+  void storeState(uint32_t* s) const override { s[0] = f2u((ap).x1), s[1] = f2u((ap).y1); }
+struct PFracDelay : Proc
+{
+  FractionalDelay d;
+  void setCoefs(const float* c) override
+  {
+    d.setMaxDelayInSamples(c[1]);
+    d.setDelayInSamples(c[0]);
+  }
+  AP1_STATE(d.mAllpassSection)
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return d(*in[0]); }
+};
+struct PFracDelayVar : Proc
+{
+  FractionalDelay d;
+  void setCoefs(const float* c) override { d.setMaxDelayInSamples(c[0]); }
+  AP1_STATE(d.mAllpassSection)
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return d(*in[0], *in[1]); }
+};
+inline void pbLoad(PitchbendableDelay& d, const uint32_t* s)
+{
+  FractionalDelay* fd[2] = {&d.mDelay1, &d.mDelay2};
+  for (int i = 0; i < 2; ++i)
+  {
+    fd[i]->mAllpassSection.x1 = u2f(s[4 * i]);
+    fd[i]->mAllpassSection.y1 = u2f(s[4 * i + 1]);
+    fd[i]->mIntegerDelay.mIntDelayInSamples = (int)s[4 * i + 2];
+    fd[i]->mAllpassSection.coeffs = u2f(s[4 * i + 3]);
+  }
+}
+inline void pbStore(const PitchbendableDelay& d, uint32_t* s)
+{
+  const FractionalDelay* fd[2] = {&d.mDelay1, &d.mDelay2};
+  for (int i = 0; i < 2; ++i)
+  {
+    s[4 * i] = f2u(fd[i]->mAllpassSection.x1);
+    s[4 * i + 1] = f2u(fd[i]->mAllpassSection.y1);
+    s[4 * i + 2] = (uint32_t)fd[i]->mIntegerDelay.mIntDelayInSamples;
+    s[4 * i + 3] = f2u(fd[i]->mAllpassSection.coeffs);
+  }
+}
+struct PPitchbend : Proc
+{
+  PitchbendableDelay d;
+  void setCoefs(const float* c) override { d.setMaxDelayInSamples(c[0]); }
+  void loadState(const uint32_t* s) override { pbLoad(d, s); }
+  void storeState(uint32_t* s) const override { pbStore(d, s); }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return d(*in[0], *in[1]); }
+};
+struct PAllpassInt : Proc
+{
+  Allpass<IntegerDelay> f;
+  void setCoefs(const float* c) override
+  {
+    f.mGain = c[0];
+    f.setMaxDelayInSamples(c[2]);
+    f.setDelayInSamples(c[1]);
+  }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0]); }
+};
+struct PAllpassFrac : Proc
+{
+  Allpass<FractionalDelay> f;
+  void setCoefs(const float* c) override
+  {
+    f.mGain = c[0];
+    f.setMaxDelayInSamples(c[2]);
+    f.setDelayInSamples(c[1]);
+  }
+  AP1_STATE(f.mDelay.mAllpassSection)
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0]); }
+};
+struct PAllpassPB : Proc
+{
+  Allpass<PitchbendableDelay> f;
+  void setCoefs(const float* c) override
+  {
+    f.mGain = c[0];
+    f.setMaxDelayInSamples(c[1]);
+  }
+  void loadState(const uint32_t* s) override { pbLoad(f.mDelay, s); }
+  void storeState(uint32_t* s) const override { pbStore(f.mDelay, s); }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0], *in[1]); }
+};
+// a DSPVector member kept between processVector calls (reverb.cpp:34,115-116)
+struct PFeedback : Proc
+{
+  DSPVector held{0.f};
+  DSPVector run(const DSPVector* const*, DSPVector*) override { return held; }
+};
+
 struct PStateless : Proc
 {
   int op;
@@ -344,7 +558,25 @@ Proc* makeProc(int op)
     case MLB_OP_DIFFERENTIATOR: return new PDifferentiator;
     case MLB_OP_INTEGRATOR: return new PIntegrator;
     case MLB_OP_FDN8: return new PFDN8;
+    case MLB_OP_ONESHOT: return new POneShot;
+    case MLB_OP_PEAK: return new PPeak;
+    case MLB_OP_RMS: return new PRMS;
+    case MLB_OP_ADSR: return new PADSR;
+    case MLB_OP_ALLPASS1: return new PAllpass1;
+    case MLB_OP_GLIDE: return new PGlide;
+    case MLB_OP_INTERPOLATOR1: return new PInterp1;
+    case MLB_OP_SAMPLE_GLIDE: return new PSampleGlide;
+    case MLB_OP_INTEGER_DELAY: return new PIntDelay;
+    case MLB_OP_INTEGER_DELAY_VAR: return new PIntDelayVar;
+    case MLB_OP_FRACTIONAL_DELAY: return new PFracDelay;
+    case MLB_OP_FRACTIONAL_DELAY_VAR: return new PFracDelayVar;
+    case MLB_OP_PITCHBEND_DELAY: return new PPitchbend;
+    case MLB_OP_ALLPASS_INT: return new PAllpassInt;
+    case MLB_OP_ALLPASS_FRAC: return new PAllpassFrac;
+    case MLB_OP_ALLPASS_PB: return new PAllpassPB;
+    case MLB_OP_FEEDBACK_READ: return new PFeedback;
     case MLB_OP_INPUT:
+    case MLB_OP_FEEDBACK_WRITE:
     case MLB_OP_FDN8_R: return nullptr;
     default: return new PStateless(op);
   }
@@ -491,6 +723,12 @@ void mlref_graph_process(mlref_graph* h, const float* in, float* out, float* mix
             rows[i] = rows2[nd.in[0]];
             continue;
           }
+          if (nd.op == MLB_OP_FEEDBACK_WRITE)
+          {
+            static_cast<PFeedback*>(g.procs[v][nd.iarg].get())->held = rows[nd.in[0]];
+            rows[i] = rows[nd.in[0]];
+            continue;
+          }
           const DSPVector* ins[3] = {nullptr, nullptr, nullptr};
           for (int k = 0; k < 3; ++k)
             if (nd.in[k] >= 0) ins[k] = &rows[nd.in[k]];
@@ -567,6 +805,34 @@ void mlref_coeffs_onepole(float omega, float* o)
 }
 float mlref_coeffs_dcblocker(float omega) { return DCBlocker::makeCoeffs(omega); }
 float mlref_db_to_gain(float dB) { return dBToGain(dB); }
+void mlref_coeffs_peak(float omega, float* o)
+{
+  auto c = Peak::makeCoeffs(omega);
+  o[0] = c.a0, o[1] = c.b1;
+}
+void mlref_coeffs_rms(float omega, float* o)
+{
+  auto c = RMS::makeCoeffs(omega);
+  o[0] = c.a0, o[1] = c.b1;
+}
+void mlref_coeffs_adsr(float a, float d, float s, float r, float sr, float* o)
+{
+  auto c = ADSR::calcCoeffs(a, d, s, r, sr);
+  o[0] = c.ka, o[1] = c.kd, o[2] = c.s, o[3] = c.kr;
+}
+float mlref_coeffs_allpass1(float d) { return Allpass1::makeCoeffs(d); }
+void mlref_coeffs_glide(float timeInSamples, float* o)
+{
+  LinearGlide g;
+  g.setGlideTimeInSamples(timeInSamples);
+  o[0] = static_cast<float>(g.mVectorsPerGlide), o[1] = g.mDyPerVector;
+}
+void mlref_coeffs_sample_glide(float timeInSamples, float* o)
+{
+  SampleAccurateLinearGlide g;
+  g.setGlideTimeInSamples(timeInSamples);
+  o[0] = static_cast<float>(g.mSamplesPerGlide), o[1] = g.mDyPerSample;
+}
 
 // sizes the survey pins (Appendix A) -- lets a test check this really is the reference
 int mlref_sizeof(int which)
@@ -640,5 +906,66 @@ double mlref_chain_sine_lopass_gain(int V, int T, const float* in, float* out,
     ic[V + v] = voices[v].lp.ic2eq;
   }
   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// ---- the Aaltoverb example's processVector, called as its author wrote it ----
+// (examples/audio-and-midi/reverb.cpp:21-123; the example itself needs RtAudio, so the
+// per-vector body is driven from here with the same functor members, the same
+// expressions and the same evaluation order.)  One reverb; in/out [T][2][64].
+// Used to check that graph_aaltoverb() really is that example, and as its CPU baseline.
+double mlref_aaltoverb(int T, const float* in, float* out, float sizeU2, float feedback,
+                       float glideSamples, int repeats)
+{
+  struct Verb
+  {
+    LinearGlide smoothFeedback, smoothDelay;
+    Allpass<PitchbendableDelay> ap[10];
+    PitchbendableDelay delayL, delayR;
+    DSPVector fbL, fbR;
+  } r;
+  static const float gains[10] = {0.75f, 0.70f, 0.625f, 0.625f, 0.7f, 0.7f, 0.6f, 0.6f, 0.5f, 0.5f};
+  static const float maxd[10] = {500.f, 500.f, 1000.f, 1000.f, 2600.f, 2600.f, 8000.f, 8000.f, 10000.f, 10000.f};
+  r.smoothFeedback.setGlideTimeInSamples(glideSamples);
+  r.smoothDelay.setGlideTimeInSamples(glideSamples);
+  for (int i = 0; i < 10; ++i)
+  {
+    r.ap[i].mGain = gains[i];
+    r.ap[i].setMaxDelayInSamples(maxd[i]);
+  }
+  r.delayL.setMaxDelayInSamples(3500.f);
+  r.delayR.setMaxDelayInSamples(3500.f);
+  const float sr = 48000;
+  if (repeats < 1) repeats = 1;
+  auto t0 = std::chrono::steady_clock::now();
+  for (int rep = 0; rep < repeats; ++rep)
+    for (int t = 0; t < T; ++t)
+    {
+      DSPVector in0(in + (size_t)t * 128), in1(in + (size_t)t * 128 + 64);
+      DSPVector vSmoothDelay = r.smoothDelay(sizeU2);
+      DSPVector vSmoothFeedback = r.smoothFeedback(feedback);
+      DSPVector vMin(kFloatsPerDSPVector);
+      DSPVector delayParamInSamples = sr * vSmoothDelay;
+      DSPVector vt1 = max(0.00476 * delayParamInSamples, vMin);
+      DSPVector vt2 = max(0.00358 * delayParamInSamples, vMin);
+      DSPVector vt3 = max(0.00973 * delayParamInSamples, vMin);
+      DSPVector vt4 = max(0.00830 * delayParamInSamples, vMin);
+      DSPVector vt5 = max(0.029 * delayParamInSamples, vMin);
+      DSPVector vt6 = max(0.021 * delayParamInSamples, vMin);
+      DSPVector vt7 = max(0.078 * delayParamInSamples, vMin);
+      DSPVector vt8 = max(0.090 * delayParamInSamples, vMin);
+      DSPVector vt9 = max(0.111 * delayParamInSamples, vMin);
+      DSPVector vt10 = max(0.096 * delayParamInSamples, vMin);
+      DSPVector monoInput = (in0 + in1);
+      DSPVector diffusedInput = r.ap[3](r.ap[2](r.ap[1](r.ap[0](monoInput, vt1), vt2), vt3), vt4);
+      DSPVector vDelayTimeL = max(0.0313 * delayParamInSamples - vMin, DSPVector(0.f));
+      DSPVector vDelayTimeR = max(0.0371 * delayParamInSamples - vMin, DSPVector(0.f));
+      DSPVector vTapL = r.ap[6](r.ap[4](diffusedInput + r.delayL(r.fbL, vDelayTimeL), vt5), vt7);
+      DSPVector vTapR = r.ap[7](r.ap[5](diffusedInput + r.delayR(r.fbR, vDelayTimeR), vt6), vt8);
+      r.fbR = r.ap[8](vTapL, vt9) * vSmoothFeedback;
+      r.fbL = r.ap[9](vTapR, vt10) * vSmoothFeedback;
+      store(vTapL, out + (size_t)t * 128);
+      store(vTapR, out + (size_t)t * 128 + 64);
+    }
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 }  // extern "C"
