@@ -194,17 +194,19 @@ enum {
   X(FEEDBACK_READ, 108, 0, 0, 0)                                                         \
   X(FEEDBACK_WRITE, 109, 1, 0, 0)
 
-/* Delay memory per voice: X(NAME, n_rows, n_rings) -- 64-float rows and rings. */
+/* Delay memory per voice: X(NAME, n_rows, n_rings) -- 64-float rows and rings.
+ * PitchbendableDelay's two FractionalDelays are fed the same input on every sample
+ * (F:1101-1103), so their two rings always hold identical data: one ring serves both. */
 #define MLB_OP_MEM_TABLE(X) \
   X(GLIDE, 1, 0)            \
   X(INTEGER_DELAY, 0, 1)    \
   X(INTEGER_DELAY_VAR, 0, 1)\
   X(FRACTIONAL_DELAY, 0, 1) \
   X(FRACTIONAL_DELAY_VAR, 0, 1) \
-  X(PITCHBEND_DELAY, 0, 2)  \
+  X(PITCHBEND_DELAY, 0, 1)  \
   X(ALLPASS_INT, 1, 1)      \
   X(ALLPASS_FRAC, 1, 1)     \
-  X(ALLPASS_PB, 1, 2)       \
+  X(ALLPASS_PB, 1, 1)       \
   X(FEEDBACK_READ, 1, 0)
 
 /* ids in [MLB_OP_MAP_FIRST, MLB_OP_MAP_END) are the stateless elementwise ops (mlb_map_*) */

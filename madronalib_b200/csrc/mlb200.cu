@@ -116,6 +116,12 @@ extern "C" int mlb_graph_layout(const mlb_node* nodes, int n_nodes, mlb_layout* 
     if (nodes[i].op == MLB_OP_FDN8_R && nodes[nodes[i].in[0]].op != MLB_OP_FDN8)
       return fail(MLB_ERR_INVALID, "node %d: FDN8_R must read an FDN8 node", i);
     if (nodes[i].op == MLB_OP_FDN8) ++n_fdn;
+    if (nodes[i].op == MLB_OP_FEEDBACK_WRITE)
+    {
+      const int rd = nodes[i].iarg;
+      if (rd < 0 || rd >= i || nodes[rd].op != MLB_OP_FEEDBACK_READ)
+        return fail(MLB_ERR_INVALID, "node %d: FEEDBACK_WRITE.iarg must name an earlier FEEDBACK_READ node", i);
+    }
     if (state_off) state_off[i] = ns;
     if (coef_off) coef_off[i] = nc;
     ns += nst;
@@ -433,6 +439,7 @@ struct mlb_graph
   // generic interpreter
   std::vector<GNode> gnodes;
   GNode* d_gnodes = nullptr;
+  int scratch_slot = 0;
   int n_slots = 0;
 
   // FDN delay memory
@@ -441,6 +448,11 @@ struct mlb_graph
   float* d_carry = nullptr;
   int ring_len = 0;
   long long blocks_done = 0;
+  // delay memory of the section-8(f) functors: member rows [V][64] and rings [V][stride] per node
+  bool has_dmem = false;
+  float* d_dmem = nullptr;
+  size_t dmem_floats = 0;
+  std::vector<unsigned> ring_stride;  // per node, 0 = no ring
 
   // chain scheduler: [0] unit counter, [1 + g] finished chunks of group g (monotonic)
   unsigned* d_sched = nullptr;
@@ -460,6 +472,20 @@ struct mlb_graph
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
 };
+
+// delay memory of an op: 64-float member rows and IntegerDelay rings per voice (MLB_OP_MEM_TABLE)
+static void op_mem(int op, int* n_rows, int* n_rings)
+{
+  *n_rows = *n_rings = 0;
+  switch (op)
+  {
+#define MLB_X_MEM(NAME, rows, rings) \
+  case MLB_OP_##NAME: *n_rows = rows, *n_rings = rings; break;
+    MLB_OP_MEM_TABLE(MLB_X_MEM)
+#undef MLB_X_MEM
+    default: break;
+  }
+}
 
 static bool is_filter(int op)
 {
@@ -667,6 +693,8 @@ static int build_generic(mlb_graph* g)
     if (slot[i] >= 0 && last_use[i] < 0 && N[i].op != MLB_OP_FDN8_R) free_slots.push_back(slot[i]);
   }
   g->n_slots = std::max(1, n_slots);
+  g->scratch_slot = g->n_slots;
+  if (g->has_dmem) g->n_slots += 4;  // delay input, two tap streams, the ring's oldest block
   const size_t smem = (size_t)g->n_slots * kSlotBytes;
   if (smem > g_smem_optin)
     return fail(MLB_ERR_UNSUPPORTED, "graph needs %d live rows (%zu B shared memory > %zu)",
@@ -674,6 +702,8 @@ static int build_generic(mlb_graph* g)
   g->kernel_name = g->exact ? "generic" : "generic(fast)";
   return MLB_OK;
 }
+
+static int size_functor_memory(mlb_graph* g);
 
 extern "C" int mlb_graph_create(const mlb_node* nodes, int n_nodes, const int32_t* outs, int n_out,
                                 int n_voices, unsigned flags, mlb_graph** out_graph)
@@ -701,7 +731,13 @@ extern "C" int mlb_graph_create(const mlb_node* nodes, int n_nodes, const int32_
   g->flags = flags;
   g->exact = !(flags & MLB_GRAPH_FAST);
   for (int i = 0; i < n_nodes; ++i)
+  {
     if (nodes[i].op == MLB_OP_FDN8) g->fdn_node = i;
+    int rows, rings;
+    op_mem(nodes[i].op, &rows, &rings);
+    if (rows || rings) g->has_dmem = true;
+  }
+  g->ring_stride.assign(n_nodes, 0u);
 
   auto cleanup = [&](int code)
   {
@@ -720,6 +756,18 @@ extern "C" int mlb_graph_create(const mlb_node* nodes, int n_nodes, const int32_
     cudaMemset(g->d_sched, 0, (n_groups + 1) * 4);
   }
   cudaMemset(g->d_state, 0, std::max<size_t>(1, lay.n_state_words) * V * 4);
+  // state of freshly constructed functors: zeros, except the "idle" markers
+  for (int i = 0; i < n_nodes; ++i)
+  {
+    int word = -1;
+    uint32_t val = 0;
+    if (nodes[i].op == MLB_OP_ADSR) word = 7, val = 4u;                   // segment{off}, F:694
+    if (nodes[i].op == MLB_OP_GLIDE) word = 2, val = 0xFFFFFFFFu;         // mVectorsRemaining{-1}, G:440
+    if (nodes[i].op == MLB_OP_SAMPLE_GLIDE) word = 3, val = 0xFFFFFFFFu;  // mSamplesRemaining{-1}, G:524
+    if (word < 0) continue;
+    std::vector<uint32_t> fill(V, val);
+    cudaMemcpy(g->d_state + (size_t)(so[i] + word) * V, fill.data(), V * 4, cudaMemcpyHostToDevice);
+  }
   cudaMemset(g->d_coef, 0, std::max<size_t>(1, lay.n_coef_words) * V * 4);
   g->h_coef.assign((size_t)lay.n_coef_words * V, 0.f);
   cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
@@ -754,6 +802,8 @@ extern "C" int mlb_graph_create(const mlb_node* nodes, int n_nodes, const int32_
       return cleanup(fail(MLB_ERR_ALLOC, "cudaMalloc of graph program failed"));
     cudaMemcpy(g->d_gnodes, g->gnodes.data(), sizeof(GNode) * g->gnodes.size(),
                cudaMemcpyHostToDevice);
+    rc = size_functor_memory(g);
+    if (rc != MLB_OK) return cleanup(rc);
   }
   *out_graph = g;
   return MLB_OK;
@@ -767,6 +817,7 @@ extern "C" int mlb_graph_destroy(mlb_graph* g)
   cudaFree(g->d_gnodes);
   cudaFree(g->d_ring);
   cudaFree(g->d_carry);
+  cudaFree(g->d_dmem);
   cudaFree(g->d_partial);
   cudaFree(g->d_sched);
   cudaFree(g->d_in);
@@ -827,6 +878,74 @@ static int size_delay_memory(mlb_graph* g)
   return MLB_OK;
 }
 
+// Lay out (and, when a ring grows or shrinks, reallocate and clear) the delay memory of the
+// section-8(f) functors.  Ring of voice v of a node: 1 << bitsToContain(floor(maxDelay_v') + 64)
+// samples (IntegerDelay::setMaxDelayInSamples, F:822-830; maxDelay' = maxDelay - 64 inside an
+// Allpass<>, F:1125-1128); every voice of a node gets the stride of the node's longest ring and
+// uses its own mask inside it.
+static int size_functor_memory(mlb_graph* g)
+{
+  if (!g->has_dmem) return MLB_OK;
+  const size_t V = (size_t)g->V;
+  const int n = (int)g->nodes.size();
+  std::vector<unsigned> stride(n, 0u);
+  std::vector<unsigned long long> row_off(n, 0ull), ring_off(n, 0ull);
+  unsigned long long total = 0;
+  for (int i = 0; i < n; ++i)
+  {
+    int rows, rings, nco = 0;
+    const int op = g->nodes[i].op;
+    op_mem(op, &rows, &rings);
+    mlb_op_info(op, nullptr, nullptr, &nco);
+    if (rows)
+    {
+      row_off[i] = total;
+      total += (unsigned long long)V * MLB_BLOCK;
+    }
+    if (rings)
+    {
+      const bool in_allpass = (op == MLB_OP_ALLPASS_INT || op == MLB_OP_ALLPASS_FRAC || op == MLB_OP_ALLPASS_PB);
+      const float* md = g->h_coef.data() + (size_t)(g->co_off[i] + nco - 1) * V;  // last coef word = maxDelay
+      int dmax = 0;
+      for (size_t v = 0; v < V; ++v)
+      {
+        const float m = md[v] - (in_allpass ? (float)MLB_BLOCK : 0.f);
+        if (!(m >= 0.f) || m > 16777216.0f)
+        {
+          if (md[v] == 0.f) continue;  // coefficients not set yet: smallest ring
+          return fail(MLB_ERR_INVALID, "node %d (%s): maxDelay coef of voice %zu is %g (need %s <= maxDelay <= 2^24)", i,
+                      mlb_op_name(op), v, (double)md[v], in_allpass ? "64" : "0");
+        }
+        dmax = std::max(dmax, (int)std::floor(m));
+      }
+      unsigned ring = 1;
+      while (ring < (unsigned)(dmax + MLB_BLOCK)) ring <<= 1;
+      stride[i] = ring;
+      ring_off[i] = total;
+      total += (unsigned long long)V * ring;
+    }
+  }
+  for (int i = 0; i < n; ++i)  // FEEDBACK_WRITE stores into its FEEDBACK_READ's row
+    if (g->nodes[i].op == MLB_OP_FEEDBACK_WRITE) row_off[i] = row_off[g->nodes[i].iarg];
+  const bool relayout = (total != g->dmem_floats) || (stride != g->ring_stride);
+  if (!relayout) return MLB_OK;
+  cudaFree(g->d_dmem);
+  g->d_dmem = nullptr;
+  g->dmem_floats = 0;
+  if (cudaMalloc(&g->d_dmem, std::max<unsigned long long>(total, 1) * 4) != cudaSuccess)
+    return fail(MLB_ERR_ALLOC, "cudaMalloc of %llu B delay memory failed", total * 4ull);
+  g->dmem_floats = (size_t)total;
+  g->ring_stride = stride;
+  for (int i = 0; i < n; ++i)
+  {
+    g->gnodes[i].ring_stride = stride[i];
+    g->gnodes[i].row_off = row_off[i];
+    g->gnodes[i].ring_off = ring_off[i];
+  }
+  CU_CHECK(cudaMemcpy(g->d_gnodes, g->gnodes.data(), sizeof(GNode) * g->gnodes.size(), cudaMemcpyHostToDevice));
+  return mlb_graph_clear_delays(g);
+}
+
 extern "C" int mlb_graph_set_coefs(mlb_graph* g, const float* coef_host)
 {
   if (!g) return fail(MLB_ERR_INVALID, "null graph");
@@ -835,6 +954,8 @@ extern "C" int mlb_graph_set_coefs(mlb_graph* g, const float* coef_host)
   const size_t bytes = (size_t)g->layout.n_coef_words * g->V * 4;
   memcpy(g->h_coef.data(), coef_host, bytes);
   int rc = size_delay_memory(g);
+  if (rc != MLB_OK) return rc;
+  rc = size_functor_memory(g);
   if (rc != MLB_OK) return rc;
   CU_CHECK(cudaMemcpy(g->d_coef, coef_host, bytes, cudaMemcpyHostToDevice));
   return MLB_OK;
@@ -867,12 +988,15 @@ extern "C" int mlb_graph_clear_delays(mlb_graph* g)
     CU_CHECK(cudaMemset(g->d_ring, 0, (size_t)g->V * 8 * g->ring_len * 4));
     CU_CHECK(cudaMemset(g->d_carry, 0, (size_t)g->V * 8 * MLB_BLOCK * 4));
   }
+  if (g->d_dmem) CU_CHECK(cudaMemset(g->d_dmem, 0, g->dmem_floats * 4));
   return MLB_OK;
 }
 extern "C" size_t mlb_graph_delay_bytes(const mlb_graph* g)
 {
-  if (!g || !g->d_ring) return 0;
-  return (size_t)g->V * 8 * ((size_t)g->ring_len + MLB_BLOCK) * 4;
+  if (!g) return 0;
+  size_t bytes = g->dmem_floats * 4;
+  if (g->d_ring) bytes += (size_t)g->V * 8 * ((size_t)g->ring_len + MLB_BLOCK) * 4;
+  return bytes;
 }
 
 static int env_int(const char* name, int dflt)
@@ -1061,6 +1185,8 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
     a.n_groups = n_groups, a.n_slots = g->n_slots;
     a.fdn_ring = g->d_ring, a.fdn_carry = g->d_carry, a.fdn_ring_len = g->ring_len;
     a.blocks_done = g->blocks_done;
+    a.dmem = g->d_dmem;
+    a.scratch_slot = g->scratch_slot;
     const size_t smem = (size_t)g->n_slots * kSlotBytes;
     if (g->exact)
     {
@@ -1079,7 +1205,7 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
   cudaEventRecord(g->ev1, stream);
   g->timed = true;
   CU_CHECK(cudaGetLastError());
-  if (g->fdn_node >= 0) g->blocks_done += T;
+  if (g->fdn_node >= 0 || g->has_dmem) g->blocks_done += T;
   if (mix_dev)
   {
     float* scratch = g->d_partial + (size_t)T * std::max(1, n_out) * n_groups * MLB_BLOCK;

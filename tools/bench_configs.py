@@ -24,7 +24,7 @@ def main():
     from madronalib_b200 import api, workloads as wl
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--only", default="2,3,4,5,map")
+    ap.add_argument("--only", default="2,3,4,5,6,map")
     ap.add_argument("--generic", action="store_true", help="force the graph interpreter kernel")
     args = ap.parse_args()
     only = set(args.only.split(","))
@@ -45,6 +45,12 @@ def main():
         cfgs.append(("config4", wl.config_4(16384), 16, lambda V, T: 4864.0 * V * T))
     if "5" in only:
         cfgs.append(("config5", wl.config_5(1024, 256), 16, lambda V, T: 256.0 * V * T))
+    if "6" in only:
+        # Aaltoverb x V.  Per reverb-block: 12 rings x (256 B write + 256 B read: the two
+        # taps of a PitchbendableDelay sit within a sample of each other) + 10 vy1 rows r/w + 2 feedback
+        # rows r/w + 2 glide rows read + 2 rows in + 2 rows out = 13824 B
+        for V6 in (4096, 16384):
+            cfgs.append(("config6_aaltoverb", wl.config_6(V6), 16, lambda V, T: 13824.0 * V * T))
     if "map" in only:
         # K3: stateless elementwise ops, n_rows x 64 elements resident in HBM
         n_rows = 1 << 20  # 64 Mi elements = 256 MB per operand (> L2)
