@@ -1099,6 +1099,12 @@ mlport_graph* mlport_graph_create(const mlb_node* nodes, int n_nodes, const int3
     g->n_state += b;
     g->n_coef += c;
     if (nodes[i].op == MLB_OP_INPUT && nodes[i].iarg + 1 > g->n_in) g->n_in = nodes[i].iarg + 1;
+    if (nodes[i].op == MLB_OP_FEEDBACK_WRITE &&
+        (nodes[i].iarg < 0 || nodes[i].iarg >= i || nodes[nodes[i].iarg].op != MLB_OP_FEEDBACK_READ))
+    {
+      mlport_graph_destroy(g);
+      return NULL;
+    }
   }
   g->state = (uint32_t*)calloc((size_t)(g->n_state > 0 ? g->n_state : 1) * (size_t)V, 4);
   g->coef = (float*)calloc((size_t)(g->n_coef > 0 ? g->n_coef : 1) * (size_t)V, 4);

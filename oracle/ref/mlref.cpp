@@ -626,6 +626,12 @@ mlref_graph* mlref_graph_create(const mlb_node* nodes, int n_nodes, const int32_
     g.nState += oi.nst;
     g.nCoef += oi.nco;
     if (nodes[i].op == MLB_OP_INPUT) g.nIn = std::max(g.nIn, nodes[i].iarg + 1);
+    if (nodes[i].op == MLB_OP_FEEDBACK_WRITE &&
+        (nodes[i].iarg < 0 || nodes[i].iarg >= i || nodes[nodes[i].iarg].op != MLB_OP_FEEDBACK_READ))
+    {
+      delete h;
+      return nullptr;
+    }
   }
   g.procs.resize(V);
   std::vector<float> c(64);

@@ -41,7 +41,7 @@ def main():
 
     # every stateless op
     for name, (_, nin, nst, nco) in OP_TABLE.items():
-        if nst or nco or nin == 0 or name == "FDN8_R":
+        if not (30 <= OP_TABLE[name][0] < 100):  # MLB_OP_MAP_FIRST..END
             continue
         g = GraphSpec()
         g.output(g.node(name, *[g.input(k) for k in range(nin)]))
@@ -91,9 +91,47 @@ def main():
     out["db_to_gain_6"] = np.float32(R.db_to_gain(6.0))
     out["dcblocker_0045"] = np.float32(R.coeffs_dcblocker(0.045))
     np.savez_compressed(os.path.join(HERE, "coeffs.npz"), **out)
-    for f in ("ops.npz", "configs.npz", "coeffs.npz"):
+    make_functors(R)
+    for f in ("ops.npz", "configs.npz", "coeffs.npz", "functors.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 
+FUNCTOR_V, FUNCTOR_T = 6, 10
+AALTOVERB_V, AALTOVERB_T = 2, 48
+
+
+def make_functors(R):
+    """every added functor and the Aaltoverb example chain, from the reference."""
+    out = {}
+    for name in wl.FUNCTOR_CASES:
+        w = wl.functor_case(name, FUNCTOR_V)
+        inp = w.inputs(FUNCTOR_T)
+        y, _, st = R.run(w.spec, w.n_voices, FUNCTOR_T, inp, w.state, w.coef)
+        out[name + "_in"], out[name + "_coef"], out[name + "_state0"] = inp, w.coef, w.state
+        out[name + "_out"], out[name + "_state1"] = y, st
+    w = wl.config_6(AALTOVERB_V)
+    inp = w.inputs(AALTOVERB_T)
+    y, _, st = R.run(w.spec, w.n_voices, AALTOVERB_T, inp, w.state, w.coef)
+    # the example's own per-vector body (mlref_aaltoverb) gives the same bits as the graph
+    for v in range(AALTOVERB_V):
+        o, _ = R.aaltoverb(inp[:, :, v, :], float(w.coef[w.spec.coef_slot(2), v]),
+                           float(w.coef[w.spec.coef_slot(3), v]), 4800.0)
+        assert np.array_equal(o.view(np.uint32), y[:, :, v, :].view(np.uint32))
+    out["aaltoverb_in"], out["aaltoverb_coef"], out["aaltoverb_state0"] = inp, w.coef, w.state
+    out["aaltoverb_out"], out["aaltoverb_state1"] = y, st
+    out["coef_adsr"] = R.coeffs("adsr", 0.01, 0.1, 0.5, 0.2, 48000.0)
+    out["coef_peak"] = R.coeffs("peak", 0.001)
+    out["coef_rms"] = R.coeffs("rms", 0.002)
+    out["coef_glide"] = R.coeffs("glide", 4800.0)
+    out["coef_sample_glide"] = R.coeffs("sample_glide", 77.7)
+    out["coef_allpass1"] = np.array([R.coeffs_allpass1(float(d)) for d in np.linspace(0.618, 1.618, 16, dtype=np.float32)],
+                                    np.float32)
+    np.savez_compressed(os.path.join(HERE, "functors.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "functors":
+        make_functors(RefOracle())
+        print("functors.npz", os.path.getsize(os.path.join(HERE, "functors.npz")), "bytes")
+    else:
+        main()

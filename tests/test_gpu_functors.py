@@ -89,3 +89,20 @@ def test_clear_delays_restarts_the_tail(gpu, port):
     finally:
         g.close()
     assert_same_bits(a, b, "after clear_delays")
+
+
+@pytest.mark.parametrize("name", wl.FUNCTOR_CASES + ("aaltoverb",))
+def test_functor_matches_committed_reference_golden(gpu, name):
+    """tests/golden/functors.npz was written by the compiled reference (make_golden.py)."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "functors.npz"))
+    inp = gold[name + "_in"]
+    T, V = inp.shape[0], inp.shape[2]
+    w = wl.config_6(V) if name == "aaltoverb" else wl.functor_case(name, V)
+    w.coef, w.state = gold[name + "_coef"], gold[name + "_state0"]
+    go, _, gs, _ = run_gpu(gpu, w, T, inp)
+    if name in ("peak", "rms"):
+        np.testing.assert_allclose(go, gold[name + "_out"], rtol=APPROX_RTOL, atol=1e-12)
+    else:
+        assert_same_bits(go, gold[name + "_out"], name)
+    assert_state_equal(gs, gold[name + "_state1"], name)

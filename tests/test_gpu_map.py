@@ -7,8 +7,7 @@ from tests.common import assert_same_bits
 
 pytestmark = pytest.mark.gpu
 
-STATELESS = [n for n, (_, nin, nst, nco) in OP_TABLE.items()
-             if nst == 0 and nco == 0 and nin >= 1 and n != "FDN8_R"]
+STATELESS = [n for n, (op, nin, nst, nco) in OP_TABLE.items() if 30 <= op < 100]  # MLB_OP_MAP_FIRST..END
 # _mm_rcp_ps / _mm_rsqrt_ps are CPU-microarchitecture-defined 12-bit approximations
 HW_APPROX = {"SQRT_APPROX": 1.5 * 2.0 ** -12, "DIVIDE_APPROX": 1.5 * 2.0 ** -12}
 
