@@ -201,14 +201,4 @@ struct RingRef
 // writes it (d mod R > R - 64): such lanes keep the ring's oldest block in a shared row
 MLB_DEV bool delay_reads_ahead(int32_t d, uint32_t mask) { return ((uint32_t)d & mask) > mask - 63u; }
 
-// What IntegerDelay::processSample (F:898-912) would read at sample n of the block with delay d,
-// given that the whole input block has already been stored at w .. w+63.
-MLB_DEV float ring_read(const RingRef& r, int n, int32_t d, bool ahead, uint32_t old_addr)
-{
-  const uint32_t m = ((uint32_t)n - (uint32_t)d) & r.mask;  // slot offset from w
-  float val = r.p[(r.w + m) & r.mask];
-  if (ahead && m < (uint32_t)MLB_BLOCK && m > (uint32_t)n) val = lds32(old_addr + m * 4u);
-  return val;
-}
-
 }  // namespace mlb

@@ -59,7 +59,6 @@ struct GenericArgs
   int fdn_ring_len;        // power of two
   long long blocks_done;   // IntegerDelay write index = (64 * blocks_done) & (ring_len - 1)
   float* dmem;             // delay memory of the section-8(f) functors (rows + rings)
-  int scratch_slot;        // first of 4 scratch row slots (delay input, two tap streams, old block)
 };
 
 struct RowRef
@@ -214,11 +213,20 @@ MLB_DEV float* node_row(const GNode& nd, const GenericArgs& a, int v)
 {
   return a.dmem + nd.row_off + (size_t)v * MLB_BLOCK;
 }
+// (the shared-memory stores are asm volatile with a memory clobber: global loads are issued in
+// batches into registers first so that they overlap instead of serialising behind each store)
 MLB_DEV void row_global_to_smem(const float* src, uint32_t dst)
 {
   const float4* s4 = reinterpret_cast<const float4*>(src);
-#pragma unroll 4
-  for (int q = 0; q < 16; ++q) sts128(dst + (uint32_t)q * 16u, s4[q]);
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+  {
+    float4 buf[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) buf[q] = s4[h * 8 + q];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sts128(dst + (uint32_t)(h * 8 + q) * 16u, buf[q]);
+  }
 }
 MLB_DEV void row_smem_to_global(RowRef x, float* dst)
 {
@@ -311,6 +319,27 @@ MLB_DEV RingRef node_ring(const GNode& nd, const GenericArgs& a, int v, int t, f
   r.p = a.dmem + nd.ring_off + (size_t)v * nd.ring_stride;
   return r;
 }
+// The delay runners keep 16-sample batches in registers: 16 (or 32) independent ring loads are in
+// flight while the previous batch runs through the allpass recurrences; nothing is staged through
+// shared memory (its stores are asm volatile + memory clobber and would serialise the loads).
+//
+// A lane whose delay can reach into the block being written ("ahead", functors.cuh) keeps the
+// ring's oldest block in a per-thread local array -- rare, so it lives in local memory.
+struct OldBlock
+{
+  float v[MLB_BLOCK];
+  MLB_DEV void save(const RingRef& r)
+  {
+    const float4* s4 = reinterpret_cast<const float4*>(r.p + r.w);
+#pragma unroll 4
+    for (int q = 0; q < 16; ++q)
+    {
+      const float4 t = s4[q];
+      v[4 * q] = t.x, v[4 * q + 1] = t.y, v[4 * q + 2] = t.z, v[4 * q + 3] = t.w;
+    }
+  }
+};
+
 // IntegerDelay block write, F:836-851 (w is a multiple of 64 and the ring holds >= 64 samples)
 MLB_DEV void ring_write_block(const RingRef& r, RowRef x)
 {
@@ -318,20 +347,69 @@ MLB_DEV void ring_write_block(const RingRef& r, RowRef x)
 #pragma unroll 4
   for (int q = 0; q < 16; ++q) d4[q] = x.get4(q);
 }
-// IntegerDelay::operator()(vx) read half, F:853-869: 64 samples from (w - d) & mask
-MLB_DEV void ring_read_block(const RingRef& r, int32_t d, uint32_t dst)
+// samples [n0, n0 + 16) of a tap with constant delay d, as IntegerDelay::processSample (F:898-912)
+// would read them given that the whole input block is already stored at w .. w+63
+MLB_DEV void ring_gather16(const RingRef& r, int n0, int32_t d, bool ahead, const OldBlock& old, float (&buf)[16])
+{
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+  {
+    const uint32_t m = ((uint32_t)(n0 + j) - (uint32_t)d) & r.mask;  // slot offset from w
+    buf[j] = r.p[(r.w + m) & r.mask];
+  }
+  if (ahead)
+  {
+#pragma unroll 1
+    for (int j = 0; j < 16; ++j)
+    {
+      const uint32_t m = ((uint32_t)(n0 + j) - (uint32_t)d) & r.mask;
+      if (m < (uint32_t)MLB_BLOCK && m > (uint32_t)(n0 + j)) buf[j] = old.v[m];
+    }
+  }
+}
+MLB_DEV void store16(uint32_t row, int n0, const float (&y)[16])
+{
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    sts128(row + (uint32_t)(n0 + 4 * q) * 4u, make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]));
+}
+MLB_DEV void store16(float* row, int n0, const float (&y)[16])
+{
+  float4* d4 = reinterpret_cast<float4*>(row + n0);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) d4[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+}
+
+// IntegerDelay::operator()(vx) read half (F:853-869), optionally followed by the Allpass1 of a
+// FractionalDelay (F:1014); DST = shared row address or global row pointer
+template <bool EX, bool AP, class DST>
+MLB_DEV void ring_block_out(const RingRef& r, int32_t d, float& x1, float& y1, float coeff, DST dst)
 {
   const uint32_t rd = (r.w - (uint32_t)d) & r.mask;
-#pragma unroll 8
-  for (int n = 0; n < MLB_BLOCK; ++n) sts32(dst + (uint32_t)n * 4u, r.p[(rd + (uint32_t)n) & r.mask]);
-}
-// in-place Allpass1 over a shared row
-template <bool EX>
-MLB_DEV void allpass1_row(uint32_t row, int n0, int n1, float& x1, float& y1, float coeff)
-{
-#pragma unroll 4
-  for (int n = n0; n < n1; ++n)
-    sts32(row + (uint32_t)n * 4u, allpass1_tick<EX>(lds32(row + (uint32_t)n * 4u), x1, y1, coeff));
+  float cur[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) cur[j] = r.p[(rd + (uint32_t)j) & r.mask];
+#pragma unroll
+  for (int s = 0; s < 4; ++s)
+  {
+    float nxt[16];
+    if (s < 3)
+    {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) nxt[j] = r.p[(rd + (uint32_t)(16 * s + 16 + j)) & r.mask];
+    }
+    if (AP)
+    {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) cur[j] = allpass1_tick<EX>(cur[j], x1, y1, coeff);
+    }
+    store16(dst, 16 * s, cur);
+    if (s < 3)
+    {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+    }
+  }
 }
 
 // IntegerDelay::operator()(vx), F:834-875.  coef: delay, maxDelay
@@ -343,125 +421,81 @@ MLB_DEV void run_int_delay_node(const GNode& nd, const GenericArgs& a, int v, bo
   const int32_t d = cvt_trunc(a.coef[(size_t)nd.co_off * a.V + v]);
   const RingRef r = node_ring<EX>(nd, a, v, t, a.coef[(size_t)(nd.co_off + 1) * a.V + v]);
   ring_write_block(r, x);
-  ring_read_block(r, d, out_addr);
+  float x1 = 0.f, y1 = 0.f;
+  ring_block_out<EX, false>(r, d, x1, y1, 0.f, out_addr);
 }
-// IntegerDelay::operator()(x, delay), F:877-896.  coef: maxDelay
-template <bool EX>
-MLB_DEV void run_int_delay_var_node(const GNode& nd, const GenericArgs& a, int v, bool live, int t, RowRef x,
-                                    RowRef dl, uint32_t out_addr, uint32_t old_addr)
+// IntegerDelay::operator()(x, delay), F:877-896 (coef: maxDelay) and
+// FractionalDelay::operator()(vx, vDelay), F:1033-1042 (coef: maxDelay; state: allpass x1, y1)
+template <bool EX, bool FRAC>
+MLB_DEV void run_delay_var_node(const GNode& nd, const GenericArgs& a, int v, bool live, int t, RowRef x,
+                                RowRef dl, uint32_t out_addr)
 {
   if (!live) return;
   const RingRef r = node_ring<EX>(nd, a, v, t, a.coef[(size_t)nd.co_off * a.V + v]);
+  OldBlock old;
   bool ahead = false;
-  for (int n = 0; n < MLB_BLOCK; ++n) ahead |= delay_reads_ahead(cvt_trunc(dl.get(n)), r.mask);
-  if (ahead) row_global_to_smem(r.p + r.w, old_addr);
-  ring_write_block(r, x);
 #pragma unroll 4
   for (int n = 0; n < MLB_BLOCK; ++n)
-    sts32(out_addr + (uint32_t)n * 4u, ring_read(r, n, cvt_trunc(dl.get(n)), ahead, old_addr));
-}
-// FractionalDelay::operator()(vx), F:1014.  state: allpass x1,y1 at st_off; delay d
-template <bool EX>
-MLB_DEV void frac_delay_block(const RingRef& r, const GenericArgs& a, int st_off, int v, float d, RowRef x,
-                              uint32_t dst)
-{
-  int32_t di;
-  float coeff;
-  frac_split<EX>(d, di, coeff);
+  {
+    int32_t di;
+    float coeff;
+    if (FRAC)
+      frac_split<EX>(dl.get(n), di, coeff);
+    else
+      di = cvt_trunc(dl.get(n));
+    ahead |= delay_reads_ahead(di, r.mask);
+  }
+  if (ahead) old.save(r);
   ring_write_block(r, x);
-  ring_read_block(r, di, dst);
-  float x1 = u2f(a.state[(size_t)st_off * a.V + v]), y1 = u2f(a.state[(size_t)(st_off + 1) * a.V + v]);
-  allpass1_row<EX>(dst, 0, MLB_BLOCK, x1, y1, coeff);
-  a.state[(size_t)st_off * a.V + v] = f2u(x1);
-  a.state[(size_t)(st_off + 1) * a.V + v] = f2u(y1);
+  float x1 = 0.f, y1 = 0.f;
+  if (FRAC) x1 = u2f(a.state[(size_t)nd.st_off * a.V + v]), y1 = u2f(a.state[(size_t)(nd.st_off + 1) * a.V + v]);
+#pragma unroll 1
+  for (int n0 = 0; n0 < MLB_BLOCK; n0 += 16)
+  {
+    float buf[16], co[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+    {
+      int32_t di;
+      co[j] = 0.f;
+      if (FRAC)
+        frac_split<EX>(dl.get(n0 + j), di, co[j]);
+      else
+        di = cvt_trunc(dl.get(n0 + j));
+      const uint32_t m = ((uint32_t)(n0 + j) - (uint32_t)di) & r.mask;
+      buf[j] = r.p[(r.w + m) & r.mask];
+      if (ahead && m < (uint32_t)MLB_BLOCK && m > (uint32_t)(n0 + j)) buf[j] = old.v[m];
+    }
+    if (FRAC)
+    {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) buf[j] = allpass1_tick<EX>(buf[j], x1, y1, co[j]);
+    }
+    store16(out_addr, n0, buf);
+  }
+  if (FRAC)
+  {
+    a.state[(size_t)nd.st_off * a.V + v] = f2u(x1);
+    a.state[(size_t)(nd.st_off + 1) * a.V + v] = f2u(y1);
+  }
 }
+// FractionalDelay::operator()(vx), F:1014.  coef: delay, maxDelay; state: allpass x1, y1
 template <bool EX>
 MLB_DEV void run_frac_delay_node(const GNode& nd, const GenericArgs& a, int v, bool live, int t, RowRef x,
                                  uint32_t out_addr)
 {
   if (!live) return;
   const RingRef r = node_ring<EX>(nd, a, v, t, a.coef[(size_t)(nd.co_off + 1) * a.V + v]);
-  frac_delay_block<EX>(r, a, nd.st_off, v, a.coef[(size_t)nd.co_off * a.V + v], x, out_addr);
-}
-// FractionalDelay::operator()(vx, vDelay), F:1033-1042
-template <bool EX>
-MLB_DEV void run_frac_delay_var_node(const GNode& nd, const GenericArgs& a, int v, bool live, int t, RowRef x,
-                                     RowRef dl, uint32_t out_addr, uint32_t old_addr)
-{
-  if (!live) return;
-  const RingRef r = node_ring<EX>(nd, a, v, t, a.coef[(size_t)nd.co_off * a.V + v]);
-  bool ahead = false;
-  for (int n = 0; n < MLB_BLOCK; ++n)
-  {
-    int32_t di;
-    float coeff;
-    frac_split<EX>(dl.get(n), di, coeff);
-    ahead |= delay_reads_ahead(di, r.mask);
-  }
-  if (ahead) row_global_to_smem(r.p + r.w, old_addr);
+  int32_t di;
+  float coeff;
+  frac_split<EX>(a.coef[(size_t)nd.co_off * a.V + v], di, coeff);
   ring_write_block(r, x);
   float x1 = u2f(a.state[(size_t)nd.st_off * a.V + v]), y1 = u2f(a.state[(size_t)(nd.st_off + 1) * a.V + v]);
-#pragma unroll 2
-  for (int n = 0; n < MLB_BLOCK; ++n)
-  {
-    int32_t di;
-    float coeff;
-    frac_split<EX>(dl.get(n), di, coeff);
-    sts32(out_addr + (uint32_t)n * 4u, allpass1_tick<EX>(ring_read(r, n, di, ahead, old_addr), x1, y1, coeff));
-  }
+  ring_block_out<EX, true>(r, di, x1, y1, coeff, out_addr);
   a.state[(size_t)nd.st_off * a.V + v] = f2u(x1);
   a.state[(size_t)(nd.st_off + 1) * a.V + v] = f2u(y1);
 }
 
-// PitchbendableDelay::operator(), F:1097-1104: two allpass-interpolated taps of ONE ring (both
-// FractionalDelays receive the same input, so their rings are identical), delay 1 retuned at
-// n % 32 == 16, delay 2 at n % 32 == 0 (F:1053-1076), crossfaded by the triangle kvFade.
-// Leaves tap 1 in row B and tap 2 in row C; DL(n) is the delay-time operand.
-template <bool EX, class DelayAt>
-MLB_DEV void pitchbend_taps(const RingRef& r, const GenericArgs& a, int st_off, int v, RowRef x, DelayAt DL,
-                            uint32_t B, uint32_t C, uint32_t old_addr)
-{
-  uint32_t st[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) st[i] = a.state[(size_t)(st_off + i) * a.V + v];
-  int32_t di1[3], di2[2];
-  float ac1[3], ac2[2];
-  di1[0] = (int32_t)st[2], ac1[0] = u2f(st[3]);
-  frac_split<EX>(DL(16), di1[1], ac1[1]);
-  frac_split<EX>(DL(48), di1[2], ac1[2]);
-  frac_split<EX>(DL(0), di2[0], ac2[0]);
-  frac_split<EX>(DL(32), di2[1], ac2[1]);
-  const bool ahead = delay_reads_ahead(di1[0], r.mask) | delay_reads_ahead(di1[1], r.mask) |
-                     delay_reads_ahead(di1[2], r.mask) | delay_reads_ahead(di2[0], r.mask) |
-                     delay_reads_ahead(di2[1], r.mask);
-  if (ahead) row_global_to_smem(r.p + r.w, old_addr);
-  ring_write_block(r, x);
-  // gather both tap streams first (independent loads), then run the two recurrences
-#pragma unroll
-  for (int s = 0; s < 3; ++s)
-  {
-    const int n0 = s == 0 ? 0 : (s == 1 ? 16 : 48), n1 = s == 0 ? 16 : (s == 1 ? 48 : 64);
-#pragma unroll 8
-    for (int n = n0; n < n1; ++n) sts32(B + (uint32_t)n * 4u, ring_read(r, n, di1[s], ahead, old_addr));
-  }
-#pragma unroll
-  for (int s = 0; s < 2; ++s)
-  {
-#pragma unroll 8
-    for (int n = 32 * s; n < 32 * s + 32; ++n) sts32(C + (uint32_t)n * 4u, ring_read(r, n, di2[s], ahead, old_addr));
-  }
-  float x1 = u2f(st[0]), y1 = u2f(st[1]);
-  allpass1_row<EX>(B, 0, 16, x1, y1, ac1[0]);
-  allpass1_row<EX>(B, 16, 48, x1, y1, ac1[1]);
-  allpass1_row<EX>(B, 48, 64, x1, y1, ac1[2]);
-  st[0] = f2u(x1), st[1] = f2u(y1), st[2] = (uint32_t)di1[2], st[3] = f2u(ac1[2]);
-  x1 = u2f(st[4]), y1 = u2f(st[5]);
-  allpass1_row<EX>(C, 0, 32, x1, y1, ac2[0]);
-  allpass1_row<EX>(C, 32, 64, x1, y1, ac2[1]);
-  st[4] = f2u(x1), st[5] = f2u(y1), st[6] = (uint32_t)di2[1], st[7] = f2u(ac2[1]);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) a.state[(size_t)(st_off + i) * a.V + v] = st[i];
-}
 // kvFade, F:1056-1062: 2 * (r > 16 ? 1 - r/32 : r/32), r = n % 32 (all values exact)
 MLB_DEV float pitchbend_fade(int n)
 {
@@ -469,80 +503,149 @@ MLB_DEV float pitchbend_fade(int n)
   const float u = __int2float_rn(rr) * 0.03125f;
   return 2.f * (rr > 16 ? 1.0f - u : u);
 }
-template <bool EX>
-MLB_DEV float pitchbend_mix(uint32_t B, uint32_t C, int n)
+
+// PitchbendableDelay::operator(), F:1097-1104: two allpass-interpolated taps of ONE ring (both
+// FractionalDelays receive the same input, so their rings are identical), delay 1 retuned at
+// n % 32 == 16, delay 2 at n % 32 == 0 (F:1053-1076), crossfaded by the triangle kvFade.
+// The caller has already stored the input block in the ring (after `prepare`).
+struct PitchbendPlan
 {
-  const float b = lds32(B + (uint32_t)n * 4u), c = lds32(C + (uint32_t)n * 4u);
-  return A<EX>::add(b, A<EX>::mul(pitchbend_fade(n), A<EX>::sub(c, b)));  // lerp, O:744
+  uint32_t st[8];
+  int32_t di1[3], di2[2];
+  float ac1[3], ac2[2];
+  bool ahead;
+};
+template <bool EX, class DelayAt>
+MLB_DEV void pitchbend_prepare(PitchbendPlan& p, const RingRef& r, const GenericArgs& a, int st_off, int v,
+                               DelayAt DL)
+{
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p.st[i] = a.state[(size_t)(st_off + i) * a.V + v];
+  p.di1[0] = (int32_t)p.st[2], p.ac1[0] = u2f(p.st[3]);
+  frac_split<EX>(DL(16), p.di1[1], p.ac1[1]);
+  frac_split<EX>(DL(48), p.di1[2], p.ac1[2]);
+  frac_split<EX>(DL(0), p.di2[0], p.ac2[0]);
+  frac_split<EX>(DL(32), p.di2[1], p.ac2[1]);
+  p.ahead = delay_reads_ahead(p.di1[0], r.mask) | delay_reads_ahead(p.di1[1], r.mask) |
+            delay_reads_ahead(p.di1[2], r.mask) | delay_reads_ahead(p.di2[0], r.mask) |
+            delay_reads_ahead(p.di2[1], r.mask);
+}
+template <bool EX, class DST>
+MLB_DEV void pitchbend_run(PitchbendPlan& p, const RingRef& r, const OldBlock& old, const GenericArgs& a,
+                           int st_off, int v, DST dst)
+{
+  float xb = u2f(p.st[0]), yb = u2f(p.st[1]), xc = u2f(p.st[4]), yc = u2f(p.st[5]);
+  float tb[16], tc[16];
+  ring_gather16(r, 0, p.di1[0], p.ahead, old, tb);
+  ring_gather16(r, 0, p.di2[0], p.ahead, old, tc);
+#pragma unroll
+  for (int s = 0; s < 4; ++s)
+  {
+    // quarter s: tap 1 uses segment {0,1,1,2}[s], tap 2 segment {0,0,1,1}[s]
+    float nb[16], nc[16];
+    if (s < 3)
+    {
+      ring_gather16(r, 16 * s + 16, p.di1[s == 2 ? 2 : 1], p.ahead, old, nb);
+      ring_gather16(r, 16 * s + 16, p.di2[s >= 1 ? 1 : 0], p.ahead, old, nc);
+    }
+    const float cb = p.ac1[s == 0 ? 0 : (s == 3 ? 2 : 1)], cc = p.ac2[s >= 2 ? 1 : 0];
+    float y[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+    {
+      const float b = allpass1_tick<EX>(tb[j], xb, yb, cb);
+      const float c = allpass1_tick<EX>(tc[j], xc, yc, cc);
+      y[j] = A<EX>::add(b, A<EX>::mul(pitchbend_fade(16 * s + j), A<EX>::sub(c, b)));  // lerp, O:744
+    }
+    store16(dst, 16 * s, y);
+    if (s < 3)
+    {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) tb[j] = nb[j], tc[j] = nc[j];
+    }
+  }
+  p.st[0] = f2u(xb), p.st[1] = f2u(yb), p.st[2] = (uint32_t)p.di1[2], p.st[3] = f2u(p.ac1[2]);
+  p.st[4] = f2u(xc), p.st[5] = f2u(yc), p.st[6] = (uint32_t)p.di2[1], p.st[7] = f2u(p.ac2[1]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a.state[(size_t)(st_off + i) * a.V + v] = p.st[i];
 }
 
 template <bool EX>
 MLB_DEV void run_pitchbend_node(const GNode& nd, const GenericArgs& a, int v, bool live, int t, RowRef x,
-                                RowRef dl, uint32_t out_addr, uint32_t B, uint32_t C, uint32_t old_addr)
+                                RowRef dl, uint32_t out_addr)
 {
   if (!live) return;
   const RingRef r = node_ring<EX>(nd, a, v, t, a.coef[(size_t)nd.co_off * a.V + v]);
-  pitchbend_taps<EX>(r, a, nd.st_off, v, x, [&](int n) { return dl.get(n); }, B, C, old_addr);
-#pragma unroll 4
-  for (int n = 0; n < MLB_BLOCK; ++n) sts32(out_addr + (uint32_t)n * 4u, pitchbend_mix<EX>(B, C, n));
+  PitchbendPlan p;
+  OldBlock old;
+  pitchbend_prepare<EX>(p, r, a, nd.st_off, v, [&](int n) { return dl.get(n); });
+  if (p.ahead) old.save(r);
+  ring_write_block(r, x);
+  pitchbend_run<EX>(p, r, old, a, nd.st_off, v, out_addr);
 }
 
-// Allpass<DELAY>::operator(), F:1135-1153: din = x - vy1 * (-g); y = din * (-g) + vy1; the row
-// `din` goes to scratch A, y to the node's output row.  vy1 is this node's member row.
-template <bool EX>
-MLB_DEV void allpass_pre(const float* vy1, float gain, RowRef x, uint32_t A_addr, uint32_t out_addr)
-{
-  using ar = A<EX>;
-  const float g = -gain;
-  const float4* v4 = reinterpret_cast<const float4*>(vy1);
-#pragma unroll 2
-  for (int q = 0; q < 16; ++q)
-  {
-    const float4 xi = x.get4(q), yi = v4[q];
-    float4 din, y;
-    din.x = ar::sub(xi.x, ar::mul(yi.x, g)), y.x = ar::add(ar::mul(din.x, g), yi.x);
-    din.y = ar::sub(xi.y, ar::mul(yi.y, g)), y.y = ar::add(ar::mul(din.y, g), yi.y);
-    din.z = ar::sub(xi.z, ar::mul(yi.z, g)), y.z = ar::add(ar::mul(din.z, g), yi.z);
-    din.w = ar::sub(xi.w, ar::mul(yi.w, g)), y.w = ar::add(ar::mul(din.w, g), yi.w);
-    sts128(A_addr + (uint32_t)q * 16u, din);
-    sts128(out_addr + (uint32_t)q * 16u, y);
-  }
-}
+// Allpass<DELAY>::operator(), F:1135-1153: din = x - vy1 * (-g); y = din * (-g) + vy1;
+// vy1 = DELAY(din).  din goes straight into the ring, y to the node's output row; vy1 is this
+// node's member row in delay memory.
 // OP = ALLPASS_INT / ALLPASS_FRAC (coef mGain, delay, maxDelay) or ALLPASS_PB (coef mGain, maxDelay;
 // second operand = delay times)
 template <int OP, bool EX>
 MLB_DEV void run_allpass_node(const GNode& nd, const GenericArgs& a, int v, bool live, int t, RowRef x,
-                              RowRef dl, uint32_t out_addr, uint32_t SA, uint32_t B, uint32_t C,
-                              uint32_t old_addr)
+                              RowRef dl, uint32_t out_addr)
 {
+  using ar = A<EX>;
   if (!live) return;
   float* vy1 = node_row(nd, a, v);
-  allpass_pre<EX>(vy1, a.coef[(size_t)nd.co_off * a.V + v], x, SA, out_addr);
-  RowRef din;
-  din.is_row = true, din.addr = SA, din.k = 0.f;
   const float blk = (float)MLB_BLOCK;
+  const float md = a.coef[(size_t)(nd.co_off + (OP == MLB_OP_ALLPASS_PB ? 1 : 2)) * a.V + v];
+  const RingRef r = node_ring<EX>(nd, a, v, t, ar::sub(md, blk));  // setMaxDelayInSamples(d - 64), F:1125-1128
+  PitchbendPlan p;
+  OldBlock old;
   if constexpr (OP == MLB_OP_ALLPASS_PB)
   {
-    const RingRef r = node_ring<EX>(nd, a, v, t, A<EX>::sub(a.coef[(size_t)(nd.co_off + 1) * a.V + v], blk));
-    pitchbend_taps<EX>(r, a, nd.st_off, v, din, [&](int n) { return A<EX>::sub(dl.get(n), blk); }, B, C,
-                       old_addr);
-#pragma unroll 4
-    for (int n = 0; n < MLB_BLOCK; ++n) vy1[n] = pitchbend_mix<EX>(B, C, n);
+    pitchbend_prepare<EX>(p, r, a, nd.st_off, v, [&](int n) { return ar::sub(dl.get(n), blk); });  // F:1151
+    if (p.ahead) old.save(r);
   }
+  {
+    const float g = -a.coef[(size_t)nd.co_off * a.V + v];
+    const float4* v4 = reinterpret_cast<const float4*>(vy1);
+    float4* ring4 = reinterpret_cast<float4*>(r.p + r.w);
+    float4 vbuf[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) vbuf[q] = v4[q];
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+    {
+      const float4 xi = x.get4(q), yi = vbuf[q];
+      float4 din, y;
+      din.x = ar::sub(xi.x, ar::mul(yi.x, g)), y.x = ar::add(ar::mul(din.x, g), yi.x);
+      din.y = ar::sub(xi.y, ar::mul(yi.y, g)), y.y = ar::add(ar::mul(din.y, g), yi.y);
+      din.z = ar::sub(xi.z, ar::mul(yi.z, g)), y.z = ar::add(ar::mul(din.z, g), yi.z);
+      din.w = ar::sub(xi.w, ar::mul(yi.w, g)), y.w = ar::add(ar::mul(din.w, g), yi.w);
+      ring4[q] = din;  // IntegerDelay block write of the delay input
+      sts128(out_addr + (uint32_t)q * 16u, y);
+    }
+  }
+  if constexpr (OP == MLB_OP_ALLPASS_PB)
+    pitchbend_run<EX>(p, r, old, a, nd.st_off, v, vy1);
   else
   {
-    const float d = A<EX>::sub(a.coef[(size_t)(nd.co_off + 1) * a.V + v], blk);  // setDelayInSamples(d - 64)
-    const RingRef r = node_ring<EX>(nd, a, v, t, A<EX>::sub(a.coef[(size_t)(nd.co_off + 2) * a.V + v], blk));
+    const float d = ar::sub(a.coef[(size_t)(nd.co_off + 1) * a.V + v], blk);  // setDelayInSamples(d - 64), F:1123
     if constexpr (OP == MLB_OP_ALLPASS_INT)
     {
-      ring_write_block(r, din);
-      ring_read_block(r, cvt_trunc(d), B);
+      float x1 = 0.f, y1 = 0.f;
+      ring_block_out<EX, false>(r, cvt_trunc(d), x1, y1, 0.f, vy1);
     }
     else
-      frac_delay_block<EX>(r, a, nd.st_off, v, d, din, B);
-    RowRef res;
-    res.is_row = true, res.addr = B, res.k = 0.f;
-    row_smem_to_global(res, vy1);
+    {
+      int32_t di;
+      float coeff;
+      frac_split<EX>(d, di, coeff);
+      float x1 = u2f(a.state[(size_t)nd.st_off * a.V + v]), y1 = u2f(a.state[(size_t)(nd.st_off + 1) * a.V + v]);
+      ring_block_out<EX, true>(r, di, x1, y1, coeff, vy1);
+      a.state[(size_t)nd.st_off * a.V + v] = f2u(x1);
+      a.state[(size_t)(nd.st_off + 1) * a.V + v] = f2u(y1);
+    }
   }
 }
 
@@ -614,9 +717,6 @@ __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
   const int v = v0 + lane;
   const bool live = v < a.V;
   const uint32_t rows = smem_u32(smem_raw) + (uint32_t)lane * kRowStride;  // [slot][lane][68]
-  // scratch rows of the delay functors: delay input, two tap streams, the ring's oldest block
-  const uint32_t sA = rows + (uint32_t)a.scratch_slot * kSlotBytes, sB = sA + kSlotBytes;
-  const uint32_t sC = sB + kSlotBytes, sOld = sC + kSlotBytes;
 
   for (int t = 0; t < a.T; ++t)
   {
@@ -641,9 +741,15 @@ __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
         {
           const float4* src = reinterpret_cast<const float4*>(
               a.in + (((size_t)t * a.n_in + nd.iarg) * a.V + (live ? v : 0)) * MLB_BLOCK);
-#pragma unroll 4
-          for (int q = 0; q < 16; ++q)
-            sts128(o + (uint32_t)q * 16u, live ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f));
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+          {
+            float4 buf[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) buf[q] = live ? __ldg(src + h * 8 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sts128(o + (uint32_t)(h * 8 + q) * 16u, buf[q]);
+          }
           break;
         }
 #define MLB_GEN_CASE(OPN) \
@@ -684,21 +790,13 @@ __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
         case MLB_OP_GLIDE: run_glide_node<EX>(nd, a, v, live, r[0], o); break;
         case MLB_OP_INTERPOLATOR1: run_interp1_node<EX>(nd, a, v, live, r[0], o); break;
         case MLB_OP_INTEGER_DELAY: run_int_delay_node<EX>(nd, a, v, live, t, r[0], o); break;
-        case MLB_OP_INTEGER_DELAY_VAR: run_int_delay_var_node<EX>(nd, a, v, live, t, r[0], r[1], o, sOld); break;
+        case MLB_OP_INTEGER_DELAY_VAR: run_delay_var_node<EX, false>(nd, a, v, live, t, r[0], r[1], o); break;
         case MLB_OP_FRACTIONAL_DELAY: run_frac_delay_node<EX>(nd, a, v, live, t, r[0], o); break;
-        case MLB_OP_FRACTIONAL_DELAY_VAR:
-          run_frac_delay_var_node<EX>(nd, a, v, live, t, r[0], r[1], o, sOld);
-          break;
-        case MLB_OP_PITCHBEND_DELAY: run_pitchbend_node<EX>(nd, a, v, live, t, r[0], r[1], o, sB, sC, sOld); break;
-        case MLB_OP_ALLPASS_INT:
-          run_allpass_node<MLB_OP_ALLPASS_INT, EX>(nd, a, v, live, t, r[0], r[1], o, sA, sB, sC, sOld);
-          break;
-        case MLB_OP_ALLPASS_FRAC:
-          run_allpass_node<MLB_OP_ALLPASS_FRAC, EX>(nd, a, v, live, t, r[0], r[1], o, sA, sB, sC, sOld);
-          break;
-        case MLB_OP_ALLPASS_PB:
-          run_allpass_node<MLB_OP_ALLPASS_PB, EX>(nd, a, v, live, t, r[0], r[1], o, sA, sB, sC, sOld);
-          break;
+        case MLB_OP_FRACTIONAL_DELAY_VAR: run_delay_var_node<EX, true>(nd, a, v, live, t, r[0], r[1], o); break;
+        case MLB_OP_PITCHBEND_DELAY: run_pitchbend_node<EX>(nd, a, v, live, t, r[0], r[1], o); break;
+        case MLB_OP_ALLPASS_INT: run_allpass_node<MLB_OP_ALLPASS_INT, EX>(nd, a, v, live, t, r[0], r[1], o); break;
+        case MLB_OP_ALLPASS_FRAC: run_allpass_node<MLB_OP_ALLPASS_FRAC, EX>(nd, a, v, live, t, r[0], r[1], o); break;
+        case MLB_OP_ALLPASS_PB: run_allpass_node<MLB_OP_ALLPASS_PB, EX>(nd, a, v, live, t, r[0], r[1], o); break;
         case MLB_OP_FEEDBACK_READ:
           if (live) row_global_to_smem(node_row(nd, a, v), o);
           break;

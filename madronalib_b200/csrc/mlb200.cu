@@ -439,7 +439,7 @@ struct mlb_graph
   // generic interpreter
   std::vector<GNode> gnodes;
   GNode* d_gnodes = nullptr;
-  int scratch_slot = 0;
+
   int n_slots = 0;
 
   // FDN delay memory
@@ -693,13 +693,11 @@ static int build_generic(mlb_graph* g)
     if (slot[i] >= 0 && last_use[i] < 0 && N[i].op != MLB_OP_FDN8_R) free_slots.push_back(slot[i]);
   }
   g->n_slots = std::max(1, n_slots);
-  g->scratch_slot = g->n_slots;
-  if (g->has_dmem) g->n_slots += 4;  // delay input, two tap streams, the ring's oldest block
   const size_t smem = (size_t)g->n_slots * kSlotBytes;
   if (smem > g_smem_optin)
     return fail(MLB_ERR_UNSUPPORTED, "graph needs %d live rows (%zu B shared memory > %zu)",
                 g->n_slots, smem, g_smem_optin);
-  g->kernel_name = g->exact ? "generic" : "generic(fast)";
+  g->kernel_name = std::string(g->exact ? "generic" : "generic(fast)") + "[" + std::to_string(g->n_slots) + " rows]";
   return MLB_OK;
 }
 
@@ -1186,7 +1184,6 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
     a.fdn_ring = g->d_ring, a.fdn_carry = g->d_carry, a.fdn_ring_len = g->ring_len;
     a.blocks_done = g->blocks_done;
     a.dmem = g->d_dmem;
-    a.scratch_slot = g->scratch_slot;
     const size_t smem = (size_t)g->n_slots * kSlotBytes;
     if (g->exact)
     {

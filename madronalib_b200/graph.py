@@ -293,11 +293,12 @@ def graph_aaltoverb():
     n["glideDelay"] = g.node("GLIDE", n["size2"])          # reverb.cpp:86
     n["glideFeedback"] = g.node("GLIDE", n["feedback"])    # :87
     dparam = g.node("MULTIPLY", n["sr"], n["glideDelay"])  # :93
-    vt = [g.node("MAX", g.node("MULTIPLY", n["apscale%d" % i], dparam), n["vmin"]) for i in range(10)]  # :94-103
     mono = g.node("ADD", in0, in1)                         # :106
 
-    def ap(i, x):  # r->mAp<i+1>(x, vt<i+1>)
-        n["ap%d" % (i + 1)] = g.node("ALLPASS_PB", x, vt[i])
+    def ap(i, x):  # r->mAp<i+1>(x, vt<i+1>), vt<i+1> = max(scale * delayParamInSamples, vMin) (:94-103);
+        # the stateless vt row is computed next to its only reader so that few rows are live at once
+        vt = g.node("MAX", g.node("MULTIPLY", n["apscale%d" % i], dparam), n["vmin"])
+        n["ap%d" % (i + 1)] = g.node("ALLPASS_PB", x, vt)
         return n["ap%d" % (i + 1)]
 
     diffused = ap(3, ap(2, ap(1, ap(0, mono))))            # :107

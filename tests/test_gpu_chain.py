@@ -128,7 +128,7 @@ def test_generic_kernel_equals_fused(gpu, port):
     inp = w.inputs(3)
     fo, _, fs, fname = run_gpu(gpu, w, 3, inp)
     go, _, gs, gname = run_gpu(gpu, w, 3, inp, flags=gpu.FLAG_FORCE_GENERIC)
-    assert fname.startswith("fused:") and gname == "generic"
+    assert fname.startswith("fused:") and gname.startswith("generic")
     assert_same_bits(go, fo)
     assert_state_equal(gs, fs)
 
@@ -227,7 +227,7 @@ def test_fdn8_fused_and_generic_agree_with_oracle(gpu, port, n_voices, n_blocks,
     po, pm, ps = port.run(w.spec, n_voices, n_blocks, inp, w.state, w.coef, want_mix=True, mix_mode=1)
     for flags, kind in ((0, "fused:fm3_fdn8"), (gpu.FLAG_FORCE_GENERIC, "generic")):
         go, gm, gs, name = run_gpu(gpu, w, n_blocks, inp, flags=flags, want_mix=True, splits=splits)
-        assert name == kind, name
+        assert name.startswith(kind), name
         assert_same_bits(go, po, kind + " out")
         assert_same_bits(gm, pm, kind + " mix")
         assert_state_equal(gs, ps, kind)

@@ -126,7 +126,7 @@ def test_pulse_and_onepole_family_in_one_graph(gpu, port):
     w = wl.Workload("pulse", g, V, coef, st)
     po, pm, ps = port.run(g, V, T, inp, st, coef, want_mix=True, mix_mode=1)
     go, gm, gs, name = run_gpu(gpu, w, T, inp, want_mix=True, splits=(2, 3))
-    assert name == "generic"
+    assert name.startswith("generic")
     assert_same_bits(go, po)
     assert_same_bits(gm, pm)
     assert_state_equal(gs, ps)
