@@ -296,6 +296,7 @@ typedef struct mlb_graph mlb_graph; /* opaque; owns device state, coefs, delay m
 #define MLB_GRAPH_EXACT 0u        /* bit-exact with the reference SSE path (default) */
 #define MLB_GRAPH_FAST 1u         /* allow FMA contraction (stated tolerance) */
 #define MLB_GRAPH_FORCE_GENERIC 2u /* skip fused specialisations, use the graph interpreter kernel */
+#define MLB_GRAPH_SINGLE_STAGE 4u  /* interpreter: one CTA per voice group, no stage pipeline across CTAs */
 
 /* Create a graph for n_voices voices on the current device.
  * outs[n_out] = node indices whose rows are written to out planes / mix bus.

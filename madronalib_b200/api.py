@@ -26,6 +26,7 @@ _cf = ctypes.c_float
 FLAG_EXACT = 0
 FLAG_FAST = 1
 FLAG_FORCE_GENERIC = 2
+FLAG_SINGLE_STAGE = 4
 
 
 class MlbError(RuntimeError):

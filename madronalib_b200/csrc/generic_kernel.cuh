@@ -37,10 +37,27 @@ struct GNode
   int st_off, co_off;
   int out_plane;   // >= 0: also written to out / mix plane
   int iarg;
+  int src_node;    // index in the caller's node list, -1 for an import pseudo-node
+  int chan_out;    // >= 0: the row is also stored to this channel plane (read by a later stage)
   // delay memory of this node (float offsets into GenericArgs::dmem)
   unsigned ring_stride;          // floats between the rings of consecutive voices (power of two)
   unsigned long long row_off;    // [V][64] member row (Allpass::vy1, LinearGlide::mCurrVec, feedback)
   unsigned long long ring_off;   // [V][ring_stride] IntegerDelay ring
+};
+
+// internal op of the stage pipeline: load a row another stage stored in channel plane `iarg`
+#define MLB_OP_IMPORT_ROW 200
+
+// One pipeline stage = the nodes [node_begin, node_end) of the program.  Before block t the stage
+// waits until every stage in wait_stage[] has finished block t, and every stage in fbwait_stage[]
+// (writers of the feedback rows it reads) has finished block t-1.
+struct GStage
+{
+  static constexpr int kMaxWait = 8;
+  int node_begin, node_end;
+  int n_wait, n_fbwait;
+  int wait_stage[kMaxWait];
+  int fbwait_stage[kMaxWait];
 };
 
 struct GenericArgs
@@ -59,6 +76,10 @@ struct GenericArgs
   int fdn_ring_len;        // power of two
   long long blocks_done;   // IntegerDelay write index = (64 * blocks_done) & (ring_len - 1)
   float* dmem;             // delay memory of the section-8(f) functors (rows + rings)
+  const GStage* stages;
+  int n_stages, n_chan;
+  unsigned* sync;          // [0] ticket counter; [1 + s*n_groups + g] blocks finished by (stage s, group g)
+  float* chan;             // channel planes [T][n_chan][V][64]
 };
 
 struct RowRef
@@ -707,12 +728,31 @@ MLB_DEV void run_fdn8_node(const GNode& nd, const GenericArgs& a, int v, bool li
   for (int l = 0; l < 8; ++l) a.state[(size_t)(nd.st_off + l) * a.V + v] = f2u(y1[l]);
 }
 
+MLB_DEV unsigned ld_acquire_u32(const unsigned* p)
+{
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+MLB_DEV void st_release_u32(unsigned* p, unsigned v)
+{
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 template <bool EX>
 __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int lane = threadIdx.x;
-  const int group = blockIdx.x;
+  // (stage, group) by ticket, stage-major: a CTA only ever waits for CTAs with smaller tickets,
+  // which are already running or done -- no assumption about block scheduling order
+  unsigned ticket = 0;
+  if (lane == 0) ticket = atomicAdd(a.sync, 1u);
+  ticket = __shfl_sync(0xffffffffu, ticket, 0);
+  const int stage = (int)(ticket / (unsigned)a.n_groups);
+  const int group = (int)(ticket % (unsigned)a.n_groups);
+  const GStage sg = a.stages[stage];
+  unsigned* const progress = a.sync + 1;
   const int v0 = group * 32;
   const int v = v0 + lane;
   const bool live = v < a.V;
@@ -720,9 +760,21 @@ __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
 
   for (int t = 0; t < a.T; ++t)
   {
-    for (int i = 0; i < a.n_nodes; ++i)
+    if (a.n_stages > 1)
     {
-      GNode nd = a.nodes[i];
+      if (lane < sg.n_wait)
+        while (ld_acquire_u32(progress + (size_t)sg.wait_stage[lane] * a.n_groups + group) <= (unsigned)t)
+          __nanosleep(100);
+      if (lane >= 8 && lane - 8 < sg.n_fbwait)
+        while (ld_acquire_u32(progress + (size_t)sg.fbwait_stage[lane - 8] * a.n_groups + group) < (unsigned)t)
+          __nanosleep(100);
+      __syncwarp();
+    }
+    GNode nxt = a.nodes[sg.node_begin];
+    for (int i = sg.node_begin; i < sg.node_end; ++i)
+    {
+      const GNode nd = nxt;
+      if (i + 1 < sg.node_end) nxt = a.nodes[i + 1];  // descriptor of the next node is in flight while this one runs
       RowRef r[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k)
@@ -737,6 +789,21 @@ __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
       {
         case MLB_OP_PARAM:
         case MLB_OP_FDN8_R: break;  // PARAM is an operand kind; FDN8_R aliases FDN8's 2nd slot
+        case MLB_OP_IMPORT_ROW:
+        {
+          const float4* src = reinterpret_cast<const float4*>(
+              a.chan + (((size_t)t * a.n_chan + nd.iarg) * a.V + (live ? v : 0)) * MLB_BLOCK);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+          {
+            float4 buf[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) buf[q] = live ? __ldcg(src + h * 8 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sts128(o + (uint32_t)(h * 8 + q) * 16u, buf[q]);
+          }
+          break;
+        }
         case MLB_OP_INPUT:
         {
           const float4* src = reinterpret_cast<const float4*>(
@@ -798,7 +865,20 @@ __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
         case MLB_OP_ALLPASS_FRAC: run_allpass_node<MLB_OP_ALLPASS_FRAC, EX>(nd, a, v, live, t, r[0], r[1], o); break;
         case MLB_OP_ALLPASS_PB: run_allpass_node<MLB_OP_ALLPASS_PB, EX>(nd, a, v, live, t, r[0], r[1], o); break;
         case MLB_OP_FEEDBACK_READ:
-          if (live) row_global_to_smem(node_row(nd, a, v), o);
+          if (live)
+          {
+            // the row may have been written by another CTA (the FEEDBACK_WRITE's stage): L2 loads
+            const float4* s4 = reinterpret_cast<const float4*>(node_row(nd, a, v));
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+            {
+              float4 buf[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) buf[q] = __ldcg(s4 + h * 8 + q);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) sts128(o + (uint32_t)(h * 8 + q) * 16u, buf[q]);
+            }
+          }
           break;
         case MLB_OP_FEEDBACK_WRITE:  // row_off is the FEEDBACK_READ node's row
           if (live)
@@ -811,6 +891,12 @@ __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
         default: dispatch_stateless<EX>(nd.op, r[0], r[1], r[2], o); break;
       }
 
+      if (nd.chan_out >= 0 && live)
+      {
+        float4* dst = reinterpret_cast<float4*>(a.chan + (((size_t)t * a.n_chan + nd.chan_out) * a.V + v) * MLB_BLOCK);
+#pragma unroll 4
+        for (int q = 0; q < 16; ++q) __stcg(dst + q, lds128(o + (uint32_t)q * 16u));
+      }
       if (nd.out_plane >= 0)
       {
         // source row of this output: PARAM nodes broadcast their scalar
@@ -851,6 +937,13 @@ __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
         }
       }
       __syncwarp();
+    }
+    if (a.n_stages > 1)
+    {
+      // publish block t of this stage: channel rows, feedback rows and delay memory written above
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) st_release_u32(progress + (size_t)stage * a.n_groups + group, (unsigned)(t + 1));
     }
   }
 }

@@ -437,8 +437,14 @@ struct mlb_graph
   FdnArgs fargs{};
 
   // generic interpreter
-  std::vector<GNode> gnodes;
+  std::vector<GNode> gnodes;   // stage programs back to back (imports + nodes)
   GNode* d_gnodes = nullptr;
+  std::vector<GStage> gstages;
+  GStage* d_gstages = nullptr;
+  int n_stages = 1, n_chan = 0;
+  unsigned* d_gsync = nullptr;  // [0] ticket, [1 + s*G + g] blocks finished by stage s of group g
+  float* d_chan = nullptr;      // channel planes [T][n_chan][V][64]
+  size_t chan_cap = 0;
 
   int n_slots = 0;
 
@@ -605,30 +611,51 @@ static bool match_fused_chain(mlb_graph* g)
   return false;
 }
 
-// Build the interpreter program: operand kinds, shared-memory slot allocation by liveness.
+static int env_int(const char* name, int dflt);
+
+// Relative cost of one node-block in the interpreter (used only to balance pipeline stages).
+static int node_cost(int op)
+{
+  if (op == MLB_OP_PARAM || op == MLB_OP_INPUT || op == MLB_OP_FDN8_R) return 0;
+  if (op >= MLB_OP_MAP_FIRST && op < MLB_OP_MAP_END) return 2;
+  switch (op)
+  {
+    case MLB_OP_ONEPOLE:
+    case MLB_OP_DIFFERENTIATOR:
+    case MLB_OP_INTEGRATOR:
+    case MLB_OP_DCBLOCKER:
+    case MLB_OP_RMS:
+    case MLB_OP_ALLPASS1: return 8;
+    case MLB_OP_FDN8: return 200;
+    case MLB_OP_ALLPASS_PB:
+    case MLB_OP_PITCHBEND_DELAY: return 40;
+    case MLB_OP_ALLPASS_INT:
+    case MLB_OP_ALLPASS_FRAC:
+    case MLB_OP_FRACTIONAL_DELAY:
+    case MLB_OP_FRACTIONAL_DELAY_VAR:
+    case MLB_OP_INTEGER_DELAY_VAR: return 20;
+    case MLB_OP_FEEDBACK_READ:
+    case MLB_OP_FEEDBACK_WRITE:
+    case MLB_OP_INTEGER_DELAY:
+    case MLB_OP_GLIDE:
+    case MLB_OP_INTERPOLATOR1: return 4;
+    default: return 16;  // SVF family, generators, envelopes
+  }
+}
+
+// Build the interpreter program.  The node list is cut into S contiguous *stages*
+// (balanced by node_cost); stage s of voice group g is run by its own one-warp CTA for all T
+// blocks, so a graph with few voices still fills the machine: stage s works on block t while
+// stage s+1 works on block t-1 (a software pipeline across CTAs).  A row that crosses a stage
+// boundary travels through a *channel* plane in global memory [T][n_chan][V][64]; per-(stage,
+// group) progress words order the producer's stores before the consumer's loads.  Inside a stage
+// rows live in shared-memory slots allocated by liveness, as before.  S = 1 is the plain
+// single-CTA-per-group interpreter.
 static int build_generic(mlb_graph* g)
 {
   const auto& N = g->nodes;
   const int n = (int)N.size();
-  std::vector<int> last_use(n, -1);
-  for (int i = 0; i < n; ++i)
-    for (int k = 0; k < MLB_MAX_INS; ++k)
-      if (N[i].in[k] >= 0) last_use[N[i].in[k]] = i;
-  // FDN8_R keeps its FDN8's second row alive: treat reads of FDN8_R as reads of that slot
-  std::vector<int> slot(n, -1), slot2(n, -1);
-  std::vector<int> free_slots;
-  int n_slots = 0;
-  auto alloc = [&]()
-  {
-    if (!free_slots.empty())
-    {
-      int s = free_slots.back();
-      free_slots.pop_back();
-      return s;
-    }
-    return n_slots++;
-  };
-  g->gnodes.assign(n, GNode{});
+  const int n_groups = (g->V + 31) / 32;
   std::vector<int> out_plane(n, -1);
   for (size_t c = 0; c < g->outs.size(); ++c)
   {
@@ -636,68 +663,224 @@ static int build_generic(mlb_graph* g)
       return fail(MLB_ERR_UNSUPPORTED, "a node may appear only once in outs");
     out_plane[g->outs[c]] = (int)c;
   }
+  // ---- choose the number of stages ----
+  long long total_cost = 0;
+  int n_real = 0;
   for (int i = 0; i < n; ++i)
   {
-    GNode& gn = g->gnodes[i];
-    gn.op = N[i].op;
-    gn.st_off = g->st_off[i];
-    gn.co_off = g->co_off[i];
-    gn.iarg = N[i].iarg;
-    gn.out_plane = out_plane[i];
-    gn.out_slot = gn.out_slot2 = -1;
+    total_cost += node_cost(N[i].op);
+    if (node_cost(N[i].op) > 0) ++n_real;
+  }
+  int S = 1;
+  {
+    const int target_warps = g_sm_count * 8;
+    S = (target_warps + n_groups - 1) / n_groups;
+    S = std::min(S, std::max(1, n_real / 3));
+    S = std::min(S, 64);
+    S = env_int("MLB_STAGES", S);
+    S = std::min(std::max(S, 1), std::max(1, n_real));
+    if (g->fdn_node >= 0) S = 1;  // FDN8_R aliases the second row of its FDN8: keep them together
+    if (g->flags & MLB_GRAPH_SINGLE_STAGE) S = 1;
+  }
+  // ---- cut points: stage_of[i], contiguous, balanced by cost ----
+  // A feedback loop (FEEDBACK_READ ... its FEEDBACK_WRITE) stays inside one stage: the reader of
+  // block t+1 would otherwise wait for a CTA with a LARGER ticket, which need not be resident.
+  std::vector<char> no_cut(n, 0);
+  for (int q = 0; q < n; ++q)
+    if (N[q].op == MLB_OP_FEEDBACK_WRITE)
+      for (int i = N[q].iarg; i < q; ++i) no_cut[i] = 1;
+  std::vector<int> stage_of(n, 0);
+  {
+    long long acc = 0;
+    int s = 0;
+    for (int i = 0; i < n; ++i)
+    {
+      stage_of[i] = s;
+      acc += node_cost(N[i].op);
+      // close the stage once it holds its share of the cost (and a real node)
+      if (s < S - 1 && !no_cut[i] && acc * S >= total_cost * (s + 1) && node_cost(N[i].op) > 0) ++s;
+    }
+    S = stage_of[n - 1] + 1;
+  }
+  // ---- channels: one per node whose row is read in a later stage (INPUT rows are re-read from `in`) ----
+  std::vector<int> chan_of(n, -1);
+  int n_chan = 0;
+  for (int i = 0; i < n; ++i)
     for (int k = 0; k < MLB_MAX_INS; ++k)
     {
       const int src = N[i].in[k];
-      gn.in_kind[k] = OPERAND_NONE;
-      gn.in_ref[k] = 0;
-      if (src < 0) continue;
-      if (N[src].op == MLB_OP_PARAM)
+      if (src < 0 || stage_of[src] == stage_of[i]) continue;
+      if (N[src].op == MLB_OP_PARAM || N[src].op == MLB_OP_INPUT) continue;
+      if (chan_of[src] < 0) chan_of[src] = n_chan++;
+    }
+  // ---- per-stage programs ----
+  g->gnodes.clear();
+  g->gstages.assign(S, GStage{});
+  int max_slots = 1;
+  for (int s = 0; s < S; ++s)
+  {
+    GStage& st = g->gstages[s];
+    st.node_begin = (int)g->gnodes.size();
+    std::vector<int> members;
+    for (int i = 0; i < n; ++i)
+      if (stage_of[i] == s) members.push_back(i);
+    // rows produced outside this stage and read inside it
+    std::vector<int> ext;
+    for (int i : members)
+      for (int k = 0; k < MLB_MAX_INS; ++k)
       {
-        gn.in_kind[k] = OPERAND_PARAM;
-        gn.in_ref[k] = g->co_off[src];
+        const int src = N[i].in[k];
+        if (src < 0 || stage_of[src] == s || N[src].op == MLB_OP_PARAM) continue;
+        if (std::find(ext.begin(), ext.end(), src) == ext.end()) ext.push_back(src);
+      }
+    // producer stages this stage must wait for (block t), and feedback partners
+    auto add_wait = [&](int ws)
+    {
+      if (ws == s) return true;
+      for (int q = 0; q < st.n_wait; ++q)
+        if (st.wait_stage[q] == ws) return true;
+      if (st.n_wait == GStage::kMaxWait) return false;
+      st.wait_stage[st.n_wait++] = ws;
+      return true;
+    };
+    auto add_fbwait = [&](int ws)
+    {
+      if (ws == s) return true;
+      for (int q = 0; q < st.n_fbwait; ++q)
+        if (st.fbwait_stage[q] == ws) return true;
+      if (st.n_fbwait == GStage::kMaxWait) return false;
+      st.fbwait_stage[st.n_fbwait++] = ws;
+      return true;
+    };
+    bool ok = true;
+    for (int src : ext)
+      if (N[src].op != MLB_OP_INPUT) ok = ok && add_wait(stage_of[src]);
+    for (int i : members)
+    {
+      // a FEEDBACK_READ at block t needs its writer's block t-1; the writer must not overwrite the
+      // row before the reader of the same block has taken it
+      if (N[i].op == MLB_OP_FEEDBACK_READ)
+        for (int q = 0; q < n; ++q)
+          if (N[q].op == MLB_OP_FEEDBACK_WRITE && N[q].iarg == i) ok = ok && add_fbwait(stage_of[q]);
+      if (N[i].op == MLB_OP_FEEDBACK_WRITE) ok = ok && add_wait(stage_of[N[i].iarg]);
+    }
+    if (!ok) return fail(MLB_ERR_UNSUPPORTED, "stage %d of the interpreter program depends on too many stages", s);
+
+    // liveness inside the stage: local index -> last local reader
+    const int n_ext = (int)ext.size(), n_loc = n_ext + (int)members.size();
+    auto local_of = [&](int node)
+    {
+      for (int e = 0; e < n_ext; ++e)
+        if (ext[e] == node) return e;
+      for (size_t m = 0; m < members.size(); ++m)
+        if (members[m] == node) return n_ext + (int)m;
+      return -1;
+    };
+    std::vector<int> last_use(n_loc, -1), slot(n_loc, -1), slot2(n_loc, -1);
+    for (size_t m = 0; m < members.size(); ++m)
+      for (int k = 0; k < MLB_MAX_INS; ++k)
+      {
+        const int src = N[members[m]].in[k];
+        if (src < 0 || N[src].op == MLB_OP_PARAM) continue;
+        last_use[local_of(src)] = n_ext + (int)m;
+      }
+    std::vector<int> free_slots;
+    int n_slots = 0;
+    auto alloc = [&]()
+    {
+      if (!free_slots.empty())
+      {
+        int q = free_slots.back();
+        free_slots.pop_back();
+        return q;
+      }
+      return n_slots++;
+    };
+    for (int li = 0; li < n_loc; ++li)
+    {
+      GNode gn{};
+      const bool is_ext = li < n_ext;
+      const int node = is_ext ? ext[li] : members[li - n_ext];
+      gn.src_node = is_ext ? -1 : node;
+      gn.out_slot = gn.out_slot2 = -1;
+      gn.out_plane = -1;
+      gn.chan_out = -1;
+      for (int k = 0; k < MLB_MAX_INS; ++k) gn.in_kind[k] = OPERAND_NONE, gn.in_ref[k] = 0;
+      if (is_ext)
+      {
+        // import: re-read an external input plane, or load the producer's channel plane
+        if (N[node].op == MLB_OP_INPUT)
+          gn.op = MLB_OP_INPUT, gn.iarg = N[node].iarg;
+        else
+          gn.op = MLB_OP_IMPORT_ROW, gn.iarg = chan_of[node];
+        slot[li] = alloc();
       }
       else
       {
-        gn.in_kind[k] = OPERAND_SLOT;
-        gn.in_ref[k] = slot[src];
+        gn.op = N[node].op;
+        gn.st_off = g->st_off[node];
+        gn.co_off = g->co_off[node];
+        gn.iarg = N[node].iarg;
+        gn.out_plane = out_plane[node];
+        gn.chan_out = chan_of[node];
+        for (int k = 0; k < MLB_MAX_INS; ++k)
+        {
+          const int src = N[node].in[k];
+          if (src < 0) continue;
+          if (N[src].op == MLB_OP_PARAM)
+            gn.in_kind[k] = OPERAND_PARAM, gn.in_ref[k] = g->co_off[src];
+          else
+            gn.in_kind[k] = OPERAND_SLOT, gn.in_ref[k] = slot[local_of(src)];
+        }
+        // allocate the output slot BEFORE freeing inputs: nodes never run in place
+        if (N[node].op == MLB_OP_FDN8_R)
+          slot[li] = slot2[local_of(N[node].in[0])];
+        else if (N[node].op != MLB_OP_PARAM)
+          slot[li] = alloc();
+        if (N[node].op == MLB_OP_FDN8) slot2[li] = alloc();
       }
-    }
-    // allocate the output slot BEFORE freeing inputs: nodes never run in place
-    if (N[i].op == MLB_OP_FDN8_R)
-      slot[i] = slot2[N[i].in[0]];
-    else if (N[i].op != MLB_OP_PARAM)
-      slot[i] = alloc();
-    if (N[i].op == MLB_OP_FDN8) slot2[i] = alloc();
-    gn.out_slot = slot[i];
-    gn.out_slot2 = slot2[i];
-    // release rows whose last reader is this node
-    for (int j = 0; j < i; ++j)
-    {
-      if (slot[j] < 0 || N[j].op == MLB_OP_FDN8_R) continue;
-      if (last_use[j] == i) free_slots.push_back(slot[j]);
-      if (N[j].op == MLB_OP_FDN8)
+      gn.out_slot = slot[li];
+      gn.out_slot2 = slot2[li];
+      g->gnodes.push_back(gn);
+      // release rows whose last reader is this node
+      for (int j = 0; j < li; ++j)
       {
-        // second row is read only through FDN8_R nodes; free it when their last reader ran
-        int lu = -1;
-        bool has_r = false;
-        for (int q = j + 1; q < n; ++q)
-          if (N[q].op == MLB_OP_FDN8_R && N[q].in[0] == j)
+        const int nj = j < n_ext ? ext[j] : members[j - n_ext];
+        if (slot[j] < 0 || N[nj].op == MLB_OP_FDN8_R) continue;
+        if (last_use[j] == li) free_slots.push_back(slot[j]);
+        if (N[nj].op == MLB_OP_FDN8 && j >= n_ext)
+        {
+          // second row is read only through FDN8_R nodes; free it when their last reader ran
+          int lu = -1;
+          bool has_r = false;
+          for (int q = j + 1; q < n_loc; ++q)
           {
-            has_r = true;
-            lu = std::max(lu, std::max(last_use[q], q));
+            const int nq = q < n_ext ? ext[q] : members[q - n_ext];
+            if (q >= n_ext && N[nq].op == MLB_OP_FDN8_R && N[nq].in[0] == nj)
+            {
+              has_r = true;
+              lu = std::max(lu, std::max(last_use[q], q));
+            }
           }
-        if ((has_r && lu == i) || (!has_r && i == j)) free_slots.push_back(slot2[j]);
+          if ((has_r && lu == li) || (!has_r && li == j)) free_slots.push_back(slot2[j]);
+        }
       }
+      // a row nobody in this stage reads can be recycled right after it was written out
+      if (slot[li] >= 0 && last_use[li] < 0 && !(li >= n_ext && N[node].op == MLB_OP_FDN8_R))
+        free_slots.push_back(slot[li]);
     }
-    // a row nobody reads can be recycled right after it was written out
-    if (slot[i] >= 0 && last_use[i] < 0 && N[i].op != MLB_OP_FDN8_R) free_slots.push_back(slot[i]);
+    st.node_end = (int)g->gnodes.size();
+    max_slots = std::max(max_slots, n_slots);
   }
-  g->n_slots = std::max(1, n_slots);
+  g->n_slots = std::max(1, max_slots);
+  g->n_stages = S;
+  g->n_chan = n_chan;
   const size_t smem = (size_t)g->n_slots * kSlotBytes;
   if (smem > g_smem_optin)
     return fail(MLB_ERR_UNSUPPORTED, "graph needs %d live rows (%zu B shared memory > %zu)",
                 g->n_slots, smem, g_smem_optin);
-  g->kernel_name = std::string(g->exact ? "generic" : "generic(fast)") + "[" + std::to_string(g->n_slots) + " rows]";
+  g->kernel_name = std::string(g->exact ? "generic" : "generic(fast)") + "[" + std::to_string(S) + " stages, " +
+                   std::to_string(g->n_slots) + " rows]";
   return MLB_OK;
 }
 
@@ -796,10 +979,14 @@ extern "C" int mlb_graph_create(const mlb_node* nodes, int n_nodes, const int32_
     g->kind = KIND_GENERIC;
     rc = build_generic(g);
     if (rc != MLB_OK) return cleanup(rc);
-    if (cudaMalloc(&g->d_gnodes, sizeof(GNode) * g->gnodes.size()) != cudaSuccess)
+    const size_t sync_words = 1 + (size_t)g->n_stages * ((V + 31) / 32);
+    if (cudaMalloc(&g->d_gnodes, sizeof(GNode) * g->gnodes.size()) != cudaSuccess ||
+        cudaMalloc(&g->d_gstages, sizeof(GStage) * g->gstages.size()) != cudaSuccess ||
+        cudaMalloc(&g->d_gsync, sync_words * 4) != cudaSuccess)
       return cleanup(fail(MLB_ERR_ALLOC, "cudaMalloc of graph program failed"));
     cudaMemcpy(g->d_gnodes, g->gnodes.data(), sizeof(GNode) * g->gnodes.size(),
                cudaMemcpyHostToDevice);
+    cudaMemcpy(g->d_gstages, g->gstages.data(), sizeof(GStage) * g->gstages.size(), cudaMemcpyHostToDevice);
     rc = size_functor_memory(g);
     if (rc != MLB_OK) return cleanup(rc);
   }
@@ -813,6 +1000,9 @@ extern "C" int mlb_graph_destroy(mlb_graph* g)
   cudaFree(g->d_state);
   cudaFree(g->d_coef);
   cudaFree(g->d_gnodes);
+  cudaFree(g->d_gstages);
+  cudaFree(g->d_gsync);
+  cudaFree(g->d_chan);
   cudaFree(g->d_ring);
   cudaFree(g->d_carry);
   cudaFree(g->d_dmem);
@@ -934,11 +1124,12 @@ static int size_functor_memory(mlb_graph* g)
     return fail(MLB_ERR_ALLOC, "cudaMalloc of %llu B delay memory failed", total * 4ull);
   g->dmem_floats = (size_t)total;
   g->ring_stride = stride;
-  for (int i = 0; i < n; ++i)
+  for (GNode& gn : g->gnodes)
   {
-    g->gnodes[i].ring_stride = stride[i];
-    g->gnodes[i].row_off = row_off[i];
-    g->gnodes[i].ring_off = ring_off[i];
+    if (gn.src_node < 0) continue;
+    gn.ring_stride = stride[gn.src_node];
+    gn.row_off = row_off[gn.src_node];
+    gn.ring_off = ring_off[gn.src_node];
   }
   CU_CHECK(cudaMemcpy(g->d_gnodes, g->gnodes.data(), sizeof(GNode) * g->gnodes.size(), cudaMemcpyHostToDevice));
   return mlb_graph_clear_delays(g);
@@ -1184,18 +1375,30 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
     a.fdn_ring = g->d_ring, a.fdn_carry = g->d_carry, a.fdn_ring_len = g->ring_len;
     a.blocks_done = g->blocks_done;
     a.dmem = g->d_dmem;
+    a.stages = g->d_gstages;
+    a.n_stages = g->n_stages;
+    a.n_chan = g->n_chan;
+    a.sync = g->d_gsync;
+    if (g->n_chan > 0)
+    {
+      rc = ensure_buf(&g->d_chan, &g->chan_cap, (size_t)T * g->n_chan * V * MLB_BLOCK * 4);
+      if (rc != MLB_OK) return rc;
+    }
+    a.chan = g->d_chan;
+    const int grid = n_groups * g->n_stages;
+    CU_CHECK(cudaMemsetAsync(g->d_gsync, 0, (1 + (size_t)grid) * 4, stream));
     const size_t smem = (size_t)g->n_slots * kSlotBytes;
     if (g->exact)
     {
       CU_CHECK(cudaFuncSetAttribute((const void*)generic_graph_kernel<true>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      generic_graph_kernel<true><<<n_groups, 32, smem, stream>>>(a);
+      generic_graph_kernel<true><<<grid, 32, smem, stream>>>(a);
     }
     else
     {
       CU_CHECK(cudaFuncSetAttribute((const void*)generic_graph_kernel<false>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      generic_graph_kernel<false><<<n_groups, 32, smem, stream>>>(a);
+      generic_graph_kernel<false><<<grid, 32, smem, stream>>>(a);
     }
     ++g_launches;
   }

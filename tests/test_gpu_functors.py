@@ -106,3 +106,19 @@ def test_functor_matches_committed_reference_golden(gpu, name):
     else:
         assert_same_bits(go, gold[name + "_out"], name)
     assert_state_equal(gs, gold[name + "_state1"], name)
+
+
+@pytest.mark.parametrize("stages", [1, 2, 5, 64])
+def test_stage_pipeline_gives_identical_bits(gpu, port, monkeypatch, stages):
+    """The interpreter cuts the program into stages run by different CTAs (rows cross through channel
+    planes, feedback rows through delay memory); any cut must give the same bits."""
+    monkeypatch.setenv("MLB_STAGES", str(stages))
+    for w, T in ((wl.config_6(70), 30), (wl.config_5(40, 64), 6), (wl.functor_case("feedback", 50), 12)):
+        inp = w.inputs(T)
+        po, pm, ps = port.run(w.spec, w.n_voices, T, inp, w.state, w.coef, want_mix=True, mix_mode=1)
+        go, gm, gs, kname = run_gpu(gpu, w, T, inp, want_mix=True, flags=gpu.FLAG_FORCE_GENERIC,
+                                    splits=(T // 2, T - T // 2))
+        assert "stages" in kname, kname
+        assert_same_bits(go, po, w.name)
+        assert_same_bits(gm, pm, w.name + " mix")
+        assert_state_equal(gs, ps, w.name)
