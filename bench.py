@@ -250,6 +250,11 @@ def run_cuda_arm(args):
     dev = torch.device("cuda", local_rank)
     w = wl.config_a(V)
     graph = api.VoiceGraph(w.spec, V, api.FLAG_FAST if args.fast else api.FLAG_EXACT)
+    # multi-GPU: SMs can be kept out of the persistent chain grid for the NCCL kernels of the overlapped
+    # mix-bus all-reduce.  Measured at 8 GPUs (profiles/scale8_r1.md): 0 reserved 5.59e12, 4 reserved
+    # 5.04e12 voice-samples/s -- the all-reduce already overlaps, so nothing is reserved by default.
+    reserved_sms = int(os.environ.get("MLB_BENCH_RESERVED_SMS", "0")) if world > 1 else 0
+    graph.reserve_sms(reserved_sms)
     graph.set_coefs(w.coef)
     graph.set_state(w.state)
 
@@ -282,7 +287,9 @@ def run_cuda_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
+    # untimed warm-up: at least 3 steps; with NCCL at least 20, its first collectives set up channels lazily
+    n_warm = max(args.warmup, 3 if world == 1 else 20)
+    for i in range(n_warm):
         step(i)
     drain()
     barrier()
@@ -399,7 +406,7 @@ def run_cuda_arm(args):
         cpu = cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "warmup": n_warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": "config A: 65536-voice SineGen->Lopass(SVF)->gain, 48 kHz, contract R "
@@ -408,6 +415,7 @@ def run_cuda_arm(args):
                                else "fast (FMA contraction allowed)"),
                 "voices_per_gpu": V, "blocks_per_step": T, "samples_per_block": BLOCK,
                 "mix_bus": use_mix, "parallelism": f"voices x{world} (weak), mix-bus all-reduce",
+                "reserved_sms": reserved_sms,
                 "l2": "inputs+outputs 2.1 GB per step >> 126 MB L2 (no flush needed)",
                 "kernel": graph.kernel_name,
             },

@@ -305,6 +305,10 @@ typedef struct mlb_graph mlb_graph; /* opaque; owns device state, coefs, delay m
 int mlb_graph_create(const mlb_node* nodes, int n_nodes, const int32_t* outs, int n_out,
                      int n_voices, unsigned flags, mlb_graph** out_graph);
 int mlb_graph_destroy(mlb_graph* g);
+/* Leave n_sms SMs out of the persistent chain grid (default 0) so that kernels of an overlapped
+ * collective -- the NCCL all-reduce of the mix bus in a multi-GPU run -- can be resident next to it
+ * (ours; the reference is single-device). */
+int mlb_graph_reserve_sms(mlb_graph* g, int n_sms);
 int mlb_graph_layout_of(const mlb_graph* g, mlb_layout* layout);
 /* name of the kernel variant chosen ("fused:sine_lopass_gain", "generic", ...) */
 const char* mlb_graph_kernel_name(const mlb_graph* g);

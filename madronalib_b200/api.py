@@ -67,6 +67,7 @@ def lib() -> ctypes.CDLL:
     L.mlb_graph_clear_delays.argtypes = [_vp]
     L.mlb_graph_delay_bytes.restype = ctypes.c_size_t
     L.mlb_graph_delay_bytes.argtypes = [_vp]
+    L.mlb_graph_reserve_sms.argtypes = [_vp, ctypes.c_int]
     L.mlb_graph_process_device.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, _vp]
     L.mlb_graph_process_host.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int]
     L.mlb_graph_last_kernel_ms.argtypes = [_vp, _vp]
@@ -244,6 +245,10 @@ class VoiceGraph:
         """Device pointers (torch tensors / ints); asynchronous on ``stream`` (cudaStream_t)."""
         _check(lib().mlb_graph_process_device(self._h, _ptr(inp), _ptr(out), _ptr(mix), int(n_blocks),
                                               stream or None))
+
+    def reserve_sms(self, n_sms: int) -> None:
+        """Keep n_sms SMs out of the persistent chain grid (room for an overlapped collective)."""
+        _check(lib().mlb_graph_reserve_sms(self._h, int(n_sms)))
 
     def last_kernel_ms(self) -> float:
         ms = ctypes.c_float(0)

@@ -454,6 +454,7 @@ struct mlb_graph
   float* d_carry = nullptr;
   int ring_len = 0;
   long long blocks_done = 0;
+  int reserved_sms = 0;
   // delay memory of the section-8(f) functors: member rows [V][64] and rings [V][stride] per node
   bool has_dmem = false;
   float* d_dmem = nullptr;
@@ -1025,6 +1026,12 @@ extern "C" int mlb_graph_destroy(mlb_graph* g)
   return MLB_OK;
 }
 
+extern "C" int mlb_graph_reserve_sms(mlb_graph* g, int n_sms)
+{
+  if (!g || n_sms < 0) return fail(MLB_ERR_INVALID, "bad argument");
+  g->reserved_sms = n_sms;
+  return MLB_OK;
+}
 extern "C" int mlb_graph_layout_of(const mlb_graph* g, mlb_layout* layout)
 {
   if (!g || !layout) return fail(MLB_ERR_INVALID, "null");
@@ -1287,7 +1294,10 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
   const size_t smem = (size_t)W * S * kBlockBytes + (size_t)W * S * 8;
   if (smem > g_smem_optin) return fail(MLB_ERR_INVALID, "chain launch needs %zu B shared memory", smem);
   const int ctas_per_sm = std::max<size_t>(1, (size_t)(227 * 1024) / (smem + 1024));
-  int n_ctas = std::min((n_groups + W - 1) / W, g_sm_count * ctas_per_sm);
+  // the grid is persistent and fills every SM's shared memory; a caller that overlaps a collective
+  // (the mix-bus all-reduce of a multi-GPU run) keeps a few SMs free for its kernels
+  const int sms = std::max(1, g_sm_count - std::max(0, g->reserved_sms));
+  int n_ctas = std::min((n_groups + W - 1) / W, sms * ctas_per_sm);
   n_ctas = std::min(std::max(env_int("MLB_CHAIN_CTAS", n_ctas), 1), (n_groups + W - 1) / W);
   CUtensorMap in_map, out_map;
   memset(&in_map, 0, sizeof(in_map));
