@@ -192,7 +192,20 @@ enum {
   /* stored by the FEEDBACK_WRITE of the previous block (zero at start);              */ \
   /* FEEDBACK_WRITE(in0).iarg = node index of its FEEDBACK_READ; it passes in0 on.    */ \
   X(FEEDBACK_READ, 108, 0, 0, 0)                                                         \
-  X(FEEDBACK_WRITE, 109, 1, 0, 0)
+  X(FEEDBACK_WRITE, 109, 1, 0, 0)                                                        \
+  /* ---- resampler primitives: HalfBandFilter, F:1245-1310.  State:   */ \
+  /* the four Allpass1 {x1,y1} pairs apa0, apa1, apb0, apb1, then b1 (9 words).          */ \
+  /* HALFBAND_UP(x) = upsampleFirstHalf(x); HALFBAND_UP_2(in = that node) =              */ \
+  /* upsampleSecondHalf(x) of the SAME filter (two rows at twice the rate);              */ \
+  /* HALFBAND_DOWN(x1, x2) = downsample(x1, x2) (two rows in, one row out).              */ \
+  /* Upsample2xFunction(fn, x) (MLDSPFunctional.h:114-160) with a stateless fn is        */ \
+  /* HALFBAND_DOWN(fn(HALFBAND_UP(x)), fn(HALFBAND_UP_2(x))).                            */ \
+  X(HALFBAND_UP, 110, 1, 9, 0)                                                           \
+  X(HALFBAND_UP_2, 111, 1, 0, 0)                                                         \
+  X(HALFBAND_DOWN, 112, 2, 9, 0)                                                         \
+  /* TempoLock(x, dydx, isr), F:1478-1579: in0 = input phasor row, in1 = ratio (sample   */ \
+  /* 0 of the row); state _omega, _x1v (fresh: _omega = -1); coef isr                    */ \
+  X(TEMPO_LOCK, 113, 2, 2, 1)
 
 /* Delay memory per voice: X(NAME, n_rows, n_rings) -- 64-float rows and rings.
  * PitchbendableDelay's two FractionalDelays are fed the same input on every sample
@@ -217,7 +230,7 @@ typedef enum mlb_op {
 #define MLB_X_ENUM(NAME, id, nin, nst, nco) MLB_OP_##NAME = id,
   MLB_OP_TABLE(MLB_X_ENUM)
 #undef MLB_X_ENUM
-  MLB_OP__END = 110
+  MLB_OP__END = 114
 } mlb_op;
 
 /* One node of a voice graph.  in[] index earlier nodes (topological order). */

@@ -201,4 +201,72 @@ struct RingRef
 // writes it (d mod R > R - 64): such lanes keep the ring's oldest block in a shared row
 MLB_DEV bool delay_reads_ahead(int32_t d, uint32_t mask) { return ((uint32_t)d & mask) > mask - 63u; }
 
+// ---- HalfBandFilter, F:1245-1310: two 2-section allpass branches (coefficients F:1305-1306) ----
+struct HalfBand
+{
+  float s[9];  // apa0{x1,y1} apa1{x1,y1} apb0{x1,y1} apb1{x1,y1} b1
+  template <bool EX>
+  MLB_DEV float a(float x)
+  {
+    return allpass1_tick<EX>(allpass1_tick<EX>(x, s[0], s[1], 0.07986642623635751f), s[2], s[3], 0.5453536510711322f);
+  }
+  template <bool EX>
+  MLB_DEV float b(float x)
+  {
+    return allpass1_tick<EX>(allpass1_tick<EX>(x, s[4], s[5], 0.28382934487410993f), s[6], s[7], 0.8344118914807379f);
+  }
+};
+
+// TempoLock::operator(), F:1494-1578 -- everything before the per-sample loop.  Returns false when
+// the input clock is stopped (output row = 0); otherwise omega / dydt drive the loop.
+template <bool EX>
+MLB_DEV bool tempo_lock_prepare(float x0, float x1s, float dydx, float isr, float& omega, float& x1v, float& dydt)
+{
+  using a = A<EX>;
+  if (x0 == -1.0f)
+  {
+    omega = -1.0f;
+    return false;
+  }
+  float dxdt;
+  if (omega > -1.f)
+  {
+    float dx = a::sub(x0, x1v);
+    if (dx < 0.f) dx = a::add(dx, 1.f);
+    dxdt = dx * 0.015625f;  // dx / 64, exact
+    dydt = a::mul(dxdt, dydx);
+    x1v = x0;
+  }
+  else
+  {
+    dxdt = a::sub(x1s, x0);
+    dydt = a::mul(dxdt, dydx);
+    x1v = a::sub(x0, dxdt * 64.f);
+    omega = fmodf(a::mul(x0, dydx), 1.0f);
+  }
+  bool lock = fabsf(a::sub(dydx, roundf(dydx))) < 0.001f;
+  const float rdydx = 1.0f / dydx;
+  if (fabsf(a::sub(rdydx, roundf(rdydx))) < 0.001f) lock = true;
+  if (lock)
+  {
+    float error;
+    if (dydx >= 1.f)
+    {
+      const float ref = a::mul(x0, dydx);
+      error = a::sub(omega, a::sub(ref, floorf(ref)));
+    }
+    else
+    {
+      const float ref = omega / dydx;
+      error = a::sub(a::sub(ref, floorf(ref)), x0);
+    }
+    const float errorDiff = a::sub(roundf(error), error);
+    float correction = a::mul(a::mul(errorDiff, isr), 4.0f);
+    const float lo = -dydt * 0.5f, hi = dydt;
+    correction = (correction < lo) ? lo : (correction > hi ? hi : correction);  // ml::clamp
+    dydt = a::add(dydt, correction);
+  }
+  return true;
+}
+
 }  // namespace mlb

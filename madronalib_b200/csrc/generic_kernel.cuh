@@ -670,6 +670,84 @@ MLB_DEV void run_allpass_node(const GNode& nd, const GenericArgs& a, int v, bool
   }
 }
 
+// HalfBandFilter::upsampleFirstHalf + upsampleSecondHalf, F:1248-1270: one input row -> two rows
+template <bool EX>
+MLB_DEV void run_halfband_up_node(const GNode& nd, const GenericArgs& a, int v, bool live, RowRef x,
+                                  uint32_t out1, uint32_t out2)
+{
+  if (!live) return;
+  HalfBand h;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) h.s[i] = u2f(a.state[(size_t)(nd.st_off + i) * a.V + v]);
+#pragma unroll 1
+  for (int q = 0; q < 16; ++q)
+  {
+    const float4 xi = x.get4(q);
+    float4 lo, hi;
+    lo.x = h.a<EX>(xi.x), lo.y = h.b<EX>(xi.x), lo.z = h.a<EX>(xi.y), lo.w = h.b<EX>(xi.y);
+    hi.x = h.a<EX>(xi.z), hi.y = h.b<EX>(xi.z), hi.z = h.a<EX>(xi.w), hi.w = h.b<EX>(xi.w);
+    const uint32_t dst = (q < 8 ? out1 : out2) + (uint32_t)((q & 7) * 2) * 16u;
+    sts128(dst, lo);
+    sts128(dst + 16u, hi);
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) a.state[(size_t)(nd.st_off + i) * a.V + v] = f2u(h.s[i]);
+}
+// HalfBandFilter::downsample(vx1, vx2), F:1272-1294: two rows -> one row
+template <bool EX>
+MLB_DEV void run_halfband_down_node(const GNode& nd, const GenericArgs& a, int v, bool live, RowRef x1,
+                                    RowRef x2, uint32_t out_addr)
+{
+  if (!live) return;
+  HalfBand h;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) h.s[i] = u2f(a.state[(size_t)(nd.st_off + i) * a.V + v]);
+#pragma unroll 1
+  for (int q = 0; q < 16; ++q)  // output float4 q <- input float4s 2q, 2q+1 of row (q < 8 ? x1 : x2)
+  {
+    const RowRef& x = q < 8 ? x1 : x2;
+    const float4 p0 = x.get4((q & 7) * 2), p1 = x.get4((q & 7) * 2 + 1);
+    float4 y;
+    float a0, b0;
+    a0 = h.a<EX>(p0.x), b0 = h.b<EX>(p0.y), y.x = A<EX>::mul(A<EX>::add(a0, h.s[8]), 0.5f), h.s[8] = b0;
+    a0 = h.a<EX>(p0.z), b0 = h.b<EX>(p0.w), y.y = A<EX>::mul(A<EX>::add(a0, h.s[8]), 0.5f), h.s[8] = b0;
+    a0 = h.a<EX>(p1.x), b0 = h.b<EX>(p1.y), y.z = A<EX>::mul(A<EX>::add(a0, h.s[8]), 0.5f), h.s[8] = b0;
+    a0 = h.a<EX>(p1.z), b0 = h.b<EX>(p1.w), y.w = A<EX>::mul(A<EX>::add(a0, h.s[8]), 0.5f), h.s[8] = b0;
+    sts128(out_addr + (uint32_t)q * 16u, y);
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) a.state[(size_t)(nd.st_off + i) * a.V + v] = f2u(h.s[i]);
+}
+// TempoLock::operator()(x, dydx, isr), F:1494-1578
+template <bool EX>
+MLB_DEV void run_tempo_lock_node(const GNode& nd, const GenericArgs& a, int v, bool live, RowRef x, RowRef ratio,
+                                 uint32_t out_addr)
+{
+  if (!live) return;
+  float omega = u2f(a.state[(size_t)nd.st_off * a.V + v]), x1v = u2f(a.state[(size_t)(nd.st_off + 1) * a.V + v]);
+  float dydt = 0.f;
+  const bool running = tempo_lock_prepare<EX>(x.get(0), x.get(1), ratio.get(0), a.coef[(size_t)nd.co_off * a.V + v],
+                                              omega, x1v, dydt);
+#pragma unroll 1
+  for (int q = 0; q < 16; ++q)
+  {
+    float y[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+    {
+      y[j] = running ? omega : 0.f;
+      if (running)
+      {
+        omega = A<EX>::add(omega, dydt);
+        if (omega > 1.0f) omega = A<EX>::sub(omega, 1.0f);
+      }
+    }
+    sts128(out_addr + (uint32_t)q * 16u, make_float4(y[0], y[1], y[2], y[3]));
+  }
+  a.state[(size_t)nd.st_off * a.V + v] = f2u(omega);
+  a.state[(size_t)(nd.st_off + 1) * a.V + v] = f2u(x1v);
+}
+
 // FDN<8>::operator() for one voice per lane (reference F:1195-1238); rings in HBM.
 template <bool EX>
 MLB_DEV void run_fdn8_node(const GNode& nd, const GenericArgs& a, int v, bool live, int t, RowRef x,
@@ -788,7 +866,13 @@ __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
       switch (nd.op)
       {
         case MLB_OP_PARAM:
-        case MLB_OP_FDN8_R: break;  // PARAM is an operand kind; FDN8_R aliases FDN8's 2nd slot
+        case MLB_OP_HALFBAND_UP_2:
+        case MLB_OP_FDN8_R: break;  // PARAM is an operand kind; FDN8_R / HALFBAND_UP_2 alias their producer's 2nd slot
+        case MLB_OP_HALFBAND_UP:
+          run_halfband_up_node<EX>(nd, a, v, live, r[0], o, rows + (uint32_t)nd.out_slot2 * kSlotBytes);
+          break;
+        case MLB_OP_HALFBAND_DOWN: run_halfband_down_node<EX>(nd, a, v, live, r[0], r[1], o); break;
+        case MLB_OP_TEMPO_LOCK: run_tempo_lock_node<EX>(nd, a, v, live, r[0], r[1], o); break;
         case MLB_OP_IMPORT_ROW:
         {
           const float4* src = reinterpret_cast<const float4*>(

@@ -115,6 +115,8 @@ extern "C" int mlb_graph_layout(const mlb_node* nodes, int n_nodes, mlb_layout* 
     }
     if (nodes[i].op == MLB_OP_FDN8_R && nodes[nodes[i].in[0]].op != MLB_OP_FDN8)
       return fail(MLB_ERR_INVALID, "node %d: FDN8_R must read an FDN8 node", i);
+    if (nodes[i].op == MLB_OP_HALFBAND_UP_2 && nodes[nodes[i].in[0]].op != MLB_OP_HALFBAND_UP)
+      return fail(MLB_ERR_INVALID, "node %d: HALFBAND_UP_2 must read a HALFBAND_UP node", i);
     if (nodes[i].op == MLB_OP_FDN8) ++n_fdn;
     if (nodes[i].op == MLB_OP_FEEDBACK_WRITE)
     {
@@ -613,11 +615,14 @@ static bool match_fused_chain(mlb_graph* g)
 }
 
 static int env_int(const char* name, int dflt);
+// ops with two output rows (the second is read through the paired *_R / *_2 op)
+static bool is_dual(int op) { return op == MLB_OP_FDN8 || op == MLB_OP_HALFBAND_UP; }
+static bool is_second(int op) { return op == MLB_OP_FDN8_R || op == MLB_OP_HALFBAND_UP_2; }
 
 // Relative cost of one node-block in the interpreter (used only to balance pipeline stages).
 static int node_cost(int op)
 {
-  if (op == MLB_OP_PARAM || op == MLB_OP_INPUT || op == MLB_OP_FDN8_R) return 0;
+  if (op == MLB_OP_PARAM || op == MLB_OP_INPUT || op == MLB_OP_FDN8_R || op == MLB_OP_HALFBAND_UP_2) return 0;
   if (op >= MLB_OP_MAP_FIRST && op < MLB_OP_MAP_END) return 2;
   switch (op)
   {
@@ -680,7 +685,6 @@ static int build_generic(mlb_graph* g)
     S = std::min(S, 64);
     S = env_int("MLB_STAGES", S);
     S = std::min(std::max(S, 1), std::max(1, n_real));
-    if (g->fdn_node >= 0) S = 1;  // FDN8_R aliases the second row of its FDN8: keep them together
     if (g->flags & MLB_GRAPH_SINGLE_STAGE) S = 1;
   }
   // ---- cut points: stage_of[i], contiguous, balanced by cost ----
@@ -688,8 +692,12 @@ static int build_generic(mlb_graph* g)
   // block t+1 would otherwise wait for a CTA with a LARGER ticket, which need not be resident.
   std::vector<char> no_cut(n, 0);
   for (int q = 0; q < n; ++q)
+  {
     if (N[q].op == MLB_OP_FEEDBACK_WRITE)
       for (int i = N[q].iarg; i < q; ++i) no_cut[i] = 1;
+    if (is_second(N[q].op))  // FDN8_R / HALFBAND_UP_2 alias the second row of their producer: same stage
+      for (int i = N[q].in[0]; i < q; ++i) no_cut[i] = 1;
+  }
   std::vector<int> stage_of(n, 0);
   {
     long long acc = 0;
@@ -834,11 +842,11 @@ static int build_generic(mlb_graph* g)
             gn.in_kind[k] = OPERAND_SLOT, gn.in_ref[k] = slot[local_of(src)];
         }
         // allocate the output slot BEFORE freeing inputs: nodes never run in place
-        if (N[node].op == MLB_OP_FDN8_R)
+        if (is_second(N[node].op))
           slot[li] = slot2[local_of(N[node].in[0])];
         else if (N[node].op != MLB_OP_PARAM)
           slot[li] = alloc();
-        if (N[node].op == MLB_OP_FDN8) slot2[li] = alloc();
+        if (is_dual(N[node].op)) slot2[li] = alloc();
       }
       gn.out_slot = slot[li];
       gn.out_slot2 = slot2[li];
@@ -847,9 +855,9 @@ static int build_generic(mlb_graph* g)
       for (int j = 0; j < li; ++j)
       {
         const int nj = j < n_ext ? ext[j] : members[j - n_ext];
-        if (slot[j] < 0 || N[nj].op == MLB_OP_FDN8_R) continue;
+        if (slot[j] < 0 || is_second(N[nj].op)) continue;
         if (last_use[j] == li) free_slots.push_back(slot[j]);
-        if (N[nj].op == MLB_OP_FDN8 && j >= n_ext)
+        if (is_dual(N[nj].op) && j >= n_ext)
         {
           // second row is read only through FDN8_R nodes; free it when their last reader ran
           int lu = -1;
@@ -857,7 +865,7 @@ static int build_generic(mlb_graph* g)
           for (int q = j + 1; q < n_loc; ++q)
           {
             const int nq = q < n_ext ? ext[q] : members[q - n_ext];
-            if (q >= n_ext && N[nq].op == MLB_OP_FDN8_R && N[nq].in[0] == nj)
+            if (q >= n_ext && is_second(N[nq].op) && N[nq].in[0] == nj)
             {
               has_r = true;
               lu = std::max(lu, std::max(last_use[q], q));
@@ -867,7 +875,7 @@ static int build_generic(mlb_graph* g)
         }
       }
       // a row nobody in this stage reads can be recycled right after it was written out
-      if (slot[li] >= 0 && last_use[li] < 0 && !(li >= n_ext && N[node].op == MLB_OP_FDN8_R))
+      if (slot[li] >= 0 && last_use[li] < 0 && !(li >= n_ext && is_second(N[node].op)))
         free_slots.push_back(slot[li]);
     }
     st.node_end = (int)g->gnodes.size();
@@ -946,6 +954,7 @@ extern "C" int mlb_graph_create(const mlb_node* nodes, int n_nodes, const int32_
     if (nodes[i].op == MLB_OP_ADSR) word = 7, val = 4u;                   // segment{off}, F:694
     if (nodes[i].op == MLB_OP_GLIDE) word = 2, val = 0xFFFFFFFFu;         // mVectorsRemaining{-1}, G:440
     if (nodes[i].op == MLB_OP_SAMPLE_GLIDE) word = 3, val = 0xFFFFFFFFu;  // mSamplesRemaining{-1}, G:524
+    if (nodes[i].op == MLB_OP_TEMPO_LOCK) word = 0, val = 0xBF800000u;    // _omega{-1.f}, F:1481
     if (word < 0) continue;
     std::vector<uint32_t> fill(V, val);
     cudaMemcpy(g->d_state + (size_t)(so[i] + word) * V, fill.data(), V * 4, cudaMemcpyHostToDevice);

@@ -173,6 +173,8 @@ class GraphSpec:
                 st[off[i] + 2] = 0xFFFFFFFF
             elif name == "SAMPLE_GLIDE":  # mSamplesRemaining{-1}, MLDSPGens.h:524
                 st[off[i] + 3] = 0xFFFFFFFF
+            elif name == "TEMPO_LOCK":    # _omega{-1.f}, MLDSPFilters.h:1481
+                st[off[i]] = 0xBF800000
         return st
 
     def new_coefs(self, n_voices: int) -> np.ndarray:

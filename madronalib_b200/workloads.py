@@ -321,6 +321,48 @@ def functor_case(name: str, n_voices: int = 40) -> Workload:
         coef[0] = (np.float32(0.3) + np.float32(0.5) * vv / np.float32(V)).astype(np.float32)
         coef[1] = np.float32(1000)
         fn = two_planes(noise, delay_rows(64.0, 1000.0, 1.0 / 5000.0))
+    elif name in ("halfband_up", "halfband_roundtrip", "upsample2x_clip"):
+        # up: both 2x rows out; roundtrip: down(up(x)); upsample2x_clip: Upsample2xFunction with the
+        # stateless fn(v) = clamp(v * drive, -1, 1) (MLDSPFunctional.h:114-160)
+        x = g.input(0)
+        up1 = g.node("HALFBAND_UP", x)
+        up2 = g.node("HALFBAND_UP_2", up1)
+        if name == "halfband_up":
+            g.output(up1, up2)
+        elif name == "halfband_roundtrip":
+            g.output(g.node("HALFBAND_DOWN", up1, up2))
+        else:
+            drive, lo, hi = g.param(), g.param(), g.param()
+            f1 = g.node("CLAMP", g.node("MULTIPLY", up1, drive), lo, hi)
+            f2 = g.node("CLAMP", g.node("MULTIPLY", up2, drive), lo, hi)
+            g.output(g.node("HALFBAND_DOWN", f1, f2))
+        coef, state = g.new_coefs(V), g.new_state(V)
+        if name == "upsample2x_clip":
+            coef[0] = (np.float32(0.5) + vv / np.float32(V) * np.float32(3.0)).astype(np.float32)
+            coef[1], coef[2] = np.float32(-1.0), np.float32(1.0)
+        fn = noise
+    elif name == "tempo_lock":
+        # input clock phasor (PhasorGen) -> TempoLock at ratio dydx_v; a few voices start stopped (-1)
+        # plane 1 is a bit mask: all-ones rows replace the clock by -1 ("stopped", F:1503-1507) for a
+        # block now and then, so the stop and restart paths run too
+        f, mask = g.input(0), g.input(1)
+        ph = g.node("PHASOR", f)
+        ratio, minus_one = g.param(), g.param()
+        clock = g.node("SELECT", minus_one, ph, mask)
+        tl = g.node("TEMPO_LOCK", clock, ratio)
+        g.output(tl)
+        coef, state = g.new_coefs(V), g.new_state(V)
+        ratios = np.array([1.0, 2.0, 0.5, 3.0, 1.5, 0.25, 4.0, 0.3337], np.float32)
+        coef[g.coef_slot(ratio)] = ratios[np.arange(V) % 8]
+        coef[g.coef_slot(minus_one)] = np.float32(-1.0)
+        coef[g.coef_slot(tl)] = np.float32(1.0 / SR)
+
+        def fn(T, t0):
+            out = np.zeros((T, 2, V, BLOCK), np.float32)
+            out[:, 0] = ((2.0 + vv) / np.float32(3000.0)).astype(np.float32)[None, :, None]
+            stop = ((np.arange(T)[:, None] + t0 + np.arange(V)[None, :]) % 9) == 4
+            out[:, 1].view(np.uint32)[stop] = 0xFFFFFFFF
+            return out
     elif name == "feedback":
         # y = x + 0.5 * y[previous block]: a 64-sample comb through the feedback edge
         x = g.input(0)
@@ -341,7 +383,8 @@ def functor_case(name: str, n_voices: int = 40) -> Workload:
 
 FUNCTOR_CASES = ("oneshot", "peak", "rms", "adsr", "allpass1", "glide", "interpolator1", "sample_glide",
                  "integer_delay", "integer_delay_var", "fractional_delay", "fractional_delay_var",
-                 "pitchbend_delay", "allpass_int", "allpass_frac", "allpass_pb", "feedback")
+                 "pitchbend_delay", "allpass_int", "allpass_frac", "allpass_pb", "feedback",
+                 "halfband_up", "halfband_roundtrip", "upsample2x_clip", "tempo_lock")
 
 
 def aaltoverb_feedback(size_u: float, decay_u: float) -> float:

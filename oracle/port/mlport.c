@@ -1005,6 +1005,130 @@ static void allpass_pre(const delay_mem* m, float gain, const float* x, float* d
   }
 }
 
+/* ---- HalfBandFilter, F:1245-1310 ---- */
+/* st: apa0{x1,y1} apa1{x1,y1} apb0{x1,y1} apb1{x1,y1} b1.  Coefficients F:1305-1306 (float-converted). */
+static const float kHbA0 = 0.07986642623635751f, kHbA1 = 0.5453536510711322f;
+static const float kHbB0 = 0.28382934487410993f, kHbB1 = 0.8344118914807379f;
+typedef struct hb_state
+{
+  float s[9];
+} hb_state;
+static void hb_load(hb_state* h, const uint32_t* st)
+{
+  for (int i = 0; i < 9; ++i) h->s[i] = u2f(st[i]);
+}
+static void hb_store(const hb_state* h, uint32_t* st)
+{
+  for (int i = 0; i < 9; ++i) st[i] = f2u(h->s[i]);
+}
+static inline float hb_a(hb_state* h, float x) /* apa1(apa0(x)) */
+{
+  return allpass1_tick(&h->s[2], &h->s[3], kHbA1, allpass1_tick(&h->s[0], &h->s[1], kHbA0, x));
+}
+static inline float hb_b(hb_state* h, float x) /* apb1(apb0(x)) */
+{
+  return allpass1_tick(&h->s[6], &h->s[7], kHbB1, allpass1_tick(&h->s[4], &h->s[5], kHbB0, x));
+}
+/* upsampleFirstHalf then upsampleSecondHalf, F:1248-1270 */
+static void hb_upsample(uint32_t* st, const float* x, float* y1, float* y2)
+{
+  hb_state h;
+  hb_load(&h, st);
+  for (int i = 0; i < NB / 2; ++i)
+  {
+    y1[2 * i] = hb_a(&h, x[i]);
+    y1[2 * i + 1] = hb_b(&h, x[i]);
+  }
+  for (int i = NB / 2; i < NB; ++i)
+  {
+    y2[2 * (i - NB / 2)] = hb_a(&h, x[i]);
+    y2[2 * (i - NB / 2) + 1] = hb_b(&h, x[i]);
+  }
+  hb_store(&h, st);
+}
+/* downsample(vx1, vx2), F:1272-1294 */
+static void hb_downsample(uint32_t* st, const float* x1, const float* x2, float* y)
+{
+  hb_state h;
+  hb_load(&h, st);
+  for (int half = 0; half < 2; ++half)
+  {
+    const float* x = half ? x2 : x1;
+    for (int i = 0; i < NB / 2; ++i)
+    {
+      float a0 = hb_a(&h, x[2 * i]);
+      float b0 = hb_b(&h, x[2 * i + 1]);
+      y[half * (NB / 2) + i] = (a0 + h.s[8]) * 0.5f;
+      h.s[8] = b0;
+    }
+  }
+  hb_store(&h, st);
+}
+
+/* TempoLock::operator(), F:1494-1578.  st: _omega, _x1v; dydx = ratio; isr = coef */
+static void gen_tempo_lock(uint32_t* st, const float* x, float dydx, float isr, float* y)
+{
+  float omega = u2f(st[0]), x1v = u2f(st[1]);
+  const float x0 = x[0];
+  float dxdt = 0.f, dydt = 0.f;
+  if (x0 == -1.0f)
+  {
+    omega = -1.0f;
+    for (int i = 0; i < NB; ++i) y[i] = 0.f;
+  }
+  else
+  {
+    if (omega > -1.f)
+    {
+      float dx = x0 - x1v;
+      if (dx < 0.f) dx += 1.f;
+      dxdt = dx / (float)NB;
+      dydt = dxdt * dydx;
+      x1v = x0;
+    }
+    else
+    {
+      dxdt = x[1] - x0;
+      dydt = dxdt * dydx;
+      x1v = x0 - dxdt * (float)NB;
+      omega = fmodf(x0 * dydx, 1.0f);
+    }
+    int lock = 0;
+    const float lockDist = 0.001f;
+    if (fabsf(dydx - roundf(dydx)) < lockDist) lock = 1;
+    float rdydx = 1.0f / dydx;
+    if (fabsf(rdydx - roundf(rdydx)) < lockDist) lock = 1;
+    if (lock)
+    {
+      float ref, refWrap, error;
+      if (dydx >= 1.f)
+      {
+        ref = x0 * dydx;
+        refWrap = ref - floorf(ref);
+        error = omega - refWrap;
+      }
+      else
+      {
+        ref = omega / dydx;
+        refWrap = ref - floorf(ref);
+        error = refWrap - x0;
+      }
+      float errorDiff = roundf(error) - error;
+      float correction = errorDiff * isr * 4.0f;
+      const float lo = -dydt * 0.5f, hi = dydt * 1.0f;
+      correction = (correction < lo) ? lo : (correction > hi ? hi : correction); /* ml::clamp, S:68-72 */
+      dydt += correction;
+    }
+    for (int i = 0; i < NB; ++i)
+    {
+      y[i] = omega;
+      omega += dydt;
+      if (omega > 1.0f) omega -= 1.0f;
+    }
+  }
+  st[0] = f2u(omega), st[1] = f2u(x1v);
+}
+
 /* ------------------------------------------------------------------ */
 /* graph runner                                                         */
 
@@ -1099,6 +1223,12 @@ mlport_graph* mlport_graph_create(const mlb_node* nodes, int n_nodes, const int3
     g->n_state += b;
     g->n_coef += c;
     if (nodes[i].op == MLB_OP_INPUT && nodes[i].iarg + 1 > g->n_in) g->n_in = nodes[i].iarg + 1;
+    if ((nodes[i].op == MLB_OP_HALFBAND_UP_2 && nodes[nodes[i].in[0]].op != MLB_OP_HALFBAND_UP) ||
+        (nodes[i].op == MLB_OP_FDN8_R && nodes[nodes[i].in[0]].op != MLB_OP_FDN8))
+    {
+      mlport_graph_destroy(g);
+      return NULL;
+    }
     if (nodes[i].op == MLB_OP_FEEDBACK_WRITE &&
         (nodes[i].iarg < 0 || nodes[i].iarg >= i || nodes[nodes[i].iarg].op != MLB_OP_FEEDBACK_READ))
     {
@@ -1290,6 +1420,10 @@ static void run_voices(mlport_graph* g, const float* in, float* out, int T, int 
             delay_pitchbend(m, st, din, dl, m->row);
             break;
           }
+          case MLB_OP_HALFBAND_UP: hb_upsample(st, a, y, rows2[i]); break;
+          case MLB_OP_HALFBAND_UP_2: memcpy(y, rows2[nd->in[0]], sizeof(float) * NB); break;
+          case MLB_OP_HALFBAND_DOWN: hb_downsample(st, a, b, y); break;
+          case MLB_OP_TEMPO_LOCK: gen_tempo_lock(st, a, b[0], co[0], y); break;
           case MLB_OP_FEEDBACK_READ: memcpy(y, g->dmem[i][v].row, sizeof(float) * NB); break;
           case MLB_OP_FEEDBACK_WRITE:
             memcpy(g->dmem[nd->iarg][v].row, a, sizeof(float) * NB);

@@ -460,6 +460,47 @@ struct PAllpassPB : Proc
   void storeState(uint32_t* s) const override { pbStore(f.mDelay, s); }
   DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0], *in[1]); }
 };
+// HalfBandFilter (F:1245-1310): the four Allpass1 sections and b1
+inline void hbLoad(HalfBandFilter& f, const uint32_t* s)
+{
+  Allpass1* ap[4] = {&f.apa0, &f.apa1, &f.apb0, &f.apb1};
+  for (int i = 0; i < 4; ++i) ap[i]->x1 = u2f(s[2 * i]), ap[i]->y1 = u2f(s[2 * i + 1]);
+  f.b1 = u2f(s[8]);
+}
+inline void hbStore(const HalfBandFilter& f, uint32_t* s)
+{
+  const Allpass1* ap[4] = {&f.apa0, &f.apa1, &f.apb0, &f.apb1};
+  for (int i = 0; i < 4; ++i) s[2 * i] = f2u(ap[i]->x1), s[2 * i + 1] = f2u(ap[i]->y1);
+  s[8] = f2u(f.b1);
+}
+struct PHalfBandUp : Proc
+{
+  HalfBandFilter f;
+  void loadState(const uint32_t* s) override { hbLoad(f, s); }
+  void storeState(uint32_t* s) const override { hbStore(f, s); }
+  DSPVector run(const DSPVector* const* in, DSPVector* out2) override
+  {
+    DSPVector a = f.upsampleFirstHalf(*in[0]);
+    *out2 = f.upsampleSecondHalf(*in[0]);
+    return a;
+  }
+};
+struct PHalfBandDown : Proc
+{
+  HalfBandFilter f;
+  void loadState(const uint32_t* s) override { hbLoad(f, s); }
+  void storeState(uint32_t* s) const override { hbStore(f, s); }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f.downsample(*in[0], *in[1]); }
+};
+struct PTempoLock : Proc
+{
+  TempoLock f;
+  float isr{0};
+  void setCoefs(const float* c) override { isr = c[0]; }
+  void loadState(const uint32_t* s) override { f._omega = u2f(s[0]), f._x1v = u2f(s[1]); }
+  void storeState(uint32_t* s) const override { s[0] = f2u(f._omega), s[1] = f2u(f._x1v); }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0], (*in[1])[0], isr); }
+};
 // a DSPVector member kept between processVector calls (reverb.cpp:34,115-116)
 struct PFeedback : Proc
 {
@@ -575,8 +616,12 @@ Proc* makeProc(int op)
     case MLB_OP_ALLPASS_FRAC: return new PAllpassFrac;
     case MLB_OP_ALLPASS_PB: return new PAllpassPB;
     case MLB_OP_FEEDBACK_READ: return new PFeedback;
+    case MLB_OP_HALFBAND_UP: return new PHalfBandUp;
+    case MLB_OP_HALFBAND_DOWN: return new PHalfBandDown;
+    case MLB_OP_TEMPO_LOCK: return new PTempoLock;
     case MLB_OP_INPUT:
     case MLB_OP_FEEDBACK_WRITE:
+    case MLB_OP_HALFBAND_UP_2:
     case MLB_OP_FDN8_R: return nullptr;
     default: return new PStateless(op);
   }
@@ -724,7 +769,7 @@ void mlref_graph_process(mlref_graph* h, const float* in, float* out, float* mix
             rows[i] = DSPVector(in + (((size_t)t * g.nIn + nd.iarg) * V + v) * 64);
             continue;
           }
-          if (nd.op == MLB_OP_FDN8_R)
+          if (nd.op == MLB_OP_FDN8_R || nd.op == MLB_OP_HALFBAND_UP_2)
           {
             rows[i] = rows2[nd.in[0]];
             continue;
@@ -973,5 +1018,20 @@ double mlref_aaltoverb(int T, const float* in, float* out, float sizeU2, float f
       store(vTapR, out + (size_t)t * 128 + 64);
     }
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ---- Upsample2xFunction<1> (MLDSPFunctional.h:114-160) called as a user would, with the stateless
+// process function fn(v) = clamp(v * drive, -1, 1).  One voice; in/out [T][64].  Checks that the
+// HALFBAND_UP / HALFBAND_UP_2 / HALFBAND_DOWN graph of workloads.functor_case("upsample2x_clip") is
+// that higher-order function.
+void mlref_upsample2x_clip(int T, const float* in, float* out, float drive)
+{
+  Upsample2xFunction<1> upper;
+  for (int t = 0; t < T; ++t)
+  {
+    DSPVector x(in + (size_t)t * 64);
+    DSPVector y = upper([&](const DSPVector v) { return clamp(v * DSPVector(drive), DSPVector(-1.f), DSPVector(1.f)); }, x);
+    store(y, out + (size_t)t * 64);
+  }
 }
 }  // extern "C"

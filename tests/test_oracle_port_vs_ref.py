@@ -94,3 +94,15 @@ def test_aaltoverb_graph_is_the_example(ref, port):
         o, _ = ref.aaltoverb(inp[:, :, v, :], size2, fb, 4800.0)
         assert np.array_equal(o.view(np.uint32), a[:, :, v, :].view(np.uint32))
     assert np.sqrt((a[-10:] ** 2).mean()) > 1e-3  # the tail is ringing, not silent
+
+
+def test_upsample2x_graph_is_the_higher_order_function(ref):
+    """HALFBAND_DOWN(fn(HALFBAND_UP(x)), fn(HALFBAND_UP_2(x))) == the reference's Upsample2xFunction<1>
+    (MLDSPFunctional.h:114-160) called directly with fn(v) = clamp(v * drive, -1, 1)."""
+    w = wl.functor_case("upsample2x_clip", 12)
+    T = 20
+    inp = w.inputs(T)
+    a, _, _ = ref.run(w.spec, 12, T, inp, w.state, w.coef)
+    for v in (0, 7, 11):
+        o = ref.upsample2x_clip(inp[:, 0, v, :], float(w.coef[0, v]))
+        assert np.array_equal(o.view(np.uint32), a[:, 0, v, :].view(np.uint32))
