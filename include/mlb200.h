@@ -291,6 +291,53 @@ const char* mlb_last_error(void);  /* thread-local message of the last failing c
 int mlb_abi_version(void);
 long long mlb_kernel_launches(void); /* count of kernels this library launched (process-wide) */
 
+/* ---- EventsToSignals::Voice bank ---------------------------------------
+ * The step BEFORE the chain: the reference's EventsToSignals (source/app/MLEventsToSignals.h:43-236)
+ * turns note / controller events into 8 control rows per voice.  Its event routing (voice
+ * allocation, stealing, unison, MPE: MLEventsToSignals.cpp:476-960) is host-side control logic and
+ * stays with the caller; what is built here is the per-voice signal generator
+ * EventsToSignals::Voice (beginProcess / writeNoteEvent / endProcess, .cpp:97-263) for V voices at
+ * once: sample-accurate gate and pitch (SampleAccurateLinearGlide), vector-accurate bend / mod /
+ * x / y / z / drift glides (LinearGlide), elapsed time, pitch drift (RandomScalarSource).
+ * Per voice and block the caller hands over one 72-byte record instead of 256-byte rows. */
+#define MLB_VOICE_ROWS 8          /* kPitch, kGate, kVoice, kZ, kX, kY, kMod, kElapsedTime (.h:16-27) */
+#define MLB_VOICE_MAX_EVENTS 4    /* note events one voice can take per 64-frame vector */
+enum {                            /* = ml::EventType (source/app/MLEvent.h:14-27) */
+  MLB_EV_NULL = 0, MLB_EV_NOTE_ON = 1, MLB_EV_NOTE_RETRIG = 2, MLB_EV_NOTE_SUSTAIN = 3, MLB_EV_NOTE_OFF = 4
+};
+enum { MLB_EVF_GLIDE = 1, MLB_EVF_RESET = 2 };                  /* writeNoteEvent(e, key, doGlide, doReset) */
+enum { MLB_SET_BEND = 1, MLB_SET_MOD = 2, MLB_SET_X = 4, MLB_SET_Y = 8, MLB_SET_Z = 16 };
+typedef struct mlb_voice_events {  /* what ONE Voice receives during ONE vector */
+  uint8_t n_events;                          /* <= MLB_VOICE_MAX_EVENTS, in time order */
+  uint8_t set_mask;                          /* which of bend/mod/x/y/z were written this vector */
+  uint8_t pad[2];
+  uint8_t time[MLB_VOICE_MAX_EVENTS];        /* Event::time, frame offset in the vector (clamped to 64) */
+  uint8_t type[MLB_VOICE_MAX_EVENTS];        /* MLB_EV_* */
+  uint8_t flags[MLB_VOICE_MAX_EVENTS];       /* MLB_EVF_* */
+  float value1[MLB_VOICE_MAX_EVENTS];        /* Event::value1 = pitch */
+  float value2[MLB_VOICE_MAX_EVENTS];        /* Event::value2 = velocity */
+  float bend, mod, x, y, z;                  /* currentPitchBend, currentMod, currentX/Y/Z when set */
+} mlb_voice_events;                          /* 68 bytes */
+
+typedef struct mlb_voices mlb_voices;  /* opaque: V Voice objects on the device */
+
+/* V voices after Voice() + reset() + setSampleRate(sr) + setPitchGlideInSeconds + setDriftAmount
+ * (.cpp:47-95).  voice_index[v] = Voice::voiceIndex (seeds the drift source with index * 232 and
+ * gives the kVoice row = index - 1, .cpp:61,292); pitch_bend[v] = the semitone range handed to
+ * endProcess (.cpp:422-428).  Arrays are per voice, host memory. */
+int mlb_voices_create(int n_voices, float sample_rate, const int32_t* voice_index, const float* pitch_glide_seconds,
+                      const float* drift_amount, const float* pitch_bend, mlb_voices** out);
+int mlb_voices_destroy(mlb_voices* vb);
+/* n_blocks vectors: beginProcess, the block's events, endProcess, for every voice.
+ * events_host [n_blocks][V]; out_host [n_blocks][MLB_VOICE_ROWS][V][64] (rows whose bit is clear in
+ * row_mask are not written; bit r = row r).  One kernel launch. */
+int mlb_voices_process_host(mlb_voices* vb, const mlb_voice_events* events_host, float* out_host,
+                            int n_blocks, unsigned row_mask);
+/* same with device-resident buffers, asynchronous on `stream`; the out planes have the layout of
+ * graph inputs, so they can be handed to mlb_graph_process_device as-is. */
+int mlb_voices_process_device(mlb_voices* vb, const mlb_voice_events* events_dev, float* out_dev,
+                              int n_blocks, unsigned row_mask, void* stream);
+
 /* ---- stateless elementwise ops on device or host buffers (K3) ----
  * y[i] = op(x1[i], x2[i], x3[i]) for n_rows*64 elements; unused inputs NULL.
  * Stands in for every DEFINE_OP* function of MLDSPOps.h:567-918 applied to a

@@ -430,3 +430,59 @@ def config_6(n_voices: int = 4096) -> Workload:
         return (x * on).astype(np.float32)
     w.inputs = _rows_inputs(fn)  # type: ignore[assignment]
     return w
+
+
+# ---- per-voice event records for the EventsToSignals::Voice bank ----
+
+VOICE_EVENTS_DTYPE = np.dtype([("n_events", "u1"), ("set_mask", "u1"), ("pad", "u1", (2,)),
+                               ("time", "u1", (4,)), ("type", "u1", (4,)), ("flags", "u1", (4,)),
+                               ("value1", "f4", (4,)), ("value2", "f4", (4,)),
+                               ("bend", "f4"), ("mod", "f4"), ("x", "f4"), ("y", "f4"), ("z", "f4")])
+assert VOICE_EVENTS_DTYPE.itemsize == 68  # struct mlb_voice_events (include/mlb200.h)
+
+EV_NOTE_ON, EV_NOTE_RETRIG, EV_NOTE_SUSTAIN, EV_NOTE_OFF = 1, 2, 3, 4
+EVF_GLIDE, EVF_RESET = 1, 2
+
+
+def voice_bank_params(n_voices: int):
+    """voice_index, pitch_glide_seconds, drift_amount, pitch_bend (semitones) per voice."""
+    v = np.arange(n_voices)
+    return ((v % 16 + 1).astype(np.int32), (np.float32(0.0) + np.float32(0.01) * (v % 7)).astype(np.float32),
+            (np.float32(0.25) * (v % 5)).astype(np.float32), np.where(v % 3 == 0, 24.0, 7.0).astype(np.float32))
+
+
+def voice_events(n_voices: int, n_blocks: int, seed: int = 1, density: float = 0.35) -> np.ndarray:
+    """A seeded performance: [T][V] records.  Each voice plays notes (on / retrigger / off, with and
+    without glide and age reset, sometimes several per vector, sometimes two at the same frame) while
+    bend / mod / x / y / z move now and then."""
+    rng = np.random.default_rng(seed)
+    ev = np.zeros((n_blocks, n_voices), VOICE_EVENTS_DTYPE)
+    held = np.zeros(n_voices, bool)
+    for t in range(n_blocks):
+        for v in range(n_voices):
+            r = ev[t, v]
+            if rng.random() < density:
+                n = int(rng.integers(1, 5))
+                times = np.sort(rng.integers(0, 65, n))  # 64 = "end of vector", clamped by the voice
+                if rng.random() < 0.2 and n > 1:
+                    times[1] = times[0]
+                for k in range(n):
+                    if held[v] and rng.random() < 0.5:
+                        typ = EV_NOTE_OFF
+                    else:
+                        typ = EV_NOTE_ON if rng.random() < 0.7 else EV_NOTE_RETRIG
+                    if rng.random() < 0.05:
+                        typ = EV_NOTE_SUSTAIN  # ignored by the voice
+                    held[v] = typ in (EV_NOTE_ON, EV_NOTE_RETRIG) or (held[v] and typ == EV_NOTE_SUSTAIN)
+                    r["time"][k] = times[k]
+                    r["type"][k] = typ
+                    r["flags"][k] = int(rng.integers(0, 4))
+                    r["value1"][k] = np.float32(rng.integers(36, 96)) / np.float32(12.0)
+                    r["value2"][k] = np.float32(rng.random() * 0.9 + 0.1)
+                r["n_events"] = n
+            if rng.random() < 0.3:
+                m = int(rng.integers(1, 32))
+                r["set_mask"] = m
+                r["bend"], r["mod"] = np.float32(rng.random() * 2 - 1), np.float32(rng.random())
+                r["x"], r["y"], r["z"] = np.float32(rng.random()), np.float32(rng.random()), np.float32(rng.random())
+    return ev

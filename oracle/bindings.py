@@ -20,6 +20,7 @@ from madronalib_b200.graph import BLOCK, GraphSpec
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_LIB = os.path.join(_HERE, "_ref", "libmlref.so")
+E2S_LIB = os.path.join(_HERE, "_ref", "libmle2s.so")
 PORT_LIB = os.path.join(_HERE, "_port", "libmlport.so")
 
 _vp = ctypes.c_void_p
@@ -195,3 +196,45 @@ class PortOracle(_Oracle):
 
     def _process(self, h, inp, out, mix, T, nthreads, mix_mode, n_shards):
         self.lib.mlport_graph_process(h, inp, out, mix, T, nthreads, mix_mode, n_shards)
+
+
+class _VoiceBank:
+    """EventsToSignals::Voice x V (SURVEY 8f row 3).  prefix/lib as for the graph oracles."""
+
+    def __init__(self, lib, prefix):
+        self.lib, self.p = lib, prefix
+        getattr(lib, prefix + "bank_create").restype = _vp
+        getattr(lib, prefix + "bank_create").argtypes = [ctypes.c_int, ctypes.c_float, _vp, _vp, _vp, _vp]
+        getattr(lib, prefix + "bank_destroy").argtypes = [_vp]
+        getattr(lib, prefix + "bank_process").restype = ctypes.c_double
+        getattr(lib, prefix + "bank_process").argtypes = [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int]
+
+    def run(self, sr, voice_index, glide_seconds, drift_amount, pitch_bend, events, splits=None, nthreads=1):
+        """events [T][V] records -> (out [T][8][V][64], seconds)."""
+        T, V = events.shape
+        vi = np.ascontiguousarray(voice_index, np.int32)
+        gs, da, pb = (np.ascontiguousarray(a, np.float32) for a in (glide_seconds, drift_amount, pitch_bend))
+        h = getattr(self.lib, self.p + "bank_create")(V, sr, _ptr(vi), _ptr(gs), _ptr(da), _ptr(pb))
+        out = np.zeros((T, 8, V, BLOCK), np.float32)
+        sec, t0 = 0.0, 0
+        try:
+            for n in (splits or (T,)):
+                e = np.ascontiguousarray(events[t0:t0 + n])
+                sec += getattr(self.lib, self.p + "bank_process")(h, n, _ptr(e), _ptr(out[t0:t0 + n]), nthreads)
+                t0 += n
+        finally:
+            getattr(self.lib, self.p + "bank_destroy")(h)
+        return out, float(sec)
+
+
+def ref_voice_bank() -> _VoiceBank:
+    """The reference's own EventsToSignals::Voice, compiled in place (oracle/_ref/libmle2s.so)."""
+    if not os.path.exists(E2S_LIB):
+        raise FileNotFoundError(E2S_LIB + " not built; run `make -C oracle ref`")
+    return _VoiceBank(ctypes.CDLL(E2S_LIB), "mle2s_")
+
+
+def port_voice_bank() -> _VoiceBank:
+    if not os.path.exists(PORT_LIB):
+        build("port")
+    return _VoiceBank(ctypes.CDLL(PORT_LIB), "mlport_")

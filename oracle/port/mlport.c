@@ -1634,3 +1634,256 @@ void mlport_coeffs_sample_glide(float t, float* o) /* G:527-532 */
   o[0] = (float)n;
   o[1] = 1.0f / (float)n;
 }
+
+/* ------------------------------------------------------------------ */
+/* EventsToSignals::Voice (source/app/MLEventsToSignals.{h,cpp}; E = the .cpp) */
+
+typedef struct lin_glide /* LinearGlide, G:433-515 */
+{
+  float curr[NB];
+  uint32_t st[3]; /* step, target, vectorsRemaining */
+  float c[2];     /* vectorsPerGlide, dyPerVector */
+} lin_glide;
+
+static void lin_glide_init(lin_glide* g) /* member defaults G:435-440 */
+{
+  memset(g, 0, sizeof(*g));
+  g->st[2] = (uint32_t)-1;
+  g->c[0] = 32.f;
+  g->c[1] = 1.f / 32;
+}
+static void lin_glide_set_value(lin_glide* g, float f) /* G:451-455 */
+{
+  g->st[1] = f2u(f);
+  g->st[2] = 0;
+}
+
+enum { GL_BEND = 0, GL_MOD, GL_X, GL_Y, GL_Z, GL_DRIFT, GL_COUNT };
+enum { ROW_PITCH = 0, ROW_GATE, ROW_VOICE, ROW_Z, ROW_X, ROW_Y, ROW_MOD, ROW_TIME }; /* .h:16-27 */
+
+typedef struct port_voice
+{
+  /* pitchGlide: SampleAccurateLinearGlide, G:517-590 */
+  uint32_t pg[4]; /* curr, step, target, samplesRemaining */
+  float pgc[2];   /* samplesPerGlide, dyPerSample */
+  lin_glide g[GL_COUNT];
+  float vel, pitch, bend, mod, x, y, z;
+  uint32_t age, ageStep;
+  int nextFrame;
+  uint32_t seed;
+  int driftCounter, nextDriftTime;
+  float curDrift, driftAmount;
+  double sr;
+  float glideSeconds;
+  int pitchGlideTimeInSamples;
+  int inhibit, recalc, voiceIndex;
+  float pitchBendRange;
+  float out[8][NB];
+} port_voice;
+
+static void sa_glide_set_time(port_voice* v, float t) /* G:527-532 */
+{
+  int n = (int)t;
+  if (n < 1) n = 1;
+  v->pgc[0] = (float)n;
+  v->pgc[1] = 1.0f / n;
+}
+static float drift_float(uint32_t* seed) /* RandomScalarSource::getFloat, S:189-202 */
+{
+  *seed = *seed * 0x0019660Du + 0x3C6EF35Fu;
+  uint32_t temp = ((*seed >> 9) & 0x007FFFFFu) | 0x3F800000u;
+  float f = u2f(temp);
+  f *= 2.f;
+  f -= 3.f;
+  return f;
+}
+/* SampleAccurateLinearGlide::nextSample for one sample */
+static float sa_glide_next(port_voice* v, float x)
+{
+  float y;
+
+  {
+    float curr = u2f(v->pg[0]), step = u2f(v->pg[1]), target = u2f(v->pg[2]);
+    int32_t remaining = (int32_t)v->pg[3];
+    const int32_t per = (int32_t)v->pgc[0];
+    if (x != target)
+    {
+      target = x;
+      remaining = per;
+    }
+    if (remaining < 0)
+    {
+    }
+    else if (remaining == 0)
+    {
+      curr = target;
+      step = 0.f;
+      remaining--;
+    }
+    else if (remaining == per)
+    {
+      step = (target - curr) * v->pgc[1];
+      remaining--;
+    }
+    else
+    {
+      curr += step;
+      remaining--;
+    }
+    v->pg[0] = f2u(curr), v->pg[1] = f2u(step), v->pg[2] = f2u(target), v->pg[3] = (uint32_t)remaining;
+    y = curr;
+  }
+  return y;
+}
+/* one output frame: E:134-140 / 185-189 / 225-236 */
+static void voice_frame(port_voice* v, int t, float gate)
+{
+  v->out[ROW_GATE][t] = gate;
+  v->out[ROW_PITCH][t] = sa_glide_next(v, v->pitch);
+  v->age += v->ageStep;
+  v->out[ROW_TIME][t] = (float)((double)v->age / (double)(float)v->sr); /* samplesToSeconds, E:12-18 */
+}
+static void voice_write_frames(port_voice* v, int endFrame) /* E:129-142 */
+{
+  for (int t = v->nextFrame; t < endFrame; ++t) voice_frame(v, t, v->vel);
+  v->nextFrame = endFrame;
+}
+
+static void voice_init(port_voice* v, int voiceIndex, float sr, float glideSeconds, float driftAmount, float bendRange)
+{
+  memset(v, 0, sizeof(*v));
+  v->pg[3] = (uint32_t)-1; /* G:520-525 */
+  v->pgc[0] = 32.f, v->pgc[1] = 1.f / 32;
+  for (int i = 0; i < GL_COUNT; ++i) lin_glide_init(&v->g[i]);
+  v->voiceIndex = voiceIndex;
+  /* reset(), E:60-85 */
+  v->seed = (uint32_t)(voiceIndex * 232);
+  for (int i = GL_BEND; i <= GL_Z; ++i) lin_glide_set_value(&v->g[i], 0.f);
+  for (int n = 0; n < NB; ++n) v->out[ROW_VOICE][n] = (float)voiceIndex - 1; /* E:292 */
+  v->sr = sr, v->recalc = 1; /* setSampleRate */
+  v->glideSeconds = glideSeconds;
+  v->driftAmount = driftAmount;
+  v->pitchBendRange = bendRange;
+}
+
+static void lin_glide_set_time(lin_glide* g, float t) { mlport_coeffs_glide(t, g->c); }
+
+static void voice_begin(port_voice* v) /* E:90-124 */
+{
+  if (v->recalc)
+  {
+    v->pitchGlideTimeInSamples = (int)(v->sr * v->glideSeconds);
+    if (!v->inhibit) sa_glide_set_time(v, (float)v->pitchGlideTimeInSamples);
+    for (int i = GL_BEND; i <= GL_Z; ++i) lin_glide_set_time(&v->g[i], (float)(v->sr * 0.02f));
+    lin_glide_set_time(&v->g[GL_DRIFT], (float)(v->sr * 8.0f));
+    v->recalc = 0;
+  }
+  v->nextFrame = 0;
+  v->driftCounter += NB;
+  if (v->driftCounter >= v->nextDriftTime)
+  {
+    float d = drift_float(&v->seed);
+    float nextTimeMul = 1.0f + fabsf(drift_float(&v->seed));
+    v->curDrift = d;
+    v->driftCounter = 0;
+    v->nextDriftTime = (int)(v->sr * nextTimeMul * 8.0f);
+  }
+}
+static void voice_note(port_voice* v, int type, int time, float v1, float v2, int doGlide, int doReset) /* E:126-220 */
+{
+  int destTime = time < 0 ? 0 : (time > NB ? NB : time);
+  switch (type)
+  {
+    case MLB_EV_NOTE_ON:
+      if (doReset) v->age = 0;
+      v->ageStep = 1;
+      v->inhibit = !doGlide;
+      sa_glide_set_time(v, doGlide ? (float)v->pitchGlideTimeInSamples : 0.f);
+      voice_write_frames(v, destTime);
+      v->pitch = v1;
+      v->vel = v2;
+      break;
+    case MLB_EV_NOTE_RETRIG:
+      if (doReset) v->age = 0;
+      v->ageStep = 1;
+      if (destTime == 0) destTime++;
+      voice_write_frames(v, destTime - 1);
+      voice_frame(v, destTime - 1, 0.f);
+      v->pitch = v1;
+      v->vel = v2;
+      v->nextFrame = destTime;
+      break;
+    case MLB_EV_NOTE_OFF:
+      voice_write_frames(v, destTime);
+      v->vel = 0.f;
+      break;
+    default: break;
+  }
+}
+static void voice_end(port_voice* v) /* E:222-262 */
+{
+  for (int t = v->nextFrame; t < NB; ++t) voice_frame(v, t, v->vel);
+  float bend[NB], drift[NB];
+  gen_glide(v->g[GL_BEND].st, v->g[GL_BEND].c, v->bend, v->g[GL_BEND].curr, bend);
+  gen_glide(v->g[GL_DRIFT].st, v->g[GL_DRIFT].c, v->curDrift, v->g[GL_DRIFT].curr, drift);
+  gen_glide(v->g[GL_MOD].st, v->g[GL_MOD].c, v->mod, v->g[GL_MOD].curr, v->out[ROW_MOD]);
+  gen_glide(v->g[GL_X].st, v->g[GL_X].c, v->x, v->g[GL_X].curr, v->out[ROW_X]);
+  gen_glide(v->g[GL_Y].st, v->g[GL_Y].c, v->y, v->g[GL_Y].curr, v->out[ROW_Y]);
+  if (v->vel == 0.f) v->z = 0.f;
+  gen_glide(v->g[GL_Z].st, v->g[GL_Z].c, v->z, v->g[GL_Z].curr, v->out[ROW_Z]);
+  for (int n = 0; n < NB; ++n)
+  {
+    float p = v->out[ROW_PITCH][n];
+    p = p + (bend[n] * v->pitchBendRange) * (1.f / 12);
+    p = p + (drift[n] * v->driftAmount) * 0.02f;
+    v->out[ROW_PITCH][n] = p;
+  }
+}
+
+typedef struct mlport_voice_bank
+{
+  int V;
+  port_voice* v;
+} mlport_voice_bank;
+
+mlport_voice_bank* mlport_bank_create(int V, float sr, const int32_t* voiceIndex, const float* glideSeconds,
+                                      const float* driftAmount, const float* pitchBend)
+{
+  mlport_voice_bank* b = (mlport_voice_bank*)calloc(1, sizeof(*b));
+  b->V = V;
+  b->v = (port_voice*)calloc((size_t)V, sizeof(port_voice));
+  for (int i = 0; i < V; ++i) voice_init(&b->v[i], voiceIndex[i], sr, glideSeconds[i], driftAmount[i], pitchBend[i]);
+  return b;
+}
+void mlport_bank_destroy(mlport_voice_bank* b)
+{
+  if (!b) return;
+  free(b->v);
+  free(b);
+}
+double mlport_bank_process(mlport_voice_bank* b, int T, const mlb_voice_events* ev, float* out, int nthreads)
+{
+  (void)nthreads;
+  const int V = b->V;
+  for (int i = 0; i < V; ++i)
+  {
+    port_voice* v = &b->v[i];
+    for (int t = 0; t < T; ++t)
+    {
+      const mlb_voice_events* r = &ev[(size_t)t * V + i];
+      voice_begin(v);
+      for (int k = 0; k < r->n_events; ++k)
+        voice_note(v, r->type[k], r->time[k], r->value1[k], r->value2[k], (r->flags[k] & MLB_EVF_GLIDE) != 0,
+                   (r->flags[k] & MLB_EVF_RESET) != 0);
+      if (r->set_mask & MLB_SET_BEND) v->bend = r->bend;
+      if (r->set_mask & MLB_SET_MOD) v->mod = r->mod;
+      if (r->set_mask & MLB_SET_X) v->x = r->x;
+      if (r->set_mask & MLB_SET_Y) v->y = r->y;
+      if (r->set_mask & MLB_SET_Z) v->z = r->z;
+      voice_end(v);
+      for (int row = 0; row < 8; ++row)
+        memcpy(out + (((size_t)t * 8 + row) * V + i) * NB, v->out[row], sizeof(float) * NB);
+    }
+  }
+  return 0.0;
+}
