@@ -21,6 +21,7 @@
 #include "../../include/mlb200.h"
 #include "chain_kernel.cuh"
 #include "fdn_kernel.cuh"
+#include "voice_kernel.cuh"
 #include "generic_kernel.cuh"
 
 using namespace mlb;
@@ -1587,4 +1588,146 @@ extern "C" int mlb_map_host(int op, const float* x1, const float* x2, const floa
   }
   freeall();
   return rc;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// EventsToSignals::Voice bank (K7, voice_kernel.cuh)
+
+struct mlb_voices
+{
+  int V = 0;
+  float sr = 0.f;
+  float gl_per = 0.f, gl_dy = 0.f, dr_per = 0.f, dr_dy = 0.f;
+  uint32_t* d_state = nullptr;
+  float* d_coef = nullptr;
+  float* d_grows = nullptr;
+  mlb_voice_events* d_ev = nullptr;
+  float* d_out = nullptr;
+  size_t ev_cap = 0, out_cap = 0;
+  cudaStream_t stream = nullptr;
+};
+
+extern "C" int mlb_voices_destroy(mlb_voices* vb)
+{
+  if (!vb) return MLB_OK;
+  cudaFree(vb->d_state);
+  cudaFree(vb->d_coef);
+  cudaFree(vb->d_grows);
+  cudaFree(vb->d_ev);
+  cudaFree(vb->d_out);
+  if (vb->stream) cudaStreamDestroy(vb->stream);
+  delete vb;
+  return MLB_OK;
+}
+
+extern "C" int mlb_voices_create(int n_voices, float sample_rate, const int32_t* voice_index,
+                                 const float* pitch_glide_seconds, const float* drift_amount,
+                                 const float* pitch_bend, mlb_voices** out)
+{
+  if (!out) return fail(MLB_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (n_voices <= 0 || !(sample_rate > 0.f) || !voice_index || !pitch_glide_seconds || !drift_amount || !pitch_bend)
+    return fail(MLB_ERR_INVALID, "bad argument");
+  int rc = ensure_init();
+  if (rc != MLB_OK) return rc;
+  const size_t V = (size_t)n_voices;
+  mlb_voices* vb = new mlb_voices;
+  vb->V = n_voices;
+  vb->sr = sample_rate;
+  // the recalc block of the first beginProcess (MLEventsToSignals.cpp:92-113), done once here
+  const double sr = (double)sample_rate;
+  float c[2];
+  mlb_coeffs_glide((float)(sr * 0.02f), c);  // kGlideTimeSeconds
+  vb->gl_per = c[0], vb->gl_dy = c[1];
+  mlb_coeffs_glide((float)(sr * 8.0f), c);   // kDriftTimeSeconds
+  vb->dr_per = c[0], vb->dr_dy = c[1];
+  std::vector<uint32_t> st((size_t)VS_COUNT * V, 0u);
+  std::vector<float> co((size_t)VC_COUNT * V, 0.f);
+  auto fbits = [](float f)
+  {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+  };
+  for (size_t v = 0; v < V; ++v)
+  {
+    const int glide_samples = (int)(sr * pitch_glide_seconds[v]);  // pitchGlideTimeInSamples, :97
+    float sg[2];
+    mlb_coeffs_sample_glide((float)glide_samples, sg);             // pitchGlide.setGlideTimeInSamples, :101
+    st[(size_t)VS_PG_REM * V + v] = 0xFFFFFFFFu;                    // mSamplesRemaining{-1}
+    st[(size_t)VS_PG_PER * V + v] = fbits(sg[0]);
+    st[(size_t)VS_PG_DY * V + v] = fbits(sg[1]);
+    for (int g = 0; g < VG_COUNT; ++g)                              // reset(): setValue(0) on all but the drift glide, :80-84
+      st[(size_t)(VS_GL + 3 * g + 2) * V + v] = (g == VG_DRIFT) ? 0xFFFFFFFFu : 0u;
+    st[(size_t)VS_SEED * V + v] = (uint32_t)(voice_index[v] * 232);  // :62
+    co[(size_t)VC_GLIDE_SAMPLES * V + v] = (float)glide_samples;
+    co[(size_t)VC_DRIFT_AMOUNT * V + v] = drift_amount[v];
+    co[(size_t)VC_BEND_RANGE * V + v] = pitch_bend[v];
+    co[(size_t)VC_VOICE_ROW * V + v] = (float)voice_index[v] - 1;   // :292
+  }
+  if (cudaMalloc(&vb->d_state, st.size() * 4) != cudaSuccess || cudaMalloc(&vb->d_coef, co.size() * 4) != cudaSuccess ||
+      cudaMalloc(&vb->d_grows, (size_t)VG_COUNT * V * MLB_BLOCK * 4) != cudaSuccess)
+  {
+    mlb_voices_destroy(vb);
+    return fail(MLB_ERR_ALLOC, "cudaMalloc of voice bank failed");
+  }
+  cudaMemcpy(vb->d_state, st.data(), st.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(vb->d_coef, co.data(), co.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemset(vb->d_grows, 0, (size_t)VG_COUNT * V * MLB_BLOCK * 4);
+  cudaStreamCreateWithFlags(&vb->stream, cudaStreamNonBlocking);
+  *out = vb;
+  return MLB_OK;
+}
+
+extern "C" int mlb_voices_process_device(mlb_voices* vb, const mlb_voice_events* events_dev, float* out_dev,
+                                         int n_blocks, unsigned row_mask, void* stream)
+{
+  if (!vb || !events_dev || (!out_dev && (row_mask & 0xFFu))) return fail(MLB_ERR_INVALID, "null argument");
+  if (n_blocks <= 0) return fail(MLB_ERR_INVALID, "n_blocks must be positive");
+  VoiceArgs a;
+  a.ev = events_dev;
+  a.out = out_dev;
+  a.state = vb->d_state;
+  a.coef = vb->d_coef;
+  a.grows = vb->d_grows;
+  a.V = vb->V, a.T = n_blocks;
+  a.row_mask = row_mask & 0xFFu;
+  a.sr = vb->sr;
+  a.gl_per = vb->gl_per, a.gl_dy = vb->gl_dy, a.dr_per = vb->dr_per, a.dr_dy = vb->dr_dy;
+  voice_bank_kernel<<<(vb->V + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+  ++g_launches;
+  CU_CHECK(cudaGetLastError());
+  return MLB_OK;
+}
+
+extern "C" int mlb_voices_process_host(mlb_voices* vb, const mlb_voice_events* events_host, float* out_host,
+                                       int n_blocks, unsigned row_mask)
+{
+  if (!vb || !events_host) return fail(MLB_ERR_INVALID, "null argument");
+  if (n_blocks <= 0) return fail(MLB_ERR_INVALID, "n_blocks must be positive");
+  row_mask &= 0xFFu;
+  if (row_mask && !out_host) return fail(MLB_ERR_INVALID, "out is null");
+  const size_t V = (size_t)vb->V, T = (size_t)n_blocks;
+  const size_t ev_bytes = T * V * sizeof(mlb_voice_events), out_bytes = T * MLB_VOICE_ROWS * V * MLB_BLOCK * 4;
+  int rc = ensure_buf(reinterpret_cast<float**>(&vb->d_ev), &vb->ev_cap, ev_bytes);
+  if (rc != MLB_OK) return rc;
+  rc = ensure_buf(&vb->d_out, &vb->out_cap, out_bytes);
+  if (rc != MLB_OK) return rc;
+  cudaStream_t s = vb->stream;
+  CU_CHECK(cudaMemcpyAsync(vb->d_ev, events_host, ev_bytes, cudaMemcpyHostToDevice, s));
+  rc = mlb_voices_process_device(vb, vb->d_ev, vb->d_out, n_blocks, row_mask, s);
+  if (rc != MLB_OK) return rc;
+  const size_t plane = V * MLB_BLOCK * 4;
+  if (row_mask == 0xFFu)
+    CU_CHECK(cudaMemcpyAsync(out_host, vb->d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+  else
+    for (size_t t = 0; t < T; ++t)
+      for (int r = 0; r < MLB_VOICE_ROWS; ++r)
+        if (row_mask & (1u << r))
+          CU_CHECK(cudaMemcpyAsync(reinterpret_cast<char*>(out_host) + (t * MLB_VOICE_ROWS + r) * plane,
+                                   reinterpret_cast<char*>(vb->d_out) + (t * MLB_VOICE_ROWS + r) * plane, plane,
+                                   cudaMemcpyDeviceToHost, s));
+  CU_CHECK(cudaStreamSynchronize(s));
+  return MLB_OK;
 }

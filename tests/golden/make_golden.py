@@ -92,6 +92,7 @@ def main():
     out["dcblocker_0045"] = np.float32(R.coeffs_dcblocker(0.045))
     np.savez_compressed(os.path.join(HERE, "coeffs.npz"), **out)
     make_functors(R)
+    make_voices()
     for f in ("ops.npz", "configs.npz", "coeffs.npz", "functors.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
@@ -129,8 +130,21 @@ def make_functors(R):
     np.savez_compressed(os.path.join(HERE, "functors.npz"), **out)
 
 
+def make_voices():
+    """SURVEY 8(f) row 3: EventsToSignals::Voice rows from the reference's own Voice (libmle2s.so)."""
+    from oracle.bindings import ref_voice_bank
+    V, T, sr = 6, 40, 48000.0
+    ev = wl.voice_events(V, T, seed=11)
+    out, _ = ref_voice_bank().run(sr, *wl.voice_bank_params(V), ev)
+    np.savez_compressed(os.path.join(HERE, "voices.npz"), events=ev.view(np.uint8), shape=np.array([T, V]),
+                        sr=np.float32(sr), out=out)
+    print("voices.npz", os.path.getsize(os.path.join(HERE, "voices.npz")), "bytes")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "functors":
+    if len(sys.argv) > 1 and sys.argv[1] == "voices":
+        make_voices()
+    elif len(sys.argv) > 1 and sys.argv[1] == "functors":
         make_functors(RefOracle())
         print("functors.npz", os.path.getsize(os.path.join(HERE, "functors.npz")), "bytes")
     else:

@@ -1,0 +1,127 @@
+"""EventsToSignals::Voice x V.  CPU: the C port against the reference's own Voice
+(compiled in place, oracle/_ref/libmle2s.so) and against committed goldens.  GPU: the CUDA bank,
+through the C ABI, against the port -- bit for bit on all 8 rows."""
+import os
+
+import numpy as np
+import pytest
+
+from madronalib_b200 import workloads as wl
+from tests.common import assert_same_bits
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "voices.npz")
+ROWS = ["pitch", "gate", "voice", "z", "x", "y", "mod", "time"]
+
+
+@pytest.fixture(scope="module")
+def port_bank():
+    from oracle import bindings
+    return bindings.port_voice_bank()
+
+
+@pytest.fixture(scope="module")
+def ref_bank():
+    from oracle import bindings
+    if not os.path.exists(bindings.E2S_LIB):
+        if os.path.isdir("/root/reference/source/app"):
+            bindings.build("ref")
+        else:
+            pytest.skip("oracle/_ref/libmle2s.so not built (no /root/reference here)")
+    return bindings.ref_voice_bank()
+
+
+@pytest.mark.parametrize("sr,seed", [(48000.0, 3), (44100.0, 4), (1000.0, 5)])
+def test_port_equals_reference_voice(ref_bank, port_bank, sr, seed):
+    """sr = 1000 makes the 8-second drift interval 125 vectors long, so the drift redraw and the drift
+    glide run inside the test."""
+    V, T = 40, 300
+    ev = wl.voice_events(V, T, seed=seed)
+    prm = wl.voice_bank_params(V)
+    a, _ = ref_bank.run(sr, *prm, ev)
+    b, _ = port_bank.run(sr, *prm, ev, splits=(7, 93, 200))
+    for r, name in enumerate(ROWS):
+        assert np.array_equal(a[:, r].view(np.uint32), b[:, r].view(np.uint32)), name
+    assert np.abs(a[:, 0]).max() > 1 and a[:, 1].max() > 0.5 and a[:, 7].max() > 0
+
+
+def test_port_matches_committed_golden(port_bank):
+    g = np.load(GOLD)
+    ev = g["events"].view(wl.VOICE_EVENTS_DTYPE).reshape(g["shape"][0], g["shape"][1])
+    V = ev.shape[1]
+    assert np.array_equal(ev.view(np.uint8), wl.voice_events(V, ev.shape[0], seed=11).view(np.uint8))
+    b, _ = port_bank.run(float(g["sr"]), *wl.voice_bank_params(V), ev)
+    assert np.array_equal(b.view(np.uint32), g["out"].view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sr,V,T,seed", [(48000.0, 70, 120, 6), (1000.0, 33, 300, 7), (44100.0, 300, 40, 8)])
+def test_gpu_voice_bank_bit_exact(gpu, port_bank, sr, V, T, seed):
+    ev = wl.voice_events(V, T, seed=seed)
+    prm = wl.voice_bank_params(V)
+    want, _ = port_bank.run(sr, *prm, ev)
+    vb = gpu.VoiceBank(sr, *prm)
+    try:
+        got = np.concatenate([vb.process_host(ev[:T // 3]), vb.process_host(ev[T // 3:])], axis=0)
+    finally:
+        vb.close()
+    for r, name in enumerate(ROWS):
+        assert_same_bits(got[:, r], want[:, r], name)
+
+
+@pytest.mark.gpu
+def test_gpu_voice_bank_matches_reference_golden_and_row_mask(gpu):
+    g = np.load(GOLD)
+    ev = g["events"].view(wl.VOICE_EVENTS_DTYPE).reshape(g["shape"][0], g["shape"][1])
+    V = ev.shape[1]
+    vb = gpu.VoiceBank(float(g["sr"]), *wl.voice_bank_params(V))
+    vb2 = gpu.VoiceBank(float(g["sr"]), *wl.voice_bank_params(V))
+    try:
+        got = vb.process_host(ev)
+        part = vb2.process_host(ev, row_mask=0b00000011)  # pitch and gate only
+    finally:
+        vb.close()
+        vb2.close()
+    assert_same_bits(got, g["out"], "voice bank vs reference golden")
+    assert_same_bits(part[:, :2], g["out"][:, :2], "row_mask planes")
+    assert not part[:, 2:].any()
+
+
+@pytest.mark.gpu
+def test_voice_rows_feed_a_graph(gpu, port_bank, port):
+    """The bank's out planes have the layout of graph inputs: pitch row -> (x 2^-7 as cycles/sample)
+    -> SineGen -> x gate row.  Whole path on the device, checked against port(bank) -> port(graph)."""
+    import torch
+    from madronalib_b200.graph import GraphSpec, SINE_ZERO_PHASE
+    V, T = 64, 20
+    ev = wl.voice_events(V, T, seed=9)
+    prm = wl.voice_bank_params(V)
+    rows, _ = port_bank.run(48000.0, *prm, ev)
+    g = GraphSpec()
+    pitch, gate = g.input(0), g.input(1)
+    k = g.param()
+    y = g.node("MULTIPLY", g.node("SINE", g.node("MULTIPLY", pitch, k)), gate)
+    g.output(y)
+    coef, state = g.new_coefs(V), g.new_state(V)
+    coef[0] = np.float32(2.0 ** -7)
+    state[0] = SINE_ZERO_PHASE
+    inp = np.ascontiguousarray(rows[:, 0:2])
+    want, _, _ = port.run(g, V, T, inp, state, coef)
+    dev = torch.device("cuda", 0)
+    d_ev = torch.from_numpy(ev.view(np.uint8).reshape(T, V, 68).copy()).to(dev)
+    d_rows = torch.zeros((T, 8, V, 64), dtype=torch.float32, device=dev)
+    vb = gpu.VoiceBank(48000.0, *prm)
+    vg = gpu.VoiceGraph(g, V)
+    try:
+        sh = torch.cuda.current_stream().cuda_stream
+        vb.process_device(d_ev, d_rows, T, 0xFF, sh)
+        d_in = d_rows[:, 0:2].contiguous()
+        d_out = torch.empty((T, 1, V, 64), dtype=torch.float32, device=dev)
+        vg.set_coefs(coef)
+        vg.set_state(state)
+        vg.process_device(d_in, d_out, None, T, sh)
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy()
+    finally:
+        vb.close()
+        vg.close()
+    assert_same_bits(got, want, "events -> voice rows -> graph")
