@@ -1659,7 +1659,7 @@ extern "C" int mlb_voices_create(int n_voices, float sample_rate, const int32_t*
     st[(size_t)VS_PG_PER * V + v] = fbits(sg[0]);
     st[(size_t)VS_PG_DY * V + v] = fbits(sg[1]);
     for (int g = 0; g < VG_COUNT; ++g)                              // reset(): setValue(0) on all but the drift glide, :80-84
-      st[(size_t)(VS_GL + 3 * g + 2) * V + v] = (g == VG_DRIFT) ? 0xFFFFFFFFu : 0u;
+      st[(size_t)(VS_GL + 4 * g + 2) * V + v] = (g == VG_DRIFT) ? 0xFFFFFFFFu : 0u;
     st[(size_t)VS_SEED * V + v] = (uint32_t)(voice_index[v] * 232);  // :62
     co[(size_t)VC_GLIDE_SAMPLES * V + v] = (float)glide_samples;
     co[(size_t)VC_DRIFT_AMOUNT * V + v] = drift_amount[v];
@@ -1695,7 +1695,10 @@ extern "C" int mlb_voices_process_device(mlb_voices* vb, const mlb_voice_events*
   a.row_mask = row_mask & 0xFFu;
   a.sr = vb->sr;
   a.gl_per = vb->gl_per, a.gl_dy = vb->gl_dy, a.dr_per = vb->dr_per, a.dr_dy = vb->dr_dy;
-  voice_bank_kernel<<<(vb->V + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+  // 4 warps x {gate, pitch (, elapsed time)} row tiles
+  const size_t smem = (size_t)4 * ((row_mask & 128u) ? 3 : 2) * kVoiceTileFloats * sizeof(float);
+  CU_CHECK(cudaFuncSetAttribute((const void*)voice_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  voice_bank_kernel<<<(vb->V + 127) / 128, 128, smem, (cudaStream_t)stream>>>(a);
   ++g_launches;
   CU_CHECK(cudaGetLastError());
   return MLB_OK;

@@ -15,8 +15,8 @@ enum VoiceGlide { VG_BEND = 0, VG_MOD, VG_X, VG_Y, VG_Z, VG_DRIFT, VG_COUNT };
 enum VoiceState
 {
   VS_PG_CURR = 0, VS_PG_STEP, VS_PG_TARGET, VS_PG_REM, VS_PG_PER, VS_PG_DY,  // pitchGlide (G:517-590)
-  VS_GL = 6,                       // 6 x {step, target, vectorsRemaining}
-  VS_VEL = VS_GL + 3 * VG_COUNT,   // currentVelocity, currentPitch, bend, mod, x, y, z
+  VS_GL = 6,                       // 6 x {step, target, vectorsRemaining, spare}
+  VS_VEL = VS_GL + 4 * VG_COUNT,   // currentVelocity, currentPitch, bend, mod, x, y, z
   VS_PITCH, VS_BEND, VS_MOD, VS_X, VS_Y, VS_Z,
   VS_AGE, VS_AGE_STEP, VS_SEED, VS_DRIFT_COUNTER, VS_NEXT_DRIFT, VS_CUR_DRIFT,
   VS_COUNT
@@ -55,88 +55,147 @@ MLB_DEV void voice_set_glide_time(VoiceRegs& r, float t)
   r.pg_dy = __fdiv_rn(1.0f, __int2float_rn(n));
 }
 // one output frame, E:134-140: gate, glided pitch, age -> seconds (samplesToSeconds, E:12-18)
-MLB_DEV void voice_frame(VoiceRegs& r, float sr, int t, float gate_v, float* gate, float* pitch, float* tm)
+// Row tiles in shared memory: [lane][65 floats] per warp -- a lane walks its own row (frames can be
+// revisited by a retrigger), then the warp stores the 32 rows with full 128-byte lines.
+constexpr int kVoiceTileStride = 65;
+constexpr int kVoiceTileFloats = 32 * kVoiceTileStride;
+
+MLB_DEV void voice_frame(VoiceRegs& r, float sr, int t, float gate_v, float* gate, float* pitch, float* tm,
+                        bool want_time)
 {
   gate[t] = gate_v;
   const float co[2] = {r.pg_per_f, r.pg_dy};
   pitch[t] = sample_glide_tick<true>(r.pitch, r.pg, co);
   r.age += r.age_step;
-  tm[t] = __double2float_rn(__ddiv_rn((double)r.age, (double)sr));
+  if (want_time) tm[t] = __double2float_rn(__ddiv_rn((double)r.age, (double)sr));  // FP64 divide only if the row is wanted
 }
-MLB_DEV void voice_write_frames(VoiceRegs& r, float sr, int end_frame, float* gate, float* pitch, float* tm)
+// the warp's 32 rows of one output plane: tile[j][0..63] -> plane[(v0 + j)][0..63], two 128-B lines per row
+MLB_DEV void voice_store_tile(const float* tile, float* plane, int v0, int V, int lane)
 {
-  for (int t = r.next_frame; t < end_frame; ++t) voice_frame(r, sr, t, r.vel, gate, pitch, tm);
-  r.next_frame = end_frame;
+  __syncwarp();
+#pragma unroll 4
+  for (int j = 0; j < 32; ++j)
+  {
+    if (v0 + j >= V) break;
+    float* dst = plane + (size_t)(v0 + j) * MLB_BLOCK;
+    __stcs(dst + lane, tile[j * kVoiceTileStride + lane]);
+    __stcs(dst + 32 + lane, tile[j * kVoiceTileStride + 32 + lane]);
+  }
+  __syncwarp();
 }
 
-// LinearGlide::operator()(float) for 4 consecutive samples (G:459-505); mode as in run_glide_node
+// LinearGlide::operator()(float), G:459-505.  The row mCurrVec lives in delay memory and is touched only
+// while the glide moves: an idle glide's row equals DSPVector(target) (landing writes the target into
+// every element, construction and setValue leave zeros with target zero).
 struct GlidePlan
 {
   int mode;  // -1 idle, 0 land on target, 1 start, 2 continue
   float step, target, cv;
-  int remaining;
 };
+// st: step, target, vectorsRemaining, (spare)
 MLB_DEV GlidePlan glide_plan(uint32_t* st, float f, float per_f, float dy, const float* row)
 {
   GlidePlan g;
-  g.step = u2f(st[0]), g.target = u2f(st[1]), g.remaining = (int32_t)st[2];
+  g.step = u2f(st[0]), g.target = u2f(st[1]);
   g.cv = 0.f;
+  const int rem_prev = (int32_t)st[2];
+  int remaining = rem_prev;
   const int per = cvt_trunc(per_f);
   if (f != g.target)
   {
     g.target = f;
-    g.remaining = per;
+    remaining = per;
   }
-  if (g.remaining < 0)
+  if (remaining < 0)
     g.mode = -1;
-  else if (g.remaining == 0)
+  else if (remaining == 0)
   {
     g.mode = 0;
     g.step = 0.f;
-    g.remaining--;
+    remaining--;
   }
-  else if (g.remaining == per)
+  else if (remaining == per)
   {
     g.mode = 1;
-    g.cv = row[MLB_BLOCK - 1];
+    // currentValue = mCurrVec[63]; an idle row is its (previous) target
+    g.cv = rem_prev < 0 ? u2f(st[1]) : row[MLB_BLOCK - 1];
     g.step = __fmul_rn(__fsub_rn(g.target, g.cv), dy);
-    g.remaining--;
+    remaining--;
   }
   else
   {
     g.mode = 2;
-    g.remaining--;
+    remaining--;
   }
-  st[0] = f2u(g.step), st[1] = f2u(g.target), st[2] = (uint32_t)g.remaining;
+  st[0] = f2u(g.step), st[1] = f2u(g.target), st[2] = (uint32_t)remaining;
   return g;
 }
-// samples 4q .. 4q+3 of the glide's output row; updates mCurrVec in delay memory when it moves
-MLB_DEV float4 glide_quad(const GlidePlan& g, float* row, int q)
+// Run one glide for this lane's vector; emit(q, float4) receives samples 4q..4q+3 when WANT is set.
+// The three modes are hoisted out of the sample loop; an idle glide whose row nobody wants costs nothing.
+template <bool WANT, class Emit>
+MLB_DEV void glide_run(const GlidePlan& g, float* row, bool live, Emit emit)
 {
-  float4 y;
+  float4* row4 = reinterpret_cast<float4*>(row);
   if (g.mode <= 0)
-    y = make_float4(g.target, g.target, g.target, g.target);  // idle rows equal their target
+  {
+    // landing: the row becomes DSPVector(target); it is not stored -- idle rows are never read
+    if (WANT)
+    {
+      const float4 y = make_float4(g.target, g.target, g.target, g.target);
+#pragma unroll 4
+      for (int q = 0; q < 16; ++q) emit(q, y);
+    }
+  }
   else if (g.mode == 1)
   {
-    y.x = __fadd_rn(g.cv, __fmul_rn(unity_ramp(4 * q), g.step));
-    y.y = __fadd_rn(g.cv, __fmul_rn(unity_ramp(4 * q + 1), g.step));
-    y.z = __fadd_rn(g.cv, __fmul_rn(unity_ramp(4 * q + 2), g.step));
-    y.w = __fadd_rn(g.cv, __fmul_rn(unity_ramp(4 * q + 3), g.step));
+#pragma unroll 2
+    for (int q = 0; q < 16; ++q)
+    {
+      float4 y;
+      y.x = __fadd_rn(g.cv, __fmul_rn(unity_ramp(4 * q), g.step));
+      y.y = __fadd_rn(g.cv, __fmul_rn(unity_ramp(4 * q + 1), g.step));
+      y.z = __fadd_rn(g.cv, __fmul_rn(unity_ramp(4 * q + 2), g.step));
+      y.w = __fadd_rn(g.cv, __fmul_rn(unity_ramp(4 * q + 3), g.step));
+      if (live) row4[q] = y;
+      if (WANT) emit(q, y);
+    }
   }
   else
   {
-    y = reinterpret_cast<const float4*>(row)[q];
-    y.x = __fadd_rn(y.x, g.step), y.y = __fadd_rn(y.y, g.step), y.z = __fadd_rn(y.z, g.step), y.w = __fadd_rn(y.w, g.step);
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h)
+    {
+      float4 buf[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) buf[q] = row4[8 * h + q];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+      {
+        float4 y = buf[q];
+        y.x = __fadd_rn(y.x, g.step), y.y = __fadd_rn(y.y, g.step), y.z = __fadd_rn(y.z, g.step), y.w = __fadd_rn(y.w, g.step);
+        if (live) row4[8 * h + q] = y;
+        if (WANT) emit(8 * h + q, y);
+      }
+    }
   }
-  if (g.mode >= 0) reinterpret_cast<float4*>(row)[q] = y;
-  return y;
 }
 
 __global__ void __launch_bounds__(128) voice_bank_kernel(const VoiceArgs a)
 {
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= a.V) return;
+  extern __shared__ float voice_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int v_raw = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v0 = v_raw - lane;
+  if (v0 >= a.V) return;                      // whole warp out of range
+  const bool live = v_raw < a.V;
+  const int v = live ? v_raw : a.V - 1;       // dead lanes shadow the last voice, their stores are masked
   const size_t V = (size_t)a.V;
+  const bool want_time = (a.row_mask & 128u) != 0;
+  const int n_tiles = want_time ? 3 : 2;  // gate, pitch (+ elapsed time)
+  float* const tiles = voice_smem + (size_t)warp * n_tiles * kVoiceTileFloats;
+  float* const gate = tiles + lane * kVoiceTileStride;
+  float* const pitch = gate + kVoiceTileFloats;
+  float* const tm = pitch + kVoiceTileFloats;
   uint32_t st[VS_COUNT];
 #pragma unroll
   for (int i = 0; i < VS_COUNT; ++i) st[i] = a.state[(size_t)i * V + v];
@@ -159,7 +218,6 @@ __global__ void __launch_bounds__(128) voice_bank_kernel(const VoiceArgs a)
   int drift_counter = (int)st[VS_DRIFT_COUNTER], next_drift = (int)st[VS_NEXT_DRIFT];
   float cur_drift = u2f(st[VS_CUR_DRIFT]);
 
-  float gate[MLB_BLOCK], pitch[MLB_BLOCK], tm[MLB_BLOCK];  // frames can be revisited (retrigger): local rows
 
   for (int t = 0; t < a.T; ++t)
   {
@@ -174,43 +232,82 @@ __global__ void __launch_bounds__(128) voice_bank_kernel(const VoiceArgs a)
       drift_counter = 0;
       next_drift = __double2int_rz(__dmul_rn(__dmul_rn((double)a.sr, (double)next_mul), 8.0));
     }
-    // ---- the vector's note events, E:126-220 ----
+    // ---- the vector's note events (E:126-220) and the tail fill of endProcess (E:224-236) ----
+    // The reference runs, per event, [pre-actions; frames up to the event; post-actions], then fills the
+    // rest of the vector.  Here every lane emits ONE frame per iteration of a warp-uniform loop and
+    // steps its own event cursor in between, so lanes with different event times do not serialise.
     const uint32_t* rec = reinterpret_cast<const uint32_t*>(a.ev + ((size_t)t * V + v));
     const uint32_t head = rec[0], times = rec[1], types = rec[2], flags = rec[3];
-    const int n_events = (int)(head & 0xFFu);
+    const int n_events = min((int)(head & 0xFFu), MLB_VOICE_MAX_EVENTS);
     const unsigned set_mask = (head >> 8) & 0xFFu;
-    for (int k = 0; k < n_events && k < MLB_VOICE_MAX_EVENTS; ++k)
+    int k = 0;
+    bool pre_applied = false, retrig_frame_done = false;
+    bool active = true;
+    while (active)
     {
-      int dest = (int)((times >> (8 * k)) & 0xFFu);
-      dest = dest > MLB_BLOCK ? MLB_BLOCK : dest;
-      const int type = (int)((types >> (8 * k)) & 0xFFu);
-      const unsigned fl = (flags >> (8 * k)) & 0xFFu;
-      const float v1 = u2f(rec[4 + k]), v2 = u2f(rec[8 + k]);
-      if (type == MLB_EV_NOTE_ON)
+      int emit_at = -1;
+      float emit_gate = 0.f;
+      while (k < n_events)
       {
-        if (fl & MLB_EVF_RESET) r.age = 0;
-        r.age_step = 1;
-        voice_set_glide_time(r, (fl & MLB_EVF_GLIDE) ? glide_samples : 0.f);
-        voice_write_frames(r, a.sr, dest, gate, pitch, tm);
-        r.pitch = v1;
-        r.vel = v2;
+        int dest = (int)((times >> (8 * k)) & 0xFFu);
+        dest = dest > MLB_BLOCK ? MLB_BLOCK : dest;
+        const int type = (int)((types >> (8 * k)) & 0xFFu);
+        const unsigned fl = (flags >> (8 * k)) & 0xFFu;
+        const bool is_on = type == MLB_EV_NOTE_ON, is_rt = type == MLB_EV_NOTE_RETRIG, is_off = type == MLB_EV_NOTE_OFF;
+        if (!(is_on || is_rt || is_off))
+        {
+          ++k;  // kNoteSustain & co: writeNoteEvent does nothing
+          continue;
+        }
+        if (!pre_applied)
+        {
+          if (is_on || is_rt)
+          {
+            if (fl & MLB_EVF_RESET) r.age = 0;
+            r.age_step = 1;
+          }
+          if (is_on) voice_set_glide_time(r, (fl & MLB_EVF_GLIDE) ? glide_samples : 0.f);
+          pre_applied = true;
+        }
+        if (is_rt && dest == 0) dest = 1;
+        const int bound = is_rt ? dest - 1 : dest;  // writeOutputFrames(bound)
+        if (r.next_frame < bound)
+        {
+          emit_at = r.next_frame++;
+          emit_gate = r.vel;
+          break;
+        }
+        r.next_frame = bound;  // writeOutputFrames always ends with nextFrameToProcess = endFrame
+        if (is_rt && !retrig_frame_done)
+        {
+          retrig_frame_done = true;  // the retrigger frame: gate 0 at dest - 1 (E:183-189)
+          emit_at = dest - 1;
+          emit_gate = 0.f;
+          break;
+        }
+        // post-actions
+        if (is_off)
+          r.vel = 0.f;
+        else
+        {
+          r.pitch = u2f(rec[4 + k]);
+          r.vel = u2f(rec[8 + k]);
+        }
+        if (is_rt) r.next_frame = dest;
+        ++k;
+        pre_applied = false, retrig_frame_done = false;
       }
-      else if (type == MLB_EV_NOTE_RETRIG)
+      if (emit_at < 0)
       {
-        if (fl & MLB_EVF_RESET) r.age = 0;
-        r.age_step = 1;
-        if (dest == 0) dest++;
-        voice_write_frames(r, a.sr, dest - 1, gate, pitch, tm);
-        voice_frame(r, a.sr, dest - 1, 0.f, gate, pitch, tm);  // the retrigger frame: gate 0
-        r.pitch = v1;
-        r.vel = v2;
-        r.next_frame = dest;
+        if (r.next_frame < MLB_BLOCK)
+        {
+          emit_at = r.next_frame++;
+          emit_gate = r.vel;
+        }
+        else
+          active = false;
       }
-      else if (type == MLB_EV_NOTE_OFF)
-      {
-        voice_write_frames(r, a.sr, dest, gate, pitch, tm);
-        r.vel = 0.f;
-      }
+      if (emit_at >= 0) voice_frame(r, a.sr, emit_at, emit_gate, gate, pitch, tm, want_time);
     }
     if (set_mask & MLB_SET_BEND) cur[0] = u2f(rec[12]);
     if (set_mask & MLB_SET_MOD) cur[1] = u2f(rec[13]);
@@ -218,42 +315,56 @@ __global__ void __launch_bounds__(128) voice_bank_kernel(const VoiceArgs a)
     if (set_mask & MLB_SET_Y) cur[3] = u2f(rec[15]);
     if (set_mask & MLB_SET_Z) cur[4] = u2f(rec[16]);
     // ---- endProcess, E:222-262 ----
-    for (int f = r.next_frame; f < MLB_BLOCK; ++f) voice_frame(r, a.sr, f, r.vel, gate, pitch, tm);
     if (r.vel == 0.f) cur[4] = 0.f;
     GlidePlan gp[VG_COUNT];
 #pragma unroll
     for (int i = 0; i < VG_COUNT; ++i)
-      gp[i] = glide_plan(&st[VS_GL + 3 * i], i == VG_DRIFT ? cur_drift : cur[i], i == VG_DRIFT ? a.dr_per : a.gl_per,
+      gp[i] = glide_plan(&st[VS_GL + 4 * i], i == VG_DRIFT ? cur_drift : cur[i], i == VG_DRIFT ? a.dr_per : a.gl_per,
                          i == VG_DRIFT ? a.dr_dy : a.gl_dy, grow[i]);
-    float* o = a.out + ((size_t)t * MLB_VOICE_ROWS * V + v) * MLB_BLOCK;
-    const size_t row_stride = V * MLB_BLOCK;
-#pragma unroll 1
-    for (int q = 0; q < 16; ++q)
+    float* const planes = a.out + (size_t)t * MLB_VOICE_ROWS * V * MLB_BLOCK;
+    const size_t plane_floats = V * MLB_BLOCK;
+    // pitch += bendGlide * pitchBend * (1/12); pitch += driftSig * driftAmount * kDriftScale  (E:255-261)
+    glide_run<true>(gp[VG_BEND], grow[VG_BEND], live, [&](int q, float4 y)
     {
-      float4 g[VG_COUNT];
-#pragma unroll
-      for (int i = 0; i < VG_COUNT; ++i) g[i] = glide_quad(gp[i], grow[i], q);
-      float4 p = make_float4(pitch[4 * q], pitch[4 * q + 1], pitch[4 * q + 2], pitch[4 * q + 3]);
       const float k12 = 1.f / 12;
-      // pitch += bendGlide * pitchBend * (1/12); pitch += driftSig * driftAmount * kDriftScale  (E:255-261)
-      p.x = __fadd_rn(p.x, __fmul_rn(__fmul_rn(g[VG_BEND].x, bend_range), k12));
-      p.y = __fadd_rn(p.y, __fmul_rn(__fmul_rn(g[VG_BEND].y, bend_range), k12));
-      p.z = __fadd_rn(p.z, __fmul_rn(__fmul_rn(g[VG_BEND].z, bend_range), k12));
-      p.w = __fadd_rn(p.w, __fmul_rn(__fmul_rn(g[VG_BEND].w, bend_range), k12));
-      p.x = __fadd_rn(p.x, __fmul_rn(__fmul_rn(g[VG_DRIFT].x, drift_amount), 0.02f));
-      p.y = __fadd_rn(p.y, __fmul_rn(__fmul_rn(g[VG_DRIFT].y, drift_amount), 0.02f));
-      p.z = __fadd_rn(p.z, __fmul_rn(__fmul_rn(g[VG_DRIFT].z, drift_amount), 0.02f));
-      p.w = __fadd_rn(p.w, __fmul_rn(__fmul_rn(g[VG_DRIFT].w, drift_amount), 0.02f));
-      float4* o4 = reinterpret_cast<float4*>(o) + q;
-      const size_t rs4 = row_stride / 4;
-      if (a.row_mask & 1u) __stcs(o4 + 0 * rs4, p);                                                                      // kPitch
-      if (a.row_mask & 2u) __stcs(o4 + 1 * rs4, make_float4(gate[4 * q], gate[4 * q + 1], gate[4 * q + 2], gate[4 * q + 3]));  // kGate
-      if (a.row_mask & 4u) __stcs(o4 + 2 * rs4, make_float4(voice_row, voice_row, voice_row, voice_row));                 // kVoice
-      if (a.row_mask & 8u) __stcs(o4 + 3 * rs4, g[VG_Z]);                                                                // kZ
-      if (a.row_mask & 16u) __stcs(o4 + 4 * rs4, g[VG_X]);                                                               // kX
-      if (a.row_mask & 32u) __stcs(o4 + 5 * rs4, g[VG_Y]);                                                               // kY
-      if (a.row_mask & 64u) __stcs(o4 + 6 * rs4, g[VG_MOD]);                                                             // kMod
-      if (a.row_mask & 128u) __stcs(o4 + 7 * rs4, make_float4(tm[4 * q], tm[4 * q + 1], tm[4 * q + 2], tm[4 * q + 3]));   // kElapsedTime
+      float* p = pitch + 4 * q;
+      p[0] = __fadd_rn(p[0], __fmul_rn(__fmul_rn(y.x, bend_range), k12));
+      p[1] = __fadd_rn(p[1], __fmul_rn(__fmul_rn(y.y, bend_range), k12));
+      p[2] = __fadd_rn(p[2], __fmul_rn(__fmul_rn(y.z, bend_range), k12));
+      p[3] = __fadd_rn(p[3], __fmul_rn(__fmul_rn(y.w, bend_range), k12));
+    });
+    glide_run<true>(gp[VG_DRIFT], grow[VG_DRIFT], live, [&](int q, float4 y)
+    {
+      float* p = pitch + 4 * q;
+      p[0] = __fadd_rn(p[0], __fmul_rn(__fmul_rn(y.x, drift_amount), 0.02f));
+      p[1] = __fadd_rn(p[1], __fmul_rn(__fmul_rn(y.y, drift_amount), 0.02f));
+      p[2] = __fadd_rn(p[2], __fmul_rn(__fmul_rn(y.z, drift_amount), 0.02f));
+      p[3] = __fadd_rn(p[3], __fmul_rn(__fmul_rn(y.w, drift_amount), 0.02f));
+    });
+    if (a.row_mask & 1u) voice_store_tile(tiles + kVoiceTileFloats, planes + 0 * plane_floats, v0, a.V, lane);    // kPitch
+    if (a.row_mask & 2u) voice_store_tile(tiles, planes + 1 * plane_floats, v0, a.V, lane);                        // kGate
+    if (want_time) voice_store_tile(tiles + 2 * kVoiceTileFloats, planes + 7 * plane_floats, v0, a.V, lane);      // kElapsedTime
+    __syncwarp();
+    // the glide-only rows reuse the gate tile: kZ(3) kX(4) kY(5) kMod(6) <- z, x, y, mod glides; kVoice(2) constant
+    if (a.row_mask & 4u)
+    {
+#pragma unroll 4
+      for (int n = 0; n < MLB_BLOCK; ++n) gate[n] = voice_row;
+      voice_store_tile(tiles, planes + 2 * plane_floats, v0, a.V, lane);
+    }
+    const int glide_of_row[4] = {VG_Z, VG_X, VG_Y, VG_MOD};
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr)
+    {
+      const int row = 3 + rr, gi = glide_of_row[rr];
+      if ((a.row_mask >> row) & 1u)
+      {
+        glide_run<true>(gp[gi], grow[gi], live, [&](int q, float4 y)
+        { gate[4 * q] = y.x, gate[4 * q + 1] = y.y, gate[4 * q + 2] = y.z, gate[4 * q + 3] = y.w; });
+        voice_store_tile(tiles, planes + (size_t)row * plane_floats, v0, a.V, lane);
+      }
+      else
+        glide_run<false>(gp[gi], grow[gi], live, [](int, float4) {});  // the glide still advances
     }
   }
 #pragma unroll
@@ -264,8 +375,11 @@ __global__ void __launch_bounds__(128) voice_bank_kernel(const VoiceArgs a)
   st[VS_BEND] = f2u(cur[0]), st[VS_MOD] = f2u(cur[1]), st[VS_X] = f2u(cur[2]), st[VS_Y] = f2u(cur[3]), st[VS_Z] = f2u(cur[4]);
   st[VS_SEED] = seed, st[VS_DRIFT_COUNTER] = (uint32_t)drift_counter, st[VS_NEXT_DRIFT] = (uint32_t)next_drift;
   st[VS_CUR_DRIFT] = f2u(cur_drift);
+  if (live)
+  {
 #pragma unroll
-  for (int i = 0; i < VS_COUNT; ++i) a.state[(size_t)i * V + v] = st[i];
+    for (int i = 0; i < VS_COUNT; ++i) a.state[(size_t)i * V + v] = st[i];
+  }
 }
 
 }  // namespace mlb

@@ -451,7 +451,7 @@ def voice_bank_params(n_voices: int):
             (np.float32(0.25) * (v % 5)).astype(np.float32), np.where(v % 3 == 0, 24.0, 7.0).astype(np.float32))
 
 
-def voice_events(n_voices: int, n_blocks: int, seed: int = 1, density: float = 0.35) -> np.ndarray:
+def voice_events(n_voices: int, n_blocks: int, seed: int = 1, density: float = 0.35, ctl: float = 0.3) -> np.ndarray:
     """A seeded performance: [T][V] records.  Each voice plays notes (on / retrigger / off, with and
     without glide and age reset, sometimes several per vector, sometimes two at the same frame) while
     bend / mod / x / y / z move now and then."""
@@ -480,7 +480,7 @@ def voice_events(n_voices: int, n_blocks: int, seed: int = 1, density: float = 0
                     r["value1"][k] = np.float32(rng.integers(36, 96)) / np.float32(12.0)
                     r["value2"][k] = np.float32(rng.random() * 0.9 + 0.1)
                 r["n_events"] = n
-            if rng.random() < 0.3:
+            if rng.random() < ctl:
                 m = int(rng.integers(1, 32))
                 r["set_mask"] = m
                 r["bend"], r["mod"] = np.float32(rng.random() * 2 - 1), np.float32(rng.random())

@@ -24,7 +24,7 @@ def main():
     from madronalib_b200 import api, workloads as wl
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--only", default="2,3,4,5,6,map")
+    ap.add_argument("--only", default="2,3,4,5,6,voices,map")
     ap.add_argument("--generic", action="store_true", help="force the graph interpreter kernel")
     args = ap.parse_args()
     only = set(args.only.split(","))
@@ -75,6 +75,34 @@ def main():
                               "algorithmic_bytes": b, "achieved_gbs": b / (ms * 1e-3) / 1e9,
                               "frac_of_measured_hbm_peak": b / (ms * 1e-3) / 1e9 / peak}), flush=True)
         del x1, x2, x3, y
+    if "voices" in only:
+        # K7: EventsToSignals::Voice x V.  Per voice-block: 68 B record in, selected rows out.
+        V7, T7 = 65536, 64
+        # a busy performance: a voice gets note events in 10 % of its vectors, controller moves in 5 %
+        ev = wl.voice_events(256, T7, seed=2, density=0.10, ctl=0.05)
+        ev = np.ascontiguousarray(np.tile(ev, (1, V7 // 256)))
+        prm = wl.voice_bank_params(V7)
+        d_ev = torch.from_numpy(ev.view(np.uint8).reshape(T7, V7, 68)).to(dev)
+        d_rows = torch.empty((T7, 8, V7, 64), dtype=torch.float32, device=dev)
+        sh = torch.cuda.current_stream().cuda_stream
+        for mask, label in ((0x03, "pitch+gate"), (0xFF, "all 8 rows")):
+            vb = api.VoiceBank(48000.0, *prm)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(2):
+                vb.process_device(d_ev, d_rows, T7, mask, sh)
+            e0.record()
+            for _ in range(args.steps):
+                vb.process_device(d_ev, d_rows, T7, mask, sh)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            b = (68.0 + 256.0 * bin(mask).count("1")) * V7 * T7
+            print(json.dumps({"config": "voices_" + label, "kernel": "voice_bank_kernel", "voices": V7, "blocks": T7,
+                              "kernel_ms": ms, "voice_samples_per_s": V7 * T7 * 64 / (ms * 1e-3),
+                              "algorithmic_bytes": b, "achieved_gbs": b / (ms * 1e-3) / 1e9,
+                              "frac_of_measured_hbm_peak": b / (ms * 1e-3) / 1e9 / peak}), flush=True)
+            vb.close()
+        del d_ev, d_rows
     for name, w, T, alg in cfgs:
         V = w.n_voices
         g = api.VoiceGraph(w.spec, V, api.FLAG_FORCE_GENERIC if args.generic else 0)
