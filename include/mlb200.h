@@ -306,7 +306,7 @@ enum {                            /* = ml::EventType (source/app/MLEvent.h:14-27
   MLB_EV_NULL = 0, MLB_EV_NOTE_ON = 1, MLB_EV_NOTE_RETRIG = 2, MLB_EV_NOTE_SUSTAIN = 3, MLB_EV_NOTE_OFF = 4
 };
 enum { MLB_EVF_GLIDE = 1, MLB_EVF_RESET = 2 };                  /* writeNoteEvent(e, key, doGlide, doReset) */
-enum { MLB_SET_BEND = 1, MLB_SET_MOD = 2, MLB_SET_X = 4, MLB_SET_Y = 8, MLB_SET_Z = 16 };
+enum { MLB_SET_BEND = 1, MLB_SET_MOD = 2, MLB_SET_X = 4, MLB_SET_Y = 8, MLB_SET_Z = 16, MLB_SET_PRESSURE = 32 };
 typedef struct mlb_voice_events {  /* what ONE Voice receives during ONE vector */
   uint8_t n_events;                          /* <= MLB_VOICE_MAX_EVENTS, in time order */
   uint8_t set_mask;                          /* which of bend/mod/x/y/z were written this vector */
@@ -317,7 +317,11 @@ typedef struct mlb_voice_events {  /* what ONE Voice receives during ONE vector 
   float value1[MLB_VOICE_MAX_EVENTS];        /* Event::value1 = pitch */
   float value2[MLB_VOICE_MAX_EVENTS];        /* Event::value2 = velocity */
   float bend, mod, x, y, z;                  /* currentPitchBend, currentMod, currentX/Y/Z when set */
-} mlb_voice_events;                          /* 68 bytes */
+  float pressure;                            /* MIDI channel pressure = controllers[128].inputValue (.cpp:601-606) */
+} mlb_voice_events;                          /* 72 bytes */
+/* flags for mlb_voices_create */
+#define MLB_VOICES_MIDI 1u  /* processVector's MIDI tail (.cpp:440-447): z row += the smoothed channel-pressure
+                             * controller (SmoothedController, .cpp:274-285), one copy per voice */
 
 typedef struct mlb_voices mlb_voices;  /* opaque: V Voice objects on the device */
 
@@ -326,7 +330,7 @@ typedef struct mlb_voices mlb_voices;  /* opaque: V Voice objects on the device 
  * gives the kVoice row = index - 1, .cpp:61,292); pitch_bend[v] = the semitone range handed to
  * endProcess (.cpp:422-428).  Arrays are per voice, host memory. */
 int mlb_voices_create(int n_voices, float sample_rate, const int32_t* voice_index, const float* pitch_glide_seconds,
-                      const float* drift_amount, const float* pitch_bend, mlb_voices** out);
+                      const float* drift_amount, const float* pitch_bend, unsigned flags, mlb_voices** out);
 int mlb_voices_destroy(mlb_voices* vb);
 /* n_blocks vectors: beginProcess, the block's events, endProcess, for every voice.
  * events_host [n_blocks][V]; out_host [n_blocks][MLB_VOICE_ROWS][V][64] (rows whose bit is clear in

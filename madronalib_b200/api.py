@@ -68,7 +68,7 @@ def lib() -> ctypes.CDLL:
     L.mlb_graph_delay_bytes.restype = ctypes.c_size_t
     L.mlb_graph_delay_bytes.argtypes = [_vp]
     L.mlb_graph_reserve_sms.argtypes = [_vp, ctypes.c_int]
-    L.mlb_voices_create.argtypes = [ctypes.c_int, _cf, _vp, _vp, _vp, _vp, _vp]
+    L.mlb_voices_create.argtypes = [ctypes.c_int, _cf, _vp, _vp, _vp, _vp, ctypes.c_uint, _vp]
     L.mlb_voices_destroy.argtypes = [_vp]
     L.mlb_voices_process_host.argtypes = [_vp, _vp, _vp, ctypes.c_int, ctypes.c_uint]
     L.mlb_voices_process_device.argtypes = [_vp, _vp, _vp, ctypes.c_int, ctypes.c_uint, _vp]
@@ -266,14 +266,17 @@ class VoiceBank:
 
     ROWS = 8
 
-    def __init__(self, sample_rate: float, voice_index, pitch_glide_seconds, drift_amount, pitch_bend):
+    MIDI = 1  # MLB_VOICES_MIDI: z row += smoothed channel pressure
+
+    def __init__(self, sample_rate: float, voice_index, pitch_glide_seconds, drift_amount, pitch_bend,
+                 flags: int = 0):
         vi = np.ascontiguousarray(voice_index, np.int32)
         gs, da, pb = (np.ascontiguousarray(a, np.float32) for a in (pitch_glide_seconds, drift_amount, pitch_bend))
         self.n_voices = int(vi.shape[0])
         assert gs.shape == da.shape == pb.shape == vi.shape
         h = ctypes.c_void_p()
         _check(lib().mlb_voices_create(self.n_voices, sample_rate, vi.ctypes.data, gs.ctypes.data, da.ctypes.data,
-                                       pb.ctypes.data, ctypes.byref(h)))
+                                       pb.ctypes.data, flags, ctypes.byref(h)))
         self._h = h
 
     def close(self) -> None:
@@ -290,7 +293,7 @@ class VoiceBank:
     def process_host(self, events: np.ndarray, row_mask: int = 0xFF) -> np.ndarray:
         """events: [T][V] array of workloads.VOICE_EVENTS_DTYPE; returns out [T][8][V][64] f32
         (planes whose bit is clear in row_mask are left zero)."""
-        assert events.ndim == 2 and events.shape[1] == self.n_voices and events.dtype.itemsize == 68
+        assert events.ndim == 2 and events.shape[1] == self.n_voices and events.dtype.itemsize == 72
         ev = np.ascontiguousarray(events)
         out = np.zeros((ev.shape[0], self.ROWS, self.n_voices, BLOCK), np.float32)
         _check(lib().mlb_voices_process_host(self._h, ev.ctypes.data, out.ctypes.data, ev.shape[0], row_mask))

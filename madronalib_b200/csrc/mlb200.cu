@@ -1598,7 +1598,8 @@ struct mlb_voices
 {
   int V = 0;
   float sr = 0.f;
-  float gl_per = 0.f, gl_dy = 0.f, dr_per = 0.f, dr_dy = 0.f;
+  float gl_per = 0.f, gl_dy = 0.f, dr_per = 0.f, dr_dy = 0.f, pc_per = 0.f, pc_dy = 0.f;
+  unsigned flags = 0;
   uint32_t* d_state = nullptr;
   float* d_coef = nullptr;
   float* d_grows = nullptr;
@@ -1623,7 +1624,7 @@ extern "C" int mlb_voices_destroy(mlb_voices* vb)
 
 extern "C" int mlb_voices_create(int n_voices, float sample_rate, const int32_t* voice_index,
                                  const float* pitch_glide_seconds, const float* drift_amount,
-                                 const float* pitch_bend, mlb_voices** out)
+                                 const float* pitch_bend, unsigned flags, mlb_voices** out)
 {
   if (!out) return fail(MLB_ERR_INVALID, "out is null");
   *out = nullptr;
@@ -1642,6 +1643,9 @@ extern "C" int mlb_voices_create(int n_voices, float sample_rate, const int32_t*
   vb->gl_per = c[0], vb->gl_dy = c[1];
   mlb_coeffs_glide((float)(sr * 8.0f), c);   // kDriftTimeSeconds
   vb->dr_per = c[0], vb->dr_dy = c[1];
+  mlb_coeffs_glide((float)(int)(sr * 0.02f), c);  // SmoothedController::process, .cpp:278-280
+  vb->pc_per = c[0], vb->pc_dy = c[1];
+  vb->flags = flags;
   std::vector<uint32_t> st((size_t)VS_COUNT * V, 0u);
   std::vector<float> co((size_t)VC_COUNT * V, 0.f);
   auto fbits = [](float f)
@@ -1659,7 +1663,7 @@ extern "C" int mlb_voices_create(int n_voices, float sample_rate, const int32_t*
     st[(size_t)VS_PG_PER * V + v] = fbits(sg[0]);
     st[(size_t)VS_PG_DY * V + v] = fbits(sg[1]);
     for (int g = 0; g < VG_COUNT; ++g)                              // reset(): setValue(0) on all but the drift glide, :80-84
-      st[(size_t)(VS_GL + 4 * g + 2) * V + v] = (g == VG_DRIFT) ? 0xFFFFFFFFu : 0u;
+      st[(size_t)(VS_GL + 4 * g + 2) * V + v] = (g == VG_DRIFT || g == VG_PRESSURE) ? 0xFFFFFFFFu : 0u;
     st[(size_t)VS_SEED * V + v] = (uint32_t)(voice_index[v] * 232);  // :62
     co[(size_t)VC_GLIDE_SAMPLES * V + v] = (float)glide_samples;
     co[(size_t)VC_DRIFT_AMOUNT * V + v] = drift_amount[v];
@@ -1695,6 +1699,8 @@ extern "C" int mlb_voices_process_device(mlb_voices* vb, const mlb_voice_events*
   a.row_mask = row_mask & 0xFFu;
   a.sr = vb->sr;
   a.gl_per = vb->gl_per, a.gl_dy = vb->gl_dy, a.dr_per = vb->dr_per, a.dr_dy = vb->dr_dy;
+  a.pc_per = vb->pc_per, a.pc_dy = vb->pc_dy;
+  a.midi = (vb->flags & MLB_VOICES_MIDI) ? 1 : 0;
   // 4 warps x {gate, pitch (, elapsed time)} row tiles
   const size_t smem = (size_t)4 * ((row_mask & 128u) ? 3 : 2) * kVoiceTileFloats * sizeof(float);
   CU_CHECK(cudaFuncSetAttribute((const void*)voice_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

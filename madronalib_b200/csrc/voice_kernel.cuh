@@ -3,7 +3,7 @@
 // glides source/DSP/MLDSPGens.h:433-590 (G).  One lane = one Voice; a launch runs n_blocks vectors:
 // beginProcess (drift), the vector's note events (sample-accurate gate / pitch glide / age), the
 // instantaneous controller values, endProcess (vector-accurate LinearGlides, bend and drift added to
-// pitch).  Input: one 68-byte mlb_voice_events record per voice and vector; output: up to 8 rows.
+// pitch).  Input: one 72-byte mlb_voice_events record per voice and vector; output: up to 8 rows.
 // Scalar state is SoA [word][V]; the six LinearGlide::mCurrVec rows are only touched while a glide
 // is moving (an idle LinearGlide's row equals its target in every lane of the row).
 #pragma once
@@ -11,13 +11,13 @@
 
 namespace mlb
 {
-enum VoiceGlide { VG_BEND = 0, VG_MOD, VG_X, VG_Y, VG_Z, VG_DRIFT, VG_COUNT };
+enum VoiceGlide { VG_BEND = 0, VG_MOD, VG_X, VG_Y, VG_Z, VG_DRIFT, VG_PRESSURE, VG_COUNT };
 enum VoiceState
 {
   VS_PG_CURR = 0, VS_PG_STEP, VS_PG_TARGET, VS_PG_REM, VS_PG_PER, VS_PG_DY,  // pitchGlide (G:517-590)
   VS_GL = 6,                       // 6 x {step, target, vectorsRemaining, spare}
   VS_VEL = VS_GL + 4 * VG_COUNT,   // currentVelocity, currentPitch, bend, mod, x, y, z
-  VS_PITCH, VS_BEND, VS_MOD, VS_X, VS_Y, VS_Z,
+  VS_PITCH, VS_BEND, VS_MOD, VS_X, VS_Y, VS_Z, VS_PRESSURE,
   VS_AGE, VS_AGE_STEP, VS_SEED, VS_DRIFT_COUNTER, VS_NEXT_DRIFT, VS_CUR_DRIFT,
   VS_COUNT
 };
@@ -35,6 +35,8 @@ struct VoiceArgs
   float sr;                    // Voice::sr (a double in the reference, set from this value)
   float gl_per, gl_dy;         // LinearGlide coefficients of bend/mod/x/y/z (sr * kGlideTimeSeconds)
   float dr_per, dr_dy;         // ... of pitchDriftGlide (sr * kDriftTimeSeconds)
+  float pc_per, pc_dy;         // ... of the channel-pressure SmoothedController (int(sr * kControllerGlideTimeSeconds))
+  int midi;                    // MLB_VOICES_MIDI: z row += smoothed channel pressure (processVector, E:432-447)
 };
 
 struct VoiceRegs
@@ -214,6 +216,7 @@ __global__ void __launch_bounds__(128) voice_bank_kernel(const VoiceArgs a)
   r.vel = u2f(st[VS_VEL]), r.pitch = u2f(st[VS_PITCH]);
   r.age = st[VS_AGE], r.age_step = st[VS_AGE_STEP];
   float cur[5] = {u2f(st[VS_BEND]), u2f(st[VS_MOD]), u2f(st[VS_X]), u2f(st[VS_Y]), u2f(st[VS_Z])};
+  float cur_pressure = u2f(st[VS_PRESSURE]);
   uint32_t seed = st[VS_SEED];
   int drift_counter = (int)st[VS_DRIFT_COUNTER], next_drift = (int)st[VS_NEXT_DRIFT];
   float cur_drift = u2f(st[VS_CUR_DRIFT]);
@@ -314,13 +317,22 @@ __global__ void __launch_bounds__(128) voice_bank_kernel(const VoiceArgs a)
     if (set_mask & MLB_SET_X) cur[2] = u2f(rec[14]);
     if (set_mask & MLB_SET_Y) cur[3] = u2f(rec[15]);
     if (set_mask & MLB_SET_Z) cur[4] = u2f(rec[16]);
+    if (set_mask & MLB_SET_PRESSURE) cur_pressure = u2f(rec[17]);
     // ---- endProcess, E:222-262 ----
     if (r.vel == 0.f) cur[4] = 0.f;
     GlidePlan gp[VG_COUNT];
 #pragma unroll
     for (int i = 0; i < VG_COUNT; ++i)
-      gp[i] = glide_plan(&st[VS_GL + 4 * i], i == VG_DRIFT ? cur_drift : cur[i], i == VG_DRIFT ? a.dr_per : a.gl_per,
-                         i == VG_DRIFT ? a.dr_dy : a.gl_dy, grow[i]);
+    {
+      if (i == VG_PRESSURE && !a.midi)
+      {
+        gp[i].mode = -1, gp[i].step = gp[i].target = gp[i].cv = 0.f;
+        continue;
+      }
+      gp[i] = glide_plan(&st[VS_GL + 4 * i], i == VG_DRIFT ? cur_drift : (i == VG_PRESSURE ? cur_pressure : cur[i]),
+                         i == VG_DRIFT ? a.dr_per : (i == VG_PRESSURE ? a.pc_per : a.gl_per),
+                         i == VG_DRIFT ? a.dr_dy : (i == VG_PRESSURE ? a.pc_dy : a.gl_dy), grow[i]);
+    }
     float* const planes = a.out + (size_t)t * MLB_VOICE_ROWS * V * MLB_BLOCK;
     const size_t plane_floats = V * MLB_BLOCK;
     // pitch += bendGlide * pitchBend * (1/12); pitch += driftSig * driftAmount * kDriftScale  (E:255-261)
@@ -361,10 +373,19 @@ __global__ void __launch_bounds__(128) voice_bank_kernel(const VoiceArgs a)
       {
         glide_run<true>(gp[gi], grow[gi], live, [&](int q, float4 y)
         { gate[4 * q] = y.x, gate[4 * q + 1] = y.y, gate[4 * q + 2] = y.z, gate[4 * q + 3] = y.w; });
+        if (gi == VG_Z && a.midi)  // voices[v].outputs.row(kZ) += controllers[128].output
+          glide_run<true>(gp[VG_PRESSURE], grow[VG_PRESSURE], live, [&](int q, float4 y)
+          {
+            gate[4 * q] = __fadd_rn(gate[4 * q], y.x), gate[4 * q + 1] = __fadd_rn(gate[4 * q + 1], y.y);
+            gate[4 * q + 2] = __fadd_rn(gate[4 * q + 2], y.z), gate[4 * q + 3] = __fadd_rn(gate[4 * q + 3], y.w);
+          });
         voice_store_tile(tiles, planes + (size_t)row * plane_floats, v0, a.V, lane);
       }
       else
+      {
         glide_run<false>(gp[gi], grow[gi], live, [](int, float4) {});  // the glide still advances
+        if (gi == VG_Z && a.midi) glide_run<false>(gp[VG_PRESSURE], grow[VG_PRESSURE], live, [](int, float4) {});
+      }
     }
   }
 #pragma unroll
@@ -373,6 +394,7 @@ __global__ void __launch_bounds__(128) voice_bank_kernel(const VoiceArgs a)
   st[VS_VEL] = f2u(r.vel), st[VS_PITCH] = f2u(r.pitch);
   st[VS_AGE] = r.age, st[VS_AGE_STEP] = r.age_step;
   st[VS_BEND] = f2u(cur[0]), st[VS_MOD] = f2u(cur[1]), st[VS_X] = f2u(cur[2]), st[VS_Y] = f2u(cur[3]), st[VS_Z] = f2u(cur[4]);
+  st[VS_PRESSURE] = f2u(cur_pressure);
   st[VS_SEED] = seed, st[VS_DRIFT_COUNTER] = (uint32_t)drift_counter, st[VS_NEXT_DRIFT] = (uint32_t)next_drift;
   st[VS_CUR_DRIFT] = f2u(cur_drift);
   if (live)

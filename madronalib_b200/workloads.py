@@ -437,8 +437,10 @@ def config_6(n_voices: int = 4096) -> Workload:
 VOICE_EVENTS_DTYPE = np.dtype([("n_events", "u1"), ("set_mask", "u1"), ("pad", "u1", (2,)),
                                ("time", "u1", (4,)), ("type", "u1", (4,)), ("flags", "u1", (4,)),
                                ("value1", "f4", (4,)), ("value2", "f4", (4,)),
-                               ("bend", "f4"), ("mod", "f4"), ("x", "f4"), ("y", "f4"), ("z", "f4")])
-assert VOICE_EVENTS_DTYPE.itemsize == 68  # struct mlb_voice_events (include/mlb200.h)
+                               ("bend", "f4"), ("mod", "f4"), ("x", "f4"), ("y", "f4"), ("z", "f4"),
+                               ("pressure", "f4")])
+assert VOICE_EVENTS_DTYPE.itemsize == 72  # struct mlb_voice_events (include/mlb200.h)
+VOICES_MIDI = 1
 
 EV_NOTE_ON, EV_NOTE_RETRIG, EV_NOTE_SUSTAIN, EV_NOTE_OFF = 1, 2, 3, 4
 EVF_GLIDE, EVF_RESET = 1, 2
@@ -481,8 +483,9 @@ def voice_events(n_voices: int, n_blocks: int, seed: int = 1, density: float = 0
                     r["value2"][k] = np.float32(rng.random() * 0.9 + 0.1)
                 r["n_events"] = n
             if rng.random() < ctl:
-                m = int(rng.integers(1, 32))
+                m = int(rng.integers(1, 64))
                 r["set_mask"] = m
+                r["pressure"] = np.float32(rng.random())
                 r["bend"], r["mod"] = np.float32(rng.random() * 2 - 1), np.float32(rng.random())
                 r["x"], r["y"], r["z"] = np.float32(rng.random()), np.float32(rng.random()), np.float32(rng.random())
     return ev

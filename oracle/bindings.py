@@ -204,17 +204,19 @@ class _VoiceBank:
     def __init__(self, lib, prefix):
         self.lib, self.p = lib, prefix
         getattr(lib, prefix + "bank_create").restype = _vp
-        getattr(lib, prefix + "bank_create").argtypes = [ctypes.c_int, ctypes.c_float, _vp, _vp, _vp, _vp]
+        getattr(lib, prefix + "bank_create").argtypes = [ctypes.c_int, ctypes.c_float, _vp, _vp, _vp, _vp,
+                                                         ctypes.c_uint]
         getattr(lib, prefix + "bank_destroy").argtypes = [_vp]
         getattr(lib, prefix + "bank_process").restype = ctypes.c_double
         getattr(lib, prefix + "bank_process").argtypes = [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int]
 
-    def run(self, sr, voice_index, glide_seconds, drift_amount, pitch_bend, events, splits=None, nthreads=1):
+    def run(self, sr, voice_index, glide_seconds, drift_amount, pitch_bend, events, splits=None, nthreads=1,
+            flags=0):
         """events [T][V] records -> (out [T][8][V][64], seconds)."""
         T, V = events.shape
         vi = np.ascontiguousarray(voice_index, np.int32)
         gs, da, pb = (np.ascontiguousarray(a, np.float32) for a in (glide_seconds, drift_amount, pitch_bend))
-        h = getattr(self.lib, self.p + "bank_create")(V, sr, _ptr(vi), _ptr(gs), _ptr(da), _ptr(pb))
+        h = getattr(self.lib, self.p + "bank_create")(V, sr, _ptr(vi), _ptr(gs), _ptr(da), _ptr(pb), flags)
         out = np.zeros((T, 8, V, BLOCK), np.float32)
         sec, t0 = 0.0, 0
         try:

@@ -1658,7 +1658,7 @@ static void lin_glide_set_value(lin_glide* g, float f) /* G:451-455 */
   g->st[2] = 0;
 }
 
-enum { GL_BEND = 0, GL_MOD, GL_X, GL_Y, GL_Z, GL_DRIFT, GL_COUNT };
+enum { GL_BEND = 0, GL_MOD, GL_X, GL_Y, GL_Z, GL_DRIFT, GL_PRESSURE, GL_COUNT };
 enum { ROW_PITCH = 0, ROW_GATE, ROW_VOICE, ROW_Z, ROW_X, ROW_Y, ROW_MOD, ROW_TIME }; /* .h:16-27 */
 
 typedef struct port_voice
@@ -1678,6 +1678,8 @@ typedef struct port_voice
   int pitchGlideTimeInSamples;
   int inhibit, recalc, voiceIndex;
   float pitchBendRange;
+  float pressure; /* SmoothedController::inputValue of controllers[128] */
+  int midi;
   float out[8][NB];
 } port_voice;
 
@@ -1776,6 +1778,8 @@ static void voice_begin(port_voice* v) /* E:90-124 */
     if (!v->inhibit) sa_glide_set_time(v, (float)v->pitchGlideTimeInSamples);
     for (int i = GL_BEND; i <= GL_Z; ++i) lin_glide_set_time(&v->g[i], (float)(v->sr * 0.02f));
     lin_glide_set_time(&v->g[GL_DRIFT], (float)(v->sr * 8.0f));
+    /* SmoothedController::process, E:274-285: int glideTimeInSamples = sr * kControllerGlideTimeSeconds */
+    lin_glide_set_time(&v->g[GL_PRESSURE], (float)(int)(v->sr * 0.02f));
     v->recalc = 0;
   }
   v->nextFrame = 0;
@@ -1838,6 +1842,12 @@ static void voice_end(port_voice* v) /* E:222-262 */
     p = p + (drift[n] * v->driftAmount) * 0.02f;
     v->out[ROW_PITCH][n] = p;
   }
+  if (v->midi) /* processVector, MIDI: z += smoothed channel pressure, E:432-447 */
+  {
+    float pr[NB];
+    gen_glide(v->g[GL_PRESSURE].st, v->g[GL_PRESSURE].c, v->pressure, v->g[GL_PRESSURE].curr, pr);
+    for (int n = 0; n < NB; ++n) v->out[ROW_Z][n] = v->out[ROW_Z][n] + pr[n];
+  }
 }
 
 typedef struct mlport_voice_bank
@@ -1847,12 +1857,16 @@ typedef struct mlport_voice_bank
 } mlport_voice_bank;
 
 mlport_voice_bank* mlport_bank_create(int V, float sr, const int32_t* voiceIndex, const float* glideSeconds,
-                                      const float* driftAmount, const float* pitchBend)
+                                      const float* driftAmount, const float* pitchBend, unsigned flags)
 {
   mlport_voice_bank* b = (mlport_voice_bank*)calloc(1, sizeof(*b));
   b->V = V;
   b->v = (port_voice*)calloc((size_t)V, sizeof(port_voice));
-  for (int i = 0; i < V; ++i) voice_init(&b->v[i], voiceIndex[i], sr, glideSeconds[i], driftAmount[i], pitchBend[i]);
+  for (int i = 0; i < V; ++i)
+  {
+    voice_init(&b->v[i], voiceIndex[i], sr, glideSeconds[i], driftAmount[i], pitchBend[i]);
+    b->v[i].midi = (flags & MLB_VOICES_MIDI) != 0;
+  }
   return b;
 }
 void mlport_bank_destroy(mlport_voice_bank* b)
@@ -1880,6 +1894,7 @@ double mlport_bank_process(mlport_voice_bank* b, int T, const mlb_voice_events* 
       if (r->set_mask & MLB_SET_X) v->x = r->x;
       if (r->set_mask & MLB_SET_Y) v->y = r->y;
       if (r->set_mask & MLB_SET_Z) v->z = r->z;
+      if (r->set_mask & MLB_SET_PRESSURE) v->pressure = r->pressure;
       voice_end(v);
       for (int row = 0; row < 8; ++row)
         memcpy(out + (((size_t)t * 8 + row) * V + i) * NB, v->out[row], sizeof(float) * NB);

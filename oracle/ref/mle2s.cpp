@@ -21,7 +21,9 @@ namespace
 struct VoiceBank
 {
   std::vector<EventsToSignals::Voice> voices;
+  std::vector<EventsToSignals::SmoothedController> pressure;  // controllers[128], one copy per voice
   std::vector<float> pitchBend;
+  bool midi{false};
 };
 }  // namespace
 
@@ -35,10 +37,13 @@ struct mle2s_bank
 // Voice() + reset() + setSampleRate + setPitchGlideInSeconds + setDriftAmount, exactly what
 // EventsToSignals' constructor and setters do for each of its voices (.cpp:283-300, 304-318, 858-873)
 mle2s_bank* mle2s_bank_create(int V, float sr, const int32_t* voiceIndex, const float* glideSeconds,
-                              const float* driftAmount, const float* pitchBend)
+                              const float* driftAmount, const float* pitchBend, unsigned flags)
 {
   auto* h = new mle2s_bank;
   h->b.voices.resize(V);
+  h->b.pressure.resize(V);
+  h->b.midi = (flags & MLB_VOICES_MIDI) != 0;
+  for (auto& c : h->b.pressure) c.setSampleRate(sr);
   h->b.pitchBend.assign(pitchBend, pitchBend + V);
   for (int v = 0; v < V; ++v)
   {
@@ -85,6 +90,14 @@ double mle2s_bank_process(mle2s_bank* h, int T, const mlb_voice_events* ev, floa
         if (r.set_mask & MLB_SET_Y) vc.currentY = r.y;
         if (r.set_mask & MLB_SET_Z) vc.currentZ = r.z;
         vc.endProcess(h->b.pitchBend[v]);
+        if (h->b.midi)
+        {
+          // processVector's tail in MIDI mode (.cpp:432-447): smooth the channel pressure, add it to z
+          auto& pc = h->b.pressure[v];
+          if (r.set_mask & MLB_SET_PRESSURE) pc.inputValue = r.pressure;
+          pc.process();
+          vc.outputs.row(kZ) += pc.output;
+        }
         for (int row = 0; row < kNumVoiceOutputRows; ++row)
           store(vc.outputs.constRow(row), out + (((size_t)t * kNumVoiceOutputRows + row) * V + v) * 64);
       }

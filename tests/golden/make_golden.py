@@ -135,7 +135,7 @@ def make_voices():
     from oracle.bindings import ref_voice_bank
     V, T, sr = 6, 40, 48000.0
     ev = wl.voice_events(V, T, seed=11)
-    out, _ = ref_voice_bank().run(sr, *wl.voice_bank_params(V), ev)
+    out, _ = ref_voice_bank().run(sr, *wl.voice_bank_params(V), ev, flags=wl.VOICES_MIDI)
     np.savez_compressed(os.path.join(HERE, "voices.npz"), events=ev.view(np.uint8), shape=np.array([T, V]),
                         sr=np.float32(sr), out=out)
     print("voices.npz", os.path.getsize(os.path.join(HERE, "voices.npz")), "bytes")

@@ -30,15 +30,15 @@ def ref_bank():
     return bindings.ref_voice_bank()
 
 
-@pytest.mark.parametrize("sr,seed", [(48000.0, 3), (44100.0, 4), (1000.0, 5)])
-def test_port_equals_reference_voice(ref_bank, port_bank, sr, seed):
+@pytest.mark.parametrize("sr,seed,flags", [(48000.0, 3, 0), (44100.0, 4, 1), (1000.0, 5, 1)])
+def test_port_equals_reference_voice(ref_bank, port_bank, sr, seed, flags):
     """sr = 1000 makes the 8-second drift interval 125 vectors long, so the drift redraw and the drift
     glide run inside the test."""
     V, T = 40, 300
     ev = wl.voice_events(V, T, seed=seed)
     prm = wl.voice_bank_params(V)
-    a, _ = ref_bank.run(sr, *prm, ev)
-    b, _ = port_bank.run(sr, *prm, ev, splits=(7, 93, 200))
+    a, _ = ref_bank.run(sr, *prm, ev, flags=flags)
+    b, _ = port_bank.run(sr, *prm, ev, splits=(7, 93, 200), flags=flags)
     for r, name in enumerate(ROWS):
         assert np.array_equal(a[:, r].view(np.uint32), b[:, r].view(np.uint32)), name
     assert np.abs(a[:, 0]).max() > 1 and a[:, 1].max() > 0.5 and a[:, 7].max() > 0
@@ -49,17 +49,18 @@ def test_port_matches_committed_golden(port_bank):
     ev = g["events"].view(wl.VOICE_EVENTS_DTYPE).reshape(g["shape"][0], g["shape"][1])
     V = ev.shape[1]
     assert np.array_equal(ev.view(np.uint8), wl.voice_events(V, ev.shape[0], seed=11).view(np.uint8))
-    b, _ = port_bank.run(float(g["sr"]), *wl.voice_bank_params(V), ev)
+    b, _ = port_bank.run(float(g["sr"]), *wl.voice_bank_params(V), ev, flags=wl.VOICES_MIDI)
     assert np.array_equal(b.view(np.uint32), g["out"].view(np.uint32))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("sr,V,T,seed", [(48000.0, 70, 120, 6), (1000.0, 33, 300, 7), (44100.0, 300, 40, 8)])
-def test_gpu_voice_bank_bit_exact(gpu, port_bank, sr, V, T, seed):
+@pytest.mark.parametrize("sr,V,T,seed,flags", [(48000.0, 70, 120, 6, 0), (1000.0, 33, 300, 7, 1),
+                                               (44100.0, 300, 40, 8, 1)])
+def test_gpu_voice_bank_bit_exact(gpu, port_bank, sr, V, T, seed, flags):
     ev = wl.voice_events(V, T, seed=seed)
     prm = wl.voice_bank_params(V)
-    want, _ = port_bank.run(sr, *prm, ev)
-    vb = gpu.VoiceBank(sr, *prm)
+    want, _ = port_bank.run(sr, *prm, ev, flags=flags)
+    vb = gpu.VoiceBank(sr, *prm, flags=flags)
     try:
         got = np.concatenate([vb.process_host(ev[:T // 3]), vb.process_host(ev[T // 3:])], axis=0)
     finally:
@@ -73,8 +74,8 @@ def test_gpu_voice_bank_matches_reference_golden_and_row_mask(gpu):
     g = np.load(GOLD)
     ev = g["events"].view(wl.VOICE_EVENTS_DTYPE).reshape(g["shape"][0], g["shape"][1])
     V = ev.shape[1]
-    vb = gpu.VoiceBank(float(g["sr"]), *wl.voice_bank_params(V))
-    vb2 = gpu.VoiceBank(float(g["sr"]), *wl.voice_bank_params(V))
+    vb = gpu.VoiceBank(float(g["sr"]), *wl.voice_bank_params(V), flags=wl.VOICES_MIDI)
+    vb2 = gpu.VoiceBank(float(g["sr"]), *wl.voice_bank_params(V), flags=wl.VOICES_MIDI)
     try:
         got = vb.process_host(ev)
         part = vb2.process_host(ev, row_mask=0b00000011)  # pitch and gate only
@@ -107,7 +108,7 @@ def test_voice_rows_feed_a_graph(gpu, port_bank, port):
     inp = np.ascontiguousarray(rows[:, 0:2])
     want, _, _ = port.run(g, V, T, inp, state, coef)
     dev = torch.device("cuda", 0)
-    d_ev = torch.from_numpy(ev.view(np.uint8).reshape(T, V, 68).copy()).to(dev)
+    d_ev = torch.from_numpy(ev.view(np.uint8).reshape(T, V, 72).copy()).to(dev)
     d_rows = torch.zeros((T, 8, V, 64), dtype=torch.float32, device=dev)
     vb = gpu.VoiceBank(48000.0, *prm)
     vg = gpu.VoiceGraph(g, V)

@@ -76,13 +76,13 @@ def main():
                               "frac_of_measured_hbm_peak": b / (ms * 1e-3) / 1e9 / peak}), flush=True)
         del x1, x2, x3, y
     if "voices" in only:
-        # K7: EventsToSignals::Voice x V.  Per voice-block: 68 B record in, selected rows out.
+        # K7: EventsToSignals::Voice x V.  Per voice-block: 72 B record in, selected rows out.
         V7, T7 = 65536, 64
         # a busy performance: a voice gets note events in 10 % of its vectors, controller moves in 5 %
         ev = wl.voice_events(256, T7, seed=2, density=0.10, ctl=0.05)
         ev = np.ascontiguousarray(np.tile(ev, (1, V7 // 256)))
         prm = wl.voice_bank_params(V7)
-        d_ev = torch.from_numpy(ev.view(np.uint8).reshape(T7, V7, 68)).to(dev)
+        d_ev = torch.from_numpy(ev.view(np.uint8).reshape(T7, V7, 72)).to(dev)
         d_rows = torch.empty((T7, 8, V7, 64), dtype=torch.float32, device=dev)
         sh = torch.cuda.current_stream().cuda_stream
         for mask, label in ((0x03, "pitch+gate"), (0xFF, "all 8 rows")):
@@ -96,7 +96,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / args.steps
-            b = (68.0 + 256.0 * bin(mask).count("1")) * V7 * T7
+            b = (72.0 + 256.0 * bin(mask).count("1")) * V7 * T7
             print(json.dumps({"config": "voices_" + label, "kernel": "voice_bank_kernel", "voices": V7, "blocks": T7,
                               "kernel_ms": ms, "voice_samples_per_s": V7 * T7 * 64 / (ms * 1e-3),
                               "algorithmic_bytes": b, "achieved_gbs": b / (ms * 1e-3) / 1e9,
