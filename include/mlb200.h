@@ -291,6 +291,24 @@ const char* mlb_last_error(void);  /* thread-local message of the last failing c
 int mlb_abi_version(void);
 long long mlb_kernel_launches(void); /* count of kernels this library launched (process-wide) */
 
+/* ---- block-rate resamplers -------------------------------------------------
+ * Upsampler(octaves) / Downsampler(octaves), source/DSP/MLDSPFilters.h:1316-1473: cascades of
+ * HalfBandFilters that change the number of blocks -- every input block of an Upsampler gives
+ * 2^octaves output blocks (write, then 2^octaves reads); a Downsampler gives one output block per
+ * 2^octaves input blocks (write returns true).  One object per voice, V voices per call.
+ * in [n_blocks_in][V][64]; out [n_blocks_out][V][64] with n_blocks_out = n_blocks_in << octaves (up)
+ * or the number of completed groups (down; the write counter carries over between calls and
+ * *n_blocks_out reports it).  octaves in [1, 4] (the reference leaves _numBuffers unset at 0). */
+typedef struct mlb_resampler mlb_resampler;
+enum { MLB_RESAMPLE_UP = 0, MLB_RESAMPLE_DOWN = 1 };
+int mlb_resampler_create(int direction, int octaves, int n_voices, mlb_resampler** out);
+int mlb_resampler_destroy(mlb_resampler* r);
+int mlb_resampler_clear(mlb_resampler* r);   /* Upsampler::clear / Downsampler::clear */
+int mlb_resampler_process_host(mlb_resampler* r, const float* in_host, float* out_host, int n_blocks_in,
+                               int* n_blocks_out);
+int mlb_resampler_process_device(mlb_resampler* r, const float* in_dev, float* out_dev, int n_blocks_in,
+                                 int* n_blocks_out, void* stream);
+
 /* ---- EventsToSignals::Voice bank ---------------------------------------
  * The step BEFORE the chain: the reference's EventsToSignals (source/app/MLEventsToSignals.h:43-236)
  * turns note / controller events into 8 control rows per voice.  Its event routing (voice

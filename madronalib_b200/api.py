@@ -68,6 +68,11 @@ def lib() -> ctypes.CDLL:
     L.mlb_graph_delay_bytes.restype = ctypes.c_size_t
     L.mlb_graph_delay_bytes.argtypes = [_vp]
     L.mlb_graph_reserve_sms.argtypes = [_vp, ctypes.c_int]
+    L.mlb_resampler_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]
+    L.mlb_resampler_destroy.argtypes = [_vp]
+    L.mlb_resampler_clear.argtypes = [_vp]
+    L.mlb_resampler_process_host.argtypes = [_vp, _vp, _vp, ctypes.c_int, _vp]
+    L.mlb_resampler_process_device.argtypes = [_vp, _vp, _vp, ctypes.c_int, _vp, _vp]
     L.mlb_voices_create.argtypes = [ctypes.c_int, _cf, _vp, _vp, _vp, _vp, ctypes.c_uint, _vp]
     L.mlb_voices_destroy.argtypes = [_vp]
     L.mlb_voices_process_host.argtypes = [_vp, _vp, _vp, ctypes.c_int, ctypes.c_uint]
@@ -302,3 +307,40 @@ class VoiceBank:
     def process_device(self, events, out, n_blocks: int, row_mask: int = 0xFF, stream: int = 0) -> None:
         _check(lib().mlb_voices_process_device(self._h, _ptr(events), _ptr(out), int(n_blocks), row_mask,
                                                stream or None))
+
+
+class ResamplerBank:
+    """Upsampler(octaves) / Downsampler(octaves) x V.  direction: 0 up, 1 down."""
+
+    UP, DOWN = 0, 1
+
+    def __init__(self, direction: int, octaves: int, n_voices: int):
+        self.direction, self.octaves, self.n_voices = direction, octaves, n_voices
+        h = ctypes.c_void_p()
+        _check(lib().mlb_resampler_create(direction, octaves, n_voices, ctypes.byref(h)))
+        self._h = h
+
+    def close(self) -> None:
+        if self._h:
+            lib().mlb_resampler_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def clear(self) -> None:
+        _check(lib().mlb_resampler_clear(self._h))
+
+    def process_host(self, x: np.ndarray) -> np.ndarray:
+        """x [T][V][64] -> [T << octaves][V][64] (up) or the completed groups (down)."""
+        x = np.ascontiguousarray(x, np.float32)
+        assert x.ndim == 3 and x.shape[1] == self.n_voices and x.shape[2] == BLOCK
+        T = x.shape[0]
+        cap = T << self.octaves if self.direction == self.UP else T
+        out = np.zeros((max(cap, 1), self.n_voices, BLOCK), np.float32)
+        n = ctypes.c_int(0)
+        _check(lib().mlb_resampler_process_host(self._h, x.ctypes.data, out.ctypes.data, T, ctypes.byref(n)))
+        return out[:n.value]

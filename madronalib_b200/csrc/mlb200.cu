@@ -22,6 +22,7 @@
 #include "chain_kernel.cuh"
 #include "fdn_kernel.cuh"
 #include "voice_kernel.cuh"
+#include "resample_kernel.cuh"
 #include "generic_kernel.cuh"
 
 using namespace mlb;
@@ -1737,6 +1738,117 @@ extern "C" int mlb_voices_process_host(mlb_voices* vb, const mlb_voice_events* e
           CU_CHECK(cudaMemcpyAsync(reinterpret_cast<char*>(out_host) + (t * MLB_VOICE_ROWS + r) * plane,
                                    reinterpret_cast<char*>(vb->d_out) + (t * MLB_VOICE_ROWS + r) * plane, plane,
                                    cudaMemcpyDeviceToHost, s));
+  CU_CHECK(cudaStreamSynchronize(s));
+  return MLB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Upsampler / Downsampler banks (K8, resample_kernel.cuh)
+
+struct mlb_resampler
+{
+  int dir = 0, oct = 0, V = 0;
+  unsigned counter = 0;
+  uint32_t* d_state = nullptr;
+  float* d_buf = nullptr;
+  float *d_in = nullptr, *d_out = nullptr;
+  size_t in_cap = 0, out_cap = 0;
+  cudaStream_t stream = nullptr;
+};
+
+extern "C" int mlb_resampler_destroy(mlb_resampler* r)
+{
+  if (!r) return MLB_OK;
+  cudaFree(r->d_state);
+  cudaFree(r->d_buf);
+  cudaFree(r->d_in);
+  cudaFree(r->d_out);
+  if (r->stream) cudaStreamDestroy(r->stream);
+  delete r;
+  return MLB_OK;
+}
+extern "C" int mlb_resampler_clear(mlb_resampler* r)
+{
+  if (!r) return fail(MLB_ERR_INVALID, "null resampler");
+  r->counter = 0;
+  CU_CHECK(cudaMemset(r->d_state, 0, (size_t)r->oct * 9 * r->V * 4));
+  if (r->d_buf) CU_CHECK(cudaMemset(r->d_buf, 0, (size_t)(2 * r->oct + 1) * r->V * MLB_BLOCK * 4));
+  return MLB_OK;
+}
+extern "C" int mlb_resampler_create(int direction, int octaves, int n_voices, mlb_resampler** out)
+{
+  if (!out) return fail(MLB_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if ((direction != MLB_RESAMPLE_UP && direction != MLB_RESAMPLE_DOWN) || octaves < 1 || octaves > 4 || n_voices <= 0)
+    return fail(MLB_ERR_INVALID, "bad argument (direction %d, octaves %d, voices %d)", direction, octaves, n_voices);
+  int rc = ensure_init();
+  if (rc != MLB_OK) return rc;
+  mlb_resampler* r = new mlb_resampler;
+  r->dir = direction, r->oct = octaves, r->V = n_voices;
+  bool ok = cudaMalloc(&r->d_state, (size_t)octaves * 9 * n_voices * 4) == cudaSuccess;
+  if (ok && direction == MLB_RESAMPLE_DOWN)
+    ok = cudaMalloc(&r->d_buf, (size_t)(2 * octaves + 1) * n_voices * MLB_BLOCK * 4) == cudaSuccess;
+  if (!ok)
+  {
+    mlb_resampler_destroy(r);
+    return fail(MLB_ERR_ALLOC, "cudaMalloc of resampler state failed");
+  }
+  cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking);
+  rc = mlb_resampler_clear(r);
+  if (rc != MLB_OK)
+  {
+    mlb_resampler_destroy(r);
+    return rc;
+  }
+  *out = r;
+  return MLB_OK;
+}
+static int resampler_out_blocks(const mlb_resampler* r, int n_in)
+{
+  if (r->dir == MLB_RESAMPLE_UP) return n_in << r->oct;
+  return (int)(((long long)r->counter + n_in) >> r->oct);
+}
+extern "C" int mlb_resampler_process_device(mlb_resampler* r, const float* in_dev, float* out_dev, int n_blocks_in,
+                                            int* n_blocks_out, void* stream)
+{
+  if (!r || !in_dev) return fail(MLB_ERR_INVALID, "null argument");
+  if (n_blocks_in <= 0) return fail(MLB_ERR_INVALID, "n_blocks_in must be positive");
+  const int n_out = resampler_out_blocks(r, n_blocks_in);
+  if (n_out > 0 && !out_dev) return fail(MLB_ERR_INVALID, "out is null");
+  ResampleArgs a;
+  a.in = in_dev, a.out = out_dev, a.state = r->d_state, a.buf = r->d_buf;
+  a.V = r->V, a.T = n_blocks_in, a.oct = r->oct, a.counter = r->counter;
+  const int grid = (r->V + 127) / 128;
+  if (r->dir == MLB_RESAMPLE_UP)
+    upsample_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  else
+  {
+    downsample_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    r->counter = (r->counter + (unsigned)n_blocks_in) & ((1u << r->oct) - 1u);
+  }
+  ++g_launches;
+  CU_CHECK(cudaGetLastError());
+  if (n_blocks_out) *n_blocks_out = n_out;
+  return MLB_OK;
+}
+extern "C" int mlb_resampler_process_host(mlb_resampler* r, const float* in_host, float* out_host, int n_blocks_in,
+                                          int* n_blocks_out)
+{
+  if (!r || !in_host) return fail(MLB_ERR_INVALID, "null argument");
+  if (n_blocks_in <= 0) return fail(MLB_ERR_INVALID, "n_blocks_in must be positive");
+  const size_t row = (size_t)r->V * MLB_BLOCK * 4;
+  const int n_out = resampler_out_blocks(r, n_blocks_in);
+  if (n_out > 0 && !out_host) return fail(MLB_ERR_INVALID, "out is null");
+  int rc = ensure_buf(&r->d_in, &r->in_cap, (size_t)n_blocks_in * row);
+  if (rc != MLB_OK) return rc;
+  rc = ensure_buf(&r->d_out, &r->out_cap, std::max<size_t>(1, (size_t)n_out) * row);
+  if (rc != MLB_OK) return rc;
+  cudaStream_t s = r->stream;
+  CU_CHECK(cudaMemcpyAsync(r->d_in, in_host, (size_t)n_blocks_in * row, cudaMemcpyHostToDevice, s));
+  rc = mlb_resampler_process_device(r, r->d_in, r->d_out, n_blocks_in, n_blocks_out, s);
+  if (rc != MLB_OK) return rc;
+  if (n_out > 0) CU_CHECK(cudaMemcpyAsync(out_host, r->d_out, (size_t)n_out * row, cudaMemcpyDeviceToHost, s));
   CU_CHECK(cudaStreamSynchronize(s));
   return MLB_OK;
 }

@@ -240,3 +240,32 @@ def port_voice_bank() -> _VoiceBank:
     if not os.path.exists(PORT_LIB):
         build("port")
     return _VoiceBank(ctypes.CDLL(PORT_LIB), "mlport_")
+
+
+class Resampler:
+    """Upsampler / Downsampler bank.  which = "ref" (the reference's own classes) or "port"."""
+
+    def __init__(self, which: str, direction: int, octaves: int, n_voices: int):
+        self.p = "mlref_" if which == "ref" else "mlport_"
+        self.lib = ctypes.CDLL(REF_LIB if which == "ref" else PORT_LIB)
+        f = getattr(self.lib, self.p + "resampler_create")
+        f.restype, f.argtypes = _vp, [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        getattr(self.lib, self.p + "resampler_destroy").argtypes = [_vp]
+        g = getattr(self.lib, self.p + "resampler_process")
+        g.restype, g.argtypes = ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]
+        self.dir, self.oct, self.V = direction, octaves, n_voices
+        self.h = f(direction, octaves, n_voices)
+
+    def process(self, x: np.ndarray) -> np.ndarray:
+        """x [T][V][64] -> [T_out][V][64]"""
+        x = np.ascontiguousarray(x, np.float32)
+        T = x.shape[0]
+        cap = T << self.oct if self.dir == 0 else T
+        out = np.zeros((max(cap, 1), self.V, BLOCK), np.float32)
+        n = getattr(self.lib, self.p + "resampler_process")(self.h, _ptr(x), _ptr(out), T)
+        return out[:n]
+
+    def close(self):
+        if self.h:
+            getattr(self.lib, self.p + "resampler_destroy")(self.h)
+            self.h = None

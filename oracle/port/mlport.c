@@ -1902,3 +1902,88 @@ double mlport_bank_process(mlport_voice_bank* b, int T, const mlb_voice_events* 
   }
   return 0.0;
 }
+
+/* ------------------------------------------------------------------ */
+/* Upsampler / Downsampler, F:1316-1473 (one per voice) */
+typedef struct mlport_resampler
+{
+  int dir, oct, V;
+  uint32_t* st;      /* [V][oct][9] HalfBandFilter states */
+  float* buf;        /* down: [V][2*oct+1][64]; up: [V][1<<oct][64] */
+  uint32_t* counter; /* down: [V] */
+} mlport_resampler;
+
+mlport_resampler* mlport_resampler_create(int dir, int oct, int V)
+{
+  mlport_resampler* r = (mlport_resampler*)calloc(1, sizeof(*r));
+  r->dir = dir, r->oct = oct, r->V = V;
+  const int nbuf = dir == MLB_RESAMPLE_UP ? (1 << oct) : 2 * oct + 1;
+  r->st = (uint32_t*)calloc((size_t)V * (size_t)oct * 9 + 1, 4);
+  r->buf = (float*)calloc((size_t)V * (size_t)nbuf * NB, 4);
+  r->counter = (uint32_t*)calloc((size_t)V, 4);
+  return r;
+}
+void mlport_resampler_destroy(mlport_resampler* r)
+{
+  if (!r) return;
+  free(r->st), free(r->buf), free(r->counter);
+  free(r);
+}
+int mlport_resampler_process(mlport_resampler* r, const float* in, float* out, int T)
+{
+  const int V = r->V, oct = r->oct, N = 1 << oct;
+  int produced = 0;
+  for (int v = 0; v < V; ++v)
+  {
+    uint32_t* st = r->st + (size_t)v * oct * 9;
+    if (r->dir == MLB_RESAMPLE_UP)
+    {
+      float* buf = r->buf + (size_t)v * N * NB; /* Upsampler::write, F:1428-1453 */
+      for (int t = 0; t < T; ++t)
+      {
+        memcpy(buf + (size_t)(N - 1) * NB, in + ((size_t)t * V + v) * NB, sizeof(float) * NB);
+        for (int j = 0; j < oct; ++j)
+        {
+          const int sourceBufs = 1 << j, destBufs = sourceBufs << 1;
+          const int srcStart = N - sourceBufs, destStart = N - destBufs;
+          for (int i = 0; i < sourceBufs; ++i)
+          {
+            float src[NB], d1[NB], d2[NB];
+            memcpy(src, buf + (size_t)(srcStart + i) * NB, sizeof(src));
+            hb_upsample(st + j * 9, src, d1, d2);
+            memcpy(buf + (size_t)(destStart + 2 * i) * NB, d1, sizeof(d1));
+            memcpy(buf + (size_t)(destStart + 2 * i + 1) * NB, d2, sizeof(d2));
+          }
+        }
+        for (int k = 0; k < N; ++k) /* the 2^octaves reads */
+          memcpy(out + (((size_t)t * N + k) * V + v) * NB, buf + (size_t)k * NB, sizeof(float) * NB);
+      }
+      produced = T * N;
+    }
+    else
+    {
+      float* buf = r->buf + (size_t)v * (2 * oct + 1) * NB; /* Downsampler::write, F:1347-1386 */
+      uint32_t counter = r->counter[v];
+      int n = 0;
+      for (int t = 0; t < T; ++t)
+      {
+        memcpy(buf + (size_t)(counter & 1u) * NB, in + ((size_t)t * V + v) * NB, sizeof(float) * NB);
+        uint32_t mask = 1;
+        for (int h = 0; h < oct; ++h)
+        {
+          if (!(counter & mask)) break;
+          mask <<= 1;
+          const int b1 = (counter & mask) != 0;
+          float d[NB];
+          hb_downsample(st + h * 9, buf + (size_t)(h * 2) * NB, buf + (size_t)(h * 2 + 1) * NB, d);
+          memcpy(buf + (size_t)(h * 2 + 2 + b1) * NB, d, sizeof(d));
+        }
+        counter = (counter + 1) & (uint32_t)(N - 1);
+        if (counter == 0) memcpy(out + ((size_t)(n++) * V + v) * NB, buf + (size_t)(2 * oct) * NB, sizeof(float) * NB);
+      }
+      r->counter[v] = counter;
+      produced = n;
+    }
+  }
+  return produced;
+}

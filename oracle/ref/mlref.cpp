@@ -1034,4 +1034,58 @@ void mlref_upsample2x_clip(int T, const float* in, float* out, float drive)
     store(y, out + (size_t)t * 64);
   }
 }
+
+// ---- Upsampler / Downsampler (MLDSPFilters.h:1316-1473), one object per voice ----
+struct mlref_resampler
+{
+  int dir, oct, V;
+  std::vector<Upsampler> up;
+  std::vector<Downsampler> down;
+};
+mlref_resampler* mlref_resampler_create(int dir, int oct, int V)
+{
+  auto* r = new mlref_resampler;
+  r->dir = dir, r->oct = oct, r->V = V;
+  for (int v = 0; v < V; ++v)
+    if (dir == MLB_RESAMPLE_UP)
+      r->up.emplace_back(oct);
+    else
+      r->down.emplace_back(oct);
+  return r;
+}
+void mlref_resampler_destroy(mlref_resampler* r) { delete r; }
+// in [T][V][64]; out [T_out][V][64]; returns T_out
+int mlref_resampler_process(mlref_resampler* r, const float* in, float* out, int T)
+{
+  const int V = r->V, N = 1 << r->oct;
+  int produced = 0;
+  if (r->dir == MLB_RESAMPLE_UP)
+  {
+    for (int t = 0; t < T; ++t)
+      for (int v = 0; v < V; ++v)
+      {
+        Upsampler& u = r->up[v];
+        if (r->oct == 0)
+        {
+          std::memcpy(out + ((size_t)t * V + v) * 64, in + ((size_t)t * V + v) * 64, 256);  // no buffers at 0 octaves
+          continue;
+        }
+        u.write(DSPVector(in + ((size_t)t * V + v) * 64));
+        for (int k = 0; k < N; ++k) store(u.read(), out + (((size_t)t * N + k) * V + v) * 64);
+      }
+    produced = T * N;
+  }
+  else
+  {
+    for (int v = 0; v < V; ++v)
+    {
+      int n = 0;
+      for (int t = 0; t < T; ++t)
+        if (r->down[v].write(DSPVector(in + ((size_t)t * V + v) * 64)))
+          store(r->down[v].read(), out + ((size_t)(n++) * V + v) * 64);
+      produced = n;
+    }
+  }
+  return produced;
+}
 }  // extern "C"

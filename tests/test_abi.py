@@ -65,6 +65,29 @@ def test_graph_layout_and_validation(L):
     assert L.mlb_graph_layout(bad, n, ctypes.byref(lay), None, None) == 1
 
 
+def test_validation_of_the_paired_and_feedback_nodes(L):
+    lay = Layout()
+    # FEEDBACK_WRITE must name an earlier FEEDBACK_READ
+    g = graph.GraphSpec()
+    x = g.input(0)
+    fb = g.feedback_read()
+    g.feedback_write(fb, g.node("ADD", x, fb))
+    assert L.mlb_graph_layout(g.c_nodes(), g.n_nodes, ctypes.byref(lay), None, None) == 0
+    bad = g.c_nodes()
+    bad[g.n_nodes - 1].iarg = 0  # the INPUT node
+    assert L.mlb_graph_layout(bad, g.n_nodes, ctypes.byref(lay), None, None) == 1
+    assert b"FEEDBACK_READ" in L.mlb_last_error()
+    # HALFBAND_UP_2 must read a HALFBAND_UP
+    h = graph.GraphSpec()
+    up = h.node("HALFBAND_UP", h.input(0))
+    h.output(h.node("HALFBAND_UP_2", up))
+    assert L.mlb_graph_layout(h.c_nodes(), h.n_nodes, ctypes.byref(lay), None, None) == 0
+    assert lay.n_state_words == 9
+    bad = h.c_nodes()
+    bad[2].inp[0] = 0
+    assert L.mlb_graph_layout(bad, h.n_nodes, ctypes.byref(lay), None, None) == 1
+
+
 def test_no_gpu_means_loud_failure_not_fallback(L):
     if api.device_count() > 0:
         pytest.skip("a GPU is visible here")
@@ -73,6 +96,9 @@ def test_no_gpu_means_loud_failure_not_fallback(L):
     assert e.value.code == 3 and "no CPU fallback" in str(e.value)
     with pytest.raises(api.MlbError):
         api.map_host("sin", np.zeros((1, 64), np.float32))
+    with pytest.raises(api.MlbError) as e:  # the Voice bank too
+        api.VoiceBank(48000.0, [1], [0.0], [0.0], [7.0])
+    assert e.value.code == 3
 
 
 def test_coefficient_design_matches_reference_golden(L):

@@ -33,6 +33,31 @@ def test_error_codes(gpu):
     with pytest.raises(gpu.MlbError):
         gf.process_host(f.inputs(1), 1)
     gf.close()
+    # delay nodes: the maxDelay coefficient sizes the ring and must be sane
+    d = wl.functor_case("allpass_frac", 8)
+    gd = gpu.VoiceGraph(d.spec, 8)
+    c = d.coef.copy()
+    c[2, 3] = np.float32(-5.0)
+    with pytest.raises(gpu.MlbError) as e:
+        gd.set_coefs(c)
+    assert e.value.code == 1 and "maxDelay" in str(e.value)
+    c[2, 3] = np.float32(np.nan)
+    with pytest.raises(gpu.MlbError):
+        gd.set_coefs(c)
+    gd.set_coefs(d.coef)  # a good upload still works afterwards
+    gd.process_host(d.inputs(2), 2)
+    gd.close()
+    # Voice bank argument checks
+    vb = gpu.VoiceBank(48000.0, [1, 2], [0.0, 0.0], [0.0, 0.0], [7.0, 7.0])
+    with pytest.raises(gpu.MlbError):
+        gpu._check(gpu.lib().mlb_voices_process_host(vb._h, None, None, 4, 0xFF))
+    ev = np.zeros((2, 2), wl.VOICE_EVENTS_DTYPE)
+    with pytest.raises(gpu.MlbError):
+        gpu._check(gpu.lib().mlb_voices_process_host(vb._h, ev.ctypes.data, None, 2, 0xFF))
+    assert gpu.lib().mlb_voices_process_host(vb._h, ev.ctypes.data, None, 2, 0) == 0  # no rows wanted: fine
+    vb.close()
+    with pytest.raises(gpu.MlbError):
+        gpu.VoiceBank(0.0, [1], [0.0], [0.0], [7.0])  # sample rate must be positive
 
 
 def test_denormals_are_honoured(gpu, port):
