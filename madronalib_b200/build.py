@@ -13,8 +13,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmlb200.so")
 SOURCES = ["mlb200.cu"]
-DEPS = ["mlb200.cu", "ops.cuh", "tma.cuh", "chain_kernel.cuh", "generic_kernel.cuh", "fdn_kernel.cuh",
-        os.path.join("..", "..", "include", "mlb200.h")]
+
+
+def _deps():
+    """Every source the library is built from: all of csrc/ plus the C ABI header."""
+    d = [f for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
+    return d + [os.path.join("..", "..", "include", "mlb200.h")]
+
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -31,7 +36,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in _deps())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -182,7 +182,7 @@ MLB_DEV void glide_run(const GlidePlan& g, float* row, bool live, Emit emit)
   }
 }
 
-__global__ void __launch_bounds__(128) voice_bank_kernel(const VoiceArgs a)
+__global__ void __launch_bounds__(128, 3) voice_bank_kernel(const VoiceArgs a)
 {
   extern __shared__ float voice_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -243,74 +243,140 @@ __global__ void __launch_bounds__(128) voice_bank_kernel(const VoiceArgs a)
     const uint32_t head = rec[0], times = rec[1], types = rec[2], flags = rec[3];
     const int n_events = min((int)(head & 0xFFu), MLB_VOICE_MAX_EVENTS);
     const unsigned set_mask = (head >> 8) & 0xFFu;
-    int k = 0;
-    bool pre_applied = false, retrig_frame_done = false;
-    bool active = true;
-    while (active)
+    // Decode the (at most 4) note events once.  ev_d = frame before which the event takes effect
+    // (retrigger: its gate-0 frame is ev_d - 1), ev_kind = 0 ignored / 1 on / 2 retrigger / 3 off.
+    int ev_d[MLB_VOICE_MAX_EVENTS], ev_kind[MLB_VOICE_MAX_EVENTS];
+    bool monotone = true;
     {
-      int emit_at = -1;
-      float emit_gate = 0.f;
-      while (k < n_events)
+      int nf = 0;  // nextFrameToProcess as the reference would see it
+#pragma unroll
+      for (int k = 0; k < MLB_VOICE_MAX_EVENTS; ++k)
       {
         int dest = (int)((times >> (8 * k)) & 0xFFu);
         dest = dest > MLB_BLOCK ? MLB_BLOCK : dest;
         const int type = (int)((types >> (8 * k)) & 0xFFu);
-        const unsigned fl = (flags >> (8 * k)) & 0xFFu;
-        const bool is_on = type == MLB_EV_NOTE_ON, is_rt = type == MLB_EV_NOTE_RETRIG, is_off = type == MLB_EV_NOTE_OFF;
-        if (!(is_on || is_rt || is_off))
+        int kind = type == MLB_EV_NOTE_ON ? 1 : type == MLB_EV_NOTE_RETRIG ? 2 : type == MLB_EV_NOTE_OFF ? 3 : 0;
+        if (k >= n_events) kind = 0;
+        if (kind == 2 && dest == 0) dest = 1;
+        const int bound = kind == 2 ? dest - 1 : dest;
+        if (kind != 0)
         {
-          ++k;  // kNoteSustain & co: writeNoteEvent does nothing
-          continue;
+          if (bound < nf) monotone = false;  // the reference would step back (e.g. a pedal-release note-off at frame 0)
+          nf = dest;
         }
-        if (!pre_applied)
+        ev_d[k] = dest, ev_kind[k] = kind;
+      }
+    }
+    if (__all_sync(0xffffffffu, monotone))
+    {
+      // Fast path: frames 0..63 are each emitted once, in order.  Event k's pre-actions (age reset, glide
+      // time) apply as soon as event k-1 is done, its post-actions (new pitch / velocity) before frame ev_d[k].
+      int k = 0;
+      auto advance = [&]()  // make the next non-ignored event current and apply its pre-actions
+      {
+        while (k < MLB_VOICE_MAX_EVENTS && ev_kind[k] == 0) ++k;
+        if (k < MLB_VOICE_MAX_EVENTS)
         {
-          if (is_on || is_rt)
+          const unsigned fl = (flags >> (8 * k)) & 0xFFu;
+          if (ev_kind[k] != 3)
           {
             if (fl & MLB_EVF_RESET) r.age = 0;
             r.age_step = 1;
           }
-          if (is_on) voice_set_glide_time(r, (fl & MLB_EVF_GLIDE) ? glide_samples : 0.f);
-          pre_applied = true;
+          if (ev_kind[k] == 1) voice_set_glide_time(r, (fl & MLB_EVF_GLIDE) ? glide_samples : 0.f);
         }
-        if (is_rt && dest == 0) dest = 1;
-        const int bound = is_rt ? dest - 1 : dest;  // writeOutputFrames(bound)
-        if (r.next_frame < bound)
-        {
-          emit_at = r.next_frame++;
-          emit_gate = r.vel;
-          break;
-        }
-        r.next_frame = bound;  // writeOutputFrames always ends with nextFrameToProcess = endFrame
-        if (is_rt && !retrig_frame_done)
-        {
-          retrig_frame_done = true;  // the retrigger frame: gate 0 at dest - 1 (E:183-189)
-          emit_at = dest - 1;
-          emit_gate = 0.f;
-          break;
-        }
-        // post-actions
-        if (is_off)
+      };
+      auto complete = [&]()  // post-actions of the current event, then move on
+      {
+        if (ev_kind[k] == 3)
           r.vel = 0.f;
         else
-        {
-          r.pitch = u2f(rec[4 + k]);
-          r.vel = u2f(rec[8 + k]);
-        }
-        if (is_rt) r.next_frame = dest;
+          r.pitch = u2f(rec[4 + k]), r.vel = u2f(rec[8 + k]);
         ++k;
-        pre_applied = false, retrig_frame_done = false;
-      }
-      if (emit_at < 0)
+        advance();
+      };
+      advance();
+#pragma unroll 1
+      for (int f = 0; f < MLB_BLOCK; ++f)
       {
-        if (r.next_frame < MLB_BLOCK)
-        {
-          emit_at = r.next_frame++;
-          emit_gate = r.vel;
-        }
-        else
-          active = false;
+        while (k < MLB_VOICE_MAX_EVENTS && ev_d[k] <= f) complete();
+        const bool retrig_frame = k < MLB_VOICE_MAX_EVENTS && ev_kind[k] == 2 && ev_d[k] - 1 == f;
+        voice_frame(r, a.sr, f, retrig_frame ? 0.f : r.vel, gate, pitch, tm, want_time);
       }
-      if (emit_at >= 0) voice_frame(r, a.sr, emit_at, emit_gate, gate, pitch, tm, want_time);
+      while (k < MLB_VOICE_MAX_EVENTS) complete();  // events at frame 64: only their value changes remain
+      r.next_frame = MLB_BLOCK;
+    }
+    else
+    {
+      int k = 0;
+      bool pre_applied = false, retrig_frame_done = false;
+      bool active = true;
+      while (active)
+      {
+        int emit_at = -1;
+        float emit_gate = 0.f;
+        while (k < n_events)
+        {
+          int dest = (int)((times >> (8 * k)) & 0xFFu);
+          dest = dest > MLB_BLOCK ? MLB_BLOCK : dest;
+          const int type = (int)((types >> (8 * k)) & 0xFFu);
+          const unsigned fl = (flags >> (8 * k)) & 0xFFu;
+          const bool is_on = type == MLB_EV_NOTE_ON, is_rt = type == MLB_EV_NOTE_RETRIG, is_off = type == MLB_EV_NOTE_OFF;
+          if (!(is_on || is_rt || is_off))
+          {
+            ++k;  // kNoteSustain & co: writeNoteEvent does nothing
+            continue;
+          }
+          if (!pre_applied)
+          {
+            if (is_on || is_rt)
+            {
+              if (fl & MLB_EVF_RESET) r.age = 0;
+              r.age_step = 1;
+            }
+            if (is_on) voice_set_glide_time(r, (fl & MLB_EVF_GLIDE) ? glide_samples : 0.f);
+            pre_applied = true;
+          }
+          if (is_rt && dest == 0) dest = 1;
+          const int bound = is_rt ? dest - 1 : dest;  // writeOutputFrames(bound)
+          if (r.next_frame < bound)
+          {
+            emit_at = r.next_frame++;
+            emit_gate = r.vel;
+            break;
+          }
+          r.next_frame = bound;  // writeOutputFrames always ends with nextFrameToProcess = endFrame
+          if (is_rt && !retrig_frame_done)
+          {
+            retrig_frame_done = true;  // the retrigger frame: gate 0 at dest - 1 (E:183-189)
+            emit_at = dest - 1;
+            emit_gate = 0.f;
+            break;
+          }
+          // post-actions
+          if (is_off)
+            r.vel = 0.f;
+          else
+          {
+            r.pitch = u2f(rec[4 + k]);
+            r.vel = u2f(rec[8 + k]);
+          }
+          if (is_rt) r.next_frame = dest;
+          ++k;
+          pre_applied = false, retrig_frame_done = false;
+        }
+        if (emit_at < 0)
+        {
+          if (r.next_frame < MLB_BLOCK)
+          {
+            emit_at = r.next_frame++;
+            emit_gate = r.vel;
+          }
+          else
+            active = false;
+        }
+        if (emit_at >= 0) voice_frame(r, a.sr, emit_at, emit_gate, gate, pitch, tm, want_time);
+      }
     }
     if (set_mask & MLB_SET_BEND) cur[0] = u2f(rec[12]);
     if (set_mask & MLB_SET_MOD) cur[1] = u2f(rec[13]);
