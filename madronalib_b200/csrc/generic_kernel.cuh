@@ -76,6 +76,7 @@ struct GenericArgs
   int fdn_ring_len;        // power of two
   long long blocks_done;   // IntegerDelay write index = (64 * blocks_done) & (ring_len - 1)
   float* dmem;             // delay memory of the section-8(f) functors (rows + rings)
+  int scratch_slot;        // first of 3 scratch row slots (graphs with Allpass<> / PitchbendableDelay nodes)
   const GStage* stages;
   int n_stages, n_chan;
   unsigned* sync;          // [0] ticket counter; [1 + s*n_groups + g] blocks finished by (stage s, group g)
@@ -147,18 +148,29 @@ template <int OP, bool EX>
 MLB_DEV void run_stateless_node(RowRef x, RowRef b, RowRef c, uint32_t out_addr)
 {
   constexpr int NIN = op_nin(OP);
-#pragma unroll 4
-  for (int q = 0; q < 16; ++q)
+  // the shared-memory accessors are ordered asm statements: load four quads of every operand first,
+  // then compute, then store, so that the LDS latencies overlap instead of adding up 16 times
+#pragma unroll 1
+  for (int q0 = 0; q0 < 16; q0 += 4)
   {
-    const float4 xi = x.get4(q);
-    const float4 bi = NIN >= 2 ? b.get4(q) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 ci = NIN >= 3 ? c.get4(q) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 y;
-    y.x = op_apply<EX>(OP, xi.x, bi.x, ci.x);
-    y.y = op_apply<EX>(OP, xi.y, bi.y, ci.y);
-    y.z = op_apply<EX>(OP, xi.z, bi.z, ci.z);
-    y.w = op_apply<EX>(OP, xi.w, bi.w, ci.w);
-    sts128(out_addr + (uint32_t)q * 16u, y);
+    float4 xi[4], bi[4], ci[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+    {
+      xi[j] = x.get4(q0 + j);
+      bi[j] = NIN >= 2 ? b.get4(q0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ci[j] = NIN >= 3 ? c.get4(q0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+    {
+      float4 y;
+      y.x = op_apply<EX>(OP, xi[j].x, bi[j].x, ci[j].x);
+      y.y = op_apply<EX>(OP, xi[j].y, bi[j].y, ci[j].y);
+      y.z = op_apply<EX>(OP, xi[j].z, bi[j].z, ci[j].z);
+      y.w = op_apply<EX>(OP, xi[j].w, bi[j].w, ci[j].w);
+      sts128(out_addr + (uint32_t)(q0 + j) * 16u, y);
+    }
   }
 }
 
@@ -528,17 +540,14 @@ MLB_DEV float pitchbend_fade(int n)
 // PitchbendableDelay::operator(), F:1097-1104: two allpass-interpolated taps of ONE ring (both
 // FractionalDelays receive the same input, so their rings are identical), delay 1 retuned at
 // n % 32 == 16, delay 2 at n % 32 == 0 (F:1053-1076), crossfaded by the triangle kvFade.
-// The caller has already stored the input block in the ring (after `prepare`).
 struct PitchbendPlan
 {
   uint32_t st[8];
   int32_t di1[3], di2[2];
   float ac1[3], ac2[2];
-  bool ahead;
 };
 template <bool EX, class DelayAt>
-MLB_DEV void pitchbend_prepare(PitchbendPlan& p, const RingRef& r, const GenericArgs& a, int st_off, int v,
-                               DelayAt DL)
+MLB_DEV void pitchbend_prepare(PitchbendPlan& p, const GenericArgs& a, int st_off, int v, DelayAt DL)
 {
 #pragma unroll
   for (int i = 0; i < 8; ++i) p.st[i] = a.state[(size_t)(st_off + i) * a.V + v];
@@ -547,43 +556,76 @@ MLB_DEV void pitchbend_prepare(PitchbendPlan& p, const RingRef& r, const Generic
   frac_split<EX>(DL(48), p.di1[2], p.ac1[2]);
   frac_split<EX>(DL(0), p.di2[0], p.ac2[0]);
   frac_split<EX>(DL(32), p.di2[1], p.ac2[1]);
-  p.ahead = delay_reads_ahead(p.di1[0], r.mask) | delay_reads_ahead(p.di1[1], r.mask) |
-            delay_reads_ahead(p.di1[2], r.mask) | delay_reads_ahead(p.di2[0], r.mask) |
-            delay_reads_ahead(p.di2[1], r.mask);
 }
-template <bool EX, class DST>
-MLB_DEV void pitchbend_run(PitchbendPlan& p, const RingRef& r, const OldBlock& old, const GenericArgs& a,
-                           int st_off, int v, DST dst)
+
+// cp.async: global -> shared without a register round trip; completion is per thread
+MLB_DEV void cp_async4(uint32_t smem_dst, const float* src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(src) : "memory");
+}
+MLB_DEV void cp_async16(uint32_t smem_dst, const float* src)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(src) : "memory");
+}
+MLB_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Tap sample n with delay d reads ring slot w + m, m = (n - d) & mask.  A slot of the CURRENT block
+// that the per-sample loop (F:898-912) has already written when it reads it (m <= n) holds this
+// block's input sample m; every other slot still holds what was in the ring before this block --
+// including slots of the current block the loop has NOT written yet (m > n, only for delays beyond the
+// ring).  So all "old" values can be fetched before the block is stored, all at once and asynchronously,
+// and the "new" ones are taken from the input row afterwards.
+MLB_DEV bool tap_is_new(uint32_t m, int n) { return m <= (uint32_t)n; }
+MLB_DEV void tap_prefetch16(const RingRef& r, int n0, int32_t d, uint32_t row)
+{
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+  {
+    const uint32_t m = ((uint32_t)(n0 + j) - (uint32_t)d) & r.mask;
+    if (!tap_is_new(m, n0 + j)) cp_async4(row + (uint32_t)(n0 + j) * 4u, r.p + ((r.w + m) & r.mask));
+  }
+}
+template <class InputAt>
+MLB_DEV float tap_value(const RingRef& r, int n, int32_t d, uint32_t row, InputAt X)
+{
+  const uint32_t m = ((uint32_t)n - (uint32_t)d) & r.mask;
+  return tap_is_new(m, n) ? X((int)m) : lds32(row + (uint32_t)n * 4u);
+}
+
+// both taps of a PitchbendableDelay into rows B and C (issue only; wait with cp_async_wait_all)
+MLB_DEV void pitchbend_prefetch(const PitchbendPlan& p, const RingRef& r, uint32_t B, uint32_t C)
+{
+  tap_prefetch16(r, 0, p.di1[0], B);
+  tap_prefetch16(r, 16, p.di1[1], B);
+  tap_prefetch16(r, 32, p.di1[1], B);
+  tap_prefetch16(r, 48, p.di1[2], B);
+  tap_prefetch16(r, 0, p.di2[0], C);
+  tap_prefetch16(r, 16, p.di2[0], C);
+  tap_prefetch16(r, 32, p.di2[1], C);
+  tap_prefetch16(r, 48, p.di2[1], C);
+}
+// the two allpass recurrences and the crossfade; X(m) = this block's input sample m
+template <bool EX, class DST, class InputAt>
+MLB_DEV void pitchbend_run(PitchbendPlan& p, const RingRef& r, uint32_t B, uint32_t C, InputAt X,
+                           const GenericArgs& a, int st_off, int v, DST dst)
 {
   float xb = u2f(p.st[0]), yb = u2f(p.st[1]), xc = u2f(p.st[4]), yc = u2f(p.st[5]);
-  float tb[16], tc[16];
-  ring_gather16(r, 0, p.di1[0], p.ahead, old, tb);
-  ring_gather16(r, 0, p.di2[0], p.ahead, old, tc);
 #pragma unroll
   for (int s = 0; s < 4; ++s)
   {
     // quarter s: tap 1 uses segment {0,1,1,2}[s], tap 2 segment {0,0,1,1}[s]
-    float nb[16], nc[16];
-    if (s < 3)
-    {
-      ring_gather16(r, 16 * s + 16, p.di1[s == 2 ? 2 : 1], p.ahead, old, nb);
-      ring_gather16(r, 16 * s + 16, p.di2[s >= 1 ? 1 : 0], p.ahead, old, nc);
-    }
-    const float cb = p.ac1[s == 0 ? 0 : (s == 3 ? 2 : 1)], cc = p.ac2[s >= 2 ? 1 : 0];
+    const int s1 = s == 0 ? 0 : (s == 3 ? 2 : 1), s2 = s >= 2 ? 1 : 0;
+    const float cb = p.ac1[s1], cc = p.ac2[s2];
     float y[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j)
     {
-      const float b = allpass1_tick<EX>(tb[j], xb, yb, cb);
-      const float c = allpass1_tick<EX>(tc[j], xc, yc, cc);
-      y[j] = A<EX>::add(b, A<EX>::mul(pitchbend_fade(16 * s + j), A<EX>::sub(c, b)));  // lerp, O:744
+      const int n = 16 * s + j;
+      const float b = allpass1_tick<EX>(tap_value(r, n, p.di1[s1], B, X), xb, yb, cb);
+      const float c = allpass1_tick<EX>(tap_value(r, n, p.di2[s2], C, X), xc, yc, cc);
+      y[j] = A<EX>::add(b, A<EX>::mul(pitchbend_fade(n), A<EX>::sub(c, b)));  // lerp, O:744
     }
     store16(dst, 16 * s, y);
-    if (s < 3)
-    {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) tb[j] = nb[j], tc[j] = nc[j];
-    }
   }
   p.st[0] = f2u(xb), p.st[1] = f2u(yb), p.st[2] = (uint32_t)p.di1[2], p.st[3] = f2u(p.ac1[2]);
   p.st[4] = f2u(xc), p.st[5] = f2u(yc), p.st[6] = (uint32_t)p.di2[1], p.st[7] = f2u(p.ac2[1]);
@@ -593,26 +635,26 @@ MLB_DEV void pitchbend_run(PitchbendPlan& p, const RingRef& r, const OldBlock& o
 
 template <bool EX>
 MLB_DEV void run_pitchbend_node(const GNode& nd, const GenericArgs& a, int v, bool live, int t, RowRef x,
-                                RowRef dl, uint32_t out_addr)
+                                RowRef dl, uint32_t out_addr, uint32_t B, uint32_t C)
 {
   if (!live) return;
   const RingRef r = node_ring<EX>(nd, a, v, t, a.coef[(size_t)nd.co_off * a.V + v]);
   PitchbendPlan p;
-  OldBlock old;
-  pitchbend_prepare<EX>(p, r, a, nd.st_off, v, [&](int n) { return dl.get(n); });
-  if (p.ahead) old.save(r);
+  pitchbend_prepare<EX>(p, a, nd.st_off, v, [&](int n) { return dl.get(n); });
+  pitchbend_prefetch(p, r, B, C);
+  cp_async_wait_all();
   ring_write_block(r, x);
-  pitchbend_run<EX>(p, r, old, a, nd.st_off, v, out_addr);
+  pitchbend_run<EX>(p, r, B, C, [&](int m) { return x.get(m); }, a, nd.st_off, v, out_addr);
 }
 
 // Allpass<DELAY>::operator(), F:1135-1153: din = x - vy1 * (-g); y = din * (-g) + vy1;
-// vy1 = DELAY(din).  din goes straight into the ring, y to the node's output row; vy1 is this
-// node's member row in delay memory.
+// vy1 = DELAY(din).  din goes into the ring (and stays in scratch row SA for taps that land in the
+// current block), y to the node's output row; vy1 is this node's member row in delay memory.
 // OP = ALLPASS_INT / ALLPASS_FRAC (coef mGain, delay, maxDelay) or ALLPASS_PB (coef mGain, maxDelay;
 // second operand = delay times)
 template <int OP, bool EX>
 MLB_DEV void run_allpass_node(const GNode& nd, const GenericArgs& a, int v, bool live, int t, RowRef x,
-                              RowRef dl, uint32_t out_addr)
+                              RowRef dl, uint32_t out_addr, uint32_t SA, uint32_t B, uint32_t C)
 {
   using ar = A<EX>;
   if (!live) return;
@@ -620,35 +662,35 @@ MLB_DEV void run_allpass_node(const GNode& nd, const GenericArgs& a, int v, bool
   const float blk = (float)MLB_BLOCK;
   const float md = a.coef[(size_t)(nd.co_off + (OP == MLB_OP_ALLPASS_PB ? 1 : 2)) * a.V + v];
   const RingRef r = node_ring<EX>(nd, a, v, t, ar::sub(md, blk));  // setMaxDelayInSamples(d - 64), F:1125-1128
+  // everything this node reads from HBM is requested up front: vy1 -> SA, the two tap streams -> B, C
+#pragma unroll
+  for (int q = 0; q < 16; ++q) cp_async16(SA + (uint32_t)q * 16u, vy1 + 4 * q);
   PitchbendPlan p;
-  OldBlock old;
   if constexpr (OP == MLB_OP_ALLPASS_PB)
   {
-    pitchbend_prepare<EX>(p, r, a, nd.st_off, v, [&](int n) { return ar::sub(dl.get(n), blk); });  // F:1151
-    if (p.ahead) old.save(r);
+    pitchbend_prepare<EX>(p, a, nd.st_off, v, [&](int n) { return ar::sub(dl.get(n), blk); });  // F:1151
+    pitchbend_prefetch(p, r, B, C);
   }
+  cp_async_wait_all();
   {
     const float g = -a.coef[(size_t)nd.co_off * a.V + v];
-    const float4* v4 = reinterpret_cast<const float4*>(vy1);
     float4* ring4 = reinterpret_cast<float4*>(r.p + r.w);
-    float4 vbuf[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) vbuf[q] = v4[q];
-#pragma unroll
+#pragma unroll 4
     for (int q = 0; q < 16; ++q)
     {
-      const float4 xi = x.get4(q), yi = vbuf[q];
+      const float4 xi = x.get4(q), yi = lds128(SA + (uint32_t)q * 16u);
       float4 din, y;
       din.x = ar::sub(xi.x, ar::mul(yi.x, g)), y.x = ar::add(ar::mul(din.x, g), yi.x);
       din.y = ar::sub(xi.y, ar::mul(yi.y, g)), y.y = ar::add(ar::mul(din.y, g), yi.y);
       din.z = ar::sub(xi.z, ar::mul(yi.z, g)), y.z = ar::add(ar::mul(din.z, g), yi.z);
       din.w = ar::sub(xi.w, ar::mul(yi.w, g)), y.w = ar::add(ar::mul(din.w, g), yi.w);
-      ring4[q] = din;  // IntegerDelay block write of the delay input
+      ring4[q] = din;                            // IntegerDelay block write of the delay input
+      sts128(SA + (uint32_t)q * 16u, din);       // ... kept for taps inside the current block
       sts128(out_addr + (uint32_t)q * 16u, y);
     }
   }
   if constexpr (OP == MLB_OP_ALLPASS_PB)
-    pitchbend_run<EX>(p, r, old, a, nd.st_off, v, vy1);
+    pitchbend_run<EX>(p, r, B, C, [&](int m) { return lds32(SA + (uint32_t)m * 4u); }, a, nd.st_off, v, vy1);
   else
   {
     const float d = ar::sub(a.coef[(size_t)(nd.co_off + 1) * a.V + v], blk);  // setDelayInSamples(d - 64), F:1123
@@ -835,6 +877,8 @@ __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
   const int v = v0 + lane;
   const bool live = v < a.V;
   const uint32_t rows = smem_u32(smem_raw) + (uint32_t)lane * kRowStride;  // [slot][lane][68]
+  // scratch rows of the allpass / pitch-bendable delay nodes: delay input, the two tap streams
+  const uint32_t sA = rows + (uint32_t)a.scratch_slot * kSlotBytes, sB = sA + kSlotBytes, sC = sB + kSlotBytes;
 
   for (int t = 0; t < a.T; ++t)
   {
@@ -944,10 +988,10 @@ __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
         case MLB_OP_INTEGER_DELAY_VAR: run_delay_var_node<EX, false>(nd, a, v, live, t, r[0], r[1], o); break;
         case MLB_OP_FRACTIONAL_DELAY: run_frac_delay_node<EX>(nd, a, v, live, t, r[0], o); break;
         case MLB_OP_FRACTIONAL_DELAY_VAR: run_delay_var_node<EX, true>(nd, a, v, live, t, r[0], r[1], o); break;
-        case MLB_OP_PITCHBEND_DELAY: run_pitchbend_node<EX>(nd, a, v, live, t, r[0], r[1], o); break;
-        case MLB_OP_ALLPASS_INT: run_allpass_node<MLB_OP_ALLPASS_INT, EX>(nd, a, v, live, t, r[0], r[1], o); break;
-        case MLB_OP_ALLPASS_FRAC: run_allpass_node<MLB_OP_ALLPASS_FRAC, EX>(nd, a, v, live, t, r[0], r[1], o); break;
-        case MLB_OP_ALLPASS_PB: run_allpass_node<MLB_OP_ALLPASS_PB, EX>(nd, a, v, live, t, r[0], r[1], o); break;
+        case MLB_OP_PITCHBEND_DELAY: run_pitchbend_node<EX>(nd, a, v, live, t, r[0], r[1], o, sB, sC); break;
+        case MLB_OP_ALLPASS_INT: run_allpass_node<MLB_OP_ALLPASS_INT, EX>(nd, a, v, live, t, r[0], r[1], o, sA, sB, sC); break;
+        case MLB_OP_ALLPASS_FRAC: run_allpass_node<MLB_OP_ALLPASS_FRAC, EX>(nd, a, v, live, t, r[0], r[1], o, sA, sB, sC); break;
+        case MLB_OP_ALLPASS_PB: run_allpass_node<MLB_OP_ALLPASS_PB, EX>(nd, a, v, live, t, r[0], r[1], o, sA, sB, sC); break;
         case MLB_OP_FEEDBACK_READ:
           if (live)
           {

@@ -443,6 +443,7 @@ struct mlb_graph
   // generic interpreter
   std::vector<GNode> gnodes;   // stage programs back to back (imports + nodes)
   GNode* d_gnodes = nullptr;
+  int scratch_slot = 0;
   std::vector<GStage> gstages;
   GStage* d_gstages = nullptr;
   int n_stages = 1, n_chan = 0;
@@ -884,6 +885,14 @@ static int build_generic(mlb_graph* g)
     max_slots = std::max(max_slots, n_slots);
   }
   g->n_slots = std::max(1, max_slots);
+  g->scratch_slot = g->n_slots;
+  for (int i = 0; i < n; ++i)
+    if (N[i].op == MLB_OP_PITCHBEND_DELAY || N[i].op == MLB_OP_ALLPASS_PB || N[i].op == MLB_OP_ALLPASS_INT ||
+        N[i].op == MLB_OP_ALLPASS_FRAC)
+    {
+      g->n_slots += 3;  // delay input + two tap streams (cp.async destinations)
+      break;
+    }
   g->n_stages = S;
   g->n_chan = n_chan;
   const size_t smem = (size_t)g->n_slots * kSlotBytes;
@@ -1396,6 +1405,7 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
     a.fdn_ring = g->d_ring, a.fdn_carry = g->d_carry, a.fdn_ring_len = g->ring_len;
     a.blocks_done = g->blocks_done;
     a.dmem = g->d_dmem;
+    a.scratch_slot = g->scratch_slot;
     a.stages = g->d_gstages;
     a.n_stages = g->n_stages;
     a.n_chan = g->n_chan;
