@@ -341,6 +341,7 @@ typedef struct mlb_voice_events {  /* what ONE Voice receives during ONE vector 
 #define MLB_VOICES_MIDI 1u  /* processVector's MIDI tail (.cpp:440-447): z row += the smoothed channel-pressure
                              * controller (SmoothedController, .cpp:274-285), one copy per voice */
 
+
 typedef struct mlb_voices mlb_voices;  /* opaque: V Voice objects on the device */
 
 /* V voices after Voice() + reset() + setSampleRate(sr) + setPitchGlideInSeconds + setDriftAmount
@@ -350,6 +351,11 @@ typedef struct mlb_voices mlb_voices;  /* opaque: V Voice objects on the device 
 int mlb_voices_create(int n_voices, float sample_rate, const int32_t* voice_index, const float* pitch_glide_seconds,
                       const float* drift_amount, const float* pitch_bend, unsigned flags, mlb_voices** out);
 int mlb_voices_destroy(mlb_voices* vb);
+/* processVector's MPE tail (.cpp:448-460): the pitch, x, y, z and mod rows of a channel voice get the rows of
+ * its instrument's main voice (voices[0]) added.  mlb_voices_set_main_voices names, per voice, the index of
+ * its main voice in the bank, or -1 (main voices themselves, or no MPE).  The rows involved must be in
+ * row_mask. */
+int mlb_voices_set_main_voices(mlb_voices* vb, const int32_t* main_voice);
 /* n_blocks vectors: beginProcess, the block's events, endProcess, for every voice.
  * events_host [n_blocks][V]; out_host [n_blocks][MLB_VOICE_ROWS][V][64] (rows whose bit is clear in
  * row_mask are not written; bit r = row r).  One kernel launch. */

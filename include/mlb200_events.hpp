@@ -9,8 +9,10 @@
 // writes the reference would have made.  tests/cpp/test_router.cpp checks it against the complete
 // reference EventsToSignals on MIDI phrases.
 //
-// Not covered: the MPE protocol (its main-voice rows are added across voices after generation,
-// .cpp:448-460) and controller 120 "all sound off" (it resets voices mid-vector, .cpp:748-755).
+// Both protocols of the reference are routed: "MIDI" (key = note number) and "MPE" (key = channel; the
+// main voice, voices[0], gets the channel-1 bend and pressure and its rows are added to the channel voices
+// by the bank, mlb_voices_set_main_voices).  Not covered: controller 120 "all sound off" (it resets voices
+// mid-vector, .cpp:748-755).
 #pragma once
 #include <algorithm>
 #include <array>
@@ -59,7 +61,13 @@ class VoiceRouter
   static constexpr int kMaxPhysicalKeys = 128;  // .h:49
   static constexpr int kChannelPressureControllerIdx = 128;
 
-  explicit VoiceRouter(int polyphony) { setPolyphony(polyphony); }
+  enum Protocol { kMIDI = 0, kMPE = 1 };
+
+  explicit VoiceRouter(int polyphony, Protocol protocol = kMIDI) : protocol_(protocol) { setPolyphony(polyphony); }
+
+  // records written per vector: MIDI: voices 1..polyphony -> records[0..polyphony-1];
+  // MPE: voices 0..polyphony (0 = the main voice) -> records[0..polyphony]
+  int recordCount() const { return protocol_ == kMPE ? polyphony_ + 1 : polyphony_; }
 
   // setPolyphony -> clear(), .cpp:312-331
   int setPolyphony(int n)
@@ -94,7 +102,7 @@ class VoiceRouter
   {
     overflow_ = 0;
     records_ = records;
-    for (int i = 0; i < polyphony_; ++i) std::memset(&records[i], 0, sizeof(mlb_voice_events));
+    for (int i = 0; i < recordCount(); ++i) std::memset(&records[i], 0, sizeof(mlb_voice_events));
     const int endTime = startTime + MLB_BLOCK;
     // the buffer is walked by index: a routed event never inserts into it
     for (size_t i = 0; i < events_.size(); ++i)
@@ -139,8 +147,8 @@ class VoiceRouter
         break;
       default: return;  // kNoteSustain and everything else: the voice ignores it
     }
-    if (v < 1 || v > polyphony_) return;  // voice 0 is the MPE main voice: no record in MIDI mode
-    mlb_voice_events& r = records_[v - 1];
+    if (v > polyphony_ || v < (protocol_ == kMPE ? 0 : 1)) return;  // MIDI: the main voice has no record
+    mlb_voice_events& r = record(v);
     if (r.n_events >= MLB_VOICE_MAX_EVENTS)
     {
       ++overflow_;
@@ -153,9 +161,11 @@ class VoiceRouter
     r.value1[k] = e.value1;
     r.value2[k] = e.value2;
   }
+  mlb_voice_events& record(int v) { return records_[protocol_ == kMPE ? v : v - 1]; }
+  int keyIndex(const Event& e) const { return protocol_ == kMPE ? e.channel : e.sourceIdx; }  // getKeyIndex, .cpp:20-43
   void setCurrent(int v, unsigned bit, float val)
   {
-    mlb_voice_events& r = records_[v - 1];
+    mlb_voice_events& r = record(v);
     r.set_mask |= (uint8_t)bit;
     switch (bit)
     {
@@ -208,15 +218,28 @@ class VoiceRouter
       case kNoteOn: noteOn(e); break;
       case kNoteOff: noteOff(e); break;
       case kController: controller(e); break;
-      case kPitchBend:
-        for (int v = 1; v < polyphony_ + 1; ++v) setCurrent(v, MLB_SET_BEND, e.value1);  // .cpp:706-711
+      case kPitchBend:  // .cpp:700-735
+        if (protocol_ == kMIDI)
+          for (int v = 1; v < polyphony_ + 1; ++v) setCurrent(v, MLB_SET_BEND, e.value1);
+        else if (e.channel == 1)
+          setCurrent(0, MLB_SET_BEND, e.value1);  // the main voice
+        else if (e.channel != 0)
+          for (int v = 1; v < polyphony_ + 1; ++v)
+            if (voices_[v].creatorKeyIdx == e.channel) setCurrent(v, MLB_SET_BEND, e.value1);
         break;
-      case kNotePressure:  // .cpp:673-683
-        for (int v = 1; v < polyphony_ + 1; ++v)
-          if (voices_[v].creatorKeyIdx == e.sourceIdx) setCurrent(v, MLB_SET_Z, e.value1);
+      case kNotePressure:  // .cpp:673-697; ignored in MPE mode
+        if (protocol_ == kMIDI)
+          for (int v = 1; v < polyphony_ + 1; ++v)
+            if (voices_[v].creatorKeyIdx == e.sourceIdx) setCurrent(v, MLB_SET_Z, e.value1);
         break;
-      case kChannelPressure:  // .cpp:634-640: controllers[128].inputValue, one smoother copy per voice
-        for (int v = 1; v < polyphony_ + 1; ++v) setCurrent(v, MLB_SET_PRESSURE, e.value1);
+      case kChannelPressure:  // .cpp:634-670
+        if (protocol_ == kMIDI)  // controllers[128].inputValue, one smoother copy per voice
+          for (int v = 1; v < polyphony_ + 1; ++v) setCurrent(v, MLB_SET_PRESSURE, e.value1);
+        else if (e.channel == 1)
+          setCurrent(0, MLB_SET_Z, e.value1);
+        else if (e.channel != 0)
+          for (int v = 1; v < polyphony_ + 1; ++v)
+            if (voices_[v].creatorKeyIdx == e.channel) setCurrent(v, MLB_SET_Z, e.value1);
         break;
       case kSustainPedal: sustainPedal(e); break;
       default: break;
@@ -224,7 +247,7 @@ class VoiceRouter
   }
   void noteOn(const Event& e)  // .cpp:513-553
   {
-    const int keyIdx = e.sourceIdx;  // getKeyIndex, MIDI, .cpp:20-28
+    const int keyIdx = keyIndex(e);
     KeyState& ks = keyStates_[keyIdx % kMaxPhysicalKeys];
     ks.state = KeyState::kOn;
     ks.noteOnIndex = currentNoteOnIndex_++;
@@ -249,7 +272,7 @@ class VoiceRouter
   }
   void noteOff(const Event& e)  // .cpp:555-628
   {
-    const int keyIdx = e.sourceIdx;
+    const int keyIdx = keyIndex(e);
     keyStates_[keyIdx % kMaxPhysicalKeys].state = sustainPedalActive_ ? KeyState::kSustained : KeyState::kOff;
     if (unison_)
     {
@@ -280,7 +303,7 @@ class VoiceRouter
   {
     const float val = e.value1;
     const int ctrl = std::min<int>(e.sourceIdx, kChannelPressureControllerIdx);
-    if (ctrl == kChannelPressureControllerIdx)  // controllers[ctrl].inputValue = val
+    if (ctrl == kChannelPressureControllerIdx && protocol_ == kMIDI)  // controllers[ctrl].inputValue = val
       for (int v = 1; v < polyphony_ + 1; ++v) setCurrent(v, MLB_SET_PRESSURE, val);
     if (ctrl == 120)
     {
@@ -298,6 +321,7 @@ class VoiceRouter
     else
       for (int v = 1; v < polyphony_ + 1; ++v)
       {
+        if (protocol_ == kMPE && voices_[v].creatorKeyIdx != e.channel) continue;  // MPE: only the channel's voices
         if (ctrl == voiceModCC_) setCurrent(v, MLB_SET_MOD, val);
         if (ctrl == 73)
           setCurrent(v, MLB_SET_X, val);
@@ -322,6 +346,7 @@ class VoiceRouter
   std::array<KeyState, kMaxPhysicalKeys> keyStates_{};
   std::vector<Event> events_;
   mlb_voice_events* records_{nullptr};
+  Protocol protocol_{kMIDI};
   int polyphony_{0};
   int lastFreeVoiceFound_{-1};
   int newestVoice_{-1};

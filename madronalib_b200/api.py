@@ -75,6 +75,7 @@ def lib() -> ctypes.CDLL:
     L.mlb_resampler_process_device.argtypes = [_vp, _vp, _vp, ctypes.c_int, _vp, _vp]
     L.mlb_voices_create.argtypes = [ctypes.c_int, _cf, _vp, _vp, _vp, _vp, ctypes.c_uint, _vp]
     L.mlb_voices_destroy.argtypes = [_vp]
+    L.mlb_voices_set_main_voices.argtypes = [_vp, _vp]
     L.mlb_voices_process_host.argtypes = [_vp, _vp, _vp, ctypes.c_int, ctypes.c_uint]
     L.mlb_voices_process_device.argtypes = [_vp, _vp, _vp, ctypes.c_int, ctypes.c_uint, _vp]
     L.mlb_graph_process_device.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, _vp]
@@ -294,6 +295,12 @@ class VoiceBank:
             self.close()
         except Exception:
             pass
+
+    def set_main_voices(self, main_voice) -> None:
+        """MPE: main_voice[v] = bank index of voice v's main voice, or -1."""
+        mv = np.ascontiguousarray(main_voice, np.int32)
+        assert mv.shape == (self.n_voices,)
+        _check(lib().mlb_voices_set_main_voices(self._h, mv.ctypes.data))
 
     def process_host(self, events: np.ndarray, row_mask: int = 0xFF) -> np.ndarray:
         """events: [T][V] array of workloads.VOICE_EVENTS_DTYPE; returns out [T][8][V][64] f32

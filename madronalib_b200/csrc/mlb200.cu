@@ -1614,6 +1614,7 @@ struct mlb_voices
   uint32_t* d_state = nullptr;
   float* d_coef = nullptr;
   float* d_grows = nullptr;
+  int32_t* d_main = nullptr;  // MPE: index of each voice's main voice, or -1
   mlb_voice_events* d_ev = nullptr;
   float* d_out = nullptr;
   size_t ev_cap = 0, out_cap = 0;
@@ -1626,6 +1627,7 @@ extern "C" int mlb_voices_destroy(mlb_voices* vb)
   cudaFree(vb->d_state);
   cudaFree(vb->d_coef);
   cudaFree(vb->d_grows);
+  cudaFree(vb->d_main);
   cudaFree(vb->d_ev);
   cudaFree(vb->d_out);
   if (vb->stream) cudaStreamDestroy(vb->stream);
@@ -1695,6 +1697,24 @@ extern "C" int mlb_voices_create(int n_voices, float sample_rate, const int32_t*
   return MLB_OK;
 }
 
+extern "C" int mlb_voices_set_main_voices(mlb_voices* vb, const int32_t* main_voice)
+{
+  if (!vb) return fail(MLB_ERR_INVALID, "null voice bank");
+  if (!main_voice)
+  {
+    cudaFree(vb->d_main);
+    vb->d_main = nullptr;
+    return MLB_OK;
+  }
+  for (int v = 0; v < vb->V; ++v)
+    if (main_voice[v] >= vb->V || (main_voice[v] >= 0 && main_voice[main_voice[v]] >= 0))
+      return fail(MLB_ERR_INVALID, "main_voice[%d] = %d is not a main voice of this bank", v, main_voice[v]);
+  if (!vb->d_main && cudaMalloc(&vb->d_main, (size_t)vb->V * 4) != cudaSuccess)
+    return fail(MLB_ERR_ALLOC, "cudaMalloc of main-voice table failed");
+  CU_CHECK(cudaMemcpy(vb->d_main, main_voice, (size_t)vb->V * 4, cudaMemcpyHostToDevice));
+  return MLB_OK;
+}
+
 extern "C" int mlb_voices_process_device(mlb_voices* vb, const mlb_voice_events* events_dev, float* out_dev,
                                          int n_blocks, unsigned row_mask, void* stream)
 {
@@ -1718,6 +1738,14 @@ extern "C" int mlb_voices_process_device(mlb_voices* vb, const mlb_voice_events*
   voice_bank_kernel<<<(vb->V + 127) / 128, 128, smem, (cudaStream_t)stream>>>(a);
   ++g_launches;
   CU_CHECK(cudaGetLastError());
+  if (vb->d_main && (a.row_mask & 0x79u))  // MPE: add the main voices' pitch / z / x / y / mod rows
+  {
+    const size_t n4 = (size_t)n_blocks * vb->V * 16;
+    const int grid = (int)std::min<size_t>((n4 + 255) / 256, (size_t)g_sm_count * 16);
+    voice_mpe_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out_dev, vb->d_main, vb->V, n_blocks, a.row_mask);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+  }
   return MLB_OK;
 }
 

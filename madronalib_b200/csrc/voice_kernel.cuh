@@ -470,4 +470,32 @@ __global__ void __launch_bounds__(128, 3) voice_bank_kernel(const VoiceArgs a)
   }
 }
 
+// processVector's MPE tail (E:448-460): pitch, x, y, z, mod rows += the rows of the instrument's main voice.
+// One thread per float4 of a (block, voice) row; planes [T][8][V][64].
+__global__ void __launch_bounds__(256) voice_mpe_add_kernel(float* out, const int32_t* main_voice, int V, int T,
+                                                             unsigned row_mask)
+{
+  const size_t n4 = (size_t)T * V * 16;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+  {
+    const int q = (int)(i & 15u);
+    const size_t tv = i >> 4;
+    const int v = (int)(tv % (size_t)V);
+    const size_t t = tv / (size_t)V;
+    const int m = main_voice[v];
+    if (m < 0) continue;
+    const int rows[5] = {0, 3, 4, 5, 6};  // kPitch, kZ, kX, kY, kMod
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+    {
+      if (!((row_mask >> rows[k]) & 1u)) continue;
+      float4* plane = reinterpret_cast<float4*>(out + (t * MLB_VOICE_ROWS + rows[k]) * (size_t)V * MLB_BLOCK);
+      float4 a = plane[(size_t)v * 16 + q];
+      const float4 b = plane[(size_t)m * 16 + q];
+      a.x = __fadd_rn(a.x, b.x), a.y = __fadd_rn(a.y, b.y), a.z = __fadd_rn(a.z, b.z), a.w = __fadd_rn(a.w, b.w);
+      plane[(size_t)v * 16 + q] = a;
+    }
+  }
+}
+
 }  // namespace mlb

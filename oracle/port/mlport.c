@@ -1854,7 +1854,17 @@ typedef struct mlport_voice_bank
 {
   int V;
   port_voice* v;
+  int32_t* main_voice; /* MPE: index of each voice's main voice or -1; NULL = none */
 } mlport_voice_bank;
+
+void mlport_bank_set_main_voices(mlport_voice_bank* b, const int32_t* main_voice)
+{
+  free(b->main_voice);
+  b->main_voice = NULL;
+  if (!main_voice) return;
+  b->main_voice = (int32_t*)malloc(sizeof(int32_t) * (size_t)b->V);
+  memcpy(b->main_voice, main_voice, sizeof(int32_t) * (size_t)b->V);
+}
 
 mlport_voice_bank* mlport_bank_create(int V, float sr, const int32_t* voiceIndex, const float* glideSeconds,
                                       const float* driftAmount, const float* pitchBend, unsigned flags)
@@ -1873,6 +1883,7 @@ void mlport_bank_destroy(mlport_voice_bank* b)
 {
   if (!b) return;
   free(b->v);
+  free(b->main_voice);
   free(b);
 }
 double mlport_bank_process(mlport_voice_bank* b, int T, const mlb_voice_events* ev, float* out, int nthreads)
@@ -1899,6 +1910,22 @@ double mlport_bank_process(mlport_voice_bank* b, int T, const mlb_voice_events* 
       for (int row = 0; row < 8; ++row)
         memcpy(out + (((size_t)t * 8 + row) * V + i) * NB, v->out[row], sizeof(float) * NB);
     }
+  }
+  if (b->main_voice) /* processVector, MPE: channel voices += the main voice's rows, E:448-460 */
+  {
+    static const int rows[5] = {ROW_PITCH, ROW_X, ROW_Y, ROW_Z, ROW_MOD};
+    for (int t = 0; t < T; ++t)
+      for (int i = 0; i < V; ++i)
+      {
+        const int m = b->main_voice[i];
+        if (m < 0) continue;
+        for (int k = 0; k < 5; ++k)
+        {
+          float* dst = out + (((size_t)t * 8 + rows[k]) * V + i) * NB;
+          const float* src = out + (((size_t)t * 8 + rows[k]) * V + m) * NB;
+          for (int n = 0; n < NB; ++n) dst[n] = dst[n] + src[n];
+        }
+      }
   }
   return 0.0;
 }

@@ -122,9 +122,10 @@ struct mle2s_full
 {
   EventsToSignals e2s;
 };
-mle2s_full* mle2s_full_create(float sr, int polyphony, float glideSeconds, float driftAmount, int unison)
+mle2s_full* mle2s_full_create(float sr, int polyphony, float glideSeconds, float driftAmount, int unison, int mpe)
 {
   auto* h = new mle2s_full;
+  if (mpe) h->e2s.setProtocol(Symbol("MPE"));
   h->e2s.setSampleRate(sr);
   h->e2s.setPolyphony(polyphony);
   h->e2s.setPitchGlideInSeconds(glideSeconds);
