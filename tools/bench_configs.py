@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--only", default="2,3,4,5,6,voices,map")
     ap.add_argument("--generic", action="store_true", help="force the graph interpreter kernel")
+    ap.add_argument("--cpu", action="store_true",
+                    help="also time the reference (oracle/_ref, all host threads) on config 6 and the Voice bank")
     args = ap.parse_args()
     only = set(args.only.split(","))
     api.init(0)
@@ -103,6 +105,32 @@ def main():
                               "frac_of_measured_hbm_peak": b / (ms * 1e-3) / 1e9 / peak}), flush=True)
             vb.close()
         del d_ev, d_rows
+    if args.cpu:
+        # the reference itself on this box's host cores (oracle/_ref; checker code, used here only as a baseline)
+        import time
+        from oracle import bindings as ob
+        cores = os.cpu_count() or 1
+        if "6" in only:
+            R = ob.RefOracle()
+            w = wl.config_6(1024)
+            inp = w.inputs(16)
+            best = 1e30
+            for _ in range(3):
+                t0 = time.perf_counter()
+                R.run(w.spec, w.n_voices, 16, inp, w.state, w.coef, want_out=True, nthreads=cores)
+                best = min(best, time.perf_counter() - t0)
+            print(json.dumps({"config": "config6_aaltoverb_reference_cpu", "threads": cores, "voices": 1024, "blocks": 16,
+                              "seconds": best, "voice_samples_per_s": 1024 * 16 * 64 / best,
+                              "note": "reference functors behind the graph interpreter of oracle/ref/mlref.cpp, "
+                                      "includes building the per-voice functor objects"}), flush=True)
+        if "voices" in only:
+            B = ob.ref_voice_bank()
+            Vc, Tc = 8192, 64
+            ev = np.ascontiguousarray(np.tile(wl.voice_events(256, Tc, seed=2, density=0.10, ctl=0.05), (1, Vc // 256)))
+            out, sec = B.run(48000.0, *wl.voice_bank_params(Vc), ev, nthreads=cores)
+            print(json.dumps({"config": "voices_reference_cpu", "threads": cores, "voices": Vc, "blocks": Tc,
+                              "seconds": sec, "voice_samples_per_s": Vc * Tc * 64 / sec,
+                              "note": "the reference's own EventsToSignals::Voice (oracle/_ref/libmle2s.so)"}), flush=True)
     for name, w, T, alg in cfgs:
         V = w.n_voices
         g = api.VoiceGraph(w.spec, V, api.FLAG_FORCE_GENERIC if args.generic else 0)
