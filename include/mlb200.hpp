@@ -174,6 +174,22 @@ class Graph
   Sig dcBlocker(Sig x) { return add(MLB_OP_DCBLOCKER, x); }
   Sig fdn8(Sig x) { return add(MLB_OP_FDN8, x); }
   Sig fdn8Right(Sig fdn) { return add(MLB_OP_FDN8_R, fdn); }
+  // the rest of the L2 functor set (MLDSPGens.h / MLDSPFilters.h), see MLB_OP_TABLE for state and coefficients
+  Sig adsr(Sig gate) { return add(MLB_OP_ADSR, gate); }
+  Sig peak(Sig x) { return add(MLB_OP_PEAK, x); }
+  Sig rms(Sig x) { return add(MLB_OP_RMS, x); }
+  Sig allpass1(Sig x) { return add(MLB_OP_ALLPASS1, x); }
+  Sig linearGlide(Sig target) { return add(MLB_OP_GLIDE, target); }
+  Sig integerDelay(Sig x) { return add(MLB_OP_INTEGER_DELAY, x); }
+  Sig fractionalDelay(Sig x) { return add(MLB_OP_FRACTIONAL_DELAY, x); }
+  Sig pitchbendableDelay(Sig x, Sig delayInSamples) { return add(MLB_OP_PITCHBEND_DELAY, x, delayInSamples); }
+  Sig allpassPitchbendable(Sig x, Sig delayInSamples) { return add(MLB_OP_ALLPASS_PB, x, delayInSamples); }
+  Sig halfBandUp(Sig x) { return add(MLB_OP_HALFBAND_UP, x); }          // upsampleFirstHalf
+  Sig halfBandUpSecond(Sig up) { return add(MLB_OP_HALFBAND_UP_2, up); } // upsampleSecondHalf of the same filter
+  Sig halfBandDown(Sig x1, Sig x2) { return add(MLB_OP_HALFBAND_DOWN, x1, x2); }
+  // a DSPVector member kept between processVector calls: read now, write at the end of the vector
+  Sig feedbackRead() { return add(MLB_OP_FEEDBACK_READ); }
+  Sig feedbackWrite(Sig reader, Sig x) { return add(MLB_OP_FEEDBACK_WRITE, x, -1, -1, reader); }
   Sig op1(int op, Sig x) { return add(op, x); }
   Sig op2(int op, Sig a, Sig b) { return add(op, a, b); }
   Sig op3(int op, Sig a, Sig b, Sig c) { return add(op, a, b, c); }
@@ -245,6 +261,51 @@ class DeviceBank
     DSPVectorArray<ROWS> y;
     process(x.getConstBuffer(), y.getBuffer(), nullptr, 1);
     return y;
+  }
+};
+
+// ---- VoiceBank: EventsToSignals::Voice x V on the GPU (mlb_voices_*; routing: mlb200_events.hpp) ----
+class VoiceBank
+{
+  mlb_voices* vb_ = nullptr;
+  int n_ = 0;
+
+ public:
+  VoiceBank(int nVoices, float sampleRate, const int32_t* voiceIndex, const float* pitchGlideSeconds,
+            const float* driftAmount, const float* pitchBendSemitones, unsigned flags = 0)
+      : n_(nVoices)
+  {
+    check(mlb_voices_create(nVoices, sampleRate, voiceIndex, pitchGlideSeconds, driftAmount, pitchBendSemitones, flags, &vb_));
+  }
+  ~VoiceBank() { mlb_voices_destroy(vb_); }
+  VoiceBank(const VoiceBank&) = delete;
+  VoiceBank& operator=(const VoiceBank&) = delete;
+  int voices() const { return n_; }
+  void setMainVoices(const int32_t* mainVoice) { check(mlb_voices_set_main_voices(vb_, mainVoice)); }
+  // events [nBlocks][voices]; out [nBlocks][MLB_VOICE_ROWS][voices][64]
+  void process(const mlb_voice_events* events, float* out, int nBlocks, unsigned rowMask = 0xFFu)
+  {
+    check(mlb_voices_process_host(vb_, events, out, nBlocks, rowMask));
+  }
+};
+
+// ---- Resampler: Upsampler(octaves) / Downsampler(octaves) x V on the GPU (mlb_resampler_*) ----
+class Resampler
+{
+  mlb_resampler* r_ = nullptr;
+
+ public:
+  Resampler(int direction, int octaves, int nVoices) { check(mlb_resampler_create(direction, octaves, nVoices, &r_)); }
+  ~Resampler() { mlb_resampler_destroy(r_); }
+  Resampler(const Resampler&) = delete;
+  Resampler& operator=(const Resampler&) = delete;
+  void clear() { check(mlb_resampler_clear(r_)); }
+  // in [nBlocksIn][voices][64] -> out; returns the number of output blocks
+  int process(const float* in, float* out, int nBlocksIn)
+  {
+    int n = 0;
+    check(mlb_resampler_process_host(r_, in, out, nBlocksIn, &n));
+    return n;
   }
 };
 

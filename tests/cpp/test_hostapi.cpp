@@ -200,6 +200,74 @@ int main()
     REQUIRE(mlb_kernel_launches() - launches0 <= 2 * callbacks);  // chain + mix-reduce per callback at most
   }
 
+  // ---- functor nodes through the C++ mirror: a 64-sample comb through a feedback edge ----
+  {
+    // y[t] = x[t] + 0.5 * y[t - 1 block]: an impulse comes back halved every 64 samples
+    Graph g;
+    const int x = g.input(0), k = g.param(), fb = g.feedbackRead();
+    const int y = g.add2(x, g.multiply(fb, k));
+    g.feedbackWrite(fb, y);
+    g.output(y);
+    DeviceBank bank(g, 2);
+    bank.setParam(k, 0, 0.5f);
+    bank.setParam(k, 1, 0.25f);
+    bank.commit();
+    std::vector<float> in(4 * 2 * 64, 0.f), out(4 * 2 * 64, 0.f);
+    in[0] = 1.f;       // voice 0, block 0, sample 0
+    in[64 + 3] = 1.f;  // voice 1, block 0, sample 3
+    bank.process(in.data(), out.data(), nullptr, 4);
+    REQUIRE(out[0] == 1.f && out[2 * 64] == 0.5f && out[4 * 64] == 0.25f && out[6 * 64] == 0.125f);
+    REQUIRE(out[64 + 3] == 1.f && out[3 * 64 + 3] == 0.25f && out[5 * 64 + 3] == 0.0625f);
+  }
+
+  // ---- Upsampler / Downsampler banks: 2x up then 2x down gives the input back, delayed and low-passed ----
+  {
+    const int V = 3, T = 24;
+    std::vector<float> x((size_t)T * V * 64), up((size_t)2 * T * V * 64), back((size_t)T * V * 64);
+    for (int t = 0; t < T; ++t)
+      for (int v = 0; v < V; ++v)
+        for (int n = 0; n < 64; ++n) x[((size_t)t * V + v) * 64 + n] = std::sin(0.05f * (float)(t * 64 + n) * (float)(v + 1));
+    Resampler upper(MLB_RESAMPLE_UP, 1, V), downer(MLB_RESAMPLE_DOWN, 1, V);
+    REQUIRE(upper.process(x.data(), up.data(), T) == 2 * T);
+    REQUIRE(downer.process(up.data(), back.data(), 2 * T) == T);
+    float best = 1e9f;
+    for (int d = 0; d < 10; ++d)  // group delay of the two half-band stages: a few samples
+    {
+      float err = 0.f;
+      for (int t = 2; t < T - 1; ++t)
+        for (int n = 0; n < 64; ++n)
+        {
+          const int i = t * 64 + n + d;
+          err = std::max(err, std::fabs(back[((size_t)(i / 64) * V + 0) * 64 + i % 64] - x[((size_t)t * V + 0) * 64 + n]));
+        }
+      best = std::min(best, err);
+    }
+    REQUIRE(best < 0.05f);
+  }
+
+  // ---- Voice bank: one note on at frame 10, velocity 0.8, no glide: gate and pitch step there ----
+  {
+    const int32_t idx[1] = {1};
+    const float glide[1] = {0.f}, drift[1] = {0.f}, bend[1] = {7.f};
+    VoiceBank vb(1, 48000.f, idx, glide, drift, bend);
+    mlb_voice_events ev[2];
+    std::memset(ev, 0, sizeof(ev));
+    ev[0].n_events = 1;
+    ev[0].time[0] = 10, ev[0].type[0] = MLB_EV_NOTE_ON, ev[0].flags[0] = MLB_EVF_RESET;
+    ev[0].value1[0] = 5.f, ev[0].value2[0] = 0.8f;
+    std::vector<float> rows((size_t)2 * MLB_VOICE_ROWS * 64);
+    vb.process(ev, rows.data(), 2);
+    const float* pitch = rows.data();            // row 0
+    const float* gate = rows.data() + 64;        // row 1
+    const float* voice = rows.data() + 2 * 64;   // row 2
+    const float* time1 = rows.data() + (size_t)(MLB_VOICE_ROWS + 7) * 64;  // elapsed time, second vector
+    REQUIRE(gate[9] == 0.f && gate[10] == 0.8f && gate[63] == 0.8f);
+    REQUIRE(pitch[9] == 0.f && pitch[11] == 5.f);
+    REQUIRE(voice[0] == 0.f);  // voiceIndex - 1
+    // the note-on's age reset and eventAgeStep = 1 precede the frames written before it (.cpp:152-165)
+    REQUIRE(std::fabs(time1[63] - 128.f / 48000.f) < 1e-7f);
+  }
+
   std::printf("%s: %d assertions, %d failed, %lld kernels launched\n", g_fail ? "FAILED" : "ALL PASSED", g_checks,
               g_fail, mlb_kernel_launches());
   return g_fail ? 1 : 0;
