@@ -479,7 +479,8 @@ struct mlb_graph
   float *d_in = nullptr, *d_out = nullptr, *d_mix = nullptr;
   size_t in_cap = 0, out_cap = 0, mix_cap = 0;
   cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
-  cudaEvent_t ev_up[16] = {}, ev_k[16] = {};
+  static constexpr int kMaxHostSlices = 64;
+  cudaEvent_t ev_up[kMaxHostSlices] = {}, ev_k[kMaxHostSlices] = {};
 
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
@@ -975,7 +976,7 @@ extern "C" int mlb_graph_create(const mlb_node* nodes, int n_nodes, const int32_
   cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&g->s_h2d, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&g->s_d2h, cudaStreamNonBlocking);
-  for (int i = 0; i < 16; ++i)
+  for (int i = 0; i < mlb_graph::kMaxHostSlices; ++i)
   {
     cudaEventCreateWithFlags(&g->ev_up[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&g->ev_k[i], cudaEventDisableTiming);
@@ -1034,7 +1035,7 @@ extern "C" int mlb_graph_destroy(mlb_graph* g)
   cudaFree(g->d_mix);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
-  for (int i = 0; i < 16; ++i)
+  for (int i = 0; i < mlb_graph::kMaxHostSlices; ++i)
   {
     if (g->ev_up[i]) cudaEventDestroy(g->ev_up[i]);
     if (g->ev_k[i]) cudaEventDestroy(g->ev_k[i]);
@@ -1473,7 +1474,7 @@ extern "C" int mlb_graph_process_host(mlb_graph* g, const float* in_host, float*
   const size_t pcie_bytes = in_bytes + (out_host ? out_bytes : 0);
   if (g->kind == KIND_FUSED && n_slices_env > 1 && g->V >= 4096 && pcie_bytes >= ((size_t)32 << 20))
   {
-    const int n_slices = std::min(n_slices_env, 16);
+    const int n_slices = std::min(n_slices_env, (int)mlb_graph::kMaxHostSlices);
     int per = (g->V + n_slices - 1) / n_slices;
     per = (per + 31) / 32 * 32;
     const size_t pitch = V * MLB_BLOCK * 4;
