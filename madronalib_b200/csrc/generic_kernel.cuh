@@ -352,12 +352,11 @@ MLB_DEV RingRef node_ring(const GNode& nd, const GenericArgs& a, int v, int t, f
   r.p = a.dmem + nd.ring_off + (size_t)v * nd.ring_stride;
   return r;
 }
-// The delay runners keep 16-sample batches in registers: 16 (or 32) independent ring loads are in
-// flight while the previous batch runs through the allpass recurrences; nothing is staged through
-// shared memory (its stores are asm volatile + memory clobber and would serialise the loads).
-//
-// A lane whose delay can reach into the block being written ("ahead", functors.cuh) keeps the
-// ring's oldest block in a per-thread local array -- rare, so it lives in local memory.
+// The fixed-delay and per-sample-delay runners keep 16-sample batches in registers (16 independent ring
+// loads in flight; the shared-memory stores are asm volatile + memory clobber and would serialise loads
+// issued between them).  In the per-sample-delay runners a lane whose delay can reach into the block being
+// written ("ahead", functors.cuh) keeps the ring's oldest block in a per-thread local array -- rare, so it
+// lives in local memory.  The pitch-bendable delay / allpass nodes use cp.async instead (below).
 struct OldBlock
 {
   float v[MLB_BLOCK];
@@ -379,26 +378,6 @@ MLB_DEV void ring_write_block(const RingRef& r, RowRef x)
   float4* d4 = reinterpret_cast<float4*>(r.p + r.w);
 #pragma unroll 4
   for (int q = 0; q < 16; ++q) d4[q] = x.get4(q);
-}
-// samples [n0, n0 + 16) of a tap with constant delay d, as IntegerDelay::processSample (F:898-912)
-// would read them given that the whole input block is already stored at w .. w+63
-MLB_DEV void ring_gather16(const RingRef& r, int n0, int32_t d, bool ahead, const OldBlock& old, float (&buf)[16])
-{
-#pragma unroll
-  for (int j = 0; j < 16; ++j)
-  {
-    const uint32_t m = ((uint32_t)(n0 + j) - (uint32_t)d) & r.mask;  // slot offset from w
-    buf[j] = r.p[(r.w + m) & r.mask];
-  }
-  if (ahead)
-  {
-#pragma unroll 1
-    for (int j = 0; j < 16; ++j)
-    {
-      const uint32_t m = ((uint32_t)(n0 + j) - (uint32_t)d) & r.mask;
-      if (m < (uint32_t)MLB_BLOCK && m > (uint32_t)(n0 + j)) buf[j] = old.v[m];
-    }
-  }
 }
 MLB_DEV void store16(uint32_t row, int n0, const float (&y)[16])
 {
