@@ -81,6 +81,8 @@ enum {
   X(TICK, 7, 1, 1, 0)           /* TickGen(freq), G:24-47; state: mOmega (f32)       */ \
   X(ONESHOT, 8, 1, 3, 0)        /* OneShotGen(freq), G:221-252; state mOmega32,mGate,*/ \
                                 /* mOmegaPrev; trigger() = set_state {0,1,0}         */ \
+  X(IMPULSE, 9, 1, 2, 0)        /* ImpulseGen(freq), G:53-103: a 17-tap Blackman-windowed sinc fired at every  */ \
+                                /* phase wrap; state _omega (f32), _outputCounter (i32; 0 at construction)     */ \
   /* SVF family ("Biquad" stand-ins) -- state: ic1eq, ic2eq */                           \
   X(LOPASS, 10, 1, 2, 3)        /* F:51-133   coef g0,g1,g2                          */ \
   X(HIPASS, 11, 1, 2, 4)        /* F:155-197  coef g0,g1,g2,k                        */ \
@@ -277,6 +279,8 @@ void mlb_coeffs_rms(float omega, float out2[2]);
 void mlb_coeffs_adsr(float a, float d, float s, float r, float sr, float out4[4]);
 float mlb_coeffs_allpass1(float d);
 void mlb_coeffs_glide(float time_in_samples, float out2[2]);
+/* ImpulseGen's table (its constructor, G:64-78): normalize(sinc(0.25) * blackman), 17 taps, host libm */
+void mlb_impulse_table(float out17[17]);
 void mlb_coeffs_sample_glide(float time_in_samples, float out2[2]);
 /* FDN<8>::setDelaysInSamples / setFilterCutoffs / mFeedbackGains, F:1171-1191.
  * Fills the 32 coef words of an FDN8 node for one voice:

@@ -91,6 +91,8 @@ def lib() -> ctypes.CDLL:
         fn.restype = None
     L.mlb_coeffs_dcblocker.argtypes = [_cf]
     L.mlb_coeffs_dcblocker.restype = _cf
+    L.mlb_impulse_table.argtypes = [_vp]
+    L.mlb_impulse_table.restype = None
     L.mlb_coeffs_allpass1.argtypes = [_cf]
     L.mlb_coeffs_allpass1.restype = _cf
     L.mlb_db_to_gain.argtypes = [_cf]
@@ -144,6 +146,13 @@ def coeffs(kind: str, *args: float) -> np.ndarray:
 
 def coeffs_dcblocker(omega: float) -> float:
     return float(lib().mlb_coeffs_dcblocker(omega))
+
+
+def impulse_table() -> np.ndarray:
+    """ImpulseGen's 17-tap table as the library builds it on the host."""
+    out = np.zeros(17, np.float32)
+    lib().mlb_impulse_table(out.ctypes.data)
+    return out
 
 
 def coeffs_allpass1(d: float) -> float:

@@ -27,6 +27,29 @@ MLB_DEV float oneshot_tick(float freq, uint32_t* st)
   return phase_to_phasor(om);  // unsignedIntToFloat(om) * 2^-32, both scalings exact
 }
 
+// ImpulseGen::operator(), G:82-102.  The 17-tap table (constructor, G:64-78) is built on the host with
+// the reference's libm calls (mlb_impulse_table) and uploaded once.  st: _omega, _outputCounter
+__constant__ float c_impulse_table[17];
+template <bool EX>
+MLB_DEV float impulse_tick(float freq, uint32_t* st)
+{
+  float om = A<EX>::add(u2f(st[0]), freq);
+  int32_t counter = (int32_t)st[1];
+  if (om > 1.0f)
+  {
+    om = A<EX>::sub(om, 1.0f);
+    counter = 0;
+  }
+  float y = 0.f;
+  if (counter < 17)
+  {
+    y = c_impulse_table[counter];
+    counter++;
+  }
+  st[0] = f2u(om), st[1] = (uint32_t)counter;
+  return y;
+}
+
 // tail of Peak / RMS, F:613,651: select(sqrtApprox(vy), 0, vy > 1e-20); sqrtApprox = x * rsqrt(x)
 // (a CPU-defined 12-bit approximation on the reference side -- compared with a tolerance)
 template <bool EX>

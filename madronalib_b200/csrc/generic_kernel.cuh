@@ -198,6 +198,7 @@ template <int OP, bool EX>
 MLB_DEV float functor_tick(float x, uint32_t* st, const float* co)
 {
   if constexpr (OP == MLB_OP_ONESHOT) return oneshot_tick<EX>(x, st);
+  if constexpr (OP == MLB_OP_IMPULSE) return impulse_tick<EX>(x, st);
   if constexpr (OP == MLB_OP_PEAK) return peak_tick<EX>(x, st, co);
   if constexpr (OP == MLB_OP_RMS) return rms_tick<EX>(x, st, co);
   if constexpr (OP == MLB_OP_ADSR) return adsr_tick<EX>(x, st, co);
@@ -955,6 +956,7 @@ __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
 #define MLB_FUN_CASE(OPN) \
   case OPN: run_functor_node<OPN, EX>(nd, a, v, live, r[0], o); break;
           MLB_FUN_CASE(MLB_OP_ONESHOT)
+          MLB_FUN_CASE(MLB_OP_IMPULSE)
           MLB_FUN_CASE(MLB_OP_PEAK)
           MLB_FUN_CASE(MLB_OP_RMS)
           MLB_FUN_CASE(MLB_OP_ADSR)

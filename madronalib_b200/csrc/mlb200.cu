@@ -246,6 +246,37 @@ extern "C" float mlb_coeffs_allpass1(float d)
   volatile float t2 = t1 * xm1;
   return t0 + t2;
 }
+// ImpulseGen's constructor, G:64-78 (window: MLDSPUtils.h:22-35; normalize / sum: MLDSPOps.h:995-1049 with
+// vecSumH's (v0 + v2) + (v1 + v3) order, MLDSPMathSSE.h:246-251)
+extern "C" void mlb_impulse_table(float t17[17])
+{
+  float row[MLB_BLOCK];
+  memset(row, 0, sizeof(row));
+  for (int i = 0; i < 17; ++i)
+  {
+    volatile float m = (1.f - 0.f) / (16.f - 0.f);
+    volatile float x = m * ((float)i - 0.f) + 0.f;
+    volatile float c1 = cosf(kTwoPiF * x);
+    volatile float c2 = cosf(2.f * kTwoPiF * x);
+    volatile float w0 = 0.5f * c1;
+    volatile float w1 = 0.42f - w0;
+    volatile float w2 = 0.08f * c2;
+    volatile float w = w1 + w2;
+    const int idx = i - 8;
+    volatile float pi_x = kTwoPiF * 0.25f * (float)idx;
+    volatile float sinc = (idx == 0) ? 1.f : sinf(pi_x) / pi_x;
+    row[i] = sinc * w;
+  }
+  volatile float sum = 0.f;
+  for (int n = 0; n < MLB_BLOCK; n += 4)
+  {
+    volatile float a = row[n] + row[n + 2];
+    volatile float b = row[n + 1] + row[n + 3];
+    volatile float ab = a + b;
+    sum = sum + ab;
+  }
+  for (int i = 0; i < 17; ++i) t17[i] = row[i] / sum;
+}
 extern "C" void mlb_coeffs_glide(float t, float o[2])
 {
   int n = (int)(t / (float)MLB_BLOCK);
@@ -322,6 +353,11 @@ extern "C" int mlb_init(int device)
     if (qres != cudaDriverEntryPointSuccess || !fn)
       return fail(MLB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     g_encode = (EncodeTiledFn)fn;
+  }
+  {
+    float table[17];
+    mlb_impulse_table(table);  // ImpulseGen's windowed sinc, host libm
+    CU_CHECK(cudaMemcpyToSymbol(c_impulse_table, table, sizeof(table)));
   }
   g_device = device;
   return MLB_OK;

@@ -219,7 +219,13 @@ def functor_case(name: str, n_voices: int = 40) -> Workload:
             return np.ascontiguousarray(d.reshape(V, T, BLOCK).transpose(1, 0, 2))[:, None]
         return fn
 
-    if name == "oneshot":
+    if name == "impulse":
+        y = g.node("IMPULSE", g.input(0))
+        g.output(y)
+        coef, state = g.new_coefs(V), g.new_state(V)
+        fn = lambda T, t0: np.broadcast_to(((1.0 + vv) / np.float32(150.0)).astype(np.float32)[None, None, :, None],
+                                           (T, 1, V, BLOCK)).copy()
+    elif name == "oneshot":
         y = g.node("ONESHOT", g.input(0))
         g.output(y)
         coef, state = g.new_coefs(V), g.new_state(V)
@@ -381,7 +387,7 @@ def functor_case(name: str, n_voices: int = 40) -> Workload:
     return w
 
 
-FUNCTOR_CASES = ("oneshot", "peak", "rms", "adsr", "allpass1", "glide", "interpolator1", "sample_glide",
+FUNCTOR_CASES = ("impulse", "oneshot", "peak", "rms", "adsr", "allpass1", "glide", "interpolator1", "sample_glide",
                  "integer_delay", "integer_delay_var", "fractional_delay", "fractional_delay_var",
                  "pitchbend_delay", "allpass_int", "allpass_frac", "allpass_pb", "feedback",
                  "halfband_up", "halfband_roundtrip", "upsample2x_clip", "tempo_lock")

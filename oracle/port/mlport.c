@@ -30,6 +30,7 @@
 #include "mlb200.h"
 
 #define NB MLB_BLOCK
+#define K_TWO_PI_F 6.2831853071795864769252867f /* ml::kTwoPi, S:23 */
 
 static inline uint32_t f2u(float f)
 {
@@ -687,6 +688,58 @@ static void gen_oneshot(uint32_t* st, const float* freq, float* y)
     y[n] = unsigned_to_float(om) * (1.0f / 4294967296.0f);
   }
   st[0] = om, st[1] = gate, st[2] = prev;
+}
+
+/* ImpulseGen, G:53-103.  Table (constructor, G:64-78): blackman window over 17 points
+ * (makeWindow U:22-26 with projections::linear({0,16},{0,1}), dspwindows::blackman U:34-35), times
+ * sinc(2 pi 0.25 (i - 8)), normalised by the row sum (normalize O:1040-1049, sum O:995-1005 with
+ * vecSumH M:246-251: (v0 + v2) + (v1 + v3) per SIMD vector, vectors accumulated in order). */
+void mlport_impulse_table(float* t17)
+{
+  float row[NB];
+  memset(row, 0, sizeof(row));
+  for (int i = 0; i < 17; ++i)
+  {
+    const float m = (1.f - 0.f) / (16.f - 0.f);
+    const float x = m * ((float)i - 0.f) + 0.f;
+    const float w = 0.42f - 0.5f * cosf(K_TWO_PI_F * x) + 0.08f * cosf(2.f * K_TWO_PI_F * x);
+    const int idx = i - 8;
+    const float pi_x = K_TWO_PI_F * 0.25f * idx;
+    const float sinc = (idx == 0) ? 1.f : sinf(pi_x) / pi_x;
+    row[i] = sinc * w;
+  }
+  float sum = 0;
+  for (int n = 0; n < NB; n += 4) sum += (row[n] + row[n + 2]) + (row[n + 1] + row[n + 3]);
+  for (int i = 0; i < 17; ++i) t17[i] = row[i] / sum;
+}
+/* ImpulseGen::operator(), G:82-102.  st: _omega, _outputCounter */
+static void gen_impulse(uint32_t* st, const float* freq, float* y)
+{
+  static float table[17];
+  static int have = 0;
+  if (!have)
+  {
+    mlport_impulse_table(table);
+    have = 1;
+  }
+  float om = u2f(st[0]);
+  int32_t counter = (int32_t)st[1];
+  for (int n = 0; n < NB; ++n)
+  {
+    y[n] = 0.f;
+    om += freq[n];
+    if (om > 1.0f)
+    {
+      om -= 1.0f;
+      counter = 0;
+    }
+    if (counter < 17)
+    {
+      y[n] = table[counter];
+      counter++;
+    }
+  }
+  st[0] = f2u(om), st[1] = (uint32_t)counter;
 }
 
 /* tail shared by Peak and RMS, F:613,651: select(sqrtApprox(vy), 0, vy > 1e-20) */
@@ -1382,6 +1435,7 @@ static void run_voices(mlport_graph* g, const float* in, float* out, int T, int 
           case MLB_OP_FDN8: fdn8_process(&g->fdn[i][v], st, co, a, y, rows2[i]); break;
           case MLB_OP_FDN8_R: memcpy(y, rows2[nd->in[0]], sizeof(float) * NB); break;
           case MLB_OP_ONESHOT: gen_oneshot(st, a, y); break;
+          case MLB_OP_IMPULSE: gen_impulse(st, a, y); break;
           case MLB_OP_PEAK: flt_peak(st, co, a, y); break;
           case MLB_OP_RMS: flt_rms(st, co, a, y); break;
           case MLB_OP_ADSR: flt_adsr(st, co, a, y); break;

@@ -262,6 +262,13 @@ struct POneShot : Proc
   void storeState(uint32_t* s) const override { s[0] = g.mOmega32, s[1] = g.mGate, s[2] = g.mOmegaPrev; }
   DSPVector run(const DSPVector* const* in, DSPVector*) override { return g(*in[0]); }
 };
+struct PImpulse : Proc
+{
+  ImpulseGen g;
+  void loadState(const uint32_t* s) override { g._omega = u2f(s[0]), g._outputCounter = (int)s[1]; }
+  void storeState(uint32_t* s) const override { s[0] = f2u(g._omega), s[1] = (uint32_t)g._outputCounter; }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return g(*in[0]); }
+};
 struct PPeak : Proc
 {
   Peak f;
@@ -600,6 +607,7 @@ Proc* makeProc(int op)
     case MLB_OP_INTEGRATOR: return new PIntegrator;
     case MLB_OP_FDN8: return new PFDN8;
     case MLB_OP_ONESHOT: return new POneShot;
+    case MLB_OP_IMPULSE: return new PImpulse;
     case MLB_OP_PEAK: return new PPeak;
     case MLB_OP_RMS: return new PRMS;
     case MLB_OP_ADSR: return new PADSR;
@@ -872,6 +880,11 @@ void mlref_coeffs_adsr(float a, float d, float s, float r, float sr, float* o)
   o[0] = c.ka, o[1] = c.kd, o[2] = c.s, o[3] = c.kr;
 }
 float mlref_coeffs_allpass1(float d) { return Allpass1::makeCoeffs(d); }
+void mlref_impulse_table(float* o)
+{
+  ImpulseGen g;
+  for (int i = 0; i < 17; ++i) o[i] = g._table[i];
+}
 void mlref_coeffs_glide(float timeInSamples, float* o)
 {
   LinearGlide g;

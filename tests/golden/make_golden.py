@@ -125,6 +125,10 @@ def make_functors(R):
     out["coef_rms"] = R.coeffs("rms", 0.002)
     out["coef_glide"] = R.coeffs("glide", 4800.0)
     out["coef_sample_glide"] = R.coeffs("sample_glide", 77.7)
+    import ctypes
+    tab = np.zeros(17, np.float32)
+    R.lib.mlref_impulse_table(tab.ctypes.data_as(ctypes.c_void_p))
+    out["impulse_table"] = tab
     out["coef_allpass1"] = np.array([R.coeffs_allpass1(float(d)) for d in np.linspace(0.618, 1.618, 16, dtype=np.float32)],
                                     np.float32)
     np.savez_compressed(os.path.join(HERE, "functors.npz"), **out)
