@@ -205,6 +205,14 @@ enum {
   X(HALFBAND_UP, 110, 1, 9, 0)                                                           \
   X(HALFBAND_UP_2, 111, 1, 0, 0)                                                         \
   X(HALFBAND_DOWN, 112, 2, 9, 0)                                                         \
+  /* Downsample2xFunction(fn, x) (MLDSPFunctional.h:166-223) with a stateless fn, as a node pair around  */ \
+  /* fn's nodes: DOWN2X_IN(x) yields downsample(mInputBuffer, x) on every second block (phase 1) and   */ \
+  /* stores x on the others; DOWN2X_OUT(fn(...)) returns upsampleFirstHalf on phase-1 blocks and the   */ \
+  /* buffered second half on the others.  State: HalfBandFilter (9 words) + mPhase; one member row     */ \
+  /* each (mInputBuffer / mOutputBuffer).  fn's nodes run on every block; their rows on phase-0 blocks */ \
+  /* are never used.                                                                                   */ \
+  X(DOWN2X_IN, 114, 1, 10, 0)                                                            \
+  X(DOWN2X_OUT, 115, 1, 10, 0)                                                           \
   /* TempoLock(x, dydx, isr), F:1478-1579: in0 = input phasor row, in1 = ratio (sample   */ \
   /* 0 of the row); state _omega, _x1v (fresh: _omega = -1); coef isr                    */ \
   X(TEMPO_LOCK, 113, 2, 2, 1)
@@ -222,7 +230,9 @@ enum {
   X(ALLPASS_INT, 1, 1)      \
   X(ALLPASS_FRAC, 1, 1)     \
   X(ALLPASS_PB, 1, 1)       \
-  X(FEEDBACK_READ, 1, 0)
+  X(FEEDBACK_READ, 1, 0)    \
+  X(DOWN2X_IN, 1, 0)        \
+  X(DOWN2X_OUT, 1, 0)
 
 /* ids in [MLB_OP_MAP_FIRST, MLB_OP_MAP_END) are the stateless elementwise ops (mlb_map_*) */
 #define MLB_OP_MAP_FIRST 30
@@ -232,7 +242,7 @@ typedef enum mlb_op {
 #define MLB_X_ENUM(NAME, id, nin, nst, nco) MLB_OP_##NAME = id,
   MLB_OP_TABLE(MLB_X_ENUM)
 #undef MLB_X_ENUM
-  MLB_OP__END = 114
+  MLB_OP__END = 116
 } mlb_op;
 
 /* One node of a voice graph.  in[] index earlier nodes (topological order). */

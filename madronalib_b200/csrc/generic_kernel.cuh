@@ -740,6 +740,81 @@ MLB_DEV void run_halfband_down_node(const GNode& nd, const GenericArgs& a, int v
 #pragma unroll
   for (int i = 0; i < 9; ++i) a.state[(size_t)(nd.st_off + i) * a.V + v] = f2u(h.s[i]);
 }
+// Downsample2xFunction (MLDSPFunctional.h:166-223) around a stateless fn: the statements before fn(...)
+// state: HalfBandFilter mDowners[0] (9 words), mPhase; member row mInputBuffer in delay memory
+template <bool EX>
+MLB_DEV void run_down2x_in_node(const GNode& nd, const GenericArgs& a, int v, bool live, RowRef x, uint32_t out_addr)
+{
+  if (!live) return;
+  float* buffer = node_row(nd, a, v);
+  const uint32_t phase = a.state[(size_t)(nd.st_off + 9) * a.V + v];
+  if (phase)
+  {
+    row_global_to_smem(buffer, out_addr);  // mInputBuffer; then downsample(mInputBuffer, vx) in place
+    HalfBand h;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) h.s[i] = u2f(a.state[(size_t)(nd.st_off + i) * a.V + v]);
+    RowRef x1;
+    x1.is_row = true, x1.addr = out_addr, x1.k = 0.f;
+#pragma unroll 1
+    for (int q = 0; q < 16; ++q)  // output quad q needs input quads 2q, 2q+1 (>= q): safe in place
+    {
+      const RowRef& src = q < 8 ? x1 : x;
+      const float4 p0 = src.get4((q & 7) * 2), p1 = src.get4((q & 7) * 2 + 1);
+      float4 y;
+      float a0, b0;
+      a0 = h.a<EX>(p0.x), b0 = h.b<EX>(p0.y), y.x = A<EX>::mul(A<EX>::add(a0, h.s[8]), 0.5f), h.s[8] = b0;
+      a0 = h.a<EX>(p0.z), b0 = h.b<EX>(p0.w), y.y = A<EX>::mul(A<EX>::add(a0, h.s[8]), 0.5f), h.s[8] = b0;
+      a0 = h.a<EX>(p1.x), b0 = h.b<EX>(p1.y), y.z = A<EX>::mul(A<EX>::add(a0, h.s[8]), 0.5f), h.s[8] = b0;
+      a0 = h.a<EX>(p1.z), b0 = h.b<EX>(p1.w), y.w = A<EX>::mul(A<EX>::add(a0, h.s[8]), 0.5f), h.s[8] = b0;
+      sts128(out_addr + (uint32_t)q * 16u, y);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a.state[(size_t)(nd.st_off + i) * a.V + v] = f2u(h.s[i]);
+  }
+  else
+  {
+    row_smem_to_global(x, buffer);  // mInputBuffer = vx; nothing for fn on this block
+#pragma unroll 4
+    for (int q = 0; q < 16; ++q) sts128(out_addr + (uint32_t)q * 16u, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+  a.state[(size_t)(nd.st_off + 9) * a.V + v] = phase ? 0u : 1u;
+}
+// ... and the statements after fn(...): state HalfBandFilter mUppers[0], mPhase; member row mOutputBuffer
+template <bool EX>
+MLB_DEV void run_down2x_out_node(const GNode& nd, const GenericArgs& a, int v, bool live, RowRef x, uint32_t out_addr)
+{
+  if (!live) return;
+  float* buffer = node_row(nd, a, v);
+  const uint32_t phase = a.state[(size_t)(nd.st_off + 9) * a.V + v];
+  if (phase)
+  {
+    HalfBand h;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) h.s[i] = u2f(a.state[(size_t)(nd.st_off + i) * a.V + v]);
+    float4* b4 = reinterpret_cast<float4*>(buffer);
+#pragma unroll 1
+    for (int q = 0; q < 16; ++q)
+    {
+      const float4 xi = x.get4(q);
+      float4 lo, hi;
+      lo.x = h.a<EX>(xi.x), lo.y = h.b<EX>(xi.x), lo.z = h.a<EX>(xi.y), lo.w = h.b<EX>(xi.y);
+      hi.x = h.a<EX>(xi.z), hi.y = h.b<EX>(xi.z), hi.z = h.a<EX>(xi.w), hi.w = h.b<EX>(xi.w);
+      if (q < 8)  // upsampleFirstHalf -> returned
+      {
+        sts128(out_addr + (uint32_t)(2 * q) * 16u, lo);
+        sts128(out_addr + (uint32_t)(2 * q + 1) * 16u, hi);
+      }
+      else  // upsampleSecondHalf -> mOutputBuffer
+        b4[2 * (q - 8)] = lo, b4[2 * (q - 8) + 1] = hi;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a.state[(size_t)(nd.st_off + i) * a.V + v] = f2u(h.s[i]);
+  }
+  else
+    row_global_to_smem(buffer, out_addr);
+  a.state[(size_t)(nd.st_off + 9) * a.V + v] = phase ? 0u : 1u;
+}
 // TempoLock::operator()(x, dydx, isr), F:1494-1578
 template <bool EX>
 MLB_DEV void run_tempo_lock_node(const GNode& nd, const GenericArgs& a, int v, bool live, RowRef x, RowRef ratio,
@@ -897,6 +972,8 @@ __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
           break;
         case MLB_OP_HALFBAND_DOWN: run_halfband_down_node<EX>(nd, a, v, live, r[0], r[1], o); break;
         case MLB_OP_TEMPO_LOCK: run_tempo_lock_node<EX>(nd, a, v, live, r[0], r[1], o); break;
+        case MLB_OP_DOWN2X_IN: run_down2x_in_node<EX>(nd, a, v, live, r[0], o); break;
+        case MLB_OP_DOWN2X_OUT: run_down2x_out_node<EX>(nd, a, v, live, r[0], o); break;
         case MLB_OP_IMPORT_ROW:
         {
           const float4* src = reinterpret_cast<const float4*>(

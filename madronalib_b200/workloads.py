@@ -347,6 +347,17 @@ def functor_case(name: str, n_voices: int = 40) -> Workload:
             coef[0] = (np.float32(0.5) + vv / np.float32(V) * np.float32(3.0)).astype(np.float32)
             coef[1], coef[2] = np.float32(-1.0), np.float32(1.0)
         fn = noise
+    elif name == "downsample2x_clip":
+        # Downsample2xFunction with the stateless fn(v) = clamp(v * drive, -1, 1) (MLDSPFunctional.h:166-223)
+        x = g.input(0)
+        drive, lo, hi = g.param(), g.param(), g.param()
+        half = g.node("DOWN2X_IN", x)
+        f = g.node("CLAMP", g.node("MULTIPLY", half, drive), lo, hi)
+        g.output(g.node("DOWN2X_OUT", f))
+        coef, state = g.new_coefs(V), g.new_state(V)
+        coef[0] = (np.float32(0.5) + vv / np.float32(V) * np.float32(3.0)).astype(np.float32)
+        coef[1], coef[2] = np.float32(-1.0), np.float32(1.0)
+        fn = noise
     elif name == "tempo_lock":
         # input clock phasor (PhasorGen) -> TempoLock at ratio dydx_v; a few voices start stopped (-1)
         # plane 1 is a bit mask: all-ones rows replace the clock by -1 ("stopped", F:1503-1507) for a
@@ -390,7 +401,7 @@ def functor_case(name: str, n_voices: int = 40) -> Workload:
 FUNCTOR_CASES = ("impulse", "oneshot", "peak", "rms", "adsr", "allpass1", "glide", "interpolator1", "sample_glide",
                  "integer_delay", "integer_delay_var", "fractional_delay", "fractional_delay_var",
                  "pitchbend_delay", "allpass_int", "allpass_frac", "allpass_pb", "feedback",
-                 "halfband_up", "halfband_roundtrip", "upsample2x_clip", "tempo_lock")
+                 "halfband_up", "halfband_roundtrip", "upsample2x_clip", "downsample2x_clip", "tempo_lock")
 
 
 def aaltoverb_feedback(size_u: float, decay_u: float) -> float:

@@ -158,6 +158,15 @@ class RefOracle(_Oracle):
         self.lib.mlref_upsample2x_clip(inp.shape[0], _ptr(inp), _ptr(out), drive)
         return out
 
+    def downsample2x_clip(self, inp: np.ndarray, drive: float) -> np.ndarray:
+        """Downsample2xFunction<1> with fn = clamp(v * drive, -1, 1) for ONE voice; inp [T][64]."""
+        inp = np.ascontiguousarray(inp, np.float32)
+        out = np.empty_like(inp)
+        self.lib.mlref_downsample2x_clip.argtypes = [ctypes.c_int, _vp, _vp, ctypes.c_float]
+        self.lib.mlref_downsample2x_clip.restype = None
+        self.lib.mlref_downsample2x_clip(inp.shape[0], _ptr(inp), _ptr(out), drive)
+        return out
+
     def aaltoverb(self, inp: np.ndarray, size_u2: float, feedback: float, glide_samples: float,
                   repeats: int = 1):
         """The reverb example's own per-vector body for ONE reverb; inp [T][2][64] -> (out, seconds)."""

@@ -1478,6 +1478,31 @@ static void run_voices(mlport_graph* g, const float* in, float* out, int T, int 
           case MLB_OP_HALFBAND_UP_2: memcpy(y, rows2[nd->in[0]], sizeof(float) * NB); break;
           case MLB_OP_HALFBAND_DOWN: hb_downsample(st, a, b, y); break;
           case MLB_OP_TEMPO_LOCK: gen_tempo_lock(st, a, b[0], co[0], y); break;
+          case MLB_OP_DOWN2X_IN: /* Downsample2xFunction, statements before fn, MLDSPFunctional.h:184-193,213-214 */
+          {
+            float* buffer = g->dmem[i][v].row;
+            memset(y, 0, sizeof(float) * NB);
+            if (st[9])
+              hb_downsample(st, buffer, a, y);
+            else
+              memcpy(buffer, a, sizeof(float) * NB);
+            st[9] = !st[9];
+            break;
+          }
+          case MLB_OP_DOWN2X_OUT: /* ... statements after fn, :196-205,215-218 */
+          {
+            float* buffer = g->dmem[i][v].row;
+            if (st[9])
+            {
+              float second[NB];
+              hb_upsample(st, a, y, second);
+              memcpy(buffer, second, sizeof(second));
+            }
+            else
+              memcpy(y, buffer, sizeof(float) * NB);
+            st[9] = !st[9];
+            break;
+          }
           case MLB_OP_FEEDBACK_READ: memcpy(y, g->dmem[i][v].row, sizeof(float) * NB); break;
           case MLB_OP_FEEDBACK_WRITE:
             memcpy(g->dmem[nd->iarg][v].row, a, sizeof(float) * NB);

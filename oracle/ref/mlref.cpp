@@ -499,6 +499,47 @@ struct PHalfBandDown : Proc
   void storeState(uint32_t* s) const override { hbStore(f, s); }
   DSPVector run(const DSPVector* const* in, DSPVector*) override { return f.downsample(*in[0], *in[1]); }
 };
+// Downsample2xFunction<1> split at its process function (MLDSPFunctional.h:166-223): the IN half performs
+// the statements before fn(...), the OUT half those after it, on the reference's own member objects.
+struct PDown2xIn : Proc
+{
+  HalfBandFilter downer;
+  DSPVector inputBuffer;
+  bool phase{false};
+  void loadState(const uint32_t* s) override { hbLoad(downer, s), phase = s[9] != 0; }
+  void storeState(uint32_t* s) const override { hbStore(downer, s), s[9] = phase ? 1u : 0u; }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override
+  {
+    DSPVector y;  // zero when there is nothing to hand to fn
+    if (phase)
+      y = downer.downsample(inputBuffer, *in[0]);
+    else
+      inputBuffer = *in[0];
+    phase = !phase;
+    return y;
+  }
+};
+struct PDown2xOut : Proc
+{
+  HalfBandFilter upper;
+  DSPVector outputBuffer;
+  bool phase{false};
+  void loadState(const uint32_t* s) override { hbLoad(upper, s), phase = s[9] != 0; }
+  void storeState(uint32_t* s) const override { hbStore(upper, s), s[9] = phase ? 1u : 0u; }
+  DSPVector run(const DSPVector* const* in, DSPVector*) override
+  {
+    DSPVector y;
+    if (phase)
+    {
+      y = upper.upsampleFirstHalf(*in[0]);
+      outputBuffer = upper.upsampleSecondHalf(*in[0]);
+    }
+    else
+      y = outputBuffer;
+    phase = !phase;
+    return y;
+  }
+};
 struct PTempoLock : Proc
 {
   TempoLock f;
@@ -627,6 +668,8 @@ Proc* makeProc(int op)
     case MLB_OP_HALFBAND_UP: return new PHalfBandUp;
     case MLB_OP_HALFBAND_DOWN: return new PHalfBandDown;
     case MLB_OP_TEMPO_LOCK: return new PTempoLock;
+    case MLB_OP_DOWN2X_IN: return new PDown2xIn;
+    case MLB_OP_DOWN2X_OUT: return new PDown2xOut;
     case MLB_OP_INPUT:
     case MLB_OP_FEEDBACK_WRITE:
     case MLB_OP_HALFBAND_UP_2:
@@ -1100,5 +1143,17 @@ int mlref_resampler_process(mlref_resampler* r, const float* in, float* out, int
     }
   }
   return produced;
+}
+
+// Downsample2xFunction<1> (MLDSPFunctional.h:166-223) called as a user would, fn(v) = clamp(v * drive, -1, 1)
+void mlref_downsample2x_clip(int T, const float* in, float* out, float drive)
+{
+  Downsample2xFunction<1> downer;
+  for (int t = 0; t < T; ++t)
+  {
+    DSPVector x(in + (size_t)t * 64);
+    DSPVector y = downer([&](const DSPVector v) { return clamp(v * DSPVector(drive), DSPVector(-1.f), DSPVector(1.f)); }, x);
+    store(y, out + (size_t)t * 64);
+  }
 }
 }  // extern "C"

@@ -106,3 +106,15 @@ def test_upsample2x_graph_is_the_higher_order_function(ref):
     for v in (0, 7, 11):
         o = ref.upsample2x_clip(inp[:, 0, v, :], float(w.coef[0, v]))
         assert np.array_equal(o.view(np.uint32), a[:, 0, v, :].view(np.uint32))
+
+
+def test_downsample2x_graph_is_the_higher_order_function(ref):
+    """DOWN2X_OUT(fn(DOWN2X_IN(x))) == the reference's Downsample2xFunction<1> (MLDSPFunctional.h:166-223)
+    called directly with fn(v) = clamp(v * drive, -1, 1)."""
+    w = wl.functor_case("downsample2x_clip", 12)
+    T = 21
+    inp = w.inputs(T)
+    a, _, _ = ref.run(w.spec, 12, T, inp, w.state, w.coef)
+    for v in (0, 7, 11):
+        o = ref.downsample2x_clip(inp[:, 0, v, :], float(w.coef[0, v]))
+        assert np.array_equal(o.view(np.uint32), a[:, 0, v, :].view(np.uint32))
