@@ -115,6 +115,71 @@ class DSPBuffer
     n = std::min(n, getReadAvailable());
     tail_.store((tail_.load(std::memory_order_relaxed) + n) & span_, std::memory_order_release);
   }
+  // copy the newest n samples without consuming anything; nothing happens when fewer are available
+  // (reference: DSPBuffer::peekMostRecent, source/DSP/MLDSPBuffer.h:344-384)
+  void peekMostRecent(float* dst, size_t n) const
+  {
+    const size_t avail = getReadAvailable();
+    if (avail < n) return;
+    copyOut((tail_.load(std::memory_order_relaxed) + (avail - n)) & span_, dst, n);
+  }
+};
+
+// PublishedSignal: a signal handed from the DSP side to outside code such as displays, decimated by
+// 2^octavesDown and stored frame-major in a DSPBuffer (reference: SignalProcessor::PublishedSignal,
+// source/app/MLSignalProcessor.h:28-105, MLSignalProcessor.cpp:11-38).  The rows it takes are host rows,
+// e.g. planes read back from mlb_graph_process_host.
+class PublishedSignal
+{
+  std::vector<float> rotate_;
+  DSPBuffer buffer_;
+  size_t channels_{0};
+  int octavesDown_{0};
+  int downsampleCtr_{0};
+
+ public:
+  PublishedSignal(int maxFrames, int maxVoices, int channels, int octavesDown)
+      : rotate_((size_t)maxFrames * channels), channels_((size_t)channels), octavesDown_(octavesDown)
+  {
+    buffer_.resize(maxFrames * channels * maxVoices);
+  }
+  size_t getNumChannels() const { return channels_; }
+  int getAvailableFrames() const { return (int)(channels_ ? buffer_.getReadAvailable() / channels_ : 0); }
+  int getReadAvailable() const { return (int)buffer_.getReadAvailable(); }
+
+  // rows: `channels` rows of 64 samples (one voice's DSPVectorArray<CHANNELS>); every 2^octavesDown-th frame
+  // of the first `frames` frames is written, the channels of a frame next to each other (writeQuick, .h:60-84)
+  void writeQuick(const float* rows, size_t frames, size_t /*voice*/ = 0)
+  {
+    size_t framesWritten = 0;
+    for (size_t f = 0; f < frames; ++f)
+    {
+      if (++downsampleCtr_ >= (1 << octavesDown_))
+      {
+        for (size_t j = 0; j < channels_; ++j) rotate_[framesWritten * channels_ + j] = rows[j * MLB_BLOCK + f];
+        ++framesWritten;
+        downsampleCtr_ = 0;
+      }
+    }
+    if (framesWritten) buffer_.write(rotate_.data(), framesWritten * channels_);
+  }
+  // one frame of `channels` contiguous values (writeQuickVert, .h:87-97)
+  void writeQuickVert(const float* frame, size_t channels, size_t /*voice*/ = 0)
+  {
+    if (++downsampleCtr_ >= (1 << octavesDown_))
+    {
+      buffer_.write(frame, channels);
+      downsampleCtr_ = 0;
+    }
+  }
+  size_t readLatest(float* dst, size_t framesRequested)  // .cpp:19-28
+  {
+    const size_t avail = buffer_.getReadAvailable();
+    if (avail > framesRequested * channels_) buffer_.discard(avail - framesRequested * channels_);
+    return buffer_.read(dst, framesRequested * channels_);
+  }
+  void peekLatest(float* dst, size_t framesRequested) const { buffer_.peekMostRecent(dst, framesRequested * channels_); }
+  size_t read(float* dst, size_t framesRequested) { return buffer_.read(dst, framesRequested * channels_); }
 };
 
 // in [n_vectors][n_inputs][64] -> out [n_vectors][n_outputs][64]: every vector the host callback needs,
