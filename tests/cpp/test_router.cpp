@@ -208,6 +208,25 @@ int main(int argc, char** argv)
   fails += run_case(8, false, 6, gpu, true);
   fails += run_case(4, false, 7, gpu, true);
   fails += run_case(15, false, 8, gpu, true);
+  // ---- limits are reported, not hidden ----
+  {
+    mlb::VoiceRouter router(1);  // one voice: every note steals it
+    for (int i = 0; i < 7; ++i)
+    {
+      mlb::Event e;
+      e.type = mlb::kNoteOn, e.channel = 1, e.sourceIdx = (uint16_t)(50 + i), e.time = 5 * i, e.value1 = 4.f, e.value2 = 0.5f;
+      router.addEvent(e);
+    }
+    mlb::Event off;
+    off.type = mlb::kController, off.sourceIdx = 120, off.time = 40, off.value1 = 0.f;  // all sound off: not routed
+    router.addEvent(off);
+    mlb_voice_events rec[1];
+    const int overflow = router.processVector(0, rec);
+    const bool ok = overflow == 7 - MLB_VOICE_MAX_EVENTS && rec[0].n_events == MLB_VOICE_MAX_EVENTS &&
+                    router.unsupportedEvents() == 1 && rec[0].type[0] == mlb::kNoteOn && rec[0].type[1] == mlb::kNoteRetrig;
+    std::printf("  overflow and unsupported-event reporting: %s\n", ok ? "ok" : "WRONG");
+    fails += ok ? 0 : 1;
+  }
   std::printf(fails ? "FAILED\n" : "ALL PASSED\n");
   return fails ? 1 : 0;
 }
