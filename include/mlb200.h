@@ -407,6 +407,10 @@ typedef struct mlb_graph mlb_graph; /* opaque; owns device state, coefs, delay m
 int mlb_graph_create(const mlb_node* nodes, int n_nodes, const int32_t* outs, int n_out,
                      int n_voices, unsigned flags, mlb_graph** out_graph);
 int mlb_graph_destroy(mlb_graph* g);
+/* Input buffers normally hold 1 + (highest INPUT plane index) planes per block.  A caller whose buffer has
+ * more planes per block -- the 8 planes of a Voice bank's output, of which a graph reads two -- declares the
+ * real count here (n_planes >= the graph's own; call before processing). */
+int mlb_graph_set_input_planes(mlb_graph* g, int n_planes);
 /* Leave n_sms SMs out of the persistent chain grid (default 0) so that kernels of an overlapped
  * collective -- the NCCL all-reduce of the mix bus in a multi-GPU run -- can be resident next to it
  * (ours; the reference is single-device). */

@@ -68,6 +68,7 @@ def lib() -> ctypes.CDLL:
     L.mlb_graph_delay_bytes.restype = ctypes.c_size_t
     L.mlb_graph_delay_bytes.argtypes = [_vp]
     L.mlb_graph_reserve_sms.argtypes = [_vp, ctypes.c_int]
+    L.mlb_graph_set_input_planes.argtypes = [_vp, ctypes.c_int]
     L.mlb_resampler_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]
     L.mlb_resampler_destroy.argtypes = [_vp]
     L.mlb_resampler_clear.argtypes = [_vp]
@@ -264,6 +265,10 @@ class VoiceGraph:
         """Device pointers (torch tensors / ints); asynchronous on ``stream`` (cudaStream_t)."""
         _check(lib().mlb_graph_process_device(self._h, _ptr(inp), _ptr(out), _ptr(mix), int(n_blocks),
                                               stream or None))
+
+    def set_input_planes(self, n_planes: int) -> None:
+        """The input buffer carries n_planes planes per block (more than the graph reads)."""
+        _check(lib().mlb_graph_set_input_planes(self._h, int(n_planes)))
 
     def reserve_sms(self, n_sms: int) -> None:
         """Keep n_sms SMs out of the persistent chain grid (room for an overlapped collective)."""

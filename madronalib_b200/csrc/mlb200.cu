@@ -1083,6 +1083,17 @@ extern "C" int mlb_graph_destroy(mlb_graph* g)
   return MLB_OK;
 }
 
+extern "C" int mlb_graph_set_input_planes(mlb_graph* g, int n_planes)
+{
+  if (!g) return fail(MLB_ERR_INVALID, "null graph");
+  int need = 0;
+  for (const mlb_node& n : g->nodes)
+    if (n.op == MLB_OP_INPUT) need = std::max(need, n.iarg + 1);
+  if (n_planes < need || n_planes > 64)
+    return fail(MLB_ERR_INVALID, "n_planes must be in [%d, 64] for this graph", need);
+  g->layout.n_inputs = n_planes;
+  return MLB_OK;
+}
 extern "C" int mlb_graph_reserve_sms(mlb_graph* g, int n_sms)
 {
   if (!g || n_sms < 0) return fail(MLB_ERR_INVALID, "bad argument");

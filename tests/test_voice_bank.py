@@ -122,7 +122,15 @@ def test_voice_rows_feed_a_graph(gpu, port_bank, port):
         vg.process_device(d_in, d_out, None, T, sh)
         torch.cuda.synchronize()
         got = d_out.cpu().numpy()
+        # the same without the slicing copy: the graph is told that its input buffer has 8 planes per block
+        vg.set_state(state)
+        vg.set_input_planes(8)
+        d_out2 = torch.empty_like(d_out)
+        vg.process_device(d_rows, d_out2, None, T, sh)
+        torch.cuda.synchronize()
+        got2 = d_out2.cpu().numpy()
     finally:
         vb.close()
         vg.close()
     assert_same_bits(got, want, "events -> voice rows -> graph")
+    assert_same_bits(got2, want, "events -> voice rows -> graph, 8-plane input buffer")
