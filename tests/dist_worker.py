@@ -22,8 +22,16 @@ from oracle.bindings import PortOracle  # noqa: E402
 def main():
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    V, T = 256, 3
-    full = wl.config_a(V)
+    for full, T in ((wl.config_a(256), 3), (wl.config_6(96), 24)):  # the headline chain; Aaltoverb (delay memory, feedback)
+        run_sharded(full, T, rank, world)
+    if rank == 0:
+        print("DIST_OK", world)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_sharded(full, T, rank, world):
+    V = full.n_voices
     inp_full = full.inputs(T)
     v0, v1 = parallel.shard_range(V, rank, world)
     shard = full.shard(rank, world)
@@ -52,9 +60,7 @@ def main():
                                 mix_mode=0)
         tol = V * np.finfo(np.float32).eps * np.abs(want_out).sum(axis=2).max()
         assert np.abs(bufs[0].numpy() - ref_order).max() <= tol
-        print("DIST_OK", world)
     dist.barrier()
-    dist.destroy_process_group()
 
 
 if __name__ == "__main__":
