@@ -1,10 +1,12 @@
 #!/usr/bin/env python
-"""Kernel-resident timing of the other BASELINE.json configurations (2-5) at full size.
+"""Kernel-resident timing of everything except the headline: BASELINE.json configurations 2-5, the
+SURVEY 8(f) workloads (config 6 = Aaltoverb x V, the EventsToSignals::Voice bank) and the elementwise maps.
 
-    python tools/bench_configs.py [--steps K] [--only 2,3,4,5]
+    python tools/bench_configs.py [--steps K] [--only 2,3,4,5,6,voices,map] [--generic] [--cpu]
 
 Prints one JSON line per configuration: kernel name, mean CUDA-event kernel time, algorithmic
-bytes per launch, achieved GB/s and fraction of the measured HBM peak.
+bytes per launch (SURVEY.md 8d / DESIGN.md), achieved GB/s and fraction of the measured HBM peak.
+--cpu also times the reference (oracle/_ref) on the box's host cores for config 6 and the Voice bank.
 Not the headline benchmark (that is bench.py / config A).
 """
 import argparse
