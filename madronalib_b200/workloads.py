@@ -506,3 +506,119 @@ def voice_events(n_voices: int, n_blocks: int, seed: int = 1, density: float = 0
                 r["bend"], r["mod"] = np.float32(rng.random() * 2 - 1), np.float32(rng.random())
                 r["x"], r["y"], r["z"] = np.float32(rng.random()), np.float32(rng.random()), np.float32(rng.random())
     return ev
+
+
+# ---- random voice graphs (tests): any DAG of the op table, for checker-vs-checker and GPU-vs-checker runs ----
+
+def random_graph_workload(seed: int, n_voices: int = 37, n_nodes: int = 24, hw_approx: bool = True) -> Workload:
+    """A random DAG over most of the op table (generators, filters, functors with delay memory, elementwise
+    ops), two external input planes, random but sane coefficients; two outputs.  hw_approx=False leaves out
+    Peak / RMS, whose outputs go through the CPU-defined rsqrt approximation (compared with a tolerance only)."""
+    from .graph import OP_INFO, OP_NAME
+    rng = np.random.default_rng(seed)
+    V = n_voices
+    g = GraphSpec()
+    rows = [g.input(0), g.input(1)]           # audio-ish rows in [-1, 1] and positive "control" rows
+    params = [g.param() for _ in range(4)]
+    unary = ["ABS", "SIN_APPROX", "COS", "SIGN", "FRACTIONAL_PART", "EXP_APPROX", "SQRT"]
+    binary = ["ADD", "SUBTRACT", "MULTIPLY", "MIN", "MAX", "GREATER_THAN", "DIVIDE"]
+    ternary = ["LERP", "CLAMP", "SELECT"]
+    filt = ["LOPASS", "HIPASS", "BANDPASS", "BELL", "ONEPOLE", "DCBLOCKER", "INTEGRATOR", "DIFFERENTIATOR", "RMS",
+            "PEAK", "ALLPASS1", "ADSR", "SAMPLE_GLIDE"]
+    if not hw_approx:
+        filt = [f for f in filt if f not in ("RMS", "PEAK")]
+    gens = ["SINE", "PHASOR", "SAW", "TICK", "ONESHOT", "IMPULSE"]
+    delays1 = ["INTEGER_DELAY", "FRACTIONAL_DELAY", "ALLPASS_INT", "ALLPASS_FRAC", "GLIDE", "INTERPOLATOR1"]
+    delays2 = ["INTEGER_DELAY_VAR", "FRACTIONAL_DELAY_VAR", "PITCHBEND_DELAY", "ALLPASS_PB"]
+    node_kind = {}
+
+    def pick(allow_param=True):
+        pool = rows + (params if allow_param else [])
+        return pool[int(rng.integers(len(pool)))]
+
+    fb = g.feedback_read() if rng.random() < 0.5 else None
+    if fb is not None:
+        rows.append(fb)
+    while g.n_nodes < n_nodes:
+        r = rng.random()
+        if r < 0.2:
+            y = g.node(unary[int(rng.integers(len(unary)))], pick(False))
+        elif r < 0.45:
+            y = g.node(binary[int(rng.integers(len(binary)))], pick(False), pick())
+        elif r < 0.55:
+            y = g.node(ternary[int(rng.integers(len(ternary)))], pick(False), pick(), pick())
+        elif r < 0.75:
+            y = g.node(filt[int(rng.integers(len(filt)))], pick(False))
+        elif r < 0.83:
+            y = g.node(gens[int(rng.integers(len(gens)))], rows[1] if rng.random() < 0.7 else params[0])
+        elif r < 0.93:
+            y = g.node(delays1[int(rng.integers(len(delays1)))], pick(False))
+        else:
+            y = g.node(delays2[int(rng.integers(len(delays2)))], pick(False), rows[1])
+        node_kind[y] = OP_NAME[g.ops[y]]
+        rows.append(y)
+    if fb is not None:
+        g.feedback_write(fb, g.node("MULTIPLY", rows[-1], params[1]))
+    g.output(rows[-1], rows[len(rows) // 2])
+    coef, state = g.new_coefs(V), g.new_state(V)
+    vv = np.arange(V, dtype=np.float32)
+    coef[g.coef_slot(params[0])] = np.float32(0.01) + np.float32(0.002) * vv      # a frequency
+    coef[g.coef_slot(params[1])] = np.float32(0.3)
+    coef[g.coef_slot(params[2])] = np.float32(-0.5) + vv / np.float32(V)
+    coef[g.coef_slot(params[3])] = np.float32(1.5)
+    for i, name in node_kind.items():
+        c0 = g.coef_slot(i)
+        n_co = OP_INFO[g.ops[i]][2]
+        om = float(0.01 + 0.2 * rng.random())
+        if name in ("LOPASS", "HIPASS", "BANDPASS"):
+            coef[c0:c0 + n_co] = api.coeffs(name.lower(), om, 0.7)[:, None]
+        elif name == "BELL":
+            coef[c0:c0 + n_co] = api.coeffs("bell", om, 0.7, 1.3)[:, None]
+        elif name in ("ONEPOLE", "RMS"):
+            coef[c0:c0 + n_co] = api.coeffs(name.lower(), om * 0.1)[:, None]
+        elif name == "PEAK":
+            coef[c0:c0 + 2] = api.coeffs("peak", om * 0.01)[:, None]
+            coef[c0 + 2] = np.float32(150)
+        elif name == "DCBLOCKER":
+            coef[c0] = np.float32(api.coeffs_dcblocker(0.045))
+        elif name == "INTEGRATOR":
+            coef[c0] = np.float32(0.01)
+        elif name == "ALLPASS1":
+            coef[c0] = np.float32(api.coeffs_allpass1(0.618 + rng.random()))
+        elif name == "ADSR":
+            coef[c0:c0 + 4] = api.coeffs("adsr", 0.001, 0.002, 0.5, 0.003, SR)[:, None]
+        elif name == "SAMPLE_GLIDE":
+            coef[c0:c0 + 2] = api.coeffs("sample_glide", 40.0)[:, None]
+        elif name == "GLIDE":
+            coef[c0:c0 + 2] = api.coeffs("glide", 192.0)[:, None]
+        elif name == "INTEGER_DELAY":
+            coef[c0] = np.float32((np.arange(V) * 7) % 200)
+            coef[c0 + 1] = np.float32(200)
+        elif name == "FRACTIONAL_DELAY":
+            coef[c0] = (np.float32(3.3) + vv * np.float32(2.1)).astype(np.float32)
+            coef[c0 + 1] = np.float32(200)
+        elif name in ("ALLPASS_INT", "ALLPASS_FRAC"):
+            coef[c0] = np.float32(0.5)
+            coef[c0 + 1] = (np.float32(70.0) + vv * np.float32(3.3)).astype(np.float32)
+            coef[c0 + 2] = np.float32(64 + 4 * V)
+        elif name in ("INTEGER_DELAY_VAR", "FRACTIONAL_DELAY_VAR", "PITCHBEND_DELAY"):
+            coef[c0] = np.float32(300)
+        elif name == "ALLPASS_PB":
+            coef[c0] = np.float32(0.6)
+            coef[c0 + 1] = np.float32(400)
+        if name == "ONESHOT":
+            state[g.state_slot(i, 1)] = 1
+        if name == "SINE":
+            state[g.state_slot(i)] = SINE_ZERO_PHASE
+    w = Workload("random%d" % seed, g, V, coef, state)
+    audio = _noise_rows(seed + 1000, V, 0.5)
+
+    def fn(T, t0):  # plane 0: noise with gaps (gates for ADSR); plane 1: positive, slowly moving (frequencies / delay times)
+        x = audio(T, t0)
+        n = (np.arange(T * BLOCK, dtype=np.float64) + t0 * BLOCK)
+        ctl = (0.004 + 0.003 * np.sin(n[None, :] * 0.001 * (1.0 + 0.01 * vv[:, None].astype(np.float64)))).astype(np.float32)
+        ctl = np.ascontiguousarray(ctl.reshape(V, T, BLOCK).transpose(1, 0, 2))[:, None]
+        gate = (((n.reshape(T, 1, 1, BLOCK) // 200) % 2) == 0)
+        return np.concatenate([(x * gate).astype(np.float32), ctl * np.float32(60.0)], axis=1)
+    w.inputs = _rows_inputs(fn)  # type: ignore[assignment]
+    return w

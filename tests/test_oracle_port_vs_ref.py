@@ -118,3 +118,17 @@ def test_downsample2x_graph_is_the_higher_order_function(ref):
     for v in (0, 7, 11):
         o = ref.downsample2x_clip(inp[:, 0, v, :], float(w.coef[0, v]))
         assert np.array_equal(o.view(np.uint32), a[:, 0, v, :].view(np.uint32))
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_graphs(ref, port, seed):
+    """Random DAGs over most of the op table (generators, filters, delay functors, feedback edges, elementwise
+    ops): the C port and the compiled reference agree bit for bit, NaNs included, with the port run split."""
+    w = wl.random_graph_workload(seed, 21, 26)
+    T = 9
+    inp = w.inputs(T)
+    a, _, ast = ref.run(w.spec, w.n_voices, T, inp, w.state, w.coef)
+    b, _, bst = port.run(w.spec, w.n_voices, T, inp, w.state, w.coef, splits=(4, 5))
+    from tests.common import assert_same_bits
+    assert_same_bits(b, a, "random graph %d" % seed)
+    assert_state_equal(bst, ast, "random graph %d" % seed)
