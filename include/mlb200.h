@@ -356,6 +356,29 @@ typedef struct mlb_voice_events {  /* what ONE Voice receives during ONE vector 
                              * controller (SmoothedController, .cpp:274-285), one copy per voice */
 
 
+/* Event routing in front of the bank (host only, no GPU needed): the C face of mlb::VoiceRouter
+ * (include/mlb200_events.hpp) = EventsToSignals::addEvent / processVector / processEvent... for the MIDI
+ * (protocol 0) and MPE (protocol 1) protocols (MLEventsToSignals.cpp:352-418, 476-960).
+ * mlb_router_process_vector writes mlb_router_record_count() records: MIDI: voice i+1 -> records[i];
+ * MPE: voice i -> records[i] (0 = the main voice).  Returns the number of note events that did not fit
+ * (MLB_VOICE_MAX_EVENTS per voice and vector), or a negative value on a null argument. */
+typedef struct mlb_router mlb_router;
+typedef struct mlb_event {   /* ml::Event, source/app/MLEvent.h:31-50 */
+  uint8_t type;              /* ml::EventType: 1 note on, 4 note off, 5 sustain pedal, 6 controller, 7 pitch bend,
+                                8 note pressure, 9 channel pressure */
+  uint8_t channel;
+  uint16_t source_idx;       /* key or controller number */
+  int32_t time;              /* frames from the start of the top-level buffer */
+  float value1, value2;
+} mlb_event;
+mlb_router* mlb_router_create(int polyphony, int protocol);
+void mlb_router_destroy(mlb_router* r);
+void mlb_router_set_unison(mlb_router* r, int on);
+void mlb_router_add_event(mlb_router* r, const mlb_event* e);
+void mlb_router_clear_events(mlb_router* r);
+int mlb_router_record_count(const mlb_router* r);
+int mlb_router_process_vector(mlb_router* r, int start_time, mlb_voice_events* records);
+
 typedef struct mlb_voices mlb_voices;  /* opaque: V Voice objects on the device */
 
 /* V voices after Voice() + reset() + setSampleRate(sr) + setPitchGlideInSeconds + setDriftAmount

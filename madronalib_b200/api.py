@@ -69,6 +69,18 @@ def lib() -> ctypes.CDLL:
     L.mlb_graph_delay_bytes.argtypes = [_vp]
     L.mlb_graph_reserve_sms.argtypes = [_vp, ctypes.c_int]
     L.mlb_graph_set_input_planes.argtypes = [_vp, ctypes.c_int]
+    L.mlb_router_create.restype = _vp
+    L.mlb_router_create.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.mlb_router_destroy.argtypes = [_vp]
+    L.mlb_router_destroy.restype = None
+    L.mlb_router_set_unison.argtypes = [_vp, ctypes.c_int]
+    L.mlb_router_set_unison.restype = None
+    L.mlb_router_add_event.argtypes = [_vp, _vp]
+    L.mlb_router_add_event.restype = None
+    L.mlb_router_clear_events.argtypes = [_vp]
+    L.mlb_router_clear_events.restype = None
+    L.mlb_router_record_count.argtypes = [_vp]
+    L.mlb_router_process_vector.argtypes = [_vp, ctypes.c_int, _vp]
     L.mlb_resampler_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]
     L.mlb_resampler_destroy.argtypes = [_vp]
     L.mlb_resampler_clear.argtypes = [_vp]
@@ -365,3 +377,45 @@ class ResamplerBank:
         n = ctypes.c_int(0)
         _check(lib().mlb_resampler_process_host(self._h, x.ctypes.data, out.ctypes.data, T, ctypes.byref(n)))
         return out[:n.value]
+
+
+class _Event(ctypes.Structure):
+    """struct mlb_event"""
+    _fields_ = [("type", ctypes.c_uint8), ("channel", ctypes.c_uint8), ("source_idx", ctypes.c_uint16),
+                ("time", ctypes.c_int32), ("value1", ctypes.c_float), ("value2", ctypes.c_float)]
+
+
+class EventRouter:
+    """EventsToSignals' event routing (host only, no GPU needed): events in, per-voice records out."""
+
+    MIDI, MPE = 0, 1
+    NOTE_ON, NOTE_OFF, SUSTAIN_PEDAL, CONTROLLER, PITCH_BEND, NOTE_PRESSURE, CHANNEL_PRESSURE = 1, 4, 5, 6, 7, 8, 9
+
+    def __init__(self, polyphony: int, protocol: int = 0, unison: bool = False):
+        self._h = lib().mlb_router_create(polyphony, protocol)
+        if not self._h:
+            raise MlbError(1, "bad router arguments")
+        if unison:
+            lib().mlb_router_set_unison(self._h, 1)
+        self.n_records = lib().mlb_router_record_count(self._h)
+
+    def close(self) -> None:
+        if self._h:
+            lib().mlb_router_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_event(self, type: int, channel: int, source_idx: int, time: int, value1: float = 0.0,
+                  value2: float = 0.0) -> None:
+        e = _Event(type, channel, source_idx, time, value1, value2)
+        lib().mlb_router_add_event(self._h, ctypes.byref(e))
+
+    def process_vector(self, start_time: int, records: np.ndarray) -> int:
+        """records: array of n_records elements of workloads.VOICE_EVENTS_DTYPE (written in place)."""
+        assert records.dtype.itemsize == 72 and records.size == self.n_records and records.flags["C_CONTIGUOUS"]
+        return int(lib().mlb_router_process_vector(self._h, start_time, records.ctypes.data))

@@ -1938,3 +1938,45 @@ extern "C" int mlb_resampler_process_host(mlb_resampler* r, const float* in_host
   CU_CHECK(cudaStreamSynchronize(s));
   return MLB_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------
+// C face of mlb::VoiceRouter (host only)
+#include "../../include/mlb200_events.hpp"
+
+struct mlb_router
+{
+  mlb::VoiceRouter router;
+  mlb_router(int polyphony, int protocol)
+      : router(polyphony, protocol == 1 ? mlb::VoiceRouter::kMPE : mlb::VoiceRouter::kMIDI)
+  {
+  }
+};
+extern "C" mlb_router* mlb_router_create(int polyphony, int protocol)
+{
+  if (polyphony < 1 || (protocol != 0 && protocol != 1)) return nullptr;
+  return new mlb_router(polyphony, protocol);
+}
+extern "C" void mlb_router_destroy(mlb_router* r) { delete r; }
+extern "C" void mlb_router_set_unison(mlb_router* r, int on)
+{
+  if (r) r->router.setUnison(on != 0);
+}
+extern "C" void mlb_router_add_event(mlb_router* r, const mlb_event* e)
+{
+  if (!r || !e) return;
+  mlb::Event ev;
+  ev.type = e->type, ev.channel = e->channel, ev.sourceIdx = e->source_idx, ev.time = e->time;
+  ev.value1 = e->value1, ev.value2 = e->value2;
+  r->router.addEvent(ev);
+}
+extern "C" void mlb_router_clear_events(mlb_router* r)
+{
+  if (r) r->router.clearEvents();
+}
+extern "C" int mlb_router_record_count(const mlb_router* r) { return r ? r->router.recordCount() : -1; }
+extern "C" int mlb_router_process_vector(mlb_router* r, int start_time, mlb_voice_events* records)
+{
+  if (!r || !records) return -1;
+  return r->router.processVector(start_time, records);
+}

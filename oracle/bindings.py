@@ -278,3 +278,36 @@ class Resampler:
         if self.h:
             getattr(self.lib, self.p + "resampler_destroy")(self.h)
             self.h = None
+
+
+class RefEventsToSignals:
+    """The complete reference EventsToSignals for one instrument (oracle/_ref/libmle2s.so)."""
+
+    def __init__(self, sr: float, polyphony: int, glide_seconds: float, drift_amount: float, unison: bool = False,
+                 mpe: bool = False):
+        if not os.path.exists(E2S_LIB):
+            raise FileNotFoundError(E2S_LIB + " not built; run `make -C oracle ref`")
+        self.lib = L = ctypes.CDLL(E2S_LIB)
+        L.mle2s_full_create.restype = _vp
+        L.mle2s_full_create.argtypes = [ctypes.c_float, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                        ctypes.c_int]
+        L.mle2s_full_destroy.argtypes = [_vp]
+        L.mle2s_full_add_event.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_float, ctypes.c_float]
+        L.mle2s_full_process.argtypes = [_vp, ctypes.c_int, _vp]
+        self.P = polyphony
+        self.h = L.mle2s_full_create(sr, polyphony, glide_seconds, drift_amount, int(unison), int(mpe))
+
+    def add_event(self, type, channel, source_idx, time, value1=0.0, value2=0.0):
+        self.lib.mle2s_full_add_event(self.h, type, channel, source_idx, time, value1, value2)
+
+    def process_vector(self, start: int) -> np.ndarray:
+        """-> [polyphony][8][64]"""
+        out = np.zeros((self.P, 8, BLOCK), np.float32)
+        self.lib.mle2s_full_process(self.h, start, _ptr(out))
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.mle2s_full_destroy(self.h)
+            self.h = None

@@ -134,3 +134,72 @@ def test_voice_rows_feed_a_graph(gpu, port_bank, port):
         vg.close()
     assert_same_bits(got, want, "events -> voice rows -> graph")
     assert_same_bits(got2, want, "events -> voice rows -> graph, 8-plane input buffer")
+
+
+@pytest.mark.parametrize("mpe,unison,polyphony", [(False, False, 4), (False, True, 3), (True, False, 6)])
+def test_router_c_abi_plus_port_bank_equals_reference(ref_bank, port_bank, mpe, unison, polyphony):
+    """The C face of the router (mlb_router_*, host only) -> records -> Voice bank (the C port here) against
+    the complete reference EventsToSignals, driven from Python with a seeded phrase."""
+    from madronalib_b200 import api
+    from oracle.bindings import RefEventsToSignals
+    sr, glide, drift, T, P = 48000.0, 0.02, 0.5, 150, polyphony
+    rng = np.random.default_rng(21 + polyphony)
+    ref = RefEventsToSignals(sr, P, glide, drift, unison=unison, mpe=mpe)
+    router = api.EventRouter(P, api.EventRouter.MPE if mpe else api.EventRouter.MIDI, unison=unison)
+    held = []
+    for t in range(T):
+        base = t * 64
+        evs = []
+        if rng.random() < 0.3:
+            key = int(rng.integers(40, 80))
+            chan = int(rng.integers(2, 10)) if mpe else 1
+            evs.append((api.EventRouter.NOTE_ON, chan, key, base + int(rng.integers(64)), key / 12.0, float(rng.random() * 0.8 + 0.2)))
+            held.append((chan, key))
+        if held and rng.random() < 0.25:
+            chan, key = held.pop(int(rng.integers(len(held))))
+            evs.append((api.EventRouter.NOTE_OFF, chan, key, base + int(rng.integers(64)), 0.0, 0.0))
+        if rng.random() < 0.2:
+            evs.append((api.EventRouter.PITCH_BEND, int(rng.integers(1, 10)), 0, base + int(rng.integers(64)), float(rng.random() * 2 - 1), 0.0))
+        if rng.random() < 0.2:
+            evs.append((api.EventRouter.CHANNEL_PRESSURE, int(rng.integers(1, 10)), 0, base + int(rng.integers(64)), float(rng.random()), 0.0))
+        if rng.random() < 0.15:
+            evs.append((api.EventRouter.CONTROLLER, int(rng.integers(1, 10)), int(rng.choice([16, 73, 74])), base + int(rng.integers(64)), float(rng.random()), 0.0))
+        if rng.random() < 0.08:
+            evs.append((api.EventRouter.SUSTAIN_PEDAL, 1, 0, base + int(rng.integers(64)), float(rng.integers(2)), 0.0))
+        for e in evs:
+            ref.add_event(*e)
+            router.add_event(*e)
+    NR = router.n_records
+    recs = np.zeros((T, NR), wl.VOICE_EVENTS_DTYPE)
+    want = np.zeros((T, P, 8, 64), np.float32)
+    for t in range(T):
+        want[t] = ref.process_vector(t * 64)
+        assert router.process_vector(t * 64, recs[t]) == 0
+    ref.close()
+    router.close()
+    first = 1 if mpe else 0
+    idx = np.arange(NR, dtype=np.int32) + (0 if mpe else 1)
+    bend = np.full(NR, 24.0 if mpe else 7.0, np.float32)
+    if mpe:
+        bend[0] = 7.0
+    # the port bank: MPE main-voice rows are added by a post-pass (mlport_bank_set_main_voices)
+    import ctypes
+    L = port_bank.lib
+    L.mlport_bank_create.restype = ctypes.c_void_p
+    gs, da = np.full(NR, glide, np.float32), np.full(NR, drift, np.float32)
+    h = L.mlport_bank_create(NR, ctypes.c_float(sr), idx.ctypes.data_as(ctypes.c_void_p), gs.ctypes.data_as(ctypes.c_void_p),
+                             da.ctypes.data_as(ctypes.c_void_p), bend.ctypes.data_as(ctypes.c_void_p), 0 if mpe else 1)
+    if mpe:
+        mainv = np.full(NR, 0, np.int32)
+        mainv[0] = -1
+        L.mlport_bank_set_main_voices.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.mlport_bank_set_main_voices(h, mainv.ctypes.data_as(ctypes.c_void_p))
+    got = np.zeros((T, 8, NR, 64), np.float32)
+    L.mlport_bank_process.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    L.mlport_bank_process.restype = ctypes.c_double
+    L.mlport_bank_process(h, T, recs.ctypes.data_as(ctypes.c_void_p), got.ctypes.data_as(ctypes.c_void_p), 1)
+    L.mlport_bank_destroy.argtypes = [ctypes.c_void_p]
+    L.mlport_bank_destroy(h)
+    got = got[:, :, first:, :].transpose(0, 2, 1, 3)  # -> [T][P][8][64]
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert want[:, :, 1].max() > 0.1  # gates happened
