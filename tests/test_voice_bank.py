@@ -203,3 +203,72 @@ def test_router_c_abi_plus_port_bank_equals_reference(ref_bank, port_bank, mpe, 
     got = got[:, :, first:, :].transpose(0, 2, 1, 3)  # -> [T][P][8][64]
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     assert want[:, :, 1].max() > 0.1  # gates happened
+
+
+# ---- fuzz: random phrases, polyphony 1..16, MIDI / unison / MPE, several sample rates, against the complete
+# reference EventsToSignals (CPU only; the bank is the C port) ----
+def _fuzz_imports():
+    import ctypes
+    from madronalib_b200 import api
+    from oracle.bindings import RefEventsToSignals
+    return ctypes, api, RefEventsToSignals
+
+
+def _router_fuzz_case(seed, PB):
+    ctypes, api, RefEventsToSignals = _fuzz_imports()
+    rng=np.random.default_rng(seed)
+    mpe=bool(rng.integers(2)); unison=bool(rng.integers(2)) and not mpe
+    P=int(rng.integers(1,17)); sr=float(rng.choice([44100.0,48000.0,96000.0])); glide=float(rng.choice([0.0,0.01,0.05])); drift=float(rng.choice([0.0,1.0]))
+    T=int(rng.integers(40,200))
+    dens=float(rng.choice([0.1,0.4,0.9]))
+    ref=RefEventsToSignals(sr,P,glide,drift,unison=unison,mpe=mpe)
+    router=api.EventRouter(P, 1 if mpe else 0, unison=unison)
+    held=[]
+    E=api.EventRouter
+    for t in range(T):
+        base=t*64
+        n=int(rng.poisson(dens))
+        for _ in range(n):
+            kind=int(rng.integers(8))
+            tm=base+int(rng.integers(64))
+            chan=int(rng.integers(1,11))
+            if kind<=2:
+                key=int(rng.integers(30,100)); ch=chan if mpe else 1
+                e=(E.NOTE_ON,ch,key,tm,key/12.0,float(rng.random()*0.9+0.1)); held.append((ch,key))
+            elif kind==3 and held:
+                ch,key=held.pop(int(rng.integers(len(held)))); e=(E.NOTE_OFF,ch,key,tm,0.0,0.0)
+            elif kind==4: e=(E.PITCH_BEND,chan,0,tm,float(rng.random()*2-1),0.0)
+            elif kind==5: e=(E.CHANNEL_PRESSURE,chan,0,tm,float(rng.random()),0.0)
+            elif kind==6: e=(E.CONTROLLER,chan,int(rng.choice([16,73,74,1,123,128,200])),tm,float(rng.choice([0.0,rng.random()])),0.0)
+            elif kind==7: e=(int(rng.choice([E.SUSTAIN_PEDAL,E.NOTE_PRESSURE])),chan,int(rng.integers(30,100)),tm,float(rng.random()),0.0)
+            else: continue
+            ref.add_event(*e); router.add_event(*e)
+    NR=router.n_records
+    recs=np.zeros((T,NR),wl.VOICE_EVENTS_DTYPE); want=np.zeros((T,P,8,64),np.float32)
+    over=0
+    for t in range(T):
+        want[t]=ref.process_vector(t*64); over+=router.process_vector(t*64,recs[t])
+    ref.close(); router.close()
+    if over: return "overflow(%d)"%over
+    first=1 if mpe else 0
+    idx=np.arange(NR,dtype=np.int32)+(0 if mpe else 1)
+    bend=np.full(NR,24.0 if mpe else 7.0,np.float32)
+    if mpe: bend[0]=7.0
+    L=PB.lib
+    gs,da=np.full(NR,glide,np.float32),np.full(NR,drift,np.float32)
+    h=L.mlport_bank_create(NR,ctypes.c_float(sr),idx.ctypes.data_as(ctypes.c_void_p),gs.ctypes.data_as(ctypes.c_void_p),da.ctypes.data_as(ctypes.c_void_p),bend.ctypes.data_as(ctypes.c_void_p),0 if mpe else 1)
+    if mpe:
+        mainv=np.full(NR,0,np.int32); mainv[0]=-1
+        L.mlport_bank_set_main_voices.argtypes=[ctypes.c_void_p,ctypes.c_void_p]; L.mlport_bank_set_main_voices(h,mainv.ctypes.data_as(ctypes.c_void_p))
+    got=np.zeros((T,8,NR,64),np.float32)
+    L.mlport_bank_process(h,T,recs.ctypes.data_as(ctypes.c_void_p),got.ctypes.data_as(ctypes.c_void_p),1)
+    L.mlport_bank_destroy.argtypes=[ctypes.c_void_p]; L.mlport_bank_destroy(h)
+    got=got[:,:,first:,:].transpose(0,2,1,3)
+    bad=int((got.view(np.uint32)!=want.view(np.uint32)).sum())
+    return "ok" if bad==0 else "MISMATCH %d (mpe=%s unison=%s P=%d sr=%g)"%(bad,mpe,unison,P,sr)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_router_fuzz_against_reference(ref_bank, port_bank, seed):
+    r = _router_fuzz_case(seed, port_bank)
+    assert r == "ok" or r.startswith("overflow"), r
