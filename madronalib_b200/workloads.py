@@ -405,14 +405,18 @@ FUNCTOR_CASES = ("impulse", "oneshot", "peak", "rms", "adsr", "allpass1", "glide
 
 
 def aaltoverb_feedback(size_u: float, decay_u: float) -> float:
-    """reverb.cpp:18-19,80-83: unityToLogParam({0.8, 20}) decay projection -> feedback gain (host-side
-    scalar maths; float like the reference's)."""
-    lo, hi = np.float32(0.8), np.float32(20.0)
-    decay_time = np.float32(lo * np.power(hi / lo, np.float32(decay_u), dtype=np.float32))
-    iters = np.float32(decay_time / np.float32(size_u * 0.5))
+    """reverb.cpp:18-19,76-83: decayTime = unityToLogParam({0.8, 20})(decayU) (MLDSPProjections.h:105-123,176-195:
+    intervalMap({0,1}, {a,b}, log{a,b})), decayIterations = decayTime / (sizeU * 0.5),
+    feedback = powf(0.001, 1 / decayIterations) -- host-side scalar maths in float, step by step as written there."""
+    f = np.float32
+    a, b = f(0.8), f(20.0)
+    x = f(decay_u) * (f(1.0) / (f(1.0) - f(0.0))) + (-f(0.0)) / (f(1.0) - f(0.0))
+    c = a * (np.power(b / a, x, dtype=np.float32) - f(1.0)) / (b - a)
+    decay_time = c * (b - a) + a
+    iters = f(decay_time / (float(f(size_u)) * 0.5))  # double product, like `sizeU*0.5` with a double literal
     if decay_u >= 1.0:
         return 1.0
-    return float(np.power(np.float32(0.001), np.float32(1.0) / iters, dtype=np.float32))
+    return float(np.power(f(0.001), f(1.0) / iters, dtype=np.float32))
 
 
 def config_6(n_voices: int = 4096) -> Workload:
