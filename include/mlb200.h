@@ -298,6 +298,11 @@ void mlb_coeffs_sample_glide(float time_in_samples, float out2[2]);
 void mlb_coeffs_fdn8(const float times[8], const float cutoffs[8], const float gains[8],
                      float out32[32]);
 
+/* The same designs for n voices in one call (pure host): op = MLB_OP_LOPASS / HIPASS / BANDPASS / LOSHELF /
+ * HISHELF / BELL / ONEPOLE; omega[n], k[n] (unused for ONEPOLE), A[n] (shelves and bell only);
+ * out[n_coef][n] in the SoA layout of mlb_graph_set_coefs. */
+int mlb_coeffs_batch(int op, size_t n, const float* omega, const float* k, const float* A, float* out);
+
 /* ---- device / context ---- */
 int mlb_init(int device);          /* select device, check sm_100; MLB_ERR_NO_DEVICE if absent */
 int mlb_device_count(void);        /* 0 when no GPU: callers must fail loudly, not fall back */
@@ -468,6 +473,10 @@ int mlb_graph_process_host(mlb_graph* g, const float* in_host, float* out_host, 
  * process_device, measured with CUDA events on the launching stream
  * (blocks until that launch has finished). */
 int mlb_graph_last_kernel_ms(mlb_graph* g, float* ms);
+/* Number of voice slices the most recent mlb_graph_process_host call was pipelined over
+ * (H2D / kernel / D2H on three streams); 1 = a single launch, -1 = null graph.  Large fused banks
+ * are sliced when the PCIe traffic of the call reaches MLB_HOST_SLICE_MIN_MB (env, default 32) MiB. */
+int mlb_graph_last_host_slices(const mlb_graph* g);
 
 #ifdef __cplusplus
 }

@@ -94,6 +94,7 @@ def lib() -> ctypes.CDLL:
     L.mlb_graph_process_device.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, _vp]
     L.mlb_graph_process_host.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int]
     L.mlb_graph_last_kernel_ms.argtypes = [_vp, _vp]
+    L.mlb_graph_last_host_slices.argtypes = [_vp]
     L.mlb_map_device.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]
     L.mlb_map_host.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_size_t]
     for name, n in (("lopass", 2), ("hipass", 2), ("bandpass", 2), ("loshelf", 3), ("hishelf", 3),
@@ -102,6 +103,7 @@ def lib() -> ctypes.CDLL:
         fn = getattr(L, "mlb_coeffs_" + name)
         fn.argtypes = [_cf] * n + [_vp]
         fn.restype = None
+    L.mlb_coeffs_batch.argtypes = [ctypes.c_int, ctypes.c_size_t, _vp, _vp, _vp, _vp]
     L.mlb_coeffs_dcblocker.argtypes = [_cf]
     L.mlb_coeffs_dcblocker.restype = _cf
     L.mlb_impulse_table.argtypes = [_vp]
@@ -154,6 +156,17 @@ _NCOEF = {"lopass": 3, "hipass": 4, "bandpass": 3, "loshelf": 5, "hishelf": 6, "
 def coeffs(kind: str, *args: float) -> np.ndarray:
     out = np.zeros(_NCOEF[kind], np.float32)
     getattr(lib(), "mlb_coeffs_" + kind)(*[_cf(a) for a in args], out.ctypes.data)
+    return out
+
+
+def coeffs_batch(kind: str, omega, k=None, A=None) -> np.ndarray:
+    """makeCoeffs of `kind` for n voices at once -> [n_coef][n] (one C call, host libm)."""
+    om = np.ascontiguousarray(omega, np.float32)
+    n = om.shape[0]
+    kk = None if k is None else np.ascontiguousarray(np.broadcast_to(np.asarray(k, np.float32), (n,)))
+    aa = None if A is None else np.ascontiguousarray(np.broadcast_to(np.asarray(A, np.float32), (n,)))
+    out = np.zeros((_NCOEF[kind], n), np.float32)
+    _check(lib().mlb_coeffs_batch(OP_ID[kind.upper()], n, om.ctypes.data, _ptr(kk), _ptr(aa), out.ctypes.data))
     return out
 
 
@@ -285,6 +298,11 @@ class VoiceGraph:
     def reserve_sms(self, n_sms: int) -> None:
         """Keep n_sms SMs out of the persistent chain grid (room for an overlapped collective)."""
         _check(lib().mlb_graph_reserve_sms(self._h, int(n_sms)))
+
+    @property
+    def last_host_slices(self) -> int:
+        """Voice slices the most recent process_host call was pipelined over (1 = one launch)."""
+        return int(lib().mlb_graph_last_host_slices(self._h))
 
     def last_kernel_ms(self) -> float:
         ms = ctypes.c_float(0)

@@ -291,6 +291,39 @@ extern "C" void mlb_coeffs_sample_glide(float t, float o[2])
   o[0] = (float)n;
   o[1] = 1.0f / (float)n;
 }
+// n voices at once: out[word][n] (the SoA layout of mlb_graph_set_coefs).  kind = the node op.
+extern "C" int mlb_coeffs_batch(int op, size_t n, const float* omega, const float* k, const float* A, float* out)
+{
+  if (!omega || !out) return fail(MLB_ERR_INVALID, "null argument");
+  int nco = 0;
+  switch (op)
+  {
+    case MLB_OP_LOPASS: case MLB_OP_BANDPASS: nco = 3; break;
+    case MLB_OP_HIPASS: case MLB_OP_BELL: nco = 4; break;
+    case MLB_OP_LOSHELF: nco = 5; break;
+    case MLB_OP_HISHELF: nco = 6; break;
+    case MLB_OP_ONEPOLE: nco = 2; break;
+    default: return fail(MLB_ERR_INVALID, "mlb_coeffs_batch: op %d has no omega/k/A coefficient design", op);
+  }
+  if (op != MLB_OP_ONEPOLE && !k) return fail(MLB_ERR_INVALID, "k is null");
+  if ((op == MLB_OP_BELL || op == MLB_OP_LOSHELF || op == MLB_OP_HISHELF) && !A) return fail(MLB_ERR_INVALID, "A is null");
+  for (size_t v = 0; v < n; ++v)
+  {
+    float c[6];
+    switch (op)
+    {
+      case MLB_OP_LOPASS: mlb_coeffs_lopass(omega[v], k[v], c); break;
+      case MLB_OP_BANDPASS: mlb_coeffs_bandpass(omega[v], k[v], c); break;
+      case MLB_OP_HIPASS: mlb_coeffs_hipass(omega[v], k[v], c); break;
+      case MLB_OP_BELL: mlb_coeffs_bell(omega[v], k[v], A[v], c); break;
+      case MLB_OP_LOSHELF: mlb_coeffs_loshelf(omega[v], k[v], A[v], c); break;
+      case MLB_OP_HISHELF: mlb_coeffs_hishelf(omega[v], k[v], A[v], c); break;
+      default: mlb_coeffs_onepole(omega[v], c); break;
+    }
+    for (int w = 0; w < nco; ++w) out[(size_t)w * n + v] = c[w];
+  }
+  return MLB_OK;
+}
 extern "C" void mlb_coeffs_fdn8(const float times[8], const float cutoffs[8], const float gains[8],
                                 float out32[32])
 {
@@ -520,6 +553,7 @@ struct mlb_graph
 
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
+  int last_host_slices = 0;  // voice slices of the most recent mlb_graph_process_host call (1 = one launch)
 };
 
 // delay memory of an op: 64-float member rows and IntegerDelay rings per voice (MLB_OP_MEM_TABLE)
@@ -1519,7 +1553,9 @@ extern "C" int mlb_graph_process_host(mlb_graph* g, const float* in_host, float*
   // Only planes that really cross PCIe count: a mix-only call (out_host == NULL) moves 256 B per
   // block and must stay ONE launch -- 16 slice launches of a 4096-voice bank are latency-bound.
   const size_t pcie_bytes = in_bytes + (out_host ? out_bytes : 0);
-  if (g->kind == KIND_FUSED && n_slices_env > 1 && g->V >= 4096 && pcie_bytes >= ((size_t)32 << 20))
+  const size_t slice_min_bytes = (size_t)env_int("MLB_HOST_SLICE_MIN_MB", 32) << 20;
+  g->last_host_slices = 1;
+  if (g->kind == KIND_FUSED && n_slices_env > 1 && g->V >= 4096 && pcie_bytes >= slice_min_bytes)
   {
     const int n_slices = std::min(n_slices_env, (int)mlb_graph::kMaxHostSlices);
     int per = (g->V + n_slices - 1) / n_slices;
@@ -1528,8 +1564,10 @@ extern "C" int mlb_graph_process_host(mlb_graph* g, const float* in_host, float*
     if (mix_host && (rc = ensure_partial(g, n_blocks, (g->V + 31) / 32)) != MLB_OK) return rc;
     int chunks = 0;
     cudaEventRecord(g->ev0, s);
+    g->last_host_slices = 0;
     for (int p = 0, va = 0; va < g->V; ++p, va += per)
     {
+      ++g->last_host_slices;
       const int vb = std::min(g->V, va + per);
       const size_t width = (size_t)(vb - va) * MLB_BLOCK * 4;
       if (n_in)
@@ -1577,6 +1615,8 @@ extern "C" int mlb_graph_process_host(mlb_graph* g, const float* in_host, float*
   CU_CHECK(cudaStreamSynchronize(s));
   return MLB_OK;
 }
+
+extern "C" int mlb_graph_last_host_slices(const mlb_graph* g) { return g ? g->last_host_slices : -1; }
 
 extern "C" int mlb_graph_last_kernel_ms(mlb_graph* g, float* ms)
 {

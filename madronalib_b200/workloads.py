@@ -79,16 +79,11 @@ def _set(coef: np.ndarray, spec: GraphSpec, node: int, values) -> None:
 
 def _svf_coefs(kind: str, n_voices: int) -> np.ndarray:
     """omega_v = 0.02 + 0.2 v/V, k = 0.5 (Bell/shelves: A = dBToGain(6)); [n_coef][V]."""
-    n = api._NCOEF[kind]
-    out = np.zeros((n, n_voices), np.float32)
-    A = api.db_to_gain(6.0)
-    for v in range(n_voices):
-        omega = np.float32(0.02) + np.float32(0.2) * np.float32(v) / np.float32(n_voices)
-        if kind in ("lopass", "hipass", "bandpass"):
-            out[:, v] = api.coeffs(kind, float(omega), 0.5)
-        else:
-            out[:, v] = api.coeffs(kind, float(omega), 0.5, A)
-    return out
+    v = np.arange(n_voices, dtype=np.float32)
+    omega = np.float32(0.02) + np.float32(0.2) * v / np.float32(n_voices)
+    if kind in ("lopass", "hipass", "bandpass"):
+        return api.coeffs_batch(kind, omega, 0.5)
+    return api.coeffs_batch(kind, omega, 0.5, api.db_to_gain(6.0))
 
 
 def config_a(n_voices: int = 65536, gain: float = 0.1) -> Workload:
@@ -127,11 +122,9 @@ def config_3(n_voices: int = 65536) -> Workload:
     spec = graph_phasor_lopass_onepole()
     coef = spec.new_coefs(n_voices)
     _set(coef, spec, 2, _svf_coefs("lopass", n_voices))
-    op = np.zeros((2, n_voices), np.float32)
-    for v in range(n_voices):
-        om = np.float32(0.001) + np.float32(0.01) * np.float32(v) / np.float32(n_voices)
-        op[:, v] = api.coeffs("onepole", float(om))
-    _set(coef, spec, 3, op)
+    vv = np.arange(n_voices, dtype=np.float32)
+    om = np.float32(0.001) + np.float32(0.01) * vv / np.float32(n_voices)
+    _set(coef, spec, 3, api.coeffs_batch("onepole", om))
     return Workload("phasor_lopass_onepole", spec, n_voices, coef, spec.new_state(n_voices))
 
 

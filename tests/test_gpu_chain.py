@@ -80,15 +80,32 @@ def test_dynamic_work_units(gpu, port, monkeypatch, n_voices, n_blocks, chunks, 
 @pytest.mark.parametrize("slices", [1, 5, 8])
 def test_host_entry_point_voice_slices(gpu, port, monkeypatch, slices):
     """mlb_graph_process_host pipelines big banks over voice slices (H2D / kernel / D2H on three
-    streams); the result must not depend on the slicing."""
+    streams, cudaMemcpy2DAsync windows, per-slice progress offsets); the result must not depend on
+    the slicing.  The slicing threshold is lowered so that this bank really takes the pipeline
+    (asserted through mlb_graph_last_host_slices); the full-size case is in test_gpu_fullsize.py."""
     monkeypatch.setenv("MLB_HOST_SLICES", str(slices))
+    monkeypatch.setenv("MLB_HOST_SLICE_MIN_MB", "1")
     V, T = 4200 + 7, 17
     w = wl.config_a(V)
     inp = w.inputs(T)
     po, pm, ps = port.run(w.spec, V, T, inp, w.state, w.coef, want_mix=True, mix_mode=1, nthreads=8)
-    go, gm, gs, _ = run_gpu(gpu, w, T, inp, want_mix=True, splits=(9, 8))
-    assert_same_bits(go, po, "out")
-    assert_same_bits(gm, pm, "mix")
+    g = gpu.VoiceGraph(w.spec, V)
+    try:
+        g.set_coefs(w.coef)
+        g.set_state(w.state)
+        outs, mixes = [], []
+        for t0, n in ((0, 9), (9, 8)):
+            o, m = g.process_host(np.ascontiguousarray(inp[t0:t0 + n]), n, want_out=True, want_mix=True)
+            # ceil(V / slices) rounded up to whole 32-voice groups per slice
+            per = -(-(-(-V // slices)) // 32) * 32
+            assert g.last_host_slices == (-(-V // per) if slices > 1 else 1), g.last_host_slices
+            outs.append(o)
+            mixes.append(m)
+        gs = g.get_state()
+    finally:
+        g.close()
+    assert_same_bits(np.concatenate(outs), po, "out")
+    assert_same_bits(np.concatenate(mixes), pm, "mix")
     assert_state_equal(gs, ps)
 
 
