@@ -46,9 +46,9 @@ extern "C" {
 #endif
 
 #define MLB_BLOCK 64           /* kFloatsPerDSPVector, MLDSPMath.h:8-9 */
-#define MLB_MAX_INS 3
+#define MLB_MAX_INS 7         /* signal inputs of a node: x + up to 6 coefficient rows (HiShelf::_vcoeffs) */
 #define MLB_FDN_LINES 8        /* FDN<8>, MLDSPFilters.h:1162 */
-#define MLB_ABI_VERSION 1
+#define MLB_ABI_VERSION 2     /* 2: MLB_MAX_INS 3 -> 7 (sizeof(mlb_node) 20 -> 36), coefficient-row filters */
 
 /* ---- status codes (the reference has no error channel) ---- */
 enum {
@@ -215,7 +215,25 @@ enum {
   X(DOWN2X_OUT, 115, 1, 10, 0)                                                           \
   /* TempoLock(x, dydx, isr), F:1478-1579: in0 = input phasor row, in1 = ratio (sample   */ \
   /* 0 of the row); state _omega, _x1v (fresh: _omega = -1); coef isr                    */ \
-  X(TEMPO_LOCK, 113, 2, 2, 1)
+  X(TEMPO_LOCK, 113, 2, 2, 1)                                                            \
+  /* ---- filters whose coefficients are SIGNAL ROWS (one value per sample), i.e. the modulated /  */ \
+  /* swept forms of the reference.  in0 = audio, in1.. = the coefficient rows in the order of the   */ \
+  /* reference's coeffNames enums; a PARAM operand is a constant row.  state: ic1eq, ic2eq.         */ \
+  /* The rows are designed on the host with the reference's own libm calls (mlb_coeffs_lopass_vec = */ \
+  /* Lopass::makeCoeffsVec, mlb_interpolate_coeffs_linear = interpolateCoeffsLinear of two          */ \
+  /* makeCoeffs results = LoShelf/HiShelf::vcoeffs) or on the device from two endpoints (RAMP).     */ \
+  X(LOPASS_V, 116, 4, 2, 0)     /* Lopass::operator()(vx, omega, k) after its makeCoeffsVec,         */ \
+                                /* F:136-152: in1..3 = rows g0, g1, g2                               */ \
+  X(LOSHELF_V, 117, 6, 2, 0)    /* LoShelf::operator()(vx, vc), F:304-319: rows a1,a2,a3,m1,m2       */ \
+  X(HISHELF_V, 118, 7, 2, 0)    /* HiShelf::operator()(vx, vc), F:385-400: rows a1,a2,a3,m0,m1,m2    */ \
+  /* Lopass::operator()(vx, omega, k) with makeCoeffsVec evaluated ON THE DEVICE (F:97-115: clamps,  */ \
+  /* two sinf and one division per sample).  CUDA sinf is not glibc sinf: this node is the           */ \
+  /* "approximate variant" of LOPASS_V with a stated tolerance, never bit-exact.      */ \
+  X(LOPASS_MOD, 119, 3, 2, 0)                                                                        \
+  /* interpolateDSPVectorLinear(start, end), O:986-990: row[n] = n * ((end - start) / 64) +          */ \
+  /* (start + (end - start) / 64); the scalar arguments are sample 0 of the operand rows (or PARAMs). */ \
+  /* One RAMP per coefficient = interpolateCoeffsLinear (F:32-44) on the device.                     */ \
+  X(RAMP, 120, 2, 0, 0)
 
 /* Delay memory per voice: X(NAME, n_rows, n_rings) -- 64-float rows and rings.
  * PitchbendableDelay's two FractionalDelays are fed the same input on every sample
@@ -242,7 +260,7 @@ typedef enum mlb_op {
 #define MLB_X_ENUM(NAME, id, nin, nst, nco) MLB_OP_##NAME = id,
   MLB_OP_TABLE(MLB_X_ENUM)
 #undef MLB_X_ENUM
-  MLB_OP__END = 116
+  MLB_OP__END = 121
 } mlb_op;
 
 /* One node of a voice graph.  in[] index earlier nodes (topological order). */
@@ -302,6 +320,17 @@ void mlb_coeffs_fdn8(const float times[8], const float cutoffs[8], const float g
  * HISHELF / BELL / ONEPOLE; omega[n], k[n] (unused for ONEPOLE), A[n] (shelves and bell only);
  * out[n_coef][n] in the SoA layout of mlb_graph_set_coefs. */
 int mlb_coeffs_batch(int op, size_t n, const float* omega, const float* k, const float* A, float* out);
+
+/* Lopass::makeCoeffsVec(omega, k), F:97-115, for ONE 64-sample block: clamps omega to <= 0.5 and k to
+ * >= 0.01 (min/max with the reference's operand order), then the per-sample makeCoeffs formula with host
+ * libm sinf.  out3x64 = rows g0, g1, g2 (the in1..3 rows of a LOPASS_V node). */
+void mlb_coeffs_lopass_vec(const float omega[64], const float k[64], float out3x64[3 * 64]);
+/* the same for n_rows blocks: omega, k [n_rows][64] -> out [n_rows][3][64] */
+void mlb_coeffs_lopass_vec_n(const float* omega, const float* k, float* out, size_t n_rows);
+/* interpolateCoeffsLinear(c0, c1), F:32-44: row i = interpolateDSPVectorLinear(c0[i], c1[i]) (O:986-990).
+ * With c0 / c1 from mlb_coeffs_loshelf / mlb_coeffs_hishelf this is LoShelf/HiShelf::vcoeffs(p0, p1)
+ * (F:283-286, 364-367).  out = [n_coeffs][64]. */
+void mlb_interpolate_coeffs_linear(const float* c0, const float* c1, int n_coeffs, float* out);
 
 /* ---- device / context ---- */
 int mlb_init(int device);          /* select device, check sm_100; MLB_ERR_NO_DEVICE if absent */

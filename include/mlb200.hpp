@@ -150,7 +150,11 @@ class Graph
 
   int add(int op, int a = -1, int b = -1, int c = -1, int iarg = 0)
   {
-    mlb_node n{op, {a, b, c}, iarg};
+    mlb_node n;
+    n.op = op;
+    for (int k = 0; k < MLB_MAX_INS; ++k) n.in[k] = -1;
+    n.in[0] = a, n.in[1] = b, n.in[2] = c;
+    n.iarg = iarg;
     nodes_.push_back(n);
     return (int)nodes_.size() - 1;
   }

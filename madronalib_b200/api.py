@@ -104,6 +104,12 @@ def lib() -> ctypes.CDLL:
         fn.argtypes = [_cf] * n + [_vp]
         fn.restype = None
     L.mlb_coeffs_batch.argtypes = [ctypes.c_int, ctypes.c_size_t, _vp, _vp, _vp, _vp]
+    L.mlb_coeffs_lopass_vec.argtypes = [_vp, _vp, _vp]
+    L.mlb_coeffs_lopass_vec.restype = None
+    L.mlb_coeffs_lopass_vec_n.argtypes = [_vp, _vp, _vp, ctypes.c_size_t]
+    L.mlb_coeffs_lopass_vec_n.restype = None
+    L.mlb_interpolate_coeffs_linear.argtypes = [_vp, _vp, ctypes.c_int, _vp]
+    L.mlb_interpolate_coeffs_linear.restype = None
     L.mlb_coeffs_dcblocker.argtypes = [_cf]
     L.mlb_coeffs_dcblocker.restype = _cf
     L.mlb_impulse_table.argtypes = [_vp]
@@ -167,6 +173,27 @@ def coeffs_batch(kind: str, omega, k=None, A=None) -> np.ndarray:
     aa = None if A is None else np.ascontiguousarray(np.broadcast_to(np.asarray(A, np.float32), (n,)))
     out = np.zeros((_NCOEF[kind], n), np.float32)
     _check(lib().mlb_coeffs_batch(OP_ID[kind.upper()], n, om.ctypes.data, _ptr(kk), _ptr(aa), out.ctypes.data))
+    return out
+
+
+def coeffs_lopass_vec(omega, k) -> np.ndarray:
+    """Lopass::makeCoeffsVec for rows of 64 samples: omega, k of shape [..., 64] -> [..., 3, 64]
+    (rows g0, g1, g2 = inputs 1..3 of a LOPASS_V node).  Host libm, one C call."""
+    om = np.ascontiguousarray(omega, np.float32)
+    kk = np.ascontiguousarray(np.broadcast_to(np.asarray(k, np.float32), om.shape))
+    assert om.shape[-1] == BLOCK
+    out = np.empty(om.shape[:-1] + (3, BLOCK), np.float32)
+    lib().mlb_coeffs_lopass_vec_n(om.ctypes.data, kk.ctypes.data, out.ctypes.data, om.size // BLOCK)
+    return out
+
+
+def interpolate_coeffs_linear(c0, c1) -> np.ndarray:
+    """interpolateCoeffsLinear(c0, c1): [n_coeffs] x 2 -> [n_coeffs][64] ramps (LoShelf/HiShelf::vcoeffs when
+    c0 / c1 come from coeffs('loshelf' / 'hishelf', ...))."""
+    a, b = np.ascontiguousarray(c0, np.float32), np.ascontiguousarray(c1, np.float32)
+    assert a.shape == b.shape and a.ndim == 1
+    out = np.empty((a.shape[0], BLOCK), np.float32)
+    lib().mlb_interpolate_coeffs_linear(a.ctypes.data, b.ctypes.data, a.shape[0], out.ctypes.data)
     return out
 
 

@@ -37,6 +37,7 @@ constexpr int kBlockBytes = 2 * kTileBytes;                 // 8192: 32 voices x
 constexpr int kChainMaxWarps = 14;                          // 14 x 2 stages x 8 KB = 224 KB per SM
 constexpr int kMaxChainState = 8;
 constexpr int kMaxChainCoef = 16;
+constexpr int kMaxChainRows = 6;                            // coefficient rows of a *_V filter (HiShelf: 6)
 
 __host__ __device__ constexpr int op_ns(int op)
 {
@@ -101,6 +102,7 @@ struct ChainArgs
   int chunk_blocks, n_chunks;   // blocks per work unit, units per group
   int st_idx[kMaxChainState];  // SoA word index of each register state slot
   int co_idx[kMaxChainCoef];
+  int cv_plane[kMaxChainRows];  // input plane of each coefficient ROW of a LOPASS_V-class filter
 };
 
 // GEN: generator op id or -1 (the chain filters the source directly)
@@ -117,15 +119,23 @@ struct Chain
   static constexpr int NC_F2 = F2 >= 0 ? op_nc(F2) : 0;
   static constexpr int NC = NC_SRC + NC_F1 + NC_F2 + (GAIN ? 1 : 0);
   static constexpr bool HAS_IN = (SRC == SRC_INPUT);
-  static_assert(NS <= kMaxChainState && NC <= kMaxChainCoef, "chain too large");
+  // F1 may be a filter whose coefficients are per-sample ROWS (LOPASS_V ...): NV extra input planes
+  static constexpr bool F1_V = (F1 == MLB_OP_LOPASS_V || F1 == MLB_OP_LOSHELF_V || F1 == MLB_OP_HISHELF_V);
+  static constexpr int NV = F1_V ? op_nin(F1) - 1 : 0;
+  static constexpr int NP = (HAS_IN ? 1 : 0) + NV;  // planes a stage of the ring holds (TMA loads per block)
+  static constexpr int NPB = NP > 0 ? NP : 1;       // 8-KB blocks per stage (the output is written over plane 0)
+  static_assert(NS <= kMaxChainState && NC <= kMaxChainCoef && NV <= kMaxChainRows, "chain too large");
 
   static MLB_DEV float tick(float in, uint32_t (&st)[NS > 0 ? NS : 1],
-                            const float (&co)[NC > 0 ? NC : 1])
+                            const float (&co)[NC > 0 ? NC : 1], const float* cv)
   {
     float x = (SRC == SRC_INPUT) ? in : ((SRC == SRC_PARAM) ? co[0] : 0.0f);
     float y = x;
     if (GEN >= 0) y = gen_tick<EX>(GEN, x, 0.0f, &st[0]);
-    if (F1 >= 0) y = filter_tick<EX>(F1, y, &st[NS_GEN], &co[NC_SRC]);
+    if (F1_V)
+      y = vfilter_tick<EX>(F1, y, &st[NS_GEN], cv);
+    else if (F1 >= 0)
+      y = filter_tick<EX>(F1, y, &st[NS_GEN], &co[NC_SRC]);
     if (F2 >= 0) y = filter_tick<EX>(F2, y, &st[NS_GEN + NS_F1], &co[NC_SRC + NC_F1]);
     if (GAIN) y = A<EX>::mul(y, co[NC - 1]);  // operator*(DSPVector, DSPVector(float)), O:345-348
     return y;
@@ -159,8 +169,9 @@ __global__ void __launch_bounds__(kChainMaxWarps * 32)
 
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();  // the swizzle formula below assumes 1024-byte aligned tiles
-  const uint32_t blocks = base + (uint32_t)(warp * S) * kBlockBytes;
-  const uint32_t bars = base + (uint32_t)(W * S) * kBlockBytes + (uint32_t)(warp * S) * 8u;
+  constexpr uint32_t kStageBytes = (uint32_t)P::NPB * kBlockBytes;
+  const uint32_t blocks = base + (uint32_t)(warp * S) * kStageBytes;
+  const uint32_t bars = base + (uint32_t)(W * S) * kStageBytes + (uint32_t)(warp * S) * 8u;
 
   auto grab = [&]() -> int
   {
@@ -191,7 +202,7 @@ __global__ void __launch_bounds__(kChainMaxWarps * 32)
 
   if (lane == 0)
   {
-    if (P::HAS_IN)
+    if (P::NP > 0)
     {
       prefetch_tensormap(&in_map);
       for (int s = 0; s < S; ++s) mbar_init(bars + 8u * s, 1);
@@ -211,9 +222,14 @@ __global__ void __launch_bounds__(kChainMaxWarps * 32)
     const UnitCursor& u = ld_in_nxt ? nxt : cur;
     if (ld_blk >= u.nblk) return false;  // stream exhausted (or next unit not known yet)
     const uint32_t bar = bars + 8u * ld_stage;
-    mbar_arrive_expect_tx(bar, kBlockBytes);
-    tma_load_4d(blocks + (uint32_t)ld_stage * kBlockBytes, &in_map, bar, 0, u.g * kTileVoices, 0,
-                (u.t0 + ld_blk) * a.n_in_planes + a.in_plane, kEvictFirst);
+    mbar_arrive_expect_tx(bar, (uint32_t)P::NP * kBlockBytes);
+    const uint32_t dst = blocks + (uint32_t)ld_stage * kStageBytes;
+    const int z0 = (u.t0 + ld_blk) * a.n_in_planes;
+    if (P::HAS_IN) tma_load_4d(dst, &in_map, bar, 0, u.g * kTileVoices, 0, z0 + a.in_plane, kEvictFirst);
+#pragma unroll
+    for (int p = 0; p < P::NV; ++p)
+      tma_load_4d(dst + (uint32_t)((P::HAS_IN ? 1 : 0) + p) * kBlockBytes, &in_map, bar, 0, u.g * kTileVoices, 0,
+                  z0 + a.cv_plane[p], kEvictFirst);
     if (++ld_stage == S) ld_stage = 0;
     if (++ld_blk == u.nblk && !ld_in_nxt)
     {
@@ -223,7 +239,7 @@ __global__ void __launch_bounds__(kChainMaxWarps * 32)
     return true;
   };
   int ahead = 0;  // (lane 0) loads issued minus blocks whose computation has started
-  if (P::HAS_IN && lane == 0)
+  if (P::NP > 0 && lane == 0)
     while (ahead < S - 1 && issue_next_load()) ++ahead;
 
   const uint32_t row_off = (uint32_t)lane * 128u;
@@ -271,8 +287,8 @@ __global__ void __launch_bounds__(kChainMaxWarps * 32)
         nxt = decode(grab());
         have_nxt = true;
       }
-      const uint32_t blk = blocks + (uint32_t)s * kBlockBytes;
-      if (P::HAS_IN)
+      const uint32_t blk = blocks + (uint32_t)s * kStageBytes;
+      if (P::NP > 0)
       {
         --ahead;
         mbar_wait(bars + 8u * s, parity);
@@ -298,12 +314,37 @@ __global__ void __launch_bounds__(kChainMaxWarps * 32)
         for (int j = 0; j < 8; ++j)
         {
           float4 y;
-          y.x = P::tick(xin[j].x, st, co);
-          y.y = P::tick(xin[j].y, st, co);
-          y.z = P::tick(xin[j].z, st, co);
-          y.w = P::tick(xin[j].w, st, co);
+          if (P::NV > 0)
+          {
+            // this quad of every coefficient row (same swizzled position in the following 8-KB planes)
+            float4 cq[P::NV > 0 ? P::NV : 1];
+#pragma unroll
+            for (int p = 0; p < P::NV; ++p)
+              cq[p] = lds128(tile + (uint32_t)((P::HAS_IN ? 1 : 0) + p) * kBlockBytes + row_off +
+                             (((uint32_t)j << 4) ^ sw));
+            float cv[P::NV > 0 ? P::NV : 1];
+#pragma unroll
+            for (int p = 0; p < P::NV; ++p) cv[p] = cq[p].x;
+            y.x = P::tick(xin[j].x, st, co, cv);
+#pragma unroll
+            for (int p = 0; p < P::NV; ++p) cv[p] = cq[p].y;
+            y.y = P::tick(xin[j].y, st, co, cv);
+#pragma unroll
+            for (int p = 0; p < P::NV; ++p) cv[p] = cq[p].z;
+            y.z = P::tick(xin[j].z, st, co, cv);
+#pragma unroll
+            for (int p = 0; p < P::NV; ++p) cv[p] = cq[p].w;
+            y.w = P::tick(xin[j].w, st, co, cv);
+          }
+          else
+          {
+            y.x = P::tick(xin[j].x, st, co, nullptr);
+            y.y = P::tick(xin[j].y, st, co, nullptr);
+            y.z = P::tick(xin[j].z, st, co, nullptr);
+            y.w = P::tick(xin[j].w, st, co, nullptr);
+          }
           sts128(tile + row_off + (((uint32_t)j << 4) ^ sw), y);
-          if (P::HAS_IN && j == 3 && h == 0 && lane == 0)
+          if (P::NP > 0 && j == 3 && h == 0 && lane == 0)
           {
             // Refill point, a quarter block after the previous block's store was issued: that
             // store has drained its shared-memory reads by now, so the wait does not stall.
@@ -380,7 +421,7 @@ __global__ void __launch_bounds__(kChainMaxWarps * 32)
       ld_in_nxt = 1;
       ld_blk = 0;
     }
-    if (P::HAS_IN && lane == 0 && ahead < S - 1)
+    if (P::NP > 0 && lane == 0 && ahead < S - 1)
     {
       if (a.write_out) bulk_wait_read<0>();  // all stages but the ones in flight are free again
       while (ahead < S - 1 && issue_next_load()) ++ahead;

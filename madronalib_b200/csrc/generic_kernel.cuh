@@ -30,8 +30,8 @@ enum
 struct GNode
 {
   int op;
-  int in_kind[3];
-  int in_ref[3];   // slot index or coef word index
+  int in_kind[MLB_MAX_INS];
+  int in_ref[MLB_MAX_INS];   // slot index or coef word index
   int out_slot;    // -1: node output never read as a row (PARAM)
   int out_slot2;   // FDN8: slot of the sumR row (read by FDN8_R), else -1
   int st_off, co_off;
@@ -191,6 +191,74 @@ MLB_DEV void dispatch_stateless(int op, RowRef x, RowRef b, RowRef c, uint32_t o
   }
 }
 
+
+// filters with coefficient ROWS (LOPASS_V / LOSHELF_V / HISHELF_V) and the device-designed LOPASS_MOD:
+// operand 0 is the audio row, operands 1.. the per-sample coefficient rows (or PARAM constants)
+template <int OP, bool EX>
+MLB_DEV void run_vfilter_node(const GNode& nd, const GenericArgs& a, int v, bool live, uint32_t rows,
+                              uint32_t out_addr)
+{
+  constexpr int NR = op_nin(OP) - 1;
+  RowRef x, c[NR];
+  x.is_row = nd.in_kind[0] == OPERAND_SLOT;
+  x.addr = rows + (uint32_t)nd.in_ref[0] * kSlotBytes;
+  x.k = (nd.in_kind[0] == OPERAND_PARAM && live) ? a.coef[(size_t)nd.in_ref[0] * a.V + v] : 0.f;
+#pragma unroll
+  for (int k = 0; k < NR; ++k)
+  {
+    c[k].is_row = nd.in_kind[k + 1] == OPERAND_SLOT;
+    c[k].addr = rows + (uint32_t)nd.in_ref[k + 1] * kSlotBytes;
+    c[k].k = (nd.in_kind[k + 1] == OPERAND_PARAM && live) ? a.coef[(size_t)nd.in_ref[k + 1] * a.V + v] : 0.f;
+  }
+  uint32_t st[2];
+  st[0] = live ? a.state[(size_t)nd.st_off * a.V + v] : 0u;
+  st[1] = live ? a.state[(size_t)(nd.st_off + 1) * a.V + v] : 0u;
+#pragma unroll 1
+  for (int q = 0; q < 16; ++q)
+  {
+    const float4 xi = x.get4(q);
+    float4 ci[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) ci[k] = c[k].get4(q);
+    float cv[NR];
+    float4 y;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) cv[k] = ci[k].x;
+    y.x = vfilter_tick<EX>(OP, xi.x, st, cv);
+#pragma unroll
+    for (int k = 0; k < NR; ++k) cv[k] = ci[k].y;
+    y.y = vfilter_tick<EX>(OP, xi.y, st, cv);
+#pragma unroll
+    for (int k = 0; k < NR; ++k) cv[k] = ci[k].z;
+    y.z = vfilter_tick<EX>(OP, xi.z, st, cv);
+#pragma unroll
+    for (int k = 0; k < NR; ++k) cv[k] = ci[k].w;
+    y.w = vfilter_tick<EX>(OP, xi.w, st, cv);
+    sts128(out_addr + (uint32_t)q * 16u, y);
+  }
+  if (live)
+  {
+    a.state[(size_t)nd.st_off * a.V + v] = st[0];
+    a.state[(size_t)(nd.st_off + 1) * a.V + v] = st[1];
+  }
+}
+
+// RAMP(start, end) = interpolateDSPVectorLinear(start[0], end[0]), O:986-990
+template <bool EX>
+MLB_DEV void run_ramp_node(RowRef s, RowRef e, uint32_t out_addr)
+{
+  const float s0 = s.get(0), e0 = e.get(0);
+#pragma unroll 4
+  for (int q = 0; q < 16; ++q)
+  {
+    float4 y;
+    y.x = ramp_sample<EX>(s0, e0, 4 * q);
+    y.y = ramp_sample<EX>(s0, e0, 4 * q + 1);
+    y.z = ramp_sample<EX>(s0, e0, 4 * q + 2);
+    y.w = ramp_sample<EX>(s0, e0, 4 * q + 3);
+    sts128(out_addr + (uint32_t)q * 16u, y);
+  }
+}
 
 // ---- SURVEY 8(f) row 2 node runners (device functions in functors.cuh) ----
 
@@ -1040,6 +1108,11 @@ __global__ void __launch_bounds__(32) generic_graph_kernel(const GenericArgs a)
           MLB_FUN_CASE(MLB_OP_ALLPASS1)
           MLB_FUN_CASE(MLB_OP_SAMPLE_GLIDE)
 #undef MLB_FUN_CASE
+        case MLB_OP_LOPASS_V: run_vfilter_node<MLB_OP_LOPASS_V, EX>(nd, a, v, live, rows, o); break;
+        case MLB_OP_LOSHELF_V: run_vfilter_node<MLB_OP_LOSHELF_V, EX>(nd, a, v, live, rows, o); break;
+        case MLB_OP_HISHELF_V: run_vfilter_node<MLB_OP_HISHELF_V, EX>(nd, a, v, live, rows, o); break;
+        case MLB_OP_LOPASS_MOD: run_vfilter_node<MLB_OP_LOPASS_MOD, EX>(nd, a, v, live, rows, o); break;
+        case MLB_OP_RAMP: run_ramp_node<EX>(r[0], r[1], o); break;
         case MLB_OP_GLIDE: run_glide_node<EX>(nd, a, v, live, r[0], o); break;
         case MLB_OP_INTERPOLATOR1: run_interp1_node<EX>(nd, a, v, live, r[0], o); break;
         case MLB_OP_INTEGER_DELAY: run_int_delay_node<EX>(nd, a, v, live, t, r[0], o); break;

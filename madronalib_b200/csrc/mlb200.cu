@@ -291,6 +291,37 @@ extern "C" void mlb_coeffs_sample_glide(float t, float o[2])
   o[0] = (float)n;
   o[1] = 1.0f / (float)n;
 }
+// Lopass::makeCoeffsVec, F:97-115 (clamps by _mm_min_ps / _mm_max_ps operand order, then per-sample makeCoeffs)
+extern "C" void mlb_coeffs_lopass_vec(const float omega[64], const float k[64], float out[3 * 64])
+{
+  for (int n = 0; n < MLB_BLOCK; ++n)
+  {
+    const float om = omega[n] < 0.5f ? omega[n] : 0.5f;  // min(omega, DSPVector(0.5f))
+    const float kk = k[n] > 0.01f ? k[n] : 0.01f;        // max(k, DSPVector(0.01f))
+    svf_g(om, kk, &out[n], &out[MLB_BLOCK + n], &out[2 * MLB_BLOCK + n]);
+  }
+}
+extern "C" void mlb_coeffs_lopass_vec_n(const float* omega, const float* k, float* out, size_t n_rows)
+{
+  for (size_t r = 0; r < n_rows; ++r)
+    mlb_coeffs_lopass_vec(omega + r * MLB_BLOCK, k + r * MLB_BLOCK, out + r * 3 * MLB_BLOCK);
+}
+// interpolateCoeffsLinear, F:32-44; interpolateDSPVectorLinear, O:986-990 (columnIndex() * interval + (start + interval))
+extern "C" void mlb_interpolate_coeffs_linear(const float* c0, const float* c1, int n_coeffs, float* out)
+{
+  for (int i = 0; i < n_coeffs; ++i)
+  {
+    volatile float diff = c1[i] - c0[i];
+    volatile float interval = diff / (float)MLB_BLOCK;
+    volatile float base = c0[i] + interval;
+    for (int n = 0; n < MLB_BLOCK; ++n)
+    {
+      volatile float ramp = (float)n * interval;
+      out[(size_t)i * MLB_BLOCK + n] = ramp + base;
+    }
+  }
+}
+
 // n voices at once: out[word][n] (the SoA layout of mlb_graph_set_coefs).  kind = the node op.
 extern "C" int mlb_coeffs_batch(int op, size_t n, const float* omega, const float* k, const float* A, float* out)
 {
@@ -442,6 +473,7 @@ struct FusedEntry
   ChainKernelFn fn;
   const char* name;
   bool has_in;
+  int n_planes;  // 8-KB planes a ring stage holds (Chain::NP): the input row and/or coefficient rows
 };
 
 #define N_ (-1)
@@ -463,14 +495,18 @@ struct FusedEntry
   X(MLB_OP_NOISE, SRC_NONE, MLB_OP_LOPASS, N_, true)                        \
   X(N_, SRC_INPUT, MLB_OP_LOPASS, N_, false)                                \
   X(N_, SRC_INPUT, MLB_OP_ONEPOLE, N_, false)                               \
-  X(N_, SRC_INPUT, MLB_OP_DCBLOCKER, N_, false)
+  X(N_, SRC_INPUT, MLB_OP_DCBLOCKER, N_, false)                             \
+  /* swept filter: coefficient ROWS as three more input planes (20 B per voice-sample) */ \
+  X(MLB_OP_SINE, SRC_INPUT, MLB_OP_LOPASS_V, N_, true)                      \
+  X(MLB_OP_SINE, SRC_PARAM, MLB_OP_LOPASS_V, N_, true)                      \
+  X(N_, SRC_INPUT, MLB_OP_LOPASS_V, N_, false)
 
 static const FusedEntry g_fused[] = {
 #define MLB_X_ENTRY(G, S, F1, F2, GN)                                                          \
   {G, S, F1, F2, GN, 1, chain_kernel<Chain<G, S, F1, F2, GN, true>>, #G "+" #F1 "+" #F2 "+" #GN, \
-   S == SRC_INPUT},                                                                            \
+   S == SRC_INPUT, Chain<G, S, F1, F2, GN, true>::NP},                                         \
       {G, S, F1, F2, GN, 0, chain_kernel<Chain<G, S, F1, F2, GN, false>>,                        \
-       #G "+" #F1 "+" #F2 "+" #GN "(fast)", S == SRC_INPUT},
+       #G "+" #F1 "+" #F2 "+" #GN "(fast)", S == SRC_INPUT, Chain<G, S, F1, F2, GN, false>::NP},
     MLB_FUSED_LIST(MLB_X_ENTRY)
 #undef MLB_X_ENTRY
 };
@@ -587,6 +623,7 @@ static bool is_filter(int op)
   }
   return false;
 }
+static bool is_vfilter(int op) { return op == MLB_OP_LOPASS_V || op == MLB_OP_LOSHELF_V || op == MLB_OP_HISHELF_V; }
 static bool is_gen1(int op)
 {
   return op == MLB_OP_SINE || op == MLB_OP_PHASOR || op == MLB_OP_SAW || op == MLB_OP_TICK;
@@ -614,7 +651,7 @@ static bool match_fused_chain(mlb_graph* g)
   }
   int filt[2] = {-1, -1};
   int nf = 0;
-  while (is_filter(N[y].op))
+  while (is_filter(N[y].op) || is_vfilter(N[y].op))
   {
     if (nf == 2) return false;
     filt[nf++] = y;
@@ -649,6 +686,18 @@ static bool match_fused_chain(mlb_graph* g)
     else
       return false;
   }
+  // a coefficient-row filter is fused only as F1, with every coefficient row an external INPUT plane
+  if (f2 >= 0 && is_vfilter(N[f2].op)) return false;
+  if (f1 >= 0 && is_vfilter(N[f1].op))
+  {
+    int nin = 0;
+    mlb_op_info(N[f1].op, &nin, nullptr, nullptr);
+    for (int k = 1; k < nin; ++k)
+    {
+      if (N[N[f1].in[k]].op != MLB_OP_INPUT) return false;
+      used[N[f1].in[k]] = 1;
+    }
+  }
   for (char u : used)
     if (!u) return false;  // every node must be on the chain (unused stateful nodes still tick)
   const int f1op = f1 >= 0 ? N[f1].op : -1, f2op = f2 >= 0 ? N[f2].op : -1;
@@ -681,6 +730,12 @@ static bool match_fused_chain(mlb_graph* g)
       if (f2 >= 0) add_coef(f2);
       if (gain_node >= 0) add_coef(gain_node);
       c.in_plane = (src == SRC_INPUT) ? N[src_node].iarg : 0;
+      if (f1 >= 0 && is_vfilter(N[f1].op))
+      {
+        int nin = 0;
+        mlb_op_info(N[f1].op, &nin, nullptr, nullptr);
+        for (int k = 1; k < nin; ++k) c.cv_plane[k - 1] = N[N[f1].in[k]].iarg;
+      }
       g->kernel_name = std::string("fused:") + e.name;
       return true;
     }
@@ -1360,17 +1415,19 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
   // queue.  W is a multiple of 4 so the four SM sub-partitions carry equal warp counts; small
   // banks simply get one warp per group.
   const size_t budget = (size_t)g_smem_optin - 64;
+  const size_t stage_bytes = (size_t)std::max(1, e.n_planes) * kBlockBytes;  // a ring stage holds n_planes blocks
   int W, S;
   if (n_groups <= g_sm_count * 4)
     W = std::max(1, (n_groups + g_sm_count - 1) / g_sm_count);
   else
     W = 12;  // 3 warps per SM sub-partition, 2-stage rings (197 KB): measured best (profiles/)
+  W = std::min(W, (int)(budget / (2 * (stage_bytes + 8))));  // multi-plane stages: fewer warps fit
   W = env_int("MLB_CHAIN_WARPS", W);
   W = std::min(std::max(W, 1), kChainMaxWarps);
   S = 2;
-  if (e.has_in)
+  if (e.n_planes > 0)
   {
-    S = (int)(budget / ((size_t)W * (kBlockBytes + 8)));
+    S = (int)(budget / ((size_t)W * (stage_bytes + 8)));
     S = std::min(std::max(S, 2), 6);
     S = env_int("MLB_CHAIN_STAGES", S);
     S = std::min(std::max(S, 2), 12);
@@ -1393,7 +1450,7 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
     g->launch_chunks = a.n_chunks;
     CU_CHECK(cudaMemsetAsync(g->d_sched, 0, 4, stream));
   }
-  const size_t smem = (size_t)W * S * kBlockBytes + (size_t)W * S * 8;
+  const size_t smem = (size_t)W * S * stage_bytes + (size_t)W * S * 8;
   if (smem > g_smem_optin) return fail(MLB_ERR_INVALID, "chain launch needs %zu B shared memory", smem);
   const int ctas_per_sm = std::max<size_t>(1, (size_t)(227 * 1024) / (smem + 1024));
   // the grid is persistent and fills every SM's shared memory; a caller that overlaps a collective
@@ -1404,7 +1461,7 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
   CUtensorMap in_map, out_map;
   memset(&in_map, 0, sizeof(in_map));
   memset(&out_map, 0, sizeof(out_map));
-  if (e.has_in)
+  if (e.n_planes > 0)
   {
     rc = make_block_map(&in_map, in_dev + (size_t)va * MLB_BLOCK, Vs, (long long)T * a.n_in_planes,
                         (long long)V * MLB_BLOCK);

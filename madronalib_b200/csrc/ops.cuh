@@ -488,6 +488,69 @@ MLB_DEV float filter_tick(int op, float x, uint32_t* st, const float* co)
   return x;
 }
 
+// ---- filters whose coefficients are per-sample rows (the reference's modulated forms) ----
+
+// Lopass::makeCoeffsVec for one sample, F:102-113, evaluated on the device.  Same operation sequence as
+// the reference; sinf is CUDA's (<= 1 ulp), not glibc's: tolerance-only (LOPASS_MOD).
+template <bool EX>
+MLB_DEV void lopass_coeffs_device(float omega, float k, float& g0, float& g1, float& g2)
+{
+  using a = A<EX>;
+  omega = sse_min(omega, 0.5f);  // F:101
+  k = sse_max(k, 0.01f);         // F:102
+  const float piOmega = a::mul(3.1415926535897932384626433f, omega);
+  const float s1 = sinf(piOmega);
+  const float s2 = sinf(a::mul(2.0f, piOmega));
+  const float ks2 = a::mul(k, s2);
+  const float nrm = __fdiv_rn(1.0f, a::add(2.f, ks2));
+  const float s1s1x2 = a::mul(a::mul(2.0f, s1), s1);  // (2*s1)*s1: the doubling is exact, sign applied below
+  g0 = a::mul(s2, nrm);
+  g1 = a::mul(a::sub(-s1s1x2, ks2), nrm);
+  g2 = a::mul(s1s1x2, nrm);
+}
+
+// cv = this sample's coefficient values in the order of the reference's coeffNames enums
+template <bool EX>
+MLB_DEV float vfilter_tick(int op, float x, uint32_t* st, const float* cv)
+{
+  using a = A<EX>;
+  float ic1 = u2f(st[0]), ic2 = u2f(st[1]), v1, v2, y = x;
+  switch (op)
+  {
+    case MLB_OP_LOPASS_V:  // F:141-149
+      svf_g_core<EX>(x, cv[0], cv[1], cv[2], ic1, ic2, v1, v2);
+      y = v2;
+      break;
+    case MLB_OP_LOPASS_MOD:
+    {
+      float g0, g1, g2;
+      lopass_coeffs_device<EX>(cv[0], cv[1], g0, g1, g2);
+      svf_g_core<EX>(x, g0, g1, g2, ic1, ic2, v1, v2);
+      y = v2;
+      break;
+    }
+    case MLB_OP_LOSHELF_V:  // F:309-316
+      svf_a_core<EX>(x, cv[0], cv[1], cv[2], ic1, ic2, v1, v2);
+      y = a::add(a::add(x, a::mul(cv[3], v1)), a::mul(cv[4], v2));
+      break;
+    case MLB_OP_HISHELF_V:  // F:390-397
+      svf_a_core<EX>(x, cv[0], cv[1], cv[2], ic1, ic2, v1, v2);
+      y = a::add(a::mul_add_mul(cv[3], x, cv[4], v1), a::mul(cv[5], v2));
+      break;
+  }
+  st[0] = f2u(ic1), st[1] = f2u(ic2);
+  return y;
+}
+
+// interpolateDSPVectorLinear(start, end)[n], O:986-990: columnIndex()*interval + (start + interval)
+template <bool EX>
+MLB_DEV float ramp_sample(float start, float end, int n)
+{
+  using a = A<EX>;
+  const float interval = __fdiv_rn(a::sub(end, start), 64.0f);
+  return a::add(a::mul((float)n, interval), a::add(start, interval));
+}
+
 // per-sample tick of a generator node.  in0 = freq, in1 = width (PULSE)
 template <bool EX>
 MLB_DEV float gen_tick(int op, float in0, float in1, uint32_t* st)

@@ -19,7 +19,6 @@ from typing import Dict, List, Sequence, Tuple
 import numpy as np
 
 BLOCK = 64  # kFloatsPerDSPVector, reference source/DSP/MLDSPMath.h:8-9
-MAX_INS = 3
 
 _HEADER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "include", "mlb200.h")
 
@@ -47,6 +46,13 @@ def _parse_mem_table() -> Dict[str, Tuple[int, int]]:
             for m in re.finditer(r"X\(\s*([A-Z0-9_]+)\s*,\s*(\d+)\s*,\s*(\d+)\s*\)", text[start:end])}
 
 
+def _parse_define(name: str) -> int:
+    with open(_HEADER, "r") as f:
+        return int(re.search(r"#define\s+" + name + r"\s+(\d+)", f.read()).group(1))
+
+
+MAX_INS = _parse_define("MLB_MAX_INS")
+ABI_VERSION = _parse_define("MLB_ABI_VERSION")
 OP_TABLE = _parse_op_table()
 OP_MEM = _parse_mem_table()
 OP_ID = {name: v[0] for name, v in OP_TABLE.items()}

@@ -446,6 +446,116 @@ def config_6(n_voices: int = 4096) -> Workload:
     return w
 
 
+# ---- coefficient-ROW (modulated / swept) filters: MLDSPFilters.h:97-115,136-152,283-286,304-319,385-400 ----
+
+SWEPT_CASES = ("lopass_v", "sine_lopass_v_gain", "lopass_v_const", "lopass_mod", "loshelf_v", "hishelf_v",
+               "loshelf_ramp")
+
+
+def swept_omega_k(n_voices: int, n_blocks: int, t0: int = 0):
+    """Per-voice cutoff / resonance sweeps (signal rate): omega in [0.02, 0.32], k in [0.05, 1.55]; [T][V][64]."""
+    n = (np.arange(n_blocks * BLOCK, dtype=np.float64) + t0 * BLOCK)[None, :]
+    v = np.arange(n_voices, dtype=np.float64)[:, None]
+    omega = 0.02 + 0.3 * (0.5 + 0.5 * np.sin(n * (0.0021 + 1e-5 * v) + 0.37 * v))
+    k = 0.05 + 1.5 * (0.5 + 0.5 * np.cos(n * 0.0013 + 0.11 * v))
+    shp = (n_voices, n_blocks, BLOCK)
+    return (np.ascontiguousarray(omega.astype(np.float32).reshape(shp).transpose(1, 0, 2)),
+            np.ascontiguousarray(k.astype(np.float32).reshape(shp).transpose(1, 0, 2)))
+
+
+def shelf_endpoints(kind: str, n_voices: int, n_points: int, t0: int = 0) -> np.ndarray:
+    """Block-rate shelf coefficients {makeCoeffs(p_t)}: p_t = (omega, k, A) moving slowly; [n_points][n_coef][V]."""
+    out = np.zeros((n_points, api._NCOEF[kind], n_voices), np.float32)
+    v = np.arange(n_voices, dtype=np.float64)
+    for i in range(n_points):
+        t = t0 + i
+        omega = (0.03 + 0.2 * (0.5 + 0.5 * np.sin(0.31 * t + 0.2 * v))).astype(np.float32)
+        k = (0.4 + 0.8 * (0.5 + 0.5 * np.cos(0.17 * t + 0.05 * v))).astype(np.float32)
+        db = -9.0 + 18.0 * (0.5 + 0.5 * np.sin(0.23 * t + 0.4 * v))
+        A = np.power(np.float32(10.0), (db / 40.0).astype(np.float32)).astype(np.float32)
+        out[i] = api.coeffs_batch(kind, omega, k, A)
+    return out
+
+
+def swept_filter_case(name: str, n_voices: int = 40, n_blocks: int = 8, x=None, omega=None, k=None) -> Workload:
+    """name in SWEPT_CASES.  Audio = seeded noise (or `x` [T][V][64]); coefficient rows designed on the host
+    with the library's own mlb_coeffs_* calls; `omega`, `k` override the sweeps."""
+    V = n_voices
+    g = GraphSpec()
+    noise = _noise_rows(21, V, 0.5)
+    audio = (lambda T, t0: noise(T, t0)[:, 0]) if x is None else (lambda T, t0: np.asarray(x, np.float32)[t0:t0 + T])
+
+    def sweeps(T, t0):
+        if omega is not None:
+            return np.asarray(omega, np.float32)[t0:t0 + T], np.asarray(k, np.float32)[t0:t0 + T]
+        return swept_omega_k(V, T, t0)
+
+    coef = state = None
+    if name in ("lopass_v", "sine_lopass_v_gain"):
+        src = g.input(0)
+        if name == "sine_lopass_v_gain":
+            src = g.node("SINE", src)
+        lp = g.node("LOPASS_V", src, g.input(1), g.input(2), g.input(3))
+        if name == "sine_lopass_v_gain":
+            lp = g.node("MULTIPLY", lp, g.param())
+        g.output(lp)
+        coef, state = g.new_coefs(V), g.new_state(V)
+        if name == "sine_lopass_v_gain":
+            coef[0] = np.float32(0.1)
+            state[0] = SINE_ZERO_PHASE
+
+        def fn(T, t0):
+            om, kk = sweeps(T, t0)
+            rows = api.coeffs_lopass_vec(om, kk)                        # [T][V][3][64]
+            first = freq_rows(V, T, t0)[:, 0] if name == "sine_lopass_v_gain" else audio(T, t0)
+            return np.ascontiguousarray(np.concatenate([first[:, None], rows.transpose(0, 2, 1, 3)], axis=1))
+    elif name == "lopass_v_const":
+        lp = g.node("LOPASS_V", g.input(0), g.param(), g.param(), g.param())
+        g.output(lp)
+        coef, state = g.new_coefs(V), g.new_state(V)
+        coef[0:3] = _svf_coefs("lopass", V)
+        fn = lambda T, t0: np.ascontiguousarray(audio(T, t0)[:, None])
+    elif name == "lopass_mod":
+        g.output(g.node("LOPASS_MOD", g.input(0), g.input(1), g.input(2)))
+        coef, state = g.new_coefs(V), g.new_state(V)
+
+        def fn(T, t0):
+            om, kk = sweeps(T, t0)
+            return np.ascontiguousarray(np.stack([audio(T, t0), om, kk], axis=1))
+    elif name in ("loshelf_v", "hishelf_v"):
+        kind = name[:-2]
+        nco = api._NCOEF[kind]
+        g.output(g.node(name.upper(), g.input(0), *[g.input(1 + i) for i in range(nco)]))
+        coef, state = g.new_coefs(V), g.new_state(V)
+
+        def fn(T, t0):
+            ep = shelf_endpoints(kind, V, T + 1, t0)                    # block t ramps from ep[t] to ep[t+1]
+            rows = np.empty((T, nco, V, BLOCK), np.float32)
+            for t in range(T):
+                for v in range(V):
+                    rows[t, :, v] = api.interpolate_coeffs_linear(ep[t, :, v], ep[t + 1, :, v])
+            return np.ascontiguousarray(np.concatenate([audio(T, t0)[:, None], rows], axis=1))
+    elif name == "loshelf_ramp":
+        # interpolateCoeffsLinear on the device: one RAMP per coefficient from two endpoint rows (sample 0 is read)
+        ramps = [g.node("RAMP", g.input(1 + 2 * i), g.input(2 + 2 * i)) for i in range(5)]
+        g.output(g.node("LOSHELF_V", g.input(0), *ramps))
+        coef, state = g.new_coefs(V), g.new_state(V)
+
+        def fn(T, t0):
+            ep = shelf_endpoints("loshelf", V, T + 1, t0)
+            planes = np.zeros((T, 11, V, BLOCK), np.float32)
+            planes[:, 0] = audio(T, t0)
+            for i in range(5):
+                planes[:, 1 + 2 * i, :, 0] = ep[:T, i]
+                planes[:, 2 + 2 * i, :, 0] = ep[1:T + 1, i]
+            return planes
+    else:
+        raise ValueError(name)
+    w = Workload("swept_" + name, g, V, coef, state)
+    w.inputs = _rows_inputs(fn)  # type: ignore[assignment]
+    return w
+
+
 # ---- SURVEY 8(f) row 3: per-voice event records for the EventsToSignals::Voice bank ----
 
 VOICE_EVENTS_DTYPE = np.dtype([("n_events", "u1"), ("set_mask", "u1"), ("pad", "u1", (2,)),

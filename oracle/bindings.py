@@ -69,6 +69,15 @@ class _Oracle:
         getattr(L, p + "coeffs_allpass1").restype = ctypes.c_float
 
     # -- coefficient design --
+    def coeffs_lopass_vec(self, omega: np.ndarray, k: np.ndarray) -> np.ndarray:
+        """Lopass::makeCoeffsVec for one block: omega[64], k[64] -> [3][64]."""
+        om, kk = np.ascontiguousarray(omega, np.float32), np.ascontiguousarray(k, np.float32)
+        out = np.empty((3, BLOCK), np.float32)
+        f = getattr(self.lib, self.prefix + "coeffs_lopass_vec")
+        f.argtypes, f.restype = [_vp, _vp, _vp], None
+        f(_ptr(om), _ptr(kk), _ptr(out))
+        return out
+
     def coeffs(self, kind: str, *args: float) -> np.ndarray:
         n = {"lopass": 3, "hipass": 4, "bandpass": 3, "loshelf": 5, "hishelf": 6, "bell": 4,
              "onepole": 2, "peak": 2, "rms": 2, "adsr": 4, "glide": 2, "sample_glide": 2}[kind]
@@ -148,6 +157,24 @@ class RefOracle(_Oracle):
         self.lib.mlref_aaltoverb.restype = ctypes.c_double
         self.lib.mlref_aaltoverb.argtypes = [ctypes.c_int, _vp, _vp, ctypes.c_float, ctypes.c_float,
                                              ctypes.c_float, ctypes.c_int]
+
+    def shelf_vcoeffs(self, kind: str, p0, p1) -> np.ndarray:
+        """LoShelf / HiShelf::vcoeffs({omega,k,A}, {omega,k,A}) -> [5 or 6][64]."""
+        a, b = np.ascontiguousarray(p0, np.float32), np.ascontiguousarray(p1, np.float32)
+        out = np.empty((5 if kind == "loshelf" else 6, BLOCK), np.float32)
+        f = getattr(self.lib, "mlref_%s_vcoeffs" % kind)
+        f.argtypes, f.restype = [_vp, _vp, _vp], None
+        f(_ptr(a), _ptr(b), _ptr(out))
+        return out
+
+    def lopass_mod(self, x: np.ndarray, omega: np.ndarray, k: np.ndarray) -> np.ndarray:
+        """Lopass::operator()(vx, omega, k) for ONE voice from cleared state; all [T][64]."""
+        x, omega, k = (np.ascontiguousarray(a, np.float32) for a in (x, omega, k))
+        out = np.empty_like(x)
+        f = self.lib.mlref_lopass_mod
+        f.argtypes, f.restype = [ctypes.c_int, _vp, _vp, _vp, _vp], None
+        f(x.shape[0], _ptr(x), _ptr(omega), _ptr(k), _ptr(out))
+        return out
 
     def upsample2x_clip(self, inp: np.ndarray, drive: float) -> np.ndarray:
         """Upsample2xFunction<1> with fn = clamp(v * drive, -1, 1) for ONE voice; inp [T][64]."""

@@ -527,6 +527,67 @@ static void flt_bell(uint32_t* st, const float* c, const float* x, float* y)
   st[0] = f2u(ic1), st[1] = f2u(ic2);
 }
 
+/* ---- coefficient-ROW forms: Lopass::operator()(vx, omega, k) after makeCoeffsVec (F:136-152),
+ * LoShelf / HiShelf::operator()(vx, vc) (F:304-319, 385-400).  r[i] = coefficient row i. ---- */
+static void flt_lopass_v(uint32_t* st, const float* const* r, const float* x, float* y)
+{
+  float ic1 = u2f(st[0]), ic2 = u2f(st[1]);
+  for (int n = 0; n < NB; ++n)
+  {
+    const float g0 = r[0][n], g1 = r[1][n], g2 = r[2][n];
+    SVF_G_CORE
+    float v2 = t2 + ic2;
+    ic1 += 2.0f * t1;
+    ic2 += 2.0f * t2;
+    y[n] = v2;
+  }
+  st[0] = f2u(ic1), st[1] = f2u(ic2);
+}
+static void flt_loshelf_v(uint32_t* st, const float* const* r, const float* x, float* y)
+{
+  float ic1 = u2f(st[0]), ic2 = u2f(st[1]);
+  for (int n = 0; n < NB; ++n)
+  {
+    const float a1 = r[0][n], a2 = r[1][n], a3 = r[2][n], m1 = r[3][n], m2 = r[4][n];
+    SVF_A_CORE
+    y[n] = v0 + m1 * v1 + m2 * v2;
+  }
+  st[0] = f2u(ic1), st[1] = f2u(ic2);
+}
+static void flt_hishelf_v(uint32_t* st, const float* const* r, const float* x, float* y)
+{
+  float ic1 = u2f(st[0]), ic2 = u2f(st[1]);
+  for (int n = 0; n < NB; ++n)
+  {
+    const float a1 = r[0][n], a2 = r[1][n], a3 = r[2][n], m0 = r[3][n], m1 = r[4][n], m2 = r[5][n];
+    SVF_A_CORE
+    y[n] = m0 * v0 + m1 * v1 + m2 * v2;
+  }
+  st[0] = f2u(ic1), st[1] = f2u(ic2);
+}
+static void svf_g(float omega, float k, float* g0, float* g1, float* g2);
+/* Lopass::makeCoeffsVec, F:97-115 */
+void mlport_coeffs_lopass_vec(const float* omega, const float* k, float* out)
+{
+  for (int n = 0; n < NB; ++n)
+  {
+    const float om = omega[n] < 0.5f ? omega[n] : 0.5f; /* _mm_min_ps(omega, 0.5) */
+    const float kk = k[n] > 0.01f ? k[n] : 0.01f;       /* _mm_max_ps(k, 0.01) */
+    svf_g(om, kk, &out[n], &out[NB + n], &out[2 * NB + n]);
+  }
+}
+/* interpolateDSPVectorLinear, O:986-990 */
+static void ramp_row(float start, float end, float* y)
+{
+  const float interval = (end - start) / (float)NB;
+  const float base = start + interval;
+  for (int n = 0; n < NB; ++n) y[n] = (float)n * interval + base;
+}
+void mlport_interpolate_coeffs_linear(const float* c0, const float* c1, int n_coeffs, float* out)
+{
+  for (int i = 0; i < n_coeffs; ++i) ramp_row(c0[i], c1[i], out + (size_t)i * NB);
+}
+
 /* OnePole::operator(), F:466-475 */
 static void flt_onepole(uint32_t* st, const float* c, const float* x, float* y)
 {
@@ -1428,6 +1489,26 @@ static void run_voices(mlport_graph* g, const float* in, float* out, int T, int 
           case MLB_OP_LOSHELF: flt_loshelf(st, co, a, y); break;
           case MLB_OP_HISHELF: flt_hishelf(st, co, a, y); break;
           case MLB_OP_BELL: flt_bell(st, co, a, y); break;
+          case MLB_OP_LOPASS_V:
+          case MLB_OP_LOSHELF_V:
+          case MLB_OP_HISHELF_V:
+          {
+            const float* r[MLB_MAX_INS - 1];
+            for (int k = 1; k < nin; ++k) r[k - 1] = rows[nd->in[k]];
+            if (nd->op == MLB_OP_LOPASS_V) flt_lopass_v(st, r, a, y);
+            if (nd->op == MLB_OP_LOSHELF_V) flt_loshelf_v(st, r, a, y);
+            if (nd->op == MLB_OP_HISHELF_V) flt_hishelf_v(st, r, a, y);
+            break;
+          }
+          case MLB_OP_LOPASS_MOD: /* makeCoeffsVec inside the operator, F:139 */
+          {
+            float vc[3 * NB];
+            const float* r[3] = {vc, vc + NB, vc + 2 * NB};
+            mlport_coeffs_lopass_vec(b, c, vc);
+            flt_lopass_v(st, r, a, y);
+            break;
+          }
+          case MLB_OP_RAMP: ramp_row(a[0], b[0], y); break;
           case MLB_OP_ONEPOLE: flt_onepole(st, co, a, y); break;
           case MLB_OP_DCBLOCKER: flt_dcblocker(st, co, a, y); break;
           case MLB_OP_DIFFERENTIATOR: flt_differentiator(st, a, y); break;

@@ -187,6 +187,69 @@ struct PBell : Proc
   SVF_STATE(f)
   DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0]); }
 };
+// ---- coefficient-row (modulated) forms ----
+// Lopass has no operator taking coefficient ROWS (only (vx, omega, k), which designs them inside, F:136-152):
+// this node restates that operator's loop on rows handed in -- the same eight lines, the reference's types.
+// tests pin it to the reference's own operator()(vx, omega, k) through mlref_lopass_mod below.
+struct PLopassV : Proc
+{
+  Lopass f;
+  SVF_STATE(f)
+  DSPVector run(const DSPVector* const* in, DSPVector*) override
+  {
+    const DSPVector &vx = *in[0], &g0 = *in[1], &g1 = *in[2], &g2 = *in[3];
+    DSPVector vy;
+    for (int n = 0; n < kFloatsPerDSPVector; ++n)
+    {
+      float v0 = vx[n];
+      float t0 = v0 - f.ic2eq;
+      float t1 = g0[n] * t0 + g1[n] * f.ic1eq;
+      float t2 = g2[n] * t0 + g0[n] * f.ic1eq;
+      float v2 = t2 + f.ic2eq;
+      f.ic1eq += 2.0f * t1;
+      f.ic2eq += 2.0f * t2;
+      vy[n] = v2;
+    }
+    return vy;
+  }
+};
+// Lopass::operator()(vx, omega, k) itself (makeCoeffsVec with glibc sinf inside)
+struct PLopassMod : Proc
+{
+  Lopass f;
+  SVF_STATE(f)
+  DSPVector run(const DSPVector* const* in, DSPVector*) override { return f(*in[0], *in[1], *in[2]); }
+};
+// LoShelf / HiShelf::operator()(vx, vc) called directly with the rows as the DSPVectorArray
+struct PLoShelfV : Proc
+{
+  LoShelf f;
+  SVF_STATE(f)
+  DSPVector run(const DSPVector* const* in, DSPVector*) override
+  {
+    DSPVectorArray<5> vc;
+    for (int i = 0; i < 5; ++i) vc.row(i) = *in[1 + i];
+    return f(*in[0], vc);
+  }
+};
+struct PHiShelfV : Proc
+{
+  HiShelf f;
+  SVF_STATE(f)
+  DSPVector run(const DSPVector* const* in, DSPVector*) override
+  {
+    DSPVectorArray<6> vc;
+    for (int i = 0; i < 6; ++i) vc.row(i) = *in[1 + i];
+    return f(*in[0], vc);
+  }
+};
+struct PRamp : Proc
+{
+  DSPVector run(const DSPVector* const* in, DSPVector*) override
+  {
+    return interpolateDSPVectorLinear((*in[0])[0], (*in[1])[0]);
+  }
+};
 struct POnePole : Proc
 {
   OnePole f;
@@ -642,6 +705,11 @@ Proc* makeProc(int op)
     case MLB_OP_LOSHELF: return new PLoShelf;
     case MLB_OP_HISHELF: return new PHiShelf;
     case MLB_OP_BELL: return new PBell;
+    case MLB_OP_LOPASS_V: return new PLopassV;
+    case MLB_OP_LOPASS_MOD: return new PLopassMod;
+    case MLB_OP_LOSHELF_V: return new PLoShelfV;
+    case MLB_OP_HISHELF_V: return new PHiShelfV;
+    case MLB_OP_RAMP: return new PRamp;
     case MLB_OP_ONEPOLE: return new POnePole;
     case MLB_OP_DCBLOCKER: return new PDCBlocker;
     case MLB_OP_DIFFERENTIATOR: return new PDifferentiator;
@@ -831,8 +899,8 @@ void mlref_graph_process(mlref_graph* h, const float* in, float* out, float* mix
             rows[i] = rows[nd.in[0]];
             continue;
           }
-          const DSPVector* ins[3] = {nullptr, nullptr, nullptr};
-          for (int k = 0; k < 3; ++k)
+          const DSPVector* ins[MLB_MAX_INS] = {};
+          for (int k = 0; k < MLB_MAX_INS; ++k)
             if (nd.in[k] >= 0) ins[k] = &rows[nd.in[k]];
           rows[i] = g.procs[v][i]->run(ins, &rows2[i]);
         }
@@ -874,6 +942,30 @@ void mlref_coeffs_lopass(float omega, float k, float* o)
 {
   auto c = Lopass::makeCoeffs(omega, k);
   o[0] = c[0], o[1] = c[1], o[2] = c[2];
+}
+// Lopass::makeCoeffsVec, F:97-115; out = rows g0, g1, g2
+void mlref_coeffs_lopass_vec(const float* omega, const float* k, float* out)
+{
+  auto vc = Lopass::makeCoeffsVec(DSPVector(omega), DSPVector(k));
+  for (int i = 0; i < 3; ++i) store(vc.constRow(i), out + 64 * i);
+}
+// LoShelf / HiShelf::vcoeffs(p0, p1) = interpolateCoeffsLinear(makeCoeffs(p0), makeCoeffs(p1)), F:283-286,364-367
+void mlref_loshelf_vcoeffs(const float* p0, const float* p1, float* out)
+{
+  auto vc = LoShelf::vcoeffs({p0[0], p0[1], p0[2]}, {p1[0], p1[1], p1[2]});
+  for (int i = 0; i < 5; ++i) store(vc.constRow(i), out + 64 * i);
+}
+void mlref_hishelf_vcoeffs(const float* p0, const float* p1, float* out)
+{
+  auto vc = HiShelf::vcoeffs({p0[0], p0[1], p0[2]}, {p1[0], p1[1], p1[2]});
+  for (int i = 0; i < 6; ++i) store(vc.constRow(i), out + 64 * i);
+}
+// Lopass::operator()(vx, omega, k) for ONE voice over T blocks, from cleared state: x, omega, k, out [T][64]
+void mlref_lopass_mod(int T, const float* x, const float* omega, const float* k, float* out)
+{
+  Lopass lp;
+  for (int t = 0; t < T; ++t)
+    store(lp(DSPVector(x + 64 * t), DSPVector(omega + 64 * t), DSPVector(k + 64 * t)), out + 64 * t);
 }
 void mlref_coeffs_hipass(float omega, float k, float* o)
 {

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(L):
     assert len(syms) >= 30
     for s in syms:
         assert hasattr(L, s), f"libmlb200.so does not export {s}"
-    assert L.mlb_abi_version() == 1
+    assert L.mlb_abi_version() == 2
 
 
 def test_op_table_matches_library(L):

@@ -26,7 +26,7 @@ def main():
     from madronalib_b200 import api, workloads as wl
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--only", default="2,3,4,5,6,voices,map")
+    ap.add_argument("--only", default="2,3,swept,4,5,6,voices,map")
     ap.add_argument("--generic", action="store_true", help="force the graph interpreter kernel")
     ap.add_argument("--cpu", action="store_true",
                     help="also time the reference (oracle/_ref, all host threads) on config 6 and the Voice bank")
@@ -44,6 +44,11 @@ def main():
             cfgs.append(("config2_" + kind, wl.config_2(kind, 4096), 64, lambda V, T: 8.0 * V * T * 64))
     if "3" in only:
         cfgs.append(("config3", wl.config_3(65536), 64, lambda V, T: 8.0 * V * T * 64))
+    if "swept" in only:
+        # the swept headline chain: SineGen -> Lopass(coefficient ROWS g0, g1, g2) -> gain; per voice-sample
+        # 4 B freq + 3 x 4 B coefficient rows in + 4 B out = 20 B (MLDSPFilters.h:136-152 after makeCoeffsVec)
+        cfgs.append(("configA_swept", wl.swept_filter_case("sine_lopass_v_gain", 65536, 16), 16,
+                     lambda V, T: 20.0 * V * T * 64))
     if "4" in only:
         # ring 8 x (256 B r + 256 B w) + freq row in + 2 rows out per voice-block = 4864 B
         cfgs.append(("config4", wl.config_4(16384), 16, lambda V, T: 4864.0 * V * T))
