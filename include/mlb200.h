@@ -333,6 +333,9 @@ void mlb_coeffs_lopass_vec_n(const float* omega, const float* k, float* out, siz
 void mlb_interpolate_coeffs_linear(const float* c0, const float* c1, int n_coeffs, float* out);
 
 /* ---- device / context ---- */
+/* One device per process (the multi-GPU model is one process per GPU): mlb_init(other) while graphs, voice
+ * banks or resamplers of the current device are alive returns MLB_ERR_INVALID.  Entry points make the
+ * library's device current on the calling thread. */
 int mlb_init(int device);          /* select device, check sm_100; MLB_ERR_NO_DEVICE if absent */
 int mlb_device_count(void);        /* 0 when no GPU: callers must fail loudly, not fall back */
 const char* mlb_last_error(void);  /* thread-local message of the last failing call */
@@ -411,6 +414,10 @@ void mlb_router_set_unison(mlb_router* r, int on);
 void mlb_router_add_event(mlb_router* r, const mlb_event* e);
 void mlb_router_clear_events(mlb_router* r);
 int mlb_router_record_count(const mlb_router* r);
+/* events the router saw but does not route (CC 120 "all sound off" resets voices in mid-vector,
+ * MLEventsToSignals.cpp:748-755: not built), since creation; -1 on null */
+int mlb_router_unsupported_count(const mlb_router* r);
+void mlb_router_set_mod_cc(mlb_router* r, int cc);   /* EventsToSignals::setModCC (.h:80) */
 int mlb_router_process_vector(mlb_router* r, int start_time, mlb_voice_events* records);
 
 typedef struct mlb_voices mlb_voices;  /* opaque: V Voice objects on the device */
@@ -447,6 +454,9 @@ int mlb_map_device(int op, const float* x1, const float* x2, const float* x3, fl
                    size_t n_rows, void* stream);
 int mlb_map_host(int op, const float* x1, const float* x2, const float* x3, float* y,
                  size_t n_rows);
+/* mlb_map_host stages through a process-wide pool of device buffers that only grows: number of times the
+ * pool was (re)allocated so far (stays constant once the largest operand size has been seen). */
+long long mlb_map_host_allocations(void);
 
 /* ---- voice graphs: Bank<>-shaped batched processors ---- */
 typedef struct mlb_graph mlb_graph; /* opaque; owns device state, coefs, delay memory */

@@ -11,6 +11,7 @@
 // project); use DeviceBank / graphs for anything performance relevant.
 #pragma once
 #include <array>
+#include <cmath>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -75,13 +76,68 @@ class DSPVectorArray
   friend DSPVectorArray operator-(const DSPVectorArray& a, const DSPVectorArray& b) { return map2(MLB_OP_SUBTRACT, a, b); }
   friend DSPVectorArray operator*(const DSPVectorArray& a, const DSPVectorArray& b) { return map2(MLB_OP_MULTIPLY, a, b); }
   friend DSPVectorArray operator/(const DSPVectorArray& a, const DSPVectorArray& b) { return map2(MLB_OP_DIVIDE, a, b); }
+  // MLDSPOps.h:312-331
+  DSPVectorArray& operator+=(const DSPVectorArray& x) { return *this = map2(MLB_OP_ADD, *this, x); }
+  DSPVectorArray& operator-=(const DSPVectorArray& x) { return *this = map2(MLB_OP_SUBTRACT, *this, x); }
+  DSPVectorArray& operator*=(const DSPVectorArray& x) { return *this = map2(MLB_OP_MULTIPLY, *this, x); }
+  DSPVectorArray& operator/=(const DSPVectorArray& x) { return *this = map2(MLB_OP_DIVIDE, *this, x); }
 };
 using DSPVector = DSPVectorArray<1>;
+
+// ---- DSPVectorArrayInt<ROWS>: the same storage read as int32 (MLDSPOps.h:370-498) ----
+template <size_t ROWS>
+class DSPVectorArrayInt
+{
+  union
+  {
+    alignas(16) float asFloat[kFloatsPerDSPVector * ROWS];
+    alignas(16) int32_t asInt[kFloatsPerDSPVector * ROWS];
+  } data_;
+
+ public:
+  explicit DSPVectorArrayInt() { operator=(0); }
+  explicit DSPVectorArrayInt(int32_t k) { operator=(k); }
+  DSPVectorArrayInt& operator=(int32_t k)
+  {
+    for (int32_t& i : data_.asInt) i = k;
+    return *this;
+  }
+  float* getBuffer() { return data_.asFloat; }
+  const float* getConstBuffer() const { return data_.asFloat; }
+  int32_t* getBufferInt() { return data_.asInt; }
+  const int32_t* getConstBufferInt() const { return data_.asInt; }
+  int32_t& operator[](int i) { return data_.asInt[i]; }
+  int32_t operator[](int i) const { return data_.asInt[i]; }
+  DSPVectorArrayInt<1>& row(int j) { return *reinterpret_cast<DSPVectorArrayInt<1>*>(data_.asInt + kFloatsPerDSPVector * j); }
+  const DSPVectorArrayInt<1>& constRow(int j) const
+  {
+    return *reinterpret_cast<const DSPVectorArrayInt<1>*>(data_.asInt + kFloatsPerDSPVector * j);
+  }
+  bool operator==(const DSPVectorArrayInt& o) const { return std::memcmp(data_.asInt, o.data_.asInt, sizeof(data_.asInt)) == 0; }
+  friend DSPVectorArrayInt operator+(const DSPVectorArrayInt& a, const DSPVectorArrayInt& b)
+  {
+    DSPVectorArrayInt y;
+    check(mlb_map_host(MLB_OP_ADD_INT32, a.getConstBuffer(), b.getConstBuffer(), nullptr, y.getBuffer(), ROWS));
+    return y;
+  }
+  friend DSPVectorArrayInt operator-(const DSPVectorArrayInt& a, const DSPVectorArrayInt& b)
+  {
+    DSPVectorArrayInt y;
+    check(mlb_map_host(MLB_OP_SUBTRACT_INT32, a.getConstBuffer(), b.getConstBuffer(), nullptr, y.getBuffer(), ROWS));
+    return y;
+  }
+};
+using DSPVectorInt = DSPVectorArrayInt<1>;
 
 template <size_t ROWS>
 inline void load(DSPVectorArray<ROWS>& dst, const float* src) { std::memcpy(dst.getBuffer(), src, sizeof(float) * kFloatsPerDSPVector * ROWS); }
 template <size_t ROWS>
 inline void store(const DSPVectorArray<ROWS>& src, float* dst) { std::memcpy(dst, src.getConstBuffer(), sizeof(float) * kFloatsPerDSPVector * ROWS); }
+// the aligned forms (MLDSPOps.h:536-562) move the same bytes; alignment only selects the SSE instruction there
+template <size_t ROWS>
+inline void loadAligned(DSPVectorArray<ROWS>& dst, const float* src) { load(dst, src); }
+template <size_t ROWS>
+inline void storeAligned(const DSPVectorArray<ROWS>& src, float* dst) { store(src, dst); }
 
 #define MLB_DEFINE_OP1(NAME, OP)                                            \
   template <size_t ROWS>                                                    \
@@ -141,6 +197,276 @@ inline DSPVectorArray<ROWS> clamp(const DSPVectorArray<ROWS>& x, const DSPVector
   check(mlb_map_host(MLB_OP_CLAMP, x.getConstBuffer(), lo.getConstBuffer(), hi.getConstBuffer(), y.getBuffer(), ROWS));
   return y;
 }
+
+// the remaining unary / binary / ternary float ops of MLDSPOps.h:584-649,744-748
+#define MLB_DEFINE_OP1B(NAME, OP)                                           \
+  template <size_t ROWS>                                                    \
+  inline DSPVectorArray<ROWS> NAME(const DSPVectorArray<ROWS>& x)           \
+  {                                                                         \
+    DSPVectorArray<ROWS> y;                                                 \
+    check(mlb_map_host(OP, x.getConstBuffer(), nullptr, nullptr, y.getBuffer(), ROWS)); \
+    return y;                                                               \
+  }
+MLB_DEFINE_OP1B(sqrtApprox, MLB_OP_SQRT_APPROX)
+MLB_DEFINE_OP1B(log2Approx, MLB_OP_LOG2_APPROX)
+MLB_DEFINE_OP1B(exp2Approx, MLB_OP_EXP2_APPROX)
+#undef MLB_DEFINE_OP1B
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> divideApprox(const DSPVectorArray<ROWS>& a, const DSPVectorArray<ROWS>& b)
+{
+  DSPVectorArray<ROWS> y;
+  check(mlb_map_host(MLB_OP_DIVIDE_APPROX, a.getConstBuffer(), b.getConstBuffer(), nullptr, y.getBuffer(), ROWS));
+  return y;
+}
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> powApprox(const DSPVectorArray<ROWS>& a, const DSPVectorArray<ROWS>& b)
+{
+  DSPVectorArray<ROWS> y;
+  check(mlb_map_host(MLB_OP_POW_APPROX, a.getConstBuffer(), b.getConstBuffer(), nullptr, y.getBuffer(), ROWS));
+  return y;
+}
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> inverseLerp(const DSPVectorArray<ROWS>& a, const DSPVectorArray<ROWS>& b,
+                                        const DSPVectorArray<ROWS>& x)
+{
+  DSPVectorArray<ROWS> y;
+  check(mlb_map_host(MLB_OP_INVERSE_LERP, a.getConstBuffer(), b.getConstBuffer(), x.getConstBuffer(), y.getBuffer(), ROWS));
+  return y;
+}
+template <size_t ROWS>
+inline DSPVectorArrayInt<ROWS> within(const DSPVectorArray<ROWS>& x, const DSPVectorArray<ROWS>& lo,
+                                      const DSPVectorArray<ROWS>& hi)
+{
+  DSPVectorArrayInt<ROWS> y;
+  check(mlb_map_host(MLB_OP_WITHIN, x.getConstBuffer(), lo.getConstBuffer(), hi.getConstBuffer(), y.getBuffer(), ROWS));
+  return y;
+}
+
+// ---- row manipulation: pure data movement, done on the host (MLDSPOps.h:1057-1383) ----
+template <size_t ROWS, size_t N>
+inline DSPVectorArray<ROWS * N> repeatRows(const DSPVectorArray<N>& x)
+{
+  DSPVectorArray<ROWS * N> y;
+  for (size_t j = 0, k = 0; j < ROWS * N; ++j, k = (k + 1 < N ? k + 1 : 0)) y.row((int)j) = x.constRow((int)k);
+  return y;
+}
+template <size_t ROWS, size_t N>
+inline DSPVectorArray<ROWS> stretchRows(const DSPVectorArray<N>& x)
+{
+  DSPVectorArray<ROWS> y;
+  for (size_t j = 0; j < ROWS; ++j)  // k = roundf(j * (N - 1) / (ROWS - 1)), MLDSPOps.h:1078
+    y.row((int)j) = x.constRow(ROWS > 1 ? (int)roundf(((float)j * ((float)N - 1.f)) / ((float)ROWS - 1.f)) : 0);
+  return y;
+}
+template <size_t ROWS, size_t N>
+inline DSPVectorArray<ROWS> zeroPadRows(const DSPVectorArray<N>& x)
+{
+  DSPVectorArray<ROWS> y;
+  for (size_t j = 0; j < (ROWS < N ? ROWS : N); ++j) y.row((int)j) = x.constRow((int)j);
+  return y;
+}
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> shiftRows(const DSPVectorArray<ROWS>& x, int rowsToShift)
+{
+  DSPVectorArray<ROWS> y;
+  for (int j = 0; j < (int)ROWS; ++j)
+  {
+    const int k = j - rowsToShift;
+    if (k >= 0 && k < (int)ROWS) y.row(j) = x.constRow(k);
+  }
+  return y;
+}
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> rotateRows(const DSPVectorArray<ROWS>& x, int rowsToRotate)
+{
+  DSPVectorArray<ROWS> y;
+  for (int j = 0; j < (int)ROWS; ++j)
+  {
+    int k = (j - rowsToRotate) % (int)ROWS;  // row 0 comes from modulo(-rowsToRotate, ROWS), MLDSPOps.h:1132
+    if (k < 0) k += (int)ROWS;
+    y.row(j) = x.constRow(k);
+  }
+  return y;
+}
+template <size_t ROWSA, size_t ROWSB>
+inline DSPVectorArray<ROWSA + ROWSB> concatRows(const DSPVectorArray<ROWSA>& a, const DSPVectorArray<ROWSB>& b)
+{
+  DSPVectorArray<ROWSA + ROWSB> y;
+  for (size_t j = 0; j < ROWSA; ++j) y.row((int)j) = a.constRow((int)j);
+  for (size_t j = 0; j < ROWSB; ++j) y.row((int)(ROWSA + j)) = b.constRow((int)j);
+  return y;
+}
+template <size_t A, size_t B, size_t C>
+inline DSPVectorArray<A + B + C> concatRows(const DSPVectorArray<A>& a, const DSPVectorArray<B>& b, const DSPVectorArray<C>& c)
+{
+  return concatRows(concatRows(a, b), c);
+}
+template <size_t A, size_t B, size_t C, size_t D>
+inline DSPVectorArray<A + B + C + D> concatRows(const DSPVectorArray<A>& a, const DSPVectorArray<B>& b,
+                                                const DSPVectorArray<C>& c, const DSPVectorArray<D>& d)
+{
+  return concatRows(concatRows(a, b, c), d);
+}
+// shuffleRows: a0 b0 a1 b1 ... then the rest of the longer argument (MLDSPOps.h:1281-1307)
+template <size_t ROWSA, size_t ROWSB>
+inline DSPVectorArray<ROWSA + ROWSB> shuffleRows(const DSPVectorArray<ROWSA> a, const DSPVectorArray<ROWSB> b)
+{
+  DSPVectorArray<ROWSA + ROWSB> y;
+  size_t ja = 0, jb = 0, jy = 0;
+  while (ja < ROWSA || jb < ROWSB)
+  {
+    if (ja < ROWSA) y.row((int)jy++) = a.constRow((int)ja++);
+    if (jb < ROWSB) y.row((int)jy++) = b.constRow((int)jb++);
+  }
+  return y;
+}
+template <size_t ROWS>
+inline DSPVectorArray<(ROWS + 1) / 2> evenRows(const DSPVectorArray<ROWS>& x)
+{
+  DSPVectorArray<(ROWS + 1) / 2> y;
+  for (size_t j = 0; j < (ROWS + 1) / 2; ++j) y.row((int)j) = x.constRow((int)(j * 2));
+  return y;
+}
+template <size_t ROWS>
+inline DSPVectorArray<ROWS / 2> oddRows(const DSPVectorArray<ROWS>& x)
+{
+  DSPVectorArray<ROWS / 2> y;
+  for (size_t j = 0; j < ROWS / 2; ++j) y.row((int)j) = x.constRow((int)(j * 2 + 1));
+  return y;
+}
+template <size_t A, size_t B, size_t ROWS>
+inline DSPVectorArray<B - A> separateRows(const DSPVectorArray<ROWS>& x)
+{
+  static_assert(B <= ROWS && A < B, "separateRows: row range");
+  DSPVectorArray<B - A> y;
+  for (size_t j = A; j < B; ++j) y.row((int)(j - A)) = x.constRow((int)j);
+  return y;
+}
+// index generators: exact small integers (MLDSPOps.h:965-966,1365-1388)
+template <size_t ROWS = 1>
+inline DSPVectorArray<ROWS> columnIndex()
+{
+  DSPVectorArray<ROWS> y;
+  for (size_t j = 0; j < ROWS; ++j)
+    for (size_t i = 0; i < kFloatsPerDSPVector; ++i) y[j * kFloatsPerDSPVector + i] = (float)i;
+  return y;
+}
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> rowIndex()
+{
+  DSPVectorArray<ROWS> y;
+  for (size_t j = 0; j < ROWS; ++j) y.row((int)j) = DSPVector((float)j);
+  return y;
+}
+inline DSPVectorInt columnIndexInt()
+{
+  DSPVectorInt y;
+  for (size_t i = 0; i < kFloatsPerDSPVector; ++i) y[(int)i] = (int32_t)i;
+  return y;
+}
+// ranges: the scalar interval is host scalar arithmetic as in the reference, the row is built on the GPU
+inline DSPVector rangeOpen(float start, float end)  // MLDSPOps.h:970-974
+{
+  const float interval = (end - start) / (kFloatsPerDSPVector);
+  return columnIndex() * DSPVector(interval) + DSPVector(start);
+}
+inline DSPVector rangeClosed(float start, float end)  // :978-982
+{
+  const float interval = (end - start) / (kFloatsPerDSPVector - 1.f);
+  return columnIndex() * DSPVector(interval) + DSPVector(start);
+}
+inline DSPVector interpolateDSPVectorLinear(float start, float end)  // :986-990
+{
+  const float interval = (end - start) / (kFloatsPerDSPVector);
+  return columnIndex() * DSPVector(interval) + DSPVector(start + interval);
+}
+// addRows: rows summed left to right from zero (MLDSPOps.h:1349-1359), every add on the GPU
+template <size_t ROWS>
+inline DSPVector addRows(const DSPVectorArray<ROWS>& x)
+{
+  DSPVector vy(0.f);
+  for (size_t j = 0; j < ROWS; ++j) vy = add(vy, x.constRow((int)j));
+  return vy;
+}
+
+// "*1" forms: the second operand is ONE row applied to every row of the first (DEFINE_OP2_MS, MLDSPOps.h:655-687)
+#define MLB_DEFINE_OP2_MS(NAME, OP)                                                            \
+  template <size_t ROWS>                                                                       \
+  inline DSPVectorArray<ROWS> NAME(const DSPVectorArray<ROWS>& a, const DSPVectorArray<1>& b)  \
+  {                                                                                            \
+    DSPVectorArray<ROWS> y;                                                                    \
+    const DSPVectorArray<ROWS> bb = repeatRows<ROWS, 1>(b);                                    \
+    check(mlb_map_host(OP, a.getConstBuffer(), bb.getConstBuffer(), nullptr, y.getBuffer(), ROWS)); \
+    return y;                                                                                  \
+  }
+MLB_DEFINE_OP2_MS(add1, MLB_OP_ADD)
+MLB_DEFINE_OP2_MS(subtract1, MLB_OP_SUBTRACT)
+MLB_DEFINE_OP2_MS(multiply1, MLB_OP_MULTIPLY)
+MLB_DEFINE_OP2_MS(divide1, MLB_OP_DIVIDE)
+MLB_DEFINE_OP2_MS(divideApprox1, MLB_OP_DIVIDE_APPROX)
+MLB_DEFINE_OP2_MS(pow1, MLB_OP_POW)
+MLB_DEFINE_OP2_MS(powApprox1, MLB_OP_POW_APPROX)
+MLB_DEFINE_OP2_MS(min1, MLB_OP_MIN)
+MLB_DEFINE_OP2_MS(max1, MLB_OP_MAX)
+#undef MLB_DEFINE_OP2_MS
+
+// int <-> float conversions, comparisons -> masks, select, int add/sub (MLDSPOps.h:692-714,779-917)
+#define MLB_DEFINE_F2I(NAME, OP)                                                     \
+  template <size_t ROWS>                                                             \
+  inline DSPVectorArrayInt<ROWS> NAME(const DSPVectorArray<ROWS>& x)                 \
+  {                                                                                  \
+    DSPVectorArrayInt<ROWS> y;                                                       \
+    check(mlb_map_host(OP, x.getConstBuffer(), nullptr, nullptr, y.getBuffer(), ROWS)); \
+    return y;                                                                        \
+  }
+MLB_DEFINE_F2I(roundFloatToInt, MLB_OP_ROUND_F2I)
+MLB_DEFINE_F2I(truncateFloatToInt, MLB_OP_TRUNC_F2I)
+#undef MLB_DEFINE_F2I
+#define MLB_DEFINE_I2F(NAME, OP)                                                     \
+  template <size_t ROWS>                                                             \
+  inline DSPVectorArray<ROWS> NAME(const DSPVectorArrayInt<ROWS>& x)                 \
+  {                                                                                  \
+    DSPVectorArray<ROWS> y;                                                          \
+    check(mlb_map_host(OP, x.getConstBuffer(), nullptr, nullptr, y.getBuffer(), ROWS)); \
+    return y;                                                                        \
+  }
+MLB_DEFINE_I2F(intToFloat, MLB_OP_INT_TO_FLOAT)
+MLB_DEFINE_I2F(unsignedIntToFloat, MLB_OP_UNSIGNED_TO_FLOAT)
+#undef MLB_DEFINE_I2F
+#define MLB_DEFINE_FF2I(NAME, OP)                                                                   \
+  template <size_t ROWS>                                                                            \
+  inline DSPVectorArrayInt<ROWS> NAME(const DSPVectorArray<ROWS>& a, const DSPVectorArray<ROWS>& b) \
+  {                                                                                                 \
+    DSPVectorArrayInt<ROWS> y;                                                                      \
+    check(mlb_map_host(OP, a.getConstBuffer(), b.getConstBuffer(), nullptr, y.getBuffer(), ROWS));  \
+    return y;                                                                                       \
+  }
+MLB_DEFINE_FF2I(equal, MLB_OP_EQUAL)
+MLB_DEFINE_FF2I(notEqual, MLB_OP_NOT_EQUAL)
+MLB_DEFINE_FF2I(greaterThan, MLB_OP_GREATER_THAN)
+MLB_DEFINE_FF2I(greaterThanOrEqual, MLB_OP_GREATER_EQUAL)
+MLB_DEFINE_FF2I(lessThan, MLB_OP_LESS_THAN)
+MLB_DEFINE_FF2I(lessThanOrEqual, MLB_OP_LESS_EQUAL)
+#undef MLB_DEFINE_FF2I
+template <size_t ROWS>  // bitwise select(resultIfTrue, resultIfFalse, conditionMask)
+inline DSPVectorArray<ROWS> select(const DSPVectorArray<ROWS>& a, const DSPVectorArray<ROWS>& b, const DSPVectorArrayInt<ROWS>& m)
+{
+  DSPVectorArray<ROWS> y;
+  check(mlb_map_host(MLB_OP_SELECT, a.getConstBuffer(), b.getConstBuffer(), m.getConstBuffer(), y.getBuffer(), ROWS));
+  return y;
+}
+template <size_t ROWS>
+inline DSPVectorArrayInt<ROWS> select(const DSPVectorArrayInt<ROWS>& a, const DSPVectorArrayInt<ROWS>& b,
+                                      const DSPVectorArrayInt<ROWS>& m)
+{
+  DSPVectorArrayInt<ROWS> y;
+  check(mlb_map_host(MLB_OP_SELECT, a.getConstBuffer(), b.getConstBuffer(), m.getConstBuffer(), y.getBuffer(), ROWS));
+  return y;
+}
+template <size_t ROWS>
+inline DSPVectorArrayInt<ROWS> addInt32(const DSPVectorArrayInt<ROWS>& a, const DSPVectorArrayInt<ROWS>& b) { return a + b; }
+template <size_t ROWS>
+inline DSPVectorArrayInt<ROWS> subtractInt32(const DSPVectorArrayInt<ROWS>& a, const DSPVectorArrayInt<ROWS>& b) { return a - b; }
 
 // ---- Graph: a fixed DAG of functors, built in the reference's functional style ----
 class Graph

@@ -115,6 +115,27 @@ class DSPBuffer
     n = std::min(n, getReadAvailable());
     tail_.store((tail_.load(std::memory_order_relaxed) + n) & span_, std::memory_order_release);
   }
+  // Overlap-add writer (reference: DSPBuffer::writeWithOverlapAdd, source/DSP/MLDSPBuffer.h:288-320): ADD n samples
+  // to what is stored from the write index on, zero the following n - overlap samples for the next window, and
+  // advance the write index by n - overlap.  Partial windows are never written (needs 2 n - overlap of space).
+  void writeWithOverlapAdd(const float* src, size_t n, size_t overlap)
+  {
+    if (getWriteAvailable() < n * 2 - overlap) return;
+    const size_t h = head_.load(std::memory_order_acquire);
+    for (size_t i = 0; i < n; ++i) store_[(h + i) & wrap_] += src[i];
+    const size_t after = (h + n) & span_;
+    for (size_t i = 0; i < n - overlap; ++i) store_[(after + i) & wrap_] = 0.f;
+    head_.store((after - overlap) & span_, std::memory_order_release);
+  }
+  // Overlapping reader (:323-340): deliver up to n samples (the last `overlap` of them may lie beyond the write
+  // index), then advance the read index by delivered - overlap.
+  void readWithOverlap(float* dst, size_t n, size_t overlap)
+  {
+    n = std::min(n, getReadAvailable() + overlap);
+    const size_t t = tail_.load(std::memory_order_acquire);
+    copyOut(t, dst, n);
+    tail_.store((t + n - overlap) & span_, std::memory_order_release);
+  }
   // copy the newest n samples without consuming anything; nothing happens when fewer are available
   // (reference: DSPBuffer::peekMostRecent, source/DSP/MLDSPBuffer.h:344-384)
   void peekMostRecent(float* dst, size_t n) const

@@ -80,6 +80,9 @@ def lib() -> ctypes.CDLL:
     L.mlb_router_clear_events.argtypes = [_vp]
     L.mlb_router_clear_events.restype = None
     L.mlb_router_record_count.argtypes = [_vp]
+    L.mlb_router_unsupported_count.argtypes = [_vp]
+    L.mlb_router_set_mod_cc.argtypes = [_vp, ctypes.c_int]
+    L.mlb_router_set_mod_cc.restype = None
     L.mlb_router_process_vector.argtypes = [_vp, ctypes.c_int, _vp]
     L.mlb_resampler_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]
     L.mlb_resampler_destroy.argtypes = [_vp]
@@ -97,6 +100,7 @@ def lib() -> ctypes.CDLL:
     L.mlb_graph_last_host_slices.argtypes = [_vp]
     L.mlb_map_device.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]
     L.mlb_map_host.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_size_t]
+    L.mlb_map_host_allocations.restype = ctypes.c_longlong
     for name, n in (("lopass", 2), ("hipass", 2), ("bandpass", 2), ("loshelf", 3), ("hishelf", 3),
                     ("bell", 3), ("onepole", 1), ("peak", 1), ("rms", 1), ("adsr", 5), ("glide", 1),
                     ("sample_glide", 1)):
@@ -232,6 +236,9 @@ def map_host(op: str, x1: np.ndarray, x2: Optional[np.ndarray] = None,
     x1 = np.ascontiguousarray(x1, np.float32)
     assert x1.size % BLOCK == 0
     xs = [None if x is None else np.ascontiguousarray(x, np.float32) for x in (x2, x3)]
+    for x in xs:
+        if x is not None and x.shape != x1.shape:
+            raise ValueError(f"map_host: operand shapes differ ({x.shape} vs {x1.shape})")
     y = np.empty_like(x1)
     _check(lib().mlb_map_host(OP_ID[op.upper()], x1.ctypes.data, _ptr(xs[0]), _ptr(xs[1]),
                               y.ctypes.data, x1.size // BLOCK))
@@ -308,6 +315,11 @@ class VoiceGraph:
             out = np.empty((T, s.n_out, V, BLOCK), np.float32)
         if want_mix and mix is None:
             mix = np.empty((T, s.n_out, BLOCK), np.float32)
+        for name, a, shape in (("out", out if want_out else None, (T, s.n_out, V, BLOCK)),
+                               ("mix", mix if want_mix else None, (T, s.n_out, BLOCK))):
+            if a is not None and not (isinstance(a, np.ndarray) and a.dtype == np.float32 and
+                                      a.flags["C_CONTIGUOUS"] and a.shape == shape):
+                raise ValueError(f"process_host: `{name}` must be a C-contiguous float32 array of shape {shape}")
         _check(lib().mlb_graph_process_host(self._h, _ptr(inp) if s.n_in else None,
                                             _ptr(out) if want_out else None,
                                             _ptr(mix) if want_mix else None, T))
@@ -459,6 +471,14 @@ class EventRouter:
                   value2: float = 0.0) -> None:
         e = _Event(type, channel, source_idx, time, value1, value2)
         lib().mlb_router_add_event(self._h, ctypes.byref(e))
+
+    @property
+    def unsupported_events(self) -> int:
+        """Events seen but not routed (CC 120 all-sound-off) since creation."""
+        return int(lib().mlb_router_unsupported_count(self._h))
+
+    def set_mod_cc(self, cc: int) -> None:
+        lib().mlb_router_set_mod_cc(self._h, int(cc))
 
     def process_vector(self, start_time: int, records: np.ndarray) -> int:
         """records: array of n_records elements of workloads.VOICE_EVENTS_DTYPE (written in place)."""

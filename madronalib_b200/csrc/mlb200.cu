@@ -125,6 +125,9 @@ extern "C" int mlb_graph_layout(const mlb_node* nodes, int n_nodes, mlb_layout* 
       const int rd = nodes[i].iarg;
       if (rd < 0 || rd >= i || nodes[rd].op != MLB_OP_FEEDBACK_READ)
         return fail(MLB_ERR_INVALID, "node %d: FEEDBACK_WRITE.iarg must name an earlier FEEDBACK_READ node", i);
+      for (int q = 0; q < i; ++q)
+        if (nodes[q].op == MLB_OP_FEEDBACK_WRITE && nodes[q].iarg == rd)
+          return fail(MLB_ERR_INVALID, "node %d: FEEDBACK_READ %d already has a FEEDBACK_WRITE (node %d)", i, rd, q);
     }
     if (state_off) state_off[i] = ns;
     if (coef_off) coef_off[i] = nc;
@@ -375,6 +378,7 @@ extern "C" void mlb_coeffs_fdn8(const float times[8], const float cutoffs[8], co
 // device
 
 static int g_device = -1;
+static std::atomic<int> g_live_handles{0};  // graphs + voice banks + resamplers alive (they hold pointers of g_device)
 static int g_sm_count = 0;
 static size_t g_smem_optin = 0;
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -401,6 +405,11 @@ extern "C" int mlb_init(int device)
     return fail(MLB_ERR_NO_DEVICE,
                 "no CUDA device visible: this library has no CPU fallback (sm_100a kernels only)");
   if (device < 0 || device >= n) return fail(MLB_ERR_INVALID, "device %d out of range (%d)", device, n);
+  // one device per process (one process per GPU is the multi-GPU model): retargeting while
+  // handles of the current device are alive would leave them with foreign pointers
+  if (g_device >= 0 && device != g_device && g_live_handles.load() > 0)
+    return fail(MLB_ERR_INVALID, "mlb_init(%d): %d handle(s) of device %d are still alive (one device per process)",
+                device, g_live_handles.load(), g_device);
   CU_CHECK(cudaSetDevice(device));
   cudaDeviceProp p;
   CU_CHECK(cudaGetDeviceProperties(&p, device));
@@ -1000,8 +1009,19 @@ static int build_generic(mlb_graph* g)
               lu = std::max(lu, std::max(last_use[q], q));
             }
           }
-          if ((has_r && lu == li) || (!has_r && li == j)) free_slots.push_back(slot2[j]);
+          if (has_r && lu == li) free_slots.push_back(slot2[j]);
         }
+      }
+      // a dual-output node whose second row nobody in this stage reads gives that row back at once
+      if (!is_ext && is_dual(N[node].op))
+      {
+        bool has_r = false;
+        for (int q = li + 1; q < n_loc; ++q)
+        {
+          const int nq = q < n_ext ? ext[q] : members[q - n_ext];
+          if (q >= n_ext && is_second(N[nq].op) && N[nq].in[0] == node) has_r = true;
+        }
+        if (!has_r) free_slots.push_back(slot2[li]);
       }
       // a row nobody in this stage reads can be recycled right after it was written out
       if (slot[li] >= 0 && last_use[li] < 0 && !(li >= n_ext && is_second(N[node].op)))
@@ -1049,6 +1069,7 @@ extern "C" int mlb_graph_create(const mlb_node* nodes, int n_nodes, const int32_
   if (rc != MLB_OK) return rc;
 
   mlb_graph* g = new mlb_graph;
+  ++g_live_handles;
   g->nodes.assign(nodes, nodes + n_nodes);
   g->outs.assign(outs, outs + n_out);
   g->st_off = so;
@@ -1169,6 +1190,7 @@ extern "C" int mlb_graph_destroy(mlb_graph* g)
   if (g->s_d2h) cudaStreamDestroy(g->s_d2h);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
+  --g_live_handles;
   return MLB_OK;
 }
 
@@ -1305,11 +1327,18 @@ extern "C" int mlb_graph_set_coefs(mlb_graph* g, const float* coef_host)
   if (g->layout.n_coef_words == 0) return MLB_OK;
   if (!coef_host) return fail(MLB_ERR_INVALID, "null coefs");
   const size_t bytes = (size_t)g->layout.n_coef_words * g->V * 4;
+  // the sizing passes read the host mirror: hand them the new values, put the old ones back when they are
+  // rejected so that the mirror never disagrees with the device copy.  NOTE: a change of any ring size
+  // re-lays-out the delay memory and clears ALL delay state of the graph (rings, member rows, write index).
+  std::vector<float> old(g->h_coef);
   memcpy(g->h_coef.data(), coef_host, bytes);
   int rc = size_delay_memory(g);
-  if (rc != MLB_OK) return rc;
-  rc = size_functor_memory(g);
-  if (rc != MLB_OK) return rc;
+  if (rc == MLB_OK) rc = size_functor_memory(g);
+  if (rc != MLB_OK)
+  {
+    g->h_coef.swap(old);
+    return rc;
+  }
   CU_CHECK(cudaMemcpy(g->d_coef, coef_host, bytes, cudaMemcpyHostToDevice));
   return MLB_OK;
 }
@@ -1711,39 +1740,58 @@ extern "C" int mlb_map_device(int op, const float* x1, const float* x2, const fl
   return MLB_OK;
 }
 
+// Device staging of mlb_map_host: four buffers (three operands + result) that only ever grow, so that the
+// host value-type operators (`a + b` on two mlb::DSPVectors) do not allocate after their first use.
+#include <mutex>
+namespace
+{
+struct MapPool
+{
+  std::mutex mu;
+  float* d[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t cap = 0;
+  cudaStream_t stream = nullptr;
+  long long allocations = 0;
+};
+MapPool g_map_pool;
+}  // namespace
+extern "C" long long mlb_map_host_allocations(void) { return g_map_pool.allocations; }
+
 extern "C" int mlb_map_host(int op, const float* x1, const float* x2, const float* x3, float* y,
                             size_t n_rows)
 {
   int nin, nst, nco;
   if (mlb_op_info(op, &nin, &nst, &nco) != MLB_OK) return fail(MLB_ERR_INVALID, "unknown op %d", op);
   if (n_rows == 0) return MLB_OK;
+  if (!x1 || !y || (nin >= 2 && !x2) || (nin >= 3 && !x3)) return fail(MLB_ERR_INVALID, "null operand");
   int rc = ensure_init();
   if (rc != MLB_OK) return rc;
   const size_t bytes = n_rows * MLB_BLOCK * 4;
-  float* d[4] = {nullptr, nullptr, nullptr, nullptr};
-  const float* h[3] = {x1, x2, x3};
-  auto freeall = [&]()
+  MapPool& P = g_map_pool;
+  std::lock_guard<std::mutex> lock(P.mu);
+  if (!P.stream) CU_CHECK(cudaStreamCreateWithFlags(&P.stream, cudaStreamNonBlocking));
+  if (bytes > P.cap)
   {
-    for (float* p : d) cudaFree(p);
-  };
-  for (int k = 0; k < 4; ++k)
-  {
-    if (k < 3 && (k >= nin || !h[k])) continue;
-    if (cudaMalloc(&d[k], bytes) != cudaSuccess)
+    const size_t want = std::max(bytes, std::max<size_t>(P.cap * 2, (size_t)64 << 10));
+    for (float*& p : P.d)
     {
-      freeall();
-      return fail(MLB_ERR_ALLOC, "cudaMalloc of %zu B failed", bytes);
+      cudaFree(p);
+      p = nullptr;
     }
-    if (k < 3) cudaMemcpy(d[k], h[k], bytes, cudaMemcpyHostToDevice);
+    P.cap = 0;
+    for (float*& p : P.d)
+      if (cudaMalloc(&p, want) != cudaSuccess) return fail(MLB_ERR_ALLOC, "cudaMalloc of %zu B failed", want);
+    P.cap = want;
+    ++P.allocations;
   }
-  rc = mlb_map_device(op, d[0], d[1], d[2], d[3], n_rows, nullptr);
-  if (rc == MLB_OK)
-  {
-    cudaError_t e = cudaMemcpy(y, d[3], bytes, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) rc = fail(MLB_ERR_CUDA, "map copy-out failed: %s", cudaGetErrorString(e));
-  }
-  freeall();
-  return rc;
+  const float* h[3] = {x1, x2, x3};
+  for (int k = 0; k < nin && k < 3; ++k)
+    CU_CHECK(cudaMemcpyAsync(P.d[k], h[k], bytes, cudaMemcpyHostToDevice, P.stream));
+  rc = mlb_map_device(op, P.d[0], nin >= 2 ? P.d[1] : nullptr, nin >= 3 ? P.d[2] : nullptr, P.d[3], n_rows, P.stream);
+  if (rc != MLB_OK) return rc;
+  CU_CHECK(cudaMemcpyAsync(y, P.d[3], bytes, cudaMemcpyDeviceToHost, P.stream));
+  CU_CHECK(cudaStreamSynchronize(P.stream));
+  return MLB_OK;
 }
 
 
@@ -1777,6 +1825,7 @@ extern "C" int mlb_voices_destroy(mlb_voices* vb)
   cudaFree(vb->d_out);
   if (vb->stream) cudaStreamDestroy(vb->stream);
   delete vb;
+  --g_live_handles;
   return MLB_OK;
 }
 
@@ -1792,6 +1841,7 @@ extern "C" int mlb_voices_create(int n_voices, float sample_rate, const int32_t*
   if (rc != MLB_OK) return rc;
   const size_t V = (size_t)n_voices;
   mlb_voices* vb = new mlb_voices;
+  ++g_live_handles;
   vb->V = n_voices;
   vb->sr = sample_rate;
   // the recalc block of the first beginProcess (MLEventsToSignals.cpp:92-113), done once here
@@ -1949,6 +1999,7 @@ extern "C" int mlb_resampler_destroy(mlb_resampler* r)
   cudaFree(r->d_out);
   if (r->stream) cudaStreamDestroy(r->stream);
   delete r;
+  --g_live_handles;
   return MLB_OK;
 }
 extern "C" int mlb_resampler_clear(mlb_resampler* r)
@@ -1968,6 +2019,7 @@ extern "C" int mlb_resampler_create(int direction, int octaves, int n_voices, ml
   int rc = ensure_init();
   if (rc != MLB_OK) return rc;
   mlb_resampler* r = new mlb_resampler;
+  ++g_live_handles;
   r->dir = direction, r->oct = octaves, r->V = n_voices;
   bool ok = cudaMalloc(&r->d_state, (size_t)octaves * 9 * n_voices * 4) == cudaSuccess;
   if (ok && direction == MLB_RESAMPLE_DOWN)
@@ -2070,6 +2122,11 @@ extern "C" void mlb_router_add_event(mlb_router* r, const mlb_event* e)
 extern "C" void mlb_router_clear_events(mlb_router* r)
 {
   if (r) r->router.clearEvents();
+}
+extern "C" int mlb_router_unsupported_count(const mlb_router* r) { return r ? r->router.unsupportedEvents() : -1; }
+extern "C" void mlb_router_set_mod_cc(mlb_router* r, int cc)
+{
+  if (r) r->router.setModCC(cc);
 }
 extern "C" int mlb_router_record_count(const mlb_router* r) { return r ? r->router.recordCount() : -1; }
 extern "C" int mlb_router_process_vector(mlb_router* r, int start_time, mlb_voice_events* records)

@@ -28,13 +28,6 @@ static int g_checks = 0, g_fail = 0;
     }                                                                   \
   } while (0)
 
-static DSPVector rangeClosed(float start, float end)  // reference MLDSPOps.h:978-982
-{
-  DSPVector v;
-  const float interval = (end - start) / (kFloatsPerDSPVector - 1.f);
-  for (size_t i = 0; i < kFloatsPerDSPVector; ++i) v[i] = (float)i * interval + start;
-  return v;
-}
 static float maxAbsDiff(const DSPVector& a, const DSPVector& b, const DSPVector* domain = nullptr)
 {
   float m = 0.f;
@@ -125,6 +118,58 @@ int main()
     REQUIRE(d[10] == 21.f);
     DSPVectorArray<2> e(3.f);
     REQUIRE((e * e)[100] == 9.f);
+  }
+
+  // ---- row operations, the int type, compound assignment, "*1" forms (MLDSPOps.h:312-331,370-498,655-687,
+  // 1057-1383; the reference's own section, Tests/dspOpsTest.cpp:187-230, builds these without assertions) ----
+  {
+    DSPVectorArray<2> a{repeatRows<2>(columnIndex())};
+    auto a2{a * 2.f};
+    REQUIRE(a2[5] == 10.f && a2[64 + 63] == 126.f);
+    DSPVector b{columnIndex()};
+    auto e = a * repeatRows<2>(b);
+    REQUIRE(e[64 + 7] == 49.f);
+    REQUIRE(multiply1(a, b) == e);  // one row applied to every row
+    auto aa = repeatRows<4>(a);
+    REQUIRE(aa.constRow(7) == b);
+    DSPVectorArray<2> g = a;
+    g.row(1) = b * 2.f;
+    auto h = stretchRows<6>(g);
+    REQUIRE(h.constRow(0) == b && h.constRow(2) == b && h.constRow(3) == g.constRow(1) && h.constRow(5) == g.constRow(1));
+    auto k = zeroPadRows<6>(columnIndex());
+    REQUIRE(k.constRow(0) == b && k.constRow(1) == DSPVector(0.f));
+    auto m = rotateRows(k, -1) * 3.f;   // row 0 moves to row 5
+    REQUIRE(m.constRow(5) == b * 3.f && m.constRow(0) == DSPVector(0.f));
+    auto n = shiftRows(k, 2);
+    REQUIRE(n.constRow(2) == b && n.constRow(0) == DSPVector(0.f));
+    DSPVectorArray<3> gains = concatRows(DSPVector{0.300f}, DSPVector{0.030f}, DSPVector{0.003f});
+    DSPVectorArray<6> gg = repeatRows<2>(gains);
+    DSPVectorArray<2> hh = separateRows<4, 6>(gg);
+    REQUIRE(hh.constRow(0) == DSPVector(0.030f) && hh.constRow(1) == DSPVector(0.003f));
+    REQUIRE(evenRows(gg).constRow(1) == DSPVector(0.003f) && oddRows(gg).constRow(0) == DSPVector(0.030f));
+    REQUIRE(shuffleRows(DSPVector(1.f), concatRows(DSPVector(2.f), DSPVector(3.f))).constRow(2) == DSPVector(3.f));
+    REQUIRE(addRows(gg)[17] == ((((0.f + 0.3f) + 0.03f) + 0.003f) + 0.3f) + 0.03f + 0.003f);
+    DSPVectorArray<2> acc(1.f);
+    acc += a;
+    acc *= DSPVectorArray<2>(2.f);
+    acc -= DSPVectorArray<2>(1.f);
+    acc /= DSPVectorArray<2>(0.5f);
+    REQUIRE(acc[3] == ((1.f + 3.f) * 2.f - 1.f) / 0.5f);
+    // ints: round / truncate, comparisons -> masks, bitwise select, int add
+    DSPVector x = columnIndex() * 0.5f - 4.f;
+    DSPVectorInt r = roundFloatToInt(x), t = truncateFloatToInt(x);
+    REQUIRE(r[1] == -4 && r[3] == -2 && t[1] == -3 && t[9] == 0);  // RN-even: -3.5 -> -4, -2.5 -> -2
+    DSPVectorInt mask = greaterThan(x, DSPVector(0.f));
+    REQUIRE(mask[8] == 0 && mask[9] == -1);
+    DSPVector sel = select(DSPVector(1.f), DSPVector(-1.f), mask);
+    REQUIRE(sel[0] == -1.f && sel[63] == 1.f);
+    REQUIRE((r + t)[1] == -7 && subtractInt32(r, t)[1] == -1);
+    REQUIRE(intToFloat(r)[3] == -2.f);
+    REQUIRE(rangeOpen(0.f, 1.f)[32] == 0.5f && interpolateDSPVectorLinear(0.f, 1.f)[63] == 1.f);
+    // the staging pool behind these operators stopped allocating long ago
+    const long long allocs = mlb_map_host_allocations();
+    for (int i = 0; i < 50; ++i) a2 = a2 + a;
+    REQUIRE(mlb_map_host_allocations() == allocs);
   }
 
   // ---- Bank<SineGen, 5>-shaped bank: rows are independent voices ----

@@ -80,6 +80,43 @@ int main()
       REQUIRE(ref.getReadAvailable() == mine.getReadAvailable());
     }
   }
+  // ---- overlap-add writer / overlapping reader in lockstep (MLDSPBuffer.h:288-340): windowed frames of
+  // `win` samples hopped by win - overlap, as an STFT resynthesis would use them ----
+  for (unsigned seed = 1; seed <= 12; ++seed)
+  {
+    unsigned s = seed * 7919u;
+    ml::DSPBuffer ref;
+    mlb::DSPBuffer mine;
+    const int size = 256 + (int)(rnd(s) % 2000);
+    REQUIRE(ref.resize(size) == mine.resize(size));
+    const size_t win = 16 + rnd(s) % 100, overlap = rnd(s) % win;
+    std::vector<float> frame(win), a(4096), b(4096);
+    float counter = 1.f;
+    for (int step = 0; step < 300; ++step)
+    {
+      const unsigned op = rnd(s) % 3;
+      if (op <= 1)
+      {
+        for (size_t i = 0; i < win; ++i) frame[i] = (counter += 0.5f);
+        ref.writeWithOverlapAdd(frame.data(), win, overlap);
+        mine.writeWithOverlapAdd(frame.data(), win, overlap);
+      }
+      else
+      {
+        const size_t n = std::min<size_t>(win, mine.getReadAvailable() + overlap);
+        if (n > overlap)
+        {
+          std::fill(a.begin(), a.begin() + win, -1.f);
+          std::fill(b.begin(), b.begin() + win, -1.f);
+          ref.readWithOverlap(a.data(), win, overlap);
+          mine.readWithOverlap(b.data(), win, overlap);
+          for (size_t i = 0; i < win; ++i) REQUIRE(a[i] == b[i]);
+        }
+      }
+      REQUIRE(ref.getReadAvailable() == mine.getReadAvailable());
+      REQUIRE(ref.getWriteAvailable() == mine.getWriteAvailable());
+    }
+  }
   // ---- batched process buffer vs the reference's per-vector loop ----
   {
     const int maxFrames = 1024;
