@@ -140,6 +140,20 @@ struct Chain
     if (GAIN) y = A<EX>::mul(y, co[NC - 1]);  // operator*(DSPVector, DSPVector(float)), O:345-348
     return y;
   }
+  // the same chain cut after the generator, for the two-warp team kernel (chain_team_kernel)
+  static constexpr bool SPLIT = (GEN >= 0) && (F1 >= 0) && !F1_V;
+  static MLB_DEV float tick_gen(float in, uint32_t (&st)[NS > 0 ? NS : 1], const float (&co)[NC > 0 ? NC : 1])
+  {
+    const float x = (SRC == SRC_INPUT) ? in : ((SRC == SRC_PARAM) ? co[0] : 0.0f);
+    return gen_tick<EX>(GEN, x, 0.0f, &st[0]);
+  }
+  static MLB_DEV float tick_flt(float y, uint32_t (&st)[NS > 0 ? NS : 1], const float (&co)[NC > 0 ? NC : 1])
+  {
+    if (F1 >= 0) y = filter_tick<EX>(F1, y, &st[NS_GEN], &co[NC_SRC]);
+    if (F2 >= 0) y = filter_tick<EX>(F2, y, &st[NS_GEN + NS_F1], &co[NC_SRC + NC_F1]);
+    if (GAIN) y = A<EX>::mul(y, co[NC - 1]);
+    return y;
+  }
 };
 
 // Work distribution: the launch is cut into units (chunk c, group g) = `chunk_blocks`
@@ -431,6 +445,197 @@ __global__ void __launch_bounds__(kChainMaxWarps * 32)
   // shared memory must outlive the last bulk stores
   if (lane == 0) bulk_wait_read<0>();
   __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// chain_team_kernel: the same fused chains for SMALL banks (fewer voice groups than ~4 per SM).
+//
+// With so few groups the persistent kernel above runs one lone warp per scheduler, and a lone warp
+// is latency-bound: every one of the ~39 instructions of a voice-sample waits for its operands
+// (measured 80 cycles per sample, config 2: 0.170 ms for 4 096 voices x 4 096 samples).  A voice's
+// time axis cannot be split, but the CHAIN can: the generator (phase accumulate + waveshape: a long
+// but time-parallel computation, the only recurrence is one integer add) and the filter (a short
+// 16-cycle recurrence) are different pipeline stages.  Here every 32-voice group is run by a TEAM
+// of two warps in one 64-thread CTA:
+//   warp G: waits for the TMA load of block t (mbarrier `full`), overwrites the frequency tile with the
+//           generator's output in place, arrives on `gen`;
+//   warp F: waits on `gen`, runs filter(s) + gain in place, sums the mix-bus columns, hands the block to
+//           the TMA store, and arrives on `free` once that store has drained its shared-memory reads.
+// Both walk a ring of S 8-KB stages; G's lane 0 keeps S-3 loads in flight.  Per sample each warp now
+// has roughly half the dependent instructions, and the two halves overlap: ~2x per group, and a
+// group costs 2 warps so banks up to 2 x 592 warps still fit one wave.
+template <class P>
+__global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ CUtensorMap in_map,
+                                                        const __grid_constant__ CUtensorMap out_map,
+                                                        const ChainArgs a)
+{
+  static_assert(P::SPLIT, "team kernel needs a generator and a filter");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;  // 0 = G (load + generator), 1 = F (filter + store)
+  const int S = a.stages;
+  const int LA = S - 3;               // loads in flight ahead of the generator
+  const uint32_t base = smem_u32(smem_raw);
+  if (base & 1023u) __trap();
+  const uint32_t bar_full = base + (uint32_t)S * kBlockBytes;
+  const uint32_t bar_gen = bar_full + 8u * (uint32_t)S;
+  const uint32_t bar_free = bar_gen + 8u * (uint32_t)S;
+  if (threadIdx.x == 0)
+  {
+    for (int s = 0; s < S; ++s)
+    {
+      mbar_init(bar_full + 8u * s, 1);
+      mbar_init(bar_gen + 8u * s, 1);
+      mbar_init(bar_free + 8u * s, 1);
+    }
+    fence_mbar_init();
+    if (P::HAS_IN) prefetch_tensormap(&in_map);
+    if (a.write_out) prefetch_tensormap(&out_map);
+  }
+  __syncthreads();
+
+  const int g = blockIdx.x;
+  const int v0 = g * kTileVoices;
+  const int v = v0 + lane;
+  const bool live = v < a.V;
+  const bool full_group = (v0 + kTileVoices <= a.V);
+  const uint32_t row_off = (uint32_t)lane * 128u;
+  const uint32_t sw = (uint32_t)(lane & 7) << 4;
+  const int T = a.T;
+
+  uint32_t st[P::NS > 0 ? P::NS : 1];
+  float co[P::NC > 0 ? P::NC : 1];
+#pragma unroll
+  for (int i = 0; i < P::NS; ++i) st[i] = live ? __ldcg(a.state + (size_t)a.st_idx[i] * a.v_stride + v) : 0u;
+#pragma unroll
+  for (int i = 0; i < P::NC; ++i) co[i] = live ? a.coef[(size_t)a.co_idx[i] * a.v_stride + v] : 0.0f;
+
+  if (warp == 0)
+  {
+    // ---------------- G: TMA loads + generator ----------------
+    auto issue_load = [&](int blk_t)
+    {
+      const int s = blk_t % S, use = blk_t / S;
+      if (use > 0) mbar_wait(bar_free + 8u * s, (uint32_t)(use - 1) & 1u);  // the store of the previous use drained
+      mbar_arrive_expect_tx(bar_full + 8u * s, kBlockBytes);
+      tma_load_4d(base + (uint32_t)s * kBlockBytes, &in_map, bar_full + 8u * s, 0, v0, 0,
+                  blk_t * a.n_in_planes + a.in_plane, kEvictFirst);
+    };
+    if (P::HAS_IN && lane == 0)
+      for (int t = 0; t < LA && t < T; ++t) issue_load(t);
+    for (int b = 0; b < T; ++b)
+    {
+      const int s = b % S, use = b / S;
+      const uint32_t blk = base + (uint32_t)s * kBlockBytes;
+      if (P::HAS_IN)
+      {
+        if (lane == 0 && b + LA < T) issue_load(b + LA);
+        mbar_wait(bar_full + 8u * s, (uint32_t)use & 1u);
+      }
+      else if (use > 0)
+        mbar_wait(bar_free + 8u * s, (uint32_t)(use - 1) & 1u);
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h)
+      {
+        const uint32_t tile = blk + (uint32_t)h * kTileBytes;
+        float4 xin[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          xin[j] = P::HAS_IN ? lds128(tile + row_off + (((uint32_t)j << 4) ^ sw)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+        {
+          float4 y;
+          y.x = P::tick_gen(xin[j].x, st, co);
+          y.y = P::tick_gen(xin[j].y, st, co);
+          y.z = P::tick_gen(xin[j].z, st, co);
+          y.w = P::tick_gen(xin[j].w, st, co);
+          sts128(tile + row_off + (((uint32_t)j << 4) ^ sw), y);
+        }
+      }
+      __syncwarp();  // every lane's rows are written before lane 0 publishes the block
+      if (lane == 0) mbar_arrive(bar_gen + 8u * s);
+    }
+#pragma unroll
+    for (int i = 0; i < P::NS_GEN; ++i)
+      if (live) __stcg(a.state + (size_t)a.st_idx[i] * a.v_stride + v, st[i]);
+  }
+  else
+  {
+    // ---------------- F: filter(s) + gain + mix bus + TMA store ----------------
+    uint32_t mix_off[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      mix_off[j] = ((((uint32_t)lane >> 2) ^ (uint32_t)j) << 4) + (((uint32_t)lane & 3u) << 2);
+    const size_t mix_block_stride = (size_t)a.n_out_planes * a.groups_stride * MLB_BLOCK;
+    float* mix_row = a.mix_partial
+                         ? a.mix_partial + ((size_t)a.out_plane * a.groups_stride + g) * MLB_BLOCK + lane
+                         : nullptr;
+    for (int b = 0; b < T; ++b)
+    {
+      const int s = b % S, use = b / S;
+      const uint32_t blk = base + (uint32_t)s * kBlockBytes;
+      mbar_wait(bar_gen + 8u * s, (uint32_t)use & 1u);
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h)
+      {
+        const uint32_t tile = blk + (uint32_t)h * kTileBytes;
+        float4 xin[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xin[j] = lds128(tile + row_off + (((uint32_t)j << 4) ^ sw));
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+        {
+          float4 y;
+          y.x = P::tick_flt(xin[j].x, st, co);
+          y.y = P::tick_flt(xin[j].y, st, co);
+          y.z = P::tick_flt(xin[j].z, st, co);
+          y.w = P::tick_flt(xin[j].w, st, co);
+          sts128(tile + row_off + (((uint32_t)j << 4) ^ sw), y);
+          if (j == 3 && h == 0 && lane == 0 && b > 0 && a.write_out)
+          {
+            // a quarter block after the previous block's store was issued it has drained its reads
+            bulk_wait_read<0>();
+            mbar_arrive(bar_free + 8u * (uint32_t)((b - 1) % S));
+          }
+        }
+        if (a.mix_partial != nullptr)
+        {
+          __syncwarp();
+          float acc = 0.0f;
+          if (full_group)
+          {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) acc = __fadd_rn(acc, lds32(tile + mix_off[r & 7] + (uint32_t)r * 128u));
+          }
+          else
+          {
+            for (int r = 0; r < 32; ++r)
+              if (v0 + r < a.V) acc = __fadd_rn(acc, lds32(tile + mix_off[r & 7] + (uint32_t)r * 128u));
+          }
+          mix_row[h * kTileSamples] = acc;
+        }
+      }
+      if (a.mix_partial != nullptr) mix_row += mix_block_stride;
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0)
+      {
+        if (a.write_out)
+        {
+          tma_store_4d(&out_map, blk, 0, v0, 0, b * a.n_out_planes + a.out_plane);
+          bulk_commit();
+        }
+        else
+          mbar_arrive(bar_free + 8u * s);  // nothing reads the stage any more
+      }
+    }
+#pragma unroll
+    for (int i = P::NS_GEN; i < P::NS; ++i)
+      if (live) __stcg(a.state + (size_t)a.st_idx[i] * a.v_stride + v, st[i]);
+    if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last bulk stores
+    __syncwarp();
+  }
 }
 
 // second stage of the mix bus.  Deterministic two-level sum (DESIGN.md "mix bus"):

@@ -483,7 +483,16 @@ struct FusedEntry
   const char* name;
   bool has_in;
   int n_planes;  // 8-KB planes a ring stage holds (Chain::NP): the input row and/or coefficient rows
+  ChainKernelFn team_fn;  // two-warp team variant for small banks (chain_team_kernel), or nullptr
 };
+template <class P>
+static constexpr ChainKernelFn team_fn_of()
+{
+  if constexpr (P::SPLIT)
+    return chain_team_kernel<P>;
+  else
+    return nullptr;
+}
 
 #define N_ (-1)
 // (GEN, SRC, F1, F2, GAIN)
@@ -513,9 +522,10 @@ struct FusedEntry
 static const FusedEntry g_fused[] = {
 #define MLB_X_ENTRY(G, S, F1, F2, GN)                                                          \
   {G, S, F1, F2, GN, 1, chain_kernel<Chain<G, S, F1, F2, GN, true>>, #G "+" #F1 "+" #F2 "+" #GN, \
-   S == SRC_INPUT, Chain<G, S, F1, F2, GN, true>::NP},                                         \
+   S == SRC_INPUT, Chain<G, S, F1, F2, GN, true>::NP, team_fn_of<Chain<G, S, F1, F2, GN, true>>()}, \
       {G, S, F1, F2, GN, 0, chain_kernel<Chain<G, S, F1, F2, GN, false>>,                        \
-       #G "+" #F1 "+" #F2 "+" #GN "(fast)", S == SRC_INPUT, Chain<G, S, F1, F2, GN, false>::NP},
+       #G "+" #F1 "+" #F2 "+" #GN "(fast)", S == SRC_INPUT, Chain<G, S, F1, F2, GN, false>::NP,    \
+       team_fn_of<Chain<G, S, F1, F2, GN, false>>()},
     MLB_FUSED_LIST(MLB_X_ENTRY)
 #undef MLB_X_ENTRY
 };
@@ -1439,6 +1449,37 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
   a.n_groups = n_groups;
   a.groups_stride = groups_total;
   a.write_out = out_dev ? 1 : 0;
+  // Small banks: a TEAM of two warps per voice group (generator | filter pipeline, chain_team_kernel):
+  // with fewer than ~4 groups per SM a lone warp per group is latency-bound, and the chain is the
+  // only axis left to split.  One 64-thread CTA per group, static assignment, no scheduler words.
+  if (e.team_fn && n_groups <= g_sm_count * 4 && env_int("MLB_CHAIN_TEAM", 1) != 0)
+  {
+    const int S = std::min(std::max(env_int("MLB_TEAM_STAGES", 6), 4), 16);
+    a.stages = S;
+    a.chunk_blocks = T, a.n_chunks = 1;
+    a.sched = g->d_sched, a.progress = g->d_sched + 1 + va / 32, a.progress_base = g->progress_base;
+    g->launch_chunks = 1;
+    const size_t smem = (size_t)S * kBlockBytes + (size_t)3 * S * 8;
+    CUtensorMap in_map, out_map;
+    memset(&in_map, 0, sizeof(in_map));
+    memset(&out_map, 0, sizeof(out_map));
+    if (e.has_in)
+    {
+      rc = make_block_map(&in_map, in_dev + (size_t)va * MLB_BLOCK, Vs, (long long)T * a.n_in_planes,
+                          (long long)V * MLB_BLOCK);
+      if (rc != MLB_OK) return rc;
+    }
+    if (out_dev)
+    {
+      rc = make_block_map(&out_map, out_dev + (size_t)va * MLB_BLOCK, Vs, (long long)T, (long long)V * MLB_BLOCK);
+      if (rc != MLB_OK) return rc;
+    }
+    CU_CHECK(cudaFuncSetAttribute((const void*)e.team_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    e.team_fn<<<n_groups, 64, smem, stream>>>(in_map, out_map, a);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+    return MLB_OK;
+  }
   // Launch shape (DESIGN.md "occupancy").  The grid is persistent: one CTA of W warps per SM,
   // each warp owns a ring of S 8-KB blocks and pulls (group, chunk) work units from an atomic
   // queue.  W is a multiple of 4 so the four SM sub-partitions carry equal warp counts; small

@@ -159,8 +159,8 @@ class GraphSpec:
         arr = (Node * max(1, self.n_nodes))()
         for i in range(self.n_nodes):
             arr[i].op = self.ops[i]
-            for k in range(MAX_INS):
-                arr[i].inp[k] = self.ins[i][k]
+            for k in range(MAX_INS):  # shorter tuples (hand-built specs) are padded with -1
+                arr[i].inp[k] = self.ins[i][k] if k < len(self.ins[i]) else -1
             arr[i].iarg = self.iargs[i]
         return arr
 
