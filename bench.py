@@ -299,7 +299,7 @@ def parity_check(w, sel, n_steps, T, inp_sel, got_rows, got_state):
 class Leg:
     """One bank on this rank (weak: the whole 65 536-voice bank; strong: this rank's V/G shard)."""
 
-    def __init__(self, torch, api, wl, dist, dev, V_bank, v0, v1, T, fast, use_mix):
+    def __init__(self, torch, api, wl, dist, dev, V_bank, v0, v1, T, fast, use_mix, collective="peer"):
         self.torch, self.api, self.dist = torch, api, dist
         full = wl.config_a(V_bank)
         self.full = full
@@ -316,8 +316,16 @@ class Leg:
         self.d_out = torch.empty((T, 1, self.V, BLOCK), dtype=torch.float32, device=dev)
         self.use_mix = use_mix
         self.d_mix = [torch.zeros((T, 1, BLOCK), dtype=torch.float32, device=dev) for _ in range(2)]
-        from madronalib_b200.parallel import MixBusReducer
-        self.reducer = MixBusReducer(dist)
+        from madronalib_b200.parallel import MixBusReducer, PeerMixBus
+        # the mix-bus all-reduce: "peer" = fused into the kernel that finishes the local sum, over NVLink peer
+        # memory (no collective call per step); "nccl" = the checked fallback, issued asynchronously
+        self.peer = None
+        self.collective = "none"
+        if dist is not None and use_mix:
+            self.collective = collective
+            if collective == "peer":
+                self.peer = PeerMixBus(dist, api, self.graph, T * BLOCK)
+        self.reducer = MixBusReducer(dist if (self.peer is None and self.collective == "nccl") else None)
         self.steps_done = 0
         self.stream = torch.cuda.current_stream()
 
@@ -375,7 +383,18 @@ class Leg:
         inp_sel = np.ascontiguousarray(self.h_in.numpy()[:, :, sel])
         return parity_check(self.w, sel, self.steps_done, self.T, inp_sel, rows, st)
 
+    def detach_collective(self):
+        """Local mix only from here on (used to measure what the collective costs)."""
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
+        self.reducer = type(self.reducer)(None)
+        self.collective = "none"
+
     def close(self):
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
         self.graph.close()
 
 
@@ -417,8 +436,9 @@ def run_cuda_arm(args):
         v0, v1 = V * rank // world, V * (rank + 1) // world
     else:
         v0, v1 = 0, V
-    leg = Leg(torch, api, wl, dist, dev, V, v0, v1, T, args.fast, use_mix)
+    leg = Leg(torch, api, wl, dist, dev, V, v0, v1, T, args.fast, use_mix, args.collective)
     graph = leg.graph
+    collective = leg.collective
     torch.cuda.synchronize()
 
     sampler = ClockSampler(physical_gpu_index(local_rank)) if rank == 0 else None
@@ -433,6 +453,15 @@ def run_cuda_arm(args):
         t = torch.tensor([par["mismatches"]], dtype=torch.int64, device=dev)
         dist.all_reduce(t)
         par["mismatches_all_ranks"] = int(t.item())
+
+    # ---- what the collective costs: the same K steps with the bus detached (local mix only) ----
+    collective_cost = None
+    if world > 1 and use_mix:
+        leg.detach_collective()
+        ms_local, _ = leg.timed(args.steps, 1)
+        collective_cost = {"kind": collective, "ms_per_step_with": ms / args.steps,
+                           "ms_per_step_local_mix_only": ms_local / args.steps,
+                           "us_per_step": 1e3 * (ms - ms_local) / args.steps}
 
     # ---- roofline of the dominant kernel: per-launch CUDA-event durations (library events on
     # the launching stream), measured live, outside the timed region above ----
@@ -536,10 +565,10 @@ def run_cuda_arm(args):
         leg.close()
         del leg.d_in, leg.d_out, leg.h_in
         if strong:
-            leg2 = Leg(torch, api, wl, dist, dev, V, 0, V, T, args.fast, use_mix)
+            leg2 = Leg(torch, api, wl, dist, dev, V, 0, V, T, args.fast, use_mix, args.collective)
         else:
             leg2 = Leg(torch, api, wl, dist, dev, V, V * rank // world, V * (rank + 1) // world, T, args.fast,
-                       use_mix)
+                       use_mix, args.collective)
         torch.cuda.synchronize()
         ms2, launches2 = leg2.timed(args.steps, args.warmup)
         vs_job2 = (V * world if strong else V) * T * BLOCK
@@ -551,7 +580,13 @@ def run_cuda_arm(args):
         other = {"scaling": "weak" if strong else "strong", "value": vs_job2 * args.steps / (ms2 * 1e-3),
                  "unit": UNIT, "ms_per_step": ms2 / args.steps, "steps": args.steps, "warmup": args.warmup,
                  "voices_per_gpu": leg2.V, "voices_total": V * world if strong else V,
-                 "gpu_launches": int(launches2), "kernel": leg2.graph.kernel_name, "parity": par2}
+                 "gpu_launches": int(launches2), "kernel": leg2.graph.kernel_name, "parity": par2,
+                 "collective": leg2.collective}
+        leg2.detach_collective()
+        ms2l, _ = leg2.timed(args.steps, 1)
+        other["collective_cost"] = {"kind": other["collective"], "ms_per_step_with": ms2 / args.steps,
+                                    "ms_per_step_local_mix_only": ms2l / args.steps,
+                                    "us_per_step": 1e3 * (ms2 - ms2l) / args.steps}
         leg2.close()
     else:
         kernel_name = graph.kernel_name
@@ -574,7 +609,7 @@ def run_cuda_arm(args):
                 "voices_per_gpu": leg.V, "voices_total": V if strong else V * world,
                 "blocks_per_step": T, "samples_per_block": BLOCK,
                 "mix_bus": use_mix,
-                "parallelism": f"voices x{world} ({mode}), mix-bus all-reduce"
+                "parallelism": f"voices x{world} ({mode}), mix-bus all-reduce ({collective})"
                                + (f"; NCCL warmed up by {nccl_warm} untimed collectives before the "
                                   f"{args.warmup} warm-up steps" if world > 1 else ""),
                 "l2": "inputs+outputs %.2f GB per step and GPU >> 126 MB L2 (no flush needed)"
@@ -587,6 +622,8 @@ def run_cuda_arm(args):
             "realtime_x": value / ((V if strong else V * world) * 48000.0),
             "parity": par,
         }
+        if collective_cost is not None:
+            line["collective_cost"] = collective_cost
         if other is not None:
             line["other_scaling"] = other
         if cpu is not None:
@@ -618,6 +655,9 @@ def main():
                     help="N > 1: weak = 65536 voices per GPU (default, the line's `value`); strong = 65536 "
                          "voices in total, V/G per GPU (SURVEY 8d).  The other mode is measured in the same run "
                          "and reported under `other_scaling`.")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the mix bus is all-reduced: peer = inside the kernel over NVLink peer memory "
+                         "(default), nccl = torch.distributed all_reduce issued asynchronously")
     ap.add_argument("--mix", type=int, default=1)
     ap.add_argument("--fast", action="store_true", help="allow FMA contraction (not bit-exact)")
     ap.add_argument("--e2e-steps", type=int, default=6)

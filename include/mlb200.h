@@ -508,6 +508,22 @@ int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float* out_dev, 
 int mlb_graph_process_host(mlb_graph* g, const float* in_host, float* out_host, float* mix_host,
                            int n_blocks);
 
+/* ---- multi-GPU mix bus: one process per GPU, voices sharded, the ONLY exchange is the sum of the
+ * per-rank mix buses (Synth::processVector's accumulate, source/app/MLSynth.h:36-60, continued over GPUs).
+ * With a mix bus attached, mlb_graph_process_* delivers in `mix` the sum over ALL ranks: the kernel that
+ * finishes the local sum writes it into every peer's exchange buffer over NVLink (CUDA IPC peer memory),
+ * raises per-plane flags, waits for the peers' flags and adds the world's rows in rank order -- bit-identical
+ * on every rank, no NCCL call, no extra launch.  Set-up: every rank creates its bus, the 64-byte handles are
+ * exchanged by whatever means the host has (torch.distributed all_gather in bench.py), every rank connects.
+ * Every rank must then issue the same sequence of process calls (as with any collective).
+ * max_floats = largest n_blocks * n_out * 64 a call will reduce. */
+typedef struct mlb_mixbus mlb_mixbus;
+int mlb_mixbus_create(int rank, int world, size_t max_floats, mlb_mixbus** out);
+int mlb_mixbus_handle(mlb_mixbus* bus, void* out64);              /* this rank's cudaIpcMemHandle_t (64 bytes) */
+int mlb_mixbus_connect(mlb_mixbus* bus, const void* handles);     /* [world][64], rank order */
+int mlb_mixbus_destroy(mlb_mixbus* bus);
+int mlb_graph_attach_mixbus(mlb_graph* g, mlb_mixbus* bus);       /* NULL detaches */
+
 /* Duration in milliseconds of the most recent chain kernel launched by
  * process_device, measured with CUDA events on the launching stream
  * (blocks until that launch has finished). */

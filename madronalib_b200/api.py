@@ -98,6 +98,11 @@ def lib() -> ctypes.CDLL:
     L.mlb_graph_process_host.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int]
     L.mlb_graph_last_kernel_ms.argtypes = [_vp, _vp]
     L.mlb_graph_last_host_slices.argtypes = [_vp]
+    L.mlb_mixbus_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(_vp)]
+    L.mlb_mixbus_handle.argtypes = [_vp, _vp]
+    L.mlb_mixbus_connect.argtypes = [_vp, _vp]
+    L.mlb_mixbus_destroy.argtypes = [_vp]
+    L.mlb_graph_attach_mixbus.argtypes = [_vp, _vp]
     L.mlb_map_device.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]
     L.mlb_map_host.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_size_t]
     L.mlb_map_host_allocations.restype = ctypes.c_longlong
@@ -334,6 +339,10 @@ class VoiceGraph:
         """The input buffer carries n_planes planes per block (more than the graph reads)."""
         _check(lib().mlb_graph_set_input_planes(self._h, int(n_planes)))
 
+    def attach_mixbus(self, bus: Optional["MixBus"]) -> None:
+        """From now on `mix` is the sum over all ranks of the bus (reduced in-kernel over NVLink)."""
+        _check(lib().mlb_graph_attach_mixbus(self._h, bus._h if bus is not None else None))
+
     def reserve_sms(self, n_sms: int) -> None:
         """Keep n_sms SMs out of the persistent chain grid (room for an overlapped collective)."""
         _check(lib().mlb_graph_reserve_sms(self._h, int(n_sms)))
@@ -347,6 +356,32 @@ class VoiceGraph:
         ms = ctypes.c_float(0)
         _check(lib().mlb_graph_last_kernel_ms(self._h, ctypes.byref(ms)))
         return float(ms.value)
+
+
+class MixBus:
+    """Multi-GPU mix bus over peer memory (mlb_mixbus_*): after ``connect`` + ``graph.attach_mixbus(bus)`` the
+    ``mix`` output of every process call is the sum over all ranks, reduced inside the kernel over NVLink."""
+
+    def __init__(self, rank: int, world: int, max_floats: int):
+        self._h = _vp()
+        self.rank, self.world = rank, world
+        _check(lib().mlb_mixbus_create(rank, world, max_floats, ctypes.byref(self._h)))
+
+    def handle(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        _check(lib().mlb_mixbus_handle(self._h, buf))
+        return buf.raw
+
+    def connect(self, handles) -> None:
+        """handles: the 64-byte handle of every rank, in rank order."""
+        blob = b"".join(bytes(h) for h in handles)
+        assert len(blob) == 64 * self.world
+        _check(lib().mlb_mixbus_connect(self._h, blob))
+
+    def close(self) -> None:
+        if self._h:
+            lib().mlb_mixbus_destroy(self._h)
+            self._h = _vp()
 
 
 class VoiceBank:

@@ -643,9 +643,48 @@ __global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ 
 //   mix[p][n]   = sum over chunks c = 0..C-1, in order, from +0
 // One CTA per plane, 64 x 16 threads: thread (n, w) owns chunks w, w+16, ...
 constexpr int kMixChunkGroups = 64;  // 64 groups x 32 voices = 2048 voices per chunk
+
+// Multi-GPU mix bus: the sum over voices continues over the GPUs of one box INSIDE this
+// kernel, through peer memory over NVLink -- a one-shot all-reduce executed by the CTA that just finished
+// plane p's local tree.  Every rank owns an exchange buffer xchg[2 parities][world][n_floats] and flags
+// flag[2][world][n_planes]; peer r's buffer is mapped here as peers[r] (cudaIpc).  Protocol for plane p of
+// call number `seq` (parity = seq & 1):
+//   1. write my 64 local sums into slot [parity][my_rank] of EVERY rank's buffer (remote stores, 256 B rows);
+//   2. __threadfence_system, then store-release flag[parity][my_rank][p] = seq on every rank;
+//   3. wait until my own flag[parity][r][p] == seq for every r (acquire loads at system scope);
+//   4. mix[p][n] = sum over r = 0..world-1, left to right from +0, of my slot [parity][r] -- the same order on
+//      every rank, so all ranks hold bit-identical results (and the CPU checker reproduces it: shards in rank
+//      order).
+// A parity is reused two calls later; a peer can only get there after it has seen this rank's flags of the
+// call in between, which this rank writes only after it finished reading: double buffering suffices.
+// No rank ever waits for a peer to FINISH, only for its writes, and every rank launches the same sequence
+// of kernels, so there is no circular wait.
+constexpr int kMaxBusRanks = 16;
+struct MixBusArgs
+{
+  float* xchg[kMaxBusRanks];     // [r]: rank r's exchange buffer (xchg[my_rank] is local memory)
+  unsigned* flags[kMaxBusRanks];  // [r]: rank r's flag words
+  int rank, world;
+  unsigned seq;
+  int n_floats;   // floats per slot (>= n_planes * 64 of this call)
+  int n_planes_cap;  // planes per flag row
+};
+
+MLB_DEV unsigned ld_acquire_sys_u32(const unsigned* p)
+{
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+MLB_DEV void st_release_sys_u32(unsigned* p, unsigned v)
+{
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __global__ void __launch_bounds__(1024) mix_reduce_kernel(const float* __restrict__ partial,
                                                           float* __restrict__ chunk_scratch,
-                                                          float* __restrict__ mix, int n_groups)
+                                                          float* __restrict__ mix, int n_groups,
+                                                          const MixBusArgs bus)
 {
   const int p = blockIdx.x, n = threadIdx.x, w = threadIdx.y;
   const int n_chunks = (n_groups + kMixChunkGroups - 1) / kMixChunkGroups;
@@ -669,12 +708,34 @@ __global__ void __launch_bounds__(1024) mix_reduce_kernel(const float* __restric
     scratch[(size_t)c * MLB_BLOCK] = acc;
   }
   __syncthreads();  // also orders the global scratch writes within the CTA
-  if (w == 0)
+  if (w != 0) return;
+  float acc = 0.0f;
+  for (int c = 0; c < n_chunks; ++c) acc = __fadd_rn(acc, scratch[(size_t)c * MLB_BLOCK]);
+  if (bus.world <= 1)
   {
-    float acc = 0.0f;
-    for (int c = 0; c < n_chunks; ++c) acc = __fadd_rn(acc, scratch[(size_t)c * MLB_BLOCK]);
     mix[(size_t)p * MLB_BLOCK + n] = acc;
+    return;
   }
+  // ---- the sum continues over the GPUs of the box (threads (n, 0): two warps of this CTA) ----
+  const unsigned parity = bus.seq & 1u;
+  const size_t slot = ((size_t)parity * bus.world + bus.rank) * bus.n_floats + (size_t)p * MLB_BLOCK + n;
+  for (int r = 0; r < bus.world; ++r) bus.xchg[r][slot] = acc;  // 1. my sums into everyone's buffer
+  __threadfence_system();
+  asm volatile("bar.sync 1, 64;" ::: "memory");  // both warps' stores are fenced before the flags go out
+  if (n < bus.world)
+  {
+    const size_t f = ((size_t)parity * bus.world + bus.rank) * bus.n_planes_cap + p;
+    st_release_sys_u32(bus.flags[n] + f, bus.seq);  // 2. one flag per destination rank
+    // 3. wait for rank n's flag in MY memory
+    const unsigned* mine = bus.flags[bus.rank] + ((size_t)parity * bus.world + n) * bus.n_planes_cap + p;
+    while (ld_acquire_sys_u32(mine) != bus.seq) __nanosleep(40);
+  }
+  asm volatile("bar.sync 1, 64;" ::: "memory");
+  __threadfence_system();
+  const float* loc = bus.xchg[bus.rank] + (size_t)parity * bus.world * bus.n_floats + (size_t)p * MLB_BLOCK + n;
+  float sum = 0.0f;
+  for (int r = 0; r < bus.world; ++r) sum = __fadd_rn(sum, __ldcv(loc + (size_t)r * bus.n_floats));  // 4.
+  mix[(size_t)p * MLB_BLOCK + n] = sum;
 }
 
 }  // namespace mlb

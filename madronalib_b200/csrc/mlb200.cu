@@ -609,6 +609,7 @@ struct mlb_graph
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   int last_host_slices = 0;  // voice slices of the most recent mlb_graph_process_host call (1 = one launch)
+  struct mlb_mixbus* bus = nullptr;  // multi-GPU: the mix bus is all-reduced over peer memory inside mix_reduce_kernel
 };
 
 // delay memory of an op: 64-float member rows and IntegerDelay rings per voice (MLB_OP_MEM_TABLE)
@@ -1391,6 +1392,106 @@ extern "C" size_t mlb_graph_delay_bytes(const mlb_graph* g)
   return bytes;
 }
 
+// ------------------------------------------------------------------------------------------
+// multi-GPU mix bus over peer memory (one process per GPU; buffers shared through CUDA IPC)
+
+struct mlb_mixbus
+{
+  int rank = 0, world = 1;
+  size_t n_floats = 0;   // floats per slot
+  int n_planes_cap = 0;  // flag words per (parity, rank)
+  void* base = nullptr;  // one allocation: xchg [2][world][n_floats] f32, then flags [2][world][n_planes_cap] u32
+  void* peer_base[kMaxBusRanks] = {};
+  bool connected = false;
+  unsigned seq = 0;
+  size_t xchg_bytes() const { return (size_t)2 * world * n_floats * 4; }
+  size_t total_bytes() const { return xchg_bytes() + (size_t)2 * world * n_planes_cap * 4; }
+};
+
+extern "C" int mlb_mixbus_create(int rank, int world, size_t max_floats, mlb_mixbus** out)
+{
+  if (!out) return fail(MLB_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (world < 1 || world > kMaxBusRanks || rank < 0 || rank >= world || max_floats == 0 || (max_floats % MLB_BLOCK))
+    return fail(MLB_ERR_INVALID, "mlb_mixbus_create: need 0 <= rank < world <= %d and max_floats a multiple of 64", kMaxBusRanks);
+  int rc = ensure_init();
+  if (rc != MLB_OK) return rc;
+  mlb_mixbus* b = new mlb_mixbus;
+  b->rank = rank, b->world = world, b->n_floats = max_floats, b->n_planes_cap = (int)(max_floats / MLB_BLOCK);
+  if (cudaMalloc(&b->base, b->total_bytes()) != cudaSuccess)
+  {
+    delete b;
+    return fail(MLB_ERR_ALLOC, "cudaMalloc of %zu B exchange buffer failed", b->total_bytes());
+  }
+  cudaMemset(b->base, 0, b->total_bytes());
+  cudaDeviceSynchronize();
+  b->peer_base[rank] = b->base;
+  b->connected = (world == 1);
+  ++g_live_handles;
+  *out = b;
+  return MLB_OK;
+}
+extern "C" int mlb_mixbus_handle(mlb_mixbus* b, void* out64)
+{
+  if (!b || !out64) return fail(MLB_ERR_INVALID, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  cudaIpcMemHandle_t h;
+  CU_CHECK(cudaIpcGetMemHandle(&h, b->base));
+  memcpy(out64, &h, 64);
+  return MLB_OK;
+}
+extern "C" int mlb_mixbus_connect(mlb_mixbus* b, const void* handles)
+{
+  if (!b || !handles) return fail(MLB_ERR_INVALID, "null argument");
+  for (int r = 0; r < b->world; ++r)
+  {
+    if (r == b->rank || b->peer_base[r]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)r * 64, 64);
+    CU_CHECK(cudaIpcOpenMemHandle(&b->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  b->connected = true;
+  return MLB_OK;
+}
+extern "C" int mlb_mixbus_destroy(mlb_mixbus* b)
+{
+  if (!b) return MLB_OK;
+  cudaDeviceSynchronize();
+  for (int r = 0; r < b->world; ++r)
+    if (r != b->rank && b->peer_base[r]) cudaIpcCloseMemHandle(b->peer_base[r]);
+  cudaFree(b->base);
+  delete b;
+  --g_live_handles;
+  return MLB_OK;
+}
+extern "C" int mlb_graph_attach_mixbus(mlb_graph* g, mlb_mixbus* b)
+{
+  if (!g) return fail(MLB_ERR_INVALID, "null graph");
+  if (b && !b->connected) return fail(MLB_ERR_INVALID, "mix bus is not connected to its peers yet");
+  g->bus = b;
+  return MLB_OK;
+}
+// kernel arguments of the next call's exchange (advances the call counter)
+static int bus_args(mlb_graph* g, int n_planes, MixBusArgs* a)
+{
+  memset(a, 0, sizeof(*a));
+  a->world = 1;
+  mlb_mixbus* b = g->bus;
+  if (!b || b->world <= 1) return MLB_OK;
+  if ((size_t)n_planes * MLB_BLOCK > b->n_floats)
+    return fail(MLB_ERR_INVALID, "mix bus holds %zu floats per rank, this call needs %zu", b->n_floats,
+                (size_t)n_planes * MLB_BLOCK);
+  a->rank = b->rank, a->world = b->world;
+  a->seq = ++b->seq;
+  a->n_floats = (int)b->n_floats, a->n_planes_cap = b->n_planes_cap;
+  for (int r = 0; r < b->world; ++r)
+  {
+    a->xchg[r] = (float*)b->peer_base[r];
+    a->flags[r] = (unsigned*)((char*)b->peer_base[r] + b->xchg_bytes());
+  }
+  return MLB_OK;
+}
+
 static int env_int(const char* name, int dflt)
 {
   const char* s = getenv(name);
@@ -1649,8 +1750,11 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
   if (mix_dev)
   {
     float* scratch = g->d_partial + (size_t)T * std::max(1, n_out) * n_groups * MLB_BLOCK;
+    MixBusArgs ba;
+    rc = bus_args(g, T * std::max(1, n_out), &ba);
+    if (rc != MLB_OK) return rc;
     mix_reduce_kernel<<<T * std::max(1, n_out), dim3(MLB_BLOCK, 16), 0, stream>>>(g->d_partial, scratch,
-                                                                                   mix_dev, n_groups);
+                                                                                   mix_dev, n_groups, ba);
     ++g_launches;
     CU_CHECK(cudaGetLastError());
   }
@@ -1723,8 +1827,11 @@ extern "C" int mlb_graph_process_host(mlb_graph* g, const float* in_host, float*
     {
       const int n_groups = (g->V + 31) / 32;
       float* scratch = g->d_partial + T * std::max<size_t>(1, n_out) * n_groups * MLB_BLOCK;
+      MixBusArgs ba;
+      rc = bus_args(g, (int)(T * std::max<size_t>(1, n_out)), &ba);
+      if (rc != MLB_OK) return rc;
       mix_reduce_kernel<<<(int)(T * std::max<size_t>(1, n_out)), dim3(MLB_BLOCK, 16), 0, s>>>(g->d_partial, scratch,
-                                                                                            g->d_mix, n_groups);
+                                                                                            g->d_mix, n_groups, ba);
       ++g_launches;
       CU_CHECK(cudaGetLastError());
       CU_CHECK(cudaMemcpyAsync(mix_host, g->d_mix, mix_bytes, cudaMemcpyDeviceToHost, s));

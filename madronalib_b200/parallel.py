@@ -49,3 +49,26 @@ class MixBusReducer:
     def drain(self) -> None:
         self.wait(0)
         self.wait(1)
+
+
+class PeerMixBus:
+    """The mix-bus all-reduce fused into the kernel that finishes the local sum (api.MixBus): every rank
+    creates an exchange buffer, the CUDA IPC handles travel through ``dist.all_gather_object`` once, and from
+    then on a process call with a `mix` output needs NO collective call -- the kernel writes its 64-sample
+    rows into every peer's buffer over NVLink and sums the world's rows in rank order.  ``MixBusReducer``
+    (NCCL / gloo) remains the checked fallback and the CPU-test path."""
+
+    def __init__(self, dist_module, api_module, graph, max_floats: int):
+        self.dist, self.graph = dist_module, graph
+        rank, world = dist_module.get_rank(), dist_module.get_world_size()
+        self.bus = api_module.MixBus(rank, world, max_floats)
+        handles = [None] * world
+        dist_module.all_gather_object(handles, self.bus.handle())
+        self.bus.connect(handles)
+        dist_module.barrier()  # nobody writes into a peer before every peer has mapped and zeroed its buffer
+        graph.attach_mixbus(self.bus)
+
+    def close(self) -> None:
+        self.graph.attach_mixbus(None)
+        self.dist.barrier()  # no peer may still be writing into this buffer
+        self.bus.close()
