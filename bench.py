@@ -323,8 +323,10 @@ class Leg:
         self.collective = "none"
         if dist is not None and use_mix:
             self.collective = collective
-            if collective == "peer":
-                self.peer = PeerMixBus(dist, api, self.graph, T * BLOCK)
+            if collective in ("peer", "peer-sync"):
+                # "peer": posting in the step's kernel, completion (wait for peers + sum) on the bus's own stream
+                # so that it overlaps the next step like an async NCCL all-reduce; "peer-sync": all in the kernel
+                self.peer = PeerMixBus(dist, api, self.graph, T * BLOCK, async_completion=(collective == "peer"))
         self.reducer = MixBusReducer(dist if (self.peer is None and self.collective == "nccl") else None)
         self.steps_done = 0
         self.stream = torch.cuda.current_stream()
@@ -343,13 +345,18 @@ class Leg:
             self.dist.barrier()
         self.torch.cuda.synchronize()
 
+    def drain(self):
+        self.reducer.drain()
+        if self.peer is not None:
+            self.graph.mix_wait(self.stream.cuda_stream)
+
     def timed(self, steps, warmup, sampler=None):
         """W untimed warm-up steps, then exactly `steps` steps bracketed by barrier + synchronize;
         device time (CUDA events on the launching stream), max over ranks."""
         torch = self.torch
         for i in range(warmup):
             self.step(i)
-        self.reducer.drain()
+        self.drain()
         self.barrier()
         launches0 = self.api.kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -359,7 +366,7 @@ class Leg:
         e0.record(self.stream)
         for i in range(steps):
             self.step(i)
-        self.reducer.drain()
+        self.drain()
         e1.record(self.stream)
         self.barrier()
         if sampler:
@@ -655,7 +662,7 @@ def main():
                     help="N > 1: weak = 65536 voices per GPU (default, the line's `value`); strong = 65536 "
                          "voices in total, V/G per GPU (SURVEY 8d).  The other mode is measured in the same run "
                          "and reported under `other_scaling`.")
-    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--collective", default="peer", choices=["peer", "peer-sync", "nccl"],
                     help="N > 1: how the mix bus is all-reduced: peer = inside the kernel over NVLink peer memory "
                          "(default), nccl = torch.distributed all_reduce issued asynchronously")
     ap.add_argument("--mix", type=int, default=1)

@@ -523,6 +523,14 @@ int mlb_mixbus_handle(mlb_mixbus* bus, void* out64);              /* this rank's
 int mlb_mixbus_connect(mlb_mixbus* bus, const void* handles);     /* [world][64], rank order */
 int mlb_mixbus_destroy(mlb_mixbus* bus);
 int mlb_graph_attach_mixbus(mlb_graph* g, mlb_mixbus* bus);       /* NULL detaches */
+/* Asynchronous completion (choose before the first process call, same on every rank): the kernel on the caller's
+ * stream only POSTS this rank's sums to the peers; waiting for the peers and adding the rows runs on the bus's
+ * own stream while the caller's stream already computes the next call (what an async NCCL all-reduce gives,
+ * without NCCL).  `mix` of a mlb_graph_process_device call is then complete only after
+ * mlb_graph_mix_wait(g, stream) -- which makes `stream` wait for the most recent call's completion -- so use
+ * one `mix` buffer per call in flight.  mlb_graph_process_host always returns finished results. */
+int mlb_mixbus_set_async(mlb_mixbus* bus, int on);
+int mlb_graph_mix_wait(mlb_graph* g, void* stream);
 
 /* Duration in milliseconds of the most recent chain kernel launched by
  * process_device, measured with CUDA events on the launching stream

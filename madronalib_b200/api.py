@@ -103,6 +103,8 @@ def lib() -> ctypes.CDLL:
     L.mlb_mixbus_connect.argtypes = [_vp, _vp]
     L.mlb_mixbus_destroy.argtypes = [_vp]
     L.mlb_graph_attach_mixbus.argtypes = [_vp, _vp]
+    L.mlb_mixbus_set_async.argtypes = [_vp, ctypes.c_int]
+    L.mlb_graph_mix_wait.argtypes = [_vp, _vp]
     L.mlb_map_device.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]
     L.mlb_map_host.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_size_t]
     L.mlb_map_host_allocations.restype = ctypes.c_longlong
@@ -343,6 +345,10 @@ class VoiceGraph:
         """From now on `mix` is the sum over all ranks of the bus (reduced in-kernel over NVLink)."""
         _check(lib().mlb_graph_attach_mixbus(self._h, bus._h if bus is not None else None))
 
+    def mix_wait(self, stream: int = 0) -> None:
+        """Make `stream` wait for the most recent call's mix bus (async mix bus only; else a no-op)."""
+        _check(lib().mlb_graph_mix_wait(self._h, stream or None))
+
     def reserve_sms(self, n_sms: int) -> None:
         """Keep n_sms SMs out of the persistent chain grid (room for an overlapped collective)."""
         _check(lib().mlb_graph_reserve_sms(self._h, int(n_sms)))
@@ -371,6 +377,10 @@ class MixBus:
         buf = ctypes.create_string_buffer(64)
         _check(lib().mlb_mixbus_handle(self._h, buf))
         return buf.raw
+
+    def set_async(self, on: bool = True) -> None:
+        """Completion (wait for peers + sum) on the bus's own stream; see mlb_mixbus_set_async."""
+        _check(lib().mlb_mixbus_set_async(self._h, int(on)))
 
     def connect(self, handles) -> None:
         """handles: the 64-byte handle of every rank, in rank order."""

@@ -1404,8 +1404,13 @@ struct mlb_mixbus
   void* peer_base[kMaxBusRanks] = {};
   bool connected = false;
   unsigned seq = 0;
+  int async = 0;                  // completion on a side stream (mlb_mixbus_set_async)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_posted = nullptr, ev_done = nullptr;
+  bool done_pending = false;
   size_t xchg_bytes() const { return (size_t)2 * world * n_floats * 4; }
-  size_t total_bytes() const { return xchg_bytes() + (size_t)2 * world * n_planes_cap * 4; }
+  size_t flag_bytes() const { return (size_t)2 * world * n_planes_cap * 4; }
+  size_t total_bytes() const { return xchg_bytes() + 2 * flag_bytes(); }  // slots, flags, acks
 };
 
 extern "C" int mlb_mixbus_create(int rank, int world, size_t max_floats, mlb_mixbus** out)
@@ -1427,6 +1432,9 @@ extern "C" int mlb_mixbus_create(int rank, int world, size_t max_floats, mlb_mix
   cudaDeviceSynchronize();
   b->peer_base[rank] = b->base;
   b->connected = (world == 1);
+  cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&b->ev_posted, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming);
   ++g_live_handles;
   *out = b;
   return MLB_OK;
@@ -1460,8 +1468,26 @@ extern "C" int mlb_mixbus_destroy(mlb_mixbus* b)
   for (int r = 0; r < b->world; ++r)
     if (r != b->rank && b->peer_base[r]) cudaIpcCloseMemHandle(b->peer_base[r]);
   cudaFree(b->base);
+  if (b->side) cudaStreamDestroy(b->side);
+  if (b->ev_posted) cudaEventDestroy(b->ev_posted);
+  if (b->ev_done) cudaEventDestroy(b->ev_done);
   delete b;
   --g_live_handles;
+  return MLB_OK;
+}
+extern "C" int mlb_mixbus_set_async(mlb_mixbus* b, int on)
+{
+  if (!b) return fail(MLB_ERR_INVALID, "null bus");
+  if (b->seq != 0 && (on != 0) != (b->async != 0))
+    return fail(MLB_ERR_INVALID, "mlb_mixbus_set_async: choose the mode before the first process call");
+  b->async = on ? 1 : 0;
+  return MLB_OK;
+}
+extern "C" int mlb_graph_mix_wait(mlb_graph* g, void* stream)
+{
+  if (!g) return fail(MLB_ERR_INVALID, "null graph");
+  mlb_mixbus* b = g->bus;
+  if (b && b->async && b->done_pending) CU_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, b->ev_done, 0));
   return MLB_OK;
 }
 extern "C" int mlb_graph_attach_mixbus(mlb_graph* g, mlb_mixbus* b)
@@ -1488,7 +1514,23 @@ static int bus_args(mlb_graph* g, int n_planes, MixBusArgs* a)
   {
     a->xchg[r] = (float*)b->peer_base[r];
     a->flags[r] = (unsigned*)((char*)b->peer_base[r] + b->xchg_bytes());
+    a->acks[r] = (unsigned*)((char*)b->peer_base[r] + b->xchg_bytes() + b->flag_bytes());
   }
+  a->async = b->async;
+  return MLB_OK;
+}
+// async mode: steps 3-4 on the bus's side stream, ordered after the post on `stream`
+static int bus_complete(mlb_graph* g, const MixBusArgs& ba, int n_planes, float* mix_dev, cudaStream_t stream)
+{
+  mlb_mixbus* b = g->bus;
+  if (!b || b->world <= 1 || !b->async) return MLB_OK;
+  CU_CHECK(cudaEventRecord(b->ev_posted, stream));
+  CU_CHECK(cudaStreamWaitEvent(b->side, b->ev_posted, 0));
+  mixbus_complete_kernel<<<n_planes, MLB_BLOCK, 0, b->side>>>(mix_dev, ba);
+  ++g_launches;
+  CU_CHECK(cudaGetLastError());
+  CU_CHECK(cudaEventRecord(b->ev_done, b->side));
+  b->done_pending = true;
   return MLB_OK;
 }
 
@@ -1755,6 +1797,8 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
     if (rc != MLB_OK) return rc;
     mix_reduce_kernel<<<T * std::max(1, n_out), dim3(MLB_BLOCK, 16), 0, stream>>>(g->d_partial, scratch,
                                                                                    mix_dev, n_groups, ba);
+    rc = bus_complete(g, ba, T * std::max(1, n_out), mix_dev, stream);
+    if (rc != MLB_OK) return rc;
     ++g_launches;
     CU_CHECK(cudaGetLastError());
   }
@@ -1832,6 +1876,10 @@ extern "C" int mlb_graph_process_host(mlb_graph* g, const float* in_host, float*
       if (rc != MLB_OK) return rc;
       mix_reduce_kernel<<<(int)(T * std::max<size_t>(1, n_out)), dim3(MLB_BLOCK, 16), 0, s>>>(g->d_partial, scratch,
                                                                                             g->d_mix, n_groups, ba);
+      rc = bus_complete(g, ba, (int)(T * std::max<size_t>(1, n_out)), g->d_mix, s);
+      if (rc != MLB_OK) return rc;
+      rc = mlb_graph_mix_wait(g, s);  // the host entry point returns finished results
+      if (rc != MLB_OK) return rc;
       ++g_launches;
       CU_CHECK(cudaGetLastError());
       CU_CHECK(cudaMemcpyAsync(mix_host, g->d_mix, mix_bytes, cudaMemcpyDeviceToHost, s));
@@ -1845,7 +1893,12 @@ extern "C" int mlb_graph_process_host(mlb_graph* g, const float* in_host, float*
                                 mix_host ? g->d_mix : nullptr, n_blocks, s);
   if (rc != MLB_OK) return rc;
   if (out_host) CU_CHECK(cudaMemcpyAsync(out_host, g->d_out, out_bytes, cudaMemcpyDeviceToHost, s));
-  if (mix_host) CU_CHECK(cudaMemcpyAsync(mix_host, g->d_mix, mix_bytes, cudaMemcpyDeviceToHost, s));
+  if (mix_host)
+  {
+    rc = mlb_graph_mix_wait(g, s);  // async mix bus: the completion runs on a side stream
+    if (rc != MLB_OK) return rc;
+    CU_CHECK(cudaMemcpyAsync(mix_host, g->d_mix, mix_bytes, cudaMemcpyDeviceToHost, s));
+  }
   CU_CHECK(cudaStreamSynchronize(s));
   return MLB_OK;
 }

@@ -58,10 +58,12 @@ class PeerMixBus:
     rows into every peer's buffer over NVLink and sums the world's rows in rank order.  ``MixBusReducer``
     (NCCL / gloo) remains the checked fallback and the CPU-test path."""
 
-    def __init__(self, dist_module, api_module, graph, max_floats: int):
+    def __init__(self, dist_module, api_module, graph, max_floats: int, async_completion: bool = False):
         self.dist, self.graph = dist_module, graph
         rank, world = dist_module.get_rank(), dist_module.get_world_size()
         self.bus = api_module.MixBus(rank, world, max_floats)
+        if async_completion:  # wait-for-peers + sum on the bus's own stream: graph.mix_wait(stream) completes it
+            self.bus.set_async(True)
         handles = [None] * world
         dist_module.all_gather_object(handles, self.bus.handle())
         self.bus.connect(handles)

@@ -27,7 +27,9 @@ def main():
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     P = PortOracle()
-    for full, T, n_calls in ((wl.config_a(2048 + 77), 5, 3), (wl.config_a(40000), 8, 2), (wl.config_4(96), 6, 2)):
+    for full, T, n_calls, use_async in ((wl.config_a(2048 + 77), 5, 3, False), (wl.config_a(40000), 8, 2, False),
+                                        (wl.config_4(96), 6, 2, False), (wl.config_a(2048 + 77), 5, 5, True),
+                                        (wl.config_a(40000), 8, 4, True)):
         V = full.n_voices
         v0, v1 = parallel.shard_range(V, rank, world)
         shard = full.shard(rank, world)
@@ -38,13 +40,14 @@ def main():
         g.set_coefs(shard.coef)
         g.set_state(shard.state)
         n_out = full.spec.n_out
-        bus = parallel.PeerMixBus(dist, api, g, T * n_out * 64)
+        bus = parallel.PeerMixBus(dist, api, g, T * n_out * 64, async_completion=use_async)
         d_in = torch.from_numpy(np.ascontiguousarray(inp_full[:, :, v0:v1])).to(dev)
         d_out = torch.empty((T * n_calls, n_out, v1 - v0, 64), dtype=torch.float32, device=dev)
         d_mix = torch.zeros((T * n_calls, n_out, 64), dtype=torch.float32, device=dev)
         sh = torch.cuda.current_stream().cuda_stream
         for c in range(n_calls):  # back-to-back calls: both parities of the exchange buffer, no host sync between
             g.process_device(d_in[c * T:(c + 1) * T], d_out[c * T:(c + 1) * T], d_mix[c * T:(c + 1) * T], T, sh)
+        g.mix_wait(sh)  # async completion: the last call's sum runs on the bus's stream (no-op otherwise)
         torch.cuda.synchronize()
         got_out, got_mix = d_out.cpu().numpy(), d_mix.cpu().numpy()
         assert np.array_equal(got_out.view(np.uint32), want_out[:, :, v0:v1].view(np.uint32)), "shard rows"
