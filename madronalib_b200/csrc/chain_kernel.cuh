@@ -96,9 +96,12 @@ struct ChainArgs
   int groups_stride;            // groups of the whole bank = row length of the mix partials
   int write_out;                // store per-voice output planes
   int stages;
-  unsigned* sched;              // unit counter (zeroed per launch)
+  unsigned* sched;              // unit counter; the warp that finishes the launch's last unit re-zeroes it
   unsigned* progress;           // [g] chunks finished by group g of this launch (monotonic)
-  unsigned progress_base;       // value of progress[g] at launch
+  unsigned* done;               // units finished in this launch (re-zeroed with sched)
+  unsigned* base_word;          // device-resident progress base: value of progress[g] "at launch"; the last
+                                // warp advances it by n_chunks.  Nothing launch-specific is baked into the
+                                // kernel arguments, so a captured CUDA graph of a process call can be replayed.
   int chunk_blocks, n_chunks;   // blocks per work unit, units per group
   int st_idx[kMaxChainState];  // SoA word index of each register state slot
   int co_idx[kMaxChainCoef];
@@ -180,6 +183,8 @@ __global__ void __launch_bounds__(kChainMaxWarps * 32)
   const int W = blockDim.x >> 5;
   const int S = a.stages;
   const int total_units = a.n_chunks * a.n_groups;
+  // read before this warp can finish a unit, i.e. before the launch's last unit can have been counted
+  const unsigned progress_base = (a.n_chunks > 1) ? __ldcg(a.base_word) : 0u;
 
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();  // the swizzle formula below assumes 1024-byte aligned tiles
@@ -187,10 +192,19 @@ __global__ void __launch_bounds__(kChainMaxWarps * 32)
   const uint32_t blocks = base + (uint32_t)(warp * S) * kStageBytes;
   const uint32_t bars = base + (uint32_t)(W * S) * kStageBytes + (uint32_t)(warp * S) * 8u;
 
+  // Every warp draws unit indices until it gets one >= total_units: exactly ONE failing draw per warp, so the
+  // counter ends at total_units + (warps of the grid), and the warp that draws that last value is the last one
+  // ever to touch the counter in this launch: it puts it back to zero for the next launch (no memset).
+  const unsigned last_draw = (unsigned)total_units + gridDim.x * (unsigned)W - 1u;
   auto grab = [&]() -> int
   {
     int u = 0;
-    if (lane == 0) u = (int)atomicAdd(a.sched, 1u);
+    if (lane == 0)
+    {
+      const unsigned d = atomicAdd(a.sched, 1u);
+      if (d == last_draw) atomicExch(a.sched, 0u);
+      u = (int)min(d, (unsigned)total_units);
+    }
     return __shfl_sync(0xffffffffu, u, 0);
   };
   auto decode = [&](int u) -> UnitCursor
@@ -279,7 +293,7 @@ __global__ void __launch_bounds__(kChainMaxWarps * 32)
     const bool full_group = (v0 + kTileVoices <= a.V);
     if (cur.t0 > 0)
     {
-      const unsigned want = a.progress_base + (unsigned)(cur.t0 / a.chunk_blocks);
+      const unsigned want = progress_base + (unsigned)(cur.t0 / a.chunk_blocks);
       const volatile unsigned* pr = a.progress + cur.g;
       while ((int)(*pr - want) < 0) __nanosleep(64);
       __threadfence();  // acquire: the predecessor's state stores are visible
@@ -417,7 +431,13 @@ __global__ void __launch_bounds__(kChainMaxWarps * 32)
       __threadfence();  // release: state stores before the progress flag
       __syncwarp();
       if (lane == 0)
-        atomicExch(a.progress + cur.g, a.progress_base + (unsigned)(cur.t0 / a.chunk_blocks) + 1u);
+        atomicExch(a.progress + cur.g, progress_base + (unsigned)(cur.t0 / a.chunk_blocks) + 1u);
+    }
+    // the launch's last unit: advance the device-resident progress base for the next launch on this stream
+    if (lane == 0 && atomicAdd(a.done, 1u) + 1u == (unsigned)total_units)
+    {
+      atomicExch(a.done, 0u);
+      if (a.n_chunks > 1) atomicAdd(a.base_word, (unsigned)a.n_chunks);
     }
     if (!have_nxt) nxt = decode(grab());
     cur = nxt;

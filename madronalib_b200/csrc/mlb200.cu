@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -472,6 +473,62 @@ static int make_block_map(CUtensorMap* map, const float* base, int V, long long 
   return MLB_OK;
 }
 
+// Encoded tensor maps are pure functions of (base, V, planes, plane stride): a graph keeps the few it has
+// built (an audio callback re-uses the same buffers call after call), so a steady-state process call does
+// no driver work besides the launches.
+struct MapKey
+{
+  const void* base;
+  int V;
+  long long n_planes, stride;
+  bool operator==(const MapKey& o) const { return base == o.base && V == o.V && n_planes == o.n_planes && stride == o.stride; }
+};
+struct MapCache
+{
+  static constexpr int kEntries = 40;  // 2 maps x 16 host slices + device-path buffers
+  MapKey key[kEntries];
+  CUtensorMap map[kEntries];
+  int n = 0, next = 0;
+  long long hits = 0, misses = 0;
+};
+static int cached_block_map(MapCache* c, CUtensorMap* out, const float* base, int V, long long n_planes,
+                            long long plane_stride_floats)
+{
+  const MapKey k{base, V, n_planes, plane_stride_floats};
+  for (int i = 0; i < c->n; ++i)
+    if (c->key[i] == k)
+    {
+      *out = c->map[i];
+      ++c->hits;
+      return MLB_OK;
+    }
+  int rc = make_block_map(out, base, V, n_planes, plane_stride_floats);
+  if (rc != MLB_OK) return rc;
+  const int slot = c->n < MapCache::kEntries ? c->n++ : (c->next++ % MapCache::kEntries);
+  c->key[slot] = k;
+  c->map[slot] = *out;
+  ++c->misses;
+  return MLB_OK;
+}
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel and size, not once per launch
+static int ensure_func_smem(const void* fn, size_t smem)
+{
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, size_t>> seen;
+  std::lock_guard<std::mutex> lock(mu);
+  for (auto& e : seen)
+    if (e.first == fn)
+    {
+      if (e.second >= smem) return MLB_OK;
+      CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      e.second = smem;
+      return MLB_OK;
+    }
+  CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  seen.emplace_back(fn, smem);
+  return MLB_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // fused chain registry
 
@@ -590,10 +647,9 @@ struct mlb_graph
   size_t dmem_floats = 0;
   std::vector<unsigned> ring_stride;  // per node, 0 = no ring
 
-  // chain scheduler: [0] unit counter, [1 + g] finished chunks of group g (monotonic)
+  // chain scheduler words, all maintained by the kernels themselves (see ChainArgs)
   unsigned* d_sched = nullptr;
-  unsigned progress_base = 0;
-  int launch_chunks = 1;  // chunks per group of the launch in flight (advances progress_base)
+  int launch_chunks = 1;  // chunks per group of the most recent launch (all slices of one host call agree)
 
   // mix bus partials
   float* d_partial = nullptr;
@@ -609,6 +665,7 @@ struct mlb_graph
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   int last_host_slices = 0;  // voice slices of the most recent mlb_graph_process_host call (1 = one launch)
+  MapCache maps;
   struct mlb_mixbus* bus = nullptr;  // multi-GPU: the mix bus is all-reduced over peer memory inside mix_reduce_kernel
 };
 
@@ -1110,9 +1167,10 @@ extern "C" int mlb_graph_create(const mlb_node* nodes, int n_nodes, const int32_
                         cudaGetErrorString(cudaGetLastError())));
   {
     const size_t n_groups = (V + 31) / 32;
-    if (cudaMalloc(&g->d_sched, (n_groups + 1) * 4) != cudaSuccess)
+    // [0] unit counter, [1 + g] finished chunks of group g, [1 + G] finished units, [2 + G] progress base
+    if (cudaMalloc(&g->d_sched, (n_groups + 3) * 4) != cudaSuccess)
       return cleanup(fail(MLB_ERR_ALLOC, "cudaMalloc of scheduler words failed"));
-    cudaMemset(g->d_sched, 0, (n_groups + 1) * 4);
+    cudaMemset(g->d_sched, 0, (n_groups + 3) * 4);
   }
   cudaMemset(g->d_state, 0, std::max<size_t>(1, lay.n_state_words) * V * 4);
   // state of freshly constructed functors: zeros, except the "idle" markers
@@ -1600,7 +1658,8 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
     const int S = std::min(std::max(env_int("MLB_TEAM_STAGES", 6), 4), 16);
     a.stages = S;
     a.chunk_blocks = T, a.n_chunks = 1;
-    a.sched = g->d_sched, a.progress = g->d_sched + 1 + va / 32, a.progress_base = g->progress_base;
+    a.sched = g->d_sched, a.progress = g->d_sched + 1 + va / 32;
+    a.done = g->d_sched + 1 + groups_total, a.base_word = g->d_sched + 2 + groups_total;
     g->launch_chunks = 1;
     const size_t smem = (size_t)S * kBlockBytes + (size_t)3 * S * 8;
     CUtensorMap in_map, out_map;
@@ -1608,16 +1667,18 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
     memset(&out_map, 0, sizeof(out_map));
     if (e.has_in)
     {
-      rc = make_block_map(&in_map, in_dev + (size_t)va * MLB_BLOCK, Vs, (long long)T * a.n_in_planes,
-                          (long long)V * MLB_BLOCK);
+      rc = cached_block_map(&g->maps, &in_map, in_dev + (size_t)va * MLB_BLOCK, Vs, (long long)T * a.n_in_planes,
+                            (long long)V * MLB_BLOCK);
       if (rc != MLB_OK) return rc;
     }
     if (out_dev)
     {
-      rc = make_block_map(&out_map, out_dev + (size_t)va * MLB_BLOCK, Vs, (long long)T, (long long)V * MLB_BLOCK);
+      rc = cached_block_map(&g->maps, &out_map, out_dev + (size_t)va * MLB_BLOCK, Vs, (long long)T,
+                            (long long)V * MLB_BLOCK);
       if (rc != MLB_OK) return rc;
     }
-    CU_CHECK(cudaFuncSetAttribute((const void*)e.team_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rc = ensure_func_smem((const void*)e.team_fn, smem);
+    if (rc != MLB_OK) return rc;
     e.team_fn<<<n_groups, 64, smem, stream>>>(in_map, out_map, a);
     ++g_launches;
     CU_CHECK(cudaGetLastError());
@@ -1659,9 +1720,9 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
     a.n_chunks = (T + a.chunk_blocks - 1) / a.chunk_blocks;
     a.sched = g->d_sched;
     a.progress = g->d_sched + 1 + va / 32;
-    a.progress_base = g->progress_base;
+    a.done = g->d_sched + 1 + groups_total;
+    a.base_word = g->d_sched + 2 + groups_total;
     g->launch_chunks = a.n_chunks;
-    CU_CHECK(cudaMemsetAsync(g->d_sched, 0, 4, stream));
   }
   const size_t smem = (size_t)W * S * stage_bytes + (size_t)W * S * 8;
   if (smem > g_smem_optin) return fail(MLB_ERR_INVALID, "chain launch needs %zu B shared memory", smem);
@@ -1676,16 +1737,18 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
   memset(&out_map, 0, sizeof(out_map));
   if (e.n_planes > 0)
   {
-    rc = make_block_map(&in_map, in_dev + (size_t)va * MLB_BLOCK, Vs, (long long)T * a.n_in_planes,
-                        (long long)V * MLB_BLOCK);
+    rc = cached_block_map(&g->maps, &in_map, in_dev + (size_t)va * MLB_BLOCK, Vs, (long long)T * a.n_in_planes,
+                          (long long)V * MLB_BLOCK);
     if (rc != MLB_OK) return rc;
   }
   if (out_dev)
   {
-    rc = make_block_map(&out_map, out_dev + (size_t)va * MLB_BLOCK, Vs, (long long)T, (long long)V * MLB_BLOCK);
+    rc = cached_block_map(&g->maps, &out_map, out_dev + (size_t)va * MLB_BLOCK, Vs, (long long)T,
+                          (long long)V * MLB_BLOCK);
     if (rc != MLB_OK) return rc;
   }
-  CU_CHECK(cudaFuncSetAttribute((const void*)e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rc = ensure_func_smem((const void*)e.fn, smem);
+  if (rc != MLB_OK) return rc;
   e.fn<<<n_ctas, W * 32, smem, stream>>>(in_map, out_map, a);
   ++g_launches;
   CU_CHECK(cudaGetLastError());
@@ -1713,12 +1776,18 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
     if (rc != MLB_OK) return rc;
   }
 
-  cudaEventRecord(g->ev0, stream);
+  // the timing events are skipped while `stream` is being captured into a CUDA graph
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(stream, &cap);
+  const bool capturing = (cap != cudaStreamCaptureStatusNone);
+  if (capturing && (g->fdn_node >= 0 || g->has_dmem || (g->bus && g->bus->world > 1)))
+    return fail(MLB_ERR_UNSUPPORTED, "CUDA-graph capture of a process call is supported for graphs without delay "
+                                     "memory and without a mix bus (their call counters are kernel arguments)");
+  if (!capturing) cudaEventRecord(g->ev0, stream);
   if (g->kind == KIND_FUSED)
   {
     rc = launch_chain_slice(g, in_dev, out_dev, mix_dev != nullptr, T, stream, 0, V);
     if (rc != MLB_OK) return rc;
-    if (g->launch_chunks > 1) g->progress_base += (unsigned)g->launch_chunks;
   }
   else if (g->kind == KIND_FDN)
   {
@@ -1785,8 +1854,11 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
     }
     ++g_launches;
   }
-  cudaEventRecord(g->ev1, stream);
-  g->timed = true;
+  if (!capturing)
+  {
+    cudaEventRecord(g->ev1, stream);
+    g->timed = true;
+  }
   CU_CHECK(cudaGetLastError());
   if (g->fdn_node >= 0 || g->has_dmem) g->blocks_done += T;
   if (mix_dev)
@@ -1866,7 +1938,6 @@ extern "C" int mlb_graph_process_host(mlb_graph* g, const float* in_host, float*
     }
     cudaEventRecord(g->ev1, s);
     g->timed = true;
-    if (g->launch_chunks > 1) g->progress_base += (unsigned)g->launch_chunks;
     if (mix_host)
     {
       const int n_groups = (g->V + 31) / 32;

@@ -279,3 +279,43 @@ def test_config5_chain256(gpu, port):
     go, _, gs, name = run_gpu(gpu, w, T, None)
     assert_same_bits(go, po, "chain256 " + name)
     assert_state_equal(gs, ps)
+
+
+@pytest.mark.parametrize("n_voices", [300, 30000])
+def test_process_call_replayed_from_a_cuda_graph(gpu, port, n_voices):
+    """Nothing launch-specific is baked into the kernel arguments (the scheduler words maintain themselves on
+    the device), so a process call captured once into a CUDA graph can be replayed: 4 replays == 4 calls.
+    300 voices = the two-warp team kernel, 30 000 = the persistent grid with state hopping between warps."""
+    import torch
+    T, reps = 8, 4
+    w = wl.config_a(n_voices)
+    inp = w.inputs(T)  # the same planes every replay, state carried
+    st, want = w.state, None
+    outs = []
+    for _ in range(reps):
+        want, _, st = port.run(w.spec, n_voices, T, inp, st, w.coef, nthreads=8)
+        outs.append(want)
+    dev = torch.device("cuda", 0)
+    g = gpu.VoiceGraph(w.spec, n_voices)
+    try:
+        g.set_coefs(w.coef)
+        g.set_state(w.state)
+        d_in = torch.from_numpy(inp).to(dev)
+        d_out = torch.empty((T, 1, n_voices, 64), dtype=torch.float32, device=dev)
+        d_mix = torch.zeros((T, 1, 64), dtype=torch.float32, device=dev)
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            g.process_device(d_in, d_out, d_mix, T, side.cuda_stream)  # first call: allocations, attributes
+            side.synchronize()
+            g.set_state(w.state)
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg, stream=side):
+                g.process_device(d_in, d_out, d_mix, T, side.cuda_stream)
+            g.set_state(w.state)  # capture does not execute
+            for r in range(reps):
+                cg.replay()
+                torch.cuda.synchronize()
+                assert_same_bits(d_out.cpu().numpy(), outs[r], "replay %d" % r)
+        assert_state_equal(g.get_state(), st)
+    finally:
+        g.close()
