@@ -523,10 +523,10 @@ int mlb_mixbus_handle(mlb_mixbus* bus, void* out64);              /* this rank's
 int mlb_mixbus_connect(mlb_mixbus* bus, const void* handles);     /* [world][64], rank order */
 int mlb_mixbus_destroy(mlb_mixbus* bus);
 int mlb_graph_attach_mixbus(mlb_graph* g, mlb_mixbus* bus);       /* NULL detaches */
-/* Asynchronous completion (choose before the first process call, same on every rank): the kernel on the caller's
- * stream only POSTS this rank's sums to the peers; waiting for the peers and adding the rows runs on the bus's
- * own stream while the caller's stream already computes the next call (what an async NCCL all-reduce gives,
- * without NCCL).  `mix` of a mlb_graph_process_device call is then complete only after
+/* Asynchronous exchange (choose before the first process call, same on every rank): the kernel on the caller's
+ * stream only leaves this rank's sums in a local staging block; writing them to the peers, waiting for the peers'
+ * rows and adding them runs in one small kernel on the bus's own stream while the caller's stream already
+ * computes the next call (what an async NCCL all-reduce gives, without NCCL; up to four calls may be in flight).  `mix` of a mlb_graph_process_device call is then complete only after
  * mlb_graph_mix_wait(g, stream) -- which makes `stream` wait for the most recent call's completion -- so use
  * one `mix` buffer per call in flight.  mlb_graph_process_host always returns finished results. */
 int mlb_mixbus_set_async(mlb_mixbus* bus, int on);

@@ -688,10 +688,12 @@ struct MixBusArgs
   unsigned seq;
   int n_floats;   // floats per slot (>= n_planes * 64 of this call)
   int n_planes_cap;  // planes per flag row
-  // async mode: this kernel only POSTS (steps 1-2); mixbus_complete_kernel (side stream) does steps 3-4 while
-  // the next call's chain kernel already runs, then acknowledges on every rank; a post waits for the acks of
-  // the call two before it (the previous user of this parity), which have normally long arrived.
+  // async mode: this kernel only leaves the local sums in `stage` (local memory, nothing on the caller's
+  // stream touches a peer); mixbus_exchange_kernel on the bus's own stream runs steps 1-4 while the next
+  // call's chain kernel already computes, then acknowledges on every rank; a post waits for the acks of the
+  // call two before it (the previous user of this parity), which have normally long arrived.
   int async;
+  float* stage;                  // this call's staging row block [n_floats] (one of four, local)
   unsigned* acks[kMaxBusRanks];  // [r]: rank r's ack words [2][world][n_planes_cap]
 };
 
@@ -742,18 +744,13 @@ __global__ void __launch_bounds__(1024) mix_reduce_kernel(const float* __restric
     return;
   }
   // ---- the sum continues over the GPUs of the box (threads (n, 0): two warps of this CTA) ----
+  if (bus.async)
+  {
+    bus.stage[(size_t)p * MLB_BLOCK + n] = acc;
+    return;
+  }
   const unsigned parity = bus.seq & 1u;
   const size_t slot = ((size_t)parity * bus.world + bus.rank) * bus.n_floats + (size_t)p * MLB_BLOCK + n;
-  if (bus.async && bus.seq > 2u)
-  {
-    // every rank has finished reading this parity's slots of call seq - 2
-    if (n < bus.world)
-    {
-      const unsigned* ack = bus.acks[bus.rank] + ((size_t)parity * bus.world + n) * bus.n_planes_cap + p;
-      while ((int)(ld_acquire_sys_u32(ack) - (bus.seq - 2u)) < 0) __nanosleep(40);
-    }
-    asm volatile("bar.sync 1, 64;" ::: "memory");
-  }
   for (int r = 0; r < bus.world; ++r) bus.xchg[r][slot] = acc;  // 1. my sums into everyone's buffer
   __threadfence_system();
   asm volatile("bar.sync 1, 64;" ::: "memory");  // both warps' stores are fenced before the flags go out
@@ -761,12 +758,10 @@ __global__ void __launch_bounds__(1024) mix_reduce_kernel(const float* __restric
   {
     const size_t f = ((size_t)parity * bus.world + bus.rank) * bus.n_planes_cap + p;
     st_release_sys_u32(bus.flags[n] + f, bus.seq);  // 2. one flag per destination rank
-    if (bus.async) return;
     // 3. wait for rank n's flag in MY memory
     const unsigned* mine = bus.flags[bus.rank] + ((size_t)parity * bus.world + n) * bus.n_planes_cap + p;
     while (ld_acquire_sys_u32(mine) != bus.seq) __nanosleep(40);
   }
-  if (bus.async) return;
   asm volatile("bar.sync 1, 64;" ::: "memory");
   __threadfence_system();
   const float* loc = bus.xchg[bus.rank] + (size_t)parity * bus.world * bus.n_floats + (size_t)p * MLB_BLOCK + n;
@@ -775,21 +770,34 @@ __global__ void __launch_bounds__(1024) mix_reduce_kernel(const float* __restric
   mix[(size_t)p * MLB_BLOCK + n] = sum;
 }
 
-// steps 3-4 of the exchange for the async mode: one 64-thread CTA per plane, launched on a side stream
-__global__ void __launch_bounds__(64) mixbus_complete_kernel(float* __restrict__ mix, const MixBusArgs bus)
+// the whole exchange (steps 1-4) for the async mode: one 64-thread CTA per plane, on the bus's own stream
+__global__ void __launch_bounds__(64) mixbus_exchange_kernel(float* __restrict__ mix, const MixBusArgs bus)
 {
   const int p = blockIdx.x, n = threadIdx.x;
   const unsigned parity = bus.seq & 1u;
+  if (bus.seq > 2u && n < bus.world)
+  {
+    // every rank has finished reading this parity's slots of call seq - 2
+    const unsigned* ack = bus.acks[bus.rank] + ((size_t)parity * bus.world + n) * bus.n_planes_cap + p;
+    while ((int)(ld_acquire_sys_u32(ack) - (bus.seq - 2u)) < 0) __nanosleep(40);
+  }
+  __syncthreads();
+  const float acc = bus.stage[(size_t)p * MLB_BLOCK + n];
+  const size_t slot = ((size_t)parity * bus.world + bus.rank) * bus.n_floats + (size_t)p * MLB_BLOCK + n;
+  for (int r = 0; r < bus.world; ++r) bus.xchg[r][slot] = acc;  // 1.
+  __threadfence_system();
+  __syncthreads();
   if (n < bus.world)
   {
+    st_release_sys_u32(bus.flags[n] + ((size_t)parity * bus.world + bus.rank) * bus.n_planes_cap + p, bus.seq);  // 2.
     const unsigned* mine = bus.flags[bus.rank] + ((size_t)parity * bus.world + n) * bus.n_planes_cap + p;
-    while (ld_acquire_sys_u32(mine) != bus.seq) __nanosleep(40);
+    while (ld_acquire_sys_u32(mine) != bus.seq) __nanosleep(40);  // 3.
   }
   __syncthreads();
   __threadfence_system();
   const float* loc = bus.xchg[bus.rank] + (size_t)parity * bus.world * bus.n_floats + (size_t)p * MLB_BLOCK + n;
   float sum = 0.0f;
-  for (int r = 0; r < bus.world; ++r) sum = __fadd_rn(sum, __ldcv(loc + (size_t)r * bus.n_floats));
+  for (int r = 0; r < bus.world; ++r) sum = __fadd_rn(sum, __ldcv(loc + (size_t)r * bus.n_floats));  // 4.
   mix[(size_t)p * MLB_BLOCK + n] = sum;
   __syncthreads();  // every thread has read its column of every slot
   if (n < bus.world)

@@ -1464,11 +1464,13 @@ struct mlb_mixbus
   unsigned seq = 0;
   int async = 0;                  // completion on a side stream (mlb_mixbus_set_async)
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_posted = nullptr, ev_done = nullptr;
+  static constexpr int kStage = 4;  // calls whose exchange may still be pending on the side stream
+  cudaEvent_t ev_posted = nullptr, ev_done[kStage] = {};
   bool done_pending = false;
   size_t xchg_bytes() const { return (size_t)2 * world * n_floats * 4; }
   size_t flag_bytes() const { return (size_t)2 * world * n_planes_cap * 4; }
-  size_t total_bytes() const { return xchg_bytes() + 2 * flag_bytes(); }  // slots, flags, acks
+  size_t stage_bytes() const { return (size_t)kStage * n_floats * 4; }
+  size_t total_bytes() const { return xchg_bytes() + 2 * flag_bytes() + stage_bytes(); }  // slots, flags, acks, staging
 };
 
 extern "C" int mlb_mixbus_create(int rank, int world, size_t max_floats, mlb_mixbus** out)
@@ -1492,7 +1494,7 @@ extern "C" int mlb_mixbus_create(int rank, int world, size_t max_floats, mlb_mix
   b->connected = (world == 1);
   cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&b->ev_posted, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming);
+  for (cudaEvent_t& e : b->ev_done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   ++g_live_handles;
   *out = b;
   return MLB_OK;
@@ -1528,7 +1530,8 @@ extern "C" int mlb_mixbus_destroy(mlb_mixbus* b)
   cudaFree(b->base);
   if (b->side) cudaStreamDestroy(b->side);
   if (b->ev_posted) cudaEventDestroy(b->ev_posted);
-  if (b->ev_done) cudaEventDestroy(b->ev_done);
+  for (cudaEvent_t e : b->ev_done)
+    if (e) cudaEventDestroy(e);
   delete b;
   --g_live_handles;
   return MLB_OK;
@@ -1545,7 +1548,8 @@ extern "C" int mlb_graph_mix_wait(mlb_graph* g, void* stream)
 {
   if (!g) return fail(MLB_ERR_INVALID, "null graph");
   mlb_mixbus* b = g->bus;
-  if (b && b->async && b->done_pending) CU_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, b->ev_done, 0));
+  if (b && b->async && b->done_pending)
+    CU_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, b->ev_done[b->seq % mlb_mixbus::kStage], 0));
   return MLB_OK;
 }
 extern "C" int mlb_graph_attach_mixbus(mlb_graph* g, mlb_mixbus* b)
@@ -1556,7 +1560,7 @@ extern "C" int mlb_graph_attach_mixbus(mlb_graph* g, mlb_mixbus* b)
   return MLB_OK;
 }
 // kernel arguments of the next call's exchange (advances the call counter)
-static int bus_args(mlb_graph* g, int n_planes, MixBusArgs* a)
+static int bus_args(mlb_graph* g, int n_planes, MixBusArgs* a, cudaStream_t stream)
 {
   memset(a, 0, sizeof(*a));
   a->world = 1;
@@ -1575,19 +1579,26 @@ static int bus_args(mlb_graph* g, int n_planes, MixBusArgs* a)
     a->acks[r] = (unsigned*)((char*)b->peer_base[r] + b->xchg_bytes() + b->flag_bytes());
   }
   a->async = b->async;
+  if (b->async)
+  {
+    // staging block of this call; its previous user (four calls ago) must have been exchanged
+    a->stage = (float*)((char*)b->base + b->xchg_bytes() + 2 * b->flag_bytes()) + (size_t)(a->seq % mlb_mixbus::kStage) * b->n_floats;
+    if (a->seq > (unsigned)mlb_mixbus::kStage)
+      CU_CHECK(cudaStreamWaitEvent(stream, b->ev_done[a->seq % mlb_mixbus::kStage], 0));
+  }
   return MLB_OK;
 }
-// async mode: steps 3-4 on the bus's side stream, ordered after the post on `stream`
+// async mode: the exchange on the bus's side stream, ordered after the local sums on `stream`
 static int bus_complete(mlb_graph* g, const MixBusArgs& ba, int n_planes, float* mix_dev, cudaStream_t stream)
 {
   mlb_mixbus* b = g->bus;
   if (!b || b->world <= 1 || !b->async) return MLB_OK;
   CU_CHECK(cudaEventRecord(b->ev_posted, stream));
   CU_CHECK(cudaStreamWaitEvent(b->side, b->ev_posted, 0));
-  mixbus_complete_kernel<<<n_planes, MLB_BLOCK, 0, b->side>>>(mix_dev, ba);
+  mixbus_exchange_kernel<<<n_planes, MLB_BLOCK, 0, b->side>>>(mix_dev, ba);
   ++g_launches;
   CU_CHECK(cudaGetLastError());
-  CU_CHECK(cudaEventRecord(b->ev_done, b->side));
+  CU_CHECK(cudaEventRecord(b->ev_done[ba.seq % mlb_mixbus::kStage], b->side));
   b->done_pending = true;
   return MLB_OK;
 }
@@ -1865,7 +1876,7 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
   {
     float* scratch = g->d_partial + (size_t)T * std::max(1, n_out) * n_groups * MLB_BLOCK;
     MixBusArgs ba;
-    rc = bus_args(g, T * std::max(1, n_out), &ba);
+    rc = bus_args(g, T * std::max(1, n_out), &ba, stream);
     if (rc != MLB_OK) return rc;
     mix_reduce_kernel<<<T * std::max(1, n_out), dim3(MLB_BLOCK, 16), 0, stream>>>(g->d_partial, scratch,
                                                                                    mix_dev, n_groups, ba);
@@ -1943,7 +1954,7 @@ extern "C" int mlb_graph_process_host(mlb_graph* g, const float* in_host, float*
       const int n_groups = (g->V + 31) / 32;
       float* scratch = g->d_partial + T * std::max<size_t>(1, n_out) * n_groups * MLB_BLOCK;
       MixBusArgs ba;
-      rc = bus_args(g, (int)(T * std::max<size_t>(1, n_out)), &ba);
+      rc = bus_args(g, (int)(T * std::max<size_t>(1, n_out)), &ba, s);
       if (rc != MLB_OK) return rc;
       mix_reduce_kernel<<<(int)(T * std::max<size_t>(1, n_out)), dim3(MLB_BLOCK, 16), 0, s>>>(g->d_partial, scratch,
                                                                                             g->d_mix, n_groups, ba);
