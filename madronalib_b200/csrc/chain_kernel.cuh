@@ -106,6 +106,7 @@ struct ChainArgs
   int st_idx[kMaxChainState];  // SoA word index of each register state slot
   int co_idx[kMaxChainCoef];
   int cv_plane[kMaxChainRows];  // input plane of each coefficient ROW of a LOPASS_V-class filter
+  unsigned long long* prof;     // team kernel, debugging only (MLB_TEAM_PROF=1): cycle counters of CTA 0
 };
 
 // GEN: generator op id or -1 (the chain filters the source directly)
@@ -543,10 +544,12 @@ __global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ 
     };
     if (P::HAS_IN && lane == 0)
       for (int t = 0; t < LA && t < T; ++t) issue_load(t);
+    long long g_wait = 0, g_comp = 0;
     for (int b = 0; b < T; ++b)
     {
       const int s = b % S, use = b / S;
       const uint32_t blk = base + (uint32_t)s * kBlockBytes;
+      const long long c0 = a.prof ? clock64() : 0;
       if (P::HAS_IN)
       {
         if (lane == 0 && b + LA < T) issue_load(b + LA);
@@ -554,6 +557,7 @@ __global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ 
       }
       else if (use > 0)
         mbar_wait(bar_free + 8u * s, (uint32_t)(use - 1) & 1u);
+      const long long c1 = a.prof ? clock64() : 0;
 #pragma unroll 1
       for (int h = 0; h < 2; ++h)
       {
@@ -565,17 +569,19 @@ __global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 8; ++j)
         {
-          float4 y;
-          y.x = P::tick_gen(xin[j].x, st, co);
-          y.y = P::tick_gen(xin[j].y, st, co);
-          y.z = P::tick_gen(xin[j].z, st, co);
-          y.w = P::tick_gen(xin[j].w, st, co);
-          sts128(tile + row_off + (((uint32_t)j << 4) ^ sw), y);
+          xin[j].x = P::tick_gen(xin[j].x, st, co);
+          xin[j].y = P::tick_gen(xin[j].y, st, co);
+          xin[j].z = P::tick_gen(xin[j].z, st, co);
+          xin[j].w = P::tick_gen(xin[j].w, st, co);
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sts128(tile + row_off + (((uint32_t)j << 4) ^ sw), xin[j]);
       }
       __syncwarp();  // every lane's rows are written before lane 0 publishes the block
       if (lane == 0) mbar_arrive(bar_gen + 8u * s);
+      if (a.prof) g_wait += c1 - c0, g_comp += clock64() - c1;
     }
+    if (a.prof && blockIdx.x == 0 && lane == 0) a.prof[0] = (unsigned long long)g_wait, a.prof[1] = (unsigned long long)g_comp;
 #pragma unroll
     for (int i = 0; i < P::NS_GEN; ++i)
       if (live) __stcg(a.state + (size_t)a.st_idx[i] * a.v_stride + v, st[i]);
@@ -591,11 +597,14 @@ __global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ 
     float* mix_row = a.mix_partial
                          ? a.mix_partial + ((size_t)a.out_plane * a.groups_stride + g) * MLB_BLOCK + lane
                          : nullptr;
+    long long f_wait = 0, f_comp = 0, f_tail = 0;
     for (int b = 0; b < T; ++b)
     {
       const int s = b % S, use = b / S;
       const uint32_t blk = base + (uint32_t)s * kBlockBytes;
+      const long long c0 = a.prof ? clock64() : 0;
       mbar_wait(bar_gen + 8u * s, (uint32_t)use & 1u);
+      const long long c1 = a.prof ? clock64() : 0;
 #pragma unroll 1
       for (int h = 0; h < 2; ++h)
       {
@@ -603,21 +612,24 @@ __global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ 
         float4 xin[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) xin[j] = lds128(tile + row_off + (((uint32_t)j << 4) ^ sw));
+        // the 32 samples of the half tile are one straight dependency chain: keep the results in registers and
+        // store them afterwards, so that no store sits between two links of the chain (a store's source
+        // registers stay reserved until it has read them)
 #pragma unroll
         for (int j = 0; j < 8; ++j)
         {
-          float4 y;
-          y.x = P::tick_flt(xin[j].x, st, co);
-          y.y = P::tick_flt(xin[j].y, st, co);
-          y.z = P::tick_flt(xin[j].z, st, co);
-          y.w = P::tick_flt(xin[j].w, st, co);
-          sts128(tile + row_off + (((uint32_t)j << 4) ^ sw), y);
-          if (j == 3 && h == 0 && lane == 0 && b > 0 && a.write_out)
-          {
-            // a quarter block after the previous block's store was issued it has drained its reads
-            bulk_wait_read<0>();
-            mbar_arrive(bar_free + 8u * (uint32_t)((b - 1) % S));
-          }
+          xin[j].x = P::tick_flt(xin[j].x, st, co);
+          xin[j].y = P::tick_flt(xin[j].y, st, co);
+          xin[j].z = P::tick_flt(xin[j].z, st, co);
+          xin[j].w = P::tick_flt(xin[j].w, st, co);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sts128(tile + row_off + (((uint32_t)j << 4) ^ sw), xin[j]);
+        if (h == 0 && lane == 0 && b > 0 && a.write_out)
+        {
+          // half a block after the previous block's store was issued it has drained its reads
+          bulk_wait_read<0>();
+          mbar_arrive(bar_free + 8u * (uint32_t)((b - 1) % S));
         }
         if (a.mix_partial != nullptr)
         {
@@ -637,6 +649,7 @@ __global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ 
         }
       }
       if (a.mix_partial != nullptr) mix_row += mix_block_stride;
+      const long long c2 = a.prof ? clock64() : 0;
       fence_proxy_async();
       __syncwarp();
       if (lane == 0)
@@ -649,7 +662,10 @@ __global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ 
         else
           mbar_arrive(bar_free + 8u * s);  // nothing reads the stage any more
       }
+      if (a.prof) f_wait += c1 - c0, f_comp += c2 - c1, f_tail += clock64() - c2;
     }
+    if (a.prof && blockIdx.x == 0 && lane == 0)
+      a.prof[2] = (unsigned long long)f_wait, a.prof[3] = (unsigned long long)f_comp, a.prof[4] = (unsigned long long)f_tail;
 #pragma unroll
     for (int i = P::NS_GEN; i < P::NS; ++i)
       if (live) __stcg(a.state + (size_t)a.st_idx[i] * a.v_stride + v, st[i]);

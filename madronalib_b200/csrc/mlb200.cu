@@ -1690,9 +1690,22 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
     }
     rc = ensure_func_smem((const void*)e.team_fn, smem);
     if (rc != MLB_OK) return rc;
+    static unsigned long long* d_prof = nullptr;
+    const bool prof = env_int("MLB_TEAM_PROF", 0) != 0;
+    if (prof && !d_prof) cudaMalloc(&d_prof, 64);
+    a.prof = prof ? d_prof : nullptr;
     e.team_fn<<<n_groups, 64, smem, stream>>>(in_map, out_map, a);
     ++g_launches;
     CU_CHECK(cudaGetLastError());
+    if (prof)
+    {
+      unsigned long long h[5];
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+      const double n = (double)T * MLB_BLOCK;
+      fprintf(stderr, "team prof (cycles per sample, CTA 0): G wait %.1f compute %.1f | F wait %.1f compute %.1f tail %.1f\n",
+              h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n);
+    }
     return MLB_OK;
   }
   // Launch shape (DESIGN.md "occupancy").  The grid is persistent: one CTA of W warps per SM,

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_peer_memory_mix_bus_all_reduce(gpu, world):
     if gpu.device_count() < world:
         pytest.skip("needs %d GPUs" % world)

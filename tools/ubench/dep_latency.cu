@@ -64,5 +64,22 @@ int main()
       }
       printf("%d warp(s)/scheduler  %-18s %6.2f cycles per iteration\n", warps, names[m], (double)h / n);
     }
+  // effective SM clock of a short, light kernel: cycles counted by clock64 / CUDA-event time
+  {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    for (int rep = 0; rep < 3; ++rep)
+    {
+      long long h = 0;
+      float ms = 0;
+      cudaEventRecord(e0);
+      k<4><<<148, 128>>>(d, c, 1.f, 0.999f, 1 << 14);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      cudaEventElapsedTime(&ms, e0, e1);
+      cudaMemcpy(&h, c, 8, cudaMemcpyDeviceToHost);
+      printf("light kernel: %lld cycles in %.3f us -> %.0f MHz effective SM clock\n", h, ms * 1e3, (double)h / (ms * 1e3));
+    }
+  }
   return 0;
 }
