@@ -479,9 +479,12 @@ __global__ void __launch_bounds__(kChainMaxWarps * 32)
 // 16-cycle recurrence) are different pipeline stages.  Here every 32-voice group is run by a TEAM
 // of two warps in one 64-thread CTA:
 //   warp G: waits for the TMA load of block t (mbarrier `full`), overwrites the frequency tile with the
-//           generator's output in place, arrives on `gen`;
-//   warp F: waits on `gen`, runs filter(s) + gain in place, sums the mix-bus columns, hands the block to
-//           the TMA store, and arrives on `free` once that store has drained its shared-memory reads.
+//           generator's output in place, arrives on the stage's `gen` NAMED barrier (bar.arrive, 64 threads);
+//   warp F: bar.sync on `gen`, runs filter(s) + gain in place, sums the mix-bus columns, hands the block to
+//           the TMA store, and arrives on the stage's `free` named barrier once that store has drained its
+//           shared-memory reads; G syncs on `free` before it refills the stage.
+// (Named barriers -- ids 1..S for gen, S+1..2S for free -- make every lane a participant of the hand-off at
+// the price of one warp-level instruction; compute-sanitizer racecheck follows them, profiles/.)
 // Both walk a ring of S 8-KB stages; G's lane 0 keeps S-3 loads in flight.  Per sample each warp now
 // has roughly half the dependent instructions, and the two halves overlap: ~2x per group, and a
 // group costs 2 warps so banks up to 2 x 592 warps still fit one wave.
@@ -499,16 +502,10 @@ __global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ 
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();
   const uint32_t bar_full = base + (uint32_t)S * kBlockBytes;
-  const uint32_t bar_gen = bar_full + 8u * (uint32_t)S;
-  const uint32_t bar_free = bar_gen + 8u * (uint32_t)S;
+  const int id_gen = 1, id_free = 1 + S;  // named barrier ids of stage s: id_gen + s, id_free + s (S <= 7)
   if (threadIdx.x == 0)
   {
-    for (int s = 0; s < S; ++s)
-    {
-      mbar_init(bar_full + 8u * s, 1);
-      mbar_init(bar_gen + 8u * s, 1);
-      mbar_init(bar_free + 8u * s, 1);
-    }
+    for (int s = 0; s < S; ++s) mbar_init(bar_full + 8u * s, 1);
     fence_mbar_init();
     if (P::HAS_IN) prefetch_tensormap(&in_map);
     if (a.write_out) prefetch_tensormap(&out_map);
@@ -534,10 +531,9 @@ __global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ 
   if (warp == 0)
   {
     // ---------------- G: TMA loads + generator ----------------
-    auto issue_load = [&](int blk_t)
+    auto issue_load = [&](int blk_t)  // lane 0, after the warp has synced on the stage's `free` barrier
     {
-      const int s = blk_t % S, use = blk_t / S;
-      if (use > 0) mbar_wait(bar_free + 8u * s, (uint32_t)(use - 1) & 1u);  // the store of the previous use drained
+      const int s = blk_t % S;
       mbar_arrive_expect_tx(bar_full + 8u * s, kBlockBytes);
       tma_load_4d(base + (uint32_t)s * kBlockBytes, &in_map, bar_full + 8u * s, 0, v0, 0,
                   blk_t * a.n_in_planes + a.in_plane, kEvictFirst);
@@ -552,11 +548,15 @@ __global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ 
       const long long c0 = a.prof ? clock64() : 0;
       if (P::HAS_IN)
       {
-        if (lane == 0 && b + LA < T) issue_load(b + LA);
+        if (b + LA < T)
+        {
+          if ((b + LA) / S > 0) named_bar_sync(id_free + (b + LA) % S, 64);  // the store of the previous use drained
+          if (lane == 0) issue_load(b + LA);
+        }
         mbar_wait(bar_full + 8u * s, (uint32_t)use & 1u);
       }
       else if (use > 0)
-        mbar_wait(bar_free + 8u * s, (uint32_t)(use - 1) & 1u);
+        named_bar_sync(id_free + s, 64);
       const long long c1 = a.prof ? clock64() : 0;
 #pragma unroll 1
       for (int h = 0; h < 2; ++h)
@@ -577,8 +577,7 @@ __global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 8; ++j) sts128(tile + row_off + (((uint32_t)j << 4) ^ sw), xin[j]);
       }
-      __syncwarp();  // every lane's rows are written before lane 0 publishes the block
-      if (lane == 0) mbar_arrive(bar_gen + 8u * s);
+      named_bar_arrive(id_gen + s, 64);  // the block's rows are written
       if (a.prof) g_wait += c1 - c0, g_comp += clock64() - c1;
     }
     if (a.prof && blockIdx.x == 0 && lane == 0) a.prof[0] = (unsigned long long)g_wait, a.prof[1] = (unsigned long long)g_comp;
@@ -603,7 +602,7 @@ __global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ 
       const int s = b % S, use = b / S;
       const uint32_t blk = base + (uint32_t)s * kBlockBytes;
       const long long c0 = a.prof ? clock64() : 0;
-      mbar_wait(bar_gen + 8u * s, (uint32_t)use & 1u);
+      named_bar_sync(id_gen + s, 64);
       const long long c1 = a.prof ? clock64() : 0;
 #pragma unroll 1
       for (int h = 0; h < 2; ++h)
@@ -625,11 +624,12 @@ __global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ 
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) sts128(tile + row_off + (((uint32_t)j << 4) ^ sw), xin[j]);
-        if (h == 0 && lane == 0 && b > 0 && a.write_out)
+        if (h == 0 && b > 0 && a.write_out)
         {
           // half a block after the previous block's store was issued it has drained its reads
-          bulk_wait_read<0>();
-          mbar_arrive(bar_free + 8u * (uint32_t)((b - 1) % S));
+          if (lane == 0) bulk_wait_read<0>();
+          __syncwarp();
+          named_bar_arrive(id_free + (b - 1) % S, 64);
         }
         if (a.mix_partial != nullptr)
         {
@@ -659,9 +659,8 @@ __global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ 
           tma_store_4d(&out_map, blk, 0, v0, 0, b * a.n_out_planes + a.out_plane);
           bulk_commit();
         }
-        else
-          mbar_arrive(bar_free + 8u * s);  // nothing reads the stage any more
       }
+      if (!a.write_out) named_bar_arrive(id_free + s, 64);  // nothing reads the stage any more
       if (a.prof) f_wait += c1 - c0, f_comp += c2 - c1, f_tail += clock64() - c2;
     }
     if (a.prof && blockIdx.x == 0 && lane == 0)

@@ -1666,13 +1666,13 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
   // only axis left to split.  One 64-thread CTA per group, static assignment, no scheduler words.
   if (e.team_fn && n_groups <= g_sm_count * 4 && env_int("MLB_CHAIN_TEAM", 1) != 0)
   {
-    const int S = std::min(std::max(env_int("MLB_TEAM_STAGES", 6), 4), 16);
+    const int S = std::min(std::max(env_int("MLB_TEAM_STAGES", 6), 4), 7);  // 2 S named barriers + barrier 0 <= 16
     a.stages = S;
     a.chunk_blocks = T, a.n_chunks = 1;
     a.sched = g->d_sched, a.progress = g->d_sched + 1 + va / 32;
     a.done = g->d_sched + 1 + groups_total, a.base_word = g->d_sched + 2 + groups_total;
     g->launch_chunks = 1;
-    const size_t smem = (size_t)S * kBlockBytes + (size_t)3 * S * 8;
+    const size_t smem = (size_t)S * kBlockBytes + (size_t)S * 8;
     CUtensorMap in_map, out_map;
     memset(&in_map, 0, sizeof(in_map));
     memset(&out_map, 0, sizeof(out_map));

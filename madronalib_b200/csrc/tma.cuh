@@ -36,6 +36,17 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
                : "memory");
 }
 
+// named barriers (bar.arrive / bar.sync) for producer -> consumer hand-offs between two warps of a CTA:
+// the producer warp arrives (does not wait), the consumer warp syncs; `threads` = both warps
+__device__ __forceinline__ void named_bar_arrive(int id, int threads)
+{
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads)
+{
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 // plain arrive (release at CTA scope): one pending count of the current phase
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
