@@ -477,32 +477,33 @@ __global__ void __launch_bounds__(kChainMaxWarps * 32)
 // time axis cannot be split, but the CHAIN can: the generator (phase accumulate + waveshape: a long
 // but time-parallel computation, the only recurrence is one integer add) and the filter (a short
 // 16-cycle recurrence) are different pipeline stages.  Here every 32-voice group is run by a TEAM
-// of two warps in one 64-thread CTA:
+// of three warps in one 96-thread CTA (the third, M, takes everything that is not arithmetic of the chain off F):
 //   warp G: waits for the TMA load of block t (mbarrier `full`), overwrites the frequency tile with the
 //           generator's output in place, arrives on the stage's `gen` NAMED barrier (bar.arrive, 64 threads);
-//   warp F: bar.sync on `gen`, runs filter(s) + gain in place, sums the mix-bus columns, hands the block to
-//           the TMA store, and arrives on the stage's `free` named barrier once that store has drained its
-//           shared-memory reads; G syncs on `free` before it refills the stage.
-// (Named barriers -- ids 1..S for gen, S+1..2S for free -- make every lane a participant of the hand-off at
-// the price of one warp-level instruction; compute-sanitizer racecheck follows them, profiles/.)
-// Both walk a ring of S 8-KB stages; G's lane 0 keeps S-3 loads in flight.  Per sample each warp now
-// has roughly half the dependent instructions, and the two halves overlap: ~2x per group, and a
-// group costs 2 warps so banks up to 2 x 592 warps still fit one wave.
+//   warp F: bar.sync on `gen`, runs filter(s) + gain in place, fences for the async proxy, arrives on `flt`;
+//   warp M: bar.sync on `flt`, hands the block to the TMA store, sums the mix-bus columns (reads only), and
+//           arrives on the stage's `free` barrier once the store has drained its shared-memory reads; G syncs
+//           on `free` before it refills the stage.
+// (Named barriers -- ids 1..S gen, S+1..2S flt, 2S+1..3S free, S = 5 -- make every lane a participant of the
+// hand-off at the price of one warp-level instruction; compute-sanitizer racecheck follows them, profiles/.)
+// All walk a ring of S 8-KB stages; G's lane 0 keeps S-3 loads in flight.  Per sample each warp now
+// has roughly half the dependent instructions, and the halves overlap: ~2x per group.
 template <class P>
-__global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ CUtensorMap in_map,
+__global__ void __launch_bounds__(96) chain_team_kernel(const __grid_constant__ CUtensorMap in_map,
                                                         const __grid_constant__ CUtensorMap out_map,
                                                         const ChainArgs a)
 {
   static_assert(P::SPLIT, "team kernel needs a generator and a filter");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;  // 0 = G (load + generator), 1 = F (filter + store)
+  const int warp = threadIdx.x >> 5;  // 0 = G (load + generator), 1 = F (filter), 2 = M (mix bus + store)
   const int S = a.stages;
   const int LA = S - 3;               // loads in flight ahead of the generator
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();
   const uint32_t bar_full = base + (uint32_t)S * kBlockBytes;
-  const int id_gen = 1, id_free = 1 + S;  // named barrier ids of stage s: id_gen + s, id_free + s (S <= 7)
+  // named barrier ids of stage s (3 S <= 15): G -> F, F -> M, M -> G
+  const int id_gen = 1, id_flt = 1 + S, id_free = 1 + 2 * S;
   if (threadIdx.x == 0)
   {
     for (int s = 0; s < S; ++s) mbar_init(bar_full + 8u * s, 1);
@@ -520,6 +521,57 @@ __global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ 
   const uint32_t row_off = (uint32_t)lane * 128u;
   const uint32_t sw = (uint32_t)(lane & 7) << 4;
   const int T = a.T;
+
+  if (warp == 2)
+  {
+    // ---------------- M: mix-bus column sums + TMA store + stage recycling ----------------
+    uint32_t mix_off[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      mix_off[j] = ((((uint32_t)lane >> 2) ^ (uint32_t)j) << 4) + (((uint32_t)lane & 3u) << 2);
+    const size_t mix_block_stride = (size_t)a.n_out_planes * a.groups_stride * MLB_BLOCK;
+    float* mix_row = a.mix_partial
+                         ? a.mix_partial + ((size_t)a.out_plane * a.groups_stride + g) * MLB_BLOCK + lane
+                         : nullptr;
+    for (int b = 0; b < T; ++b)
+    {
+      const int s = b % S;
+      const uint32_t blk = base + (uint32_t)s * kBlockBytes;
+      named_bar_sync(id_flt + s, 64);  // F's rows of the block are written (and fenced for the async proxy)
+      if (lane == 0 && a.write_out)
+      {
+        tma_store_4d(&out_map, blk, 0, v0, 0, b * a.n_out_planes + a.out_plane);
+        bulk_commit();
+      }
+      if (a.mix_partial != nullptr)
+      {
+        // lane n sums sample column n over the 32 voice rows, rows in voice order, from +0 (reads only:
+        // concurrent with the store's reads)
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h)
+        {
+          const uint32_t tile = blk + (uint32_t)h * kTileBytes;
+          float acc = 0.0f;
+          if (full_group)
+          {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) acc = __fadd_rn(acc, lds32(tile + mix_off[r & 7] + (uint32_t)r * 128u));
+          }
+          else
+          {
+            for (int r = 0; r < 32; ++r)
+              if (v0 + r < a.V) acc = __fadd_rn(acc, lds32(tile + mix_off[r & 7] + (uint32_t)r * 128u));
+          }
+          mix_row[h * kTileSamples] = acc;
+        }
+        mix_row += mix_block_stride;
+      }
+      if (lane == 0 && a.write_out) bulk_wait_read<0>();  // the store has drained its shared-memory reads
+      __syncwarp();
+      named_bar_arrive(id_free + s, 64);  // G may refill the stage
+    }
+    return;
+  }
 
   uint32_t st[P::NS > 0 ? P::NS : 1];
   float co[P::NC > 0 ? P::NC : 1];
@@ -587,19 +639,11 @@ __global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ 
   }
   else
   {
-    // ---------------- F: filter(s) + gain + mix bus + TMA store ----------------
-    uint32_t mix_off[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      mix_off[j] = ((((uint32_t)lane >> 2) ^ (uint32_t)j) << 4) + (((uint32_t)lane & 3u) << 2);
-    const size_t mix_block_stride = (size_t)a.n_out_planes * a.groups_stride * MLB_BLOCK;
-    float* mix_row = a.mix_partial
-                         ? a.mix_partial + ((size_t)a.out_plane * a.groups_stride + g) * MLB_BLOCK + lane
-                         : nullptr;
-    long long f_wait = 0, f_comp = 0, f_tail = 0;
+    // ---------------- F: filter(s) + gain, nothing else ----------------
+    long long f_wait = 0, f_comp = 0;
     for (int b = 0; b < T; ++b)
     {
-      const int s = b % S, use = b / S;
+      const int s = b % S;
       const uint32_t blk = base + (uint32_t)s * kBlockBytes;
       const long long c0 = a.prof ? clock64() : 0;
       named_bar_sync(id_gen + s, 64);
@@ -611,9 +655,6 @@ __global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ 
         float4 xin[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) xin[j] = lds128(tile + row_off + (((uint32_t)j << 4) ^ sw));
-        // the 32 samples of the half tile are one straight dependency chain: keep the results in registers and
-        // store them afterwards, so that no store sits between two links of the chain (a store's source
-        // registers stay reserved until it has read them)
 #pragma unroll
         for (int j = 0; j < 8; ++j)
         {
@@ -624,52 +665,16 @@ __global__ void __launch_bounds__(64) chain_team_kernel(const __grid_constant__ 
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) sts128(tile + row_off + (((uint32_t)j << 4) ^ sw), xin[j]);
-        if (h == 0 && b > 0 && a.write_out)
-        {
-          // half a block after the previous block's store was issued it has drained its reads
-          if (lane == 0) bulk_wait_read<0>();
-          __syncwarp();
-          named_bar_arrive(id_free + (b - 1) % S, 64);
-        }
-        if (a.mix_partial != nullptr)
-        {
-          __syncwarp();
-          float acc = 0.0f;
-          if (full_group)
-          {
-#pragma unroll
-            for (int r = 0; r < 32; ++r) acc = __fadd_rn(acc, lds32(tile + mix_off[r & 7] + (uint32_t)r * 128u));
-          }
-          else
-          {
-            for (int r = 0; r < 32; ++r)
-              if (v0 + r < a.V) acc = __fadd_rn(acc, lds32(tile + mix_off[r & 7] + (uint32_t)r * 128u));
-          }
-          mix_row[h * kTileSamples] = acc;
-        }
       }
-      if (a.mix_partial != nullptr) mix_row += mix_block_stride;
-      const long long c2 = a.prof ? clock64() : 0;
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0)
-      {
-        if (a.write_out)
-        {
-          tma_store_4d(&out_map, blk, 0, v0, 0, b * a.n_out_planes + a.out_plane);
-          bulk_commit();
-        }
-      }
-      if (!a.write_out) named_bar_arrive(id_free + s, 64);  // nothing reads the stage any more
-      if (a.prof) f_wait += c1 - c0, f_comp += c2 - c1, f_tail += clock64() - c2;
+      fence_proxy_async();               // this lane's rows are visible to the TMA unit ...
+      named_bar_arrive(id_flt + s, 64);  // ... before M hands the block to it
+      if (a.prof) f_wait += c1 - c0, f_comp += clock64() - c1;
     }
     if (a.prof && blockIdx.x == 0 && lane == 0)
-      a.prof[2] = (unsigned long long)f_wait, a.prof[3] = (unsigned long long)f_comp, a.prof[4] = (unsigned long long)f_tail;
+      a.prof[2] = (unsigned long long)f_wait, a.prof[3] = (unsigned long long)f_comp, a.prof[4] = 0ull;
 #pragma unroll
     for (int i = P::NS_GEN; i < P::NS; ++i)
       if (live) __stcg(a.state + (size_t)a.st_idx[i] * a.v_stride + v, st[i]);
-    if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last bulk stores
-    __syncwarp();
   }
 }
 
@@ -790,11 +795,14 @@ __global__ void __launch_bounds__(64) mixbus_exchange_kernel(float* __restrict__
 {
   const int p = blockIdx.x, n = threadIdx.x;
   const unsigned parity = bus.seq & 1u;
+  // (this kernel runs beside the next call's chain kernel: it polls its own memory with plain volatile loads
+  // at a relaxed pace and fences once after the flag showed up)
   if (bus.seq > 2u && n < bus.world)
   {
     // every rank has finished reading this parity's slots of call seq - 2
-    const unsigned* ack = bus.acks[bus.rank] + ((size_t)parity * bus.world + n) * bus.n_planes_cap + p;
-    while ((int)(ld_acquire_sys_u32(ack) - (bus.seq - 2u)) < 0) __nanosleep(40);
+    const volatile unsigned* ack = bus.acks[bus.rank] + ((size_t)parity * bus.world + n) * bus.n_planes_cap + p;
+    while ((int)(*ack - (bus.seq - 2u)) < 0) __nanosleep(200);
+    __threadfence_system();
   }
   __syncthreads();
   const float acc = bus.stage[(size_t)p * MLB_BLOCK + n];
@@ -805,8 +813,9 @@ __global__ void __launch_bounds__(64) mixbus_exchange_kernel(float* __restrict__
   if (n < bus.world)
   {
     st_release_sys_u32(bus.flags[n] + ((size_t)parity * bus.world + bus.rank) * bus.n_planes_cap + p, bus.seq);  // 2.
-    const unsigned* mine = bus.flags[bus.rank] + ((size_t)parity * bus.world + n) * bus.n_planes_cap + p;
-    while (ld_acquire_sys_u32(mine) != bus.seq) __nanosleep(40);  // 3.
+    const volatile unsigned* mine = bus.flags[bus.rank] + ((size_t)parity * bus.world + n) * bus.n_planes_cap + p;
+    while (*mine != bus.seq) __nanosleep(200);  // 3.
+    __threadfence_system();
   }
   __syncthreads();
   __threadfence_system();

@@ -1664,9 +1664,12 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
   // Small banks: a TEAM of two warps per voice group (generator | filter pipeline, chain_team_kernel):
   // with fewer than ~4 groups per SM a lone warp per group is latency-bound, and the chain is the
   // only axis left to split.  One 64-thread CTA per group, static assignment, no scheduler words.
-  if (e.team_fn && n_groups <= g_sm_count * 4 && env_int("MLB_CHAIN_TEAM", 1) != 0)
+  // Up to 5 teams per SM with 5-stage rings (5 x 41 KB), 6 with 4-stage rings; beyond that one warp per group.
+  const int teams_per_sm = (n_groups + g_sm_count - 1) / g_sm_count;
+  if (e.team_fn && teams_per_sm <= 6 && env_int("MLB_CHAIN_TEAM", 1) != 0)
   {
-    const int S = std::min(std::max(env_int("MLB_TEAM_STAGES", 6), 4), 7);  // 2 S named barriers + barrier 0 <= 16
+    // 3 S named barriers + barrier 0 <= 16  ->  S <= 5
+    const int S = std::min(std::max(env_int("MLB_TEAM_STAGES", teams_per_sm <= 5 ? 5 : 4), 4), 5);
     a.stages = S;
     a.chunk_blocks = T, a.n_chunks = 1;
     a.sched = g->d_sched, a.progress = g->d_sched + 1 + va / 32;
@@ -1694,7 +1697,7 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
     const bool prof = env_int("MLB_TEAM_PROF", 0) != 0;
     if (prof && !d_prof) cudaMalloc(&d_prof, 64);
     a.prof = prof ? d_prof : nullptr;
-    e.team_fn<<<n_groups, 64, smem, stream>>>(in_map, out_map, a);
+    e.team_fn<<<n_groups, 96, smem, stream>>>(in_map, out_map, a);
     ++g_launches;
     CU_CHECK(cudaGetLastError());
     if (prof)
@@ -1703,8 +1706,8 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
       cudaStreamSynchronize(stream);
       cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
       const double n = (double)T * MLB_BLOCK;
-      fprintf(stderr, "team prof (cycles per sample, CTA 0): G wait %.1f compute %.1f | F wait %.1f compute %.1f tail %.1f\n",
-              h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n);
+      fprintf(stderr, "team prof (cycles per sample, CTA 0): G wait %.1f compute %.1f | F wait %.1f compute %.1f\n",
+              h[0] / n, h[1] / n, h[2] / n, h[3] / n);
     }
     return MLB_OK;
   }
@@ -1714,12 +1717,21 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
   // banks simply get one warp per group.
   const size_t budget = (size_t)g_smem_optin - 64;
   const size_t stage_bytes = (size_t)std::max(1, e.n_planes) * kBlockBytes;  // a ring stage holds n_planes blocks
+  const int w_cap = std::min(kChainMaxWarps, (int)(budget / (2 * (stage_bytes + 8))));  // warps whose 2-stage rings fit
+  // Three regimes (n_groups = 32-voice groups of this launch):
+  //   * up to 8 warps per SM cover every group (n_groups <= 8 * SMs): W = ceil(n_groups / SMs) warps per
+  //     CTA, every warp owns ONE group for the whole launch (n_chunks = 1): no state hopping, no progress waits,
+  //     and the spare shared memory deepens each warp's ring.  (Cutting such a launch into time chunks adds no
+  //     parallelism -- a group's chunks are serial anyway -- it only idles the warps beyond n_groups.)
+  //   * more groups: W = 12 (3 per SM sub-partition, 2-stage rings, 197 KB: measured best, profiles/), work
+  //     units = (group, chunk of the launch's blocks) so that SM-to-SM speed differences and the tail stay
+  //     balanced (static one-group-per-warp measured 0.415 ms against 0.361 ms at 2 048 groups, round 1).
   int W, S;
-  if (n_groups <= g_sm_count * 4)
+  const bool one_warp_per_group = n_groups <= g_sm_count * std::min(w_cap, 8);
+  if (one_warp_per_group)
     W = std::max(1, (n_groups + g_sm_count - 1) / g_sm_count);
   else
-    W = 12;  // 3 warps per SM sub-partition, 2-stage rings (197 KB): measured best (profiles/)
-  W = std::min(W, (int)(budget / (2 * (stage_bytes + 8))));  // multi-plane stages: fewer warps fit
+    W = std::min(12, w_cap);
   W = env_int("MLB_CHAIN_WARPS", W);
   W = std::min(std::max(W, 1), kChainMaxWarps);
   S = 2;
@@ -1737,6 +1749,7 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
     const int n_warps_resident = g_sm_count * W;
     int n_chunks = (int)((6LL * n_warps_resident + n_groups - 1) / n_groups);
     n_chunks = std::min(std::max(n_chunks, 1), std::max(1, T / 8));
+    if (one_warp_per_group && n_groups <= n_warps_resident) n_chunks = 1;
     n_chunks = env_int("MLB_CHAIN_CHUNKS", n_chunks);
     if (force_chunks > 0) n_chunks = force_chunks;  // all slices of one call must agree
     n_chunks = std::min(std::max(n_chunks, 1), T);
