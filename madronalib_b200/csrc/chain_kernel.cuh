@@ -790,41 +790,51 @@ __global__ void __launch_bounds__(1024) mix_reduce_kernel(const float* __restric
   mix[(size_t)p * MLB_BLOCK + n] = sum;
 }
 
-// the whole exchange (steps 1-4) for the async mode: one 64-thread CTA per plane, on the bus's own stream
-__global__ void __launch_bounds__(64) mixbus_exchange_kernel(float* __restrict__ mix, const MixBusArgs bus)
+// the whole exchange (steps 1-4) for the async mode, on the bus's own stream: 256-thread CTAs, each 64-thread
+// quarter owns one plane (few CTAs: this kernel runs beside the next call's chain kernel)
+constexpr int kExchangePlanesPerCta = 4;
+__global__ void __launch_bounds__(64 * kExchangePlanesPerCta) mixbus_exchange_kernel(float* __restrict__ mix,
+                                                                                     const MixBusArgs bus, int n_planes)
 {
-  const int p = blockIdx.x, n = threadIdx.x;
+  const int n = threadIdx.x & 63;
+  const int p = blockIdx.x * kExchangePlanesPerCta + (threadIdx.x >> 6);
+  const bool active = p < n_planes;
   const unsigned parity = bus.seq & 1u;
-  // (this kernel runs beside the next call's chain kernel: it polls its own memory with plain volatile loads
-  // at a relaxed pace and fences once after the flag showed up)
-  if (bus.seq > 2u && n < bus.world)
+  // (polls its own memory with plain volatile loads at a relaxed pace and fences once after the flag showed up)
+  if (active && bus.seq > 2u && n < bus.world)
   {
     // every rank has finished reading this parity's slots of call seq - 2
     const volatile unsigned* ack = bus.acks[bus.rank] + ((size_t)parity * bus.world + n) * bus.n_planes_cap + p;
-    while ((int)(*ack - (bus.seq - 2u)) < 0) __nanosleep(200);
+    while ((int)(*ack - (bus.seq - 2u)) < 0) __nanosleep(100);
     __threadfence_system();
   }
   __syncthreads();
-  const float acc = bus.stage[(size_t)p * MLB_BLOCK + n];
   const size_t slot = ((size_t)parity * bus.world + bus.rank) * bus.n_floats + (size_t)p * MLB_BLOCK + n;
-  for (int r = 0; r < bus.world; ++r) bus.xchg[r][slot] = acc;  // 1.
+  if (active)
+  {
+    const float acc = bus.stage[(size_t)p * MLB_BLOCK + n];
+    for (int r = 0; r < bus.world; ++r) bus.xchg[r][slot] = acc;  // 1.
+  }
   __threadfence_system();
   __syncthreads();
-  if (n < bus.world)
+  if (active && n < bus.world)
   {
     st_release_sys_u32(bus.flags[n] + ((size_t)parity * bus.world + bus.rank) * bus.n_planes_cap + p, bus.seq);  // 2.
     const volatile unsigned* mine = bus.flags[bus.rank] + ((size_t)parity * bus.world + n) * bus.n_planes_cap + p;
-    while (*mine != bus.seq) __nanosleep(200);  // 3.
+    while (*mine != bus.seq) __nanosleep(100);  // 3.
     __threadfence_system();
   }
   __syncthreads();
   __threadfence_system();
-  const float* loc = bus.xchg[bus.rank] + (size_t)parity * bus.world * bus.n_floats + (size_t)p * MLB_BLOCK + n;
-  float sum = 0.0f;
-  for (int r = 0; r < bus.world; ++r) sum = __fadd_rn(sum, __ldcv(loc + (size_t)r * bus.n_floats));  // 4.
-  mix[(size_t)p * MLB_BLOCK + n] = sum;
+  if (active)
+  {
+    const float* loc = bus.xchg[bus.rank] + (size_t)parity * bus.world * bus.n_floats + (size_t)p * MLB_BLOCK + n;
+    float sum = 0.0f;
+    for (int r = 0; r < bus.world; ++r) sum = __fadd_rn(sum, __ldcv(loc + (size_t)r * bus.n_floats));  // 4.
+    mix[(size_t)p * MLB_BLOCK + n] = sum;
+  }
   __syncthreads();  // every thread has read its column of every slot
-  if (n < bus.world)
+  if (active && n < bus.world)
     st_release_sys_u32(bus.acks[n] + ((size_t)parity * bus.world + bus.rank) * bus.n_planes_cap + p, bus.seq);
 }
 

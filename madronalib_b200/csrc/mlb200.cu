@@ -1493,6 +1493,13 @@ extern "C" int mlb_mixbus_create(int rank, int world, size_t max_floats, mlb_mix
   b->peer_base[rank] = b->base;
   b->connected = (world == 1);
   cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking);
+  // The exchange kernel runs BESIDE the next call's chain kernel, whose CTAs need the SM configured for the
+  // maximum shared-memory carve-out: a resident CTA that prefers another L1 / shared split keeps the chain CTA
+  // off its SM until it has finished (measured: 16 us per step).  Ask for the same split.
+  cudaFuncSetAttribute((const void*)mixbus_exchange_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                       (int)cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute((const void*)mix_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                       (int)cudaSharedmemCarveoutMaxShared);
   cudaEventCreateWithFlags(&b->ev_posted, cudaEventDisableTiming);
   for (cudaEvent_t& e : b->ev_done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   ++g_live_handles;
@@ -1593,11 +1600,17 @@ static int bus_complete(mlb_graph* g, const MixBusArgs& ba, int n_planes, float*
 {
   mlb_mixbus* b = g->bus;
   if (!b || b->world <= 1 || !b->async) return MLB_OK;
+  static const int dbg = env_int("MLB_BUS_DEBUG", 0);  // timing experiments only: 1 = events but no kernel, 2 = nothing
+  if (dbg == 2) return MLB_OK;
   CU_CHECK(cudaEventRecord(b->ev_posted, stream));
   CU_CHECK(cudaStreamWaitEvent(b->side, b->ev_posted, 0));
-  mixbus_exchange_kernel<<<n_planes, MLB_BLOCK, 0, b->side>>>(mix_dev, ba);
-  ++g_launches;
-  CU_CHECK(cudaGetLastError());
+  if (dbg != 1)
+  {
+    mixbus_exchange_kernel<<<(n_planes + kExchangePlanesPerCta - 1) / kExchangePlanesPerCta,
+                             64 * kExchangePlanesPerCta, 0, b->side>>>(mix_dev, ba, n_planes);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+  }
   CU_CHECK(cudaEventRecord(b->ev_done[ba.seq % mlb_mixbus::kStage], b->side));
   b->done_pending = true;
   return MLB_OK;
