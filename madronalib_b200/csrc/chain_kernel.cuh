@@ -107,6 +107,7 @@ struct ChainArgs
   int co_idx[kMaxChainCoef];
   int cv_plane[kMaxChainRows];  // input plane of each coefficient ROW of a LOPASS_V-class filter
   unsigned long long* prof;     // team kernel, debugging only (MLB_TEAM_PROF=1): cycle counters of CTA 0
+  int n_sms;                    // team kernel: SM count (role rotation between the CTAs that share an SM)
 };
 
 // GEN: generator op id or -1 (the chain filters the source directly)
@@ -489,14 +490,23 @@ __global__ void __launch_bounds__(kChainMaxWarps * 32)
 // All walk a ring of S 8-KB stages; G's lane 0 keeps S-3 loads in flight.  Per sample each warp now
 // has roughly half the dependent instructions, and the halves overlap: ~2x per group.
 template <class P>
-__global__ void __launch_bounds__(96) chain_team_kernel(const __grid_constant__ CUtensorMap in_map,
+__global__ void __launch_bounds__(128) chain_team_kernel(const __grid_constant__ CUtensorMap in_map,
                                                         const __grid_constant__ CUtensorMap out_map,
                                                         const ChainArgs a)
 {
   static_assert(P::SPLIT, "team kernel needs a generator and a filter");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;  // 0 = G (load + generator), 1 = F (filter), 2 = M (mix bus + store)
+  // Which scheduler a warp lands on, and with whom it shares it, decides the pace of the busiest role (F).
+  // Measured (tools/probe_team.py, 64 blocks, kernel ms at 4 096 / 8 192 / 12 288 / 16 384 voices):
+  //   three-warp CTAs, fixed roles               0.078 / 0.097 / --    / 0.100   (the SM hands out warp slots round
+  //                                                                               robin, so odd-sized CTAs rotate by themselves)
+  //   four-warp CTAs, roles rotated by CTA index  0.077 / 0.081 / 0.116 / 0.204   (the fourth warp exits at once)
+  //   three-warp CTAs, roles rotated mod 3        0.077 / 0.113 / 0.133 / 0.156
+  // -> the host launches 128 threads (rotation) up to two teams per SM and 96 threads (fixed roles) above.
+  const bool four = blockDim.x == 128;
+  const int rot = four ? (int)((blockIdx.x + blockIdx.x / (unsigned)a.n_sms) & 3u) : 0;
+  const int warp = four ? (int)(((threadIdx.x >> 5) - rot) & 3) : (int)(threadIdx.x >> 5);  // role: 0 = G, 1 = F, 2 = M
   const int S = a.stages;
   const int LA = S - 3;               // loads in flight ahead of the generator
   const uint32_t base = smem_u32(smem_raw);
@@ -512,6 +522,7 @@ __global__ void __launch_bounds__(96) chain_team_kernel(const __grid_constant__ 
     if (a.write_out) prefetch_tensormap(&out_map);
   }
   __syncthreads();
+  if (warp == 3) return;
 
   const int g = blockIdx.x;
   const int v0 = g * kTileVoices;

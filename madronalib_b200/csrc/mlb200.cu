@@ -433,6 +433,10 @@ extern "C" int mlb_init(int device)
     mlb_impulse_table(table);  // ImpulseGen's windowed sinc, host libm
     CU_CHECK(cudaMemcpyToSymbol(c_impulse_table, table, sizeof(table)));
   }
+  // mix_reduce_kernel runs between two chain kernels that need the maximum shared-memory carve-out: keep the
+  // SMs in that configuration instead of switching the L1 / shared split twice per step
+  cudaFuncSetAttribute((const void*)mix_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                       (int)cudaSharedmemCarveoutMaxShared);
   g_device = device;
   return MLB_OK;
 }
@@ -525,6 +529,9 @@ static int ensure_func_smem(const void* fn, size_t smem)
       return MLB_OK;
     }
   CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // every kernel of this library wants the SM's L1 / shared split at "maximum shared": the rings of several CTAs
+  // (or one 197-KB CTA) per SM set the occupancy, and kernels that follow each other then never make the SM switch
+  CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   seen.emplace_back(fn, smem);
   return MLB_OK;
 }
@@ -1498,8 +1505,6 @@ extern "C" int mlb_mixbus_create(int rank, int world, size_t max_floats, mlb_mix
   // off its SM until it has finished (measured: 16 us per step).  Ask for the same split.
   cudaFuncSetAttribute((const void*)mixbus_exchange_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                        (int)cudaSharedmemCarveoutMaxShared);
-  cudaFuncSetAttribute((const void*)mix_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                       (int)cudaSharedmemCarveoutMaxShared);
   cudaEventCreateWithFlags(&b->ev_posted, cudaEventDisableTiming);
   for (cudaEvent_t& e : b->ev_done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   ++g_live_handles;
@@ -1677,12 +1682,13 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
   // Small banks: a TEAM of two warps per voice group (generator | filter pipeline, chain_team_kernel):
   // with fewer than ~4 groups per SM a lone warp per group is latency-bound, and the chain is the
   // only axis left to split.  One 64-thread CTA per group, static assignment, no scheduler words.
-  // Up to 5 teams per SM with 5-stage rings (5 x 41 KB), 6 with 4-stage rings; beyond that one warp per group.
+  // Up to 4 teams per SM (5-stage rings, 41 KB each); beyond that one warp per group.
+  // (teams at 5 and 6 per SM measured no better than one lone warp per group: 0.204 ms at 20 480 and 24 576 voices)
   const int teams_per_sm = (n_groups + g_sm_count - 1) / g_sm_count;
-  if (e.team_fn && teams_per_sm <= 6 && env_int("MLB_CHAIN_TEAM", 1) != 0)
+  if (e.team_fn && teams_per_sm <= 4 && env_int("MLB_CHAIN_TEAM", 1) != 0)
   {
     // 3 S named barriers + barrier 0 <= 16  ->  S <= 5
-    const int S = std::min(std::max(env_int("MLB_TEAM_STAGES", teams_per_sm <= 5 ? 5 : 4), 4), 5);
+    const int S = std::min(std::max(env_int("MLB_TEAM_STAGES", 5), 4), 5);
     a.stages = S;
     a.chunk_blocks = T, a.n_chunks = 1;
     a.sched = g->d_sched, a.progress = g->d_sched + 1 + va / 32;
@@ -1710,7 +1716,9 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
     const bool prof = env_int("MLB_TEAM_PROF", 0) != 0;
     if (prof && !d_prof) cudaMalloc(&d_prof, 64);
     a.prof = prof ? d_prof : nullptr;
-    e.team_fn<<<n_groups, 96, smem, stream>>>(in_map, out_map, a);
+    a.n_sms = g_sm_count;
+    const int team_threads = teams_per_sm <= 2 ? 128 : 96;  // see chain_team_kernel: role rotation only pays up to 2 teams per SM
+    e.team_fn<<<n_groups, team_threads, smem, stream>>>(in_map, out_map, a);
     ++g_launches;
     CU_CHECK(cudaGetLastError());
     if (prof)
@@ -1719,6 +1727,9 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
       cudaStreamSynchronize(stream);
       cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
       const double n = (double)T * MLB_BLOCK;
+      int occ = -1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e.team_fn, 96, smem);
+      fprintf(stderr, "team launch: %d groups, S = %d, %zu B smem, occupancy %d CTAs/SM\n", n_groups, S, smem, occ);
       fprintf(stderr, "team prof (cycles per sample, CTA 0): G wait %.1f compute %.1f | F wait %.1f compute %.1f\n",
               h[0] / n, h[1] / n, h[2] / n, h[3] / n);
     }

@@ -272,23 +272,28 @@ __global__ void __launch_bounds__(128, 3) voice_bank_kernel(const VoiceArgs a)
       // Fast path: frames 0..63 are each emitted once, in order.  Event k's pre-actions (age reset, glide
       // time) apply as soon as event k-1 is done, its post-actions (new pitch / velocity) before frame ev_d[k].
       int k = 0;
+      // the current event's frame and kind are kept in scalars (cur_d = 1000 when there is none), so that the
+      // 64-iteration frame loop below never indexes the decoded event arrays
+      int cur_d = 1000, cur_kind = 0;
       auto advance = [&]()  // make the next non-ignored event current and apply its pre-actions
       {
         while (k < MLB_VOICE_MAX_EVENTS && ev_kind[k] == 0) ++k;
+        cur_d = 1000, cur_kind = 0;
         if (k < MLB_VOICE_MAX_EVENTS)
         {
+          cur_d = ev_d[k], cur_kind = ev_kind[k];
           const unsigned fl = (flags >> (8 * k)) & 0xFFu;
-          if (ev_kind[k] != 3)
+          if (cur_kind != 3)
           {
             if (fl & MLB_EVF_RESET) r.age = 0;
             r.age_step = 1;
           }
-          if (ev_kind[k] == 1) voice_set_glide_time(r, (fl & MLB_EVF_GLIDE) ? glide_samples : 0.f);
+          if (cur_kind == 1) voice_set_glide_time(r, (fl & MLB_EVF_GLIDE) ? glide_samples : 0.f);
         }
       };
       auto complete = [&]()  // post-actions of the current event, then move on
       {
-        if (ev_kind[k] == 3)
+        if (cur_kind == 3)
           r.vel = 0.f;
         else
           r.pitch = u2f(rec[4 + k]), r.vel = u2f(rec[8 + k]);
@@ -299,8 +304,8 @@ __global__ void __launch_bounds__(128, 3) voice_bank_kernel(const VoiceArgs a)
 #pragma unroll 1
       for (int f = 0; f < MLB_BLOCK; ++f)
       {
-        while (k < MLB_VOICE_MAX_EVENTS && ev_d[k] <= f) complete();
-        const bool retrig_frame = k < MLB_VOICE_MAX_EVENTS && ev_kind[k] == 2 && ev_d[k] - 1 == f;
+        while (cur_d <= f) complete();
+        const bool retrig_frame = cur_kind == 2 && cur_d - 1 == f;
         voice_frame(r, a.sr, f, retrig_frame ? 0.f : r.vel, gate, pitch, tm, want_time);
       }
       while (k < MLB_VOICE_MAX_EVENTS) complete();  // events at frame 64: only their value changes remain
