@@ -24,6 +24,8 @@
 // materialised separately: it is exactly what the next block writes into the ring at its write
 // position, so it is written there directly at the end of the block that produces it.
 #pragma once
+#include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "ops.cuh"
@@ -55,17 +57,18 @@ struct FdnLaunch
 
 constexpr int kFdnRow = 68;                      // floats per delay row: 16-B aligned, = 4 mod 32
 constexpr int kFdnVoice = 8 * kFdnRow + 2 * 64 + 8;  // 8 delay rows + 2 input/x rows (+pad: = 8 mod 32)
-constexpr int kFdnWarpsPerCta = 4;
+constexpr int kFdnMaxWarpsPerCta = 8;  // the host picks 4..8 warps per CTA so that the launch fills whole waves
 
 template <bool EX>
-__global__ void __launch_bounds__(kFdnWarpsPerCta * 32, 4) fdn8_kernel(const FdnLaunch a)
+__global__ void __launch_bounds__(kFdnMaxWarpsPerCta * 32, 2) fdn8_kernel(const FdnLaunch a)
 {
   extern __shared__ __align__(16) float fdn_smem[];
   using ar = A<EX>;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wpc = blockDim.x >> 5;         // warps per CTA (run-time: chosen by the host per bank size)
   const int vq = lane >> 3, k = lane & 7;  // voice within the warp, delay line / sample slot
-  const int v = (blockIdx.x * kFdnWarpsPerCta + warp) * 4 + vq;
-  if ((blockIdx.x * kFdnWarpsPerCta + warp) * 4 >= a.V) return;  // warp-uniform
+  const int v = (blockIdx.x * wpc + warp) * 4 + vq;
+  if ((blockIdx.x * wpc + warp) * 4 >= a.V) return;  // warp-uniform
   const bool live = v < a.V;
 
   float* vbase = fdn_smem + (size_t)(warp * 4 + vq) * kFdnVoice;
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(kFdnWarpsPerCta * 32, 4) fdn8_kernel(const Fdn
   // xbuf[t & 1]; the generator turns it into the x row in place
   const uint32_t s_vbase = smem_u32(vbase), s_drow = s_vbase + (uint32_t)(k * kFdnRow) * 4u;
   const uint32_t s_xbuf0 = s_vbase + (uint32_t)(8 * kFdnRow) * 4u;
-  const uint32_t bars = smem_u32(fdn_smem + (size_t)kFdnWarpsPerCta * 4 * kFdnVoice) + warp * 24u;
+  const uint32_t bars = smem_u32(fdn_smem + (size_t)wpc * 4 * kFdnVoice) + warp * 24u;
   const uint32_t ringbar = bars, xbar0 = bars + 8u;  // xbar[b] = xbar0 + 8 b
 
   if (lane == 0)
@@ -416,22 +419,30 @@ inline int launch_fm3_fdn8(const FdnArgs& f, bool exact, uint32_t* state, const 
   a.state = state, a.coef = coef, a.ring = ring, a.in = in, a.out = out;
   a.ring_len = ring_len, a.blocks_done = blocks_done;
   a.V = V, a.T = T, a.n_in = n_in;
-  const int voices_per_cta = kFdnWarpsPerCta * 4;
-  const int n_ctas = (V + voices_per_cta - 1) / voices_per_cta;
-  const size_t smem = (size_t)kFdnWarpsPerCta * 4 * kFdnVoice * 4 + kFdnWarpsPerCta * 24;
-  cudaError_t e;
+  // Warps per CTA.  Config 4 (16 384 voices = 1 024 four-warp CTAs over 4 x 148 slots) runs 1.73 waves, but fitting
+  // whole waves does not pay: measured at 16 384 voices x 16 blocks (MLB_FDN_WARPS, round 2) 4 warps per CTA
+  // (16 resident warps per SM) 0.255 ms, 5: 0.282, 6: 0.352, 7 (14 resident warps, two even waves): 0.281,
+  // 8: 0.279 -- the kernel is bound by how many ring reads are in flight, i.e. by resident warps, not by the tail.
+  const void* fn = exact ? (const void*)fdn8_kernel<true> : (const void*)fdn8_kernel<false>;
+  const int units = (V + 3) / 4;
+  int best_wpc = 4;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[exact ? 1 : 0])
+  {
+    const size_t smem_max = (size_t)kFdnMaxWarpsPerCta * 4 * kFdnVoice * 4 + kFdnMaxWarpsPerCta * 24;
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess) return MLB_ERR_CUDA;
+    cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    attr_set[exact ? 1 : 0] = true;
+  }
+  const char* force = getenv("MLB_FDN_WARPS");
+  if (force && *force) best_wpc = std::min(std::max(atoi(force), 1), kFdnMaxWarpsPerCta);
+  const int wpc = best_wpc;
+  const int n_ctas = (units + wpc - 1) / wpc;
+  const size_t smem = (size_t)wpc * 4 * kFdnVoice * 4 + (size_t)wpc * 24;
   if (exact)
-  {
-    e = cudaFuncSetAttribute((const void*)fdn8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return MLB_ERR_CUDA;
-    fdn8_kernel<true><<<n_ctas, kFdnWarpsPerCta * 32, smem, stream>>>(a);
-  }
+    fdn8_kernel<true><<<n_ctas, wpc * 32, smem, stream>>>(a);
   else
-  {
-    e = cudaFuncSetAttribute((const void*)fdn8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return MLB_ERR_CUDA;
-    fdn8_kernel<false><<<n_ctas, kFdnWarpsPerCta * 32, smem, stream>>>(a);
-  }
+    fdn8_kernel<false><<<n_ctas, wpc * 32, smem, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? MLB_OK : MLB_ERR_CUDA;
 }
 }  // namespace mlb
