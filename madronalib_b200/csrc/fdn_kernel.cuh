@@ -57,10 +57,10 @@ struct FdnLaunch
 
 constexpr int kFdnRow = 68;                      // floats per delay row: 16-B aligned, = 4 mod 32
 constexpr int kFdnVoice = 8 * kFdnRow + 2 * 64 + 8;  // 8 delay rows + 2 input/x rows (+pad: = 8 mod 32)
-constexpr int kFdnMaxWarpsPerCta = 8;  // the host picks 4..8 warps per CTA so that the launch fills whole waves
+constexpr int kFdnMaxWarpsPerCta = 4;  // warps per CTA (MLB_FDN_WARPS picks fewer for experiments)
 
 template <bool EX>
-__global__ void __launch_bounds__(kFdnMaxWarpsPerCta * 32, 2) fdn8_kernel(const FdnLaunch a)
+__global__ void __launch_bounds__(128, 4) fdn8_kernel(const FdnLaunch a)
 {
   extern __shared__ __align__(16) float fdn_smem[];
   using ar = A<EX>;
@@ -422,7 +422,8 @@ inline int launch_fm3_fdn8(const FdnArgs& f, bool exact, uint32_t* state, const 
   // Warps per CTA.  Config 4 (16 384 voices = 1 024 four-warp CTAs over 4 x 148 slots) runs 1.73 waves, but fitting
   // whole waves does not pay: measured at 16 384 voices x 16 blocks (MLB_FDN_WARPS, round 2) 4 warps per CTA
   // (16 resident warps per SM) 0.255 ms, 5: 0.282, 6: 0.352, 7 (14 resident warps, two even waves): 0.281,
-  // 8: 0.279 -- the kernel is bound by how many ring reads are in flight, i.e. by resident warps, not by the tail.
+  // 8: 0.279 -- nor does a fifth CTA per SM at 96 registers (0.276 ms): the launch shape is not the lever; the
+  // serialised per-lane bulk copies and the ring read that starts only after the previous block's store are.
   const void* fn = exact ? (const void*)fdn8_kernel<true> : (const void*)fdn8_kernel<false>;
   const int units = (V + 3) / 4;
   int best_wpc = 4;
