@@ -328,6 +328,12 @@ class Leg:
                 # so that it overlaps the next step like an async NCCL all-reduce; "peer-sync": all in the kernel
                 self.peer = PeerMixBus(dist, api, self.graph, T * BLOCK, async_completion=(collective == "peer"))
         self.reducer = MixBusReducer(dist if (self.peer is None and self.collective == "nccl") else None)
+        # the reduction of the mix partials (and the multi-GPU exchange behind it) runs on the graph's own stream,
+        # beside the next step's kernel; d_mix is double-buffered and the timed region ends with mix_wait (drain).
+        # Not with NCCL: its all-reduce has to be ordered after the finished local mix on the caller's stream.
+        self.mix_async = bool(use_mix and self.collective != "nccl" and not os.environ.get("MLB_BENCH_SYNC_MIX"))
+        if self.mix_async:
+            self.graph.set_mix_async(True)
         self.steps_done = 0
         self.stream = torch.cuda.current_stream()
 
@@ -347,7 +353,7 @@ class Leg:
 
     def drain(self):
         self.reducer.drain()
-        if self.peer is not None:
+        if self.peer is not None or self.mix_async:
             self.graph.mix_wait(self.stream.cuda_stream)
 
     def timed(self, steps, warmup, sampler=None):
@@ -616,6 +622,8 @@ def run_cuda_arm(args):
                 "voices_per_gpu": leg.V, "voices_total": V if strong else V * world,
                 "blocks_per_step": T, "samples_per_block": BLOCK,
                 "mix_bus": use_mix,
+                "mix_reduce": "asynchronous (own stream, overlaps the next step; joined before the timed region ends)"
+                              if leg.mix_async else "on the step's stream",
                 "parallelism": f"voices x{world} ({mode}), mix-bus all-reduce ({collective})"
                                + (f"; NCCL warmed up by {nccl_warm} untimed collectives before the "
                                   f"{args.warmup} warm-up steps" if world > 1 else ""),

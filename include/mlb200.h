@@ -530,6 +530,11 @@ int mlb_graph_attach_mixbus(mlb_graph* g, mlb_mixbus* bus);       /* NULL detach
  * mlb_graph_mix_wait(g, stream) -- which makes `stream` wait for the most recent call's completion -- so use
  * one `mix` buffer per call in flight.  mlb_graph_process_host always returns finished results. */
 int mlb_mixbus_set_async(mlb_mixbus* bus, int on);
+/* The same for ONE GPU (and in front of the exchange on several): with mix_async on, mlb_graph_process_device leaves only
+ * the chain kernel on the caller's stream; the reduction of the per-group partials into `mix` (mix_reduce_kernel, 3 % of a
+ * config-A step) runs on the graph's own stream beside the next call's kernel, from partials double-buffered by call
+ * parity.  `mix` of a call is complete after mlb_graph_mix_wait(g, stream); use one `mix` buffer per call in flight. */
+int mlb_graph_set_mix_async(mlb_graph* g, int on);
 int mlb_graph_mix_wait(mlb_graph* g, void* stream);
 
 /* Duration in milliseconds of the most recent chain kernel launched by

@@ -105,6 +105,7 @@ def lib() -> ctypes.CDLL:
     L.mlb_graph_attach_mixbus.argtypes = [_vp, _vp]
     L.mlb_mixbus_set_async.argtypes = [_vp, ctypes.c_int]
     L.mlb_graph_mix_wait.argtypes = [_vp, _vp]
+    L.mlb_graph_set_mix_async.argtypes = [_vp, ctypes.c_int]
     L.mlb_map_device.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]
     L.mlb_map_host.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_size_t]
     L.mlb_map_host_allocations.restype = ctypes.c_longlong
@@ -344,6 +345,11 @@ class VoiceGraph:
     def attach_mixbus(self, bus: Optional["MixBus"]) -> None:
         """From now on `mix` is the sum over all ranks of the bus (reduced in-kernel over NVLink)."""
         _check(lib().mlb_graph_attach_mixbus(self._h, bus._h if bus is not None else None))
+
+    def set_mix_async(self, on: bool = True) -> None:
+        """mix_reduce (and the multi-GPU exchange) on the graph's own stream, overlapping the next call; a call's
+        `mix` is complete after mix_wait(stream)."""
+        _check(lib().mlb_graph_set_mix_async(self._h, int(on)))
 
     def mix_wait(self, stream: int = 0) -> None:
         """Make `stream` wait for the most recent call's mix bus (async mix bus only; else a no-op)."""

@@ -673,6 +673,14 @@ struct mlb_graph
   bool timed = false;
   int last_host_slices = 0;  // voice slices of the most recent mlb_graph_process_host call (1 = one launch)
   MapCache maps;
+  // asynchronous mix bus (mlb_graph_set_mix_async): mix_reduce_kernel (and the multi-GPU exchange) run on s_mix,
+  // beside the next call's chain kernel; the per-group partials are double-buffered by call parity
+  int mix_async = 0;
+  cudaStream_t s_mix = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_mixdone[4] = {};
+  unsigned mix_seq = 0;
+  bool mix_pending = false;
+  float* partial_cur = nullptr;  // the partial buffer of the call being issued
   struct mlb_mixbus* bus = nullptr;  // multi-GPU: the mix bus is all-reduced over peer memory inside mix_reduce_kernel
 };
 
@@ -1262,6 +1270,10 @@ extern "C" int mlb_graph_destroy(mlb_graph* g)
     if (g->ev_up[i]) cudaEventDestroy(g->ev_up[i]);
     if (g->ev_k[i]) cudaEventDestroy(g->ev_k[i]);
   }
+  if (g->s_mix) cudaStreamDestroy(g->s_mix);
+  if (g->ev_main) cudaEventDestroy(g->ev_main);
+  for (cudaEvent_t e : g->ev_mixdone)
+    if (e) cudaEventDestroy(e);
   if (g->s_h2d) cudaStreamDestroy(g->s_h2d);
   if (g->s_d2h) cudaStreamDestroy(g->s_d2h);
   if (g->stream) cudaStreamDestroy(g->stream);
@@ -1560,6 +1572,8 @@ extern "C" int mlb_graph_mix_wait(mlb_graph* g, void* stream)
 {
   if (!g) return fail(MLB_ERR_INVALID, "null graph");
   mlb_mixbus* b = g->bus;
+  if (g->mix_async && g->mix_pending)
+    CU_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, g->ev_mixdone[g->mix_seq & 3u], 0));
   if (b && b->async && b->done_pending)
     CU_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, b->ev_done[b->seq % mlb_mixbus::kStage], 0));
   return MLB_OK;
@@ -1642,9 +1656,11 @@ static int ensure_partial(mlb_graph* g, int T, int n_groups)
 {
   // per-group partials followed by the per-chunk scratch of mix_reduce_kernel
   const size_t n_chunks = ((size_t)n_groups + kMixChunkGroups - 1) / kMixChunkGroups;
-  const size_t need = (size_t)T * std::max<size_t>(1, g->outs.size()) * ((size_t)n_groups + n_chunks) * MLB_BLOCK * 4;
+  const size_t one = (size_t)T * std::max<size_t>(1, g->outs.size()) * ((size_t)n_groups + n_chunks) * MLB_BLOCK * 4;
+  const size_t need = one * (g->mix_async ? 2 : 1);  // async: two buffers, alternating by call parity
   if (need > g->partial_cap)
   {
+    if (g->mix_pending) cudaStreamSynchronize(g->s_mix);  // nothing may still read the old buffers
     cudaFree(g->d_partial);
     g->d_partial = nullptr;
     g->partial_cap = 0;
@@ -1652,6 +1668,7 @@ static int ensure_partial(mlb_graph* g, int T, int n_groups)
       return fail(MLB_ERR_ALLOC, "cudaMalloc of %zu B mix partials failed", need);
     g->partial_cap = need;
   }
+  g->partial_cur = g->d_partial;
   return MLB_OK;
 }
 
@@ -1669,7 +1686,7 @@ static int launch_chain_slice(mlb_graph* g, const float* in_dev, float* out_dev,
   ChainArgs a = g->cargs;
   a.state = g->d_state + va;
   a.coef = g->d_coef + va;
-  a.mix_partial = want_mix ? g->d_partial + (size_t)(va / 32) * MLB_BLOCK : nullptr;
+  a.mix_partial = want_mix ? g->partial_cur + (size_t)(va / 32) * MLB_BLOCK : nullptr;
   a.V = Vs;
   a.T = T;
   a.v_stride = V;
@@ -1835,13 +1852,20 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
   {
     rc = ensure_partial(g, T, n_groups);
     if (rc != MLB_OK) return rc;
+    if (g->mix_async)
+    {
+      // this call's partial buffer; its previous user (two calls ago) must have been reduced
+      ++g->mix_seq;
+      g->partial_cur = g->d_partial + (size_t)(g->mix_seq & 1u) * (g->partial_cap / 8);
+      if (g->mix_seq > 2u) CU_CHECK(cudaStreamWaitEvent(stream, g->ev_mixdone[(g->mix_seq - 2u) & 3u], 0));
+    }
   }
 
   // the timing events are skipped while `stream` is being captured into a CUDA graph
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(stream, &cap);
   const bool capturing = (cap != cudaStreamCaptureStatusNone);
-  if (capturing && (g->fdn_node >= 0 || g->has_dmem || (g->bus && g->bus->world > 1)))
+  if (capturing && (g->fdn_node >= 0 || g->has_dmem || (g->bus && g->bus->world > 1) || (g->mix_async && mix_dev)))
     return fail(MLB_ERR_UNSUPPORTED, "CUDA-graph capture of a process call is supported for graphs without delay "
                                      "memory and without a mix bus (their call counters are kernel arguments)");
   if (!capturing) cudaEventRecord(g->ev0, stream);
@@ -1866,7 +1890,7 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
     ++g_launches;
     if (mix_dev)
     {
-      mix_partial_from_planes_kernel<<<dim3(n_groups, T * 2), MLB_BLOCK, 0, stream>>>(planes, g->d_partial, V,
+      mix_partial_from_planes_kernel<<<dim3(n_groups, T * 2), MLB_BLOCK, 0, stream>>>(planes, g->partial_cur, V,
                                                                                       n_groups);
       ++g_launches;
     }
@@ -1881,7 +1905,7 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
     a.coef = g->d_coef;
     a.in = in_dev;
     a.out = out_dev;
-    a.mix_partial = mix_dev ? g->d_partial : nullptr;
+    a.mix_partial = mix_dev ? g->partial_cur : nullptr;
     a.V = V, a.T = T, a.n_in = std::max(1, n_in), a.n_out = std::max(1, n_out);
     a.n_groups = n_groups, a.n_slots = g->n_slots;
     a.fdn_ring = g->d_ring, a.fdn_carry = g->d_carry, a.fdn_ring_len = g->ring_len;
@@ -1924,17 +1948,45 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
   if (g->fdn_node >= 0 || g->has_dmem) g->blocks_done += T;
   if (mix_dev)
   {
-    float* scratch = g->d_partial + (size_t)T * std::max(1, n_out) * n_groups * MLB_BLOCK;
+    // asynchronous mix bus: the reduction leaves the caller's stream here and runs beside the next call's kernel
+    cudaStream_t ms = stream;
+    if (g->mix_async)
+    {
+      CU_CHECK(cudaEventRecord(g->ev_main, stream));
+      CU_CHECK(cudaStreamWaitEvent(g->s_mix, g->ev_main, 0));
+      ms = g->s_mix;
+    }
+    float* scratch = g->partial_cur + (size_t)T * std::max(1, n_out) * n_groups * MLB_BLOCK;
     MixBusArgs ba;
-    rc = bus_args(g, T * std::max(1, n_out), &ba, stream);
+    rc = bus_args(g, T * std::max(1, n_out), &ba, ms);
     if (rc != MLB_OK) return rc;
-    mix_reduce_kernel<<<T * std::max(1, n_out), dim3(MLB_BLOCK, 16), 0, stream>>>(g->d_partial, scratch,
-                                                                                   mix_dev, n_groups, ba);
-    rc = bus_complete(g, ba, T * std::max(1, n_out), mix_dev, stream);
-    if (rc != MLB_OK) return rc;
+    mix_reduce_kernel<<<T * std::max(1, n_out), dim3(MLB_BLOCK, 16), 0, ms>>>(g->partial_cur, scratch, mix_dev,
+                                                                               n_groups, ba);
     ++g_launches;
     CU_CHECK(cudaGetLastError());
+    if (g->mix_async)
+    {
+      CU_CHECK(cudaEventRecord(g->ev_mixdone[g->mix_seq & 3u], ms));
+      g->mix_pending = true;
+    }
+    rc = bus_complete(g, ba, T * std::max(1, n_out), mix_dev, ms);
+    if (rc != MLB_OK) return rc;
   }
+  return MLB_OK;
+}
+
+extern "C" int mlb_graph_set_mix_async(mlb_graph* g, int on)
+{
+  if (!g) return fail(MLB_ERR_INVALID, "null graph");
+  if (g->mix_pending) CU_CHECK(cudaStreamSynchronize(g->s_mix));
+  g->mix_pending = false;
+  if (on && !g->s_mix)
+  {
+    CU_CHECK(cudaStreamCreateWithFlags(&g->s_mix, cudaStreamNonBlocking));
+    CU_CHECK(cudaEventCreateWithFlags(&g->ev_main, cudaEventDisableTiming));
+    for (cudaEvent_t& e : g->ev_mixdone) CU_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  g->mix_async = on ? 1 : 0;
   return MLB_OK;
 }
 
@@ -1970,6 +2022,7 @@ extern "C" int mlb_graph_process_host(mlb_graph* g, const float* in_host, float*
     per = (per + 31) / 32 * 32;
     const size_t pitch = V * MLB_BLOCK * 4;
     if (mix_host && (rc = ensure_partial(g, n_blocks, (g->V + 31) / 32)) != MLB_OK) return rc;
+    if (mix_host && (rc = mlb_graph_mix_wait(g, s)) != MLB_OK) return rc;  // an asynchronous reduce may still read the partials
     int chunks = 0;
     cudaEventRecord(g->ev0, s);
     g->last_host_slices = 0;
@@ -2002,11 +2055,11 @@ extern "C" int mlb_graph_process_host(mlb_graph* g, const float* in_host, float*
     if (mix_host)
     {
       const int n_groups = (g->V + 31) / 32;
-      float* scratch = g->d_partial + T * std::max<size_t>(1, n_out) * n_groups * MLB_BLOCK;
+      float* scratch = g->partial_cur + T * std::max<size_t>(1, n_out) * n_groups * MLB_BLOCK;
       MixBusArgs ba;
       rc = bus_args(g, (int)(T * std::max<size_t>(1, n_out)), &ba, s);
       if (rc != MLB_OK) return rc;
-      mix_reduce_kernel<<<(int)(T * std::max<size_t>(1, n_out)), dim3(MLB_BLOCK, 16), 0, s>>>(g->d_partial, scratch,
+      mix_reduce_kernel<<<(int)(T * std::max<size_t>(1, n_out)), dim3(MLB_BLOCK, 16), 0, s>>>(g->partial_cur, scratch,
                                                                                             g->d_mix, n_groups, ba);
       rc = bus_complete(g, ba, (int)(T * std::max<size_t>(1, n_out)), g->d_mix, s);
       if (rc != MLB_OK) return rc;

@@ -41,6 +41,8 @@ def main():
         g.set_state(shard.state)
         n_out = full.spec.n_out
         bus = parallel.PeerMixBus(dist, api, g, T * n_out * 64, async_completion=use_async)
+        if use_async and V > 30000:
+            g.set_mix_async(True)  # the local reduction on the graph's own stream as well
         d_in = torch.from_numpy(np.ascontiguousarray(inp_full[:, :, v0:v1])).to(dev)
         d_out = torch.empty((T * n_calls, n_out, v1 - v0, 64), dtype=torch.float32, device=dev)
         d_mix = torch.zeros((T * n_calls, n_out, 64), dtype=torch.float32, device=dev)

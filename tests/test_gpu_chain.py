@@ -319,3 +319,36 @@ def test_process_call_replayed_from_a_cuda_graph(gpu, port, n_voices):
         assert_state_equal(g.get_state(), st)
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("n_voices", [700, 30000])
+def test_asynchronous_mix_reduce(gpu, port, n_voices):
+    """mlb_graph_set_mix_async: mix_reduce_kernel leaves the caller's stream (partials double-buffered by call
+    parity); five back-to-back calls with their own mix buffers, joined by mix_wait, equal the checker."""
+    import torch
+    T, calls = 4, 5
+    w = wl.config_a(n_voices)
+    inp = w.inputs(T * calls)
+    po, pm, ps = port.run(w.spec, n_voices, T * calls, inp, w.state, w.coef, want_mix=True, mix_mode=1, nthreads=8)
+    dev = torch.device("cuda", 0)
+    g = gpu.VoiceGraph(w.spec, n_voices)
+    try:
+        g.set_coefs(w.coef)
+        g.set_state(w.state)
+        g.set_mix_async(True)
+        d_in = torch.from_numpy(inp).to(dev)
+        d_out = torch.empty((T * calls, 1, n_voices, 64), dtype=torch.float32, device=dev)
+        d_mix = torch.zeros((T * calls, 1, 64), dtype=torch.float32, device=dev)
+        sh = torch.cuda.current_stream().cuda_stream
+        torch.cuda.synchronize()
+        for c in range(calls):
+            g.process_device(d_in[c * T:(c + 1) * T], d_out[c * T:(c + 1) * T], d_mix[c * T:(c + 1) * T], T, sh)
+        g.mix_wait(sh)
+        torch.cuda.synchronize()
+        assert_same_bits(d_out.cpu().numpy(), po, "out")
+        assert_same_bits(d_mix.cpu().numpy(), pm, "mix (asynchronous reduce)")
+        # the host entry point still returns finished results
+        o, m = g.process_host(np.ascontiguousarray(inp[:T]), T, want_out=False, want_mix=True)
+        assert np.isfinite(m).all()
+    finally:
+        g.close()
