@@ -1960,6 +1960,9 @@ extern "C" int mlb_graph_process_device(mlb_graph* g, const float* in_dev, float
     MixBusArgs ba;
     rc = bus_args(g, T * std::max(1, n_out), &ba, ms);
     if (rc != MLB_OK) return rc;
+    // (asynchronous mode, measured on config A: 1024-thread CTAs do not fit beside a resident chain CTA and run in
+    // the gaps between chain kernels: 0.3820 -> 0.3775 ms per step; 256-thread CTAs that DO run beside it only slow
+    // the HBM-bound chain kernel down by what they read: 0.3803 ms.  The reduction costs bandwidth, not latency.)
     mix_reduce_kernel<<<T * std::max(1, n_out), dim3(MLB_BLOCK, 16), 0, ms>>>(g->partial_cur, scratch, mix_dev,
                                                                                n_groups, ba);
     ++g_launches;

@@ -1,8 +1,3 @@
-(python -m pytest tests/test_gpu_chain.py tests/test_gpu_fullsize.py -x -q -k "fdn or config4 or config_4" 2>&1 | tail -n 2
-python tools/bench_configs.py --only 4 2>&1 | cut -c1-260
-MLB_TEAM_PROF=0 python - <<'PY'
-import sys; sys.path.insert(0,'.')
-from madronalib_b200 import api
-import ctypes
-PY
+(python -m pytest tests/test_gpu_chain.py -x -q -k "asynchronous or mix" 2>&1 | tail -n 2
+python bench.py --steps 50 --warmup 5 --no-variants --no-cpu-baseline > gpurun_out/r2l_bench.json 2> gpurun_out/r2l_bench.err; tail -n 2 gpurun_out/r2l_bench.err
 ) > gpurun_out/r2j_team.txt 2>&1
