@@ -324,14 +324,27 @@ class Leg:
         if dist is not None and use_mix:
             self.collective = collective
             if collective in ("peer", "peer-sync"):
-                # "peer": posting in the step's kernel, completion (wait for peers + sum) on the bus's own stream
-                # so that it overlaps the next step like an async NCCL all-reduce; "peer-sync": all in the kernel
-                self.peer = PeerMixBus(dist, api, self.graph, T * BLOCK, async_completion=(collective == "peer"))
-        self.reducer = MixBusReducer(dist if (self.peer is None and self.collective == "nccl") else None)
+                # "peer": the exchange (write to peers, wait for their rows, sum) on the bus's own stream so that it
+                # overlaps the next step like an async NCCL all-reduce; "peer-sync": all in the step's kernel.
+                # Should CUDA IPC be unavailable on a box, every rank falls back to NCCL together and says so.
+                err = None
+                try:
+                    self.peer = PeerMixBus(dist, api, self.graph, T * BLOCK, async_completion=(collective == "peer"))
+                except Exception as e:  # noqa: BLE001 -- reported in the JSON line, never silent
+                    err = repr(e)
+                flag = self.torch.tensor([0 if err is None else 1], dtype=self.torch.int32, device=dev)
+                dist.all_reduce(flag)
+                if int(flag.item()) != 0:
+                    if self.peer is not None:
+                        self.peer.close()
+                        self.peer = None
+                    self.collective = "nccl (peer-memory mix bus unavailable: %s)" % (err or "failed on another rank")
+        self.reducer = MixBusReducer(dist if (self.peer is None and self.collective.startswith("nccl")) else None)
         # the reduction of the mix partials (and the multi-GPU exchange behind it) runs on the graph's own stream,
         # beside the next step's kernel; d_mix is double-buffered and the timed region ends with mix_wait (drain).
         # Not with NCCL: its all-reduce has to be ordered after the finished local mix on the caller's stream.
-        self.mix_async = bool(use_mix and self.collective != "nccl" and not os.environ.get("MLB_BENCH_SYNC_MIX"))
+        self.mix_async = bool(use_mix and not self.collective.startswith("nccl") and
+                              not os.environ.get("MLB_BENCH_SYNC_MIX"))
         if self.mix_async:
             self.graph.set_mix_async(True)
         self.steps_done = 0
