@@ -176,6 +176,15 @@ class RefOracle(_Oracle):
         f(x.shape[0], _ptr(x), _ptr(omega), _ptr(k), _ptr(out))
         return out
 
+    def kitchen(self, inp: np.ndarray) -> np.ndarray:
+        """tests/cpp/kitchen_body.h compiled against the reference (one instance); inp [T][2][64] -> [T][2][64]."""
+        inp = np.ascontiguousarray(inp, np.float32)
+        out = np.empty_like(inp)
+        self.lib.mlref_kitchen.argtypes = [ctypes.c_int, _vp, _vp]
+        self.lib.mlref_kitchen.restype = None
+        self.lib.mlref_kitchen(inp.shape[0], _ptr(inp), _ptr(out))
+        return out
+
     def upsample2x_clip(self, inp: np.ndarray, drive: float) -> np.ndarray:
         """Upsample2xFunction<1> with fn = clamp(v * drive, -1, 1) for ONE voice; inp [T][64]."""
         inp = np.ascontiguousarray(inp, np.float32)

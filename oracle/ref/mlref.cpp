@@ -1168,6 +1168,36 @@ double mlref_aaltoverb(int T, const float* in, float* out, float sizeU2, float f
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// ---- tests/cpp/kitchen_body.h compiled against the reference itself: the SAME source the tracing layer compiles
+// (tests/cpp/test_trace.cpp), so that "same spelling, same bits" is checked on a body that uses far more functors
+// than the two examples.  One instance; in [T][2][64] (gate, freq rows), out [T][2][64].
+}  // extern "C"
+namespace kitchen_ref
+{
+using namespace ml;
+#include "../../tests/cpp/kitchen_body.h"
+struct Ctx
+{
+  DSPVectorDynamic inputs{2}, outputs{2};
+};
+}  // namespace kitchen_ref
+extern "C"
+{
+void mlref_kitchen(int T, const float* in, float* out)
+{
+  kitchen_ref::KitchenState st;
+  kitchen_ref::kitchenInit(st);
+  kitchen_ref::Ctx ctx;
+  for (int t = 0; t < T; ++t)
+  {
+    ctx.inputs[0] = DSPVector(in + (size_t)t * 128);
+    ctx.inputs[1] = DSPVector(in + (size_t)t * 128 + 64);
+    kitchen_ref::kitchenProcess(&ctx, &st);
+    store(ctx.outputs[0], out + (size_t)t * 128);
+    store(ctx.outputs[1], out + (size_t)t * 128 + 64);
+  }
+}
+
 // ---- Upsample2xFunction<1> (MLDSPFunctional.h:114-160) called as a user would, with the stateless
 // process function fn(v) = clamp(v * drive, -1, 1).  One voice; in/out [T][64].  Checks that the
 // HALFBAND_UP / HALFBAND_UP_2 / HALFBAND_DOWN graph of workloads.functor_case("upsample2x_clip") is

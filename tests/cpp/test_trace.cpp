@@ -176,6 +176,10 @@ void shelfProcess(AudioContext* ctx, void* state)
   ctx->outputs[0] = s->shelf(s->noise() * 0.25f + two.constRow(0) * two.constRow(1), vc);
 }
 
+// ---------------------------------------------------------------- the shared body (also compiled against the reference)
+#include "kitchen_body.h"
+void kitchenProcessFn(AudioContext* ctx, void* state) { kitchenProcess(ctx, state); }
+
 struct Case
 {
   const char* name;
@@ -187,7 +191,7 @@ int main(int argc, char** argv)
 {
   if (argc < 3)
   {
-    std::fprintf(stderr, "usage: test_trace dump|run|stream <sine|reverb|chain|shelf> ...\n");
+    std::fprintf(stderr, "usage: test_trace dump|run|stream <sine|reverb|chain|shelf|kitchen> ...\n");
     return 2;
   }
   const std::string mode = argv[1], which = argv[2];
@@ -199,6 +203,8 @@ int main(int argc, char** argv)
   chain.lp.coeffs = Lopass::makeCoeffs(0.1f, 1.0f);
   ShelfState shelf;
   shelf.noise.setSeed(7);
+  KitchenState kitchen;
+  kitchenInit(kitchen);
 
   size_t nIn = 0, nOut = 0;
   SignalProcessFn fn = nullptr;
@@ -207,6 +213,7 @@ int main(int argc, char** argv)
   if (which == "reverb") nIn = 2, nOut = 2, fn = processVector, state = &verb;  // the example sums inputs[0] + inputs[1]
   if (which == "chain") nIn = 0, nOut = 1, fn = chainProcess, state = &chain;
   if (which == "shelf") nIn = 1, nOut = 1, fn = shelfProcess, state = &shelf;
+  if (which == "kitchen") nIn = 2, nOut = 2, fn = kitchenProcessFn, state = &kitchen;
   if (!fn) return 2;
   try
   {

@@ -116,6 +116,30 @@ def test_shelf_trace_port_equals_reference(ref, port):
     assert np.isfinite(ro).all() and np.abs(ro).max() > 1e-3
 
 
+def kitchen_input(T, V=1):
+    """gate row (amplitude 0.8 while ((n mod 900) < 500), else 0) and a slowly moving frequency row."""
+    n = np.arange(T * 64).reshape(T, 1, 1, 64)
+    gate = (((n % 900) < 500) * np.float32(0.8)).astype(np.float32)
+    freq = (np.float32(220.0 / 48000.0) * (1.0 + 0.1 * np.sin(n * 0.001))).astype(np.float32)
+    x = np.concatenate([gate, freq], axis=1)
+    return np.ascontiguousarray(np.repeat(x, V, axis=2))
+
+
+def test_kitchen_body_same_source_same_bits(ref, port):
+    """tests/cpp/kitchen_body.h -- ONE source file, compiled against the reference (`using namespace ml;`, inside
+    oracle/ref/mlref.cpp) and against the tracing layer (`using namespace mlb::tr;`): every generator, the SVF family,
+    one-poles, ADSR, followers, glides, delays, Allpass<IntegerDelay>, vcoeffs, compound assignment, a carried
+    DSPVector member.  The traced graph evaluated by either checker equals the reference build of the same source."""
+    g, coef, state = traced("kitchen")
+    T = 40
+    x = kitchen_input(T)
+    want = ref.kitchen(x[:, :, 0])
+    for O in (ref, port):
+        out, _, _ = O.run(g, 1, T, x, state, coef)
+        assert_same_bits(out[:, :, 0], want, "kitchen body: traced graph vs the reference build of the same source")
+    assert np.isfinite(want).all() and np.abs(want).max() > 0.05
+
+
 def _run_gpu_case(tmp_path, case, V, T, inp):
     build_exe()
     fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
@@ -127,7 +151,8 @@ def _run_gpu_case(tmp_path, case, V, T, inp):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case,V,T", [("chain", 70, 6), ("sine", 33, 4), ("reverb", 37, 24), ("shelf", 40, 5)])
+@pytest.mark.parametrize("case,V,T", [("chain", 70, 6), ("sine", 33, 4), ("reverb", 37, 24), ("shelf", 40, 5),
+                                      ("kitchen", 35, 20)])
 def test_traced_examples_on_gpu(gpu, port, tmp_path, case, V, T):
     from oracle import bindings
     O = bindings.RefOracle() if bindings.ref_available() else port
@@ -138,6 +163,8 @@ def test_traced_examples_on_gpu(gpu, port, tmp_path, case, V, T):
     if case == "shelf":
         inp = np.ascontiguousarray(np.broadcast_to((0.001 * (1 + np.arange(V, dtype=np.float32)))[None, None, :, None],
                                                    (T, 1, V, 64)))
+    if case == "kitchen":
+        inp = kitchen_input(T, V)
     _run_gpu_case(tmp_path, case, V, T, inp)
     got = np.fromfile(str(tmp_path / "out.bin"), np.float32).reshape(T, g.n_out, V, 64)
     want, _, _ = O.run(g, V, T, inp, state, coef)
@@ -145,6 +172,8 @@ def test_traced_examples_on_gpu(gpu, port, tmp_path, case, V, T):
     if case == "reverb" and bindings.ref_available():
         body, _ = O.aaltoverb(inp[:, :, 0], 1.0, wl.aaltoverb_feedback(0.5, 0.5), 0.1 * 48000)
         assert_same_bits(got[:, :, 5], body, "GPU vs the reverb example's own body")
+    if case == "kitchen" and bindings.ref_available():
+        assert_same_bits(got[:, :, 7], O.kitchen(inp[:, :, 0]), "GPU vs the reference build of kitchen_body.h")
 
 
 @pytest.mark.gpu
