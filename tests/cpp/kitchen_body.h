@@ -98,13 +98,15 @@ inline void kitchenProcess(KITCHEN_CTX* ctx, void* state)
   DSPVector wet = s->ap(s->fdelay(s->idelay(y))) * 0.4f + s->carried * 0.3f;
   s->carried = s->dc(wet);
 
-  // followers, an integrator, some elementwise maths
-  DSPVector level = max(s->peak(y), s->rms(y) * 1.5f);
+  // an integrator and some elementwise maths: output 0 stays free of the envelope followers
   DSPVector shaped = clamp(sin(wet * 2.f) * 0.7f + lerp(y, wet, 0.25f), DSPVector(-1.f), DSPVector(1.f));
   DSPVector slow = s->smooth(abs(shaped)) - s->integ(shaped * 0.001f);
-  shaped *= min(level + 0.1f, DSPVector(1.f));
-  shaped /= sqrt(level * level + 1.f);
+  shaped *= min(abs(wet) + 0.1f, DSPVector(1.f));
+  shaped /= sqrt(wet * wet + 1.f);
 
-  ctx->outputs[0] = shaped;
-  ctx->outputs[1] = slow + exp(level * -2.f) * 0.1f;
+  // followers (Peak and RMS use the CPU's 12-bit rsqrt approximation: tolerance-only on any other hardware)
+  DSPVector level = max(s->peak(y), s->rms(y) * 1.5f);
+
+  ctx->outputs[0] = shaped + slow * 0.5f;
+  ctx->outputs[1] = level + exp(level * -2.f) * 0.1f;
 }

@@ -168,12 +168,17 @@ def test_traced_examples_on_gpu(gpu, port, tmp_path, case, V, T):
     _run_gpu_case(tmp_path, case, V, T, inp)
     got = np.fromfile(str(tmp_path / "out.bin"), np.float32).reshape(T, g.n_out, V, 64)
     want, _, _ = O.run(g, V, T, inp, state, coef)
+    if case == "kitchen":
+        # output 1 is built on Peak / RMS (the CPU's 12-bit rsqrt approximation): tolerance-only off the CPU
+        assert_same_bits(got[:, 0], want[:, 0], "kitchen output 0 traced on the GPU")
+        assert np.abs(got[:, 1] - want[:, 1]).max() <= 2e-3 * np.abs(want[:, 1]).max()
+        if bindings.ref_available():
+            assert_same_bits(got[:, 0, 7], O.kitchen(inp[:, :, 0])[:, 0], "GPU vs the reference build of kitchen_body.h")
+        return
     assert_same_bits(got, want, case + " traced on the GPU")
     if case == "reverb" and bindings.ref_available():
         body, _ = O.aaltoverb(inp[:, :, 0], 1.0, wl.aaltoverb_feedback(0.5, 0.5), 0.1 * 48000)
         assert_same_bits(got[:, :, 5], body, "GPU vs the reverb example's own body")
-    if case == "kitchen" and bindings.ref_available():
-        assert_same_bits(got[:, :, 7], O.kitchen(inp[:, :, 0]), "GPU vs the reference build of kitchen_body.h")
 
 
 @pytest.mark.gpu
