@@ -900,7 +900,10 @@ static int build_generic(mlb_graph* g)
   }
   int S = 1;
   {
-    const int target_warps = g_sm_count * 8;
+    // one warp per scheduler: a second warp on a scheduler halves the pace of both (a lone warp issues every
+    // ~2.4 cycles, profiles/dep_latency_r2.txt), and every extra stage costs a block of pipeline fill.  Measured on
+    // config 5 (32 groups, T = 16): 8 stages 0.930 ms, 16: 0.768, 24: 0.791, 37: 0.852, 48: 0.914, 64: 1.014
+    const int target_warps = g_sm_count * 4;
     S = (target_warps + n_groups - 1) / n_groups;
     S = std::min(S, std::max(1, n_real / 3));
     S = std::min(S, 64);
