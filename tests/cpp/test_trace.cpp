@@ -1,8 +1,10 @@
 // tests/cpp/test_trace.cpp -- the reference's own example process functions, compiled against the tracing
 // layer (include/mlb200_trace.hpp) with ONLY the namespace changed:
-//   examples/audio-and-midi/sine.cpp:16-36    (SineExampleState, sineProcess)
-//   examples/audio-and-midi/reverb.cpp:12-124 (AaltoverbState, initializeReverb, processVector)
-// plus the SURVEY 8c plumbing chain 0.5 * Lopass{0.1, 1.0}(SineGen.clear()(440/48000)) and a swept shelf.
+//   examples/audio-and-midi/sine.cpp:9-36     (constants, SineExampleState, sineProcess)
+//   examples/audio-and-midi/reverb.cpp:12-124 (constants, unityToDecay, AaltoverbState, initializeReverb, processVector)
+// (their text is included from tests/cpp/_ref/*.inc, generated from the reference at build time, not committed),
+// plus the SURVEY 8c plumbing chain 0.5 * Lopass{0.1, 1.0}(SineGen.clear()(440/48000)), a swept shelf, and
+// tests/cpp/kitchen_body.h, which is also compiled against the reference itself.
 //
 //   test_trace dump <case>                      trace only (no GPU needed), print the graph as JSON
 //   test_trace run <case> <instances> <blocks> <in.bin> <out.bin>
@@ -19,133 +21,27 @@
 
 #include "mlb200_trace.hpp"
 
+// ---------------------------------------------------------------- the reference's own example bodies
+// examples/audio-and-midi/sine.cpp and reverb.cpp, everything between `using namespace ml;` and `int main()`,
+// byte for byte: extracted at build time by tests/cpp/make_example_bodies.py into tests/cpp/_ref/ (git-ignored;
+// the reference's text is not part of this repository).  The only change is the namespace they see.
+#if __has_include("_ref/sine_body.inc") && __has_include("_ref/reverb_body.inc")
+#define HAVE_REFERENCE_EXAMPLES 1
+namespace sine_example
+{
 using namespace mlb::tr;  // the reference says: using namespace ml;
-
-// ---------------------------------------------------------------- sine.cpp:9-36
-constexpr int kSampleRate = 48000;
-constexpr float kOutputGain = 0.1f;
-
-struct SineExampleState
+#include "_ref/sine_body.inc"
+}  // namespace sine_example
+namespace reverb_example
 {
-  SineGen s1, s2;
-};
+using namespace mlb::tr;  // the reference says: using namespace ml;
+#include "_ref/reverb_body.inc"
+}  // namespace reverb_example
+#else
+#define HAVE_REFERENCE_EXAMPLES 0
+#endif
 
-void sineProcess(AudioContext* ctx, void* state)
-{
-  auto procState = static_cast<SineExampleState*>(state);
-
-  // Running the sine generators makes DSPVectors as output.
-  // The input parameter is omega: the frequency in Hz divided by the sample rate.
-  // The output sines are multiplied by the gain.
-  ctx->outputs[0] = procState->s1(220.f / kSampleRate) * kOutputGain;
-  ctx->outputs[1] = procState->s2(275.f / kSampleRate) * kOutputGain;
-}
-
-// ---------------------------------------------------------------- reverb.cpp:17-124
-constexpr float kDecayLo = 0.8, kDecayHi = 20;
-Projection unityToDecay(projections::unityToLogParam({kDecayLo, kDecayHi}));
-
-struct AaltoverbState
-{
-  // parameter smoothers
-  LinearGlide mSmoothFeedback;
-  LinearGlide mSmoothDelay;
-
-  // reverb machinery
-  Allpass<PitchbendableDelay> mAp1, mAp2, mAp3, mAp4;
-  Allpass<PitchbendableDelay> mAp5, mAp6, mAp7, mAp8, mAp9, mAp10;
-  PitchbendableDelay mDelayL, mDelayR;
-
-  // feedback storage
-  DSPVector mvFeedbackL, mvFeedbackR;
-};
-
-void initializeReverb(AaltoverbState& r)
-{
-  // set fixed parameters for reverb
-  r.mSmoothFeedback.setGlideTimeInSamples(0.1f * kSampleRate);
-  r.mSmoothDelay.setGlideTimeInSamples(0.1f * kSampleRate);
-
-  // set allpass filter coefficients
-  r.mAp1.mGain = 0.75f;
-  r.mAp2.mGain = 0.70f;
-  r.mAp3.mGain = 0.625f;
-  r.mAp4.mGain = 0.625f;
-  r.mAp5.mGain = r.mAp6.mGain = 0.7f;
-  r.mAp7.mGain = r.mAp8.mGain = 0.6f;
-  r.mAp9.mGain = r.mAp10.mGain = 0.5f;
-
-  // allocate delay memory
-  r.mAp1.setMaxDelayInSamples(500.f);
-  r.mAp2.setMaxDelayInSamples(500.f);
-  r.mAp3.setMaxDelayInSamples(1000.f);
-  r.mAp4.setMaxDelayInSamples(1000.f);
-  r.mAp5.setMaxDelayInSamples(2600.f);
-  r.mAp6.setMaxDelayInSamples(2600.f);
-  r.mAp7.setMaxDelayInSamples(8000.f);
-  r.mAp8.setMaxDelayInSamples(8000.f);
-  r.mAp9.setMaxDelayInSamples(10000.f);
-  r.mAp10.setMaxDelayInSamples(10000.f);
-  r.mDelayL.setMaxDelayInSamples(3500.f);
-  r.mDelayR.setMaxDelayInSamples(3500.f);
-}
-
-void processVector(AudioContext* ctx, void* stateData)
-{
-  AaltoverbState* r = static_cast<AaltoverbState*>(stateData);
-
-  const float sr = kSampleRate;
-  const float RT60const = 0.001f;
-
-  // size and decay parameters from 0-1. It will be more interesting to change these over time in some way.
-  float sizeU = 0.5f;
-  float decayU = 0.5f;
-
-  // generate delay and feedback scalars
-  float decayTime = unityToDecay(decayU);
-  float decayIterations = decayTime / (sizeU * 0.5);
-  float feedback = (decayU < 1.0f) ? powf(RT60const, 1.0f / decayIterations) : 1.0f;
-
-  // generate smoothed delay time and feedback gain vectors
-  DSPVector vSmoothDelay = r->mSmoothDelay(sizeU * 2.0f);
-  DSPVector vSmoothFeedback = r->mSmoothFeedback(feedback);
-
-  // get the minimum possible delay in samples, which is the length of a DSPVector.
-  DSPVector vMin(kFloatsPerDSPVector);
-
-  // get smoothed allpass times in samples
-  DSPVector delayParamInSamples = sr * vSmoothDelay;
-  DSPVector vt1 = max(0.00476 * delayParamInSamples, vMin);
-  DSPVector vt2 = max(0.00358 * delayParamInSamples, vMin);
-  DSPVector vt3 = max(0.00973 * delayParamInSamples, vMin);
-  DSPVector vt4 = max(0.00830 * delayParamInSamples, vMin);
-  DSPVector vt5 = max(0.029 * delayParamInSamples, vMin);
-  DSPVector vt6 = max(0.021 * delayParamInSamples, vMin);
-  DSPVector vt7 = max(0.078 * delayParamInSamples, vMin);
-  DSPVector vt8 = max(0.090 * delayParamInSamples, vMin);
-  DSPVector vt9 = max(0.111 * delayParamInSamples, vMin);
-  DSPVector vt10 = max(0.096 * delayParamInSamples, vMin);
-
-  // sum stereo inputs and diffuse with four allpass filters in series
-  DSPVector monoInput = (ctx->inputs[0] + ctx->inputs[1]);
-  DSPVector diffusedInput = r->mAp4(r->mAp3(r->mAp2(r->mAp1(monoInput, vt1), vt2), vt3), vt4);
-
-  // get delay times in samples, subtracting the constant delay of one DSPVector and clamping to zero
-  DSPVector vDelayTimeL = max(0.0313 * delayParamInSamples - vMin, DSPVector(0.f));
-  DSPVector vDelayTimeR = max(0.0371 * delayParamInSamples - vMin, DSPVector(0.f));
-
-  // sum diffused input with feedback, and apply late diffusion of two more allpass filters to each channel
-  DSPVector vTapL = r->mAp7(r->mAp5(diffusedInput + r->mDelayL(r->mvFeedbackL, vDelayTimeL), vt5), vt7);
-  DSPVector vTapR = r->mAp8(r->mAp6(diffusedInput + r->mDelayR(r->mvFeedbackR, vDelayTimeR), vt6), vt8);
-
-  // apply final allpass filter and gain, and store the feedback
-  r->mvFeedbackR = r->mAp9(vTapL, vt9) * vSmoothFeedback;
-  r->mvFeedbackL = r->mAp10(vTapR, vt10) * vSmoothFeedback;
-
-  // write the stereo outputs
-  ctx->outputs[0] = vTapL;
-  ctx->outputs[1] = vTapR;
-}
+using namespace mlb::tr;
 
 // ---------------------------------------------------------------- SURVEY 8c plumbing chain (config 1)
 struct ChainState
@@ -195,9 +91,11 @@ int main(int argc, char** argv)
     return 2;
   }
   const std::string mode = argv[1], which = argv[2];
-  SineExampleState sine;
-  AaltoverbState verb;
-  initializeReverb(verb);
+#if HAVE_REFERENCE_EXAMPLES
+  sine_example::SineExampleState sine;
+  reverb_example::AaltoverbState verb;
+  reverb_example::initializeReverb(verb);
+#endif
   ChainState chain;
   chain.osc.clear();
   chain.lp.coeffs = Lopass::makeCoeffs(0.1f, 1.0f);
@@ -209,15 +107,23 @@ int main(int argc, char** argv)
   size_t nIn = 0, nOut = 0;
   SignalProcessFn fn = nullptr;
   void* state = nullptr;
-  if (which == "sine") nIn = 0, nOut = 2, fn = sineProcess, state = &sine;
-  if (which == "reverb") nIn = 2, nOut = 2, fn = processVector, state = &verb;  // the example sums inputs[0] + inputs[1]
+#if HAVE_REFERENCE_EXAMPLES
+  if (which == "sine") nIn = 0, nOut = 2, fn = sine_example::sineProcess, state = &sine;
+  if (which == "reverb") nIn = 2, nOut = 2, fn = reverb_example::processVector, state = &verb;  // the example sums inputs[0] + inputs[1]
+#else
+  if (which == "sine" || which == "reverb")
+  {
+    std::printf("reference example bodies not generated (tests/cpp/make_example_bodies.py)\n");
+    return 4;
+  }
+#endif
   if (which == "chain") nIn = 0, nOut = 1, fn = chainProcess, state = &chain;
   if (which == "shelf") nIn = 1, nOut = 1, fn = shelfProcess, state = &shelf;
   if (which == "kitchen") nIn = 2, nOut = 2, fn = kitchenProcessFn, state = &kitchen;
   if (!fn) return 2;
   try
   {
-    AudioContext ctx(nIn, nOut, kSampleRate);
+    AudioContext ctx(nIn, nOut, 48000);
     TracedProcessor proc;
     proc.trace(&ctx, fn, state);
     if (mode == "dump")

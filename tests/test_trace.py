@@ -9,6 +9,7 @@ the reverb must equal the example's own per-vector body run on the compiled refe
 import json
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -27,7 +28,14 @@ def build_exe():
         build.build()
     libdir = os.path.dirname(api.LIB_PATH)
     src = os.path.join(ROOT, "tests", "cpp", "test_trace.cpp")
+    gen = os.path.join(ROOT, "tests", "cpp", "make_example_bodies.py")
+    if os.path.isdir("/root/reference/examples") and not os.path.exists(
+            os.path.join(ROOT, "tests", "cpp", "_ref", "reverb_body.inc")):
+        subprocess.run([sys.executable, gen], check=True)  # the reference's example bodies: generated, never committed
     hdrs = [os.path.join(ROOT, "include", h) for h in ("mlb200_trace.hpp", "mlb200.hpp", "mlb200_host.hpp", "mlb200.h")]
+    hdrs += [os.path.join(ROOT, "tests", "cpp", f) for f in ("kitchen_body.h",)]
+    hdrs += [p for p in (os.path.join(ROOT, "tests", "cpp", "_ref", f) for f in ("sine_body.inc", "reverb_body.inc"))
+             if os.path.exists(p)]
     if os.path.exists(EXE) and all(os.path.getmtime(EXE) > os.path.getmtime(p) for p in [src] + hdrs):
         return
     cmd = ["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), src, "-o", EXE,
@@ -40,6 +48,8 @@ def traced(case: str, n_voices: int = 1):
     """-> (GraphSpec, coef [n_coef][V], state [n_state][V]) of the graph test_trace records for `case`."""
     build_exe()
     r = subprocess.run([EXE, "dump", case], capture_output=True, text=True, timeout=60)
+    if r.returncode == 4:
+        pytest.skip("the reference's example bodies were not generated (tests/cpp/make_example_bodies.py needs /root/reference)")
     assert r.returncode == 0, r.stdout + r.stderr
     d = json.loads(r.stdout)
     g = GraphSpec()
