@@ -296,6 +296,53 @@ def parity_check(w, sel, n_steps, T, inp_sel, got_rows, got_state):
             "checker": kind}
 
 
+def contract_e_legs(torch, api, wl, w, V, T, args, n_e2e, h_out, h_mix, vs_per_step):
+    """Contract E through mlb_synth_process_host (pinned event records in), with a bit-compare of 64 sampled
+    voices against the CPU checker (port bank -> port / reference graph) outside the timed regions."""
+    res = {}
+    prm = wl.synth_bank_params(V)
+    ev_np = wl.synth_events(V, T)
+    h_ev = torch.empty(ev_np.nbytes, dtype=torch.uint8).pin_memory()
+    h_ev.numpy()[:] = ev_np.view(np.uint8).reshape(-1)
+    ev = h_ev.numpy().view(ev_np.dtype).reshape(T, V)
+    bank = api.VoiceBank(48000.0, *prm)
+    g = api.VoiceGraph(w.spec, V, api.FLAG_FAST if args.fast else api.FLAG_EXACT)
+    try:
+        g.set_coefs(w.coef)
+        g.set_state(w.state)
+        calls = 0
+        for name, want_out in (("contract_E", True), ("contract_E_mix", False)):
+            o = h_out.numpy() if want_out else None
+            g.process_events_host(bank, ev, want_out=want_out, want_mix=True, out=o, mix=h_mix)
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                g.process_events_host(bank, ev, want_out=want_out, want_mix=True, out=o, mix=h_mix)
+            dt = time.perf_counter() - t0
+            calls += 1 + n_e2e
+            res[name] = {"value": vs_per_step * n_e2e / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / n_e2e,
+                         "h2d_bytes_per_step": int(ev.nbytes),
+                         "d2h_bytes_per_step": int((h_out.numel() * 4 if want_out else 0) + h_mix.nbytes),
+                         "time_chunks": g.last_host_slices,
+                         "kernels": "voice_bank_kernel (kPitch row) -> " + g.kernel_name,
+                         "path": "mlb_synth_process_host (pinned event records; rows stay in HBM)"}
+            if want_out and not args.no_parity:
+                from oracle import bindings
+                sel = np.linspace(0, V - 1, 64).astype(np.int64)
+                rows, _ = bindings.port_voice_bank().run(48000.0, *(p_[sel] for p_ in prm),
+                                                         np.ascontiguousarray(np.tile(ev[:, sel], (calls, 1))))
+                O = bindings.RefOracle() if bindings.ref_available() else bindings.PortOracle()
+                want, _, _ = O.run(w.spec, len(sel), T * calls, np.ascontiguousarray(rows[:, 0:1]),
+                                   np.ascontiguousarray(w.state[:, sel]), np.ascontiguousarray(w.coef[:, sel]))
+                a = np.ascontiguousarray(h_out.numpy()[:, 0][:, sel]).view(np.uint32)
+                b = want[T * (calls - 1):, 0].view(np.uint32)
+                res[name]["parity"] = {"rows": int(len(sel)), "blocks": int(T), "steps_replayed": int(calls),
+                                       "mismatches": int(np.any(a != b, axis=(0, 2)).sum())}
+    finally:
+        g.close()
+        bank.close()
+    return res
+
+
 class Leg:
     """One bank on this rank (weak: the whole 65 536-voice bank; strong: this rank's V/G shard)."""
 
@@ -580,6 +627,14 @@ def run_cuda_arm(args):
                               "d2h_bytes_per_step": int((h_out.numel() * 4 if want_out else 0) + h_mix.nbytes),
                               "kernel": graph_s.kernel_name}
         graph_s.close()
+        # E = event records in (72 B per voice and vector; EventsToSignals::processVector on the device,
+        #     MLEventsToSignals.cpp:383-470), the kPitch row feeding the SAME fused chain as its frequency row
+        #     without leaving HBM, per-voice rows (+ mix bus) out;  E_mix = events in, mix bus out only
+        #     (Synth::processVector, MLSynth.h:36-60).  mlb_synth_process_host, time-chunked on three streams.
+        try:
+            variants.update(contract_e_legs(torch, api, wl, w, V, T, args, n_e2e, h_out, h_mix, vs_per_step))
+        except Exception as ex:  # a reported side leg: its failure must not lose the graded line
+            variants["contract_E"] = {"error": repr(ex)}
     del h_out
 
     # ---- the other scaling mode of SURVEY 8(d) beside the headline one (N > 1 only): weak = every GPU
@@ -658,7 +713,7 @@ def run_cuda_arm(args):
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     bad = 0
-    for p_ in (par, other["parity"] if other else None):
+    for p_ in (par, other["parity"] if other else None, variants.get("contract_E", {}).get("parity")):
         if p_ is not None:
             bad += p_.get("mismatches_all_ranks", p_["mismatches"])
     if bad:

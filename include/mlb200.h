@@ -546,6 +546,21 @@ int mlb_graph_last_kernel_ms(mlb_graph* g, float* ms);
  * are sliced when the PCIe traffic of the call reaches MLB_HOST_SLICE_MIN_MB (env, default 32) MiB. */
 int mlb_graph_last_host_slices(const mlb_graph* g);
 
+
+/* Events -> signals -> chain in one call, host buffers, only the event records going up ("contract E"):
+ * what a synth built on the reference does per top-level buffer -- EventsToSignals::processVector
+ * (MLEventsToSignals.cpp:383-470), then Synth::processVector's loop of processVoice calls reading the
+ * voice.outputs rows and accumulating into the outputs (MLSynth.h:36-60,67-71) -- for all voices of the
+ * bank.  The graph's INPUT plane r is Voice row r (kPitch = 0, kGate = 1, ... MLEventsToSignals.h:14-26);
+ * the bank generates exactly the rows the graph reads, on the device, into the graph's input buffer.
+ * events_host [n_blocks][V] (72 B per voice and vector instead of 256 B per input row); out_host
+ * [n_blocks][n_out][V][64] or NULL; mix_host [n_blocks][n_out][64] or NULL.  Pipelined over time chunks
+ * (MLB_SYNTH_CHUNK_BLOCKS, env; default: rows of a chunk <= 1 GiB) on three streams; returns when the host
+ * buffers are complete; mlb_graph_last_host_slices() then reports the number of chunks.
+ * MLB_ERR_INVALID when the bank and the graph differ in voice count or the graph reads no Voice row. */
+int mlb_synth_process_host(mlb_voices* vb, mlb_graph* g, const mlb_voice_events* events_host,
+                           float* out_host, float* mix_host, int n_blocks);
+
 #ifdef __cplusplus
 }
 #endif

@@ -560,6 +560,7 @@ class DeviceBank
 
   int rows() const { return rows_; }
   const char* kernelName() const { return mlb_graph_kernel_name(g_); }
+  mlb_graph* handle() const { return g_; }
 
   // like assigning `bank[row].coeffs = T::makeCoeffs(...)` in the reference
   void setCoeffs(int node, int row, const float* c, int n)
@@ -611,6 +612,7 @@ class VoiceBank
   VoiceBank(const VoiceBank&) = delete;
   VoiceBank& operator=(const VoiceBank&) = delete;
   int voices() const { return n_; }
+  mlb_voices* handle() const { return vb_; }
   void setMainVoices(const int32_t* mainVoice) { check(mlb_voices_set_main_voices(vb_, mainVoice)); }
   // events [nBlocks][voices]; out [nBlocks][MLB_VOICE_ROWS][voices][64]
   void process(const mlb_voice_events* events, float* out, int nBlocks, unsigned rowMask = 0xFFu)
@@ -618,6 +620,16 @@ class VoiceBank
     check(mlb_voices_process_host(vb_, events, out, nBlocks, rowMask));
   }
 };
+
+// Events -> signals -> voice DSP in one call (mlb_synth_process_host): what EventsToSignals::processVector
+// followed by Synth::processVector does per vector (MLEventsToSignals.cpp:383-470, MLSynth.h:36-60), for
+// nBlocks vectors of the whole bank.  The graph's input(r) is Voice row r (kPitch = 0, kGate = 1, ...);
+// events [nBlocks][rows]; out [nBlocks][n_out][rows][64] or null; mix [nBlocks][n_out][64] or null.
+inline void processEvents(VoiceBank& voices, DeviceBank& bank, const mlb_voice_events* events, float* out, float* mix,
+                          int nBlocks)
+{
+  check(mlb_synth_process_host(voices.handle(), bank.handle(), events, out, mix, nBlocks));
+}
 
 // ---- Resampler: Upsampler(octaves) / Downsampler(octaves) x V on the GPU (mlb_resampler_*) ----
 class Resampler

@@ -95,6 +95,7 @@ def lib() -> ctypes.CDLL:
     L.mlb_voices_process_host.argtypes = [_vp, _vp, _vp, ctypes.c_int, ctypes.c_uint]
     L.mlb_voices_process_device.argtypes = [_vp, _vp, _vp, ctypes.c_int, ctypes.c_uint, _vp]
     L.mlb_graph_process_device.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, _vp]
+    L.mlb_synth_process_host.argtypes = [_vp, _vp, _vp, _vp, _vp, ctypes.c_int]
     L.mlb_graph_process_host.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int]
     L.mlb_graph_last_kernel_ms.argtypes = [_vp, _vp]
     L.mlb_graph_last_host_slices.argtypes = [_vp]
@@ -329,6 +330,30 @@ class VoiceGraph:
                                       a.flags["C_CONTIGUOUS"] and a.shape == shape):
                 raise ValueError(f"process_host: `{name}` must be a C-contiguous float32 array of shape {shape}")
         _check(lib().mlb_graph_process_host(self._h, _ptr(inp) if s.n_in else None,
+                                            _ptr(out) if want_out else None,
+                                            _ptr(mix) if want_mix else None, T))
+        return out, mix
+
+    def process_events_host(self, bank: "VoiceBank", events: np.ndarray, want_out: bool = True,
+                            want_mix: bool = False, out: Optional[np.ndarray] = None,
+                            mix: Optional[np.ndarray] = None):
+        """Contract E (mlb_synth_process_host): event records [T][V] in, the graph's rows / mix bus out.
+        The graph's INPUT plane r is Voice row r of ``bank``; the rows never leave the device."""
+        s, V = self.spec, self.n_voices
+        if not (isinstance(events, np.ndarray) and events.ndim == 2 and events.shape[1] == V and
+                events.dtype.itemsize == 72 and events.flags["C_CONTIGUOUS"]):
+            raise ValueError("process_events_host: `events` must be a C-contiguous [T][V] array of 72-byte records")
+        T = int(events.shape[0])
+        if want_out and out is None:
+            out = np.empty((T, s.n_out, V, BLOCK), np.float32)
+        if want_mix and mix is None:
+            mix = np.empty((T, s.n_out, BLOCK), np.float32)
+        for name, a, shape in (("out", out if want_out else None, (T, s.n_out, V, BLOCK)),
+                               ("mix", mix if want_mix else None, (T, s.n_out, BLOCK))):
+            if a is not None and not (isinstance(a, np.ndarray) and a.dtype == np.float32 and
+                                      a.flags["C_CONTIGUOUS"] and a.shape == shape):
+                raise ValueError(f"process_events_host: `{name}` must be a C-contiguous float32 array of shape {shape}")
+        _check(lib().mlb_synth_process_host(bank._h, self._h, events.ctypes.data,
                                             _ptr(out) if want_out else None,
                                             _ptr(mix) if want_mix else None, T))
         return out, mix

@@ -2319,10 +2319,17 @@ extern "C" int mlb_voices_process_device(mlb_voices* vb, const mlb_voice_events*
   a.gl_per = vb->gl_per, a.gl_dy = vb->gl_dy, a.dr_per = vb->dr_per, a.dr_dy = vb->dr_dy;
   a.pc_per = vb->pc_per, a.pc_dy = vb->pc_dy;
   a.midi = (vb->flags & MLB_VOICES_MIDI) ? 1 : 0;
-  // 4 warps x {gate, pitch (, elapsed time)} row tiles
-  const size_t smem = (size_t)4 * ((row_mask & 128u) ? 3 : 2) * kVoiceTileFloats * sizeof(float);
-  CU_CHECK(cudaFuncSetAttribute((const void*)voice_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  voice_bank_kernel<<<(vb->V + 127) / 128, 128, smem, (cudaStream_t)stream>>>(a);
+  // warps x {gate, pitch (, elapsed time)} 8 KB row tiles; 7 warps per CTA and two CTAs per SM put the
+  // 2 048 warps of a 65 536-voice bank on the 148 SMs in one wave (voice_kernel.cuh)
+  const int wpc = env_int("MLB_VOICE_WARPS", (row_mask & 128u) ? kVoiceWarpsPerCtaTime : kVoiceWarpsPerCta);
+  if (wpc < 1 || wpc > kVoiceWarpsPerCta) return fail(MLB_ERR_INVALID, "MLB_VOICE_WARPS must be in [1, %d]", kVoiceWarpsPerCta);
+  const size_t smem = (size_t)wpc * ((row_mask & 128u) ? 3 : 2) * kVoiceTileFloats * sizeof(float);
+  {
+    int rc = ensure_func_smem((const void*)voice_bank_kernel, smem);
+    if (rc != MLB_OK) return rc;
+  }
+  const int n_warps = (vb->V + 31) / 32;
+  voice_bank_kernel<<<(n_warps + wpc - 1) / wpc, 32 * wpc, smem, (cudaStream_t)stream>>>(a);
   ++g_launches;
   CU_CHECK(cudaGetLastError());
   if (vb->d_main && (a.row_mask & 0x79u))  // MPE: add the main voices' pitch / z / x / y / mod rows
@@ -2367,6 +2374,91 @@ extern "C" int mlb_voices_process_host(mlb_voices* vb, const mlb_voice_events* e
   return MLB_OK;
 }
 
+
+// Events -> signals -> chain with nothing but the event records crossing PCIe ("contract E"):
+// the Voice bank writes the rows the graph reads (EventsToSignals::processVector,
+// MLEventsToSignals.cpp:383-470) into a device buffer that IS the graph's input (the bank's out planes
+// have the layout of graph inputs, plane r = row r), and the graph runs on it in the same stream.
+// Pipelined over TIME chunks -- blocks are contiguous in every buffer involved, and both the bank and
+// the graph carry their state from launch to launch -- so that the H2D copy of chunk c+1's records, the
+// two kernels of chunk c and the D2H copy of chunk c-1's output rows overlap.
+extern "C" int mlb_synth_process_host(mlb_voices* vb, mlb_graph* g, const mlb_voice_events* events_host,
+                                      float* out_host, float* mix_host, int n_blocks)
+{
+  if (!vb || !g || !events_host) return fail(MLB_ERR_INVALID, "null argument");
+  if (n_blocks <= 0) return fail(MLB_ERR_INVALID, "n_blocks must be positive");
+  if (vb->V != g->V) return fail(MLB_ERR_INVALID, "voice bank has %d voices, graph has %d", vb->V, g->V);
+  unsigned row_mask = 0;
+  for (const mlb_node& n : g->nodes)
+    if (n.op == MLB_OP_INPUT)
+    {
+      if (n.iarg < 0 || n.iarg >= MLB_VOICE_ROWS)
+        return fail(MLB_ERR_INVALID, "graph INPUT plane %d is not a Voice row (0..%d)", n.iarg, MLB_VOICE_ROWS - 1);
+      row_mask |= 1u << n.iarg;
+    }
+  if (!row_mask) return fail(MLB_ERR_INVALID, "graph reads no Voice row (no INPUT node)");
+  if (g->outs.empty() && (out_host || mix_host)) return fail(MLB_ERR_INVALID, "graph has no outputs");
+  int rc = ensure_init();
+  if (rc != MLB_OK) return rc;
+  const size_t V = (size_t)g->V, T = (size_t)n_blocks, n_out = g->outs.size();
+  const size_t plane = V * MLB_BLOCK * 4;
+  // rows of one chunk stay under ~1 GB (8 planes per block are addressed, only the masked ones are touched)
+  int Tc = env_int("MLB_SYNTH_CHUNK_BLOCKS", 0);
+  if (Tc <= 0) Tc = (int)std::max<size_t>(1, ((size_t)1 << 30) / (MLB_VOICE_ROWS * plane));
+  Tc = std::min<int>(Tc, n_blocks);
+  Tc = std::max<int>(Tc, (n_blocks + mlb_graph::kMaxHostSlices - 1) / mlb_graph::kMaxHostSlices);
+  const size_t ev_bytes = T * V * sizeof(mlb_voice_events);
+  if ((rc = ensure_buf(reinterpret_cast<float**>(&vb->d_ev), &vb->ev_cap, ev_bytes)) != MLB_OK) return rc;
+  if ((rc = ensure_buf(&vb->d_out, &vb->out_cap, (size_t)Tc * MLB_VOICE_ROWS * plane)) != MLB_OK) return rc;
+  if (out_host && (rc = ensure_buf(&g->d_out, &g->out_cap, T * n_out * plane)) != MLB_OK) return rc;
+  if (mix_host && (rc = ensure_buf(&g->d_mix, &g->mix_cap, T * n_out * MLB_BLOCK * 4)) != MLB_OK) return rc;
+  const int saved_inputs = g->layout.n_inputs;
+  g->layout.n_inputs = MLB_VOICE_ROWS;
+  cudaStream_t s = g->stream;
+  rc = MLB_OK;
+  int p = 0;
+  for (size_t t0 = 0; t0 < T && rc == MLB_OK; t0 += (size_t)Tc, ++p)
+  {
+    const int tc = (int)std::min<size_t>((size_t)Tc, T - t0);
+    cudaError_t ce = cudaMemcpyAsync(vb->d_ev + t0 * V, events_host + t0 * V, (size_t)tc * V * sizeof(mlb_voice_events),
+                                     cudaMemcpyHostToDevice, g->s_h2d);
+    if (ce == cudaSuccess) ce = cudaEventRecord(g->ev_up[p], g->s_h2d);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s, g->ev_up[p], 0);
+    if (ce != cudaSuccess)
+    {
+      rc = fail(MLB_ERR_CUDA, "events H2D: %s", cudaGetErrorString(ce));
+      break;
+    }
+    rc = mlb_voices_process_device(vb, vb->d_ev + t0 * V, vb->d_out, tc, row_mask, s);
+    if (rc != MLB_OK) break;
+    rc = mlb_graph_process_device(g, vb->d_out, out_host ? g->d_out + t0 * n_out * V * MLB_BLOCK : nullptr,
+                                  mix_host ? g->d_mix + t0 * n_out * MLB_BLOCK : nullptr, tc, s);
+    if (rc != MLB_OK) break;
+    if (out_host)
+    {
+      ce = cudaEventRecord(g->ev_k[p], s);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(g->s_d2h, g->ev_k[p], 0);
+      if (ce == cudaSuccess)
+        ce = cudaMemcpyAsync(out_host + t0 * n_out * V * MLB_BLOCK, g->d_out + t0 * n_out * V * MLB_BLOCK,
+                             (size_t)tc * n_out * plane, cudaMemcpyDeviceToHost, g->s_d2h);
+      if (ce != cudaSuccess) rc = fail(MLB_ERR_CUDA, "rows D2H: %s", cudaGetErrorString(ce));
+    }
+  }
+  g->layout.n_inputs = saved_inputs;
+  g->last_host_slices = p;
+  if (rc == MLB_OK && mix_host)
+  {
+    rc = mlb_graph_mix_wait(g, s);
+    if (rc == MLB_OK && cudaMemcpyAsync(mix_host, g->d_mix, T * n_out * MLB_BLOCK * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+      rc = fail(MLB_ERR_CUDA, "mix D2H failed");
+  }
+  // drain all three streams whatever happened: nothing may still touch the caller's buffers on return
+  cudaStreamSynchronize(g->s_h2d);
+  cudaError_t e1 = cudaStreamSynchronize(s), e2 = cudaStreamSynchronize(g->s_d2h);
+  if (rc == MLB_OK && (e1 != cudaSuccess || e2 != cudaSuccess))
+    rc = fail(MLB_ERR_CUDA, "synth pipeline: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  return rc;
+}
 
 // ------------------------------------------------------------------------------------------
 // Upsampler / Downsampler banks (K8, resample_kernel.cuh)

@@ -57,22 +57,28 @@ MLB_DEV void voice_set_glide_time(VoiceRegs& r, float t)
   r.pg_dy = __fdiv_rn(1.0f, __int2float_rn(n));
 }
 // one output frame, E:134-140: gate, glided pitch, age -> seconds (samplesToSeconds, E:12-18)
-// Row tiles in shared memory: [lane][65 floats] per warp -- a lane walks its own row (frames can be
-// revisited by a retrigger), then the warp stores the 32 rows with full 128-byte lines.
-constexpr int kVoiceTileStride = 65;
-constexpr int kVoiceTileFloats = 32 * kVoiceTileStride;
+// Row tiles in shared memory: 32 rows x 64 floats per warp, 8 KB, unpadded, swizzled by 16-byte groups:
+// frames 4g..4g+3 of row j sit in group g ^ (j & 7) of the row.  A lane reads and writes its own row with
+// 128-bit accesses (each quarter-warp touches 8 different groups), and the warp stores one row with two full
+// 128-byte lines from 32 different banks.  8 KB instead of a padded 32 x 65 tile is what lets 14 warps
+// (2 CTAs of 7) live on an SM: 65 536 voices = 2 048 warps <= 148 x 14, ONE wave instead of 1.15 waves of
+// 12 warps per SM (which cost two).
+constexpr int kVoiceTileFloats = 32 * MLB_BLOCK;
+constexpr int kVoiceWarpsPerCta = 7;       // gate + pitch tiles: 7 x 16 KB = 112 KB per CTA, two CTAs per SM
+constexpr int kVoiceWarpsPerCtaTime = 4;   // + elapsed-time tile: 4 x 24 KB
 
-MLB_DEV void voice_frame(VoiceRegs& r, float sr, int t, float gate_v, float* gate, float* pitch, float* tm,
-                        bool want_time)
+// frame t of this lane's row (scalar access: the retrigger path, which can revisit frames); sw = (lane & 7) << 2
+MLB_DEV int voice_word(int t, int sw) { return t ^ sw; }
+
+MLB_DEV void voice_tick(VoiceRegs& r, float sr, bool want_time, float& p, float& tm)
 {
-  gate[t] = gate_v;
   const float co[2] = {r.pg_per_f, r.pg_dy};
-  pitch[t] = sample_glide_tick<true>(r.pitch, r.pg, co);
+  p = sample_glide_tick<true>(r.pitch, r.pg, co);
   r.age += r.age_step;
-  if (want_time) tm[t] = __double2float_rn(__ddiv_rn((double)r.age, (double)sr));  // FP64 divide only if the row is wanted
+  if (want_time) tm = __double2float_rn(__ddiv_rn((double)r.age, (double)sr));  // FP64 divide only if the row is wanted
 }
-// the warp's 32 rows of one output plane: tile[j][0..63] -> plane[(v0 + j)][0..63], two 128-B lines per row
-MLB_DEV void voice_store_tile(const float* tile, float* plane, int v0, int V, int lane)
+// the warp's 32 rows of one output plane: tile row j -> plane[(v0 + j)][0..63], two 128-B lines per row
+__device__ __noinline__ void voice_store_tile(const float* tile, float* plane, int v0, int V, int lane)
 {
   __syncwarp();
 #pragma unroll 4
@@ -80,8 +86,9 @@ MLB_DEV void voice_store_tile(const float* tile, float* plane, int v0, int V, in
   {
     if (v0 + j >= V) break;
     float* dst = plane + (size_t)(v0 + j) * MLB_BLOCK;
-    __stcs(dst + lane, tile[j * kVoiceTileStride + lane]);
-    __stcs(dst + 32 + lane, tile[j * kVoiceTileStride + 32 + lane]);
+    const float* row = tile + j * MLB_BLOCK + ((((lane >> 2) ^ (j & 7)) << 2) | (lane & 3));
+    __stcs(dst + lane, row[0]);
+    __stcs(dst + 32 + lane, row[32]);
   }
   __syncwarp();
 }
@@ -94,13 +101,21 @@ struct GlidePlan
   int mode;  // -1 idle, 0 land on target, 1 start, 2 continue
   float step, target, cv;
 };
-// st: step, target, vectorsRemaining, (spare)
-MLB_DEV GlidePlan glide_plan(uint32_t* st, float f, float per_f, float dy, const float* row)
+// st: step, target, vectorsRemaining -> updated in place.  Out of line: seven calls per vector, and the kernel's
+// instruction footprint is what its warps stall on (one copy instead of seven).
+struct GlidePlanned
 {
   GlidePlan g;
-  g.step = u2f(st[0]), g.target = u2f(st[1]);
+  uint32_t s0, s1, s2;
+};
+__device__ __noinline__ GlidePlanned glide_plan(uint32_t s0, uint32_t s1, uint32_t s2, float f, float per_f, float dy,
+                                                 const float* row)
+{
+  GlidePlanned o;
+  GlidePlan& g = o.g;
+  g.step = u2f(s0), g.target = u2f(s1);
   g.cv = 0.f;
-  const int rem_prev = (int32_t)st[2];
+  const int rem_prev = (int32_t)s2;
   int remaining = rem_prev;
   const int per = cvt_trunc(per_f);
   if (f != g.target)
@@ -120,7 +135,7 @@ MLB_DEV GlidePlan glide_plan(uint32_t* st, float f, float per_f, float dy, const
   {
     g.mode = 1;
     // currentValue = mCurrVec[63]; an idle row is its (previous) target
-    g.cv = rem_prev < 0 ? u2f(st[1]) : row[MLB_BLOCK - 1];
+    g.cv = rem_prev < 0 ? u2f(s1) : row[MLB_BLOCK - 1];
     g.step = __fmul_rn(__fsub_rn(g.target, g.cv), dy);
     remaining--;
   }
@@ -129,62 +144,145 @@ MLB_DEV GlidePlan glide_plan(uint32_t* st, float f, float per_f, float dy, const
     g.mode = 2;
     remaining--;
   }
-  st[0] = f2u(g.step), st[1] = f2u(g.target), st[2] = (uint32_t)remaining;
-  return g;
+  o.s0 = f2u(g.step), o.s1 = f2u(g.target), o.s2 = (uint32_t)remaining;
+  return o;
 }
-// Run one glide for this lane's vector; emit(q, float4) receives samples 4q..4q+3 when WANT is set.
-// The three modes are hoisted out of the sample loop; an idle glide whose row nobody wants costs nothing.
-template <bool WANT, class Emit>
-MLB_DEV void glide_run(const GlidePlan& g, float* row, bool live, Emit emit)
+// ---- the glides of a vector, run TRANSPOSED: the warp walks its 32 voices, lane = sample index ----
+// A lane plans its own voice's glides (glide_plan above, scalars only); the 64-sample rows are then produced
+// row by row with the warp across the samples, so that
+//   * the mode of a row is warp-uniform (no divergence between idle / starting / moving glides),
+//   * a moving glide's row in delay memory is read and written as two full 128-byte lines (a lane walking
+//     its own 256-byte row touched 32 sectors per load and fetched each twice), and idle rows cost no memory,
+//   * the loads of several rows are in flight together (four rows per step, predicated),
+//   * the finished sample goes straight to the output plane (the kPitch row picks up bend and drift on the
+//     way out of its tile; the glide-only rows never see shared memory).
+// What a lane offers to the others: mode, a = step (moving / starting) or target (idle), b = start value.
+struct GlideLane
 {
-  float4* row4 = reinterpret_cast<float4*>(row);
-  if (g.mode <= 0)
+  int mode;  // <= 0 idle, 1 start, 2 continue
+  float a, b;
+};
+MLB_DEV GlideLane glide_lane(const GlidePlan& g)
+{
+  GlideLane l;
+  l.mode = g.mode;
+  l.a = g.mode >= 1 ? g.step : g.target;
+  l.b = g.cv;
+  return l;
+}
+MLB_DEV GlideLane glide_of(const GlideLane& mine, int j)  // voice j's plan, to every lane
+{
+  GlideLane l;
+  l.mode = __shfl_sync(0xffffffffu, mine.mode, j);
+  l.a = __shfl_sync(0xffffffffu, mine.a, j);
+  l.b = __shfl_sync(0xffffffffu, mine.b, j);
+  return l;
+}
+// sample n of the row: idle -> target; start -> cv + ramp[n] * step; continue -> row[n] + step  (G:459-505)
+MLB_DEV float glide_sample(const GlideLane& l, float r, int n)
+{
+  const float y2 = __fadd_rn(r, l.a);
+  const float y1 = __fadd_rn(l.b, __fmul_rn(unity_ramp(n), l.a));
+  return l.mode == 2 ? y2 : (l.mode == 1 ? y1 : l.a);
+}
+// Advance one glide whose row nobody wants: only the voices whose glide moves are visited, four at a time.
+__device__ __noinline__ void glide_advance(int m_mode, float m_a, float m_b, float* grow_base, int v0, int V, int lane)
+{
+  GlideLane mine;
+  mine.mode = m_mode, mine.a = m_a, mine.b = m_b;
+  unsigned act = __ballot_sync(0xffffffffu, mine.mode >= 1 && v0 + lane < V);
+  while (act)
   {
-    // landing: the row becomes DSPVector(target); it is not stored -- idle rows are never read
-    if (WANT)
+    int jj[4];
+    bool ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
     {
-      const float4 y = make_float4(g.target, g.target, g.target, g.target);
-#pragma unroll 4
-      for (int q = 0; q < 16; ++q) emit(q, y);
+      ok[k] = act != 0u;
+      jj[k] = ok[k] ? __ffs(act) - 1 : 0;
+      act &= act - (ok[k] ? 1u : 0u);
+    }
+    GlideLane l[4];
+    float r0[4], r1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) l[k] = glide_of(mine, jj[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+      const float* row = grow_base + (size_t)(v0 + jj[k]) * MLB_BLOCK + lane;
+      const bool ld = ok[k] && l[k].mode == 2;
+      r0[k] = ld ? row[0] : 0.f;
+      r1[k] = ld ? row[32] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+      if (!ok[k]) continue;
+      float* row = grow_base + (size_t)(v0 + jj[k]) * MLB_BLOCK + lane;
+      row[0] = glide_sample(l[k], r0[k], lane);
+      row[32] = glide_sample(l[k], r1[k], lane + 32);
     }
   }
-  else if (g.mode == 1)
-  {
-#pragma unroll 2
-    for (int q = 0; q < 16; ++q)
-    {
-      float4 y;
-      y.x = __fadd_rn(g.cv, __fmul_rn(unity_ramp(4 * q), g.step));
-      y.y = __fadd_rn(g.cv, __fmul_rn(unity_ramp(4 * q + 1), g.step));
-      y.z = __fadd_rn(g.cv, __fmul_rn(unity_ramp(4 * q + 2), g.step));
-      y.w = __fadd_rn(g.cv, __fmul_rn(unity_ramp(4 * q + 3), g.step));
-      if (live) row4[q] = y;
-      if (WANT) emit(q, y);
-    }
-  }
-  else
-  {
+}
+// One glide-only output row (kZ / kX / kY / kMod) for the warp's 32 voices: sample -> plane, moving rows updated
+// in delay memory.  With `extra`, a second glide (the MIDI channel-pressure glide, added to kZ) runs alongside.
+__device__ __noinline__ void glide_row_out(int m_mode, float m_a, float m_b, float* grow_base, bool extra, int x_mode,
+                                           float x_a, float x_b, float* extra_base, float* plane, int v0, int V, int lane)
+{
+  GlideLane mine, xmine;
+  mine.mode = m_mode, mine.a = m_a, mine.b = m_b;
+  xmine.mode = x_mode, xmine.a = x_a, xmine.b = x_b;
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h)
+  for (int j0 = 0; j0 < 32; j0 += 4)
+  {
+    if (v0 + j0 >= V) break;
+    GlideLane l[4], e[4];
+    float r0[4], r1[4], s0[4], s1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
     {
-      float4 buf[8];
+      l[k] = glide_of(mine, j0 + k);
+      if (extra) e[k] = glide_of(xmine, j0 + k);
+    }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) buf[q] = row4[8 * h + q];
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
+    for (int k = 0; k < 4; ++k)
+    {
+      const bool ok = v0 + j0 + k < V;
+      const float* row = grow_base + (size_t)(v0 + j0 + k) * MLB_BLOCK + lane;
+      const bool ld = ok && l[k].mode == 2;
+      r0[k] = ld ? row[0] : 0.f;
+      r1[k] = ld ? row[32] : 0.f;
+      s0[k] = s1[k] = 0.f;
+      if (extra)
       {
-        float4 y = buf[q];
-        y.x = __fadd_rn(y.x, g.step), y.y = __fadd_rn(y.y, g.step), y.z = __fadd_rn(y.z, g.step), y.w = __fadd_rn(y.w, g.step);
-        if (live) row4[8 * h + q] = y;
-        if (WANT) emit(8 * h + q, y);
+        const float* xrow = extra_base + (size_t)(v0 + j0 + k) * MLB_BLOCK + lane;
+        const bool lx = ok && e[k].mode == 2;
+        s0[k] = lx ? xrow[0] : 0.f;
+        s1[k] = lx ? xrow[32] : 0.f;
       }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+      if (v0 + j0 + k >= V) break;
+      const size_t off = (size_t)(v0 + j0 + k) * MLB_BLOCK + lane;
+      float y0 = glide_sample(l[k], r0[k], lane), y1 = glide_sample(l[k], r1[k], lane + 32);
+      if (l[k].mode >= 1) grow_base[off] = y0, grow_base[off + 32] = y1;
+      if (extra)
+      {
+        const float x0 = glide_sample(e[k], s0[k], lane), x1 = glide_sample(e[k], s1[k], lane + 32);
+        if (e[k].mode >= 1) extra_base[off] = x0, extra_base[off + 32] = x1;
+        y0 = __fadd_rn(y0, x0), y1 = __fadd_rn(y1, x1);
+      }
+      __stcs(plane + off, y0);
+      __stcs(plane + off + 32, y1);
     }
   }
 }
 
-__global__ void __launch_bounds__(128, 3) voice_bank_kernel(const VoiceArgs a)
+__global__ void __launch_bounds__(32 * kVoiceWarpsPerCta, 2) voice_bank_kernel(const VoiceArgs a)
 {
-  extern __shared__ float voice_smem[];
+  extern __shared__ __align__(16) float voice_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int v_raw = blockIdx.x * blockDim.x + threadIdx.x;
   const int v0 = v_raw - lane;
@@ -195,19 +293,21 @@ __global__ void __launch_bounds__(128, 3) voice_bank_kernel(const VoiceArgs a)
   const bool want_time = (a.row_mask & 128u) != 0;
   const int n_tiles = want_time ? 3 : 2;  // gate, pitch (+ elapsed time)
   float* const tiles = voice_smem + (size_t)warp * n_tiles * kVoiceTileFloats;
-  float* const gate = tiles + lane * kVoiceTileStride;
+  float* const gate = tiles + lane * MLB_BLOCK;  // this lane's row, groups swizzled by l7
   float* const pitch = gate + kVoiceTileFloats;
   float* const tm = pitch + kVoiceTileFloats;
-  uint32_t st[VS_COUNT];
+  const int l7 = lane & 7, sw = l7 << 2;
+  float4* const gate4 = reinterpret_cast<float4*>(gate);
+  float4* const pitch4 = reinterpret_cast<float4*>(pitch);
+  float4* const tm4 = reinterpret_cast<float4*>(tm);
+  uint32_t st[VS_COUNT];  // the glide words [VS_GL, VS_VEL) are not kept here (see glide_plan below)
 #pragma unroll
-  for (int i = 0; i < VS_COUNT; ++i) st[i] = a.state[(size_t)i * V + v];
+  for (int i = 0; i < VS_COUNT; ++i)
+    if (i < VS_GL || i >= VS_VEL) st[i] = a.state[(size_t)i * V + v];
   const float glide_samples = a.coef[(size_t)VC_GLIDE_SAMPLES * V + v];  // (float)pitchGlideTimeInSamples
   const float drift_amount = a.coef[(size_t)VC_DRIFT_AMOUNT * V + v];
   const float bend_range = a.coef[(size_t)VC_BEND_RANGE * V + v];
   const float voice_row = a.coef[(size_t)VC_VOICE_ROW * V + v];
-  float* grow[VG_COUNT];
-#pragma unroll
-  for (int i = 0; i < VG_COUNT; ++i) grow[i] = a.grows + ((size_t)i * V + v) * MLB_BLOCK;
 
   VoiceRegs r;
 #pragma unroll
@@ -240,6 +340,12 @@ __global__ void __launch_bounds__(128, 3) voice_bank_kernel(const VoiceArgs a)
     // rest of the vector.  Here every lane emits ONE frame per iteration of a warp-uniform loop and
     // steps its own event cursor in between, so lanes with different event times do not serialise.
     const uint32_t* rec = reinterpret_cast<const uint32_t*>(a.ev + ((size_t)t * V + v));
+    if (t + 1 < a.T)  // the next vector's record (72 B, streamed from DRAM once): have it in L2 by then
+    {
+      const char* nx = reinterpret_cast<const char*>(a.ev + ((size_t)(t + 1) * V + v));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 64));
+    }
     const uint32_t head = rec[0], times = rec[1], types = rec[2], flags = rec[3];
     const int n_events = min((int)(head & 0xFFu), MLB_VOICE_MAX_EVENTS);
     const unsigned set_mask = (head >> 8) & 0xFFu;
@@ -302,11 +408,34 @@ __global__ void __launch_bounds__(128, 3) voice_bank_kernel(const VoiceArgs a)
       };
       advance();
 #pragma unroll 1
-      for (int f = 0; f < MLB_BLOCK; ++f)
+      for (int q = 0; q < MLB_BLOCK / 4; ++q)
       {
-        while (cur_d <= f) complete();
-        const bool retrig_frame = cur_kind == 2 && cur_d - 1 == f;
-        voice_frame(r, a.sr, f, retrig_frame ? 0.f : r.vel, gate, pitch, tm, want_time);
+        // nothing of the current event falls into frames 4q .. 4q+3 (a retrigger's gate-0 frame is cur_d - 1):
+        // four plain frames, one 128-bit store per row
+        if (cur_d > 4 * q + 3 + (cur_kind == 2 ? 1 : 0))
+        {
+          float p[4], tmv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) voice_tick(r, a.sr, want_time, p[i], tmv[i]);
+          gate4[q ^ l7] = make_float4(r.vel, r.vel, r.vel, r.vel);
+          pitch4[q ^ l7] = make_float4(p[0], p[1], p[2], p[3]);
+          if (want_time) tm4[q ^ l7] = make_float4(tmv[0], tmv[1], tmv[2], tmv[3]);
+        }
+        else
+        {
+#pragma unroll 1
+          for (int f = 4 * q; f < 4 * q + 4; ++f)
+          {
+            while (cur_d <= f) complete();
+            const bool retrig_frame = cur_kind == 2 && cur_d - 1 == f;
+            float pv, tv = 0.f;
+            const float gv = retrig_frame ? 0.f : r.vel;
+            voice_tick(r, a.sr, want_time, pv, tv);
+            const int x = voice_word(f, sw);
+            gate[x] = gv, pitch[x] = pv;
+            if (want_time) tm[x] = tv;
+          }
+        }
       }
       while (k < MLB_VOICE_MAX_EVENTS) complete();  // events at frame 64: only their value changes remain
       r.next_frame = MLB_BLOCK;
@@ -380,7 +509,14 @@ __global__ void __launch_bounds__(128, 3) voice_bank_kernel(const VoiceArgs a)
           else
             active = false;
         }
-        if (emit_at >= 0) voice_frame(r, a.sr, emit_at, emit_gate, gate, pitch, tm, want_time);
+        if (emit_at >= 0)
+        {
+          float pv, tv = 0.f;
+          voice_tick(r, a.sr, want_time, pv, tv);
+          const int x = voice_word(emit_at, sw);
+          gate[x] = emit_gate, pitch[x] = pv;
+          if (want_time) tm[x] = tv;
+        }
       }
     }
     if (set_mask & MLB_SET_BEND) cur[0] = u2f(rec[12]);
@@ -400,64 +536,113 @@ __global__ void __launch_bounds__(128, 3) voice_bank_kernel(const VoiceArgs a)
         gp[i].mode = -1, gp[i].step = gp[i].target = gp[i].cv = 0.f;
         continue;
       }
-      gp[i] = glide_plan(&st[VS_GL + 4 * i], i == VG_DRIFT ? cur_drift : (i == VG_PRESSURE ? cur_pressure : cur[i]),
-                         i == VG_DRIFT ? a.dr_per : (i == VG_PRESSURE ? a.pc_per : a.gl_per),
-                         i == VG_DRIFT ? a.dr_dy : (i == VG_PRESSURE ? a.pc_dy : a.gl_dy), grow[i]);
+      // {step, target, vectorsRemaining} live in the state array between vectors (coalesced [word][V] lines),
+      // not in registers across the frame loop
+      uint32_t* const gw = a.state + (size_t)(VS_GL + 4 * i) * V + v;
+      const GlidePlanned o =
+          glide_plan(gw[0], gw[V], gw[2 * V], i == VG_DRIFT ? cur_drift : (i == VG_PRESSURE ? cur_pressure : cur[i]),
+                     i == VG_DRIFT ? a.dr_per : (i == VG_PRESSURE ? a.pc_per : a.gl_per),
+                     i == VG_DRIFT ? a.dr_dy : (i == VG_PRESSURE ? a.pc_dy : a.gl_dy),
+                     a.grows + ((size_t)i * V + v) * MLB_BLOCK);
+      gp[i] = o.g;
+      if (live) gw[0] = o.s0, gw[V] = o.s1, gw[2 * V] = o.s2;
     }
     float* const planes = a.out + (size_t)t * MLB_VOICE_ROWS * V * MLB_BLOCK;
     const size_t plane_floats = V * MLB_BLOCK;
-    // pitch += bendGlide * pitchBend * (1/12); pitch += driftSig * driftAmount * kDriftScale  (E:255-261)
-    glide_run<true>(gp[VG_BEND], grow[VG_BEND], live, [&](int q, float4 y)
+    GlideLane gl[VG_COUNT];
+#pragma unroll
+    for (int i = 0; i < VG_COUNT; ++i) gl[i] = glide_lane(gp[i]);
+    __syncwarp();  // the tiles are complete
+    // ---- kPitch: the tile row + bendGlide * pitchBend * (1/12) + driftSig * driftAmount * kDriftScale (E:255-261),
+    //      straight to the plane; the bend and drift glides advance whether or not the row is wanted ----
     {
-      const float k12 = 1.f / 12;
-      float* p = pitch + 4 * q;
-      p[0] = __fadd_rn(p[0], __fmul_rn(__fmul_rn(y.x, bend_range), k12));
-      p[1] = __fadd_rn(p[1], __fmul_rn(__fmul_rn(y.y, bend_range), k12));
-      p[2] = __fadd_rn(p[2], __fmul_rn(__fmul_rn(y.z, bend_range), k12));
-      p[3] = __fadd_rn(p[3], __fmul_rn(__fmul_rn(y.w, bend_range), k12));
-    });
-    glide_run<true>(gp[VG_DRIFT], grow[VG_DRIFT], live, [&](int q, float4 y)
-    {
-      float* p = pitch + 4 * q;
-      p[0] = __fadd_rn(p[0], __fmul_rn(__fmul_rn(y.x, drift_amount), 0.02f));
-      p[1] = __fadd_rn(p[1], __fmul_rn(__fmul_rn(y.y, drift_amount), 0.02f));
-      p[2] = __fadd_rn(p[2], __fmul_rn(__fmul_rn(y.z, drift_amount), 0.02f));
-      p[3] = __fadd_rn(p[3], __fmul_rn(__fmul_rn(y.w, drift_amount), 0.02f));
-    });
-    if (a.row_mask & 1u) voice_store_tile(tiles + kVoiceTileFloats, planes + 0 * plane_floats, v0, a.V, lane);    // kPitch
+      const bool want_pitch = (a.row_mask & 1u) != 0;
+      const float* tp = tiles + kVoiceTileFloats;
+      float* const gb = a.grows + (size_t)VG_BEND * V * MLB_BLOCK;
+      float* const gd = a.grows + (size_t)VG_DRIFT * V * MLB_BLOCK;
+#pragma unroll 1
+      for (int j0 = 0; j0 < 32; j0 += 4)
+      {
+        if (v0 + j0 >= a.V) break;
+        GlideLane lb[4], ld[4];
+        float rng[4], amt[4], b0[4], b1[4], d0[4], d1[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+          lb[k] = glide_of(gl[VG_BEND], j0 + k);
+          ld[k] = glide_of(gl[VG_DRIFT], j0 + k);
+          rng[k] = __shfl_sync(0xffffffffu, bend_range, j0 + k);
+          amt[k] = __shfl_sync(0xffffffffu, drift_amount, j0 + k);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+          const bool ok = v0 + j0 + k < a.V;
+          const size_t off = (size_t)(v0 + j0 + k) * MLB_BLOCK + lane;
+          const bool l1 = ok && lb[k].mode == 2, l2 = ok && ld[k].mode == 2;
+          b0[k] = l1 ? gb[off] : 0.f;
+          b1[k] = l1 ? gb[off + 32] : 0.f;
+          d0[k] = l2 ? gd[off] : 0.f;
+          d1[k] = l2 ? gd[off + 32] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+          const int j = j0 + k;
+          if (v0 + j >= a.V) break;
+          const size_t off = (size_t)(v0 + j) * MLB_BLOCK + lane;
+          const float yb0 = glide_sample(lb[k], b0[k], lane), yb1 = glide_sample(lb[k], b1[k], lane + 32);
+          const float yd0 = glide_sample(ld[k], d0[k], lane), yd1 = glide_sample(ld[k], d1[k], lane + 32);
+          if (lb[k].mode >= 1) gb[off] = yb0, gb[off + 32] = yb1;
+          if (ld[k].mode >= 1) gd[off] = yd0, gd[off + 32] = yd1;
+          if (want_pitch)
+          {
+            const float k12 = 1.f / 12;
+            const float* row = tp + j * MLB_BLOCK + ((((lane >> 2) ^ (j & 7)) << 2) | (lane & 3));
+            float p0 = row[0], p1 = row[32];
+            p0 = __fadd_rn(p0, __fmul_rn(__fmul_rn(yb0, rng[k]), k12));
+            p1 = __fadd_rn(p1, __fmul_rn(__fmul_rn(yb1, rng[k]), k12));
+            p0 = __fadd_rn(p0, __fmul_rn(__fmul_rn(yd0, amt[k]), 0.02f));
+            p1 = __fadd_rn(p1, __fmul_rn(__fmul_rn(yd1, amt[k]), 0.02f));
+            __stcs(planes + off, p0);
+            __stcs(planes + off + 32, p1);
+          }
+        }
+      }
+    }
     if (a.row_mask & 2u) voice_store_tile(tiles, planes + 1 * plane_floats, v0, a.V, lane);                        // kGate
     if (want_time) voice_store_tile(tiles + 2 * kVoiceTileFloats, planes + 7 * plane_floats, v0, a.V, lane);      // kElapsedTime
-    __syncwarp();
-    // the glide-only rows reuse the gate tile: kZ(3) kX(4) kY(5) kMod(6) <- z, x, y, mod glides; kVoice(2) constant
-    if (a.row_mask & 4u)
+    if (a.row_mask & 4u)  // kVoice: voiceIndex - 1 in every sample
     {
+      float* const pv = planes + 2 * plane_floats;
 #pragma unroll 4
-      for (int n = 0; n < MLB_BLOCK; ++n) gate[n] = voice_row;
-      voice_store_tile(tiles, planes + 2 * plane_floats, v0, a.V, lane);
+      for (int j = 0; j < 32; ++j)
+      {
+        if (v0 + j >= a.V) break;
+        const float c = __shfl_sync(0xffffffffu, voice_row, j);
+        __stcs(pv + (size_t)(v0 + j) * MLB_BLOCK + lane, c);
+        __stcs(pv + (size_t)(v0 + j) * MLB_BLOCK + 32 + lane, c);
+      }
     }
+    // the glide-only rows: kZ(3) kX(4) kY(5) kMod(6) <- z, x, y, mod glides (kZ += the channel-pressure glide in MIDI mode)
     const int glide_of_row[4] = {VG_Z, VG_X, VG_Y, VG_MOD};
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr)
     {
       const int row = 3 + rr, gi = glide_of_row[rr];
+      float* const gbase = a.grows + (size_t)gi * V * MLB_BLOCK;
+      float* const pbase = a.grows + (size_t)VG_PRESSURE * V * MLB_BLOCK;
+      const bool with_pressure = gi == VG_Z && a.midi;
       if ((a.row_mask >> row) & 1u)
-      {
-        glide_run<true>(gp[gi], grow[gi], live, [&](int q, float4 y)
-        { gate[4 * q] = y.x, gate[4 * q + 1] = y.y, gate[4 * q + 2] = y.z, gate[4 * q + 3] = y.w; });
-        if (gi == VG_Z && a.midi)  // voices[v].outputs.row(kZ) += controllers[128].output
-          glide_run<true>(gp[VG_PRESSURE], grow[VG_PRESSURE], live, [&](int q, float4 y)
-          {
-            gate[4 * q] = __fadd_rn(gate[4 * q], y.x), gate[4 * q + 1] = __fadd_rn(gate[4 * q + 1], y.y);
-            gate[4 * q + 2] = __fadd_rn(gate[4 * q + 2], y.z), gate[4 * q + 3] = __fadd_rn(gate[4 * q + 3], y.w);
-          });
-        voice_store_tile(tiles, planes + (size_t)row * plane_floats, v0, a.V, lane);
-      }
+        glide_row_out(gl[gi].mode, gl[gi].a, gl[gi].b, gbase, with_pressure, gl[VG_PRESSURE].mode, gl[VG_PRESSURE].a,
+                      gl[VG_PRESSURE].b, pbase, planes + (size_t)row * plane_floats, v0, a.V, lane);
       else
       {
-        glide_run<false>(gp[gi], grow[gi], live, [](int, float4) {});  // the glide still advances
-        if (gi == VG_Z && a.midi) glide_run<false>(gp[VG_PRESSURE], grow[VG_PRESSURE], live, [](int, float4) {});
+        glide_advance(gl[gi].mode, gl[gi].a, gl[gi].b, gbase, v0, a.V, lane);  // the glide still advances
+        if (with_pressure) glide_advance(gl[VG_PRESSURE].mode, gl[VG_PRESSURE].a, gl[VG_PRESSURE].b, pbase, v0, a.V, lane);
       }
     }
+    __syncwarp();  // rows written across lanes are read by their own lane (glide_plan) in the next vector
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) st[VS_PG_CURR + i] = r.pg[i];
@@ -471,7 +656,8 @@ __global__ void __launch_bounds__(128, 3) voice_bank_kernel(const VoiceArgs a)
   if (live)
   {
 #pragma unroll
-    for (int i = 0; i < VS_COUNT; ++i) a.state[(size_t)i * V + v] = st[i];
+    for (int i = 0; i < VS_COUNT; ++i)
+      if (i < VS_GL || i >= VS_VEL) a.state[(size_t)i * V + v] = st[i];
   }
 }
 

@@ -615,6 +615,25 @@ def voice_events(n_voices: int, n_blocks: int, seed: int = 1, density: float = 0
     return ev
 
 
+def synth_bank_params(n_voices: int):
+    """voice_bank_params with a pitch-bend range of 0 semitones: the kPitch row is then the glided note
+    pitch plus drift, usable as a SineGen frequency row as it stands (see synth_events)."""
+    vi, gs, da, pb = voice_bank_params(n_voices)
+    return vi, gs, da, np.zeros_like(pb)
+
+
+def synth_events(n_voices: int, n_blocks: int, seed: int = 2, density: float = 0.10, ctl: float = 0.05,
+                 pitch_scale: float = 2.0 ** -5) -> np.ndarray:
+    """Contract-E performance for a bank of any size: a 256-voice seeded performance repeated across the
+    bank, note pitches scaled so that the kPitch row can drive SineGen directly (note / 12 * 2^-5 =
+    0.09 .. 0.25 cycles per sample; the reference leaves the pitch -> frequency mapping to the client,
+    MLSynth.h:67-71)."""
+    base = voice_events(min(n_voices, 256), n_blocks, seed=seed, density=density, ctl=ctl)
+    base["value1"] *= np.float32(pitch_scale)
+    reps = (n_voices + base.shape[1] - 1) // base.shape[1]
+    return np.ascontiguousarray(np.tile(base, (1, reps))[:, :n_voices])
+
+
 # ---- random voice graphs (tests): any DAG of the op table, for checker-vs-checker and GPU-vs-checker runs ----
 
 def random_graph_workload(seed: int, n_voices: int = 37, n_nodes: int = 24, hw_approx: bool = True) -> Workload:

@@ -313,6 +313,40 @@ int main()
     REQUIRE(std::fabs(time1[63] - 128.f / 48000.f) < 1e-7f);
   }
 
+  // ---- events -> signals -> voice DSP in one call: sine(kPitch row) * kGate row, two voices, the mix bus
+  //      is their sum; voice 1 never gets a note and stays silent ----
+  {
+    const int32_t idx[2] = {1, 2};
+    const float glide[2] = {0.f, 0.f}, drift[2] = {0.f, 0.f}, bend[2] = {0.f, 0.f};
+    VoiceBank vb(2, 48000.f, idx, glide, drift, bend);
+    Graph g;
+    g.output(g.multiply(g.sine(g.input(0)), g.input(1)));
+    DeviceBank bank(g, 2);
+    bank.commit();
+    mlb_voice_events ev[3 * 2];
+    std::memset(ev, 0, sizeof(ev));
+    ev[0].n_events = 1;
+    ev[0].time[0] = 10, ev[0].type[0] = MLB_EV_NOTE_ON, ev[0].flags[0] = MLB_EVF_RESET;
+    ev[0].value1[0] = 0.01f, ev[0].value2[0] = 0.5f;
+    std::vector<float> out((size_t)3 * 2 * 64), mix((size_t)3 * 64);
+    processEvents(vb, bank, ev, out.data(), mix.data(), 3);
+    float peak = 0.f;
+    bool silent1 = true, mixok = true, pre = true;
+    for (int t = 0; t < 3; ++t)
+      for (int n = 0; n < 64; ++n)
+      {
+        const float a = out[((size_t)t * 2 + 0) * 64 + n], b = out[((size_t)t * 2 + 1) * 64 + n];
+        if (t == 0 && n < 10 && a != 0.f) pre = false;
+        peak = std::max(peak, std::fabs(a));
+        silent1 = silent1 && b == 0.f;
+        mixok = mixok && mix[(size_t)t * 64 + n] == a + b;
+      }
+    REQUIRE(pre);                        // gate is 0 before the note on
+    REQUIRE(peak > 0.4f && peak < 0.501f);  // a 480 Hz sine at velocity 0.5
+    REQUIRE(silent1);
+    REQUIRE(mixok);
+  }
+
   std::printf("%s: %d assertions, %d failed, %lld kernels launched\n", g_fail ? "FAILED" : "ALL PASSED", g_checks,
               g_fail, mlb_kernel_launches());
   return g_fail ? 1 : 0;
