@@ -2321,15 +2321,21 @@ extern "C" int mlb_voices_process_device(mlb_voices* vb, const mlb_voice_events*
   a.midi = (vb->flags & MLB_VOICES_MIDI) ? 1 : 0;
   // warps x {gate, pitch (, elapsed time)} 8 KB row tiles; 7 warps per CTA and two CTAs per SM put the
   // 2 048 warps of a 65 536-voice bank on the 148 SMs in one wave (voice_kernel.cuh)
-  const int wpc = env_int("MLB_VOICE_WARPS", (row_mask & 128u) ? kVoiceWarpsPerCtaTime : kVoiceWarpsPerCta);
-  if (wpc < 1 || wpc > kVoiceWarpsPerCta) return fail(MLB_ERR_INVALID, "MLB_VOICE_WARPS must be in [1, %d]", kVoiceWarpsPerCta);
-  const size_t smem = (size_t)wpc * ((row_mask & 128u) ? 3 : 2) * kVoiceTileFloats * sizeof(float);
+  const bool want_time = (row_mask & 128u) != 0;
+  const int wpc_max = want_time ? kVoiceWarpsPerCtaTime : kVoiceWarpsPerCta;
+  const int wpc = env_int("MLB_VOICE_WARPS", wpc_max);
+  if (wpc < 1 || wpc > wpc_max) return fail(MLB_ERR_INVALID, "MLB_VOICE_WARPS must be in [1, %d]", wpc_max);
+  const size_t smem = (size_t)wpc * (want_time ? 3 : 2) * kVoiceTileFloats * sizeof(float);
+  const void* fn = want_time ? (const void*)voice_bank_kernel<true> : (const void*)voice_bank_kernel<false>;
   {
-    int rc = ensure_func_smem((const void*)voice_bank_kernel, smem);
+    int rc = ensure_func_smem(fn, smem);
     if (rc != MLB_OK) return rc;
   }
   const int n_warps = (vb->V + 31) / 32;
-  voice_bank_kernel<<<(n_warps + wpc - 1) / wpc, 32 * wpc, smem, (cudaStream_t)stream>>>(a);
+  if (want_time)
+    voice_bank_kernel<true><<<(n_warps + wpc - 1) / wpc, 32 * wpc, smem, (cudaStream_t)stream>>>(a);
+  else
+    voice_bank_kernel<false><<<(n_warps + wpc - 1) / wpc, 32 * wpc, smem, (cudaStream_t)stream>>>(a);
   ++g_launches;
   CU_CHECK(cudaGetLastError());
   if (vb->d_main && (a.row_mask & 0x79u))  // MPE: add the main voices' pitch / z / x / y / mod rows

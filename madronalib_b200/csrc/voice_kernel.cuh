@@ -70,12 +70,13 @@ constexpr int kVoiceWarpsPerCtaTime = 4;   // + elapsed-time tile: 4 x 24 KB
 // frame t of this lane's row (scalar access: the retrigger path, which can revisit frames); sw = (lane & 7) << 2
 MLB_DEV int voice_word(int t, int sw) { return t ^ sw; }
 
+// samplesToSeconds (E:12-18) is an FP64 divide: only in the kernel instance that writes the elapsed-time row
 MLB_DEV void voice_tick(VoiceRegs& r, float sr, bool want_time, float& p, float& tm)
 {
   const float co[2] = {r.pg_per_f, r.pg_dy};
   p = sample_glide_tick<true>(r.pitch, r.pg, co);
   r.age += r.age_step;
-  if (want_time) tm = __double2float_rn(__ddiv_rn((double)r.age, (double)sr));  // FP64 divide only if the row is wanted
+  if (want_time) tm = __double2float_rn(__ddiv_rn((double)r.age, (double)sr));
 }
 // the warp's 32 rows of one output plane: tile row j -> plane[(v0 + j)][0..63], two 128-B lines per row
 __device__ __noinline__ void voice_store_tile(const float* tile, float* plane, int v0, int V, int lane)
@@ -232,10 +233,26 @@ __device__ __noinline__ void glide_row_out(int m_mode, float m_a, float m_b, flo
   GlideLane mine, xmine;
   mine.mode = m_mode, mine.a = m_a, mine.b = m_b;
   xmine.mode = x_mode, xmine.a = x_a, xmine.b = x_b;
+  unsigned moving = __ballot_sync(0xffffffffu, mine.mode >= 1);
+  if (extra) moving |= __ballot_sync(0xffffffffu, xmine.mode >= 1);
 #pragma unroll 1
   for (int j0 = 0; j0 < 32; j0 += 4)
   {
     if (v0 + j0 >= V) break;
+    if (((moving >> j0) & 0xFu) == 0u)  // four idle voices: their rows are their targets, nothing in delay memory
+    {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+      {
+        if (v0 + j0 + k >= V) break;
+        float y = __shfl_sync(0xffffffffu, mine.a, j0 + k);
+        if (extra) y = __fadd_rn(y, __shfl_sync(0xffffffffu, xmine.a, j0 + k));
+        const size_t off = (size_t)(v0 + j0 + k) * MLB_BLOCK + lane;
+        __stcs(plane + off, y);
+        __stcs(plane + off + 32, y);
+      }
+      continue;
+    }
     GlideLane l[4], e[4];
     float r0[4], r1[4], s0[4], s1[4];
 #pragma unroll
@@ -280,7 +297,11 @@ __device__ __noinline__ void glide_row_out(int m_mode, float m_a, float m_b, flo
   }
 }
 
-__global__ void __launch_bounds__(32 * kVoiceWarpsPerCta, 2) voice_bank_kernel(const VoiceArgs a)
+// Two instances: TIME = false (gate + pitch tiles, 7 warps per CTA, at most 128 registers so that two CTAs share an SM)
+// and TIME = true (a third tile for the elapsed-time row and the FP64 divide per frame; 4 warps per CTA, free to use
+// more registers).
+template <bool TIME>
+__global__ void __launch_bounds__(32 * (TIME ? kVoiceWarpsPerCtaTime : kVoiceWarpsPerCta), 2) voice_bank_kernel(const VoiceArgs a)
 {
   extern __shared__ __align__(16) float voice_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -290,7 +311,7 @@ __global__ void __launch_bounds__(32 * kVoiceWarpsPerCta, 2) voice_bank_kernel(c
   const bool live = v_raw < a.V;
   const int v = live ? v_raw : a.V - 1;       // dead lanes shadow the last voice, their stores are masked
   const size_t V = (size_t)a.V;
-  const bool want_time = (a.row_mask & 128u) != 0;
+  constexpr bool want_time = TIME;  // == (a.row_mask & 128) != 0, the host picks the instance
   const int n_tiles = want_time ? 3 : 2;  // gate, pitch (+ elapsed time)
   float* const tiles = voice_smem + (size_t)warp * n_tiles * kVoiceTileFloats;
   float* const gate = tiles + lane * MLB_BLOCK;  // this lane's row, groups swizzled by l7

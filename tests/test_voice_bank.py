@@ -70,6 +70,29 @@ def test_gpu_voice_bank_bit_exact(gpu, port_bank, sr, V, T, seed, flags):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mask,flags", [(0x7F, 1), (0x7C, 0), (0x49, 1), (0x80, 0)])
+def test_gpu_voice_bank_row_masks(gpu, port_bank, mask, flags):
+    """The kernel instance without the elapsed-time row (two tiles, 7 warps per CTA) writing the glide-only rows,
+    with and without the MIDI pressure glide; rows that are not wanted still advance their glides (second call)."""
+    sr, V, T = 48000.0, 270, 60
+    ev = wl.voice_events(V, T, seed=31)
+    prm = wl.voice_bank_params(V)
+    want, _ = port_bank.run(sr, *prm, ev, flags=flags)
+    vb = gpu.VoiceBank(sr, *prm, flags=flags)
+    try:
+        a = vb.process_host(ev[:T // 2], row_mask=mask)
+        b = vb.process_host(ev[T // 2:])  # all rows: every glide must be where the reference's is
+    finally:
+        vb.close()
+    for r, name in enumerate(ROWS):
+        if mask & (1 << r):
+            assert_same_bits(a[:, r], want[:T // 2, r], "masked call, " + name)
+        else:
+            assert not a[:, r].any()
+        assert_same_bits(b[:, r], want[T // 2:, r], "following full call, " + name)
+
+
+@pytest.mark.gpu
 def test_gpu_voice_bank_matches_reference_golden_and_row_mask(gpu):
     g = np.load(GOLD)
     ev = g["events"].view(wl.VOICE_EVENTS_DTYPE).reshape(g["shape"][0], g["shape"][1])
