@@ -200,7 +200,7 @@ enum {
   /* HALFBAND_UP(x) = upsampleFirstHalf(x); HALFBAND_UP_2(in = that node) =              */ \
   /* upsampleSecondHalf(x) of the SAME filter (two rows at twice the rate);              */ \
   /* HALFBAND_DOWN(x1, x2) = downsample(x1, x2) (two rows in, one row out).              */ \
-  /* Upsample2xFunction(fn, x) (MLDSPFunctional.h:114-160) with a stateless fn is        */ \
+  /* Upsample2xFunction(fn, x) (MLDSPFunctional.h:114-160) is (fn's functors: MLB_AGAIN) */ \
   /* HALFBAND_DOWN(fn(HALFBAND_UP(x)), fn(HALFBAND_UP_2(x))).                            */ \
   X(HALFBAND_UP, 110, 1, 9, 0)                                                           \
   X(HALFBAND_UP_2, 111, 1, 0, 0)                                                         \
@@ -267,8 +267,21 @@ typedef enum mlb_op {
 typedef struct mlb_node {
   int32_t op;               /* mlb_op */
   int32_t in[MLB_MAX_INS];  /* producer node indices, -1 = unused */
-  int32_t iarg;             /* INPUT: external input plane index k */
+  int32_t iarg;             /* INPUT: external input plane index k; FEEDBACK_WRITE: its FEEDBACK_READ node;
+                               a functor node: 0, or MLB_AGAIN(t) (below) */
 } mlb_node;
+
+/* The same functor OBJECT called again in the same vector: a node with iarg = MLB_AGAIN(t) is a further call of
+ * the functor of the earlier node t (same op, itself not an AGAIN node) on other inputs.  It owns no state,
+ * coefficient or member-row words: it reads and writes those of node t, so the functor ticks once per call in node
+ * order -- what happens to the functors inside a process function that Upsample2xFunction runs twice per vector
+ * (MLDSPFunctional.h:114-160: fn(upsampled first half), fn(upsampled second half); the reference's tutorial wraps a
+ * sine generator this way, examples/tutorial/dspOpsExample.cpp:100-102).  Allowed for ops that have state or
+ * coefficients and no ring in delay memory (a ring's write index is the vector count, MLDSPFilters.h:836-851 run
+ * once per vector), and not for INPUT / PARAM / FEEDBACK_* / FDN8* / HALFBAND_* / DOWN2X_*.  Such graphs run on the
+ * graph interpreter; node t and its AGAIN nodes are kept in one pipeline stage. */
+#define MLB_AGAIN(t) (-1 - (t))
+#define MLB_AGAIN_TARGET(iarg) (-1 - (iarg))
 
 /* Word offsets of every node inside the state / coef SoA. */
 typedef struct mlb_layout {

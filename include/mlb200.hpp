@@ -13,6 +13,7 @@
 #include <array>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -468,6 +469,54 @@ inline DSPVectorArrayInt<ROWS> addInt32(const DSPVectorArrayInt<ROWS>& a, const 
 template <size_t ROWS>
 inline DSPVectorArrayInt<ROWS> subtractInt32(const DSPVectorArrayInt<ROWS>& a, const DSPVectorArrayInt<ROWS>& b) { return a - b; }
 
+// ---- map: the higher-order helpers of MLDSPFunctional.h:23-100.  The argument is an arbitrary host function,
+// so these are plain host loops by nature (element forms) or one call per row (row forms; the row function itself
+// may well be made of the GPU-backed operators above). ----
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> map(std::function<float()> f, const DSPVectorArray<ROWS>& /*shape only*/)
+{
+  DSPVectorArray<ROWS> y;
+  for (size_t n = 0; n < kFloatsPerDSPVector * ROWS; ++n) y[n] = f();
+  return y;
+}
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> map(std::function<float(float)> f, const DSPVectorArray<ROWS>& x)
+{
+  DSPVectorArray<ROWS> y;
+  for (size_t n = 0; n < kFloatsPerDSPVector * ROWS; ++n) y[n] = f(x[n]);
+  return y;
+}
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> map(std::function<float(int)> f, const DSPVectorArrayInt<ROWS>& x)
+{
+  DSPVectorArray<ROWS> y;
+  for (size_t n = 0; n < kFloatsPerDSPVector * ROWS; ++n) y[n] = f(x[(int)n]);
+  return y;
+}
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> map(std::function<DSPVector(const DSPVector)> f, const DSPVectorArray<ROWS>& x)
+{
+  DSPVectorArray<ROWS> y;
+  for (size_t j = 0; j < ROWS; ++j) y.row((int)j) = f(x.constRow((int)j));
+  return y;
+}
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> map(std::function<DSPVector(const DSPVector, int)> f, const DSPVectorArray<ROWS>& x)
+{
+  DSPVectorArray<ROWS> y;
+  for (size_t j = 0; j < ROWS; ++j) y.row((int)j) = f(x.constRow((int)j), (int)j);
+  return y;
+}
+// the reference's sixth overload hands the row INDEX to a (DSPVector, DSPVector) function: the index arrives
+// broadcast, as DSPVector(float(j)) (MLDSPFunctional.h:90-100)
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> map(std::function<DSPVector(const DSPVector, const DSPVector)> f, const DSPVectorArray<ROWS>& x)
+{
+  DSPVectorArray<ROWS> y;
+  for (size_t j = 0; j < ROWS; ++j) y.row((int)j) = f(x.constRow((int)j), DSPVector((float)j));
+  return y;
+}
+
 // ---- Graph: a fixed DAG of functors, built in the reference's functional style ----
 class Graph
 {
@@ -520,6 +569,9 @@ class Graph
   // a DSPVector member kept between processVector calls: read now, write at the end of the vector
   Sig feedbackRead() { return add(MLB_OP_FEEDBACK_READ); }
   Sig feedbackWrite(Sig reader, Sig x) { return add(MLB_OP_FEEDBACK_WRITE, x, -1, -1, reader); }
+  // the functor of node `first` called once more in the same vector, on other inputs (MLB_AGAIN in mlb200.h): it shares
+  // that node's state and coefficients -- e.g. the functors of a process function that Upsample2xFunction runs twice
+  Sig again(Sig first, Sig a = -1, Sig b = -1, Sig c = -1) { return add(nodes_[(size_t)first].op, a, b, c, MLB_AGAIN(first)); }
   Sig op1(int op, Sig x) { return add(op, x); }
   Sig op2(int op, Sig a, Sig b) { return add(op, a, b); }
   Sig op3(int op, Sig a, Sig b, Sig c) { return add(op, a, b, c); }

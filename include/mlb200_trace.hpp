@@ -32,6 +32,10 @@
 // that it can be set per instance afterwards.  Coefficient design (makeCoeffs) runs on the host through
 // mlb_coeffs_* = the reference's own libm calls.
 //
+// A functor object records ONE node per vector.  The exception is the process function handed to
+// Upsample2xFunction<N> (MLDSPFunctional.h:114-160), which the wrapper runs twice: the functors inside it are called a
+// second time, and record MLB_AGAIN nodes (mlb200.h) -- further calls of the same functor, same state.
+//
 // Header only; link against libmlb200.so.  No sample arithmetic happens on the CPU here.
 #pragma once
 #include <array>
@@ -75,6 +79,11 @@ class Recorder
   std::map<int, int> opIndexToNode;    // this pass
   std::map<int, int> feedbackReaders;  // stale opIndex -> FEEDBACK_READ node of this pass
   bool active = false;
+  // a functor object called AGAIN in the same vector (allowed inside the second run of a process function by
+  // Upsample2xFunction): its next node becomes a further call of its first one (MLB_AGAIN in mlb200.h)
+  int repeatDepth = 0;
+  int pendingAgain = -1;        // node of the functor's first call in this pass
+  int* pendingOwner = nullptr;  // where a functor's first call wants its node index written
 
   static Recorder*& current()
   {
@@ -95,6 +104,7 @@ class Recorder
     opCounter = 0;
     opIndexToNode.clear();
     feedbackReaders.clear();
+    repeatDepth = 0, pendingAgain = -1, pendingOwner = nullptr;
     active = true;
   }
   int addNode(int op, std::initializer_list<int> ins, int iarg = 0, bool userOp = true)
@@ -110,6 +120,18 @@ class Recorder
     t.node.iarg = iarg;
     t.coef.assign((size_t)nco, 0.f);
     t.state.assign((size_t)nst, 0u);
+    if (userOp && (nst > 0 || nco > 0) && (pendingOwner || pendingAgain >= 0))  // the node of the functor that just said once()
+    {
+      if (pendingAgain >= 0)
+      {
+        if (nodes[(size_t)pendingAgain].node.op != op)
+          throw Error(MLB_ERR_UNSUPPORTED, "mlb::tr: a functor called again in a vector recorded a different operation");
+        t.node.iarg = MLB_AGAIN(pendingAgain);
+      }
+      else
+        *pendingOwner = (int)nodes.size();
+      pendingAgain = -1, pendingOwner = nullptr;
+    }
     if (userOp)
     {
       t.opIndex = opCounter++;
@@ -283,11 +305,22 @@ class Functor
 {
  protected:
   int lastEpoch_ = 0;
+  int firstNode_ = -1;  // the node this object recorded when it was first called in the current pass
   void once()
   {
     Recorder& r = Recorder::get();
-    if (lastEpoch_ == r.epoch) throw Error(MLB_ERR_UNSUPPORTED, "mlb::tr: a functor object may be called once per vector");
+    if (lastEpoch_ == r.epoch)
+    {
+      // called again in the same vector: only inside the second run of a process function by Upsample2xFunction,
+      // where the reference object would simply tick a second time (MLDSPFunctional.h:138-140)
+      if (r.repeatDepth == 0 || firstNode_ < 0)
+        throw Error(MLB_ERR_UNSUPPORTED, "mlb::tr: a functor object may be called once per vector");
+      r.pendingAgain = firstNode_, r.pendingOwner = nullptr;
+      return;
+    }
     lastEpoch_ = r.epoch;
+    firstNode_ = -1;
+    r.pendingOwner = &firstNode_, r.pendingAgain = -1;
   }
   static TNode& nodeOf(const DSPVector& d) { return Recorder::get().nodes[(size_t)d.node]; }
 };
@@ -806,6 +839,54 @@ class Bank
   }
 };
 
+// Upsample2xFunction<IN_ROWS>, MLDSPFunctional.h:114-160: the input rows upsampled by two half-band filters, the
+// process function run on BOTH halves, the two results downsampled to one row.  The functors inside fn are called
+// twice per vector, as in the reference (the second call records MLB_AGAIN nodes: same state, ticked again);
+// functors with a delay ring cannot be (the graph is then rejected when it is compiled).
+template <int IN_ROWS>
+class Upsample2xFunction : public Functor
+{
+  using inputType = DSPVectorArray<(size_t)IN_ROWS>;
+  using ProcessFn = std::function<DSPVector(const inputType)>;
+
+ public:
+  DSPVector operator()(ProcessFn fn, const inputType& vx)
+  {
+    once();  // the wrapper's own half-band filters are one-per-vector objects like any functor
+    Recorder& r = Recorder::get();
+    r.pendingOwner = nullptr, r.pendingAgain = -1;  // (its nodes are recorded here, not through a functor member)
+    inputType first, second;
+    for (int j = 0; j < IN_ROWS; ++j)
+    {
+      DSPVector up = op1(MLB_OP_HALFBAND_UP, vx.constRow(j));  // mUppers[j].upsampleFirstHalf
+      first.row(j) = up;
+      second.row(j) = DSPVector::ofNode(r.addNode(MLB_OP_HALFBAND_UP_2, {up.node}));  // ... upsampleSecondHalf
+    }
+    const DSPVector y1 = fn(first);
+    ++r.repeatDepth;
+    DSPVector y2;
+    try
+    {
+      y2 = fn(second);
+    }
+    catch (...)
+    {
+      --r.repeatDepth;
+      throw;
+    }
+    --r.repeatDepth;
+    return op2(MLB_OP_HALFBAND_DOWN, y1, y2);  // mDowners[0].downsample
+  }
+  // the one-row form: upper(fn, x) with DSPVector in and out (dspOpsExample.cpp:100-102)
+  template <int R = IN_ROWS, typename = typename std::enable_if<R == 1>::type>
+  DSPVector operator()(std::function<DSPVector(const DSPVector)> fn, const DSPVector& x)
+  {
+    inputType in;
+    in.row(0) = x;
+    return (*this)([&](const inputType a) { return fn(a.constRow(0)); }, in);
+  }
+};
+
 // ---- scalar host helpers the examples use (MLDSPProjections.h:15-23,105-123,176-195) ----
 struct Interval
 {
@@ -947,6 +1028,10 @@ class TracedProcessor
   size_t inputs() const { return nIn_; }
   size_t outputs() const { return nOut_; }
 
+  static bool isAgain(const mlb_node& n)
+  {
+    return n.iarg < 0 && n.op != MLB_OP_INPUT && n.op != MLB_OP_PARAM && n.op != MLB_OP_FEEDBACK_WRITE;
+  }
   // Write the traced graph as JSON (nodes, outs, initial coefficient and state words): lets a test or a tool
   // rebuild it elsewhere (tests/test_trace.py feeds it to the CPU checkers).
   void dump(FILE* f) const
@@ -958,14 +1043,15 @@ class TracedProcessor
       std::fprintf(f, "%s{\"op\": %d, \"in\": [", i ? ", " : "", t.node.op);
       for (int k = 0; k < MLB_MAX_INS; ++k) std::fprintf(f, "%s%d", k ? ", " : "", t.node.in[k]);
       std::fprintf(f, "], \"iarg\": %d, \"coef\": [", t.node.iarg);
-      for (size_t k = 0; k < t.coef.size(); ++k)
+      const bool again = isAgain(t.node);  // a further call of an earlier functor owns no words
+      for (size_t k = 0; k < t.coef.size() && !again; ++k)
       {
         uint32_t u;
         std::memcpy(&u, &t.coef[k], 4);
         std::fprintf(f, "%s%u", k ? ", " : "", u);  // bit patterns: exact round trip
       }
       std::fprintf(f, "], \"state\": [");
-      for (size_t k = 0; k < t.state.size(); ++k) std::fprintf(f, "%s%u", k ? ", " : "", t.state[k]);
+      for (size_t k = 0; k < t.state.size() && !again; ++k) std::fprintf(f, "%s%u", k ? ", " : "", t.state[k]);
       std::fprintf(f, "], \"name\": \"%s\"}", t.name.c_str());
     }
     std::fprintf(f, "], \"outs\": [");
@@ -985,6 +1071,7 @@ class TracedProcessor
     for (size_t i = 0; i < rec_.nodes.size(); ++i)
     {
       const TNode& t = rec_.nodes[i];
+      if (isAgain(t.node)) continue;  // the words belong to the functor's first call
       for (size_t k = 0; k < t.coef.size(); ++k)
         for (int v = 0; v < instances; ++v) coef_[(size_t)(coOff_[i] + (int)k) * instances + v] = t.coef[k];
       for (size_t k = 0; k < t.state.size(); ++k)

@@ -87,6 +87,33 @@ extern "C" const char* mlb_op_name(int op)
   return "?";
 }
 
+// delay memory of an op: 64-float member rows and IntegerDelay rings per voice (MLB_OP_MEM_TABLE)
+static void op_mem(int op, int* n_rows, int* n_rings);
+
+// MLB_AGAIN (mlb200.h): may a node of this op be a further call of an earlier functor?
+static bool again_allowed(int op)
+{
+  int nin = 0, nst = 0, nco = 0, rows = 0, rings = 0;
+  if (mlb_op_info(op, &nin, &nst, &nco) != MLB_OK) return false;
+  op_mem(op, &rows, &rings);
+  if (rings != 0 || (nst == 0 && nco == 0)) return false;
+  switch (op)
+  {
+    case MLB_OP_INPUT: case MLB_OP_PARAM: case MLB_OP_FEEDBACK_READ: case MLB_OP_FEEDBACK_WRITE: case MLB_OP_FDN8:
+    case MLB_OP_FDN8_R: case MLB_OP_HALFBAND_UP: case MLB_OP_HALFBAND_UP_2: case MLB_OP_HALFBAND_DOWN:
+    case MLB_OP_DOWN2X_IN: case MLB_OP_DOWN2X_OUT:
+      return false;
+    default: return true;
+  }
+}
+// the node whose functor node i calls again, or -1
+static int again_target(const mlb_node* nodes, int i)
+{
+  const int op = nodes[i].op;
+  if (op == MLB_OP_INPUT || op == MLB_OP_PARAM || op == MLB_OP_FEEDBACK_WRITE) return -1;  // iarg has its own meaning / none
+  return nodes[i].iarg < 0 ? MLB_AGAIN_TARGET(nodes[i].iarg) : -1;
+}
+
 extern "C" int mlb_graph_layout(const mlb_node* nodes, int n_nodes, mlb_layout* layout,
                                 int32_t* state_off, int32_t* coef_off)
 {
@@ -129,6 +156,20 @@ extern "C" int mlb_graph_layout(const mlb_node* nodes, int n_nodes, mlb_layout* 
       for (int q = 0; q < i; ++q)
         if (nodes[q].op == MLB_OP_FEEDBACK_WRITE && nodes[q].iarg == rd)
           return fail(MLB_ERR_INVALID, "node %d: FEEDBACK_READ %d already has a FEEDBACK_WRITE (node %d)", i, rd, q);
+    }
+    const int again = again_target(nodes, i);
+    if (again >= 0)
+    {
+      if (!again_allowed(nodes[i].op))
+        return fail(MLB_ERR_INVALID, "node %d (%s): iarg %d -- this op cannot be called again in a vector (MLB_AGAIN)", i,
+                    mlb_op_name(nodes[i].op), nodes[i].iarg);
+      if (again >= i || nodes[again].op != nodes[i].op || again_target(nodes, again) >= 0)
+        return fail(MLB_ERR_INVALID, "node %d (%s): MLB_AGAIN(%d) must name an earlier node of the same op that is not "
+                    "itself an AGAIN node", i, mlb_op_name(nodes[i].op), again);
+      // a further call of node `again`: its words, no words of its own
+      if (state_off) state_off[i] = state_off[again];
+      if (coef_off) coef_off[i] = coef_off[again];
+      continue;
     }
     if (state_off) state_off[i] = ns;
     if (coef_off) coef_off[i] = nc;
@@ -722,8 +763,10 @@ static bool is_gen1(int op)
 }
 
 // Recognise  out = [gain *] F2( F1( GEN(src) ) )  and fill g->cargs index maps.
+static bool has_again_nodes(const mlb_graph* g);
 static bool match_fused_chain(mlb_graph* g)
 {
+  if (has_again_nodes(g)) return false;  // a functor called twice per vector: interpreter only
   if (g->outs.size() != 1) return false;
   const auto& N = g->nodes;
   std::vector<char> used(N.size(), 0);
@@ -835,6 +878,12 @@ static bool match_fused_chain(mlb_graph* g)
   return false;
 }
 
+static bool has_again_nodes(const mlb_graph* g)
+{
+  for (int i = 0; i < (int)g->nodes.size(); ++i)
+    if (again_target(g->nodes.data(), i) >= 0) return true;
+  return false;
+}
 static int env_int(const char* name, int dflt);
 // ops with two output rows (the second is read through the paired *_R / *_2 op)
 static bool is_dual(int op) { return op == MLB_OP_FDN8 || op == MLB_OP_HALFBAND_UP; }
@@ -921,6 +970,10 @@ static int build_generic(mlb_graph* g)
       for (int i = N[q].iarg; i < q; ++i) no_cut[i] = 1;
     if (is_second(N[q].op))  // FDN8_R / HALFBAND_UP_2 alias the second row of their producer: same stage
       for (int i = N[q].in[0]; i < q; ++i) no_cut[i] = 1;
+    // MLB_AGAIN: the calls of one functor share its state words, which a node loads and stores once per vector --
+    // they must run in node order inside one CTA
+    if (again_target(N.data(), q) >= 0)
+      for (int i = again_target(N.data(), q); i < q; ++i) no_cut[i] = 1;
   }
   std::vector<int> stage_of(n, 0);
   {
@@ -1222,7 +1275,7 @@ extern "C" int mlb_graph_create(const mlb_node* nodes, int n_nodes, const int32_
   {
     matched = match_fused_chain(g);
     if (matched) g->kind = KIND_FUSED;
-    if (!matched && match_fm3_fdn8(g->nodes, g->outs, g->st_off, g->co_off, &g->fargs))
+    if (!matched && !has_again_nodes(g) && match_fm3_fdn8(g->nodes, g->outs, g->st_off, g->co_off, &g->fargs))
     {
       matched = true;
       g->kind = KIND_FDN;
@@ -1362,6 +1415,11 @@ static int size_functor_memory(mlb_graph* g)
     const int op = g->nodes[i].op;
     op_mem(op, &rows, &rings);
     mlb_op_info(op, nullptr, nullptr, &nco);
+    if (again_target(g->nodes.data(), i) >= 0)  // MLB_AGAIN: the member row of the functor's first call (no rings, by rule)
+    {
+      row_off[i] = row_off[again_target(g->nodes.data(), i)];
+      continue;
+    }
     if (rows)
     {
       row_off[i] = total;

@@ -104,6 +104,19 @@ class GraphSpec:
     def node(self, name: str, *inputs: int) -> int:
         return self._add(name.upper(), *inputs)
 
+    def again(self, target: int, *inputs: int) -> int:
+        """The functor of node `target` called once more in the same vector, on other inputs (MLB_AGAIN in mlb200.h:
+        what happens to the functors of a process function that Upsample2xFunction runs twice per vector)."""
+        if not (0 <= target < len(self.ops)) or self.again_target(target) >= 0:
+            raise ValueError("again: target must be an earlier node that is not itself an `again` node")
+        return self._add(OP_NAME[self.ops[target]], *inputs, iarg=-1 - target)
+
+    def again_target(self, node: int) -> int:
+        """The node whose functor `node` calls again, or -1."""
+        if OP_NAME[self.ops[node]] in ("INPUT", "PARAM", "FEEDBACK_WRITE") or self.iargs[node] >= 0:
+            return -1
+        return -1 - self.iargs[node]
+
     def feedback_read(self) -> int:
         """The row stored by `feedback_write` on the previous block (zeros at start)."""
         return self._add("FEEDBACK_READ")
@@ -133,7 +146,12 @@ class GraphSpec:
 
     def offsets(self) -> Tuple[List[int], List[int], int, int]:
         st, co, ns, nc = [], [], 0, 0
-        for op in self.ops:
+        for i, op in enumerate(self.ops):
+            t = self.again_target(i)
+            if t >= 0:  # a further call of node t's functor: its words, none of its own
+                st.append(st[t])
+                co.append(co[t])
+                continue
             st.append(ns)
             co.append(nc)
             ns += OP_INFO[op][1]

@@ -340,6 +340,24 @@ def functor_case(name: str, n_voices: int = 40) -> Workload:
             coef[0] = (np.float32(0.5) + vv / np.float32(V) * np.float32(3.0)).astype(np.float32)
             coef[1], coef[2] = np.float32(-1.0), np.float32(1.0)
         fn = noise
+    elif name == "upsample2x_osc":
+        # Upsample2xFunction<1> with a STATEFUL process function, fn(v) = lp(osc(v * 0.5)): the SineGen and the
+        # Lopass are called twice per vector (MLB_AGAIN), as in the reference's tutorial
+        # (examples/tutorial/dspOpsExample.cpp:100-102 wraps a sine generator this way)
+        x = g.input(0)
+        up1 = g.node("HALFBAND_UP", x)
+        up2 = g.node("HALFBAND_UP_2", up1)
+        half = g.param()
+        s1 = g.node("SINE", g.node("MULTIPLY", up1, half))
+        l1 = g.node("LOPASS", s1)
+        s2 = g.again(s1, g.node("MULTIPLY", up2, half))
+        l2 = g.again(l1, s2)
+        g.output(g.node("HALFBAND_DOWN", l1, l2))
+        coef, state = g.new_coefs(V), g.new_state(V)
+        coef[g.coef_slot(half)] = np.float32(0.5)
+        _set(coef, g, l1, _svf_coefs("lopass", V))
+        state[g.state_slot(s1)] = SINE_ZERO_PHASE
+        fn = lambda T, t0: freq_rows(V, T, t0, 0, V)
     elif name == "downsample2x_clip":
         # Downsample2xFunction with the stateless fn(v) = clamp(v * drive, -1, 1) (MLDSPFunctional.h:166-223)
         x = g.input(0)
@@ -394,7 +412,7 @@ def functor_case(name: str, n_voices: int = 40) -> Workload:
 FUNCTOR_CASES = ("impulse", "oneshot", "peak", "rms", "adsr", "allpass1", "glide", "interpolator1", "sample_glide",
                  "integer_delay", "integer_delay_var", "fractional_delay", "fractional_delay_var",
                  "pitchbend_delay", "allpass_int", "allpass_frac", "allpass_pb", "feedback",
-                 "halfband_up", "halfband_roundtrip", "upsample2x_clip", "downsample2x_clip", "tempo_lock")
+                 "halfband_up", "halfband_roundtrip", "upsample2x_clip", "upsample2x_osc", "downsample2x_clip", "tempo_lock")
 
 
 def aaltoverb_feedback(size_u: float, decay_u: float) -> float:
@@ -636,10 +654,13 @@ def synth_events(n_voices: int, n_blocks: int, seed: int = 2, density: float = 0
 
 # ---- random voice graphs (tests): any DAG of the op table, for checker-vs-checker and GPU-vs-checker runs ----
 
-def random_graph_workload(seed: int, n_voices: int = 37, n_nodes: int = 24, hw_approx: bool = True) -> Workload:
+def random_graph_workload(seed: int, n_voices: int = 37, n_nodes: int = 24, hw_approx: bool = True,
+                          again_prob: float = 0.0) -> Workload:
     """A random DAG over most of the op table (generators, filters, functors with delay memory, elementwise
     ops), two external input planes, random but sane coefficients; two outputs.  hw_approx=False leaves out
-    Peak / RMS, whose outputs go through the CPU-defined rsqrt approximation (compared with a tolerance only)."""
+    Peak / RMS, whose outputs go through the CPU-defined rsqrt approximation (compared with a tolerance only).
+    again_prob > 0: generators, filters and glides are, with that probability, called AGAIN in the same vector on
+    other inputs (MLB_AGAIN; the default 0 leaves the graphs of a seed as they always were)."""
     from .graph import OP_INFO, OP_NAME
     rng = np.random.default_rng(seed)
     V = n_voices
@@ -683,6 +704,13 @@ def random_graph_workload(seed: int, n_voices: int = 37, n_nodes: int = 24, hw_a
             y = g.node(delays2[int(rng.integers(len(delays2)))], pick(False), rows[1])
         node_kind[y] = OP_NAME[g.ops[y]]
         rows.append(y)
+        name = node_kind[y]
+        if again_prob and (name in filt or name in gens or name in ("GLIDE", "INTERPOLATOR1")) and \
+                rng.random() < again_prob:
+            if name in gens:
+                rows.append(g.again(y, rows[1] if rng.random() < 0.5 else params[0]))
+            else:
+                rows.append(g.again(y, pick(False)))
     if fb is not None:
         g.feedback_write(fb, g.node("MULTIPLY", rows[-1], params[1]))
     g.output(rows[-1], rows[len(rows) // 2])

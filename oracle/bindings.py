@@ -185,6 +185,15 @@ class RefOracle(_Oracle):
         self.lib.mlref_kitchen(inp.shape[0], _ptr(inp), _ptr(out))
         return out
 
+    def upsample_body(self, inp: np.ndarray) -> np.ndarray:
+        """tests/cpp/upsample_body.h compiled against the reference (one instance); inp [T][2][64] -> [T][1][64]."""
+        inp = np.ascontiguousarray(inp, np.float32)
+        out = np.empty((inp.shape[0], 1, 64), np.float32)
+        self.lib.mlref_upsample_body.argtypes = [ctypes.c_int, _vp, _vp]
+        self.lib.mlref_upsample_body.restype = None
+        self.lib.mlref_upsample_body(inp.shape[0], _ptr(inp), _ptr(out))
+        return out
+
     def upsample2x_clip(self, inp: np.ndarray, drive: float) -> np.ndarray:
         """Upsample2xFunction<1> with fn = clamp(v * drive, -1, 1) for ONE voice; inp [T][64]."""
         inp = np.ascontiguousarray(inp, np.float32)
@@ -192,6 +201,17 @@ class RefOracle(_Oracle):
         self.lib.mlref_upsample2x_clip.argtypes = [ctypes.c_int, _vp, _vp, ctypes.c_float]
         self.lib.mlref_upsample2x_clip.restype = None
         self.lib.mlref_upsample2x_clip(inp.shape[0], _ptr(inp), _ptr(out), drive)
+        return out
+
+    def upsample2x_osc(self, inp: np.ndarray, phase0: int, g3) -> np.ndarray:
+        """Upsample2xFunction<1> with the STATEFUL fn = lp(osc(v * 0.5)) (the reference's SineGen and Lopass called
+        twice per vector) for ONE voice; inp [T][64]."""
+        inp = np.ascontiguousarray(inp, np.float32)
+        g3 = np.ascontiguousarray(g3, np.float32)
+        out = np.empty_like(inp)
+        self.lib.mlref_upsample2x_osc.argtypes = [ctypes.c_int, _vp, _vp, ctypes.c_uint32, _vp]
+        self.lib.mlref_upsample2x_osc.restype = None
+        self.lib.mlref_upsample2x_osc(inp.shape[0], _ptr(inp), _ptr(out), int(phase0), _ptr(g3))
         return out
 
     def downsample2x_clip(self, inp: np.ndarray, drive: float) -> np.ndarray:

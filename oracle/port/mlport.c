@@ -1273,6 +1273,7 @@ typedef struct mlport_graph
   float* coef;     /* [n_coef][V] */
   fdn8_mem** fdn;  /* [n_nodes] -> array of V, or NULL */
   delay_mem** dmem; /* [n_nodes] -> array of V, or NULL */
+  int* again;      /* [n_nodes]: MLB_AGAIN target (the node whose words and member rows this node uses), or -1 */
 } mlport_graph;
 
 int mlport_abi_version(void) { return MLB_ABI_VERSION; }
@@ -1293,7 +1294,7 @@ void mlport_graph_destroy(mlport_graph* g)
   if (g->dmem)
   {
     for (int i = 0; i < g->n_nodes; ++i)
-      if (g->dmem[i])
+      if (g->dmem[i] && !(g->again && g->again[i] >= 0))
       {
         for (int v = 0; v < g->V; ++v) free(g->dmem[i][v].ring[0]), free(g->dmem[i][v].ring[1]);
         free(g->dmem[i]);
@@ -1304,6 +1305,7 @@ void mlport_graph_destroy(mlport_graph* g)
   free(g->outs);
   free(g->st_off);
   free(g->co_off);
+  free(g->again);
   free(g->state);
   free(g->coef);
   free(g);
@@ -1324,6 +1326,7 @@ mlport_graph* mlport_graph_create(const mlb_node* nodes, int n_nodes, const int3
   g->co_off = (int*)calloc((size_t)n_nodes, sizeof(int));
   g->fdn = (fdn8_mem**)calloc((size_t)n_nodes, sizeof(fdn8_mem*));
   g->dmem = (delay_mem**)calloc((size_t)n_nodes, sizeof(delay_mem*));
+  g->again = (int*)calloc((size_t)n_nodes, sizeof(int));
   for (int i = 0; i < n_nodes; ++i)
   {
     int a, b, c;
@@ -1331,6 +1334,25 @@ mlport_graph* mlport_graph_create(const mlb_node* nodes, int n_nodes, const int3
     {
       mlport_graph_destroy(g);
       return NULL;
+    }
+    /* MLB_AGAIN (mlb200.h): a further call of an earlier functor in the same vector uses that node's words */
+    g->again[i] = -1;
+    if (nodes[i].iarg < 0 && nodes[i].op != MLB_OP_INPUT && nodes[i].op != MLB_OP_PARAM &&
+        nodes[i].op != MLB_OP_FEEDBACK_WRITE)
+    {
+      const int t = MLB_AGAIN_TARGET(nodes[i].iarg);
+      const int op = nodes[i].op;
+      if (t >= i || nodes[t].op != op || g->again[t] >= 0 || (b == 0 && c == 0) || op == MLB_OP_FEEDBACK_READ ||
+          op == MLB_OP_FDN8 || op == MLB_OP_FDN8_R || op == MLB_OP_HALFBAND_UP || op == MLB_OP_HALFBAND_UP_2 ||
+          op == MLB_OP_HALFBAND_DOWN || op == MLB_OP_DOWN2X_IN || op == MLB_OP_DOWN2X_OUT)
+      {
+        mlport_graph_destroy(g);
+        return NULL;
+      }
+      g->again[i] = t;
+      g->st_off[i] = g->st_off[t];
+      g->co_off[i] = g->co_off[t];
+      continue;
     }
     g->st_off[i] = g->n_state;
     g->co_off[i] = g->n_coef;
@@ -1376,6 +1398,16 @@ mlport_graph* mlport_graph_create(const mlb_node* nodes, int n_nodes, const int3
       default: break;
     }
     if (n_rows == 0 && n_rings == 0) continue;
+    if (g->again[i] >= 0)
+    {
+      if (n_rings)  /* a ring's write index is the vector count: such a functor cannot tick twice per vector */
+      {
+        mlport_graph_destroy(g);
+        return NULL;
+      }
+      g->dmem[i] = g->dmem[g->again[i]];  /* the functor's member row */
+      continue;
+    }
     g->dmem[i] = (delay_mem*)calloc((size_t)V, sizeof(delay_mem));
     int a, b, nco;
     op_info(nodes[i].op, &a, &b, &nco);

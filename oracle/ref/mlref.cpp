@@ -751,6 +751,7 @@ struct Graph
   std::vector<mlb_node> nodes;
   std::vector<int> outs;
   std::vector<int> stOff, coOff;
+  std::vector<int> again;  // MLB_AGAIN target per node (the node whose functor OBJECT this node calls once more), or -1
   int nState{0}, nCoef{0}, nIn{0}, V{0};
   // procs[v][node]
   std::vector<std::vector<std::unique_ptr<Proc>>> procs;
@@ -777,6 +778,7 @@ mlref_graph* mlref_graph_create(const mlb_node* nodes, int n_nodes, const int32_
   g.V = V;
   g.stOff.resize(n_nodes);
   g.coOff.resize(n_nodes);
+  g.again.assign(n_nodes, -1);
   for (int i = 0; i < n_nodes; ++i)
   {
     OpInfo oi;
@@ -784,6 +786,21 @@ mlref_graph* mlref_graph_create(const mlb_node* nodes, int n_nodes, const int32_
     {
       delete h;
       return nullptr;
+    }
+    // MLB_AGAIN (mlb200.h): the same reference functor object is simply called again -- no second object
+    if (nodes[i].iarg < 0 && nodes[i].op != MLB_OP_INPUT && nodes[i].op != MLB_OP_PARAM &&
+        nodes[i].op != MLB_OP_FEEDBACK_WRITE)
+    {
+      const int t = MLB_AGAIN_TARGET(nodes[i].iarg);
+      if (t >= i || nodes[t].op != nodes[i].op || g.again[t] >= 0 || (oi.nst == 0 && oi.nco == 0))
+      {
+        delete h;
+        return nullptr;
+      }
+      g.again[i] = t;
+      g.stOff[i] = g.stOff[t];
+      g.coOff[i] = g.coOff[t];
+      continue;
     }
     g.stOff[i] = g.nState;
     g.coOff[i] = g.nCoef;
@@ -806,6 +823,7 @@ mlref_graph* mlref_graph_create(const mlb_node* nodes, int n_nodes, const int32_
     {
       OpInfo oi;
       opInfo(nodes[i].op, oi);
+      if (g.again[i] >= 0) continue;  // no object of its own
       g.procs[v][i].reset(makeProc(nodes[i].op));
       if (g.procs[v][i] && oi.nco > 0)
       {
@@ -902,7 +920,7 @@ void mlref_graph_process(mlref_graph* h, const float* in, float* out, float* mix
           const DSPVector* ins[MLB_MAX_INS] = {};
           for (int k = 0; k < MLB_MAX_INS; ++k)
             if (nd.in[k] >= 0) ins[k] = &rows[nd.in[k]];
-          rows[i] = g.procs[v][i]->run(ins, &rows2[i]);
+          rows[i] = g.procs[v][g.again[i] >= 0 ? g.again[i] : i]->run(ins, &rows2[i]);
         }
         if (o)
           for (int c = 0; c < nOut; ++c)
@@ -1198,6 +1216,35 @@ void mlref_kitchen(int T, const float* in, float* out)
   }
 }
 
+// ---- tests/cpp/upsample_body.h compiled against the reference itself (the tracing layer compiles the same file):
+// a process function with state run at twice the rate by Upsample2xFunction<1>.  One instance; in [T][2][64]
+// (frequency, gate rows), out [T][64].
+}  // extern "C"
+namespace upsample_ref
+{
+using namespace ml;
+#include "../../tests/cpp/upsample_body.h"
+struct Ctx
+{
+  DSPVectorDynamic inputs{2}, outputs{1};
+};
+}  // namespace upsample_ref
+extern "C"
+{
+void mlref_upsample_body(int T, const float* in, float* out)
+{
+  upsample_ref::UpsampleState st;
+  upsample_ref::upsampleInit(st);
+  upsample_ref::Ctx ctx;
+  for (int t = 0; t < T; ++t)
+  {
+    ctx.inputs[0] = DSPVector(in + (size_t)t * 128);
+    ctx.inputs[1] = DSPVector(in + (size_t)t * 128 + 64);
+    upsample_ref::upsampleProcess(&ctx, &st);
+    store(ctx.outputs[0], out + (size_t)t * 64);
+  }
+}
+
 // ---- Upsample2xFunction<1> (MLDSPFunctional.h:114-160) called as a user would, with the stateless
 // process function fn(v) = clamp(v * drive, -1, 1).  One voice; in/out [T][64].  Checks that the
 // HALFBAND_UP / HALFBAND_UP_2 / HALFBAND_DOWN graph of workloads.functor_case("upsample2x_clip") is
@@ -1209,6 +1256,26 @@ void mlref_upsample2x_clip(int T, const float* in, float* out, float drive)
   {
     DSPVector x(in + (size_t)t * 64);
     DSPVector y = upper([&](const DSPVector v) { return clamp(v * DSPVector(drive), DSPVector(-1.f), DSPVector(1.f)); }, x);
+    store(y, out + (size_t)t * 64);
+  }
+}
+
+// ---- Upsample2xFunction<1> with a STATEFUL process function, fn(v) = lp(osc(v * 0.5)): the reference's own
+// SineGen and Lopass objects, called twice per vector by the wrapper (MLDSPFunctional.h:138-140), as the tutorial
+// does with a sine generator (examples/tutorial/dspOpsExample.cpp:100-102).  One voice; in/out [T][64]; phase0 =
+// the SineGen's phasor word, g[3] = the Lopass coefficients.  What an MLB_AGAIN graph
+// (workloads.functor_case("upsample2x_osc")) must equal.
+void mlref_upsample2x_osc(int T, const float* in, float* out, uint32_t phase0, const float* g3)
+{
+  Upsample2xFunction<1> upper;
+  SineGen osc;
+  osc._phasor.clear(phase0);
+  Lopass lp;
+  lp.coeffs = {g3[0], g3[1], g3[2]};
+  for (int t = 0; t < T; ++t)
+  {
+    DSPVector x(in + (size_t)t * 64);
+    DSPVector y = upper([&](const DSPVector v) { return lp(osc(v * DSPVector(0.5f))); }, x);
     store(y, out + (size_t)t * 64);
   }
 }

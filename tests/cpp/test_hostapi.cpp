@@ -40,8 +40,48 @@ static float maxAbsDiff(const DSPVector& a, const DSPVector& b, const DSPVector*
   return m;
 }
 
+// host-only parts of the value types (no device needed): the map helpers of MLDSPFunctional.h:23-100,
+// as tests/DSPOpsTest.cpp uses them (map with a lambda == the loop it stands for)
+static int host_only_checks()
+{
+  int bad = 0;
+  DSPVectorArray<3> x;
+  for (size_t n = 0; n < 3 * kFloatsPerDSPVector; ++n) x[n] = 0.25f * (float)n - 7.f;
+  int calls = 0;
+  const auto counted = map<3>([&]() { return (float)calls++; }, x);
+  bad += !(calls == 3 * (int)kFloatsPerDSPVector && counted[5] == 5.f && counted[191] == 191.f);
+  const auto sq = map<3>([](float v) { return v * v; }, x);
+  for (size_t n = 0; n < 3 * kFloatsPerDSPVector; ++n) bad += !(sq[n] == x[n] * x[n]);
+  DSPVectorArrayInt<2> xi;
+  for (int n = 0; n < 2 * (int)kFloatsPerDSPVector; ++n) xi[n] = n - 3;
+  const auto half = map<2>([](int v) { return 0.5f * (float)v; }, xi);
+  bad += !(half[0] == -1.5f && half[127] == 62.f);
+  // row forms: a row function that needs no device (assignment and indexing only)
+  const auto rev = map<3>(std::function<DSPVector(const DSPVector)>([](const DSPVector r) {
+                            DSPVector y;
+                            for (size_t i = 0; i < kFloatsPerDSPVector; ++i) y[i] = r[kFloatsPerDSPVector - 1 - i];
+                            return y;
+                          }),
+                          x);
+  bad += !(rev[0] == x[63] && rev[64 + 10] == x[64 + 53] && rev[191] == x[128]);
+  const auto tagged = map<3>(std::function<DSPVector(const DSPVector, int)>([](const DSPVector r, int j) {
+                               DSPVector y(r);
+                               y[0] = (float)(100 + j);
+                               return y;
+                             }),
+                             x);
+  bad += !(tagged[0] == 100.f && tagged[64] == 101.f && tagged[128] == 102.f && tagged[129] == x[129]);
+  const auto idx = map<3>(std::function<DSPVector(const DSPVector, const DSPVector)>(
+                              [](const DSPVector, const DSPVector j) { return j; }),
+                          x);
+  bad += !(idx[7] == 0.f && idx[64 + 7] == 1.f && idx[191] == 2.f);
+  std::printf("host-only checks (map helpers): %s\n", bad ? "FAILED" : "ok");
+  return bad;
+}
+
 int main()
 {
+  if (host_only_checks()) return 1;
   if (mlb_device_count() < 1)
   {
     // no silent fallback: creating a bank must fail loudly

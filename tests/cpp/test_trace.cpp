@@ -4,7 +4,8 @@
 //   examples/audio-and-midi/reverb.cpp:12-124 (constants, unityToDecay, AaltoverbState, initializeReverb, processVector)
 // (their text is included from tests/cpp/_ref/*.inc, generated from the reference at build time, not committed),
 // plus the SURVEY 8c plumbing chain 0.5 * Lopass{0.1, 1.0}(SineGen.clear()(440/48000)), a swept shelf, and
-// tests/cpp/kitchen_body.h, which is also compiled against the reference itself.
+// tests/cpp/kitchen_body.h and tests/cpp/upsample_body.h (a stateful process function inside Upsample2xFunction<1>),
+// which are also compiled against the reference itself.
 //
 //   test_trace dump <case>                      trace only (no GPU needed), print the graph as JSON
 //   test_trace run <case> <instances> <blocks> <in.bin> <out.bin>
@@ -75,6 +76,19 @@ void shelfProcess(AudioContext* ctx, void* state)
 // ---------------------------------------------------------------- the shared body (also compiled against the reference)
 #include "kitchen_body.h"
 void kitchenProcessFn(AudioContext* ctx, void* state) { kitchenProcess(ctx, state); }
+// a process function with state inside Upsample2xFunction<1> (also compiled against the reference)
+#include "upsample_body.h"
+void upsampleProcessFn(AudioContext* ctx, void* state) { upsampleProcess(ctx, state); }
+// calling a functor twice per vector OUTSIDE an Upsample2xFunction stays an error
+struct TwiceState
+{
+  SineGen osc;
+};
+void twiceProcess(AudioContext* ctx, void* state)
+{
+  auto s = static_cast<TwiceState*>(state);
+  ctx->outputs[0] = s->osc(0.01f) + s->osc(0.02f);
+}
 
 struct Case
 {
@@ -87,7 +101,7 @@ int main(int argc, char** argv)
 {
   if (argc < 3)
   {
-    std::fprintf(stderr, "usage: test_trace dump|run|stream <sine|reverb|chain|shelf|kitchen> ...\n");
+    std::fprintf(stderr, "usage: test_trace dump|run|stream <sine|reverb|chain|shelf|kitchen|upsample|twice> ...\n");
     return 2;
   }
   const std::string mode = argv[1], which = argv[2];
@@ -103,6 +117,9 @@ int main(int argc, char** argv)
   shelf.noise.setSeed(7);
   KitchenState kitchen;
   kitchenInit(kitchen);
+  UpsampleState upsample;
+  upsampleInit(upsample);
+  TwiceState twice;
 
   size_t nIn = 0, nOut = 0;
   SignalProcessFn fn = nullptr;
@@ -120,6 +137,8 @@ int main(int argc, char** argv)
   if (which == "chain") nIn = 0, nOut = 1, fn = chainProcess, state = &chain;
   if (which == "shelf") nIn = 1, nOut = 1, fn = shelfProcess, state = &shelf;
   if (which == "kitchen") nIn = 2, nOut = 2, fn = kitchenProcessFn, state = &kitchen;
+  if (which == "upsample") nIn = 2, nOut = 1, fn = upsampleProcessFn, state = &upsample;
+  if (which == "twice") nIn = 0, nOut = 1, fn = twiceProcess, state = &twice;
   if (!fn) return 2;
   try
   {

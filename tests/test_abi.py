@@ -88,6 +88,56 @@ def test_validation_of_the_paired_and_feedback_nodes(L):
     assert L.mlb_graph_layout(bad, h.n_nodes, ctypes.byref(lay), None, None) == 1
 
 
+def test_again_nodes_share_the_words_of_their_functor(L):
+    """MLB_AGAIN: a further call of an earlier functor owns no words; the C layout, the Python layout and both oracles
+    agree; the rules of mlb200.h are enforced."""
+    from madronalib_b200 import workloads as wl
+    g = wl.functor_case("upsample2x_osc", 4).spec
+    n = g.n_nodes
+    lay = Layout()
+    so, co = (ctypes.c_int32 * n)(), (ctypes.c_int32 * n)()
+    assert L.mlb_graph_layout(g.c_nodes(), n, ctypes.byref(lay), so, co) == 0
+    st, cf, ns, nc = g.offsets()
+    assert list(so) == st and list(co) == cf and (lay.n_state_words, lay.n_coef_words) == (ns, nc) == (21, 4)
+    again = [i for i in range(n) if g.again_target(i) >= 0]
+    assert len(again) == 2 and all(so[i] == so[g.again_target(i)] and co[i] == co[g.again_target(i)] for i in again)
+
+    def rejects(edit, words):
+        bad = g.c_nodes()
+        edit(bad)
+        assert L.mlb_graph_layout(bad, n, ctypes.byref(lay), None, None) == 1
+        assert words in L.mlb_last_error(), L.mlb_last_error()
+
+    a = again[0]
+    rejects(lambda b: setattr(b[a], "iarg", -1 - a), b"earlier node")        # itself / a later node
+    rejects(lambda b: setattr(b[a], "iarg", -1 - 0), b"same op")             # node 0 is the INPUT
+    rejects(lambda b: setattr(b[again[1]], "iarg", -1 - again[0]), b"same op")
+    # an AGAIN node cannot be the target of another one
+    h = graph.GraphSpec()
+    x = h.input(0)
+    s1 = h.node("SINE", x)
+    s2 = h.again(s1, x)
+    with pytest.raises(ValueError):
+        h.again(s2, x)
+    bad = graph.GraphSpec()
+    bad.ops, bad.ins, bad.iargs = list(h.ops) + [h.ops[s1]], list(h.ins) + [h.ins[s1]], list(h.iargs) + [-1 - s2]
+    assert L.mlb_graph_layout(bad.c_nodes(), 4, ctypes.byref(lay), None, None) == 1
+    # functors with a ring in delay memory, stateless ops and the paired / feedback nodes cannot be called again
+    for name, nin in (("INTEGER_DELAY", 1), ("ALLPASS_PB", 2), ("ADD", 2), ("HALFBAND_UP", 1), ("FDN8", 1)):
+        q = graph.GraphSpec()
+        ins = [q.input(k) for k in range(nin)]
+        first = q.node(name, *ins)
+        q.ops.append(q.ops[first]), q.ins.append(q.ins[first]), q.iargs.append(-1 - first)
+        assert L.mlb_graph_layout(q.c_nodes(), q.n_nodes, ctypes.byref(lay), None, None) == 1, name
+        assert b"cannot be called again" in L.mlb_last_error()
+    # ... while a functor with a member row but no ring can (LinearGlide keeps mCurrVec)
+    q = graph.GraphSpec()
+    first = q.node("GLIDE", q.input(0))
+    q.output(q.again(first, q.input(1)))
+    assert L.mlb_graph_layout(q.c_nodes(), q.n_nodes, ctypes.byref(lay), None, None) == 0
+    assert lay.n_state_words == graph.OP_INFO[graph.OP_ID["GLIDE"]][1]
+
+
 def test_no_gpu_means_loud_failure_not_fallback(L):
     if api.device_count() > 0:
         pytest.skip("a GPU is visible here")

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from madronalib_b200 import workloads as wl
-from madronalib_b200.graph import OP_TABLE, GraphSpec
+from madronalib_b200.graph import OP_NAME, OP_TABLE, GraphSpec
 from tests.common import assert_state_equal
 
 
@@ -106,6 +106,58 @@ def test_upsample2x_graph_is_the_higher_order_function(ref):
     for v in (0, 7, 11):
         o = ref.upsample2x_clip(inp[:, 0, v, :], float(w.coef[0, v]))
         assert np.array_equal(o.view(np.uint32), a[:, 0, v, :].view(np.uint32))
+
+
+def test_upsample2x_with_a_stateful_process_function(ref, port):
+    """MLB_AGAIN: fn(v) = lp(osc(v * 0.5)) run twice per vector by Upsample2xFunction<1> -- the graph in which the
+    SINE and LOPASS nodes are called again == the reference's wrapper around its own SineGen and Lopass objects
+    (MLDSPFunctional.h:114-160; the tutorial wraps a sine generator this way, dspOpsExample.cpp:100-102)."""
+    V, T = 12, 24
+    w = wl.functor_case("upsample2x_osc", V)
+    g = w.spec
+    assert g.n_state == 9 + 1 + 2 + 9 and g.n_coef == 1 + 3   # the AGAIN nodes own no words
+    inp = w.inputs(T)
+    a, _, sa = ref.run(g, V, T, inp, w.state, w.coef, splits=(5, 19))
+    b, _, sb = port.run(g, V, T, inp, w.state, w.coef)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(sa, sb)
+    sine = [i for i, op in enumerate(g.ops) if OP_NAME[op] == "SINE"]
+    lp = [i for i, op in enumerate(g.ops) if OP_NAME[op] == "LOPASS"]
+    assert g.again_target(sine[1]) == sine[0] and g.again_target(lp[1]) == lp[0]
+    assert g.state_slot(sine[1]) == g.state_slot(sine[0]) and g.coef_slot(lp[1]) == g.coef_slot(lp[0])
+    c0 = g.coef_slot(lp[0])
+    for v in (0, 5, 11):
+        o = ref.upsample2x_osc(inp[:, 0, v, :], int(w.state[g.state_slot(sine[0]), v]), w.coef[c0:c0 + 3, v])
+        assert np.array_equal(o.view(np.uint32), a[:, 0, v, :].view(np.uint32))
+    assert np.abs(a).max() > 0.3
+    # ticking twice matters: with two independent functors per kind instead, the signal is another one
+    h = GraphSpec()
+    h.ops, h.ins, h.outs = list(g.ops), list(g.ins), list(g.outs)
+    h.iargs = [0 if g.again_target(i) >= 0 else g.iargs[i] for i in range(g.n_nodes)]
+    assert h.n_state == g.n_state + 3 and h.n_coef == g.n_coef + 3
+    hc, hs = h.new_coefs(V), h.new_state(V)
+    hc[h.coef_slot(3)] = 0.5  # the param node
+    for n in lp:
+        hc[h.coef_slot(n):h.coef_slot(n) + 3] = w.coef[c0:c0 + 3]
+    for n in sine:
+        hs[h.state_slot(n)] = w.state[g.state_slot(sine[0])]
+    c, _, _ = port.run(h, V, T, inp, hs, hc)
+    assert not np.array_equal(c, b)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_graphs_with_functors_called_again(ref, port, seed):
+    """Random DAGs in which generators, filters and glides are called AGAIN in the same vector (MLB_AGAIN): the port
+    (words shared through the layout) against the compiled reference (the same functor object simply called twice)."""
+    w = wl.random_graph_workload(100 + seed, n_voices=9, n_nodes=30, again_prob=0.5)
+    g = w.spec
+    n_again = sum(g.again_target(i) >= 0 for i in range(g.n_nodes))
+    assert n_again >= 2
+    T = 12
+    inp = w.inputs(T)
+    a, _, sa = ref.run(g, 9, T, inp, w.state, w.coef, splits=(5, 7))
+    b, _, sb = port.run(g, 9, T, inp, w.state, w.coef)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), seed
+    assert_state_equal(sb, sa, "state after, seed %d" % seed)
 
 
 def test_downsample2x_graph_is_the_higher_order_function(ref):

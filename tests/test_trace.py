@@ -33,7 +33,7 @@ def build_exe():
             os.path.join(ROOT, "tests", "cpp", "_ref", "reverb_body.inc")):
         subprocess.run([sys.executable, gen], check=True)  # the reference's example bodies: generated, never committed
     hdrs = [os.path.join(ROOT, "include", h) for h in ("mlb200_trace.hpp", "mlb200.hpp", "mlb200_host.hpp", "mlb200.h")]
-    hdrs += [os.path.join(ROOT, "tests", "cpp", f) for f in ("kitchen_body.h",)]
+    hdrs += [os.path.join(ROOT, "tests", "cpp", f) for f in ("kitchen_body.h", "upsample_body.h")]
     hdrs += [p for p in (os.path.join(ROOT, "tests", "cpp", "_ref", f) for f in ("sine_body.inc", "reverb_body.inc"))
              if os.path.exists(p)]
     if os.path.exists(EXE) and all(os.path.getmtime(EXE) > os.path.getmtime(p) for p in [src] + hdrs):
@@ -150,6 +150,40 @@ def test_kitchen_body_same_source_same_bits(ref, port):
     assert np.isfinite(want).all() and np.abs(want).max() > 0.05
 
 
+def upsample_input(T, V=1):
+    """a slowly moving frequency row (original rate) and a gate row"""
+    n = np.arange(T * 64).reshape(T, 1, 1, 64)
+    freq = (np.float32(330.0 / 48000.0) * (1.0 + 0.2 * np.sin(n * 0.0007))).astype(np.float32)
+    gate = (((n % 700) < 450) * np.float32(0.9)).astype(np.float32)
+    x = np.concatenate([freq, gate], axis=1)
+    return np.ascontiguousarray(np.repeat(x, V, axis=2))
+
+
+def test_upsample_body_same_source_same_bits(ref, port):
+    """tests/cpp/upsample_body.h -- ONE source, compiled against the reference and against the tracing layer: a process
+    function WITH STATE (SineGen, SawGen, Lopass, Bell, OnePole, ADSR, LinearGlide) run twice per vector by
+    Upsample2xFunction<1>.  The tracing layer records the second run as MLB_AGAIN nodes; the traced graph evaluated
+    by either checker equals the reference build of the same source."""
+    from madronalib_b200.graph import OP_NAME
+    g, coef, state = traced("upsample")
+    again = [i for i in range(g.n_nodes) if g.again_target(i) >= 0]
+    assert sorted(OP_NAME[g.ops[i]] for i in again) == ["ADSR", "BELL", "GLIDE", "LOPASS", "ONEPOLE", "SAW", "SINE"]
+    assert all(OP_NAME[g.ops[i]] != "NOISE" for i in again)  # called once per vector, outside fn
+    T = 40
+    x = upsample_input(T)
+    want = ref.upsample_body(x[:, :, 0])
+    for O in (ref, port):
+        out, _, _ = O.run(g, 1, T, x, state, coef)
+        assert_same_bits(out[:, :, 0], want, "upsample body: traced graph vs the reference build of the same source")
+    assert np.isfinite(want).all() and np.abs(want).max() > 0.05
+
+
+def test_a_functor_called_twice_outside_an_upsampler_is_refused():
+    build_exe()
+    r = subprocess.run([EXE, "dump", "twice"], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "once per vector" in (r.stdout + r.stderr)
+
+
 def _run_gpu_case(tmp_path, case, V, T, inp):
     build_exe()
     fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
@@ -162,7 +196,7 @@ def _run_gpu_case(tmp_path, case, V, T, inp):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case,V,T", [("chain", 70, 6), ("sine", 33, 4), ("reverb", 37, 24), ("shelf", 40, 5),
-                                      ("kitchen", 35, 20)])
+                                      ("kitchen", 35, 20), ("upsample", 36, 18)])
 def test_traced_examples_on_gpu(gpu, port, tmp_path, case, V, T):
     from oracle import bindings
     O = bindings.RefOracle() if bindings.ref_available() else port
@@ -175,6 +209,8 @@ def test_traced_examples_on_gpu(gpu, port, tmp_path, case, V, T):
                                                    (T, 1, V, 64)))
     if case == "kitchen":
         inp = kitchen_input(T, V)
+    if case == "upsample":
+        inp = upsample_input(T, V)
     _run_gpu_case(tmp_path, case, V, T, inp)
     got = np.fromfile(str(tmp_path / "out.bin"), np.float32).reshape(T, g.n_out, V, 64)
     want, _, _ = O.run(g, V, T, inp, state, coef)
@@ -186,6 +222,8 @@ def test_traced_examples_on_gpu(gpu, port, tmp_path, case, V, T):
             assert_same_bits(got[:, 0, 7], O.kitchen(inp[:, :, 0])[:, 0], "GPU vs the reference build of kitchen_body.h")
         return
     assert_same_bits(got, want, case + " traced on the GPU")
+    if case == "upsample" and bindings.ref_available():
+        assert_same_bits(got[:, :, 7], O.upsample_body(inp[:, :, 0]), "GPU vs the reference build of upsample_body.h")
     if case == "reverb" and bindings.ref_available():
         body, _ = O.aaltoverb(inp[:, :, 0], 1.0, wl.aaltoverb_feedback(0.5, 0.5), 0.1 * 48000)
         assert_same_bits(got[:, :, 5], body, "GPU vs the reverb example's own body")
