@@ -82,6 +82,7 @@ class Recorder
   // a functor object called AGAIN in the same vector (allowed inside the second run of a process function by
   // Upsample2xFunction): its next node becomes a further call of its first one (MLB_AGAIN in mlb200.h)
   int repeatDepth = 0;
+  int forbidFunctors = 0;       // > 0 inside a Downsample2xFunction's process function (see there)
   int pendingAgain = -1;        // node of the functor's first call in this pass
   int* pendingOwner = nullptr;  // where a functor's first call wants its node index written
 
@@ -104,7 +105,7 @@ class Recorder
     opCounter = 0;
     opIndexToNode.clear();
     feedbackReaders.clear();
-    repeatDepth = 0, pendingAgain = -1, pendingOwner = nullptr;
+    repeatDepth = 0, forbidFunctors = 0, pendingAgain = -1, pendingOwner = nullptr;
     active = true;
   }
   int addNode(int op, std::initializer_list<int> ins, int iarg = 0, bool userOp = true)
@@ -309,6 +310,10 @@ class Functor
   void once()
   {
     Recorder& r = Recorder::get();
+    if (r.forbidFunctors > 0)
+      throw Error(MLB_ERR_UNSUPPORTED,
+                  "mlb::tr: the process function of a Downsample2xFunction must be stateless (its functors would have to "
+                  "tick on every second vector only)");
     if (lastEpoch_ == r.epoch)
     {
       // called again in the same vector: only inside the second run of a process function by Upsample2xFunction,
@@ -878,6 +883,47 @@ class Upsample2xFunction : public Functor
     return op2(MLB_OP_HALFBAND_DOWN, y1, y2);  // mDowners[0].downsample
   }
   // the one-row form: upper(fn, x) with DSPVector in and out (dspOpsExample.cpp:100-102)
+  template <int R = IN_ROWS, typename = typename std::enable_if<R == 1>::type>
+  DSPVector operator()(std::function<DSPVector(const DSPVector)> fn, const DSPVector& x)
+  {
+    inputType in;
+    in.row(0) = x;
+    return (*this)([&](const inputType a) { return fn(a.constRow(0)); }, in);
+  }
+};
+
+// Downsample2xFunction<IN_ROWS>, MLDSPFunctional.h:166-223: on every second vector the input (this vector and the
+// buffered previous one) is downsampled, the process function runs on that half-rate vector and its result is upsampled
+// into this vector and the next.  Recorded as DOWN2X_IN per input row, fn's nodes, DOWN2X_OUT (mlb200.h).  fn must be
+// stateless: its nodes run on every vector here, its functors would have to tick on every second one only.
+template <int IN_ROWS>
+class Downsample2xFunction : public Functor
+{
+  using inputType = DSPVectorArray<(size_t)IN_ROWS>;
+  using ProcessFn = std::function<DSPVector(const inputType)>;
+
+ public:
+  DSPVector operator()(ProcessFn fn, const inputType& vx)
+  {
+    once();
+    Recorder& r = Recorder::get();
+    r.pendingOwner = nullptr, r.pendingAgain = -1;
+    inputType half;
+    for (int j = 0; j < IN_ROWS; ++j) half.row(j) = op1(MLB_OP_DOWN2X_IN, vx.constRow(j));
+    ++r.forbidFunctors;
+    DSPVector y;
+    try
+    {
+      y = fn(half);
+    }
+    catch (...)
+    {
+      --r.forbidFunctors;
+      throw;
+    }
+    --r.forbidFunctors;
+    return op1(MLB_OP_DOWN2X_OUT, y);
+  }
   template <int R = IN_ROWS, typename = typename std::enable_if<R == 1>::type>
   DSPVector operator()(std::function<DSPVector(const DSPVector)> fn, const DSPVector& x)
   {

@@ -186,9 +186,9 @@ class RefOracle(_Oracle):
         return out
 
     def upsample_body(self, inp: np.ndarray) -> np.ndarray:
-        """tests/cpp/upsample_body.h compiled against the reference (one instance); inp [T][2][64] -> [T][1][64]."""
+        """tests/cpp/upsample_body.h compiled against the reference (one instance); inp [T][2][64] -> [T][2][64]."""
         inp = np.ascontiguousarray(inp, np.float32)
-        out = np.empty((inp.shape[0], 1, 64), np.float32)
+        out = np.empty((inp.shape[0], 2, 64), np.float32)
         self.lib.mlref_upsample_body.argtypes = [ctypes.c_int, _vp, _vp]
         self.lib.mlref_upsample_body.restype = None
         self.lib.mlref_upsample_body(inp.shape[0], _ptr(inp), _ptr(out))

@@ -1217,8 +1217,8 @@ void mlref_kitchen(int T, const float* in, float* out)
 }
 
 // ---- tests/cpp/upsample_body.h compiled against the reference itself (the tracing layer compiles the same file):
-// a process function with state run at twice the rate by Upsample2xFunction<1>.  One instance; in [T][2][64]
-// (frequency, gate rows), out [T][64].
+// a process function with state run at twice the rate by Upsample2xFunction<1>, a stateless one at half the rate by
+// Downsample2xFunction<1>.  One instance; in [T][2][64] (frequency, gate rows), out [T][2][64].
 }  // extern "C"
 namespace upsample_ref
 {
@@ -1226,7 +1226,7 @@ using namespace ml;
 #include "../../tests/cpp/upsample_body.h"
 struct Ctx
 {
-  DSPVectorDynamic inputs{2}, outputs{1};
+  DSPVectorDynamic inputs{2}, outputs{2};
 };
 }  // namespace upsample_ref
 extern "C"
@@ -1241,7 +1241,8 @@ void mlref_upsample_body(int T, const float* in, float* out)
     ctx.inputs[0] = DSPVector(in + (size_t)t * 128);
     ctx.inputs[1] = DSPVector(in + (size_t)t * 128 + 64);
     upsample_ref::upsampleProcess(&ctx, &st);
-    store(ctx.outputs[0], out + (size_t)t * 64);
+    store(ctx.outputs[0], out + (size_t)t * 128);
+    store(ctx.outputs[1], out + (size_t)t * 128 + 64);
   }
 }
 

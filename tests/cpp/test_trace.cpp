@@ -89,6 +89,17 @@ void twiceProcess(AudioContext* ctx, void* state)
   auto s = static_cast<TwiceState*>(state);
   ctx->outputs[0] = s->osc(0.01f) + s->osc(0.02f);
 }
+// ... and so does a functor inside the process function of a Downsample2xFunction
+struct HalfRateState
+{
+  Downsample2xFunction<1> downer;
+  OnePole smooth;
+};
+void halfRateProcess(AudioContext* ctx, void* state)
+{
+  auto s = static_cast<HalfRateState*>(state);
+  ctx->outputs[0] = s->downer([&](const DSPVector v) { return s->smooth(v); }, DSPVector(0.5f));
+}
 
 struct Case
 {
@@ -120,6 +131,7 @@ int main(int argc, char** argv)
   UpsampleState upsample;
   upsampleInit(upsample);
   TwiceState twice;
+  HalfRateState halfRate;
 
   size_t nIn = 0, nOut = 0;
   SignalProcessFn fn = nullptr;
@@ -137,8 +149,9 @@ int main(int argc, char** argv)
   if (which == "chain") nIn = 0, nOut = 1, fn = chainProcess, state = &chain;
   if (which == "shelf") nIn = 1, nOut = 1, fn = shelfProcess, state = &shelf;
   if (which == "kitchen") nIn = 2, nOut = 2, fn = kitchenProcessFn, state = &kitchen;
-  if (which == "upsample") nIn = 2, nOut = 1, fn = upsampleProcessFn, state = &upsample;
+  if (which == "upsample") nIn = 2, nOut = 2, fn = upsampleProcessFn, state = &upsample;
   if (which == "twice") nIn = 0, nOut = 1, fn = twiceProcess, state = &twice;
+  if (which == "halfrate") nIn = 0, nOut = 1, fn = halfRateProcess, state = &halfRate;
   if (!fn) return 2;
   try
   {

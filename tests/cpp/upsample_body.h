@@ -4,7 +4,8 @@
 // A process function with STATE run at twice the rate by Upsample2xFunction<1> (MLDSPFunctional.h:114-160), the way
 // the reference's tutorial wraps a sine generator (examples/tutorial/dspOpsExample.cpp:100-102): the oscillator, the
 // filters, the envelope and the glide inside `fn` are called twice per vector.  One input row (frequency in cycles
-// per sample at the ORIGINAL rate), one gate row; one output row.
+// per sample at the ORIGINAL rate), one gate row; output 0 = that, output 1 = a stateless process function run at HALF
+// the rate by Downsample2xFunction<1> (MLDSPFunctional.h:166-223).
 #pragma once
 
 static volatile float kUpsampleParams[] = {0.11f, 0.8f, 0.004f, 0.05f, 1.3f, 4.f, 0.002f, 0.01f, 0.7f, 0.02f};
@@ -13,6 +14,7 @@ inline float up(int i) { return kUpsampleParams[i]; }
 struct UpsampleState
 {
   Upsample2xFunction<1> upper;
+  Downsample2xFunction<1> downer;
   SineGen osc;
   SawGen saw;
   Lopass lp;
@@ -49,4 +51,7 @@ inline void upsampleProcess(UPSAMPLE_CTX* ctx, void* state)
     return s->smooth(s->bell(s->lp(o * e)));
   };
   ctx->outputs[0] = s->upper(fn, freq) * gate + dither;
+  // a waveshaper at half the rate: stateless, as the half-rate wrapper requires here
+  auto shaper = [&](const DSPVector v) { return clamp(v * 3.f, DSPVector(-1.f), DSPVector(1.f)) * 0.5f; };
+  ctx->outputs[1] = s->downer(shaper, ctx->outputs[0] + gate * 0.25f);
 }

@@ -162,13 +162,15 @@ def upsample_input(T, V=1):
 def test_upsample_body_same_source_same_bits(ref, port):
     """tests/cpp/upsample_body.h -- ONE source, compiled against the reference and against the tracing layer: a process
     function WITH STATE (SineGen, SawGen, Lopass, Bell, OnePole, ADSR, LinearGlide) run twice per vector by
-    Upsample2xFunction<1>.  The tracing layer records the second run as MLB_AGAIN nodes; the traced graph evaluated
-    by either checker equals the reference build of the same source."""
+    Upsample2xFunction<1> (the tracing layer records the second run as MLB_AGAIN nodes), and a stateless one run at half
+    the rate by Downsample2xFunction<1>; the traced graph evaluated by either checker equals the reference build of the
+    same source."""
     from madronalib_b200.graph import OP_NAME
     g, coef, state = traced("upsample")
     again = [i for i in range(g.n_nodes) if g.again_target(i) >= 0]
     assert sorted(OP_NAME[g.ops[i]] for i in again) == ["ADSR", "BELL", "GLIDE", "LOPASS", "ONEPOLE", "SAW", "SINE"]
     assert all(OP_NAME[g.ops[i]] != "NOISE" for i in again)  # called once per vector, outside fn
+    assert [OP_NAME[op] for op in g.ops].count("DOWN2X_IN") == 1 and g.n_out == 2
     T = 40
     x = upsample_input(T)
     want = ref.upsample_body(x[:, :, 0])
@@ -182,6 +184,8 @@ def test_a_functor_called_twice_outside_an_upsampler_is_refused():
     build_exe()
     r = subprocess.run([EXE, "dump", "twice"], capture_output=True, text=True, timeout=60)
     assert r.returncode != 0 and "once per vector" in (r.stdout + r.stderr)
+    r = subprocess.run([EXE, "dump", "halfrate"], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "must be stateless" in (r.stdout + r.stderr)
 
 
 def _run_gpu_case(tmp_path, case, V, T, inp):
