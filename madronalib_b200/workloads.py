@@ -412,7 +412,10 @@ def functor_case(name: str, n_voices: int = 40) -> Workload:
 FUNCTOR_CASES = ("impulse", "oneshot", "peak", "rms", "adsr", "allpass1", "glide", "interpolator1", "sample_glide",
                  "integer_delay", "integer_delay_var", "fractional_delay", "fractional_delay_var",
                  "pitchbend_delay", "allpass_int", "allpass_frac", "allpass_pb", "feedback",
-                 "halfband_up", "halfband_roundtrip", "upsample2x_clip", "upsample2x_osc", "downsample2x_clip", "tempo_lock")
+                 "halfband_up", "halfband_roundtrip", "upsample2x_clip", "downsample2x_clip", "tempo_lock")
+# functor cases with MLB_AGAIN nodes (a functor called again in the same vector): kept apart so that their GPU tests
+# can be collected last (tests/test_zz_gpu_again.py)
+AGAIN_CASES = ("upsample2x_osc",)
 
 
 def aaltoverb_feedback(size_u: float, decay_u: float) -> float:

@@ -104,7 +104,7 @@ AALTOVERB_V, AALTOVERB_T = 2, 48
 def make_functors(R):
     """every added functor and the Aaltoverb example chain, from the reference."""
     out = {}
-    for name in wl.FUNCTOR_CASES:
+    for name in wl.FUNCTOR_CASES + wl.AGAIN_CASES:
         w = wl.functor_case(name, FUNCTOR_V)
         inp = w.inputs(FUNCTOR_T)
         y, _, st = R.run(w.spec, w.n_voices, FUNCTOR_T, inp, w.state, w.coef)

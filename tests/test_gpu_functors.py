@@ -146,42 +146,3 @@ def test_random_graphs_bit_exact(gpu, port, monkeypatch, seed):
         finite = np.isfinite(pm) & np.isfinite(gm)
         assert np.array_equal(gm[finite].view(np.uint32), pm[finite].view(np.uint32))
 
-
-@pytest.mark.parametrize("seed", [217, 226, 238])
-def test_random_graphs_with_functors_called_again(gpu, port, monkeypatch, seed):
-    """MLB_AGAIN on the device: random DAGs in which generators, filters and glides are called again in the same
-    vector (the further call reads and writes the words of the first), default stage count and forced cuts (a functor
-    and its further calls stay in one stage).  Seeds screened on the CPU: every node's row is finite, so no NaN sign
-    enters (see test_random_graphs_bit_exact); the port is pinned to the compiled reference on the same generator
-    (test_oracle_port_vs_ref.py::test_random_graphs_with_functors_called_again)."""
-    w = wl.random_graph_workload(seed, 41, 28, hw_approx=False, again_prob=0.5)
-    g = w.spec
-    assert sum(g.again_target(i) >= 0 for i in range(g.n_nodes)) >= 3
-    T = 9
-    inp = w.inputs(T)
-    po, _, ps = port.run(g, w.n_voices, T, inp, w.state, w.coef)
-    assert np.isfinite(po).all()
-    for stages in (None, 4, 64):
-        if stages:
-            monkeypatch.setenv("MLB_STAGES", str(stages))
-        go, _, gs, kname = run_gpu(gpu, w, T, inp, splits=(4, 5))
-        assert kname.startswith("generic"), kname
-        assert_same_bits(go, po, "random graph with AGAIN nodes %d (%s)" % (seed, kname))
-        assert_state_equal(gs, ps, "random graph with AGAIN nodes %d (%s)" % (seed, kname))
-
-
-def test_upsample2x_with_a_stateful_process_function_on_the_device(gpu, ref):
-    """The reference's own Upsample2xFunction<1> around its own SineGen and Lopass objects (both called twice per
-    vector) against the MLB_AGAIN graph on the device."""
-    V, T = 70, 20
-    w = wl.functor_case("upsample2x_osc", V)
-    inp = w.inputs(T)
-    go, _, gs, kname = run_gpu(gpu, w, T, inp, splits=(7, 13))
-    assert kname.startswith("generic"), kname
-    g = w.spec
-    from madronalib_b200.graph import OP_NAME
-    sine = next(i for i in range(g.n_nodes) if OP_NAME[g.ops[i]] == "SINE")
-    c0 = g.coef_slot(next(i for i in range(g.n_nodes) if OP_NAME[g.ops[i]] == "LOPASS"))
-    for v in (0, 31, 32, 69):
-        o = ref.upsample2x_osc(inp[:, 0, v, :], int(w.state[g.state_slot(sine), v]), w.coef[c0:c0 + 3, v])
-        assert_same_bits(go[:, 0, v, :], o, "Upsample2xFunction with a stateful fn, voice %d" % v)

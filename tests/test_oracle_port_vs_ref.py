@@ -64,7 +64,7 @@ def test_reference_chain_loop_equals_graph(ref):
     assert np.array_equal(got.view(np.uint32), want[:, 0].view(np.uint32)) and sec > 0
 
 
-@pytest.mark.parametrize("name", wl.FUNCTOR_CASES)
+@pytest.mark.parametrize("name", wl.FUNCTOR_CASES + wl.AGAIN_CASES)
 def test_functor_cases(ref, port, name):
     """every added functor, port == compiled reference, bit for bit, with the
     port run split over three calls (state and delay memory carried inside the oracle)."""

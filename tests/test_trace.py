@@ -200,7 +200,7 @@ def _run_gpu_case(tmp_path, case, V, T, inp):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case,V,T", [("chain", 70, 6), ("sine", 33, 4), ("reverb", 37, 24), ("shelf", 40, 5),
-                                      ("kitchen", 35, 20), ("upsample", 36, 18)])
+                                      ("kitchen", 35, 20)])
 def test_traced_examples_on_gpu(gpu, port, tmp_path, case, V, T):
     from oracle import bindings
     O = bindings.RefOracle() if bindings.ref_available() else port
@@ -213,8 +213,6 @@ def test_traced_examples_on_gpu(gpu, port, tmp_path, case, V, T):
                                                    (T, 1, V, 64)))
     if case == "kitchen":
         inp = kitchen_input(T, V)
-    if case == "upsample":
-        inp = upsample_input(T, V)
     _run_gpu_case(tmp_path, case, V, T, inp)
     got = np.fromfile(str(tmp_path / "out.bin"), np.float32).reshape(T, g.n_out, V, 64)
     want, _, _ = O.run(g, V, T, inp, state, coef)
@@ -226,8 +224,6 @@ def test_traced_examples_on_gpu(gpu, port, tmp_path, case, V, T):
             assert_same_bits(got[:, 0, 7], O.kitchen(inp[:, :, 0])[:, 0], "GPU vs the reference build of kitchen_body.h")
         return
     assert_same_bits(got, want, case + " traced on the GPU")
-    if case == "upsample" and bindings.ref_available():
-        assert_same_bits(got[:, :, 7], O.upsample_body(inp[:, :, 0]), "GPU vs the reference build of upsample_body.h")
     if case == "reverb" and bindings.ref_available():
         body, _ = O.aaltoverb(inp[:, :, 0], 1.0, wl.aaltoverb_feedback(0.5, 0.5), 0.1 * 48000)
         assert_same_bits(got[:, :, 5], body, "GPU vs the reverb example's own body")
