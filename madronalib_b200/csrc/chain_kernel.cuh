@@ -22,7 +22,9 @@
 //   * results are written IN PLACE into the block and leave through one TMA store
 //     (UTMASTG.4D); ragged V is clipped by the tensor map (zero fill on load, clip on store);
 //   * optional mix bus: after a tile is computed, lane n sums column n over the 32 voice
-//     rows (conflict-free through the same swizzle) into partial[plane][group][64];
+//     rows into partial[plane][group][64].  This column walk is NOT conflict-free under the
+//     row swizzle: ncu counts 4.3 M of the kernel's 30 M shared wavefronts as bank conflicts
+//     (14 %, profiles/ncu_chainA_r2_summary.json) -- all of them here;
 //     a second tiny kernel adds the per-group partials in group order (deterministic).
 #pragma once
 #include "ops.cuh"
