@@ -844,6 +844,50 @@ class Bank
   }
 };
 
+// HalfBandFilter, MLDSPFilters.h:1245-1310, used directly: one object works in one direction per vector --
+// upsampleFirstHalf(x) then upsampleSecondHalf(x) of the same x (two rows at twice the rate), or downsample(x1, x2).
+class HalfBandFilter : public Functor
+{
+  int upNode_ = -1, upEpoch_ = 0;
+
+ public:
+  void clear() {}
+  DSPVector upsampleFirstHalf(const DSPVector& vx)
+  {
+    once();
+    DSPVector y = op1(MLB_OP_HALFBAND_UP, vx);
+    upNode_ = y.node, upEpoch_ = Recorder::get().epoch;
+    return y;
+  }
+  DSPVector upsampleSecondHalf(const DSPVector& /*the same vx*/)
+  {
+    Recorder& r = Recorder::get();
+    if (upEpoch_ != r.epoch || upNode_ < 0)
+      throw Error(MLB_ERR_UNSUPPORTED, "mlb::tr: HalfBandFilter::upsampleSecondHalf needs upsampleFirstHalf of the same vector first");
+    return DSPVector::ofNode(r.addNode(MLB_OP_HALFBAND_UP_2, {upNode_}));
+  }
+  DSPVector downsample(const DSPVector& vx1, const DSPVector& vx2)
+  {
+    once();
+    return op2(MLB_OP_HALFBAND_DOWN, vx1, vx2);
+  }
+};
+
+// TempoLock, MLDSPFilters.h:1478-1579: a phasor locked to the input phasor at the ratio dydx
+class TempoLock : public Functor
+{
+ public:
+  void clear() {}
+  DSPVector operator()(const DSPVector& x, float dydx, float isr)
+  {
+    once();
+    DSPVector y = op2(MLB_OP_TEMPO_LOCK, x, DSPVector(dydx));
+    nodeOf(y).coef[0] = isr;
+    nodeOf(y).state[0] = 0xBF800000u;  // _omega{-1.f}: stopped, MLDSPFilters.h:1481
+    return y;
+  }
+};
+
 // Upsample2xFunction<IN_ROWS>, MLDSPFunctional.h:114-160: the input rows upsampled by two half-band filters, the
 // process function run on BOTH halves, the two results downsampled to one row.  The functors inside fn are called
 // twice per vector, as in the reference (the second call records MLB_AGAIN nodes: same state, ticked again);

@@ -5,7 +5,8 @@
 // the reference's tutorial wraps a sine generator (examples/tutorial/dspOpsExample.cpp:100-102): the oscillator, the
 // filters, the envelope and the glide inside `fn` are called twice per vector.  One input row (frequency in cycles
 // per sample at the ORIGINAL rate), one gate row; output 0 = that, output 1 = a stateless process function run at HALF
-// the rate by Downsample2xFunction<1> (MLDSPFunctional.h:166-223).
+// the rate by Downsample2xFunction<1> (MLDSPFunctional.h:166-223), then a HalfBandFilter pair used directly
+// (MLDSPFilters.h:1245-1310) plus a TempoLock (MLDSPFilters.h:1478-1579).
 #pragma once
 
 static volatile float kUpsampleParams[] = {0.11f, 0.8f, 0.004f, 0.05f, 1.3f, 4.f, 0.002f, 0.01f, 0.7f, 0.02f};
@@ -23,6 +24,10 @@ struct UpsampleState
   ADSR env;
   LinearGlide glide;
   NoiseGen noise;  // called once per vector, outside fn
+  // the half-band filter used directly, and a clock follower
+  HalfBandFilter hbUp, hbDown;
+  PhasorGen clock;
+  TempoLock lock;
 };
 
 inline void upsampleInit(UpsampleState& s)
@@ -53,5 +58,9 @@ inline void upsampleProcess(UPSAMPLE_CTX* ctx, void* state)
   ctx->outputs[0] = s->upper(fn, freq) * gate + dither;
   // a waveshaper at half the rate: stateless, as the half-rate wrapper requires here
   auto shaper = [&](const DSPVector v) { return clamp(v * 3.f, DSPVector(-1.f), DSPVector(1.f)) * 0.5f; };
-  ctx->outputs[1] = s->downer(shaper, ctx->outputs[0] + gate * 0.25f);
+  DSPVector half = s->downer(shaper, ctx->outputs[0] + gate * 0.25f);
+  // HalfBandFilter by hand: both 2x halves, scaled differently, back down; TempoLock follows a clock at 3/2
+  DSPVector a = s->hbUp.upsampleFirstHalf(half), b = s->hbUp.upsampleSecondHalf(half);
+  DSPVector locked = s->lock(s->clock(freq * 0.01f), 1.5f, 1.f / 48000.f);
+  ctx->outputs[1] = s->hbDown.downsample(a * 0.75f, b * 1.25f) + locked * 0.1f;
 }
