@@ -799,11 +799,62 @@ class Allpass<FractionalDelay> : public Functor
   }
 };
 
-// FDN<SIZE>, MLDSPFilters.h:1162-1239.  The device kernel is FDN<8>.
+// FDN<SIZE>, MLDSPFilters.h:1162-1239.  Any SIZE is recorded as what it is made of -- SIZE IntegerDelays fed by the
+// vectors kept from the previous call (they become one-block feedback edges like any carried DSPVector member), the
+// stereo sums, the Householder step, SIZE OnePoles, the gains -- in the reference's operation order, so with its bits
+// (tests/test_oracle_port_vs_ref.py::test_fdn_of_any_size_written_out_with_its_parts).  FDN<8> (below) is ONE node
+// with its own kernel.  The delays are sized for exactly their length (the reference never sizes them: SURVEY D7).
 template <int SIZE>
-class FDN : public Functor
+class FDN
 {
-  static_assert(SIZE == 8, "the device FDN kernel is FDN<8> (MLB_FDN_LINES)");
+  std::array<IntegerDelay, (size_t)SIZE> delays_;
+  std::array<OnePole, (size_t)SIZE> filters_;
+  std::array<DSPVector, (size_t)SIZE> lines_;  // mDelayInputVectors: read before they are assigned
+
+ public:
+  std::array<float, (size_t)SIZE> mFeedbackGains{};
+  void setDelaysInSamples(std::array<float, (size_t)SIZE> times)
+  {
+    for (int n = 0; n < SIZE; ++n)
+    {
+      int len = (int)(times[(size_t)n] - (float)kFloatsPerDSPVector);  // one vector of latency is in the feedback edge
+      if (len < 1) len = 1;
+      delays_[(size_t)n].setMaxDelayInSamples((float)len);
+      delays_[(size_t)n].setDelayInSamples(len);
+    }
+  }
+  void setFilterCutoffs(std::array<float, (size_t)SIZE> omegas)
+  {
+    for (int n = 0; n < SIZE; ++n) filters_[(size_t)n].coeffs = OnePole::makeCoeffs(omegas[(size_t)n]);
+  }
+  DSPVectorArray<2> operator()(const DSPVector& x)
+  {
+    for (int n = 0; n < SIZE; ++n) lines_[(size_t)n] = delays_[(size_t)n](lines_[(size_t)n]);
+    DSPVector sumR, sumL;  // zero filled
+    for (int n = 0; n < (SIZE & ~1); ++n)
+    {
+      if (n & 1)
+        sumL += lines_[(size_t)n];
+      else
+        sumR += lines_[(size_t)n];
+    }
+    DSPVector sumOfDelays;
+    for (int n = 0; n < SIZE; ++n) sumOfDelays += lines_[(size_t)n];
+    sumOfDelays *= DSPVector(2.0f / SIZE);  // the unit-gain Householder matrix: identity minus 2 / SIZE
+    for (int n = 0; n < SIZE; ++n)
+    {
+      DSPVector& line = lines_[(size_t)n];
+      line -= sumOfDelays;
+      line = filters_[(size_t)n](line) * DSPVector(mFeedbackGains[(size_t)n]);
+      line += x;
+    }
+    return concatRows(sumL, sumR);
+  }
+};
+template <>
+class FDN<8> : public Functor
+{
+  static constexpr int SIZE = 8;
   std::array<float, 8> times_{}, cutoffs_{};
 
  public:

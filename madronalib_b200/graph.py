@@ -259,6 +259,38 @@ def graph_fm3_fdn8() -> GraphSpec:
     return g.output(fl, fr)
 
 
+def graph_fdn(size: int) -> Tuple["GraphSpec", Dict[str, List[int]]]:
+    """FDN<SIZE> for any SIZE, written out with the nodes it is made of (MLDSPFilters.h:1162-1239): SIZE IntegerDelays fed
+    by the vectors kept from the previous call (one-block feedback edges), the stereo sums, the Householder matrix as
+    "minus 2/SIZE times the sum", SIZE OnePoles, the feedback gains, plus the input.  (SIZE = 8 also has the fused FDN8
+    node and kernel.)  Same operation order as the reference, so the same bits.  Input plane 0; outputs sumL, sumR.
+    Returns the graph and the node indices a caller sets coefficients on: 'delay', 'filter', 'gain' (per line),
+    'zero' and 'k' (the constants 0 and 2.0f / SIZE)."""
+    g = GraphSpec()
+    x = g.input(0)
+    zero, k = g.param(), g.param()
+    readers = [g.feedback_read() for _ in range(size)]
+    d = [g.node("INTEGER_DELAY", r) for r in readers]           # mDelayInputVectors[n] = mDelays[n](mDelayInputVectors[n])
+    sum_r, sum_l = zero, zero                                   # DSPVector sumR, sumL: zero-filled
+    for n in range(size & ~1):
+        if n & 1:
+            sum_l = g.node("ADD", sum_l, d[n])
+        else:
+            sum_r = g.node("ADD", sum_r, d[n])
+    total = zero
+    for n in range(size):
+        total = g.node("ADD", total, d[n])
+    total = g.node("MULTIPLY", total, k)                        # sumOfDelays *= DSPVector(2.0f / SIZE)
+    filt, gain = [], []
+    for n in range(size):
+        f = g.node("ONEPOLE", g.node("SUBTRACT", d[n], total))
+        gn = g.param()
+        g.feedback_write(readers[n], g.node("ADD", g.node("MULTIPLY", f, gn), x))
+        filt.append(f), gain.append(gn)
+    g.output(sum_l, sum_r)
+    return g, {"delay": d, "filter": filt, "gain": gain, "zero": [zero], "k": [k]}
+
+
 def graph_chain256(n_nodes: int = 256) -> GraphSpec:
     """Config 5: NoiseGen feeding a chain cycling 8 node kinds.
 

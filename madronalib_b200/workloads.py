@@ -155,6 +155,36 @@ def config_4(n_voices: int = 16384) -> Workload:
     return w
 
 
+def fdn_case(size: int, n_voices: int = 40):
+    """FDN<size> written out with IntegerDelay / OnePole / feedback-edge nodes (graph.graph_fdn): per-voice delay
+    times, cutoffs and gains; a noise burst in.  Returns (workload, times [size][V], cutoffs [size], gains [size])."""
+    from .graph import graph_fdn
+    V = n_voices
+    g, idx = graph_fdn(size)
+    coef, state = g.new_coefs(V), g.new_state(V)
+    base = np.array([67, 73, 91, 103, 127, 149, 173, 199, 211, 233, 257, 281, 307, 331, 353, 379], np.float32)[:size]
+    times = base[:, None] + np.float32(37.0) * (np.arange(V, dtype=np.float32) % 5)[None, :]      # [size][V]
+    cutoffs = (np.float32(0.08) + np.float32(0.05) * (np.arange(size, dtype=np.float32) % 5)).astype(np.float32)
+    gains = (np.float32(0.55) - np.float32(0.01) * np.arange(size, dtype=np.float32)).astype(np.float32)
+    coef[g.coef_slot(idx["zero"][0])] = np.float32(0.0)
+    coef[g.coef_slot(idx["k"][0])] = np.float32(2.0) / np.float32(size)
+    for n in range(size):
+        length = np.maximum(1, (times[n] - np.float32(BLOCK)).astype(np.int32)).astype(np.float32)  # FDN::setDelaysInSamples
+        coef[g.coef_slot(idx["delay"][n])] = length         # IntegerDelay::setDelayInSamples(len)
+        coef[g.coef_slot(idx["delay"][n], 1)] = length      # ... sized for exactly that delay (SURVEY D7 shim)
+        _set(coef, g, idx["filter"][n], np.repeat(api.coeffs("onepole", float(cutoffs[n]))[:, None], V, 1))
+        coef[g.coef_slot(idx["gain"][n])] = gains[n]
+    w = Workload("fdn%d" % size, g, V, coef, state)
+    noise = _noise_rows(31 + size, V, 0.5)
+
+    def fn(T, t0=0, v0=0, v1=None, out=None):
+        x = noise(T, t0)
+        x[6:] = 0  # a burst, then the tail
+        return x
+    w.inputs = fn  # type: ignore[assignment]
+    return w, times, cutoffs, gains
+
+
 def config_5(n_instances: int = 1024, n_nodes: int = 256) -> Workload:
     """256-node chain cycling 8 node kinds, fed by NoiseGen seeded with the instance index."""
     spec = graph_chain256(n_nodes)

@@ -185,6 +185,25 @@ class RefOracle(_Oracle):
         self.lib.mlref_kitchen(inp.shape[0], _ptr(inp), _ptr(out))
         return out
 
+    def fdn(self, size: int, inp: np.ndarray, times, cutoffs, gains) -> np.ndarray:
+        """The reference's FDN<size> object itself (size 4, 6, 8 or 16), one voice; inp [T][64] -> [T][2][64]."""
+        inp = np.ascontiguousarray(inp, np.float32)
+        t, c, g = (np.ascontiguousarray(a, np.float32) for a in (times, cutoffs, gains))
+        out = np.empty((inp.shape[0], 2, 64), np.float32)
+        self.lib.mlref_fdn_run.argtypes = [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]
+        self.lib.mlref_fdn_run.restype = ctypes.c_int
+        assert self.lib.mlref_fdn_run(size, inp.shape[0], _ptr(inp), _ptr(out), _ptr(t), _ptr(c), _ptr(g)) == 0
+        return out
+
+    def fdn_body(self, inp: np.ndarray) -> np.ndarray:
+        """tests/cpp/fdn_body.h compiled against the reference (one instance); inp [T][2][64] -> [T][2][64]."""
+        inp = np.ascontiguousarray(inp, np.float32)
+        out = np.empty((inp.shape[0], 2, 64), np.float32)
+        self.lib.mlref_fdn_body.argtypes = [ctypes.c_int, _vp, _vp]
+        self.lib.mlref_fdn_body.restype = None
+        self.lib.mlref_fdn_body(inp.shape[0], _ptr(inp), _ptr(out))
+        return out
+
     def upsample_body(self, inp: np.ndarray) -> np.ndarray:
         """tests/cpp/upsample_body.h compiled against the reference (one instance); inp [T][2][64] -> [T][2][64]."""
         inp = np.ascontiguousarray(inp, np.float32)

@@ -1216,6 +1216,83 @@ void mlref_kitchen(int T, const float* in, float* out)
   }
 }
 
+// ---- FDN<SIZE> itself for SIZE = 4, 6, 16 (MLDSPFilters.h:1162-1239), one voice; in [T][64], out [T][2][64] (sumL, sumR).
+// The delays are sized for exactly their length, as for FDN<8> above (FDN never sizes them: SURVEY D7).  What the
+// written-out graph of graph.graph_fdn(size) must equal.
+}  // extern "C"
+namespace
+{
+template <int SIZE>
+void runFdn(int T, const float* in, float* out, const float* times, const float* cutoffs, const float* gains)
+{
+  FDN<SIZE> f;
+  std::array<float, SIZE> t, c;
+  for (int n = 0; n < SIZE; ++n) t[n] = times[n], c[n] = cutoffs[n], f.mFeedbackGains[n] = gains[n];
+  f.setFilterCutoffs(c);
+  for (int n = 0; n < SIZE; ++n)
+  {
+    int len = static_cast<int>(times[n] - kFloatsPerDSPVector);  // FDN::setDelaysInSamples, :1180-1184
+    len = std::max(1, len);
+    f.mDelays[n].setMaxDelayInSamples(static_cast<float>(len));
+  }
+  f.setDelaysInSamples(t);
+  for (int b = 0; b < T; ++b)
+  {
+    DSPVectorArray<2> y = f(DSPVector(in + (size_t)b * 64));
+    store(y.constRow(0), out + (size_t)b * 128);
+    store(y.constRow(1), out + (size_t)b * 128 + 64);
+  }
+}
+}  // namespace
+extern "C"
+{
+int mlref_fdn_run(int size, int T, const float* in, float* out, const float* times, const float* cutoffs,
+                  const float* gains)
+{
+  switch (size)
+  {
+    case 4: runFdn<4>(T, in, out, times, cutoffs, gains); return 0;
+    case 6: runFdn<6>(T, in, out, times, cutoffs, gains); return 0;
+    case 8: runFdn<8>(T, in, out, times, cutoffs, gains); return 0;
+    case 16: runFdn<16>(T, in, out, times, cutoffs, gains); return 0;
+    default: return 1;
+  }
+}
+
+// ---- tests/cpp/fdn_body.h compiled against the reference itself (the tracing layer compiles the same file): FDN<4> and
+// FDN<6>.  One instance; in [T][2][64], out [T][2][64].
+}  // extern "C"
+namespace fdn_ref
+{
+using namespace ml;
+// the reference never sizes an FDN's delay lines: size them for exactly their length, as PFDN8 does
+#define FDN_SIZE_DELAYS(fdn, times)                                                      \
+  for (size_t n_ = 0; n_ < (times).size(); ++n_)                                         \
+  (fdn).mDelays[n_].setMaxDelayInSamples(static_cast<float>(std::max(1, static_cast<int>((times)[n_] - kFloatsPerDSPVector))))
+#include "../../tests/cpp/fdn_body.h"
+#undef FDN_SIZE_DELAYS
+struct Ctx
+{
+  DSPVectorDynamic inputs{2}, outputs{2};
+};
+}  // namespace fdn_ref
+extern "C"
+{
+void mlref_fdn_body(int T, const float* in, float* out)
+{
+  fdn_ref::FdnState st;
+  fdn_ref::fdnInit(st);
+  fdn_ref::Ctx ctx;
+  for (int t = 0; t < T; ++t)
+  {
+    ctx.inputs[0] = DSPVector(in + (size_t)t * 128);
+    ctx.inputs[1] = DSPVector(in + (size_t)t * 128 + 64);
+    fdn_ref::fdnProcess(&ctx, &st);
+    store(ctx.outputs[0], out + (size_t)t * 128);
+    store(ctx.outputs[1], out + (size_t)t * 128 + 64);
+  }
+}
+
 // ---- tests/cpp/upsample_body.h compiled against the reference itself (the tracing layer compiles the same file):
 // a process function with state run at twice the rate by Upsample2xFunction<1>, a stateless one at half the rate by
 // Downsample2xFunction<1>.  One instance; in [T][2][64] (frequency, gate rows), out [T][2][64].

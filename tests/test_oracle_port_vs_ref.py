@@ -160,6 +160,24 @@ def test_random_graphs_with_functors_called_again(ref, port, seed):
     assert_state_equal(sb, sa, "state after, seed %d" % seed)
 
 
+@pytest.mark.parametrize("size", [4, 6, 8, 16])
+def test_fdn_of_any_size_written_out_with_its_parts(ref, port, size):
+    """FDN<SIZE> (MLDSPFilters.h:1162-1239) for SIZE other than the fused 8: the graph made of SIZE IntegerDelays, the
+    sums, the Householder step, SIZE OnePoles, gains and one-block feedback edges (graph.graph_fdn) == the reference's
+    own FDN<SIZE> object, bit for bit, on both checkers (SIZE = 8 included as a cross-check of the recipe)."""
+    V, T = 7, 40
+    w, times, cutoffs, gains = wl.fdn_case(size, V)
+    inp = w.inputs(T)
+    a, _, sa = ref.run(w.spec, V, T, inp, w.state, w.coef, splits=(9, 31))
+    b, _, sb = port.run(w.spec, V, T, inp, w.state, w.coef)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert_state_equal(sb, sa, "fdn%d" % size)
+    for v in (0, 3, 6):
+        o = ref.fdn(size, inp[:, 0, v, :], times[:, v], cutoffs, gains)
+        assert np.array_equal(o.view(np.uint32), a[:, :, v, :].view(np.uint32)), (size, v)
+    assert np.sqrt((a[-8:] ** 2).mean()) > 1e-4  # the tail rings
+
+
 def test_downsample2x_graph_is_the_higher_order_function(ref):
     """DOWN2X_OUT(fn(DOWN2X_IN(x))) == the reference's Downsample2xFunction<1> (MLDSPFunctional.h:166-223)
     called directly with fn(v) = clamp(v * drive, -1, 1)."""

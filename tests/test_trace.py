@@ -33,7 +33,7 @@ def build_exe():
             os.path.join(ROOT, "tests", "cpp", "_ref", "reverb_body.inc")):
         subprocess.run([sys.executable, gen], check=True)  # the reference's example bodies: generated, never committed
     hdrs = [os.path.join(ROOT, "include", h) for h in ("mlb200_trace.hpp", "mlb200.hpp", "mlb200_host.hpp", "mlb200.h")]
-    hdrs += [os.path.join(ROOT, "tests", "cpp", f) for f in ("kitchen_body.h", "upsample_body.h")]
+    hdrs += [os.path.join(ROOT, "tests", "cpp", f) for f in ("kitchen_body.h", "upsample_body.h", "fdn_body.h")]
     hdrs += [p for p in (os.path.join(ROOT, "tests", "cpp", "_ref", f) for f in ("sine_body.inc", "reverb_body.inc"))
              if os.path.exists(p)]
     if os.path.exists(EXE) and all(os.path.getmtime(EXE) > os.path.getmtime(p) for p in [src] + hdrs):
@@ -178,6 +178,25 @@ def test_upsample_body_same_source_same_bits(ref, port):
         out, _, _ = O.run(g, 1, T, x, state, coef)
         assert_same_bits(out[:, :, 0], want, "upsample body: traced graph vs the reference build of the same source")
     assert np.isfinite(want).all() and np.abs(want).max() > 0.05
+
+
+def test_fdn_body_same_source_same_bits(ref, port):
+    """tests/cpp/fdn_body.h -- ONE source, compiled against the reference and against the tracing layer: FDN<4> and FDN<6>
+    (MLDSPFilters.h:1162-1239; the device has one fused node for FDN<8> only).  The tracing layer records them as the
+    IntegerDelays, OnePoles, sums and feedback edges they are made of; the traced graph evaluated by either checker
+    equals the reference build of the same source."""
+    from madronalib_b200.graph import OP_NAME
+    g, coef, state = traced("fdn")
+    names = [OP_NAME[op] for op in g.ops]
+    assert names.count("INTEGER_DELAY") == 10 and names.count("ONEPOLE") == 10
+    assert names.count("FEEDBACK_READ") == 10 and names.count("FEEDBACK_WRITE") == 10 and "FDN8" not in names
+    T = 60
+    x = reverb_input(T)
+    want = ref.fdn_body(x[:, :, 0])
+    for O in (ref, port):
+        out, _, _ = O.run(g, 1, T, x, state, coef)
+        assert_same_bits(out[:, :, 0], want, "fdn body: traced graph vs the reference build of the same source")
+    assert np.isfinite(want).all() and np.abs(want).max() > 0.05 and np.sqrt((want[-10:] ** 2).mean()) > 1e-8  # a decaying tail
 
 
 def test_a_functor_called_twice_outside_an_upsampler_is_refused():

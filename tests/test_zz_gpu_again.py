@@ -1,5 +1,6 @@
-"""GPU parity of MLB_AGAIN graphs (a functor called again in the same vector, mlb200.h): a process function with state
-inside Upsample2xFunction.  Collected LAST on purpose (the file name): these tests were written after the round's GPU
+"""GPU parity of the features added after the round's GPU budget was spent: MLB_AGAIN graphs (a functor called again in
+the same vector, mlb200.h: a process function with state inside Upsample2xFunction) and FDN<SIZE> for sizes other than
+8, written out with the nodes it is made of.  Collected LAST on purpose (the file name): these tests were written after the round's GPU
 budget was spent and have only been rehearsed on the CPU checkers, so under `pytest -x` a surprise here cannot hide
 the rest of the suite.  The CPU side of the feature: test_abi.py, test_oracle_port_vs_ref.py, test_oracle_golden.py,
 test_trace.py."""
@@ -94,3 +95,35 @@ def test_traced_upsample_body_on_gpu(gpu, port, tmp_path):
     assert_same_bits(got, want, "upsample body traced on the GPU")
     if bindings.ref_available():
         assert_same_bits(got[:, :, 7], O.upsample_body(inp[:, :, 0]), "GPU vs the reference build of upsample_body.h")
+
+
+@pytest.mark.parametrize("size", [4, 6, 16])
+def test_fdn_of_any_size_on_the_device(gpu, port, ref, size):
+    """FDN<SIZE> written out with IntegerDelay / OnePole / feedback-edge nodes (graph.graph_fdn) through the interpreter,
+    against the port and against the reference's own FDN<SIZE> object."""
+    V, T = 45, 30
+    w, times, cutoffs, gains = wl.fdn_case(size, V)
+    inp = w.inputs(T)
+    po, _, ps = port.run(w.spec, V, T, inp, w.state, w.coef)
+    go, _, gs, kname = run_gpu(gpu, w, T, inp, splits=(11, 19))
+    assert kname.startswith("generic"), kname
+    assert_same_bits(go, po, "fdn%d (%s)" % (size, kname))
+    assert_state_equal(gs, ps, "fdn%d" % size)
+    for v in (0, 44):
+        assert_same_bits(go[:, :, v, :], ref.fdn(size, inp[:, 0, v, :], times[:, v], cutoffs, gains), "vs FDN<%d> itself" % size)
+
+
+def test_traced_fdn_body_on_gpu(gpu, port, tmp_path):
+    """tests/cpp/fdn_body.h (FDN<4> + FDN<6>) traced and run on the device == the reference build of the same source."""
+    from oracle import bindings
+    from tests.test_trace import _run_gpu_case, reverb_input, traced
+    V, T = 34, 40
+    O = bindings.RefOracle() if bindings.ref_available() else port
+    g, coef, state = traced("fdn", V)
+    inp = reverb_input(T, V)
+    _run_gpu_case(tmp_path, "fdn", V, T, inp)
+    got = np.fromfile(str(tmp_path / "out.bin"), np.float32).reshape(T, g.n_out, V, 64)
+    want, _, _ = O.run(g, V, T, inp, state, coef)
+    assert_same_bits(got, want, "fdn body traced on the GPU")
+    if bindings.ref_available():
+        assert_same_bits(got[:, :, 5], O.fdn_body(inp[:, :, 0]), "GPU vs the reference build of fdn_body.h")
