@@ -290,6 +290,132 @@ inline DSPVectorArray<2> concatRows(const DSPVector& a, const DSPVector& b)
   y.row(0) = a, y.row(1) = b;
   return y;
 }
+// ---- DSPVectorArray<ROWS> as a value: rowwise arithmetic, MLDSPOps.h:337-358 ----
+#define MLB_TR_ARRAY_OP(SYM, OP)                                                                              \
+  template <size_t ROWS>                                                                                      \
+  inline DSPVectorArray<ROWS> operator SYM(const DSPVectorArray<ROWS>& a, const DSPVectorArray<ROWS>& b)      \
+  {                                                                                                           \
+    DSPVectorArray<ROWS> y;                                                                                   \
+    for (size_t j = 0; j < ROWS; ++j) y.row((int)j) = op2(OP, a.constRow((int)j), b.constRow((int)j));        \
+    return y;                                                                                                 \
+  }                                                                                                           \
+  template <size_t ROWS>                                                                                      \
+  inline DSPVectorArray<ROWS>& operator SYM##=(DSPVectorArray<ROWS>& a, const DSPVectorArray<ROWS>& b)        \
+  {                                                                                                           \
+    return a = a SYM b;                                                                                       \
+  }
+MLB_TR_ARRAY_OP(+, MLB_OP_ADD)
+MLB_TR_ARRAY_OP(-, MLB_OP_SUBTRACT)
+MLB_TR_ARRAY_OP(*, MLB_OP_MULTIPLY)
+MLB_TR_ARRAY_OP(/, MLB_OP_DIVIDE)
+#undef MLB_TR_ARRAY_OP
+
+// ---- row operations, MLDSPOps.h:1056-1359: pure rearrangements of the symbolic rows (no nodes), except addRows ----
+// output row j = input row src(j), or a zero row where src(j) < 0
+template <size_t OUT, size_t N, class F>
+inline DSPVectorArray<OUT> mapRows(const DSPVectorArray<N>& x, F src)
+{
+  DSPVectorArray<OUT> y;
+  for (size_t j = 0; j < OUT; ++j)
+  {
+    const int k = src((int)j);
+    y.row((int)j) = (k >= 0 && k < (int)N) ? x.constRow(k) : DSPVector(0.f);
+  }
+  return y;
+}
+template <size_t ROWS, size_t N>
+inline DSPVectorArray<ROWS * N> repeatRows(const DSPVectorArray<N>& x)  // the N rows over and over
+{
+  return mapRows<ROWS * N>(x, [](int j) { return j % (int)N; });
+}
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> repeatRows(const DSPVector& x)  // (a DSPVector is a one-row array in the reference)
+{
+  DSPVectorArray<ROWS> y;
+  for (size_t j = 0; j < ROWS; ++j) y.row((int)j) = x;
+  return y;
+}
+template <size_t ROWS, size_t N>
+inline DSPVectorArray<ROWS> stretchRows(const DSPVectorArray<N>& x)  // nearest input row for every output row
+{
+  return mapRows<ROWS>(x, [](int j) { return (int)roundf((j * ((float)N - 1.f)) / ((float)ROWS - 1.f)); });
+}
+template <size_t ROWS, size_t N>
+inline DSPVectorArray<ROWS> zeroPadRows(const DSPVectorArray<N>& x)
+{
+  return mapRows<ROWS>(x, [](int j) { return j < (int)N ? j : -1; });
+}
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> shiftRows(const DSPVectorArray<ROWS>& x, int rowsToShift)  // zeros come in from outside
+{
+  return mapRows<ROWS>(x, [=](int j) { const int k = j - rowsToShift; return (k >= 0 && k < (int)ROWS) ? k : -1; });
+}
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> rotateRows(const DSPVectorArray<ROWS>& x, int rowsToRotate)
+{
+  return mapRows<ROWS>(x, [=](int j) { const int m = (int)ROWS; return (((j - rowsToRotate) % m) + m) % m; });
+}
+template <size_t A, size_t B>
+inline DSPVectorArray<A + B> shuffleRows(const DSPVectorArray<A>& a, const DSPVectorArray<B>& b)  // a0 b0 a1 b1 ..., then the rest
+{
+  DSPVectorArray<A + B> y;
+  size_t ja = 0, jb = 0, jy = 0;
+  while (ja < A || jb < B)
+  {
+    if (ja < A) y.row((int)jy++) = a.constRow((int)ja++);
+    if (jb < B) y.row((int)jy++) = b.constRow((int)jb++);
+  }
+  return y;
+}
+template <size_t ROWS>
+inline DSPVectorArray<(ROWS + 1) / 2> evenRows(const DSPVectorArray<ROWS>& x)
+{
+  return mapRows<(ROWS + 1) / 2>(x, [](int j) { return 2 * j; });
+}
+template <size_t ROWS>
+inline DSPVectorArray<ROWS / 2> oddRows(const DSPVectorArray<ROWS>& x)
+{
+  return mapRows<ROWS / 2>(x, [](int j) { return 2 * j + 1; });
+}
+template <size_t A, size_t B, size_t ROWS>
+inline DSPVectorArray<B - A> separateRows(const DSPVectorArray<ROWS>& x)  // rows [A, B)
+{
+  static_assert(B <= ROWS && A < ROWS, "separateRows: range out of bounds");
+  return mapRows<B - A>(x, [](int j) { return j + (int)A; });
+}
+template <size_t ROWS>
+inline DSPVector addRows(const DSPVectorArray<ROWS>& x)  // from a zero row, left to right (MLDSPOps.h:1349-1359)
+{
+  DSPVector y(0.f);
+  for (size_t j = 0; j < ROWS; ++j) y = add(y, x.constRow((int)j));
+  return y;
+}
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> rowIndex()  // row j filled with j
+{
+  DSPVectorArray<ROWS> y;
+  for (size_t j = 0; j < ROWS; ++j) y.row((int)j) = DSPVector((float)j);
+  return y;
+}
+// columnIndex() = 0, 1, ... 63: exactly interpolateDSPVectorLinear(-1, 63) (interval 1, first value -1 + 1);
+// rangeOpen / rangeClosed as the reference composes them from it (MLDSPOps.h:965-982)
+inline DSPVector columnIndex() { return interpolateDSPVectorLinear(-1.f, 63.f); }
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> columnIndex()
+{
+  return repeatRows<ROWS>(columnIndex());
+}
+inline DSPVector rangeOpen(float start, float end)
+{
+  const float interval = (end - start) / (float)kFloatsPerDSPVector;
+  return columnIndex() * DSPVector(interval) + DSPVector(start);
+}
+inline DSPVector rangeClosed(float start, float end)
+{
+  const float interval = (end - start) / ((float)kFloatsPerDSPVector - 1.f);
+  return columnIndex() * DSPVector(interval) + DSPVector(start);
+}
+
 // interpolateCoeffsLinear, MLDSPFilters.h:32-44
 template <size_t N>
 inline DSPVectorArray<N> interpolateCoeffsLinear(const std::array<float, N> c0, const std::array<float, N> c1)

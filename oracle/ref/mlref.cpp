@@ -1293,6 +1293,34 @@ void mlref_fdn_body(int T, const float* in, float* out)
   }
 }
 
+// ---- tests/cpp/rows_body.h compiled against the reference itself (the tracing layer compiles the same file):
+// DSPVectorArray<ROWS> as a value, the row operations, Bank with array arguments.  in [T][64], out [T][2][64].
+}  // extern "C"
+namespace rows_ref
+{
+using namespace ml;
+#include "../../tests/cpp/rows_body.h"
+struct Ctx
+{
+  DSPVectorDynamic inputs{1}, outputs{2};
+};
+}  // namespace rows_ref
+extern "C"
+{
+void mlref_rows_body(int T, const float* in, float* out)
+{
+  rows_ref::RowsState st;
+  rows_ref::rowsInit(st);
+  rows_ref::Ctx ctx;
+  for (int t = 0; t < T; ++t)
+  {
+    ctx.inputs[0] = DSPVector(in + (size_t)t * 64);
+    rows_ref::rowsProcess(&ctx, &st);
+    store(ctx.outputs[0], out + (size_t)t * 128);
+    store(ctx.outputs[1], out + (size_t)t * 128 + 64);
+  }
+}
+
 // ---- tests/cpp/upsample_body.h compiled against the reference itself (the tracing layer compiles the same file):
 // a process function with state run at twice the rate by Upsample2xFunction<1>, a stateless one at half the rate by
 // Downsample2xFunction<1>.  One instance; in [T][2][64] (frequency, gate rows), out [T][2][64].

@@ -79,6 +79,9 @@ void kitchenProcessFn(AudioContext* ctx, void* state) { kitchenProcess(ctx, stat
 // a process function with state inside Upsample2xFunction<1> (also compiled against the reference)
 #include "upsample_body.h"
 void upsampleProcessFn(AudioContext* ctx, void* state) { upsampleProcess(ctx, state); }
+// DSPVectorArray<ROWS> as a value and the row operations (also compiled against the reference)
+#include "rows_body.h"
+void rowsProcessFn(AudioContext* ctx, void* state) { rowsProcess(ctx, state); }
 // FDN<4> and FDN<6>, recorded as the nodes they are made of (also compiled against the reference)
 #define FDN_SIZE_DELAYS(fdn, times) (void)0  // mlb::tr::FDN sizes its delay lines in setDelaysInSamples
 #include "fdn_body.h"
@@ -117,7 +120,7 @@ int main(int argc, char** argv)
 {
   if (argc < 3)
   {
-    std::fprintf(stderr, "usage: test_trace dump|run|stream <sine|reverb|chain|shelf|kitchen|upsample|fdn|twice|halfrate> ...\n");
+    std::fprintf(stderr, "usage: test_trace dump|run|stream <sine|reverb|chain|shelf|kitchen|upsample|fdn|rows|twice|halfrate> ...\n");
     return 2;
   }
   const std::string mode = argv[1], which = argv[2];
@@ -137,6 +140,8 @@ int main(int argc, char** argv)
   upsampleInit(upsample);
   FdnState fdn;
   fdnInit(fdn);
+  RowsState rows;
+  rowsInit(rows);
   TwiceState twice;
   HalfRateState halfRate;
 
@@ -158,6 +163,7 @@ int main(int argc, char** argv)
   if (which == "kitchen") nIn = 2, nOut = 2, fn = kitchenProcessFn, state = &kitchen;
   if (which == "upsample") nIn = 2, nOut = 2, fn = upsampleProcessFn, state = &upsample;
   if (which == "fdn") nIn = 2, nOut = 2, fn = fdnProcessFn, state = &fdn;
+  if (which == "rows") nIn = 1, nOut = 2, fn = rowsProcessFn, state = &rows;
   if (which == "twice") nIn = 0, nOut = 1, fn = twiceProcess, state = &twice;
   if (which == "halfrate") nIn = 0, nOut = 1, fn = halfRateProcess, state = &halfRate;
   if (!fn) return 2;

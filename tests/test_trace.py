@@ -33,7 +33,7 @@ def build_exe():
             os.path.join(ROOT, "tests", "cpp", "_ref", "reverb_body.inc")):
         subprocess.run([sys.executable, gen], check=True)  # the reference's example bodies: generated, never committed
     hdrs = [os.path.join(ROOT, "include", h) for h in ("mlb200_trace.hpp", "mlb200.hpp", "mlb200_host.hpp", "mlb200.h")]
-    hdrs += [os.path.join(ROOT, "tests", "cpp", f) for f in ("kitchen_body.h", "upsample_body.h", "fdn_body.h")]
+    hdrs += [os.path.join(ROOT, "tests", "cpp", f) for f in ("kitchen_body.h", "upsample_body.h", "fdn_body.h", "rows_body.h")]
     hdrs += [p for p in (os.path.join(ROOT, "tests", "cpp", "_ref", f) for f in ("sine_body.inc", "reverb_body.inc"))
              if os.path.exists(p)]
     if os.path.exists(EXE) and all(os.path.getmtime(EXE) > os.path.getmtime(p) for p in [src] + hdrs):
@@ -197,6 +197,21 @@ def test_fdn_body_same_source_same_bits(ref, port):
         out, _, _ = O.run(g, 1, T, x, state, coef)
         assert_same_bits(out[:, :, 0], want, "fdn body: traced graph vs the reference build of the same source")
     assert np.isfinite(want).all() and np.abs(want).max() > 0.05 and np.sqrt((want[-10:] ** 2).mean()) > 1e-8  # a decaying tail
+
+
+def test_rows_body_same_source_same_bits(ref, port):
+    """tests/cpp/rows_body.h -- ONE source, compiled against the reference and against the tracing layer:
+    DSPVectorArray<ROWS> as a value (rowwise + - * / and compound forms), every row operation of MLDSPOps.h:1056-1383,
+    rowIndex / columnIndex / rangeOpen / rangeClosed, Bank<T, ROWS> with array arguments."""
+    g, coef, state = traced("rows")
+    T = 30
+    n = np.arange(T * 64).reshape(T, 1, 1, 64)
+    x = (np.float32(110.0 / 48000.0) * (1.0 + 0.3 * np.sin(n * 0.002))).astype(np.float32)
+    want = ref.rows_body(x[:, :, 0])
+    for O in (ref, port):
+        out, _, _ = O.run(g, 1, T, x, state, coef)
+        assert_same_bits(out[:, :, 0], want, "rows body: traced graph vs the reference build of the same source")
+    assert np.isfinite(want).all() and np.abs(want[:, 0]).max() > 0.1 and np.abs(want[:, 1]).max() > 0.05
 
 
 def test_a_functor_called_twice_outside_an_upsampler_is_refused():

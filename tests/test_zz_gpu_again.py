@@ -1,6 +1,6 @@
 """GPU parity of the features added after the round's GPU budget was spent: MLB_AGAIN graphs (a functor called again in
-the same vector, mlb200.h: a process function with state inside Upsample2xFunction) and FDN<SIZE> for sizes other than
-8, written out with the nodes it is made of.  Collected LAST on purpose (the file name): these tests were written after the round's GPU
+the same vector, mlb200.h: a process function with state inside Upsample2xFunction) FDN<SIZE> for sizes other than
+8, written out with the nodes it is made of, and the array-valued spellings of the tracing layer.  Collected LAST on purpose (the file name): these tests were written after the round's GPU
 budget was spent and have only been rehearsed on the CPU checkers, so under `pytest -x` a surprise here cannot hide
 the rest of the suite.  The CPU side of the feature: test_abi.py, test_oracle_port_vs_ref.py, test_oracle_golden.py,
 test_trace.py."""
@@ -127,3 +127,22 @@ def test_traced_fdn_body_on_gpu(gpu, port, tmp_path):
     assert_same_bits(got, want, "fdn body traced on the GPU")
     if bindings.ref_available():
         assert_same_bits(got[:, :, 5], O.fdn_body(inp[:, :, 0]), "GPU vs the reference build of fdn_body.h")
+
+
+def test_traced_rows_body_on_gpu(gpu, port, tmp_path):
+    """tests/cpp/rows_body.h (DSPVectorArray<ROWS> as a value, the row operations, Bank with array arguments) traced and
+    run on the device == the reference build of the same source."""
+    from oracle import bindings
+    from tests.test_trace import _run_gpu_case, traced
+    V, T = 33, 12
+    O = bindings.RefOracle() if bindings.ref_available() else port
+    g, coef, state = traced("rows", V)
+    n = np.arange(T * 64).reshape(T, 1, 1, 64)
+    inp = np.ascontiguousarray(np.repeat((np.float32(110.0 / 48000.0) * (1.0 + 0.3 * np.sin(n * 0.002))).astype(np.float32),
+                                         V, axis=2))
+    _run_gpu_case(tmp_path, "rows", V, T, inp)
+    got = np.fromfile(str(tmp_path / "out.bin"), np.float32).reshape(T, g.n_out, V, 64)
+    want, _, _ = O.run(g, V, T, inp, state, coef)
+    assert_same_bits(got, want, "rows body traced on the GPU")
+    if bindings.ref_available():
+        assert_same_bits(got[:, :, 9], O.rows_body(inp[:, :, 0]), "GPU vs the reference build of rows_body.h")
