@@ -264,6 +264,54 @@ inline DSPVector clamp(const DSPVector& x, const DSPVector& lo, const DSPVector&
 // interpolateDSPVectorLinear(start, end), MLDSPOps.h:986-990
 inline DSPVector interpolateDSPVectorLinear(const DSPVector& start, const DSPVector& end) { return op2(MLB_OP_RAMP, start, end); }
 
+// DSPVectorInt: a row of int32 (MLDSPOps.h:370-498).  On the device a row is 64 words either way; the type only says
+// how the words are read, as in the reference (whose int and float vectors share their storage layout).
+class DSPVectorInt
+{
+ public:
+  DSPVector bits;  // the symbolic row
+  DSPVectorInt() : bits(intAsFloat(0)) {}
+  explicit DSPVectorInt(int32_t k) : bits(intAsFloat(k)) {}
+  static float intAsFloat(int32_t k)
+  {
+    float f;
+    std::memcpy(&f, &k, 4);
+    return f;
+  }
+  static DSPVectorInt of(const DSPVector& d)
+  {
+    DSPVectorInt y;
+    y.bits = d;
+    return y;
+  }
+};
+// conversions, MLDSPOps.h:780-820
+inline DSPVectorInt roundFloatToInt(const DSPVector& x) { return DSPVectorInt::of(op1(MLB_OP_ROUND_F2I, x)); }
+inline DSPVectorInt truncateFloatToInt(const DSPVector& x) { return DSPVectorInt::of(op1(MLB_OP_TRUNC_F2I, x)); }
+inline DSPVector intToFloat(const DSPVectorInt& x) { return op1(MLB_OP_INT_TO_FLOAT, x.bits); }
+inline DSPVector unsignedIntToFloat(const DSPVectorInt& x) { return op1(MLB_OP_UNSIGNED_TO_FLOAT, x.bits); }
+// int arithmetic, MLDSPOps.h:713-714
+inline DSPVectorInt addInt32(const DSPVectorInt& a, const DSPVectorInt& b) { return DSPVectorInt::of(op2(MLB_OP_ADD_INT32, a.bits, b.bits)); }
+inline DSPVectorInt subtractInt32(const DSPVectorInt& a, const DSPVectorInt& b) { return DSPVectorInt::of(op2(MLB_OP_SUBTRACT_INT32, a.bits, b.bits)); }
+// comparisons give all-ones / all-zeros masks, MLDSPOps.h:851-856
+#define MLB_TR_CMP(NAME, OP) \
+  inline DSPVectorInt NAME(const DSPVector& a, const DSPVector& b) { return DSPVectorInt::of(op2(OP, a, b)); }
+MLB_TR_CMP(equal, MLB_OP_EQUAL)
+MLB_TR_CMP(notEqual, MLB_OP_NOT_EQUAL)
+MLB_TR_CMP(greaterThan, MLB_OP_GREATER_THAN)
+MLB_TR_CMP(greaterThanOrEqual, MLB_OP_GREATER_EQUAL)
+MLB_TR_CMP(lessThan, MLB_OP_LESS_THAN)
+MLB_TR_CMP(lessThanOrEqual, MLB_OP_LESS_EQUAL)
+#undef MLB_TR_CMP
+// bitwise select(resultIfTrue, resultIfFalse, mask), float and int forms, MLDSPOps.h:886,917
+inline DSPVector select(const DSPVector& a, const DSPVector& b, const DSPVectorInt& m) { return op3(MLB_OP_SELECT, a, b, m.bits); }
+inline DSPVectorInt select(const DSPVectorInt& a, const DSPVectorInt& b, const DSPVectorInt& m)
+{
+  return DSPVectorInt::of(op3(MLB_OP_SELECT, a.bits, b.bits, m.bits));
+}
+// within(x, lo, hi): is x in [lo, hi) -- a mask in a float row, MLDSPOps.h:748
+inline DSPVector within(const DSPVector& x, const DSPVector& lo, const DSPVector& hi) { return op3(MLB_OP_WITHIN, x, lo, hi); }
+
 // DSPVectorArray<ROWS>: ROWS symbolic rows (MLDSPOps.h:94-353); rowwise use only
 template <size_t ROWS>
 class DSPVectorArray
@@ -309,6 +357,34 @@ MLB_TR_ARRAY_OP(-, MLB_OP_SUBTRACT)
 MLB_TR_ARRAY_OP(*, MLB_OP_MULTIPLY)
 MLB_TR_ARRAY_OP(/, MLB_OP_DIVIDE)
 #undef MLB_TR_ARRAY_OP
+
+// the "1" forms, MLDSPOps.h:678-687: the second operand is ONE row, used for every row of the first
+#define MLB_TR_ARRAY_OP1(NAME, OP)                                                               \
+  template <size_t ROWS>                                                                         \
+  inline DSPVectorArray<ROWS> NAME(const DSPVectorArray<ROWS>& a, const DSPVector& b)            \
+  {                                                                                              \
+    DSPVectorArray<ROWS> y;                                                                      \
+    for (size_t j = 0; j < ROWS; ++j) y.row((int)j) = op2(OP, a.constRow((int)j), b);            \
+    return y;                                                                                    \
+  }
+MLB_TR_ARRAY_OP1(add1, MLB_OP_ADD)
+MLB_TR_ARRAY_OP1(subtract1, MLB_OP_SUBTRACT)
+MLB_TR_ARRAY_OP1(multiply1, MLB_OP_MULTIPLY)
+MLB_TR_ARRAY_OP1(divide1, MLB_OP_DIVIDE)
+MLB_TR_ARRAY_OP1(divideApprox1, MLB_OP_DIVIDE_APPROX)
+MLB_TR_ARRAY_OP1(pow1, MLB_OP_POW)
+MLB_TR_ARRAY_OP1(powApprox1, MLB_OP_POW_APPROX)
+MLB_TR_ARRAY_OP1(min1, MLB_OP_MIN)
+MLB_TR_ARRAY_OP1(max1, MLB_OP_MAX)
+#undef MLB_TR_ARRAY_OP1
+// lerp of two arrays with one scalar mixture, MLDSPOps.h:753-775
+template <size_t ROWS>
+inline DSPVectorArray<ROWS> lerp(const DSPVectorArray<ROWS>& a, const DSPVectorArray<ROWS>& b, float m)
+{
+  DSPVectorArray<ROWS> y;
+  for (size_t j = 0; j < ROWS; ++j) y.row((int)j) = lerp(a.constRow((int)j), b.constRow((int)j), DSPVector(m));
+  return y;
+}
 
 // ---- row operations, MLDSPOps.h:1056-1359: pure rearrangements of the symbolic rows (no nodes), except addRows ----
 // output row j = input row src(j), or a zero row where src(j) < 0

@@ -4,7 +4,8 @@
 // DSPVectorArray<ROWS> used as a value, the way a bank of voices is written in the reference: rowwise arithmetic on
 // whole arrays, the row operations of MLDSPOps.h:1056-1383 (repeatRows, stretchRows, zeroPadRows, shiftRows, rotateRows,
 // shuffleRows, evenRows / oddRows, separateRows, concatRows, addRows, rowIndex, columnIndex, rangeOpen / rangeClosed)
-// and Bank<T, ROWS> with array arguments.  One input row (a frequency), two output rows.
+// Bank<T, ROWS> with array arguments, the "1" forms (multiply1, min1, ...), the array lerp, comparisons, select,
+// int <-> float conversions and int arithmetic.  One input row (a frequency), two output rows.
 #pragma once
 
 struct RowsState
@@ -45,6 +46,16 @@ inline void rowsProcess(ROWS_CTX* ctx, void* state)
   DSPVectorArray<4> turned = rotateRows(back, 1) - shiftRows(back, -1) * repeatRows<4>(DSPVector(0.25f));
   DSPVectorArray<6> padded = zeroPadRows<6>(turned);
   DSPVectorArray<3> mid = separateRows<1, 4>(padded);
-  ctx->outputs[0] = addRows(turned) * 0.25f + rangeOpen(0.f, 0.001f);
+  // comparisons, select, int <-> float conversions and int arithmetic on the way out
+  DSPVector mixed = addRows(turned) * 0.25f;
+  DSPVectorInt hot = greaterThan(abs(mixed), DSPVector(0.2f));
+  DSPVector folded = select(mixed * 0.5f + sign(mixed) * 0.1f, mixed, hot);
+  DSPVectorInt steps = addInt32(roundFloatToInt(folded * 8.f), truncateFloatToInt(columnIndex() * 0.125f));
+  DSPVector stair = intToFloat(subtractInt32(steps, DSPVectorInt(3))) * 0.001f;
+  DSPVector gate = select(DSPVector(1.f), DSPVector(0.5f), lessThanOrEqual(f, DSPVector(0.0025f)));
+  folded = folded * gate + select(stair, DSPVector(0.f), notEqual(within(folded, DSPVector(-0.1f), DSPVector(0.1f)), DSPVector(0.f)));
+  DSPVectorArray<4> pushed = max1(min1(multiply1(back, gate), DSPVector(0.9f)), DSPVector(-0.9f));
+  pushed = lerp(pushed, turned, 0.25f);
+  ctx->outputs[0] = folded + addRows(subtract1(pushed, stair)) * 0.01f + rangeOpen(0.f, 0.001f);
   ctx->outputs[1] = addRows(stretchRows<5>(mid)) * 0.2f + columnIndex() * 1e-6f;
 }

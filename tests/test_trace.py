@@ -202,7 +202,8 @@ def test_fdn_body_same_source_same_bits(ref, port):
 def test_rows_body_same_source_same_bits(ref, port):
     """tests/cpp/rows_body.h -- ONE source, compiled against the reference and against the tracing layer:
     DSPVectorArray<ROWS> as a value (rowwise + - * / and compound forms), every row operation of MLDSPOps.h:1056-1383,
-    rowIndex / columnIndex / rangeOpen / rangeClosed, Bank<T, ROWS> with array arguments."""
+    rowIndex / columnIndex / rangeOpen / rangeClosed, Bank<T, ROWS> with array arguments, the "1" forms, the array lerp,
+    comparisons, select, int <-> float conversions, int arithmetic (a symbolic DSPVectorInt)."""
     g, coef, state = traced("rows")
     T = 30
     n = np.arange(T * 64).reshape(T, 1, 1, 64)
