@@ -559,6 +559,14 @@ int mlb_graph_last_kernel_ms(mlb_graph* g, float* ms);
  * are sliced when the PCIe traffic of the call reaches MLB_HOST_SLICE_MIN_MB (env, default 32) MiB. */
 int mlb_graph_last_host_slices(const mlb_graph* g);
 
+/* The graph interpreter's host-side plan, without a device (tests, tools): the pipeline stage of every node (-1 for
+ * nodes that run in no stage, e.g. PARAM), the number of stages and of 8.5-KB shared-memory row slots the program needs,
+ * for a B200 (148 SMs, 227 KB) unless mlb_init has seen another device; MLB_STAGES (env) forces the stage count as it
+ * does for mlb_graph_create.  Fails like mlb_graph_create does when the graph cannot be planned (too many live rows,
+ * a stage depending on too many stages).  Any pointer may be NULL. */
+int mlb_graph_plan(const mlb_node* nodes, int n_nodes, const int32_t* outs, int n_out, int n_voices, unsigned flags,
+                   int32_t* stage_of, int32_t* n_stages, int32_t* n_row_slots);
+
 
 /* Events -> signals -> chain in one call, host buffers, only the event records going up ("contract E"):
  * what a synth built on the reference does per top-level buffer -- EventsToSignals::processVector

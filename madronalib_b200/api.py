@@ -59,6 +59,7 @@ def lib() -> ctypes.CDLL:
                                    ctypes.c_uint, ctypes.POINTER(_vp)]
     L.mlb_graph_destroy.argtypes = [_vp]
     L.mlb_graph_layout_of.argtypes = [_vp, _vp]
+    L.mlb_graph_plan.argtypes = [_vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_uint, _vp, _vp, _vp]
     L.mlb_graph_kernel_name.restype = ctypes.c_char_p
     L.mlb_graph_kernel_name.argtypes = [_vp]
     L.mlb_graph_set_coefs.argtypes = [_vp, _vp]
@@ -257,6 +258,17 @@ def map_host(op: str, x1: np.ndarray, x2: Optional[np.ndarray] = None,
 def map_device(op: str, x1, x2, x3, y, n_rows: int, stream: int = 0) -> None:
     _check(lib().mlb_map_device(OP_ID[op.upper()], _ptr(x1), _ptr(x2), _ptr(x3), _ptr(y), n_rows,
                                 stream or None))
+
+
+def plan(spec: GraphSpec, n_voices: int, flags: int = 0):
+    """The graph interpreter's host-side plan, no device needed (mlb_graph_plan): (stage of every node -- -1 for PARAM
+    and the like --, number of stages, number of shared-memory row slots)."""
+    n = spec.n_nodes
+    stage = (ctypes.c_int32 * max(1, n))()
+    ns, rows = ctypes.c_int32(), ctypes.c_int32()
+    _check(lib().mlb_graph_plan(spec.c_nodes(), n, spec.c_outs(), spec.n_out, int(n_voices), int(flags), stage,
+                                ctypes.byref(ns), ctypes.byref(rows)))
+    return list(stage)[:n], int(ns.value), int(rows.value)
 
 
 class VoiceGraph:

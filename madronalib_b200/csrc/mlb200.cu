@@ -1191,6 +1191,45 @@ static int build_generic(mlb_graph* g)
 
 static int size_functor_memory(mlb_graph* g);
 
+// The interpreter's host-side plan for a graph, WITHOUT a device: which pipeline stage every node goes to and how many
+// shared-memory row slots the program needs (assuming a B200: 148 SMs, 227 KB of shared memory per CTA, unless a device
+// has been initialised).  The same build_generic() that mlb_graph_create runs; lets the planner's rules -- a feedback
+// loop, a paired second row, a functor and its MLB_AGAIN calls stay in one stage; the row pool fits -- be tested on a CPU.
+extern "C" int mlb_graph_plan(const mlb_node* nodes, int n_nodes, const int32_t* outs, int n_out, int n_voices,
+                              unsigned flags, int32_t* stage_of, int32_t* n_stages, int32_t* n_row_slots)
+{
+  if (n_voices <= 0) return fail(MLB_ERR_INVALID, "n_voices must be positive");
+  if (n_out < 0 || (n_out > 0 && !outs)) return fail(MLB_ERR_INVALID, "bad outs");
+  mlb_layout lay;
+  std::vector<int32_t> so(std::max(1, n_nodes)), co(std::max(1, n_nodes));
+  int rc = mlb_graph_layout(nodes, n_nodes, &lay, so.data(), co.data());
+  if (rc != MLB_OK) return rc;
+  for (int c = 0; c < n_out; ++c)
+    if (outs[c] < 0 || outs[c] >= n_nodes) return fail(MLB_ERR_INVALID, "outs[%d] out of range", c);
+  const int sm_saved = g_sm_count;
+  const size_t smem_saved = g_smem_optin;
+  if (g_sm_count == 0) g_sm_count = 148;
+  if (g_smem_optin == 0) g_smem_optin = 232448;
+  mlb_graph g;  // host fields only: nothing here touches the CUDA runtime
+  g.nodes.assign(nodes, nodes + n_nodes);
+  g.outs.assign(outs, outs + n_out);
+  g.st_off = so, g.co_off = co, g.layout = lay;
+  g.V = n_voices, g.flags = flags, g.exact = !(flags & MLB_GRAPH_FAST);
+  rc = build_generic(&g);
+  g_sm_count = sm_saved, g_smem_optin = smem_saved;
+  if (rc != MLB_OK) return rc;
+  if (stage_of)
+  {
+    for (int i = 0; i < n_nodes; ++i) stage_of[i] = -1;  // PARAM nodes and the like belong to no stage
+    for (int s = 0; s < (int)g.gstages.size(); ++s)
+      for (int k = g.gstages[s].node_begin; k < g.gstages[s].node_end; ++k)
+        if (g.gnodes[k].src_node >= 0) stage_of[g.gnodes[k].src_node] = s;
+  }
+  if (n_stages) *n_stages = g.n_stages;
+  if (n_row_slots) *n_row_slots = g.n_slots;
+  return MLB_OK;
+}
+
 extern "C" int mlb_graph_create(const mlb_node* nodes, int n_nodes, const int32_t* outs, int n_out,
                                 int n_voices, unsigned flags, mlb_graph** out_graph)
 {
