@@ -1,8 +1,8 @@
 """GPU parity of the features added after the round's GPU budget was spent: MLB_AGAIN graphs (a functor called again in
 the same vector, mlb200.h: a process function with state inside Upsample2xFunction) FDN<SIZE> for sizes other than
-8, written out with the nodes it is made of, and the array-valued spellings of the tracing layer.  Collected LAST on purpose (the file name): these tests were written after the round's GPU
-budget was spent and have only been rehearsed on the CPU checkers, so under `pytest -x` a surprise here cannot hide
-the rest of the suite.  The CPU side of the feature: test_abi.py, test_oracle_port_vs_ref.py, test_oracle_golden.py,
+8, written out with the nodes it is made of, and the array-valued spellings of the tracing layer.  Collected last (the file name): these tests were written when the round's GPU budget was
+nearly spent and were rehearsed on the CPU checkers first; they met the hardware in the round's last, 7-second call
+(13 passed, profiles/gpu_tests_late_r2.txt).  The CPU side of the feature: test_abi.py, test_oracle_port_vs_ref.py, test_oracle_golden.py,
 test_trace.py."""
 import os
 
