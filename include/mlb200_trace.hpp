@@ -825,6 +825,8 @@ class ADSR : public FixedFilter<MLB_OP_ADSR, 4>
 class Allpass1 : public FixedFilter<MLB_OP_ALLPASS1, 1>
 {
  public:
+  Allpass1() = default;
+  Allpass1(float a) { coeffs = {a}; }  // the reference's only constructor, MLDSPFilters.h:927
   static Coeffs makeCoeffs(float d) { return {mlb_coeffs_allpass1(d)}; }
 };
 

@@ -1293,6 +1293,39 @@ void mlref_fdn_body(int T, const float* in, float* out)
   }
 }
 
+// ---- tests/cpp/rest_body.h compiled against the reference itself (the tracing layer compiles the same file): the functor
+// spellings the other shared bodies leave out, FDN<8> included.  One instance; in [T][2][64], out [T][2][64].
+}  // extern "C"
+namespace rest_ref
+{
+using namespace ml;
+#define FDN_SIZE_DELAYS(fdn, times)                                                      \
+  for (size_t n_ = 0; n_ < (times).size(); ++n_)                                         \
+  (fdn).mDelays[n_].setMaxDelayInSamples(static_cast<float>(std::max(1, static_cast<int>((times)[n_] - kFloatsPerDSPVector))))
+#include "../../tests/cpp/rest_body.h"
+#undef FDN_SIZE_DELAYS
+struct Ctx
+{
+  DSPVectorDynamic inputs{2}, outputs{2};
+};
+}  // namespace rest_ref
+extern "C"
+{
+void mlref_rest_body(int T, const float* in, float* out)
+{
+  rest_ref::RestState st;
+  rest_ref::restInit(st);
+  rest_ref::Ctx ctx;
+  for (int t = 0; t < T; ++t)
+  {
+    ctx.inputs[0] = DSPVector(in + (size_t)t * 128);
+    ctx.inputs[1] = DSPVector(in + (size_t)t * 128 + 64);
+    rest_ref::restProcess(&ctx, &st);
+    store(ctx.outputs[0], out + (size_t)t * 128);
+    store(ctx.outputs[1], out + (size_t)t * 128 + 64);
+  }
+}
+
 // ---- tests/cpp/rows_body.h compiled against the reference itself (the tracing layer compiles the same file):
 // DSPVectorArray<ROWS> as a value, the row operations, Bank with array arguments.  in [T][64], out [T][2][64].
 }  // extern "C"

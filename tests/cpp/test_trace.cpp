@@ -79,6 +79,11 @@ void kitchenProcessFn(AudioContext* ctx, void* state) { kitchenProcess(ctx, stat
 // a process function with state inside Upsample2xFunction<1> (also compiled against the reference)
 #include "upsample_body.h"
 void upsampleProcessFn(AudioContext* ctx, void* state) { upsampleProcess(ctx, state); }
+// the functor spellings the other bodies leave out (also compiled against the reference)
+#define FDN_SIZE_DELAYS(fdn, times) (void)0
+#include "rest_body.h"
+#undef FDN_SIZE_DELAYS
+void restProcessFn(AudioContext* ctx, void* state) { restProcess(ctx, state); }
 // DSPVectorArray<ROWS> as a value and the row operations (also compiled against the reference)
 #include "rows_body.h"
 void rowsProcessFn(AudioContext* ctx, void* state) { rowsProcess(ctx, state); }
@@ -120,7 +125,7 @@ int main(int argc, char** argv)
 {
   if (argc < 3)
   {
-    std::fprintf(stderr, "usage: test_trace dump|run|stream <sine|reverb|chain|shelf|kitchen|upsample|fdn|rows|twice|halfrate> ...\n");
+    std::fprintf(stderr, "usage: test_trace dump|run|stream <sine|reverb|chain|shelf|kitchen|upsample|fdn|rows|rest|twice|halfrate> ...\n");
     return 2;
   }
   const std::string mode = argv[1], which = argv[2];
@@ -142,6 +147,8 @@ int main(int argc, char** argv)
   fdnInit(fdn);
   RowsState rows;
   rowsInit(rows);
+  RestState rest;
+  restInit(rest);
   TwiceState twice;
   HalfRateState halfRate;
 
@@ -164,6 +171,7 @@ int main(int argc, char** argv)
   if (which == "upsample") nIn = 2, nOut = 2, fn = upsampleProcessFn, state = &upsample;
   if (which == "fdn") nIn = 2, nOut = 2, fn = fdnProcessFn, state = &fdn;
   if (which == "rows") nIn = 1, nOut = 2, fn = rowsProcessFn, state = &rows;
+  if (which == "rest") nIn = 2, nOut = 2, fn = restProcessFn, state = &rest;
   if (which == "twice") nIn = 0, nOut = 1, fn = twiceProcess, state = &twice;
   if (which == "halfrate") nIn = 0, nOut = 1, fn = halfRateProcess, state = &halfRate;
   if (!fn) return 2;

@@ -33,7 +33,7 @@ def build_exe():
             os.path.join(ROOT, "tests", "cpp", "_ref", "reverb_body.inc")):
         subprocess.run([sys.executable, gen], check=True)  # the reference's example bodies: generated, never committed
     hdrs = [os.path.join(ROOT, "include", h) for h in ("mlb200_trace.hpp", "mlb200.hpp", "mlb200_host.hpp", "mlb200.h")]
-    hdrs += [os.path.join(ROOT, "tests", "cpp", f) for f in ("kitchen_body.h", "upsample_body.h", "fdn_body.h", "rows_body.h")]
+    hdrs += [os.path.join(ROOT, "tests", "cpp", f) for f in ("kitchen_body.h", "upsample_body.h", "fdn_body.h", "rows_body.h", "rest_body.h")]
     hdrs += [p for p in (os.path.join(ROOT, "tests", "cpp", "_ref", f) for f in ("sine_body.inc", "reverb_body.inc"))
              if os.path.exists(p)]
     if os.path.exists(EXE) and all(os.path.getmtime(EXE) > os.path.getmtime(p) for p in [src] + hdrs):
@@ -213,6 +213,34 @@ def test_rows_body_same_source_same_bits(ref, port):
         out, _, _ = O.run(g, 1, T, x, state, coef)
         assert_same_bits(out[:, :, 0], want, "rows body: traced graph vs the reference build of the same source")
     assert np.isfinite(want).all() and np.abs(want[:, 0]).max() > 0.1 and np.abs(want[:, 1]).max() > 0.05
+
+
+def rest_input(T, V=1):
+    """a noise burst (then silence) and a delay-time row sweeping 70 .. 330 samples"""
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((T, 1, 1, 64)) * 0.3).astype(np.float32)
+    x[T // 2:] = 0
+    n = np.arange(T * 64).reshape(T, 1, 1, 64)
+    d = (np.float32(200.0) + np.float32(130.0) * np.sin(n * 0.0031)).astype(np.float32)
+    return np.ascontiguousarray(np.repeat(np.concatenate([x, d], axis=1), V, axis=2))
+
+
+def test_rest_body_same_source_same_bits(ref, port):
+    """tests/cpp/rest_body.h -- ONE source, compiled against the reference and against the tracing layer: ImpulseGen,
+    OneShotGen, Interpolator1, Allpass1, Differentiator, FractionalDelay (fixed and per-sample), IntegerDelay
+    (per-sample), Allpass<FractionalDelay>, PitchbendableDelay used directly, and the fused FDN<8> node."""
+    from madronalib_b200.graph import OP_NAME
+    g, coef, state = traced("rest")
+    names = {OP_NAME[op] for op in g.ops}
+    assert {"IMPULSE", "ONESHOT", "INTERPOLATOR1", "ALLPASS1", "DIFFERENTIATOR", "FRACTIONAL_DELAY", "FRACTIONAL_DELAY_VAR",
+            "INTEGER_DELAY_VAR", "ALLPASS_FRAC", "PITCHBEND_DELAY", "FDN8", "FDN8_R"} <= names
+    T = 48
+    x = rest_input(T)
+    want = ref.rest_body(x[:, :, 0])
+    for O in (ref, port):
+        out, _, _ = O.run(g, 1, T, x, state, coef)
+        assert_same_bits(out[:, :, 0], want, "rest body: traced graph vs the reference build of the same source")
+    assert np.isfinite(want).all() and np.abs(want).max() > 0.05 and np.abs(want[-6:]).max() > 1e-6
 
 
 def test_a_functor_called_twice_outside_an_upsampler_is_refused():
