@@ -278,8 +278,10 @@ typedef struct mlb_node {
  * (MLDSPFunctional.h:114-160: fn(upsampled first half), fn(upsampled second half); the reference's tutorial wraps a
  * sine generator this way, examples/tutorial/dspOpsExample.cpp:100-102).  Allowed for ops that have state or
  * coefficients and no ring in delay memory (a ring's write index is the vector count, MLDSPFilters.h:836-851 run
- * once per vector), and not for INPUT / PARAM / FEEDBACK_* / FDN8* / HALFBAND_* / DOWN2X_*.  Such graphs run on the
- * graph interpreter; node t and its AGAIN nodes are kept in one pipeline stage. */
+ * once per vector), and not for INPUT / PARAM / FEEDBACK_* / FDN8* / HALFBAND_UP_2 / DOWN2X_*.  (HALFBAND_UP and
+ * HALFBAND_DOWN may be: the stages of an Upsampler(octaves) / Downsampler(octaves) run their one filter several times per
+ * vector, MLDSPFilters.h:1345-1372,1427-1448; a HALFBAND_UP called again gets its own HALFBAND_UP_2.)  Such graphs run on
+ * the graph interpreter; node t and its AGAIN nodes are kept in one pipeline stage. */
 #define MLB_AGAIN(t) (-1 - (t))
 #define MLB_AGAIN_TARGET(iarg) (-1 - (iarg))
 

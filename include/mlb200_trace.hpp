@@ -32,9 +32,10 @@
 // that it can be set per instance afterwards.  Coefficient design (makeCoeffs) runs on the host through
 // mlb_coeffs_* = the reference's own libm calls.
 //
-// A functor object records ONE node per vector.  The exception is the process function handed to
-// Upsample2xFunction<N> (MLDSPFunctional.h:114-160), which the wrapper runs twice: the functors inside it are called a
-// second time, and record MLB_AGAIN nodes (mlb200.h) -- further calls of the same functor, same state.
+// A functor object called more than once in a vector -- by Upsample2xFunction<N> (MLDSPFunctional.h:114-160), which runs
+// its process function twice, or in an oversampled loop between an Upsampler and a Downsampler -- ticks once per call, as
+// the reference's objects do: the further calls record MLB_AGAIN nodes (mlb200.h), same functor, same state.  Functors
+// with a delay ring cannot be called again (the graph is refused when trace() lays it out).
 //
 // Header only; link against libmlb200.so.  No sample arithmetic happens on the CPU here.
 #pragma once
@@ -518,10 +519,11 @@ class Functor
                   "tick on every second vector only)");
     if (lastEpoch_ == r.epoch)
     {
-      // called again in the same vector: only inside the second run of a process function by Upsample2xFunction,
-      // where the reference object would simply tick a second time (MLDSPFunctional.h:138-140)
-      if (r.repeatDepth == 0 || firstNode_ < 0)
-        throw Error(MLB_ERR_UNSUPPORTED, "mlb::tr: a functor object may be called once per vector");
+      // called again in the same vector: the reference object would simply tick once more (a process function run twice
+      // by Upsample2xFunction, MLDSPFunctional.h:138-140; an oversampled loop between an Upsampler and a Downsampler).
+      // Recorded as a further call of the first node (MLB_AGAIN); a functor with a delay ring cannot be -- trace()
+      // reports that when it lays the graph out.
+      if (firstNode_ < 0) throw Error(MLB_ERR_UNSUPPORTED, "mlb::tr: this object cannot be called again in the same vector");
       r.pendingAgain = firstNode_, r.pendingOwner = nullptr;
       return;
     }
@@ -1189,6 +1191,95 @@ class Upsample2xFunction : public Functor
     in.row(0) = x;
     return (*this)([&](const inputType a) { return fn(a.constRow(0)); }, in);
   }
+};
+
+// Upsampler(octaves) / Downsampler(octaves), MLDSPFilters.h:1316-1473, used inside ONE process function: write a vector,
+// read 2^octaves vectors at the higher rate, process them, write them to the Downsampler, read one vector back -- an
+// oversampled loop.  Stage j of either cascade owns one half-band filter and runs it 2^j (up) / 2^(octaves-1-j) (down)
+// times per vector: the first call records a HALFBAND node, the others MLB_AGAIN calls of it.  (The block-rate-changing
+// use -- several process calls per write -- is the mlb_resampler_* bank.)
+class Upsampler
+{
+  int octaves_;
+  std::vector<int> firstNode_, firstEpoch_;  // per stage: the filter's first call in the current pass
+  std::vector<DSPVector> rows_;
+  size_t readIdx_ = 0;
+
+ public:
+  explicit Upsampler(int octavesUp) : octaves_(octavesUp), firstNode_((size_t)octavesUp, -1), firstEpoch_((size_t)octavesUp, 0) {}
+  void clear() {}
+  void write(const DSPVector& x)
+  {
+    Recorder& r = Recorder::get();
+    rows_.assign(1, x);
+    for (int j = 0; j < octaves_; ++j)
+    {
+      std::vector<DSPVector> next;
+      for (const DSPVector& src : rows_)
+      {
+        const int in = src.resolve();
+        const bool again = firstEpoch_[(size_t)j] == r.epoch;
+        const int up = r.addNode(MLB_OP_HALFBAND_UP, {in}, again ? MLB_AGAIN(firstNode_[(size_t)j]) : 0);
+        if (!again) firstNode_[(size_t)j] = up, firstEpoch_[(size_t)j] = r.epoch;
+        next.push_back(DSPVector::ofNode(up));
+        next.push_back(DSPVector::ofNode(r.addNode(MLB_OP_HALFBAND_UP_2, {up})));
+      }
+      rows_.swap(next);
+    }
+    readIdx_ = 0;
+  }
+  DSPVector read()  // after a write, 1 << octaves reads are available
+  {
+    if (readIdx_ >= rows_.size()) throw Error(MLB_ERR_INVALID, "mlb::tr: Upsampler::read past the vectors of the last write");
+    return rows_[readIdx_++];
+  }
+};
+class Downsampler
+{
+  int octaves_;
+  std::vector<int> firstNode_, firstEpoch_;
+  std::vector<DSPVector> buffers_;  // 2 per octave + the output, as in the reference
+  uint32_t counter_ = 0;
+  int epoch_ = 0;
+
+ public:
+  explicit Downsampler(int octavesDown)
+      : octaves_(octavesDown), firstNode_((size_t)octavesDown, -1), firstEpoch_((size_t)octavesDown, 0),
+        buffers_((size_t)(2 * octavesDown + 1))
+  {
+  }
+  void clear() {}
+  bool write(const DSPVector& v)  // true when a new output vector is ready (every 2^octaves writes)
+  {
+    Recorder& r = Recorder::get();
+    if (epoch_ != r.epoch)
+    {
+      if (counter_ != 0)
+        throw Error(MLB_ERR_UNSUPPORTED, "mlb::tr: a Downsampler must be written 2^octaves times in every vector");
+      epoch_ = r.epoch;
+    }
+    if (octaves_ == 0)
+    {
+      buffers_[0] = v;
+      return true;
+    }
+    buffers_[counter_ & 1u] = v;
+    uint32_t mask = 1;
+    for (int h = 0; h < octaves_; ++h)
+    {
+      if (!(counter_ & mask)) break;  // an octave runs when its bit and all lesser bits are 1
+      mask <<= 1;
+      const bool b1 = (counter_ & mask) != 0;
+      const int x1 = buffers_[(size_t)(2 * h)].resolve(), x2 = buffers_[(size_t)(2 * h + 1)].resolve();
+      const bool again = firstEpoch_[(size_t)h] == r.epoch;
+      const int down = r.addNode(MLB_OP_HALFBAND_DOWN, {x1, x2}, again ? MLB_AGAIN(firstNode_[(size_t)h]) : 0);
+      if (!again) firstNode_[(size_t)h] = down, firstEpoch_[(size_t)h] = r.epoch;
+      buffers_[(size_t)(2 * h + 2 + (b1 ? 1 : 0))] = DSPVector::ofNode(down);
+    }
+    counter_ = (counter_ + 1u) & ((1u << octaves_) - 1u);
+    return counter_ == 0;
+  }
+  DSPVector read() const { return buffers_.back(); }
 };
 
 // Downsample2xFunction<IN_ROWS>, MLDSPFunctional.h:166-223: on every second vector the input (this vector and the

@@ -100,9 +100,8 @@ static bool again_allowed(int op)
   switch (op)
   {
     case MLB_OP_INPUT: case MLB_OP_PARAM: case MLB_OP_FEEDBACK_READ: case MLB_OP_FEEDBACK_WRITE: case MLB_OP_FDN8:
-    case MLB_OP_FDN8_R: case MLB_OP_HALFBAND_UP: case MLB_OP_HALFBAND_UP_2: case MLB_OP_HALFBAND_DOWN:
-    case MLB_OP_DOWN2X_IN: case MLB_OP_DOWN2X_OUT:
-      return false;
+    case MLB_OP_FDN8_R: case MLB_OP_HALFBAND_UP_2: case MLB_OP_DOWN2X_IN: case MLB_OP_DOWN2X_OUT:
+      return false;  // (a HALFBAND_UP called again has its own HALFBAND_UP_2 reading ITS second row)
     default: return true;
   }
 }

@@ -195,6 +195,15 @@ class RefOracle(_Oracle):
         assert self.lib.mlref_fdn_run(size, inp.shape[0], _ptr(inp), _ptr(out), _ptr(t), _ptr(c), _ptr(g)) == 0
         return out
 
+    def oversample_body(self, inp: np.ndarray) -> np.ndarray:
+        """tests/cpp/oversample_body.h compiled against the reference (one instance); inp [T][1][64] -> [T][2][64]."""
+        inp = np.ascontiguousarray(inp, np.float32)
+        out = np.empty((inp.shape[0], 2, 64), np.float32)
+        self.lib.mlref_oversample_body.argtypes = [ctypes.c_int, _vp, _vp]
+        self.lib.mlref_oversample_body.restype = None
+        self.lib.mlref_oversample_body(inp.shape[0], _ptr(inp), _ptr(out))
+        return out
+
     def rest_body(self, inp: np.ndarray) -> np.ndarray:
         """tests/cpp/rest_body.h compiled against the reference (one instance); inp [T][2][64] -> [T][2][64]."""
         inp = np.ascontiguousarray(inp, np.float32)

@@ -1343,8 +1343,8 @@ mlport_graph* mlport_graph_create(const mlb_node* nodes, int n_nodes, const int3
       const int t = MLB_AGAIN_TARGET(nodes[i].iarg);
       const int op = nodes[i].op;
       if (t >= i || nodes[t].op != op || g->again[t] >= 0 || (b == 0 && c == 0) || op == MLB_OP_FEEDBACK_READ ||
-          op == MLB_OP_FDN8 || op == MLB_OP_FDN8_R || op == MLB_OP_HALFBAND_UP || op == MLB_OP_HALFBAND_UP_2 ||
-          op == MLB_OP_HALFBAND_DOWN || op == MLB_OP_DOWN2X_IN || op == MLB_OP_DOWN2X_OUT)
+          op == MLB_OP_FDN8 || op == MLB_OP_FDN8_R || op == MLB_OP_HALFBAND_UP_2 || op == MLB_OP_DOWN2X_IN ||
+          op == MLB_OP_DOWN2X_OUT)
       {
         mlport_graph_destroy(g);
         return NULL;

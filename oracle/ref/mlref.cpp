@@ -1293,6 +1293,34 @@ void mlref_fdn_body(int T, const float* in, float* out)
   }
 }
 
+// ---- tests/cpp/oversample_body.h compiled against the reference itself (the tracing layer compiles the same file):
+// oversampled loops between an Upsampler and a Downsampler inside one process call.  in [T][64], out [T][2][64].
+}  // extern "C"
+namespace oversample_ref
+{
+using namespace ml;
+#include "../../tests/cpp/oversample_body.h"
+struct Ctx
+{
+  DSPVectorDynamic inputs{1}, outputs{2};
+};
+}  // namespace oversample_ref
+extern "C"
+{
+void mlref_oversample_body(int T, const float* in, float* out)
+{
+  oversample_ref::OversampleState st;
+  oversample_ref::oversampleInit(st);
+  oversample_ref::Ctx ctx;
+  for (int t = 0; t < T; ++t)
+  {
+    ctx.inputs[0] = DSPVector(in + (size_t)t * 64);
+    oversample_ref::oversampleProcess(&ctx, &st);
+    store(ctx.outputs[0], out + (size_t)t * 128);
+    store(ctx.outputs[1], out + (size_t)t * 128 + 64);
+  }
+}
+
 // ---- tests/cpp/rest_body.h compiled against the reference itself (the tracing layer compiles the same file): the functor
 // spellings the other shared bodies leave out, FDN<8> included.  One instance; in [T][2][64], out [T][2][64].
 }  // extern "C"

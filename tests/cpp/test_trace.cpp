@@ -79,6 +79,9 @@ void kitchenProcessFn(AudioContext* ctx, void* state) { kitchenProcess(ctx, stat
 // a process function with state inside Upsample2xFunction<1> (also compiled against the reference)
 #include "upsample_body.h"
 void upsampleProcessFn(AudioContext* ctx, void* state) { upsampleProcess(ctx, state); }
+// oversampled loops between an Upsampler and a Downsampler (also compiled against the reference)
+#include "oversample_body.h"
+void oversampleProcessFn(AudioContext* ctx, void* state) { oversampleProcess(ctx, state); }
 // the functor spellings the other bodies leave out (also compiled against the reference)
 #define FDN_SIZE_DELAYS(fdn, times) (void)0
 #include "rest_body.h"
@@ -92,15 +95,15 @@ void rowsProcessFn(AudioContext* ctx, void* state) { rowsProcess(ctx, state); }
 #include "fdn_body.h"
 #undef FDN_SIZE_DELAYS
 void fdnProcessFn(AudioContext* ctx, void* state) { fdnProcess(ctx, state); }
-// calling a functor twice per vector OUTSIDE an Upsample2xFunction stays an error
+// a functor with a delay ring cannot be called twice per vector (its ring is written once per vector)
 struct TwiceState
 {
-  SineGen osc;
+  IntegerDelay delay{100};
 };
 void twiceProcess(AudioContext* ctx, void* state)
 {
   auto s = static_cast<TwiceState*>(state);
-  ctx->outputs[0] = s->osc(0.01f) + s->osc(0.02f);
+  ctx->outputs[0] = s->delay(DSPVector(0.01f)) + s->delay(DSPVector(0.02f));
 }
 // ... and so does a functor inside the process function of a Downsample2xFunction
 struct HalfRateState
@@ -125,7 +128,7 @@ int main(int argc, char** argv)
 {
   if (argc < 3)
   {
-    std::fprintf(stderr, "usage: test_trace dump|run|stream <sine|reverb|chain|shelf|kitchen|upsample|fdn|rows|rest|twice|halfrate> ...\n");
+    std::fprintf(stderr, "usage: test_trace dump|run|stream <sine|reverb|chain|shelf|kitchen|upsample|fdn|rows|rest|oversample|twice|halfrate> ...\n");
     return 2;
   }
   const std::string mode = argv[1], which = argv[2];
@@ -149,6 +152,8 @@ int main(int argc, char** argv)
   rowsInit(rows);
   RestState rest;
   restInit(rest);
+  OversampleState oversample;
+  oversampleInit(oversample);
   TwiceState twice;
   HalfRateState halfRate;
 
@@ -172,6 +177,7 @@ int main(int argc, char** argv)
   if (which == "fdn") nIn = 2, nOut = 2, fn = fdnProcessFn, state = &fdn;
   if (which == "rows") nIn = 1, nOut = 2, fn = rowsProcessFn, state = &rows;
   if (which == "rest") nIn = 2, nOut = 2, fn = restProcessFn, state = &rest;
+  if (which == "oversample") nIn = 1, nOut = 2, fn = oversampleProcessFn, state = &oversample;
   if (which == "twice") nIn = 0, nOut = 1, fn = twiceProcess, state = &twice;
   if (which == "halfrate") nIn = 0, nOut = 1, fn = halfRateProcess, state = &halfRate;
   if (!fn) return 2;

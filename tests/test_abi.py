@@ -123,14 +123,22 @@ def test_again_nodes_share_the_words_of_their_functor(L):
     bad.ops, bad.ins, bad.iargs = list(h.ops) + [h.ops[s1]], list(h.ins) + [h.ins[s1]], list(h.iargs) + [-1 - s2]
     assert L.mlb_graph_layout(bad.c_nodes(), 4, ctypes.byref(lay), None, None) == 1
     # functors with a ring in delay memory, stateless ops and the paired / feedback nodes cannot be called again
-    for name, nin in (("INTEGER_DELAY", 1), ("ALLPASS_PB", 2), ("ADD", 2), ("HALFBAND_UP", 1), ("FDN8", 1)):
+    for name, nin in (("INTEGER_DELAY", 1), ("ALLPASS_PB", 2), ("ADD", 2), ("DOWN2X_IN", 1), ("FDN8", 1)):
         q = graph.GraphSpec()
         ins = [q.input(k) for k in range(nin)]
         first = q.node(name, *ins)
         q.ops.append(q.ops[first]), q.ins.append(q.ins[first]), q.iargs.append(-1 - first)
         assert L.mlb_graph_layout(q.c_nodes(), q.n_nodes, ctypes.byref(lay), None, None) == 1, name
         assert b"cannot be called again" in L.mlb_last_error()
-    # ... while a functor with a member row but no ring can (LinearGlide keeps mCurrVec)
+    # ... while the half-band filters can (the stages of an Upsampler / Downsampler run theirs several times per vector)
+    q = graph.GraphSpec()
+    x = q.input(0)
+    u1 = q.node("HALFBAND_UP", x)
+    u1b = q.node("HALFBAND_UP_2", u1)
+    u2 = q.again(u1, u1b)
+    q.output(q.node("HALFBAND_UP_2", u2))
+    assert L.mlb_graph_layout(q.c_nodes(), q.n_nodes, ctypes.byref(lay), None, None) == 0 and lay.n_state_words == 9
+    # ... and so can a functor with a member row but no ring (LinearGlide keeps mCurrVec)
     q = graph.GraphSpec()
     first = q.node("GLIDE", q.input(0))
     q.output(q.again(first, q.input(1)))

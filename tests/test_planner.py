@@ -93,7 +93,7 @@ def test_a_network_too_wide_for_shared_memory_is_refused():
 
 def test_traced_bodies_plan(monkeypatch):
     from tests.test_trace import traced
-    for case in ("kitchen", "upsample", "fdn", "rows", "rest", "shelf", "chain"):
+    for case in ("kitchen", "upsample", "fdn", "rows", "rest", "oversample", "shelf", "chain"):
         g, _, _ = traced(case)
         for s, (stage, n_stages, rows) in _plans(g, 36, monkeypatch):
             _check_rules(g, stage)

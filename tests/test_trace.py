@@ -33,7 +33,7 @@ def build_exe():
             os.path.join(ROOT, "tests", "cpp", "_ref", "reverb_body.inc")):
         subprocess.run([sys.executable, gen], check=True)  # the reference's example bodies: generated, never committed
     hdrs = [os.path.join(ROOT, "include", h) for h in ("mlb200_trace.hpp", "mlb200.hpp", "mlb200_host.hpp", "mlb200.h")]
-    hdrs += [os.path.join(ROOT, "tests", "cpp", f) for f in ("kitchen_body.h", "upsample_body.h", "fdn_body.h", "rows_body.h", "rest_body.h")]
+    hdrs += [os.path.join(ROOT, "tests", "cpp", f) for f in ("kitchen_body.h", "upsample_body.h", "fdn_body.h", "rows_body.h", "rest_body.h", "oversample_body.h")]
     hdrs += [p for p in (os.path.join(ROOT, "tests", "cpp", "_ref", f) for f in ("sine_body.inc", "reverb_body.inc"))
              if os.path.exists(p)]
     if os.path.exists(EXE) and all(os.path.getmtime(EXE) > os.path.getmtime(p) for p in [src] + hdrs):
@@ -243,10 +243,31 @@ def test_rest_body_same_source_same_bits(ref, port):
     assert np.isfinite(want).all() and np.abs(want).max() > 0.05 and np.abs(want[-6:]).max() > 1e-6
 
 
-def test_a_functor_called_twice_outside_an_upsampler_is_refused():
+def test_oversample_body_same_source_same_bits(ref, port):
+    """tests/cpp/oversample_body.h -- ONE source, compiled against the reference and against the tracing layer: oversampled
+    loops inside one process call between an Upsampler and a Downsampler (MLDSPFilters.h:1316-1473), 4x and 2x, with
+    functors that run at the high rate (called four / two times per vector) and an oscillator called twice in a vector.
+    Every repeated call is an MLB_AGAIN node, the half-band filters of the cascades included."""
+    from madronalib_b200.graph import OP_NAME
+    g, coef, state = traced("oversample")
+    again = sorted(OP_NAME[g.ops[i]] for i in range(g.n_nodes) if g.again_target(i) >= 0)
+    assert again == sorted(["LOPASS"] * 3 + ["ONEPOLE"] * 3 + ["DCBLOCKER"] + ["SINE"] + ["HALFBAND_UP"] + ["HALFBAND_DOWN"])
+    T = 36
+    rng = np.random.default_rng(9)
+    x = (rng.standard_normal((T, 1, 1, 64)) * 0.4).astype(np.float32)
+    want = ref.oversample_body(x[:, :, 0])
+    for O in (ref, port):
+        out, _, _ = O.run(g, 1, T, x, state, coef)
+        assert_same_bits(out[:, :, 0], want, "oversample body: traced graph vs the reference build of the same source")
+    assert np.isfinite(want).all() and np.abs(want[:, 0]).max() > 0.1 and np.abs(want[:, 1]).max() > 0.05
+
+
+def test_what_cannot_be_called_twice_is_refused():
+    """a functor with a delay ring called twice in a vector (its ring is written once per vector), and a functor inside
+    the process function of a Downsample2xFunction"""
     build_exe()
     r = subprocess.run([EXE, "dump", "twice"], capture_output=True, text=True, timeout=60)
-    assert r.returncode != 0 and "once per vector" in (r.stdout + r.stderr)
+    assert r.returncode != 0 and "cannot be called again" in (r.stdout + r.stderr)
     r = subprocess.run([EXE, "dump", "halfrate"], capture_output=True, text=True, timeout=60)
     assert r.returncode != 0 and "must be stateless" in (r.stdout + r.stderr)
 
