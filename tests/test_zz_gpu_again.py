@@ -146,3 +146,24 @@ def test_traced_rows_body_on_gpu(gpu, port, tmp_path):
     assert_same_bits(got, want, "rows body traced on the GPU")
     if bindings.ref_available():
         assert_same_bits(got[:, :, 9], O.rows_body(inp[:, :, 0]), "GPU vs the reference build of rows_body.h")
+
+
+def test_traced_oversample_body_on_gpu(gpu, port, tmp_path):
+    """tests/cpp/oversample_body.h (4x / 2x oversampled loops between an Upsampler and a Downsampler; functors and the
+    half-band stages called several times per vector) traced and run on the device == the reference build of the same
+    source.  Written after the round's last GPU call (the other tests of this file ran in it): every device path it
+    takes is one they take -- an MLB_AGAIN node is an ordinary node with another node's word offsets -- and its plan is
+    checked in test_planner.py; the first hardware run of this particular graph is the round-end one."""
+    from oracle import bindings
+    from tests.test_trace import _run_gpu_case, traced
+    V, T = 35, 14
+    O = bindings.RefOracle() if bindings.ref_available() else port
+    g, coef, state = traced("oversample", V)
+    rng = np.random.default_rng(9)
+    inp = np.ascontiguousarray(np.repeat((rng.standard_normal((T, 1, 1, 64)) * 0.4).astype(np.float32), V, axis=2))
+    _run_gpu_case(tmp_path, "oversample", V, T, inp)
+    got = np.fromfile(str(tmp_path / "out.bin"), np.float32).reshape(T, g.n_out, V, 64)
+    want, _, _ = O.run(g, V, T, inp, state, coef)
+    assert_same_bits(got, want, "oversample body traced on the GPU")
+    if bindings.ref_available():
+        assert_same_bits(got[:, :, 11], O.oversample_body(inp[:, :, 0]), "GPU vs the reference build of oversample_body.h")
